@@ -1,0 +1,193 @@
+/* rd_env.h -- C ABI of the B200-native batched racing-environment step (librd_env.so).
+ *
+ * This is the drop-in boundary of SURVEY.md §8-b.  Every entry point names the reference interface it
+ * replaces (paths relative to the reference tree, CPS-TUWien/racing_dreamer).  The arithmetic behind
+ * a1/a2/a7/a8 lives in the un-vendored racecar_gym + PyBullet in the reference; the call sites cited here
+ * are where the reference's Python reaches it.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ or torch types cross this boundary.
+ *   - every `*_dev` pointer is a CUDA device pointer owned by the CALLER (e.g. a torch tensor's data_ptr);
+ *     `*_host` pointers are host memory.  The library owns only the handle, the env state and the maps.
+ *   - all calls return 0 on success or a negative rd_status; rd_last_error() gives the sticky message.
+ *   - calls taking `stream` (a cudaStream_t passed as void*) are asynchronous on that stream.
+ *   - a handle is bound to the CUDA device current at rd_create and is not thread-safe.
+ */
+#ifndef RD_ENV_H
+#define RD_ENV_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RD_ABI_VERSION 1
+
+typedef struct rd_env rd_env; /* opaque */
+
+typedef enum rd_status {
+  RD_OK = 0,
+  RD_ERR_INVALID = -1,   /* bad argument / configuration */
+  RD_ERR_CUDA = -2,      /* CUDA runtime error (message has the cudaError string) */
+  RD_ERR_STATE = -3,     /* call order: maps not uploaded / not assigned / not reset */
+  RD_ERR_NOMEM = -4,
+  RD_ERR_NO_DEVICE = -5  /* no usable sm_100 device: there is NO CPU fallback */
+} rd_status;
+
+/* reset modes [REF dreamer/wrappers.py:86-92 FixedResetMode; dreamer/dream.py:105-108,120] */
+enum { RD_RESET_GRID = 0, RD_RESET_RANDOM = 1, RD_RESET_RANDOM_BIDIRECTIONAL = 2 };
+/* tasks [REF dreamer/scenarios/max_progress/austria.yml:8-10; baselines/racing/environment/tasks.py:4-22] */
+enum { RD_TASK_MAX_PROGRESS = 0, RD_TASK_MAX_SPEED = 1 };
+/* observation outputs produced by rd_step/rd_reset */
+enum {
+  RD_OBS_LIDAR = 1,          /* f32 [N, n_beams] metres */
+  RD_OBS_OCCUPANCY = 2,      /* u8 [N, 64, 64] 'lidar_occupancy' [REF dreamer/wrappers.py:372-414] */
+  RD_OBS_LIDAR_NORM = 4      /* lidar stored as r/15 - 0.5 [REF dreamer/tools.py:274] instead of metres */
+};
+/* action_repeat edge semantics [REF dreamer/wrappers.py:107-116 | baselines/.../single_agent.py:31-40] */
+enum { RD_REPEAT_DREAMER = 0, RD_REPEAT_BASELINES = 1 };
+
+/* state layout of rd_get_state / rd_set_state: f64 [RD_NF64][n_envs], i32 [RD_NI32][n_envs] (SoA) */
+enum {
+  RD_S_X = 0, RD_S_Y, RD_S_STEER, RD_S_V, RD_S_YAW, RD_S_YAWRATE, RD_S_SLIP,
+  RD_S_TIME,       /* seconds since reset */
+  RD_S_PROGRESS,   /* progress map value at the pose, [0,1] */
+  RD_S_LAST,       /* lap + progress at the previous tick (reward bookkeeping) */
+  RD_S_RETURN,     /* episode return so far */
+  RD_S_START,      /* lap + progress at the last reset (episode progress = lap + progress - start) */
+  RD_NF64
+};
+enum {
+  RD_I_LAP = 0,     /* starts at 1 [REF dreamer/wrappers.py:218] */
+  RD_I_CHECKPOINT,
+  RD_I_FLAGS,       /* bit0 wrong_way, bit1 wall_collision, bit2 needs_reset, bit3 left_map, bit4 nan */
+  RD_I_AGENT_STEP,  /* TimeLimit counter [REF dreamer/wrappers.py:147-154] */
+  RD_I_EPISODE,     /* episodes started (reset-sampling counter) */
+  RD_I_MAP,         /* map id of this env */
+  RD_NI32
+};
+enum { RD_F_WRONG_WAY = 1, RD_F_COLLISION = 2, RD_F_NEEDS_RESET = 4, RD_F_LEFT_MAP = 8, RD_F_NAN = 16 };
+
+/* Single-track (bicycle) vehicle model parameters, SURVEY.md Appendix C [NEW-SPEC; in-tree anchors:
+ * wheelbase 0.3302 REF ros_agent/agents/follow_the_gap/src/agent.py:78, max steering 0.42 and
+ * max velocity 5.0 REF ros_agent/models/dreamer/racing_dreamer.py:14-16]. */
+typedef struct rd_vehicle {
+  double mu, c_sf, c_sr, lf, lr, h_cg, mass, inertia;
+  double steer_min, steer_max, steer_vel_max; /* rad, rad/s */
+  double v_switch, a_max, v_min, v_max;       /* CommonRoad acceleration constraint */
+  double v_kinematic;                         /* |v| below this: kinematic model */
+  double a_drive, a_brake, c_drag;            /* motor>=0: a = motor*a_drive - c_drag*v ; motor<0: braking */
+  double steer_gain;                          /* steer target = steering * steer_gain * steer_max */
+  double body_length, body_width;             /* collision footprint (centred on the pose) */
+} rd_vehicle;
+
+typedef struct rd_config {
+  int32_t abi_version;        /* = RD_ABI_VERSION */
+  int32_t n_envs;
+  int32_t n_beams;            /* 1080 [REF dreamer/dream.py:66] */
+  int32_t action_repeat;      /* R [REF dreamer/dream.py:55, dreamer/wrappers.py:98-116] */
+  int32_t repeat_semantics;   /* RD_REPEAT_* */
+  int32_t obs_flags;          /* RD_OBS_* */
+  int32_t task;               /* RD_TASK_* */
+  int32_t laps;               /* done when lap > laps */
+  int32_t terminate_on_collision;
+  int32_t n_checkpoints;
+  int32_t time_limit_steps;   /* TimeLimit wrapper, in agent steps; 0 = off [REF dreamer/wrappers.py:137-158] */
+  int32_t auto_reset;         /* 1: a done env is reset inside the same step (obs = first obs of the new episode) */
+  int32_t reset_mode;         /* RD_RESET_* used by auto-reset */
+  int32_t rescale_actions;    /* 1: a' = (a+1)/2*(high-low)+low [REF dreamer/wrappers.py:129-134] */
+  int32_t clip_actions;       /* 1: clip to [-1,1] first [REF baselines/racing/environment/single_agent.py:55-56] */
+  int32_t progress_abs;       /* 1: reward uses |delta progress| */
+  int64_t env_id_offset;      /* global id of env 0 (rank * n_envs for sharded runs): seeds differ per shard */
+  uint64_t seed;
+  double dt;                  /* 0.01 s sim tick [REF dreamer/callbacks.py:23] */
+  double time_limit;          /* seconds [REF dreamer/scenarios/max_progress/austria.yml:10] */
+  double collision_reward, progress_reward, frame_reward;
+  double action_low[2], action_high[2]; /* [motor, steering] [REF dreamer/dream.py:138] */
+  double lidar_fov;           /* rad, 270 deg [REF dreamer/tools.py:84-86] */
+  double lidar_range_min, lidar_range_max; /* metres; 15 m [REF dreamer/tools.py:274] */
+  double lidar_offset;        /* sensor position ahead of the pose along the heading, metres */
+  float lidar_noise;          /* multiplicative U(1-a,1+a); 0 = off */
+  float reserved0;
+  rd_vehicle vehicle;
+} rd_config;
+
+/* Fills `cfg` with the defaults of the reference's dreamer training setup (action_repeat 4, laps 10, ...). */
+void rd_default_config(rd_config* cfg);
+
+/* Device pointers for one step's results.  Any pointer may be NULL = "do not produce".
+ * [REF dreamer/wrappers.py:62-69 (obs dict + speed), :210-226 (Collect: f32 casts, progress, time)] */
+typedef struct rd_outputs {
+  float* lidar_dev;           /* [N, n_beams] */
+  uint8_t* occupancy_dev;     /* [N, 64*64]   */
+  float* pose_dev;            /* [N, 6] x,y,z,roll,pitch,yaw [REF dreamer/wrappers.py:395-401] */
+  float* velocity_dev;        /* [N, 6] body-frame linear (vx,vy,0) + angular (0,0,yaw_rate) */
+  float* speed_dev;           /* [N]   ||velocity[:3]|| ; 0 right after a reset [REF wrappers.py:66,74] */
+  float* reward_dev;          /* [N]   summed over the repeated ticks [REF wrappers.py:110-116] */
+  uint8_t* done_dev;          /* [N]   */
+  float* progress_dev;        /* [N]   info['progress'] of the (possibly terminal) state */
+  int32_t* lap_dev;           /* [N]   info['lap'] */
+  float* time_dev;            /* [N]   info['time'] */
+  uint8_t* flags_dev;         /* [N]   RD_F_* bits of the (possibly terminal) state */
+} rd_outputs;
+
+/* episode statistics accumulated on the device since the last rd_read_stats(reset=1)
+ * [REF dreamer/tools.py:159-206 simulate(): per-episode return and max progress] */
+typedef struct rd_stats {
+  double episodes, return_sum, progress_sum, length_sum, collisions, laps_completed, env_steps, timeouts;
+} rd_stats;
+
+/* ---- lifecycle: replaces RaceCarBaseEnv.__init__ -> MultiAgentScenario.from_spec + MultiAgentRaceEnv
+ *      [REF dreamer/wrappers.py:10-16] ---- */
+int rd_create(const rd_config* cfg, rd_env** out);
+void rd_destroy(rd_env* env);
+const char* rd_last_error(const rd_env* env_or_null);
+int rd_abi_version(void);
+
+/* ---- maps: replaces world._maps['occupancy'|'progress'|'obstacle'] = GridMap(np.load(maps.npz)[...])
+ *      [REF dreamer/plotting/plot_trajectories.py:26-37; dreamer/wrappers.py:376]; all host pointers.
+ *      bits: y-up rows of `row_words` u32, bit=1 drivable; dist: y-up u16 wavefront distance (cells);
+ *      (col0,row0_yup): full-image cell index of the crop's lower-left cell; origin/resolution of the FULL image. */
+int rd_upload_map(rd_env* env, int map_id, const uint32_t* bits_host, int h, int w, int row_words,
+                  const uint16_t* dist_host, int dmax, double resolution, double origin_x, double origin_y,
+                  int col0, int row0_yup, int full_h, const double* start_poses_host, int n_start,
+                  const double* reset_poses_host, int n_reset);
+/* map id per env (host int32[n_envs]); envs are grouped by map internally. */
+int rd_assign_maps(rd_env* env, const int32_t* env_map_id_host);
+
+/* ---- reset: replaces env.reset(mode=...) [REF dreamer/wrappers.py:71-77,91-92,156-158,410-414].
+ *      mask_dev: u8[N] (NULL = all). Writes the reset observation of every env into `out`. ---- */
+int rd_reset(rd_env* env, const uint8_t* mask_dev, int mode, const rd_outputs* out, void* stream);
+
+/* ---- step: replaces Collect/TimeLimit/OccupancyMapObs/ReduceActionSpace/ActionRepeat/RaceCarWrapper.step
+ *      -> MultiAgentRaceEnv.step [REF dreamer/wrappers.py:62-69,107-116,129-134,147-154,210-226,390-408].
+ *      actions_dev: f32 [N,2] = [motor, steering] agent-facing ([-1,1] when rescale_actions). ---- */
+int rd_step(rd_env* env, const float* actions_dev, const rd_outputs* out, void* stream);
+
+/* ---- stage entry points (teacher-forced parity tests; each is one kernel of the step) ---- */
+/* a2 LiDAR [REF dreamer/scenarios/max_progress/austria.yml:7 'lidar' sensor]: poses f64 [n,3]=(x,y,yaw),
+ * map_ids i32[n] sorted ascending or NULL (= map 0), ranges f32 [n, n_beams]. */
+int rd_lidar_cast(rd_env* env, const double* poses_dev, const int32_t* map_ids_host, int n,
+                  float* ranges_dev, void* stream);
+/* a5 OccupancyMapObs.step [REF dreamer/wrappers.py:390-408]: poses f64 [n,3], out u8 [n,64*64]. */
+int rd_occupancy_obs(rd_env* env, const double* poses_dev, const int32_t* map_ids_host, int n,
+                     uint8_t* out_dev, void* stream);
+/* a1 dynamics only: state f64 [7][n] SoA (x,y,steer,v,yaw,yaw_rate,slip) in/out,
+ * commands f64 [n,2] = sim-facing (motor, steering), n_ticks ticks of cfg.dt. */
+int rd_dynamics(rd_env* env, double* state_dev, const double* commands_dev, int n, int n_ticks, void* stream);
+
+/* ---- state access (checkpoint/resume; teacher forcing) ---- */
+int rd_get_state(rd_env* env, double* f64_dev, int32_t* i32_dev, void* stream);
+int rd_set_state(rd_env* env, const double* f64_dev, const int32_t* i32_dev, void* stream);
+
+/* ---- episode statistics (K5): device-side accumulators -> host struct (synchronises `stream`) ---- */
+int rd_read_stats(rd_env* env, rd_stats* out_host, int reset, void* stream);
+
+/* ---- introspection for bench/profiling: kernels launched by this handle so far ---- */
+int64_t rd_launch_count(const rd_env* env);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RD_ENV_H */

@@ -1,0 +1,147 @@
+"""ctypes mirror of include/rd_env.h and the loader of librd_env.so.
+
+The loader fails loudly: there is no CPU or PyTorch fallback for the env step.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+ABI_VERSION = 1
+
+# enums (include/rd_env.h)
+RESET_GRID, RESET_RANDOM, RESET_RANDOM_BIDIRECTIONAL = 0, 1, 2
+RESET_MODES = {"grid": RESET_GRID, "random": RESET_RANDOM, "random_bidirectional": RESET_RANDOM_BIDIRECTIONAL}
+TASK_MAX_PROGRESS, TASK_MAX_SPEED = 0, 1
+TASKS = {"maximize_progress": TASK_MAX_PROGRESS, "max_progress": TASK_MAX_PROGRESS,
+         "max_speed": TASK_MAX_SPEED, "maximize_speed": TASK_MAX_SPEED}
+OBS_LIDAR, OBS_OCCUPANCY, OBS_LIDAR_NORM = 1, 2, 4
+REPEAT_DREAMER, REPEAT_BASELINES = 0, 1
+
+S_X, S_Y, S_STEER, S_V, S_YAW, S_YAWRATE, S_SLIP, S_TIME, S_PROGRESS, S_LAST, S_RETURN, S_START, NF64 = range(13)
+I_LAP, I_CHECKPOINT, I_FLAGS, I_AGENT_STEP, I_EPISODE, I_MAP, NI32 = range(7)
+F_WRONG_WAY, F_COLLISION, F_NEEDS_RESET, F_LEFT_MAP, F_NAN = 1, 2, 4, 8, 16
+
+
+class RdVehicle(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "mu", "c_sf", "c_sr", "lf", "lr", "h_cg", "mass", "inertia",
+        "steer_min", "steer_max", "steer_vel_max",
+        "v_switch", "a_max", "v_min", "v_max",
+        "v_kinematic",
+        "a_drive", "a_brake", "c_drag",
+        "steer_gain",
+        "body_length", "body_width")]
+
+
+class RdConfig(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("n_envs", C.c_int32), ("n_beams", C.c_int32), ("action_repeat", C.c_int32),
+        ("repeat_semantics", C.c_int32), ("obs_flags", C.c_int32), ("task", C.c_int32), ("laps", C.c_int32),
+        ("terminate_on_collision", C.c_int32), ("n_checkpoints", C.c_int32), ("time_limit_steps", C.c_int32),
+        ("auto_reset", C.c_int32), ("reset_mode", C.c_int32), ("rescale_actions", C.c_int32),
+        ("clip_actions", C.c_int32), ("progress_abs", C.c_int32),
+        ("env_id_offset", C.c_int64), ("seed", C.c_uint64),
+        ("dt", C.c_double), ("time_limit", C.c_double),
+        ("collision_reward", C.c_double), ("progress_reward", C.c_double), ("frame_reward", C.c_double),
+        ("action_low", C.c_double * 2), ("action_high", C.c_double * 2),
+        ("lidar_fov", C.c_double), ("lidar_range_min", C.c_double), ("lidar_range_max", C.c_double),
+        ("lidar_offset", C.c_double),
+        ("lidar_noise", C.c_float), ("reserved0", C.c_float),
+        ("vehicle", RdVehicle),
+    ]
+
+    def copy(self) -> "RdConfig":
+        out = RdConfig()
+        C.memmove(C.byref(out), C.byref(self), C.sizeof(RdConfig))
+        return out
+
+
+class RdOutputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "lidar_dev", "occupancy_dev", "pose_dev", "velocity_dev", "speed_dev", "reward_dev", "done_dev",
+        "progress_dev", "lap_dev", "time_dev", "flags_dev")]
+
+
+class RdStats(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "episodes", "return_sum", "progress_sum", "length_sum", "collisions", "laps_completed", "env_steps",
+        "timeouts")]
+
+    def as_dict(self):
+        return {n: float(getattr(self, n)) for n, _ in self._fields_}
+
+
+EXPORTS = (
+    "rd_default_config", "rd_create", "rd_destroy", "rd_last_error", "rd_abi_version", "rd_upload_map",
+    "rd_assign_maps", "rd_reset", "rd_step", "rd_lidar_cast", "rd_occupancy_obs", "rd_dynamics",
+    "rd_get_state", "rd_set_state", "rd_read_stats", "rd_launch_count",
+)
+
+LIB_PATH = Path(__file__).resolve().parent / "librd_env.so"
+_lib = None
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def load_library() -> C.CDLL:
+    """Load librd_env.so (built in-tree by __graft_entry__.build() / `make -C racing_dreamer_b200/csrc`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = Path(os.environ.get("RD_ENV_LIB", LIB_PATH))
+    if not path.exists():
+        raise NativeLibraryError(
+            f"{path} is missing: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'). "
+            "There is no CPU fallback for the env step.")
+    lib = C.CDLL(str(path))
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise NativeLibraryError(f"{path} does not export {name}")
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    lib.rd_default_config.argtypes = [C.POINTER(RdConfig)]
+    lib.rd_default_config.restype = None
+    lib.rd_create.argtypes = [C.POINTER(RdConfig), C.POINTER(vp)]
+    lib.rd_create.restype = i32
+    lib.rd_destroy.argtypes = [vp]
+    lib.rd_destroy.restype = None
+    lib.rd_last_error.argtypes = [vp]
+    lib.rd_last_error.restype = C.c_char_p
+    lib.rd_abi_version.argtypes = []
+    lib.rd_abi_version.restype = i32
+    lib.rd_upload_map.argtypes = [vp, i32, vp, i32, i32, i32, vp, i32, C.c_double, C.c_double, C.c_double,
+                                  i32, i32, i32, vp, i32, vp, i32]
+    lib.rd_upload_map.restype = i32
+    lib.rd_assign_maps.argtypes = [vp, vp]
+    lib.rd_assign_maps.restype = i32
+    lib.rd_reset.argtypes = [vp, vp, i32, C.POINTER(RdOutputs), vp]
+    lib.rd_reset.restype = i32
+    lib.rd_step.argtypes = [vp, vp, C.POINTER(RdOutputs), vp]
+    lib.rd_step.restype = i32
+    lib.rd_lidar_cast.argtypes = [vp, vp, vp, i32, vp, vp]
+    lib.rd_lidar_cast.restype = i32
+    lib.rd_occupancy_obs.argtypes = [vp, vp, vp, i32, vp, vp]
+    lib.rd_occupancy_obs.restype = i32
+    lib.rd_dynamics.argtypes = [vp, vp, vp, i32, i32, vp]
+    lib.rd_dynamics.restype = i32
+    lib.rd_get_state.argtypes = [vp, vp, vp, vp]
+    lib.rd_get_state.restype = i32
+    lib.rd_set_state.argtypes = [vp, vp, vp, vp]
+    lib.rd_set_state.restype = i32
+    lib.rd_read_stats.argtypes = [vp, C.POINTER(RdStats), i32, vp]
+    lib.rd_read_stats.restype = i32
+    lib.rd_launch_count.argtypes = [vp]
+    lib.rd_launch_count.restype = i64
+    if lib.rd_abi_version() != ABI_VERSION:
+        raise NativeLibraryError(f"{path}: ABI version {lib.rd_abi_version()} != {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def default_config() -> RdConfig:
+    cfg = RdConfig()
+    load_library().rd_default_config(C.byref(cfg))
+    return cfg

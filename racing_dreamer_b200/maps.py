@@ -1,0 +1,345 @@
+"""Track-map compiler: ROS map_server yaml+image -> the grids the env step consumes.
+
+Restates the semantics of the reference's offline generator
+[REF docs/maps/costmaps/generate-costmap.py:30-52 (load/threshold/start pixel),
+ :131-224 (finish-line blocking + 8-neighbour wavefront), :380-382 (EDT), :405-420 (npz keys)]
+and the track-name table of SURVEY.md §8-a6.  It is host-side, offline work (the reference
+runs it once per track too); its output is cached as a small ``.npz`` under
+``racing_dreamer_b200/data/tracks`` so nothing at run time needs the source images.
+
+Compiled layout (all arrays cropped to the track bounding box + MARGIN cells, image row order):
+
+* ``drivable``  bool (h, w)      = reference ``drivable_area`` (wavefront-reachable + finish line)
+* ``dist``      uint16 (h, w)    = wavefront distance in cells (finish-line cells = dmax)
+                                   -> ``norm_distance_from_start = dist / dmax``
+* ``edt_sq``    uint32 (h, w)    = squared Euclidean distance (cells^2) to the nearest
+                                   non-drivable cell -> ``norm_distance_to_obstacle``
+* ``start_poses`` / ``reset_poses`` float64 (n, 3) = (x, y, yaw) for reset modes
+  'grid' / 'random' [NEW-SPEC: the reference's sampler lives in racecar_gym, not in tree].
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+import os
+from pathlib import Path
+from typing import Dict, Optional
+
+import numpy as np
+
+MARGIN = 4  # cells of guaranteed non-drivable border around the crop (the ray march relies on >= 1)
+
+DATA_DIR = Path(__file__).resolve().parent / "data" / "tracks"
+
+# racecar_gym track name -> map file stem in docs/maps/maps (lap lengths cross-checked there)
+TRACK_FILES: Dict[str, str] = {
+    "austria": "f1_aut",
+    "barcelona": "f1_esp",
+    "gbr": "f1_gbr",
+    "treitlstrasse_v2": "Treitlstrasse_3-U_v2",
+    "columbia": "columbia_small",
+    "circle_cw": "circle",
+}
+
+
+@dataclasses.dataclass
+class TrackMap:
+    name: str
+    source: str
+    resolution: float
+    origin: tuple           # (ox, oy) world coordinates of the lower-left corner of the FULL image
+    full_shape: tuple       # (H, W) of the full image
+    r0: int                 # crop origin, image row/col in the full image
+    c0: int
+    drivable: np.ndarray    # bool (h, w)
+    dist: np.ndarray        # uint16 (h, w)
+    dmax: int
+    edt_sq: np.ndarray      # uint32 (h, w)
+    edt_sq_max: int
+    start_poses: np.ndarray  # f64 (n, 3)
+    reset_poses: np.ndarray  # f64 (m, 3)
+
+    # ---- geometry helpers (the one convention used by oracle, kernels and the GridMap shim) ----
+    @property
+    def h(self) -> int:
+        return int(self.drivable.shape[0])
+
+    @property
+    def w(self) -> int:
+        return int(self.drivable.shape[1])
+
+    @property
+    def inv_res(self) -> float:
+        return 1.0 / self.resolution
+
+    @property
+    def cy0(self) -> int:
+        """y-up cell index (in the full image) of the crop's bottom row."""
+        return self.full_shape[0] - 1 - (self.r0 + self.h - 1)
+
+    def to_pixel(self, x: float, y: float):
+        """(row, col) in the FULL image; row = H-1-floor((y-oy)/res) [REF generate-costmap.py:49-52]."""
+        col = math.floor((x - self.origin[0]) * self.inv_res)
+        row = self.full_shape[0] - 1 - math.floor((y - self.origin[1]) * self.inv_res)
+        return row, col
+
+    def lap_length_m(self) -> float:
+        return self.dmax * self.resolution
+
+    # ---- full-size reference-format arrays (what the reference's maps.npz holds) ----
+    def _paste(self, crop: np.ndarray, dtype) -> np.ndarray:
+        full = np.zeros(self.full_shape, dtype=dtype)
+        full[self.r0:self.r0 + self.h, self.c0:self.c0 + self.w] = crop
+        return full
+
+    def full_drivable(self) -> np.ndarray:
+        return self._paste(self.drivable, bool)
+
+    def full_norm_distance_from_start(self) -> np.ndarray:
+        d = self._paste(self.dist, np.float64) * float(self.resolution)
+        return d / np.amax(d)
+
+    def full_norm_distance_to_obstacle(self) -> np.ndarray:
+        d = np.sqrt(self._paste(self.edt_sq, np.float64)) * float(self.resolution)
+        return d / np.amax(d)
+
+    # ---- device layouts ----
+    def row_words(self) -> int:
+        """32-bit words per bit-packed row: >= ceil(w/32), forced odd so that vertically adjacent
+        cells fall into different shared-memory banks."""
+        rw = (self.w + 31) // 32
+        return rw | 1
+
+    def packed_bits_yup(self) -> np.ndarray:
+        """uint32 (h, row_words) bit grid, row 0 = lowest y; bit (cx & 31) of word (cx >> 5)."""
+        rw = self.row_words()
+        yup = self.drivable[::-1]
+        padded = np.zeros((self.h, rw * 32), dtype=np.uint8)
+        padded[:, : self.w] = yup
+        b = padded.reshape(self.h, rw, 32).astype(np.uint32)
+        words = (b << np.arange(32, dtype=np.uint32)[None, None, :]).sum(axis=2, dtype=np.uint64)
+        return words.astype(np.uint32)
+
+    def dist_yup(self) -> np.ndarray:
+        return np.ascontiguousarray(self.dist[::-1])
+
+    # ---- io ----
+    def save(self, path: os.PathLike) -> None:
+        np.savez_compressed(
+            path,
+            name=self.name, source=self.source, resolution=self.resolution,
+            origin=np.asarray(self.origin, np.float64), full_shape=np.asarray(self.full_shape, np.int64),
+            r0=self.r0, c0=self.c0,
+            drivable=np.packbits(self.drivable, axis=1), w=self.w,
+            dist=self.dist, dmax=self.dmax, edt_sq=self.edt_sq, edt_sq_max=self.edt_sq_max,
+            start_poses=self.start_poses, reset_poses=self.reset_poses,
+        )
+
+    @staticmethod
+    def load(path: os.PathLike) -> "TrackMap":
+        z = np.load(path, allow_pickle=False)
+        w = int(z["w"])
+        drivable = np.unpackbits(z["drivable"], axis=1)[:, :w].astype(bool)
+        return TrackMap(
+            name=str(z["name"]), source=str(z["source"]), resolution=float(z["resolution"]),
+            origin=tuple(float(v) for v in z["origin"]), full_shape=tuple(int(v) for v in z["full_shape"]),
+            r0=int(z["r0"]), c0=int(z["c0"]), drivable=drivable, dist=z["dist"], dmax=int(z["dmax"]),
+            edt_sq=z["edt_sq"], edt_sq_max=int(z["edt_sq_max"]),
+            start_poses=z["start_poses"], reset_poses=z["reset_poses"],
+        )
+
+
+# --------------------------------------------------------------------------------------------
+# compiler
+# --------------------------------------------------------------------------------------------
+def _read_gray(image_path: Path) -> np.ndarray:
+    """Grey image as float64, as ``skimage.io.imread(as_gray=True).astype(float)`` yields it
+    [REF generate-costmap.py:39]: RGB(A) -> 0.2125 R + 0.7154 G + 0.0721 B on [0,1] (alpha is 255
+    everywhere in the in-tree PNGs, so blending is the identity); single-channel files stay as stored."""
+    from PIL import Image
+
+    im = Image.open(image_path)
+    a = np.asarray(im)
+    if a.ndim == 2:
+        return a.astype(np.float64)
+    rgb = a[..., :3].astype(np.float64) / 255.0
+    if a.shape[2] == 4:
+        alpha = a[..., 3:4].astype(np.float64) / 255.0
+        rgb = rgb * alpha + (1.0 - alpha)
+    return rgb @ np.array([0.2125, 0.7154, 0.0721])
+
+
+def _wavefront(free: np.ndarray, seed_rc) -> np.ndarray:
+    """8-neighbour (Chebyshev) wavefront distance from the seed over ``free`` cells
+    [REF generate-costmap.py:198-209: repeated 3x3 dilation, new pixels get the current distance].
+    Returns int32 distances, -1 where unreached."""
+    h, w = free.shape
+    dist = np.full((h, w), -1, dtype=np.int32)
+    dist[seed_rc] = 0
+    fr = np.array([seed_rc[0]], dtype=np.int64)
+    fc = np.array([seed_rc[1]], dtype=np.int64)
+    d = 0
+    offs = [(-1, -1), (-1, 0), (-1, 1), (0, -1), (0, 1), (1, -1), (1, 0), (1, 1)]
+    while fr.size:
+        d += 1
+        nr = np.concatenate([fr + a for a, _ in offs])
+        nc = np.concatenate([fc + b for _, b in offs])
+        ok = (nr >= 0) & (nr < h) & (nc >= 0) & (nc < w)
+        nr, nc = nr[ok], nc[ok]
+        ok = free[nr, nc] & (dist[nr, nc] < 0)
+        nr, nc = nr[ok], nc[ok]
+        if nr.size == 0:
+            break
+        lin = np.unique(nr * w + nc)
+        fr, fc = lin // w, lin % w
+        dist[fr, fc] = d
+    return dist
+
+
+def compile_track(yaml_path: os.PathLike, name: Optional[str] = None, start_xy=(0.0, 0.0),
+                  reset_clearance_m: float = 0.4, max_reset_poses: int = 4096) -> TrackMap:
+    import yaml
+    from scipy import ndimage
+
+    yaml_path = Path(yaml_path)
+    with open(yaml_path) as f:
+        props = yaml.safe_load(f)
+    res = float(props["resolution"])
+    ox, oy = float(props["origin"][0]), float(props["origin"][1])
+    gray = _read_gray(yaml_path.parent / props["image"])
+    H, W = gray.shape
+    binary = (gray / np.amax(gray)) > float(props["occupied_thresh"])     # [REF :42-43]
+
+    # start pixel [REF :49-52]; the reference mixes shape[1] with the row axis (square images only) --
+    # here the row flip uses the row count.
+    gx = int((start_xy[0] - ox) / res)
+    gy = int(H - (start_xy[1] - oy) / res - 1)
+    if not binary[gy, gx]:
+        raise ValueError(f"start pixel ({gy},{gx}) of {yaml_path.name} is not free")
+
+    # finish line: free cells of the column one behind the start, walked down and up [REF :151-163]
+    free = binary.copy()
+    finish = np.zeros_like(free)
+    col = gx - 1
+    r = gy
+    while free[r, col]:
+        free[r, col] = False
+        finish[r, col] = True
+        r += 1
+    r = gy - 1
+    while free[r, col]:
+        free[r, col] = False
+        finish[r, col] = True
+        r -= 1
+
+    dist = _wavefront(free, (gy, gx))
+    reached = dist >= 0
+    dmax = int(dist.max()) + 1                 # loop-exit value of current_distance [REF :198-220]
+    dist = np.where(reached, dist, 0)
+    dist[finish] = dmax
+    drivable = reached | finish                # [REF :223]
+    if dmax > 65535:
+        raise ValueError("wavefront distance overflows uint16")
+
+    edt = ndimage.distance_transform_edt(drivable)     # [REF :380]
+    edt_sq = np.rint(edt * edt).astype(np.uint32)
+
+    rows = np.flatnonzero(drivable.any(axis=1))
+    cols = np.flatnonzero(drivable.any(axis=0))
+    r0, r1 = max(rows[0] - MARGIN, 0), min(rows[-1] + MARGIN + 1, H)
+    c0, c1 = max(cols[0] - MARGIN, 0), min(cols[-1] + MARGIN + 1, W)
+    sl = (slice(r0, r1), slice(c0, c1))
+
+    tm = TrackMap(
+        name=name or yaml_path.stem, source=yaml_path.stem, resolution=res, origin=(ox, oy), full_shape=(H, W),
+        r0=int(r0), c0=int(c0), drivable=drivable[sl].copy(), dist=dist[sl].astype(np.uint16), dmax=dmax,
+        edt_sq=edt_sq[sl].copy(), edt_sq_max=int(edt_sq.max()),
+        start_poses=np.zeros((0, 3)), reset_poses=np.zeros((0, 3)),
+    )
+    tm.start_poses = _grid_poses(tm, start_xy)
+    tm.reset_poses = _random_reset_poses(tm, reset_clearance_m, max_reset_poses)
+    return tm
+
+
+def _heading_field(tm: TrackMap, rows: np.ndarray, cols: np.ndarray, k: int = 6) -> np.ndarray:
+    """Yaw of increasing progress at crop cells (rows, cols): gradient of the wavefront distance over a
+    (2k+1)^2 window, using only drivable cells whose distance is within the window's reach (so the
+    wrap at the finish line does not leak in).  World frame: +x = +col, +y = -row."""
+    d = tm.dist.astype(np.float64)
+    drv = tm.drivable
+    h, w = drv.shape
+    yaw = np.zeros(rows.size)
+    for i, (r, c) in enumerate(zip(rows, cols)):
+        ra, rb = max(r - k, 0), min(r + k + 1, h)
+        ca, cb = max(c - k, 0), min(c + k + 1, w)
+        win = d[ra:rb, ca:cb] - d[r, c]
+        m = drv[ra:rb, ca:cb] & (np.abs(win) <= 2 * k)
+        rr, cc = np.mgrid[ra:rb, ca:cb]
+        gx = np.sum(np.where(m, win * (cc - c), 0.0))
+        gy = np.sum(np.where(m, win * -(rr - r), 0.0))
+        yaw[i] = math.atan2(gy, gx)
+    return yaw
+
+
+def _cell_centre(tm: TrackMap, r: np.ndarray, c: np.ndarray):
+    x = tm.origin[0] + (tm.c0 + c + 0.5) * tm.resolution
+    y = tm.origin[1] + (tm.full_shape[0] - 1 - (tm.r0 + r) + 0.5) * tm.resolution
+    return x, y
+
+
+def _grid_poses(tm: TrackMap, start_xy) -> np.ndarray:
+    """'grid' reset: the start position itself, heading along increasing progress, plus three staggered
+    slots ahead of it for multi-car worlds [NEW-SPEC]."""
+    row, col = tm.to_pixel(float(start_xy[0]), float(start_xy[1]))
+    r, c = row - tm.r0, col - tm.c0
+    yaw0 = float(_heading_field(tm, np.array([r]), np.array([c]))[0])
+    poses = [(float(start_xy[0]), float(start_xy[1]), yaw0)]
+    for k in range(1, 4):
+        dx, dy = 0.8 * k, (0.25 if k % 2 else -0.25)
+        x = start_xy[0] + dx * math.cos(yaw0) - dy * math.sin(yaw0)
+        y = start_xy[1] + dx * math.sin(yaw0) + dy * math.cos(yaw0)
+        poses.append((x, y, yaw0))
+    return np.asarray(poses, dtype=np.float64)
+
+
+def _random_reset_poses(tm: TrackMap, clearance_m: float, max_n: int) -> np.ndarray:
+    """'random' reset candidates: cell centres with obstacle clearance >= clearance_m, evenly
+    subsampled along progress, heading along increasing progress [NEW-SPEC]."""
+    need = (clearance_m / tm.resolution) ** 2
+    ok = tm.drivable & (tm.edt_sq >= need) & (tm.dist > 12) & (tm.dist < tm.dmax - 12)
+    rows, cols = np.nonzero(ok)
+    if rows.size == 0:
+        return tm.start_poses[:1].copy()
+    order = np.lexsort((cols, rows, tm.dist[rows, cols]))
+    if order.size > max_n:
+        order = order[np.linspace(0, order.size - 1, max_n).astype(np.int64)]
+    rows, cols = rows[order], cols[order]
+    x, y = _cell_centre(tm, rows, cols)
+    yaw = _heading_field(tm, rows, cols)
+    return np.stack([x, y, yaw], axis=1).astype(np.float64)
+
+
+# --------------------------------------------------------------------------------------------
+# registry
+# --------------------------------------------------------------------------------------------
+_cache: Dict[str, TrackMap] = {}
+
+
+def load_track(name: str) -> TrackMap:
+    """Compiled track by racecar_gym name (``austria``) or by map file stem (``f1_aut``)."""
+    if name in _cache:
+        return _cache[name]
+    stem = TRACK_FILES.get(name, name)
+    path = DATA_DIR / f"{stem}.npz"
+    if not path.exists():
+        raise FileNotFoundError(
+            f"no compiled track '{name}' ({path}); build it with tools/compile_tracks.py from a map_server yaml")
+    tm = TrackMap.load(path)
+    tm.name = name
+    _cache[name] = tm
+    return tm
+
+
+def available_tracks():
+    stems = {p.stem for p in DATA_DIR.glob("*.npz")}
+    return sorted([n for n, s in TRACK_FILES.items() if s in stems] + sorted(stems))
