@@ -37,7 +37,8 @@ class _Map(C.Structure):
 
 class _Outputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
-        "lidar", "occupancy", "pose", "velocity", "speed", "reward", "done", "progress", "lap", "time", "flags")]
+        "lidar", "occupancy", "pose", "velocity", "speed", "reward", "done", "progress", "lap", "time", "flags",
+        "reward64")]
 
 
 def _load():
@@ -110,7 +111,7 @@ class Oracle:
             pose=np.zeros((n, 6), np.float32), velocity=np.zeros((n, 6), np.float32),
             speed=np.zeros(n, np.float32), reward=np.zeros(n, np.float32), done=np.zeros(n, np.uint8),
             progress=np.zeros(n, np.float32), lap=np.zeros(n, np.int32), time=np.zeros(n, np.float32),
-            flags=np.zeros(n, np.uint8))
+            flags=np.zeros(n, np.uint8), reward64=np.zeros(n, np.float64))
 
     def _c_outputs(self) -> _Outputs:
         o = _Outputs()
@@ -127,11 +128,18 @@ class Oracle:
                            C.c_int(mode), C.byref(o))
         return self.out
 
-    def step(self, actions: np.ndarray):
-        a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.n, 2)
+    def step(self, actions: np.ndarray = None, commands: np.ndarray = None):
+        """actions: agent-facing float32 [n,2] (clip/rescale applied per cfg);
+        commands: sim-facing float64 [n,2] = racecar_gym's {'motor','steering'} (bypasses the action transform)."""
+        a = c = None
+        if commands is not None:
+            c = np.ascontiguousarray(commands, dtype=np.float64).reshape(self.n, 2)
+        else:
+            a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.n, 2)
         o = self._c_outputs()
         self.lib.orc_step(C.byref(self.cfg), self._cmaps, C.c_void_p(self.f64.ctypes.data),
-                          C.c_void_p(self.i32.ctypes.data), C.c_void_p(a.ctypes.data), C.byref(o),
+                          C.c_void_p(self.i32.ctypes.data), C.c_void_p(a.ctypes.data if a is not None else None),
+                          C.c_void_p(c.ctypes.data if c is not None else None), C.byref(o),
                           C.byref(self.stats), C.c_int(self.n_threads))
         return self.out
 

@@ -409,6 +409,7 @@ static void reset_one(const rd_config* cfg, const orc_map* maps, orc_view* s, in
 typedef struct orc_outputs {
   float* lidar; uint8_t* occupancy; float* pose; float* velocity; float* speed; float* reward;
   uint8_t* done; float* progress; int32_t* lap; float* time; uint8_t* flags;
+  double* reward64; /* un-rounded step reward (the reference sums python floats [REF dreamer/wrappers.py:114]) */
 } orc_outputs;
 
 static void orc_occupancy_one(const orc_map* m, double x, double y, double yaw, uint8_t* out);
@@ -471,7 +472,7 @@ ORC_API void orc_reset(const rd_config* cfg, const orc_map* maps, double* f64, i
 /* One agent step of one env: ReduceActionSpace -> ActionRepeat{tick: dynamics, maps, lap logic, reward,
  * done} -> TimeLimit -> (auto-reset) [REF dreamer/wrappers.py:129-134,107-116,147-154]. */
 static void step_one(const rd_config* cfg, const orc_map* maps, orc_view* s, int e, const float* actions,
-                     const orc_outputs* o, rd_stats* st, int* was_reset) {
+                     const double* commands, const orc_outputs* o, rd_stats* st, int* was_reset) {
   const orc_map* m = &maps[s->i[RD_I_MAP][e]];
   *was_reset = 0;
   if (s->i[RD_I_FLAGS][e] & RD_F_NEEDS_RESET) { /* frozen until reset [REF wrappers.py:148 'Must reset'] */
@@ -483,11 +484,23 @@ static void step_one(const rd_config* cfg, const orc_map* maps, orc_view* s, int
     if (o->flags) o->flags[e] = (uint8_t)s->i[RD_I_FLAGS][e];
     return;
   }
-  /* a4 action transform: f32 in, float64 arithmetic as numpy does [REF wrappers.py:129-134; single_agent.py:55-56] */
-  double a[2] = {(double)actions[2 * e], (double)actions[2 * e + 1]};
-  for (int k = 0; k < 2; ++k) {
-    if (cfg->clip_actions) a[k] = a[k] < -1.0 ? -1.0 : (a[k] > 1.0 ? 1.0 : a[k]);
-    if (cfg->rescale_actions) a[k] = (a[k] + 1.0) / 2.0 * (cfg->action_high[k] - cfg->action_low[k]) + cfg->action_low[k];
+  /* a4 action transform [REF dreamer/wrappers.py:129-134; baselines single_agent.py:55-56].  The policy hands
+   * over a float32 array; numpy keeps `(action + 1) / 2` in float32 (python scalars are weak) and promotes to
+   * float64 only at `* (high - low)` because low/high are float64 arrays.  `commands` (float64, sim-facing)
+   * bypasses the transform: that is racecar_gym's own step({'motor','steering'}) entry. */
+  double a[2];
+  if (commands) { a[0] = commands[2 * e]; a[1] = commands[2 * e + 1]; }
+  else {
+    for (int k = 0; k < 2; ++k) {
+      float af = actions[2 * e + k];
+      if (cfg->clip_actions) af = af < -1.0f ? -1.0f : (af > 1.0f ? 1.0f : af);
+      if (cfg->rescale_actions) {
+        float t = (af + 1.0f) / 2.0f;
+        a[k] = (double)t * (cfg->action_high[k] - cfg->action_low[k]) + cfg->action_low[k];
+      } else {
+        a[k] = (double)af;
+      }
+    }
   }
   double q[7];
   for (int k = 0; k < 7; ++k) q[k] = s->f[k][e];
@@ -543,6 +556,7 @@ static void step_one(const rd_config* cfg, const orc_map* maps, orc_view* s, int
   if (done && !cfg->auto_reset) flags |= RD_F_NEEDS_RESET;
   s->i[RD_I_FLAGS][e] = flags;
   if (o->reward) o->reward[e] = (float)total;
+  if (o->reward64) o->reward64[e] = total;
   if (o->done) o->done[e] = (uint8_t)done;
   if (o->progress) o->progress[e] = (float)p;
   if (o->lap) o->lap[e] = lap;
@@ -565,7 +579,8 @@ static void step_one(const rd_config* cfg, const orc_map* maps, orc_view* s, int
 
 /* env.step(actions) for the whole batch.  stats may be NULL.  n_threads >= 1. */
 ORC_API void orc_step(const rd_config* cfg, const orc_map* maps, double* f64, int32_t* i32,
-                      const float* actions, const orc_outputs* out, rd_stats* stats, int n_threads) {
+                      const float* actions, const double* commands, const orc_outputs* out, rd_stats* stats,
+                      int n_threads) {
   int n = cfg->n_envs, nb = cfg->n_beams;
   orc_view s = view_of(f64, i32, n);
   double* ca = (double*)malloc(sizeof(double) * 2 * nb);
@@ -582,7 +597,7 @@ ORC_API void orc_step(const rd_config* cfg, const orc_map* maps, double* f64, in
     for (int e = 0; e < n; ++e) {
       int was_reset = 0;
       int frozen = (s.i[RD_I_FLAGS][e] & RD_F_NEEDS_RESET) != 0;
-      step_one(cfg, maps, &s, e, actions, out, &loc, &was_reset);
+      step_one(cfg, maps, &s, e, actions, commands, out, &loc, &was_reset);
       if (!frozen) write_obs(cfg, maps, ca, sa, &s, e, out, was_reset);
     }
 #pragma omp critical

@@ -1,0 +1,104 @@
+// rd_common.cuh -- shared device-side types and helpers of librd_env.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rd_env.h"
+
+#define RD_MAX_MAPS 8
+#define RD_SUB_BITS 12            // ray origin quantum: 2^-12 cell
+#define RD_SUB (1 << RD_SUB_BITS)
+#define RD_DIR_BITS 18            // ray direction quantum: 2^-18
+#define RD_OCC_IN 220             // OccupancyMapObs crop [REF dreamer/wrappers.py:398-399]
+#define RD_OCC_MID 200
+#define RD_OCC_OUT 64
+
+// One track on the device.  bits: y-up rows of rw u32 words, bit = drivable.  dist: y-up u16.
+struct DevMap {
+  const uint32_t* bits;
+  const uint16_t* dist;
+  const double* start;   // [n_start][3]
+  const double* reset;   // [n_reset][3]
+  int h, w, rw, col0, row0, full_h, dmax, n_start, n_reset;
+  int bits_bytes;        // h*rw*4 rounded up to 16 (bulk-copy granularity)
+  double res, inv_res, ox, oy;
+};
+
+// Per-env record handed from the dynamics/reset kernel to the LiDAR and occupancy kernels (48 B, 16-B aligned).
+struct __align__(16) OriginRec {
+  int32_t px, py;        // sensor origin in 2^-12 cells relative to the crop (valid only if `valid`)
+  int32_t valid;         // origin inside a drivable cell
+  uint32_t gid;          // global env id (noise counter)
+  uint32_t episode, step;
+  int32_t was_reset;     // env was reset in this call (occupancy obs = zeros) ; 2 = frozen (leave outputs)
+  int32_t pad;
+  double c, s;           // cos/sin of the heading
+};
+
+struct LidarParams {
+  int n_beams;
+  int groups;            // ceil(n_beams / 32)
+  int normalize;         // RD_OBS_LIDAR_NORM
+  float range_min, range_max, noise;
+  float scale;           // metres per (sub-cell / direction unit) = 2^(DIR-SUB) * resolution
+  int64_t rsub;          // range_max in sub-cells
+  uint32_t key0, key1;   // Philox key of the noise stream
+};
+
+// ---- Philox4x32-10 (counter-based RNG; identical integer arithmetic in the oracle) ----
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+#define RD_STREAM_RESET 0x52455345u
+#define RD_STREAM_LIDAR 0x4c494441u
+
+// ---- map lookups (global memory, read-only path) ----
+__device__ __forceinline__ bool rd_cell_of(const DevMap& m, double x, double y, int& cx, int& cy) {
+  double u = (x - m.ox) * m.inv_res;
+  double v = (y - m.oy) * m.inv_res;
+  double fu = floor(u), fv = floor(v);
+  if (!(fu > -1.0e9 && fu < 1.0e9 && fv > -1.0e9 && fv < 1.0e9)) { cx = -1; cy = -1; return false; }
+  cx = (int)fu - m.col0;
+  cy = (int)fv - m.row0;
+  return cx >= 0 && cx < m.w && cy >= 0 && cy < m.h;
+}
+__device__ __forceinline__ int rd_drivable_at(const DevMap& m, int cx, int cy) {
+  if (cx < 0 || cx >= m.w || cy < 0 || cy >= m.h) return 0;
+  return (__ldg(m.bits + (size_t)cy * m.rw + (cx >> 5)) >> (cx & 31)) & 1u;
+}
+
+// ---- mbarrier / bulk-copy (TMA, 1-D) wrappers ----
+__device__ __forceinline__ uint32_t rd_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rd_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rd_smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void rd_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rd_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rd_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   rd_smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(rd_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void rd_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(rd_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}

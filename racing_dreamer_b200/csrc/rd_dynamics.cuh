@@ -1,0 +1,340 @@
+// rd_dynamics.cuh -- K2: action transform + single-track dynamics + progress/lap/collision + reward/done
+// + TimeLimit + auto-reset, one thread per env.
+//
+// Replaces, fused into one pass: ReduceActionSpace._normalize [REF dreamer/wrappers.py:129-134] (and the
+// baselines clip [REF baselines/racing/environment/single_agent.py:55-56]), ActionRepeat.step
+// [REF dreamer/wrappers.py:107-116], MultiAgentRaceEnv.step -> pybullet.stepSimulation + task reward/done
+// (racecar_gym, not in tree; call site [REF dreamer/wrappers.py:63-64]), RaceCarWrapper's speed obs
+// [REF dreamer/wrappers.py:66] and TimeLimit.step [REF dreamer/wrappers.py:147-154].
+//
+// State is SoA float64 (x, y, steer, v, yaw, yaw_rate, slip, ...) so that a warp's loads of one field are
+// one coalesced 256-B request; all arithmetic is float64 in a fixed operation order (the translation unit is
+// compiled with -fmad=false) so the result matches the CPU oracle to the rounding of sin/cos/tan.
+#pragma once
+#include "rd_common.cuh"
+#include "rd_lidar.cuh"
+
+struct StepParams {
+  rd_config cfg;
+  double* f64;      // [RD_NF64][n]
+  int32_t* i32;     // [RD_NI32][n]
+  double* stats;    // [8] accumulators (rd_stats order)
+  OriginRec* recs;  // [n]
+  const DevMap* maps;
+  int n;
+};
+
+struct OutPtrs {
+  float* pose; float* velocity; float* speed; float* reward; uint8_t* done; float* progress; int32_t* lap;
+  float* time; uint8_t* flags; uint8_t* occupancy;
+};
+
+__device__ __forceinline__ void st_rhs(const rd_vehicle& p, const double (&q)[7], double sv, double acc, double (&f)[7]) {
+  const double g = 9.81;
+  const double steer = q[2], v = q[3], yaw = q[4], yr = q[5], slip = q[6];
+  double svc;
+  if ((steer <= p.steer_min && sv <= 0.0) || (steer >= p.steer_max && sv >= 0.0)) svc = 0.0;
+  else if (sv <= -p.steer_vel_max) svc = -p.steer_vel_max;
+  else if (sv >= p.steer_vel_max) svc = p.steer_vel_max;
+  else svc = sv;
+  double pos_limit = (v > p.v_switch) ? (p.a_max * p.v_switch / v) : p.a_max;
+  double ac;
+  if ((v <= p.v_min && acc <= 0.0) || (v >= p.v_max && acc >= 0.0)) ac = 0.0;
+  else if (acc <= -p.a_max) ac = -p.a_max;
+  else if (acc >= pos_limit) ac = pos_limit;
+  else ac = acc;
+  const double lwb = p.lf + p.lr;
+  if (fabs(v) < p.v_kinematic) {
+    double cs = cos(steer);
+    double tn = tan(steer);
+    f[0] = v * cos(yaw);
+    f[1] = v * sin(yaw);
+    f[2] = svc;
+    f[3] = ac;
+    f[4] = (v / lwb) * tn;
+    f[5] = (ac / lwb) * tn + (v / (lwb * (cs * cs))) * svc;
+    f[6] = 0.0;
+  } else {
+    double rear = g * p.lf + ac * p.h_cg;
+    double front = g * p.lr - ac * p.h_cg;
+    double k_yr = (-p.mu * p.mass / (v * p.inertia * lwb)) *
+                  (p.lf * p.lf * p.c_sf * front + p.lr * p.lr * p.c_sr * rear);
+    double k_sl = (p.mu * p.mass / (p.inertia * lwb)) * (p.lr * p.c_sr * rear - p.lf * p.c_sf * front);
+    double k_st = (p.mu * p.mass / (p.inertia * lwb)) * (p.lf * p.c_sf * front);
+    double b_yr = (p.mu / (v * v * lwb)) * (p.c_sr * rear * p.lr - p.c_sf * front * p.lf) - 1.0;
+    double b_sl = (p.mu / (v * lwb)) * (p.c_sr * rear + p.c_sf * front);
+    double b_st = (p.mu / (v * lwb)) * (p.c_sf * front);
+    double ang = slip + yaw;
+    f[0] = v * cos(ang);
+    f[1] = v * sin(ang);
+    f[2] = svc;
+    f[3] = ac;
+    f[4] = yr;
+    f[5] = (k_yr * yr + k_sl * slip) + k_st * steer;
+    f[6] = (b_yr * yr - b_sl * slip) + b_st * steer;
+  }
+}
+
+__device__ __forceinline__ void st_tick(const rd_config& cfg, double (&q)[7], double motor, double steering) {
+  const rd_vehicle& p = cfg.vehicle;
+  const double dt = cfg.dt;
+  double target = steering * p.steer_gain * p.steer_max;
+  double sv = (target - q[2]) / dt;
+  double acc = (motor >= 0.0) ? (motor * p.a_drive - p.c_drag * q[3]) : (motor * p.a_brake - p.c_drag * q[3]);
+  double k1[7], k2[7], k3[7], k4[7], t[7];
+  const double h2 = 0.5 * dt, h6 = dt / 6.0;
+  st_rhs(p, q, sv, acc, k1);
+#pragma unroll
+  for (int i = 0; i < 7; ++i) t[i] = q[i] + h2 * k1[i];
+  st_rhs(p, t, sv, acc, k2);
+#pragma unroll
+  for (int i = 0; i < 7; ++i) t[i] = q[i] + h2 * k2[i];
+  st_rhs(p, t, sv, acc, k3);
+#pragma unroll
+  for (int i = 0; i < 7; ++i) t[i] = q[i] + dt * k3[i];
+  st_rhs(p, t, sv, acc, k4);
+#pragma unroll
+  for (int i = 0; i < 7; ++i) q[i] = q[i] + h6 * (((k1[i] + 2.0 * k2[i]) + 2.0 * k3[i]) + k4[i]);
+}
+
+__device__ __forceinline__ int rd_checkpoint_of(const rd_config& cfg, double p) {
+  int c = (int)(p * (double)cfg.n_checkpoints);
+  return c > cfg.n_checkpoints - 1 ? cfg.n_checkpoints - 1 : c;
+}
+__device__ __forceinline__ bool rd_progress_at(const DevMap& m, double x, double y, double& p) {
+  int cx, cy;
+  if (!rd_cell_of(m, x, y, cx, cy)) return false;
+  if (!rd_drivable_at(m, cx, cy)) return false;
+  p = (double)__ldg(m.dist + (size_t)cy * m.w + cx) / (double)m.dmax;
+  return true;
+}
+__device__ __forceinline__ bool rd_collides(const rd_config& cfg, const DevMap& m, double x, double y, double yaw) {
+  int cx, cy;
+  if (!rd_cell_of(m, x, y, cx, cy) || !rd_drivable_at(m, cx, cy)) return true;
+  double c = cos(yaw), s = sin(yaw);
+  double hl = 0.5 * cfg.vehicle.body_length, hw = 0.5 * cfg.vehicle.body_width;
+  double ax = hl * c, ay = hl * s, bx = hw * s, by = hw * c;
+  double px[4] = {(x + ax) - bx, (x + ax) + bx, (x - ax) - bx, (x - ax) + bx};
+  double py[4] = {(y + ay) + by, (y + ay) - by, (y - ay) + by, (y - ay) - by};
+  bool col = false;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (!rd_cell_of(m, px[k], py[k], cx, cy) || !rd_drivable_at(m, cx, cy)) col = true;
+  return col;
+}
+
+// reset of one env: pose from the map's tables (grid slot 0 or a Philox-sampled candidate)
+// [REF dreamer/wrappers.py:91-92 reset(mode=...); sampler itself is racecar_gym -> NEW-SPEC]
+__device__ __forceinline__ void rd_reset_one(const StepParams& P, int e, int mode) {
+  const rd_config& cfg = P.cfg;
+  const int n = P.n;
+  const DevMap& m = P.maps[P.i32[(size_t)RD_I_MAP * n + e]];
+  const uint32_t episode = (uint32_t)P.i32[(size_t)RD_I_EPISODE * n + e];
+  const uint64_t gid = (uint64_t)(cfg.env_id_offset + e);
+  double x, y, yaw;
+  if (mode == RD_RESET_GRID || m.n_reset <= 0) {
+    x = m.start[0]; y = m.start[1]; yaw = m.start[2];
+  } else {
+    uint32_t c[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), episode, 0u};
+    philox4x32_10(c, (uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32) ^ RD_STREAM_RESET);
+    uint32_t idx = __umulhi(c[0], (uint32_t)m.n_reset);
+    x = m.reset[3 * idx]; y = m.reset[3 * idx + 1]; yaw = m.reset[3 * idx + 2];
+    if (mode == RD_RESET_RANDOM_BIDIRECTIONAL && (c[1] & 1u)) yaw = yaw + 3.14159265358979323846;
+  }
+  double* f = P.f64;
+  f[(size_t)RD_S_X * n + e] = x; f[(size_t)RD_S_Y * n + e] = y; f[(size_t)RD_S_STEER * n + e] = 0.0;
+  f[(size_t)RD_S_V * n + e] = 0.0; f[(size_t)RD_S_YAW * n + e] = yaw; f[(size_t)RD_S_YAWRATE * n + e] = 0.0;
+  f[(size_t)RD_S_SLIP * n + e] = 0.0; f[(size_t)RD_S_TIME * n + e] = 0.0;
+  double p = 0.0;
+  rd_progress_at(m, x, y, p);
+  f[(size_t)RD_S_PROGRESS * n + e] = p;
+  f[(size_t)RD_S_LAST * n + e] = 1.0 + p;
+  f[(size_t)RD_S_START * n + e] = 1.0 + p;
+  f[(size_t)RD_S_RETURN * n + e] = 0.0;
+  int32_t* I = P.i32;
+  I[(size_t)RD_I_LAP * n + e] = 1;
+  I[(size_t)RD_I_CHECKPOINT * n + e] = rd_checkpoint_of(cfg, p);
+  I[(size_t)RD_I_FLAGS * n + e] = 0;
+  I[(size_t)RD_I_AGENT_STEP * n + e] = 0;
+  I[(size_t)RD_I_EPISODE * n + e] = (int32_t)(episode + 1u);
+}
+
+// observation scalars + the origin record for the LiDAR / occupancy kernels, from the committed state
+__device__ __forceinline__ void rd_write_obs(const StepParams& P, const OutPtrs& o, int e, int was_reset) {
+  const int n = P.n;
+  const double* f = P.f64;
+  const int32_t* I = P.i32;
+  const int mid = I[(size_t)RD_I_MAP * n + e];
+  const double x = f[(size_t)RD_S_X * n + e], y = f[(size_t)RD_S_Y * n + e], yaw = f[(size_t)RD_S_YAW * n + e];
+  const double v = f[(size_t)RD_S_V * n + e], slip = f[(size_t)RD_S_SLIP * n + e];
+  OriginRec rec;
+  rd_make_origin(P.maps[mid], x, y, yaw, P.cfg.lidar_offset, rec);
+  rec.gid = (uint32_t)(P.cfg.env_id_offset + e);
+  rec.episode = (uint32_t)I[(size_t)RD_I_EPISODE * n + e];
+  rec.step = (uint32_t)I[(size_t)RD_I_AGENT_STEP * n + e];
+  rec.was_reset = was_reset;
+  rec.pad = mid;
+  P.recs[e] = rec;
+  const double two_pi = 6.283185307179586;
+  const double wy = yaw - rint(yaw / two_pi) * two_pi;
+  const double vx = v * cos(slip), vy = v * sin(slip);
+  if (o.pose) {
+    float* p = o.pose + (size_t)e * 6;
+    p[0] = (float)x; p[1] = (float)y; p[2] = 0.f; p[3] = 0.f; p[4] = 0.f; p[5] = (float)wy;
+  }
+  if (o.velocity) {
+    float* q = o.velocity + (size_t)e * 6;
+    q[0] = (float)vx; q[1] = (float)vy; q[2] = 0.f; q[3] = 0.f; q[4] = 0.f;
+    q[5] = (float)f[(size_t)RD_S_YAWRATE * n + e];
+  }
+  if (o.speed) o.speed[e] = (float)sqrt(vx * vx + vy * vy);  // [REF dreamer/wrappers.py:66]
+}
+
+__global__ void __launch_bounds__(128) k_reset(StepParams P, OutPtrs o, const uint8_t* __restrict__ mask, int mode) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P.n) return;
+  const int n = P.n;
+  const bool sel = (!mask || mask[e]);
+  if (sel) rd_reset_one(P, e, mode);
+  rd_write_obs(P, o, e, sel ? 1 : 3);  // 3: not reset here -> occupancy output left untouched
+  if (sel) {
+    if (o.reward) o.reward[e] = 0.f;
+    if (o.done) o.done[e] = 0;
+    if (o.progress) o.progress[e] = (float)P.f64[(size_t)RD_S_PROGRESS * n + e];
+    if (o.lap) o.lap[e] = P.i32[(size_t)RD_I_LAP * n + e];
+    if (o.time) o.time[e] = 0.f;
+    if (o.flags) o.flags[e] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_step(StepParams P, OutPtrs o, const float* __restrict__ actions) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = P.n;
+  const rd_config& cfg = P.cfg;
+  double st[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // rd_stats contributions of this env
+  if (e < n) {
+    double* f = P.f64;
+    int32_t* I = P.i32;
+    int flags = I[(size_t)RD_I_FLAGS * n + e];
+    if (flags & RD_F_NEEDS_RESET) {  // frozen until reset [REF dreamer/wrappers.py:148]
+      if (o.reward) o.reward[e] = 0.f;
+      if (o.done) o.done[e] = 1;
+      if (o.progress) o.progress[e] = (float)f[(size_t)RD_S_PROGRESS * n + e];
+      if (o.lap) o.lap[e] = I[(size_t)RD_I_LAP * n + e];
+      if (o.time) o.time[e] = (float)f[(size_t)RD_S_TIME * n + e];
+      if (o.flags) o.flags[e] = (uint8_t)flags;
+      P.recs[e].was_reset = 2;
+    } else {
+      const DevMap& m = P.maps[I[(size_t)RD_I_MAP * n + e]];
+      // a4 [REF dreamer/wrappers.py:129-134; baselines single_agent.py:55-56]: numpy keeps (action+1)/2 of a
+      // float32 policy output in float32 and promotes to float64 at `* (high-low)` (float64 arrays).
+      double a[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        float af = actions[2 * e + k];
+        if (cfg.clip_actions) af = af < -1.0f ? -1.0f : (af > 1.0f ? 1.0f : af);
+        if (cfg.rescale_actions) {
+          const float t = __fdiv_rn(__fadd_rn(af, 1.0f), 2.0f);
+          a[k] = (double)t * (cfg.action_high[k] - cfg.action_low[k]) + cfg.action_low[k];
+        } else {
+          a[k] = (double)af;
+        }
+      }
+      double q[7];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) q[k] = f[(size_t)k * n + e];
+      double time = f[(size_t)RD_S_TIME * n + e], p = f[(size_t)RD_S_PROGRESS * n + e];
+      double last = f[(size_t)RD_S_LAST * n + e];
+      int lap = I[(size_t)RD_I_LAP * n + e], cp = I[(size_t)RD_I_CHECKPOINT * n + e];
+      double total = 0.0;
+      int done = 0;
+      const int ncp = cfg.n_checkpoints;
+      for (int t = 0; t < cfg.action_repeat; ++t) {  // ActionRepeat [REF dreamer/wrappers.py:107-116]
+        st_tick(cfg, q, a[0], a[1]);
+        time = time + cfg.dt;
+        const bool col = rd_collides(cfg, m, q[0], q[1], q[4]);
+        int cx, cy;
+        const bool inside = rd_cell_of(m, q[0], q[1], cx, cy);
+        flags &= ~(RD_F_COLLISION | RD_F_LEFT_MAP);
+        if (col) flags |= RD_F_COLLISION;
+        if (!inside) flags |= RD_F_LEFT_MAP;
+        if (!(q[0] == q[0] && q[1] == q[1] && q[3] == q[3] && q[4] == q[4])) flags |= RD_F_NAN;
+        rd_progress_at(m, q[0], q[1], p);
+        const int cn = rd_checkpoint_of(cfg, p);
+        if (cn == cp + 1) { cp = cn; flags &= ~RD_F_WRONG_WAY; }
+        else if (cp == ncp - 1 && cn == 0 && ncp > 1) { lap += 1; cp = 0; flags &= ~RD_F_WRONG_WAY; }
+        else if (cn == cp - 1 || (cp == 0 && cn == ncp - 1 && ncp > 1)) { flags |= RD_F_WRONG_WAY; }
+        const double cur = (double)lap + p;
+        double r;
+        bool d;
+        if (cfg.task == RD_TASK_MAX_SPEED) {  // [REF baselines/racing/environment/tasks.py:6-18]
+          r = col ? -1.0 : -exp(fabs(a[1]) - q[3] * cos(q[6]));
+          d = false;
+        } else {  // maximize_progress [REF dreamer/scenarios/max_progress/austria.yml:8-10]
+          double delta = cur - last;
+          if (delta > 0.5) delta = delta - 1.0;
+          if (delta < -0.5) delta = delta + 1.0;
+          if (cfg.progress_abs) delta = fabs(delta);
+          r = cfg.frame_reward + cfg.progress_reward * delta;
+          if (col) r = r + cfg.collision_reward;
+          d = (cfg.terminate_on_collision && col) || (lap > cfg.laps) || (time > cfg.time_limit);
+        }
+        last = cur;
+        total = total + r;
+        if (d && !(cfg.repeat_semantics == RD_REPEAT_BASELINES && t == 0 && cfg.action_repeat > 1)) { done = 1; break; }
+      }
+      const int agent_step = I[(size_t)RD_I_AGENT_STEP * n + e] + 1;  // TimeLimit [REF dreamer/wrappers.py:147-154]
+      int timeout = 0;
+      if (cfg.time_limit_steps > 0 && agent_step >= cfg.time_limit_steps) { timeout = !done; done = 1; }
+      const double ret = f[(size_t)RD_S_RETURN * n + e] + total;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) f[(size_t)k * n + e] = q[k];
+      f[(size_t)RD_S_TIME * n + e] = time; f[(size_t)RD_S_PROGRESS * n + e] = p;
+      f[(size_t)RD_S_LAST * n + e] = last; f[(size_t)RD_S_RETURN * n + e] = ret;
+      I[(size_t)RD_I_LAP * n + e] = lap; I[(size_t)RD_I_CHECKPOINT * n + e] = cp;
+      I[(size_t)RD_I_AGENT_STEP * n + e] = agent_step;
+      if (done && !cfg.auto_reset) flags |= RD_F_NEEDS_RESET;
+      I[(size_t)RD_I_FLAGS * n + e] = flags;
+      if (o.reward) o.reward[e] = (float)total;
+      if (o.done) o.done[e] = (uint8_t)done;
+      if (o.progress) o.progress[e] = (float)p;
+      if (o.lap) o.lap[e] = lap;
+      if (o.time) o.time[e] = (float)time;
+      if (o.flags) o.flags[e] = (uint8_t)flags;
+      st[6] = 1.0;
+      if (done) {
+        st[0] = 1.0; st[1] = ret; st[2] = ((double)lap + p) - f[(size_t)RD_S_START * n + e];
+        st[3] = (double)agent_step; st[4] = (flags & RD_F_COLLISION) ? 1.0 : 0.0; st[5] = (double)(lap - 1);
+        st[7] = timeout ? 1.0 : 0.0;
+      }
+      int was_reset = 0;
+      if (done && cfg.auto_reset) { rd_reset_one(P, e, cfg.reset_mode); was_reset = 1; }
+      rd_write_obs(P, o, e, was_reset);
+    }
+  }
+  // K5 episode statistics: warp reduce, one atomic per warp and counter
+  // [REF dreamer/tools.py:159-206 simulate(): per-episode return / progress lists]
+  const unsigned any_done = __ballot_sync(0xffffffffu, st[0] != 0.0);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (k != 6 && !any_done) continue;
+    double v = st[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(P.stats + k, v);
+  }
+}
+
+// a1 stage entry: dynamics only, state [7][n] SoA, commands [n][2] sim-facing (rd_dynamics)
+__global__ void __launch_bounds__(128) k_dynamics(rd_config cfg, double* __restrict__ state,
+                                                   const double* __restrict__ commands, int n, int n_ticks) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  double q[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) q[k] = state[(size_t)k * n + e];
+  const double motor = commands[2 * e], steering = commands[2 * e + 1];
+  for (int t = 0; t < n_ticks; ++t) st_tick(cfg, q, motor, steering);
+#pragma unroll
+  for (int k = 0; k < 7; ++k) state[(size_t)k * n + e] = q[k];
+}

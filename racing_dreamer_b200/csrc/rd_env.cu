@@ -1,0 +1,504 @@
+// rd_env.cu -- librd_env.so: the C ABI of include/rd_env.h over the sm_100a kernels.
+//
+// One handle = one CUDA device, one batch of envs.  The library owns the env state (SoA float64/int32),
+// the uploaded maps and a few scratch arrays; every I/O buffer is a caller-owned device pointer.
+// There is no CPU path: rd_create fails with RD_ERR_NO_DEVICE when no sm_100 device is usable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "rd_common.cuh"
+#include "rd_dynamics.cuh"
+#include "rd_lidar.cuh"
+#include "rd_occupancy.cuh"
+
+#define RD_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct HostMap {
+  DevMap dev{};
+  void* d_bits = nullptr;
+  void* d_dist = nullptr;
+  void* d_start = nullptr;
+  void* d_reset = nullptr;
+  bool present = false;
+};
+
+}  // namespace
+
+struct rd_env {
+  rd_config cfg{};
+  int device = 0;
+  int sm_count = 0;
+  int n = 0;
+  double* d_f64 = nullptr;
+  int32_t* d_i32 = nullptr;
+  double* d_stats = nullptr;
+  OriginRec* d_recs = nullptr;
+  double* d_beam_tab = nullptr;
+  DevMap* d_maps = nullptr;
+  int32_t* d_env_order = nullptr;  // env indices grouped by map
+  OccScratch occ{};
+  HostMap maps[RD_MAX_MAPS];
+  std::vector<int> order_offset;   // RD_MAX_MAPS + 1 offsets into d_env_order
+  bool maps_dirty = true, assigned = false, was_reset = false;
+  // scratch for the stage entry points
+  OriginRec* d_stage_recs = nullptr;
+  int32_t* d_stage_ids = nullptr;
+  int stage_cap = 0;
+  int64_t launches = 0;
+  std::string error;
+};
+
+namespace {
+
+int fail(rd_env* env, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  if (env) env->error = buf;
+  return code;
+}
+
+#define CUDA_TRY(env, expr)                                                                         \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) return fail(env, RD_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e));  \
+  } while (0)
+
+void default_config(rd_config* c) {
+  std::memset(c, 0, sizeof(*c));
+  c->abi_version = RD_ABI_VERSION;
+  c->n_envs = 1;
+  c->n_beams = 1080;          // [REF dreamer/dream.py:66]
+  c->action_repeat = 4;       // [REF dreamer/dream.py:55]
+  c->repeat_semantics = RD_REPEAT_DREAMER;
+  c->obs_flags = RD_OBS_LIDAR;
+  c->task = RD_TASK_MAX_PROGRESS;
+  c->laps = 10;               // [REF dreamer/scenarios/max_progress/austria.yml:10]
+  c->terminate_on_collision = 1;
+  c->n_checkpoints = 20;
+  c->time_limit_steps = 0;
+  c->auto_reset = 0;
+  c->reset_mode = RD_RESET_GRID;
+  c->rescale_actions = 1;
+  c->clip_actions = 0;
+  c->progress_abs = 0;
+  c->env_id_offset = 0;
+  c->seed = 0;
+  c->dt = 0.01;               // [REF dreamer/callbacks.py:23]
+  c->time_limit = 180.0;
+  c->collision_reward = -1.0;
+  c->progress_reward = 100.0;
+  c->frame_reward = 0.0;
+  c->action_low[0] = 0.005; c->action_low[1] = -1.0;   // [REF dreamer/dream.py:138]
+  c->action_high[0] = 1.0;  c->action_high[1] = 1.0;
+  c->lidar_fov = 270.0 * (3.14159265358979323846 / 180.0);  // [REF dreamer/tools.py:84-86]
+  c->lidar_range_min = 0.25;
+  c->lidar_range_max = 15.0;  // [REF dreamer/tools.py:274]
+  c->lidar_offset = 0.0;
+  c->lidar_noise = 0.0f;
+  rd_vehicle* v = &c->vehicle;
+  v->mu = 1.0489; v->c_sf = 4.718; v->c_sr = 5.4562; v->lf = 0.15875; v->lr = 0.17145; v->h_cg = 0.074;
+  v->mass = 3.74; v->inertia = 0.04712;
+  v->steer_min = -0.42; v->steer_max = 0.42; v->steer_vel_max = 3.2;  // [REF ros_agent/models/dreamer/racing_dreamer.py:14]
+  v->v_switch = 7.319; v->a_max = 9.51; v->v_min = 0.0; v->v_max = 5.0;  // [REF racing_dreamer.py:16]
+  v->v_kinematic = 0.5;
+  v->a_drive = 6.0; v->a_brake = 8.26; v->c_drag = 1.0;  // [REF ros_agent/agents/follow_the_gap/src/agent.py:74]
+  v->steer_gain = 1.0;
+  v->body_length = 0.50; v->body_width = 0.27;
+}
+
+int sync_maps(rd_env* env) {
+  if (!env->maps_dirty) return RD_OK;
+  DevMap host[RD_MAX_MAPS];
+  for (int i = 0; i < RD_MAX_MAPS; ++i) host[i] = env->maps[i].dev;
+  CUDA_TRY(env, cudaMemcpy(env->d_maps, host, sizeof(host), cudaMemcpyHostToDevice));
+  env->maps_dirty = false;
+  return RD_OK;
+}
+
+LidarParams lidar_params(const rd_env* env, const DevMap& m) {
+  const rd_config& c = env->cfg;
+  LidarParams lp{};
+  lp.n_beams = c.n_beams;
+  lp.groups = (c.n_beams + 31) / 32;
+  lp.normalize = (c.obs_flags & RD_OBS_LIDAR_NORM) ? 1 : 0;
+  lp.range_min = (float)c.lidar_range_min;
+  lp.range_max = (float)c.lidar_range_max;
+  lp.noise = c.lidar_noise;
+  lp.scale = (float)((double)(1 << (RD_DIR_BITS - RD_SUB_BITS)) * m.res);
+  lp.rsub = (int64_t)std::rint(c.lidar_range_max * m.inv_res * (double)RD_SUB);
+  lp.key0 = (uint32_t)c.seed;
+  lp.key1 = (uint32_t)(c.seed >> 32) ^ RD_STREAM_LIDAR;
+  return lp;
+}
+
+// LiDAR launch for the envs of one map: persistent CTAs, grid = resident CTAs on all SMs.
+template <int WARPS>
+int launch_lidar_t(rd_env* env, int map_id, const OriginRec* recs, const int32_t* order, int n_env, float* out,
+                   cudaStream_t s) {
+  const DevMap& m = env->maps[map_id].dev;
+  LidarParams lp = lidar_params(env, m);
+  const size_t tab_bytes = ((size_t)2 * lp.n_beams * 8 + 15) & ~(size_t)15;
+  const size_t smem = 16 + tab_bytes + (size_t)m.bits_bytes;
+  auto kern = k_lidar<WARPS>;
+  CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CUDA_TRY(env, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+  if (per_sm < 1) return fail(env, RD_ERR_INVALID, "map %d (%zu B) does not fit in shared memory", map_id, smem);
+  const long long items = (long long)n_env * lp.groups;
+  long long grid = std::min<long long>((items + WARPS - 1) / WARPS, (long long)env->sm_count * per_sm);
+  if (grid < 1) return RD_OK;
+  kern<<<(unsigned)grid, WARPS * 32, smem, s>>>(env->d_maps, map_id, recs, order, n_env, lp, env->d_beam_tab, out);
+  env->launches++;
+  CUDA_TRY(env, cudaGetLastError());
+  return RD_OK;
+}
+
+int launch_lidar(rd_env* env, int map_id, const OriginRec* recs, const int32_t* order, int n_env, float* out,
+                 cudaStream_t s) {
+  const DevMap& m = env->maps[map_id].dev;
+  // small maps: 16-warp CTAs (several per SM); large maps: 32-warp CTAs so one resident copy feeds 32 warps
+  if (m.bits_bytes > 72 * 1024) return launch_lidar_t<32>(env, map_id, recs, order, n_env, out, s);
+  return launch_lidar_t<16>(env, map_id, recs, order, n_env, out, s);
+}
+
+int launch_occupancy(rd_env* env, int map_id, const OriginRec* recs, const double* poses_xyyaw,
+                     const int32_t* order, int n_env, uint8_t* out, cudaStream_t s) {
+  int rc = occ_launch(env->occ, env->d_maps, map_id, env->maps[map_id].dev, recs, poses_xyyaw, env->d_f64, env->n,
+                      order, n_env, out, env->sm_count, s, &env->launches);
+  if (rc != 0) return fail(env, RD_ERR_CUDA, "occupancy launch: %s", cudaGetErrorString((cudaError_t)rc));
+  return RD_OK;
+}
+
+OutPtrs out_ptrs(const rd_outputs* o) {
+  OutPtrs p{};
+  if (o) {
+    p.pose = o->pose_dev; p.velocity = o->velocity_dev; p.speed = o->speed_dev; p.reward = o->reward_dev;
+    p.done = o->done_dev; p.progress = o->progress_dev; p.lap = o->lap_dev; p.time = o->time_dev;
+    p.flags = o->flags_dev; p.occupancy = o->occupancy_dev;
+  }
+  return p;
+}
+
+StepParams step_params(rd_env* env) {
+  StepParams P{};
+  P.cfg = env->cfg;
+  P.f64 = env->d_f64; P.i32 = env->d_i32; P.stats = env->d_stats; P.recs = env->d_recs; P.maps = env->d_maps;
+  P.n = env->n;
+  return P;
+}
+
+int observe(rd_env* env, const rd_outputs* out, cudaStream_t s) {
+  if (!out) return RD_OK;
+  for (int mid = 0; mid < RD_MAX_MAPS; ++mid) {
+    const int n_env = env->order_offset[mid + 1] - env->order_offset[mid];
+    if (n_env == 0) continue;
+    const int32_t* order = env->d_env_order + env->order_offset[mid];
+    if (out->lidar_dev && (env->cfg.obs_flags & RD_OBS_LIDAR)) {
+      int rc = launch_lidar(env, mid, env->d_recs, order, n_env, out->lidar_dev, s);
+      if (rc) return rc;
+    }
+    if (out->occupancy_dev && (env->cfg.obs_flags & RD_OBS_OCCUPANCY)) {
+      int rc = launch_occupancy(env, mid, env->d_recs, nullptr, order, n_env, out->occupancy_dev, s);
+      if (rc) return rc;
+    }
+  }
+  return RD_OK;
+}
+
+int ensure_stage(rd_env* env, int n) {
+  if (n <= env->stage_cap) return RD_OK;
+  if (env->d_stage_recs) cudaFree(env->d_stage_recs);
+  if (env->d_stage_ids) cudaFree(env->d_stage_ids);
+  env->d_stage_recs = nullptr; env->d_stage_ids = nullptr; env->stage_cap = 0;
+  CUDA_TRY(env, cudaMalloc(&env->d_stage_recs, sizeof(OriginRec) * (size_t)n));
+  CUDA_TRY(env, cudaMalloc(&env->d_stage_ids, sizeof(int32_t) * (size_t)n));
+  env->stage_cap = n;
+  return RD_OK;
+}
+
+// map_ids_host: ascending or NULL.  Fills runs[mid] = (first, count) and uploads the ids.
+int stage_runs(rd_env* env, const int32_t* ids, int n, int (*runs)[2], cudaStream_t s) {
+  for (int i = 0; i < RD_MAX_MAPS; ++i) runs[i][0] = runs[i][1] = 0;
+  if (!ids) {
+    if (!env->maps[0].present) return fail(env, RD_ERR_STATE, "map 0 not uploaded");
+    runs[0][0] = 0; runs[0][1] = n;
+    return RD_OK;
+  }
+  for (int i = 0; i < n; ++i) {
+    const int id = ids[i];
+    if (id < 0 || id >= RD_MAX_MAPS || !env->maps[id].present) return fail(env, RD_ERR_INVALID, "map id %d not uploaded", id);
+    if (i > 0 && id < ids[i - 1]) return fail(env, RD_ERR_INVALID, "map_ids must be ascending");
+    if (runs[id][1] == 0) runs[id][0] = i;
+    runs[id][1]++;
+  }
+  CUDA_TRY(env, cudaMemcpyAsync(env->d_stage_ids, ids, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
+  return RD_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+RD_API void rd_default_config(rd_config* cfg) { if (cfg) default_config(cfg); }
+RD_API int rd_abi_version(void) { return RD_ABI_VERSION; }
+RD_API const char* rd_last_error(const rd_env* env) { return env ? env->error.c_str() : g_last_error.c_str(); }
+RD_API int64_t rd_launch_count(const rd_env* env) { return env ? env->launches : 0; }
+
+RD_API int rd_create(const rd_config* cfg, rd_env** out) {
+  if (!cfg || !out) return fail(nullptr, RD_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != RD_ABI_VERSION) return fail(nullptr, RD_ERR_INVALID, "abi_version %d != %d", cfg->abi_version, RD_ABI_VERSION);
+  if (cfg->n_envs < 1 || cfg->n_beams < 1 || cfg->n_beams > 8192 || cfg->action_repeat < 1 || cfg->n_checkpoints < 1 ||
+      !(cfg->dt > 0.0) || !(cfg->lidar_range_max > 0.0))
+    return fail(nullptr, RD_ERR_INVALID, "bad config (n_envs %d, n_beams %d, action_repeat %d)", cfg->n_envs, cfg->n_beams, cfg->action_repeat);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    cudaGetLastError();
+    return fail(nullptr, RD_ERR_NO_DEVICE, "no CUDA device: librd_env has no CPU fallback");
+  }
+  int dev = 0;
+  CUDA_TRY(nullptr, cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail(nullptr, RD_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+  rd_env* env = new (std::nothrow) rd_env();
+  if (!env) return fail(nullptr, RD_ERR_NOMEM, "out of host memory");
+  env->cfg = *cfg;
+  env->device = dev;
+  env->sm_count = prop.multiProcessorCount;
+  env->n = cfg->n_envs;
+  env->order_offset.assign(RD_MAX_MAPS + 1, 0);
+  const size_t n = (size_t)env->n;
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc(p, bytes); if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes); } };
+  alloc((void**)&env->d_f64, sizeof(double) * RD_NF64 * n);
+  alloc((void**)&env->d_i32, sizeof(int32_t) * RD_NI32 * n);
+  alloc((void**)&env->d_stats, sizeof(double) * 8);
+  alloc((void**)&env->d_recs, sizeof(OriginRec) * n);
+  alloc((void**)&env->d_beam_tab, sizeof(double) * 2 * (size_t)cfg->n_beams);
+  alloc((void**)&env->d_maps, sizeof(DevMap) * RD_MAX_MAPS);
+  alloc((void**)&env->d_env_order, sizeof(int32_t) * n);
+  if (e != cudaSuccess) {
+    int rc = fail(nullptr, e == cudaErrorMemoryAllocation ? RD_ERR_NOMEM : RD_ERR_CUDA, "allocation: %s", cudaGetErrorString(e));
+    rd_destroy(env);
+    return rc;
+  }
+  // beam table: angle_i = fov/2 - i*fov/(n-1) [REF dreamer/tools.py:84-86], float64 cos | sin
+  std::vector<double> tab(2 * (size_t)cfg->n_beams);
+  for (int i = 0; i < cfg->n_beams; ++i) {
+    double a = (cfg->n_beams > 1) ? (0.5 * cfg->lidar_fov - (double)i * (cfg->lidar_fov / (double)(cfg->n_beams - 1))) : 0.0;
+    tab[i] = std::cos(a);
+    tab[cfg->n_beams + i] = std::sin(a);
+  }
+  e = cudaMemcpy(env->d_beam_tab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { int rc = fail(nullptr, RD_ERR_CUDA, "beam table upload: %s", cudaGetErrorString(e)); rd_destroy(env); return rc; }
+  *out = env;
+  return RD_OK;
+}
+
+RD_API void rd_destroy(rd_env* env) {
+  if (!env) return;
+  cudaFree(env->d_f64); cudaFree(env->d_i32); cudaFree(env->d_stats); cudaFree(env->d_recs);
+  cudaFree(env->d_beam_tab); cudaFree(env->d_maps); cudaFree(env->d_env_order);
+  cudaFree(env->d_stage_recs); cudaFree(env->d_stage_ids);
+  occ_free(env->occ);
+  for (auto& m : env->maps) { cudaFree(m.d_bits); cudaFree(m.d_dist); cudaFree(m.d_start); cudaFree(m.d_reset); }
+  delete env;
+}
+
+RD_API int rd_upload_map(rd_env* env, int map_id, const uint32_t* bits_host, int h, int w, int row_words,
+                         const uint16_t* dist_host, int dmax, double resolution, double origin_x, double origin_y,
+                         int col0, int row0_yup, int full_h, const double* start_poses_host, int n_start,
+                         const double* reset_poses_host, int n_reset) {
+  if (!env) return fail(nullptr, RD_ERR_INVALID, "null handle");
+  if (map_id < 0 || map_id >= RD_MAX_MAPS) return fail(env, RD_ERR_INVALID, "map_id %d out of range [0,%d)", map_id, RD_MAX_MAPS);
+  if (!bits_host || !dist_host || !start_poses_host || h < 3 || w < 3 || row_words * 32 < w || n_start < 1 || dmax < 1 || !(resolution > 0.0))
+    return fail(env, RD_ERR_INVALID, "bad map arguments");
+  // the ray march relies on a non-drivable border: verify it instead of trusting the caller
+  for (int x = 0; x < w; ++x) {
+    if (((bits_host[(size_t)0 * row_words + (x >> 5)] >> (x & 31)) & 1u) || ((bits_host[(size_t)(h - 1) * row_words + (x >> 5)] >> (x & 31)) & 1u))
+      return fail(env, RD_ERR_INVALID, "map %d: border row has drivable cells", map_id);
+  }
+  for (int y = 0; y < h; ++y) {
+    const uint32_t* row = bits_host + (size_t)y * row_words;
+    if ((row[0] & 1u) || ((row[(w - 1) >> 5] >> ((w - 1) & 31)) & 1u)) return fail(env, RD_ERR_INVALID, "map %d: border column has drivable cells", map_id);
+    for (int x = w; x < row_words * 32; ++x)
+      if ((row[x >> 5] >> (x & 31)) & 1u) return fail(env, RD_ERR_INVALID, "map %d: padding bits set", map_id);
+  }
+  HostMap& m = env->maps[map_id];
+  cudaFree(m.d_bits); cudaFree(m.d_dist); cudaFree(m.d_start); cudaFree(m.d_reset);
+  m = HostMap{};
+  const size_t bits_bytes = (size_t)h * row_words * 4;
+  const size_t bits_padded = (bits_bytes + 15) & ~(size_t)15;
+  CUDA_TRY(env, cudaMalloc(&m.d_bits, bits_padded));
+  CUDA_TRY(env, cudaMemset(m.d_bits, 0, bits_padded));
+  CUDA_TRY(env, cudaMemcpy(m.d_bits, bits_host, bits_bytes, cudaMemcpyHostToDevice));
+  CUDA_TRY(env, cudaMalloc(&m.d_dist, sizeof(uint16_t) * (size_t)h * w));
+  CUDA_TRY(env, cudaMemcpy(m.d_dist, dist_host, sizeof(uint16_t) * (size_t)h * w, cudaMemcpyHostToDevice));
+  CUDA_TRY(env, cudaMalloc(&m.d_start, sizeof(double) * 3 * (size_t)n_start));
+  CUDA_TRY(env, cudaMemcpy(m.d_start, start_poses_host, sizeof(double) * 3 * (size_t)n_start, cudaMemcpyHostToDevice));
+  if (n_reset > 0 && reset_poses_host) {
+    CUDA_TRY(env, cudaMalloc(&m.d_reset, sizeof(double) * 3 * (size_t)n_reset));
+    CUDA_TRY(env, cudaMemcpy(m.d_reset, reset_poses_host, sizeof(double) * 3 * (size_t)n_reset, cudaMemcpyHostToDevice));
+  } else {
+    n_reset = 0;
+  }
+  DevMap& d = m.dev;
+  d.bits = (const uint32_t*)m.d_bits; d.dist = (const uint16_t*)m.d_dist;
+  d.start = (const double*)m.d_start; d.reset = (const double*)m.d_reset;
+  d.h = h; d.w = w; d.rw = row_words; d.col0 = col0; d.row0 = row0_yup; d.full_h = full_h; d.dmax = dmax;
+  d.n_start = n_start; d.n_reset = n_reset; d.bits_bytes = (int)bits_padded;
+  d.res = resolution; d.inv_res = 1.0 / resolution; d.ox = origin_x; d.oy = origin_y;
+  m.present = true;
+  env->maps_dirty = true;
+  return RD_OK;
+}
+
+RD_API int rd_assign_maps(rd_env* env, const int32_t* ids) {
+  if (!env) return fail(nullptr, RD_ERR_INVALID, "null handle");
+  const int n = env->n;
+  std::vector<int32_t> id(n, 0);
+  if (ids) std::copy(ids, ids + n, id.begin());
+  std::vector<int> count(RD_MAX_MAPS, 0);
+  for (int e = 0; e < n; ++e) {
+    if (id[e] < 0 || id[e] >= RD_MAX_MAPS || !env->maps[id[e]].present) return fail(env, RD_ERR_INVALID, "env %d: map id %d not uploaded", e, id[e]);
+    count[id[e]]++;
+  }
+  env->order_offset[0] = 0;
+  for (int m = 0; m < RD_MAX_MAPS; ++m) env->order_offset[m + 1] = env->order_offset[m] + count[m];
+  std::vector<int> cursor(env->order_offset.begin(), env->order_offset.end() - 1);
+  std::vector<int32_t> order(n);
+  for (int e = 0; e < n; ++e) order[cursor[id[e]]++] = e;
+  CUDA_TRY(env, cudaMemcpy(env->d_env_order, order.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice));
+  CUDA_TRY(env, cudaMemcpy(env->d_i32 + (size_t)RD_I_MAP * n, id.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice));
+  int rc = sync_maps(env);
+  if (rc) return rc;
+  env->assigned = true;
+  return RD_OK;
+}
+
+RD_API int rd_reset(rd_env* env, const uint8_t* mask_dev, int mode, const rd_outputs* out, void* stream) {
+  if (!env) return fail(nullptr, RD_ERR_INVALID, "null handle");
+  if (!env->assigned) return fail(env, RD_ERR_STATE, "rd_assign_maps has not been called");
+  if (mode < RD_RESET_GRID || mode > RD_RESET_RANDOM_BIDIRECTIONAL) return fail(env, RD_ERR_INVALID, "bad reset mode %d", mode);
+  int rc = sync_maps(env);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  k_reset<<<(env->n + 127) / 128, 128, 0, s>>>(step_params(env), out_ptrs(out), mask_dev, mode);
+  env->launches++;
+  CUDA_TRY(env, cudaGetLastError());
+  env->was_reset = true;
+  return observe(env, out, s);
+}
+
+RD_API int rd_step(rd_env* env, const float* actions_dev, const rd_outputs* out, void* stream) {
+  if (!env || !actions_dev) return fail(env, RD_ERR_INVALID, "null argument");
+  if (!env->assigned) return fail(env, RD_ERR_STATE, "rd_assign_maps has not been called");
+  if (!env->was_reset) return fail(env, RD_ERR_STATE, "Must reset environment.");  // [REF dreamer/wrappers.py:148]
+  cudaStream_t s = (cudaStream_t)stream;
+  k_step<<<(env->n + 127) / 128, 128, 0, s>>>(step_params(env), out_ptrs(out), actions_dev);
+  env->launches++;
+  CUDA_TRY(env, cudaGetLastError());
+  return observe(env, out, s);
+}
+
+RD_API int rd_lidar_cast(rd_env* env, const double* poses_dev, const int32_t* map_ids_host, int n, float* ranges_dev,
+                         void* stream) {
+  if (!env || !poses_dev || !ranges_dev || n < 0) return fail(env, RD_ERR_INVALID, "bad argument");
+  if (n == 0) return RD_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = sync_maps(env);
+  if (rc) return rc;
+  if ((rc = ensure_stage(env, n))) return rc;
+  int runs[RD_MAX_MAPS][2];
+  if ((rc = stage_runs(env, map_ids_host, n, runs, s))) return rc;
+  k_origin_from_poses<<<(n + 127) / 128, 128, 0, s>>>(env->d_maps, map_ids_host ? env->d_stage_ids : nullptr, poses_dev, n,
+                                                     env->cfg.lidar_offset, env->d_stage_recs);
+  env->launches++;
+  CUDA_TRY(env, cudaGetLastError());
+  for (int mid = 0; mid < RD_MAX_MAPS; ++mid) {
+    if (runs[mid][1] == 0) continue;
+    const size_t first = (size_t)runs[mid][0];
+    rc = launch_lidar(env, mid, env->d_stage_recs + first, nullptr, runs[mid][1], ranges_dev + first * env->cfg.n_beams, s);
+    if (rc) return rc;
+  }
+  return RD_OK;
+}
+
+RD_API int rd_occupancy_obs(rd_env* env, const double* poses_dev, const int32_t* map_ids_host, int n, uint8_t* out_dev,
+                            void* stream) {
+  if (!env || !poses_dev || !out_dev || n < 0) return fail(env, RD_ERR_INVALID, "bad argument");
+  if (n == 0) return RD_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = sync_maps(env);
+  if (rc) return rc;
+  if ((rc = ensure_stage(env, n))) return rc;
+  int runs[RD_MAX_MAPS][2];
+  if ((rc = stage_runs(env, map_ids_host, n, runs, s))) return rc;
+  for (int mid = 0; mid < RD_MAX_MAPS; ++mid) {
+    if (runs[mid][1] == 0) continue;
+    const size_t first = (size_t)runs[mid][0];
+    rc = launch_occupancy(env, mid, nullptr, poses_dev + 3 * first, nullptr, runs[mid][1], out_dev + first * 4096, s);
+    if (rc) return rc;
+  }
+  return RD_OK;
+}
+
+RD_API int rd_dynamics(rd_env* env, double* state_dev, const double* commands_dev, int n, int n_ticks, void* stream) {
+  if (!env || !state_dev || !commands_dev || n < 0 || n_ticks < 0) return fail(env, RD_ERR_INVALID, "bad argument");
+  if (n == 0) return RD_OK;
+  k_dynamics<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(env->cfg, state_dev, commands_dev, n, n_ticks);
+  env->launches++;
+  CUDA_TRY(env, cudaGetLastError());
+  return RD_OK;
+}
+
+RD_API int rd_get_state(rd_env* env, double* f64_dev, int32_t* i32_dev, void* stream) {
+  if (!env) return fail(nullptr, RD_ERR_INVALID, "null handle");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)env->n;
+  if (f64_dev) CUDA_TRY(env, cudaMemcpyAsync(f64_dev, env->d_f64, sizeof(double) * RD_NF64 * n, cudaMemcpyDeviceToDevice, s));
+  if (i32_dev) CUDA_TRY(env, cudaMemcpyAsync(i32_dev, env->d_i32, sizeof(int32_t) * RD_NI32 * n, cudaMemcpyDeviceToDevice, s));
+  return RD_OK;
+}
+
+RD_API int rd_set_state(rd_env* env, const double* f64_dev, const int32_t* i32_dev, void* stream) {
+  if (!env) return fail(nullptr, RD_ERR_INVALID, "null handle");
+  if (!env->assigned) return fail(env, RD_ERR_STATE, "rd_assign_maps has not been called");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)env->n;
+  if (f64_dev) CUDA_TRY(env, cudaMemcpyAsync(env->d_f64, f64_dev, sizeof(double) * RD_NF64 * n, cudaMemcpyDeviceToDevice, s));
+  if (i32_dev) {
+    // everything but the map row: map assignment is owned by rd_assign_maps (the env grouping depends on it)
+    CUDA_TRY(env, cudaMemcpyAsync(env->d_i32, i32_dev, sizeof(int32_t) * (size_t)RD_I_MAP * n, cudaMemcpyDeviceToDevice, s));
+  }
+  env->was_reset = true;
+  return RD_OK;
+}
+
+RD_API int rd_read_stats(rd_env* env, rd_stats* out_host, int reset, void* stream) {
+  if (!env || !out_host) return fail(env, RD_ERR_INVALID, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  double h[8];
+  CUDA_TRY(env, cudaMemcpyAsync(h, env->d_stats, sizeof(h), cudaMemcpyDeviceToHost, s));
+  if (reset) CUDA_TRY(env, cudaMemsetAsync(env->d_stats, 0, sizeof(h), s));
+  CUDA_TRY(env, cudaStreamSynchronize(s));
+  out_host->episodes = h[0]; out_host->return_sum = h[1]; out_host->progress_sum = h[2]; out_host->length_sum = h[3];
+  out_host->collisions = h[4]; out_host->laps_completed = h[5]; out_host->env_steps = h[6]; out_host->timeouts = h[7];
+  return RD_OK;
+}

@@ -1,0 +1,283 @@
+"""BatchedRaceEnv -- the batched tensor API over librd_env.so.
+
+PyTorch is plumbing here (device memory, streams); every number is produced by the CUDA kernels behind
+the C ABI in ``include/rd_env.h``.  There is no CPU path: constructing an env without the native library
+or without a CUDA device raises.
+
+Reference interfaces mirrored (argument meaning and defaults):
+* ``RaceCarBaseEnv(track, task)`` + scenario YAML params [REF dreamer/wrappers.py:10-16;
+  dreamer/scenarios/max_progress/austria.yml:8-10]
+* ``ActionRepeat(amount)``, ``ReduceActionSpace(low, high)``, ``TimeLimit(duration)``, ``FixedResetMode(mode)``,
+  ``OccupancyMapObs`` [REF dreamer/wrappers.py:86-158,372-414; dreamer/dream.py:134-140]
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Dict, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _abi
+from .maps import TrackMap, load_track
+
+
+@dataclasses.dataclass
+class EnvConfig:
+    """Host-side mirror of ``rd_config``; defaults = the reference's dreamer training setup."""
+    tracks: Sequence[Union[str, TrackMap]] = ("austria",)
+    n_envs: int = 1
+    action_repeat: int = 4                      # [REF dreamer/dream.py:55]
+    obs_type: str = "lidar"                     # 'lidar' | 'lidar_occupancy' [REF dreamer/dream.py:64-66]
+    normalize_lidar: bool = False               # store r/15-0.5 [REF dreamer/tools.py:274]
+    task: str = "maximize_progress"
+    laps: int = 10
+    time_limit: float = 180.0
+    terminate_on_collision: bool = True
+    collision_reward: float = -1.0
+    progress_reward: float = 100.0
+    frame_reward: float = 0.0
+    n_checkpoints: int = 20
+    time_limit_steps: int = 0                   # TimeLimit(duration) in agent steps; 0 = off
+    auto_reset: bool = True
+    reset_mode: str = "grid"
+    rescale_actions: bool = True                # ReduceActionSpace
+    action_low: Sequence[float] = (0.005, -1.0)  # [REF dreamer/dream.py:138]
+    action_high: Sequence[float] = (1.0, 1.0)
+    clip_actions: bool = False
+    repeat_semantics: str = "dreamer"           # 'dreamer' | 'baselines'
+    progress_abs: bool = False
+    n_beams: int = 1080
+    lidar_noise: float = 0.0
+    seed: int = 0
+    env_id_offset: int = 0
+    map_ids: Optional[Sequence[int]] = None     # per-env index into `tracks`; default: env i -> track i % len
+
+
+def _fill_config(cfg: _abi.RdConfig, ec: EnvConfig) -> None:
+    cfg.n_envs = int(ec.n_envs)
+    cfg.n_beams = int(ec.n_beams)
+    cfg.action_repeat = int(ec.action_repeat)
+    cfg.repeat_semantics = {"dreamer": _abi.REPEAT_DREAMER, "baselines": _abi.REPEAT_BASELINES}[ec.repeat_semantics]
+    flags = _abi.OBS_LIDAR
+    if ec.obs_type == "lidar_occupancy":
+        flags |= _abi.OBS_OCCUPANCY
+    elif ec.obs_type != "lidar":
+        raise ValueError(f"obs_type {ec.obs_type!r}: expected 'lidar' or 'lidar_occupancy'")
+    if ec.normalize_lidar:
+        flags |= _abi.OBS_LIDAR_NORM
+    cfg.obs_flags = flags
+    cfg.task = _abi.TASKS[ec.task]
+    cfg.laps = int(ec.laps)
+    cfg.terminate_on_collision = int(ec.terminate_on_collision)
+    cfg.n_checkpoints = int(ec.n_checkpoints)
+    cfg.time_limit_steps = int(ec.time_limit_steps)
+    cfg.auto_reset = int(ec.auto_reset)
+    cfg.reset_mode = _abi.RESET_MODES[ec.reset_mode]
+    cfg.rescale_actions = int(ec.rescale_actions)
+    cfg.clip_actions = int(ec.clip_actions)
+    cfg.progress_abs = int(ec.progress_abs)
+    cfg.env_id_offset = int(ec.env_id_offset)
+    cfg.seed = int(ec.seed) & 0xFFFFFFFFFFFFFFFF
+    cfg.time_limit = float(ec.time_limit)
+    cfg.collision_reward = float(ec.collision_reward)
+    cfg.progress_reward = float(ec.progress_reward)
+    cfg.frame_reward = float(ec.frame_reward)
+    for k in range(2):
+        cfg.action_low[k] = float(ec.action_low[k])
+        cfg.action_high[k] = float(ec.action_high[k])
+    cfg.lidar_noise = float(ec.lidar_noise)
+
+
+class BatchedRaceEnv:
+    """N independent single-car racing envs stepped by one GPU.
+
+    ``reset(mask=None, mode=None) -> obs`` and ``step(actions f32[N,2]) -> (obs, reward, done, info)``, all
+    values CUDA tensors that alias persistent output buffers (valid until the next call).
+    """
+
+    def __init__(self, config: Optional[EnvConfig] = None, device: Union[str, torch.device, None] = None,
+                 raw_config: Optional[_abi.RdConfig] = None, **kwargs):
+        self.lib = _abi.load_library()
+        if not torch.cuda.is_available():
+            raise _abi.NativeLibraryError("BatchedRaceEnv needs a CUDA device: the env step has no CPU fallback")
+        ec = config if config is not None else EnvConfig(**kwargs)
+        self.config = ec
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.tracks = [t if isinstance(t, TrackMap) else load_track(t) for t in ec.tracks]
+        if raw_config is not None:
+            cfg = raw_config.copy()
+        else:
+            cfg = _abi.default_config()
+            _fill_config(cfg, ec)
+        self.cfg = cfg
+        self.n = int(cfg.n_envs)
+        self.n_beams = int(cfg.n_beams)
+        self._handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.rd_create(C.byref(cfg), C.byref(self._handle)), None)
+            self._keep = []
+            for mid, tm in enumerate(self.tracks):
+                bits = np.ascontiguousarray(tm.packed_bits_yup())
+                dist = np.ascontiguousarray(tm.dist_yup())
+                start = np.ascontiguousarray(tm.start_poses, dtype=np.float64)
+                rst = np.ascontiguousarray(tm.reset_poses, dtype=np.float64)
+                self._check(self.lib.rd_upload_map(
+                    self._handle, mid, bits.ctypes.data, tm.h, tm.w, tm.row_words(), dist.ctypes.data, tm.dmax,
+                    tm.resolution, tm.origin[0], tm.origin[1], tm.c0, tm.cy0, tm.full_shape[0],
+                    start.ctypes.data, start.shape[0], rst.ctypes.data, rst.shape[0]))
+            if ec.map_ids is not None:
+                ids = np.ascontiguousarray(ec.map_ids, dtype=np.int32)
+            else:
+                ids = (np.arange(self.n, dtype=np.int32) % len(self.tracks)).astype(np.int32)
+            if ids.shape != (self.n,):
+                raise ValueError("map_ids must have one entry per env")
+            self.map_ids = ids
+            self._check(self.lib.rd_assign_maps(self._handle, ids.ctypes.data))
+            self._alloc()
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc(self):
+        n, dev = self.n, self.device
+        occ = bool(self.cfg.obs_flags & _abi.OBS_OCCUPANCY)
+        self.buf: Dict[str, Optional[torch.Tensor]] = dict(
+            lidar=torch.zeros((n, self.n_beams), dtype=torch.float32, device=dev),
+            occupancy=torch.zeros((n, 64, 64, 1), dtype=torch.uint8, device=dev) if occ else None,
+            pose=torch.zeros((n, 6), dtype=torch.float32, device=dev),
+            velocity=torch.zeros((n, 6), dtype=torch.float32, device=dev),
+            speed=torch.zeros((n,), dtype=torch.float32, device=dev),
+            reward=torch.zeros((n,), dtype=torch.float32, device=dev),
+            done=torch.zeros((n,), dtype=torch.uint8, device=dev),
+            progress=torch.zeros((n,), dtype=torch.float32, device=dev),
+            lap=torch.zeros((n,), dtype=torch.int32, device=dev),
+            time=torch.zeros((n,), dtype=torch.float32, device=dev),
+            flags=torch.zeros((n,), dtype=torch.uint8, device=dev),
+        )
+        o = _abi.RdOutputs()
+        for k, f in (("lidar", "lidar_dev"), ("occupancy", "occupancy_dev"), ("pose", "pose_dev"),
+                     ("velocity", "velocity_dev"), ("speed", "speed_dev"), ("reward", "reward_dev"),
+                     ("done", "done_dev"), ("progress", "progress_dev"), ("lap", "lap_dev"), ("time", "time_dev"),
+                     ("flags", "flags_dev")):
+            t = self.buf[k]
+            setattr(o, f, t.data_ptr() if t is not None else None)
+        self._out = o
+        self._actions = torch.zeros((n, 2), dtype=torch.float32, device=dev)
+
+    def _check(self, rc: int, handle="self"):
+        if rc != 0:
+            h = self._handle if handle == "self" else None
+            msg = self.lib.rd_last_error(h)
+            raise RuntimeError(f"librd_env error {rc}: {msg.decode() if msg else '?'}")
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ------------------------------------------------------------------ env API
+    def _obs(self) -> Dict[str, torch.Tensor]:
+        obs = {"lidar": self.buf["lidar"], "pose": self.buf["pose"], "velocity": self.buf["velocity"],
+               "speed": self.buf["speed"]}
+        if self.buf["occupancy"] is not None:
+            obs["lidar_occupancy"] = self.buf["occupancy"]
+        return obs
+
+    def _info(self) -> Dict[str, torch.Tensor]:
+        fl = self.buf["flags"]
+        return {"progress": self.buf["progress"], "lap": self.buf["lap"], "time": self.buf["time"],
+                "wrong_way": (fl & _abi.F_WRONG_WAY) != 0, "wall_collision": (fl & _abi.F_COLLISION) != 0,
+                "flags": fl, "pose": self.buf["pose"], "velocity": self.buf["velocity"]}
+
+    def reset(self, mask: Optional[torch.Tensor] = None, mode: Optional[str] = None) -> Dict[str, torch.Tensor]:
+        m = _abi.RESET_MODES[mode] if mode is not None else int(self.cfg.reset_mode)
+        mp = None
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            if mask.shape != (self.n,):
+                raise ValueError("mask must have shape (n_envs,)")
+            mp = mask.data_ptr()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.rd_reset(self._handle, mp, m, C.byref(self._out), self._stream()))
+        return self._obs()
+
+    def step(self, actions: torch.Tensor):
+        if actions.shape != (self.n, 2):
+            raise ValueError(f"actions must have shape ({self.n}, 2), got {tuple(actions.shape)}")
+        a = actions
+        if a.dtype != torch.float32 or a.device != self.device or not a.is_contiguous():
+            self._actions.copy_(a, non_blocking=True)
+            a = self._actions
+        with torch.cuda.device(self.device):
+            self._check(self.lib.rd_step(self._handle, a.data_ptr(), C.byref(self._out), self._stream()))
+        return self._obs(), self.buf["reward"], self.buf["done"].bool(), self._info()
+
+    def step_raw(self, actions_ptr: int) -> None:
+        """rd_step on a raw device pointer; results land in ``self.buf`` (bench / tight loops)."""
+        self._check(self.lib.rd_step(self._handle, actions_ptr, C.byref(self._out), self._stream()))
+
+    # ------------------------------------------------------------------ stage entry points (parity tests)
+    def lidar_cast(self, poses: torch.Tensor, map_ids: Optional[np.ndarray] = None) -> torch.Tensor:
+        p = poses.to(device=self.device, dtype=torch.float64).contiguous().reshape(-1, 3)
+        out = torch.empty((p.shape[0], self.n_beams), dtype=torch.float32, device=self.device)
+        ids = None if map_ids is None else np.ascontiguousarray(map_ids, dtype=np.int32)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.rd_lidar_cast(self._handle, p.data_ptr(), ids.ctypes.data if ids is not None else None,
+                                               p.shape[0], out.data_ptr(), self._stream()))
+        return out
+
+    def occupancy_obs(self, poses: torch.Tensor, map_ids: Optional[np.ndarray] = None) -> torch.Tensor:
+        p = poses.to(device=self.device, dtype=torch.float64).contiguous().reshape(-1, 3)
+        out = torch.empty((p.shape[0], 64, 64), dtype=torch.uint8, device=self.device)
+        ids = None if map_ids is None else np.ascontiguousarray(map_ids, dtype=np.int32)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.rd_occupancy_obs(self._handle, p.data_ptr(),
+                                                  ids.ctypes.data if ids is not None else None, p.shape[0],
+                                                  out.data_ptr(), self._stream()))
+        return out
+
+    def dynamics(self, state: torch.Tensor, commands: torch.Tensor, n_ticks: int) -> torch.Tensor:
+        s = state.to(device=self.device, dtype=torch.float64).contiguous().clone()
+        if s.shape[0] != 7:
+            raise ValueError("state must be [7, n]")
+        cmd = commands.to(device=self.device, dtype=torch.float64).contiguous().reshape(-1, 2)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.rd_dynamics(self._handle, s.data_ptr(), cmd.data_ptr(), s.shape[1], int(n_ticks),
+                                             self._stream()))
+        return s
+
+    # ------------------------------------------------------------------ state / stats
+    def get_state(self):
+        f = torch.empty((_abi.NF64, self.n), dtype=torch.float64, device=self.device)
+        i = torch.empty((_abi.NI32, self.n), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.rd_get_state(self._handle, f.data_ptr(), i.data_ptr(), self._stream()))
+        return f, i
+
+    def set_state(self, f64: torch.Tensor, i32: torch.Tensor) -> None:
+        f = f64.to(device=self.device, dtype=torch.float64).contiguous()
+        i = i32.to(device=self.device, dtype=torch.int32).contiguous()
+        if f.shape != (_abi.NF64, self.n) or i.shape != (_abi.NI32, self.n):
+            raise ValueError("state shapes must be [NF64, n] and [NI32, n]")
+        with torch.cuda.device(self.device):
+            self._check(self.lib.rd_set_state(self._handle, f.data_ptr(), i.data_ptr(), self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()  # f/i may be temporaries
+
+    def read_stats(self, reset: bool = False) -> Dict[str, float]:
+        st = _abi.RdStats()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.rd_read_stats(self._handle, C.byref(st), int(reset), self._stream()))
+        return st.as_dict()
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.rd_launch_count(self._handle))
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            self.lib.rd_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,161 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in tests/golden/ by running the UNMODIFIED reference classes.
+
+Runs only in the build container (needs /root/reference, scipy, Pillow); the fixtures it writes are
+committed so that the parity tests can run where /root/reference does not exist (the GPU box).
+
+  occupancy_golden.npz     OccupancyMapObs.step outputs [REF dreamer/wrappers.py:390-408] for seeded poses on
+                           three tracks (scipy.ndimage.rotate + PIL resize of THIS image: scipy 1.18 / Pillow 12).
+  dreamer_stack_golden.npz BASELINE config 1: the reference wrapper stack of dream.py
+                           (RaceCarWrapper -> ActionRepeat(4) -> ReduceActionSpace -> OccupancyMapObs ->
+                           FixedResetMode('grid') -> TimeLimit -> Collect) [REF dreamer/dream.py:103-140] over the
+                           one-tick oracle env, Columbia, 1000 float32 actions from RandomState(0).
+  baselines_stack_golden.npz  the model-free chain's action path: Flatten(clip) -> ActionRepeat(4) with the
+                           baselines edge semantics [REF baselines/racing/environment/single_agent.py:31-62].
+
+usage: python tests/golden/make_golden.py
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+
+from oracle import ref_stubs  # noqa: E402
+from oracle.ref_env import GridMapShim, OracleRaceEnv, make_reference_stack  # noqa: E402
+from racing_dreamer_b200 import load_track  # noqa: E402
+
+OUT = Path(__file__).resolve().parent
+
+
+def occupancy_golden():
+    import types
+    W = ref_stubs.reference_wrappers()
+    rng = np.random.RandomState(1234)
+    tracks, poses, images = [], [], []
+    for ti, name in enumerate(["austria", "columbia", "treitlstrasse_v2"]):
+        tm = load_track(name)
+
+        class Fake:
+            agent_ids = ["A"]
+            scenario = types.SimpleNamespace(world=types.SimpleNamespace(_maps={"occupancy": GridMapShim(tm)}))
+            pose = None
+
+            def step(self, a):
+                return {"A": {}}, {"A": 0.0}, {"A": False}, {"A": {"pose": self.pose}}
+
+        env = Fake()
+        occ = W.OccupancyMapObs(env)
+        p = tm.reset_poses[rng.randint(0, len(tm.reset_poses), 24)].copy()
+        p[:, 2] += rng.uniform(-np.pi, np.pi, 24)
+        p[:, :2] += rng.uniform(-0.3, 0.3, (24, 2))
+        p[0] = tm.start_poses[0]                       # yaw exactly 0
+        p[1] = (p[1, 0], p[1, 1], np.pi / 2)           # axis-aligned rotations
+        p[2] = (p[2, 0], p[2, 1], -np.pi / 4)
+        p[3] = (p[3, 0], p[3, 1], np.pi)
+        for q in p:
+            env.pose = np.array([q[0], q[1], 0.0, 0.0, 0.0, q[2]])
+            o, _, _, _ = occ.step(None)
+            img = o["A"]["lidar_occupancy"]
+            assert img.shape == (64, 64, 1) and img.dtype == np.uint8 and img.max() <= 1
+            images.append(np.packbits(img[..., 0], axis=1))
+            poses.append(q)
+            tracks.append(ti)
+    np.savez_compressed(OUT / "occupancy_golden.npz", track_names=np.array(["austria", "columbia", "treitlstrasse_v2"]),
+                        track=np.array(tracks, np.int32), poses=np.array(poses, np.float64),
+                        images=np.array(images, np.uint8))
+    print("occupancy_golden:", len(poses), "poses")
+
+
+def dreamer_stack_golden(n_steps=1000, action_repeat=4, duration=125):
+    """config 1 [REF dreamer/dream.py:55,57,109: time_limit 2000 ticks / action_repeat]; a shorter TimeLimit (125
+    agent steps) so that the time-limit branch also fires inside 1000 steps."""
+    tm = load_track("columbia")
+    env = make_reference_stack(tm, action_repeat=action_repeat, time_limit_steps=duration, reset_mode="grid")
+    actions = np.random.RandomState(0).uniform(-1, 1, (n_steps, 2)).astype(np.float32)
+    # damp the steering a little so that episodes last more than a handful of steps
+    actions[:, 1] *= 0.35
+    rec = {k: [] for k in ("reward", "done", "progress", "lap", "time", "speed", "pose", "velocity", "lidar_sum",
+                           "occ_popcount", "reset_before", "wrong_way", "collision")}
+    lidar_full, occ_full = [], []
+    need_reset = True
+    for t in range(n_steps):
+        rec["reset_before"].append(need_reset)
+        if need_reset:
+            obs = env.reset()
+            assert obs["A"]["speed"] == 0.0 and not obs["A"]["lidar_occupancy"].any()
+        obs, rew, done, info = env.step({"A": actions[t]})
+        o, i = obs["A"], info["A"]
+        rec["reward"].append(rew["A"])
+        rec["done"].append(done["A"])
+        rec["progress"].append(i["progress"])
+        rec["lap"].append(i["lap"])
+        rec["time"].append(i["time"])
+        rec["wrong_way"].append(i["wrong_way"])
+        rec["collision"].append(i["wall_collision"])
+        rec["speed"].append(o["speed"])
+        rec["pose"].append(o["pose"])
+        rec["velocity"].append(o["velocity"])
+        rec["lidar_sum"].append(np.sum(o["lidar"], dtype=np.float64))
+        rec["occ_popcount"].append(int(o["lidar_occupancy"].sum()))
+        if t % 20 == 0:
+            lidar_full.append(o["lidar"])
+            occ_full.append(np.packbits(o["lidar_occupancy"][..., 0], axis=1))
+        need_reset = bool(done["A"])
+    out = {k: np.asarray(v) for k, v in rec.items()}
+    assert out["speed"].dtype == np.float32 and out["pose"].dtype == np.float32  # Collect casts [REF wrappers.py:240-250]
+    np.savez_compressed(OUT / "dreamer_stack_golden.npz", actions=actions, action_repeat=action_repeat,
+                        duration=duration, lidar_every20=np.asarray(lidar_full), occ_every20=np.asarray(occ_full),
+                        reward=out["reward"].astype(np.float64), **{k: v for k, v in out.items() if k != "reward"})
+    print("dreamer_stack_golden: episodes", int(out["done"].sum()), "collisions", int(out["collision"].sum()),
+          "max progress", float((out["lap"] + out["progress"] - 1).max()))
+
+
+def baselines_stack_golden(n_steps=400, repeat=4):
+    B = ref_stubs.reference_baselines_env()
+    import gym
+    tm = load_track("austria")
+
+    class Single(gym.Wrapper):  # SingleAgentRaceEnv surface over the one-tick oracle env
+        def __init__(self, env):
+            super().__init__(env)
+            self.action_space = env.action_space["A"]
+            self.observation_space = env.observation_space["A"]
+
+        def step(self, action):
+            o, r, d, i = self.env.step({"A": action})
+            return o["A"], r["A"], d["A"], i["A"]
+
+        def reset(self, **kw):
+            return self.env.reset(**kw)["A"]
+
+    env = Single(OracleRaceEnv(tm))
+    env = B.Flatten(env, flatten_obs=False, flatten_actions=True)
+    env = B.ActionRepeat(env, n=repeat)
+    actions = np.random.RandomState(5).uniform(-1.4, 1.4, (n_steps, 2)).astype(np.float32)  # exercises the clip
+    actions[:, 0] = np.abs(actions[:, 0]) * 0.6 + 0.1
+    actions[::7, 0] = 1.3                                   # > 1: clipped by Flatten
+    actions[:, 1] *= 0.45
+    rec = {k: [] for k in ("reward", "done", "progress", "lap", "time", "reset_before", "collision", "lidar_sum")}
+    need_reset = True
+    for t in range(n_steps):
+        rec["reset_before"].append(need_reset)
+        if need_reset:
+            env.reset(mode="grid")
+        o, r, d, i = env.step(actions[t])
+        rec["reward"].append(r); rec["done"].append(d); rec["progress"].append(i["progress"]); rec["lap"].append(i["lap"])
+        rec["time"].append(i["time"]); rec["collision"].append(i["wall_collision"])
+        rec["lidar_sum"].append(np.sum(o["lidar"].astype(np.float32), dtype=np.float64))
+        need_reset = bool(d)
+    np.savez_compressed(OUT / "baselines_stack_golden.npz", actions=actions, repeat=repeat,
+                        **{k: np.asarray(v) for k, v in rec.items()})
+    print("baselines_stack_golden: episodes", int(np.sum(rec["done"])))
+
+
+if __name__ == "__main__":
+    assert ref_stubs.available(), "/root/reference is required to regenerate the golden fixtures"
+    occupancy_golden()
+    dreamer_stack_golden()
+    baselines_stack_golden()

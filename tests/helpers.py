@@ -1,0 +1,88 @@
+"""Shared replay logic: drive a fused env (CPU oracle or the CUDA path) through a golden trajectory that was
+recorded from the reference wrapper stack, and collect the same per-step quantities."""
+import numpy as np
+
+from racing_dreamer_b200 import _abi
+
+
+def fused_dreamer_config(cfg, action_repeat, duration, occupancy=True):
+    """rd_config equivalent of dream.py's env stack [REF dreamer/dream.py:103-140] with FixedResetMode('grid')."""
+    cfg.n_envs = 1
+    cfg.action_repeat = int(action_repeat)
+    cfg.repeat_semantics = _abi.REPEAT_DREAMER
+    cfg.rescale_actions = 1
+    cfg.clip_actions = 0
+    cfg.time_limit_steps = int(duration)
+    cfg.auto_reset = 0
+    cfg.reset_mode = _abi.RESET_GRID
+    cfg.obs_flags = _abi.OBS_LIDAR | (_abi.OBS_OCCUPANCY if occupancy else 0)
+    return cfg
+
+
+def fused_baselines_config(cfg, repeat):
+    """Flatten(clip) -> ActionRepeat(n) of the model-free chain [REF baselines/racing/environment/single_agent.py:31-62]."""
+    cfg.n_envs = 1
+    cfg.action_repeat = int(repeat)
+    cfg.repeat_semantics = _abi.REPEAT_BASELINES
+    cfg.rescale_actions = 0
+    cfg.clip_actions = 1
+    cfg.time_limit_steps = 0
+    cfg.auto_reset = 0
+    cfg.obs_flags = _abi.OBS_LIDAR
+    return cfg
+
+
+def replay(reset_fn, step_fn, actions, reset_before):
+    """reset_fn() -> None ; step_fn(a[1,2] f32) -> dict of numpy arrays (batch 1).  Returns dict of stacked records."""
+    rec = {}
+    for t in range(actions.shape[0]):
+        if reset_before[t]:
+            reset_fn()
+        out = step_fn(actions[t:t + 1])
+        for k, v in out.items():
+            if v is None:
+                continue
+            rec.setdefault(k, []).append(np.array(v[0]))
+    return {k: np.stack(v) for k, v in rec.items()}
+
+
+def assert_matches_dreamer_golden(rec, g, lidar_tol=0.0, float_tol=0.0):
+    """Flags/occupancy bit-exact always; float quantities within the given tolerance (0 = bit-exact)."""
+    def close(a, b, tol):
+        a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+        if tol == 0.0:
+            assert np.array_equal(a, b), f"max |diff| {np.abs(a - b).max()}"
+        else:
+            assert np.all(np.abs(a - b) <= tol * np.maximum(1.0, np.abs(b))), f"max |diff| {np.abs(a - b).max()}"
+    assert np.array_equal(rec["done"].astype(bool), g["done"])
+    assert np.array_equal(rec["lap"], g["lap"])
+    fl = rec["flags"]
+    assert np.array_equal((fl & _abi.F_COLLISION) != 0, g["collision"])
+    assert np.array_equal((fl & _abi.F_WRONG_WAY) != 0, g["wrong_way"])
+    occ = rec["occupancy"].reshape(len(fl), 64, 64)
+    assert np.array_equal(occ.reshape(len(occ), -1).sum(1), g["occ_popcount"])
+    assert np.array_equal(np.packbits(occ[::20], axis=2), g["occ_every20"])
+    close(rec["reward"], g["reward"].astype(np.float32), float_tol)
+    close(rec["progress"], g["progress"].astype(np.float32), float_tol)
+    close(rec["time"], g["time"].astype(np.float32), float_tol)
+    close(rec["speed"], g["speed"], float_tol)
+    close(rec["pose"], g["pose"], float_tol)
+    close(rec["velocity"], g["velocity"], float_tol)
+    if lidar_tol == 0.0:
+        assert np.array_equal(rec["lidar"][::20], g["lidar_every20"])
+    else:
+        assert np.abs(rec["lidar"][::20] - g["lidar_every20"]).max() <= lidar_tol
+    assert np.abs(rec["lidar"].sum(1, dtype=np.float64) - g["lidar_sum"]).max() <= max(lidar_tol * 1080, 0.0)
+
+
+def assert_matches_baselines_golden(rec, g, float_tol=0.0, lidar_tol=0.0):
+    assert np.array_equal(rec["done"].astype(bool), g["done"])
+    assert np.array_equal(rec["lap"], g["lap"])
+    assert np.array_equal((rec["flags"] & _abi.F_COLLISION) != 0, g["collision"])
+    for k in ("reward", "progress", "time"):
+        a, b = rec[k].astype(np.float64), g[k].astype(np.float32).astype(np.float64)
+        if float_tol == 0.0:
+            assert np.array_equal(a, b), k
+        else:
+            assert np.all(np.abs(a - b) <= float_tol * np.maximum(1.0, np.abs(b))), k
+    assert np.abs(rec["lidar"].sum(1, dtype=np.float64) - g["lidar_sum"]).max() <= lidar_tol * 1080
