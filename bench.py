@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s (and LiDAR beams/s) of the batched racing-environment step on B200.
+
+Contract (driver): `python bench.py --gpus N --steps K --warmup W [--impl reference]`; for N > 1 it is launched
+under torchrun, one rank per GPU.  Rank 0 prints ONE JSON line.
+
+Workload (BASELINE.json configs[1]): Austria track, 1080-beam LiDAR, 4096 batched envs per GPU, action_repeat 8,
+obs 'lidar' f32, reset mode 'random' (seed 1), scripted actions motor=+0.6, steering=0.8*sin(2*pi*k/50 + phi_i),
+auto-reset on.  A "step" = one env.step() of the whole batch.
+
+* value       device-resident env-steps/s: actions already in HBM, outputs stay in HBM; CUDA events per step
+              on the launching stream, L2 flushed between steps (outside the events); max over ranks.
+* e2e         the same metric through the host-facing call (HostSteppedEnv.step: numpy actions in pinned
+              memory -> H2D -> kernels -> D2H of every observation/result array -> numpy), wall clock.
+* roofline    dominant kernel k_lidar: algorithmic bytes per launch / its mean launch duration (CUDA events
+              inside librd_env, rd_enable_timing), against MEASURED_PEAKS.json hbm_gbs.
+* cpu_baseline  the CPU oracle (oracle/rd_oracle.c, kind "port") on all host threads, bounded sample.
+* --impl reference  the reference arm: the same oracle port timed on the host cores (the reference's env
+              arithmetic lives in un-vendored racecar_gym + pybullet, so no reference build exists: DESIGN.md).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+TRACK = "austria"
+N_ENVS = 4096
+N_BEAMS = 1080
+ACTION_REPEAT = 8
+PERIOD = 50
+# state r/w 224 + action 8 + lidar 4320 + scalars 24 + pose/velocity 48
+ALGO_BYTES_PER_ENV_STEP = 4624
+# k_lidar alone: 1080 f32 ranges written + one 48-byte origin record read per env
+LIDAR_BYTES_PER_ENV = N_BEAMS * 4 + 48
+WORKLOAD = f"config2: {TRACK} {N_BEAMS}-beam lidar, {N_ENVS} envs/GPU, action_repeat={ACTION_REPEAT}, obs=lidar f32"
+
+
+def scripted_actions(n, rank=0):
+    """[PERIOD, n, 2] float32: motor +0.6, steering 0.8*sin(2*pi*k/50 + phi_i), phi_i from a seeded stream."""
+    rng = np.random.Generator(np.random.Philox(key=2 + 1000 * rank))
+    phi = rng.uniform(0.0, 2.0 * np.pi, n)
+    k = np.arange(PERIOD)[:, None]
+    a = np.empty((PERIOD, n, 2), np.float32)
+    a[..., 0] = 0.6
+    a[..., 1] = (0.8 * np.sin(2.0 * np.pi * k / PERIOD + phi[None, :])).astype(np.float32)
+    return a
+
+
+def env_config(n_envs, rank=0, obs_type="lidar"):
+    from racing_dreamer_b200 import EnvConfig
+    return EnvConfig(tracks=(TRACK,), n_envs=n_envs, action_repeat=ACTION_REPEAT, obs_type=obs_type, auto_reset=True,
+                     reset_mode="random", seed=1, env_id_offset=rank * n_envs, time_limit_steps=2000 // ACTION_REPEAT)
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def cpu_oracle_run(n_envs, steps, warmup, threads, rank=0):
+    """Times the oracle port on `threads` host threads: `steps` env.step() calls of `n_envs` envs."""
+    from oracle import Oracle
+    from racing_dreamer_b200 import _abi, load_track
+    from racing_dreamer_b200.env import _fill_config
+    from oracle import default_config
+    cfg = default_config()
+    _fill_config(cfg, env_config(n_envs, rank))
+    orc = Oracle(cfg, [load_track(TRACK)], n_threads=threads)
+    orc.reset(mode=_abi.RESET_RANDOM)
+    acts = scripted_actions(n_envs, rank)
+    for k in range(warmup):
+        orc.step(acts[k % PERIOD])
+    t0 = time.perf_counter()
+    for k in range(steps):
+        orc.step(acts[(warmup + k) % PERIOD])
+    dt = time.perf_counter() - t0
+    return n_envs * steps / dt, dt
+
+
+def reference_arm(args):
+    """`--impl reference`: the reference's CPU env path on the host cores.  The reference is Python whose env
+    arithmetic lives in un-vendored racecar_gym + pybullet (not installable offline), so this times the oracle
+    port (oracle/rd_oracle.c) with every host thread, on the same config/metric as our arm."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    # size each step (env sample) so that steps+warmup finish in about two minutes
+    rate, _ = cpu_oracle_run(256, 2, 1, threads)
+    total_steps = max(1, args.steps + args.warmup)
+    n_sample = int(min(N_ENVS, max(threads, rate * 110.0 / total_steps)))
+    value, dt = cpu_oracle_run(n_sample, args.steps, args.warmup, threads)
+    line = {
+        "metric": "env_steps_per_s", "value": value, "unit": "env-steps/s", "impl": "reference", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "beams_per_s": value * N_BEAMS,
+        "config": {"workload": WORKLOAD, "sample": f"{n_sample} of {N_ENVS} envs per step"},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                         "sample": f"{n_sample} envs x {args.steps} steps, oracle/rd_oracle.c, {threads} OpenMP threads"},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=N_ENVS, help="envs per GPU (bench default = BASELINE config 2)")
+    ap.add_argument("--obs", default="lidar", choices=["lidar", "lidar_occupancy"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 200)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from racing_dreamer_b200 import BatchedRaceEnv
+    from racing_dreamer_b200.host import HostSteppedEnv
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.envs
+    env = BatchedRaceEnv(env_config(n, rank, args.obs), device=dev)
+    acts = torch.from_numpy(scripted_actions(n, rank)).to(dev)      # inputs resident in HBM before timing
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    env.reset()
+    for k in range(args.warmup):
+        env.step_raw(acts[k % PERIOD].data_ptr())
+    barrier()
+
+    # ---- timed region: K steps, each bracketed by CUDA events on the launching stream, L2 flushed in between ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    env.enable_timing(True)
+    env.read_timing(reset=True)
+    launches0 = env.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        env.step_raw(acts[(args.warmup + k) % PERIOD].data_ptr())
+        ev[k][1].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = env.launch_count - launches0
+    timing = env.read_timing(reset=True)
+    env.enable_timing(False)
+    gpu_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    # back-to-back (no flush, one event pair) for reference
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    b0.record()
+    for k in range(args.steps):
+        env.step_raw(acts[k % PERIOD].data_ptr())
+    b1.record()
+    barrier()
+    b2b_ms = b0.elapsed_time(b1)
+    clocks = sampler.stop() if rank == 0 else None
+    stats = env.read_stats()
+
+    t = torch.tensor([gpu_ms, b2b_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    gpu_ms_max, b2b_ms_max = float(t[0]), float(t[1])
+
+    # ---- e2e: host numpy actions -> pinned -> H2D -> step -> D2H of all results -> numpy ----
+    e2e_steps = args.e2e_steps or min(args.steps, 200)
+    henv = HostSteppedEnv(env_config(n, rank, args.obs), device=dev, n_shards=4)
+    hacts = scripted_actions(n, rank)
+    henv.reset()
+    for k in range(5):
+        henv.step(hacts[k % PERIOD])
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        out = henv.step(hacts[(5 + k) % PERIOD])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    assert out["lidar"].shape == (n, N_BEAMS) and np.isfinite(out["reward"]).all()
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * e2e_steps / float(te[0])
+
+    # ---- the only collective of the system: episode statistics gathered across ranks at log cadence ----
+    st = torch.tensor([stats[k] for k in sorted(stats)], dtype=torch.float64, device=dev)
+    if world > 1:
+        gathered = [torch.zeros_like(st) for _ in range(world)]
+        dist.all_gather(gathered, st)
+        st = torch.stack(gathered).sum(0)
+    stats_all = dict(zip(sorted(stats), st.tolist()))
+
+    if rank == 0:
+        value = world * n * args.steps / (gpu_ms_max / 1e3)
+        peak, peak_src = measured_peak_gbs()
+        lidar_ms = timing["lidar_ms"] / max(1, timing["lidar_launches"])
+        lidar_gbs = LIDAR_BYTES_PER_ENV * n / (lidar_ms * 1e-3) / 1e9 if lidar_ms > 0 else 0.0
+        line = {
+            "metric": "env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": gpu_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64 dynamics / i32 ray march / f32 ranges", "data": "synthetic",
+            "beams_per_s": value * N_BEAMS,
+            "sim_ticks_per_s": value * ACTION_REPEAT,
+            "config": {"workload": WORKLOAD if (n == N_ENVS and args.obs == "lidar") else
+                       f"{TRACK} {N_BEAMS}-beam, {n} envs/GPU, action_repeat={ACTION_REPEAT}, obs={args.obs}",
+                       "envs_per_gpu": n, "l2": "flushed between steps (256 MiB memset outside the per-step events)",
+                       "parallelism": f"env-sharded x{world}, no collective in step"},
+            "ms_per_step_back_to_back": b2b_ms_max / args.steps,
+            "wall_s_timed_region": wall,
+            "roofline": {"bound": "hbm", "kernel": "k_lidar", "achieved": lidar_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": lidar_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel_ms": lidar_ms, "kernel_share_of_step": timing["lidar_ms"] / max(gpu_ms, 1e-9),
+                         "algorithmic_bytes_per_launch": LIDAR_BYTES_PER_ENV * n,
+                         "step_algorithmic_gbs": ALGO_BYTES_PER_ENV_STEP * value / world / 1e9,
+                         "note": "on-chip bound (shared-memory bit tests + issue slots), see DESIGN.md"},
+            "kernel_ms": {"k_step": timing["step_ms"] / max(1, timing["step_launches"]), "k_lidar": lidar_ms,
+                          "k_occupancy": timing["occupancy_ms"] / max(1, timing["occupancy_launches"])},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": henv.h2d_bytes_per_step,
+                    "d2h_bytes_per_step": henv.d2h_bytes_per_step, "steps": e2e_steps, "shards": len(henv.shards)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "episode_stats": stats_all,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            rate, _ = cpu_oracle_run(256, 2, 1, threads)
+            n_s = int(min(N_ENVS, max(threads, rate * 1.0)))     # ~1 s per step
+            steps_s = 12
+            v, dt = cpu_oracle_run(n_s, steps_s, 2, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                                    "sample": f"{n_s} envs x {steps_s} steps of the same workload, oracle/rd_oracle.c, "
+                                              f"{threads} OpenMP threads, {dt:.1f} s"}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    henv.close()
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

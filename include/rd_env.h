@@ -184,8 +184,17 @@ int rd_set_state(rd_env* env, const double* f64_dev, const int32_t* i32_dev, voi
 /* ---- episode statistics (K5): device-side accumulators -> host struct (synchronises `stream`) ---- */
 int rd_read_stats(rd_env* env, rd_stats* out_host, int reset, void* stream);
 
-/* ---- introspection for bench/profiling: kernels launched by this handle so far ---- */
+/* ---- introspection for bench/profiling ---- */
+/* kernels launched by this handle so far */
 int64_t rd_launch_count(const rd_env* env);
+/* per-kernel device time: when enabled, every launch is bracketed by CUDA events on its stream;
+ * rd_read_timing synchronises those events and returns the accumulated milliseconds per kernel class. */
+typedef struct rd_timing {
+  double step_ms, lidar_ms, occupancy_ms, reset_ms;
+  int64_t step_launches, lidar_launches, occupancy_launches, reset_launches;
+} rd_timing;
+int rd_enable_timing(rd_env* env, int enable);
+int rd_read_timing(rd_env* env, rd_timing* out_host, int reset);
 
 #ifdef __cplusplus
 }

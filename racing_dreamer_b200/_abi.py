@@ -73,10 +73,19 @@ class RdStats(C.Structure):
         return {n: float(getattr(self, n)) for n, _ in self._fields_}
 
 
+class RdTiming(C.Structure):
+    _fields_ = [("step_ms", C.c_double), ("lidar_ms", C.c_double), ("occupancy_ms", C.c_double),
+                ("reset_ms", C.c_double), ("step_launches", C.c_int64), ("lidar_launches", C.c_int64),
+                ("occupancy_launches", C.c_int64), ("reset_launches", C.c_int64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 EXPORTS = (
     "rd_default_config", "rd_create", "rd_destroy", "rd_last_error", "rd_abi_version", "rd_upload_map",
     "rd_assign_maps", "rd_reset", "rd_step", "rd_lidar_cast", "rd_occupancy_obs", "rd_dynamics",
-    "rd_get_state", "rd_set_state", "rd_read_stats", "rd_launch_count",
+    "rd_get_state", "rd_set_state", "rd_read_stats", "rd_launch_count", "rd_enable_timing", "rd_read_timing",
 )
 
 LIB_PATH = Path(__file__).resolve().parent / "librd_env.so"
@@ -135,6 +144,10 @@ def load_library() -> C.CDLL:
     lib.rd_read_stats.restype = i32
     lib.rd_launch_count.argtypes = [vp]
     lib.rd_launch_count.restype = i64
+    lib.rd_enable_timing.argtypes = [vp, i32]
+    lib.rd_enable_timing.restype = i32
+    lib.rd_read_timing.argtypes = [vp, C.POINTER(RdTiming), i32]
+    lib.rd_read_timing.restype = i32
     if lib.rd_abi_version() != ABI_VERSION:
         raise NativeLibraryError(f"{path}: ABI version {lib.rd_abi_version()} != {ABI_VERSION}")
     _lib = lib

@@ -57,6 +57,12 @@ struct rd_env {
   int32_t* d_stage_ids = nullptr;
   int stage_cap = 0;
   int64_t launches = 0;
+  // optional per-kernel timing (rd_enable_timing)
+  bool timing = false;
+  struct Timed { cudaEvent_t a, b; int kind; };
+  std::vector<Timed> timed;
+  std::vector<cudaEvent_t> event_pool;
+  rd_timing acc{};
   std::string error;
 };
 
@@ -131,6 +137,25 @@ int sync_maps(rd_env* env) {
   return RD_OK;
 }
 
+enum { T_STEP = 0, T_LIDAR = 1, T_OCC = 2, T_RESET = 3 };
+
+cudaEvent_t take_event(rd_env* env) {
+  if (!env->event_pool.empty()) { cudaEvent_t e = env->event_pool.back(); env->event_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+// brackets the launches issued during its lifetime with two events on `s`
+struct ScopedTiming {
+  rd_env* env; cudaStream_t s; int kind; cudaEvent_t a = nullptr;
+  ScopedTiming(rd_env* e, cudaStream_t st, int k) : env(e), s(st), kind(k) {
+    if (env->timing) { a = take_event(env); cudaEventRecord(a, s); }
+  }
+  ~ScopedTiming() {
+    if (a) { cudaEvent_t b = take_event(env); cudaEventRecord(b, s); env->timed.push_back({a, b, kind}); }
+  }
+};
+
 LidarParams lidar_params(const rd_env* env, const DevMap& m) {
   const rd_config& c = env->cfg;
   LidarParams lp{};
@@ -163,7 +188,10 @@ int launch_lidar_t(rd_env* env, int map_id, const OriginRec* recs, const int32_t
   const long long items = (long long)n_env * lp.groups;
   long long grid = std::min<long long>((items + WARPS - 1) / WARPS, (long long)env->sm_count * per_sm);
   if (grid < 1) return RD_OK;
-  kern<<<(unsigned)grid, WARPS * 32, smem, s>>>(env->d_maps, map_id, recs, order, n_env, lp, env->d_beam_tab, out);
+  {
+    ScopedTiming tm(env, s, T_LIDAR);
+    kern<<<(unsigned)grid, WARPS * 32, smem, s>>>(env->d_maps, map_id, recs, order, n_env, lp, env->d_beam_tab, out);
+  }
   env->launches++;
   CUDA_TRY(env, cudaGetLastError());
   return RD_OK;
@@ -179,6 +207,7 @@ int launch_lidar(rd_env* env, int map_id, const OriginRec* recs, const int32_t* 
 
 int launch_occupancy(rd_env* env, int map_id, const OriginRec* recs, const double* poses_xyyaw,
                      const int32_t* order, int n_env, uint8_t* out, cudaStream_t s) {
+  ScopedTiming tm(env, s, T_OCC);
   int rc = occ_launch(env->occ, env->d_maps, map_id, env->maps[map_id].dev, recs, poses_xyyaw, env->d_f64, env->n,
                       order, n_env, out, env->sm_count, s, &env->launches);
   if (rc != 0) return fail(env, RD_ERR_CUDA, "occupancy launch: %s", cudaGetErrorString((cudaError_t)rc));
@@ -317,6 +346,8 @@ RD_API void rd_destroy(rd_env* env) {
   cudaFree(env->d_beam_tab); cudaFree(env->d_maps); cudaFree(env->d_env_order);
   cudaFree(env->d_stage_recs); cudaFree(env->d_stage_ids);
   occ_free(env->occ);
+  for (auto& t : env->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+  for (auto& e : env->event_pool) cudaEventDestroy(e);
   for (auto& m : env->maps) { cudaFree(m.d_bits); cudaFree(m.d_dist); cudaFree(m.d_start); cudaFree(m.d_reset); }
   delete env;
 }
@@ -399,7 +430,10 @@ RD_API int rd_reset(rd_env* env, const uint8_t* mask_dev, int mode, const rd_out
   int rc = sync_maps(env);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  k_reset<<<(env->n + 127) / 128, 128, 0, s>>>(step_params(env), out_ptrs(out), mask_dev, mode);
+  {
+    ScopedTiming tm(env, s, T_RESET);
+    k_reset<<<(env->n + 127) / 128, 128, 0, s>>>(step_params(env), out_ptrs(out), mask_dev, mode);
+  }
   env->launches++;
   CUDA_TRY(env, cudaGetLastError());
   env->was_reset = true;
@@ -411,7 +445,10 @@ RD_API int rd_step(rd_env* env, const float* actions_dev, const rd_outputs* out,
   if (!env->assigned) return fail(env, RD_ERR_STATE, "rd_assign_maps has not been called");
   if (!env->was_reset) return fail(env, RD_ERR_STATE, "Must reset environment.");  // [REF dreamer/wrappers.py:148]
   cudaStream_t s = (cudaStream_t)stream;
-  k_step<<<(env->n + 127) / 128, 128, 0, s>>>(step_params(env), out_ptrs(out), actions_dev);
+  {
+    ScopedTiming tm(env, s, T_STEP);
+    k_step<<<(env->n + 127) / 128, 128, 0, s>>>(step_params(env), out_ptrs(out), actions_dev);
+  }
   env->launches++;
   CUDA_TRY(env, cudaGetLastError());
   return observe(env, out, s);
@@ -500,5 +537,32 @@ RD_API int rd_read_stats(rd_env* env, rd_stats* out_host, int reset, void* strea
   CUDA_TRY(env, cudaStreamSynchronize(s));
   out_host->episodes = h[0]; out_host->return_sum = h[1]; out_host->progress_sum = h[2]; out_host->length_sum = h[3];
   out_host->collisions = h[4]; out_host->laps_completed = h[5]; out_host->env_steps = h[6]; out_host->timeouts = h[7];
+  return RD_OK;
+}
+
+RD_API int rd_enable_timing(rd_env* env, int enable) {
+  if (!env) return fail(nullptr, RD_ERR_INVALID, "null handle");
+  env->timing = enable != 0;
+  return RD_OK;
+}
+
+RD_API int rd_read_timing(rd_env* env, rd_timing* out_host, int reset) {
+  if (!env || !out_host) return fail(env, RD_ERR_INVALID, "null argument");
+  for (auto& t : env->timed) {
+    CUDA_TRY(env, cudaEventSynchronize(t.b));
+    float ms = 0.f;
+    CUDA_TRY(env, cudaEventElapsedTime(&ms, t.a, t.b));
+    switch (t.kind) {
+      case T_STEP: env->acc.step_ms += ms; env->acc.step_launches++; break;
+      case T_LIDAR: env->acc.lidar_ms += ms; env->acc.lidar_launches++; break;
+      case T_OCC: env->acc.occupancy_ms += ms; env->acc.occupancy_launches++; break;
+      default: env->acc.reset_ms += ms; env->acc.reset_launches++; break;
+    }
+    env->event_pool.push_back(t.a);
+    env->event_pool.push_back(t.b);
+  }
+  env->timed.clear();
+  *out_host = env->acc;
+  if (reset) env->acc = rd_timing{};
   return RD_OK;
 }

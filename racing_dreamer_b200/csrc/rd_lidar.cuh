@@ -87,7 +87,8 @@ k_lidar(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict
       const long long lx = (lp.rsub * adx) >> RD_DIR_BITS, ly = (lp.rsub * ady) >> RD_DIR_BITS;
       const int nx = (adx != 0 && lx >= bx) ? (int)((lx - bx) >> RD_SUB_BITS) + 1 : 0;
       const int ny = (ady != 0 && ly >= by) ? (int)((ly - by) >> RD_SUB_BITS) + 1 : 0;
-      int n = nx + ny;
+      const int n0 = nx + ny;
+      int n = n0;
       const int stepx = DX > 0 ? 1 : -1;
       const int steprow = DY > 0 ? rw : -rw;
       const int ex = ady << RD_SUB_BITS, ey = adx << RD_SUB_BITS;
@@ -104,8 +105,9 @@ k_lidar(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict
       }
       if (hit) {
         int num, den;
-        if (lastx) { num = bx + (abs(ix - ix0) - 1) * RD_SUB; den = adx; }
-        else       { num = by + (abs(row - iy0 * rw) / rw - 1) * RD_SUB; den = ady; }
+        const int xs = abs(ix - ix0);            // x-crossings taken; the rest of the n0-n steps were y-crossings
+        if (lastx) { num = bx + (xs - 1) * RD_SUB; den = adx; }
+        else       { num = by + ((n0 - n) - xs - 1) * RD_SUB; den = ady; }
         r = __fmul_rn(__fdiv_rn((float)num, (float)den), lp.scale);
       } else {
         r = lp.range_max;

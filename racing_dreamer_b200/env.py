@@ -267,6 +267,15 @@ class BatchedRaceEnv:
             self._check(self.lib.rd_read_stats(self._handle, C.byref(st), int(reset), self._stream()))
         return st.as_dict()
 
+    def enable_timing(self, enable: bool = True) -> None:
+        self._check(self.lib.rd_enable_timing(self._handle, int(enable)))
+
+    def read_timing(self, reset: bool = False) -> Dict[str, float]:
+        t = _abi.RdTiming()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.rd_read_timing(self._handle, C.byref(t), int(reset)))
+        return t.as_dict()
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.rd_launch_count(self._handle))

@@ -1,0 +1,323 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI (librd_env.so) and is
+compared with the CPU oracle on the same seeded inputs, and with the golden fixtures recorded from the reference.
+
+Tolerances (BASELINE.json north_star): occupancy grids and termination/lap/wrong-way flags bit-exact; LiDAR ranges
+within 1e-3 m; dynamics state within 1e-5 relative after N steps.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from racing_dreamer_b200 import _abi
+
+pytestmark = pytest.mark.gpu
+
+LIDAR_TOL_M = 1e-3
+DYN_RTOL = 1e-5
+THREADS = os.cpu_count() or 1
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    torch.cuda.set_device(0)
+    return torch
+
+
+def make_env(torch, **kw):
+    from racing_dreamer_b200 import BatchedRaceEnv, EnvConfig
+    return BatchedRaceEnv(EnvConfig(**kw), device="cuda:0")
+
+
+def make_oracle(env, n_threads=THREADS):
+    from oracle import Oracle
+    return Oracle(env.cfg, env.tracks, env.map_ids, n_threads=n_threads)
+
+
+def random_poses(tm, n, rng, jitter=0.15, any_yaw=True):
+    p = tm.reset_poses[rng.randint(0, len(tm.reset_poses), n)].copy()
+    p[:, :2] += rng.uniform(-jitter, jitter, (n, 2))
+    p[:, 2] = rng.uniform(-np.pi, np.pi, n) if any_yaw else p[:, 2] + rng.uniform(-0.6, 0.6, n)
+    return p
+
+
+# ---------------------------------------------------------------------------------------------- a2 LiDAR
+@pytest.mark.parametrize("track", ["austria", "columbia", "treitlstrasse_v2", "barcelona", "gbr"])
+def test_lidar_vs_oracle(torch_cuda, track):
+    torch = torch_cuda
+    env = make_env(torch, tracks=(track,), n_envs=8)
+    orc = make_oracle(env)
+    tm = env.tracks[0]
+    rng = np.random.RandomState(11)
+    poses = random_poses(tm, 1024, rng)
+    poses[0] = tm.start_poses[0]
+    poses[1] = (1e6, 1e6, 0.3)                 # far outside the map
+    poses[2] = (poses[2, 0], poses[2, 1], 0.0)  # axis-aligned beams
+    poses[3] = (poses[3, 0], poses[3, 1], np.pi / 2)
+    got = env.lidar_cast(torch.from_numpy(poses)).cpu().numpy()
+    want = orc.lidar_cast(poses)
+    assert got.shape == (1024, 1080)
+    assert np.abs(got - want).max() <= LIDAR_TOL_M
+    assert (got != want).mean() < 1e-4          # in practice bit-identical: the march is integer-only
+    assert got.min() >= 0.25 - 1e-6 and got.max() <= 15.0
+    assert np.all(got[1] == np.float32(0.25))   # sensor outside the drivable area: every beam reads range_min
+    env.close()
+
+
+def test_lidar_mixed_maps_ragged_and_empty(torch_cuda):
+    torch = torch_cuda
+    env = make_env(torch, tracks=("barcelona", "austria"), n_envs=4)
+    orc = make_oracle(env)
+    rng = np.random.RandomState(5)
+    pa = random_poses(env.tracks[0], 37, rng)      # ragged: not a multiple of anything
+    pb = random_poses(env.tracks[1], 91, rng)
+    poses = np.concatenate([pa, pb])
+    ids = np.array([0] * 37 + [1] * 91, np.int32)
+    got = env.lidar_cast(torch.from_numpy(poses), ids).cpu().numpy()
+    assert np.abs(got - orc.lidar_cast(poses, ids)).max() <= LIDAR_TOL_M
+    assert env.lidar_cast(torch.zeros((0, 3), dtype=torch.float64)).shape == (0, 1080)   # empty input
+    with pytest.raises(RuntimeError):
+        env.lidar_cast(torch.from_numpy(poses), ids[::-1].copy())                          # ids must be ascending
+    env.close()
+
+
+def test_lidar_properties_full_size(torch_cuda):
+    """Size-independent properties at BASELINE config-2 size (4096 envs x 1080 beams): range bounds; turning the car
+    by exactly one beam step shifts the scan by one index (up to re-quantisation of the ray); idempotence."""
+    torch = torch_cuda
+    env = make_env(torch, tracks=("austria",), n_envs=8)
+    tm = env.tracks[0]
+    rng = np.random.RandomState(2)
+    poses = random_poses(tm, 4096, rng)
+    a = env.lidar_cast(torch.from_numpy(poses)).cpu().numpy()
+    assert a.min() >= np.float32(0.25) and a.max() <= np.float32(15.0)
+    step = float(env.cfg.lidar_fov) / 1079.0
+    shifted = poses.copy()
+    shifted[:, 2] -= step                      # heading turned right by one beam: beam i now looks where beam i+1 did
+    b = env.lidar_cast(torch.from_numpy(shifted)).cpu().numpy()
+    d = np.abs(b[:, :-1] - a[:, 1:])
+    assert np.median(d) < 1e-3 and (d < 0.05).mean() > 0.97
+    assert np.array_equal(a, env.lidar_cast(torch.from_numpy(poses)).cpu().numpy())
+    env.close()
+
+
+def test_lidar_noise_and_normalisation(torch_cuda):
+    torch = torch_cuda
+    env = make_env(torch, tracks=("columbia",), n_envs=8, lidar_noise=0.03, normalize_lidar=True, seed=99)
+    orc = make_oracle(env)
+    poses = random_poses(env.tracks[0], 256, np.random.RandomState(8))
+    got = env.lidar_cast(torch.from_numpy(poses)).cpu().numpy()
+    want = orc.lidar_cast(poses)
+    assert np.abs(got - want).max() <= LIDAR_TOL_M / 15.0
+    assert got.min() >= -0.5 and got.max() <= 0.5       # r/15 - 0.5 [REF dreamer/tools.py:274]
+    env.close()
+
+
+# ---------------------------------------------------------------------------------------------- a1 dynamics
+def test_dynamics_vs_oracle(torch_cuda):
+    torch = torch_cuda
+    env = make_env(torch, tracks=("austria",), n_envs=8)
+    orc = make_oracle(env)
+    rng = np.random.RandomState(4)
+    n = 2048
+    state = np.zeros((7, n))
+    state[0] = rng.uniform(-5, 5, n)
+    state[1] = rng.uniform(-5, 5, n)
+    state[2] = rng.uniform(-0.4, 0.4, n)
+    state[3] = rng.uniform(0.0, 4.5, n)
+    state[4] = rng.uniform(-np.pi, np.pi, n)
+    state[5] = rng.uniform(-1, 1, n)
+    state[6] = rng.uniform(-0.2, 0.2, n)
+    cmd = np.stack([rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)], 1)
+    for ticks in (1, 8, 400):
+        got = env.dynamics(torch.from_numpy(state), torch.from_numpy(cmd), ticks).cpu().numpy()
+        want = orc.dynamics(state, cmd, ticks)
+        scale = np.maximum(np.abs(want), 1.0)
+        assert np.all(np.abs(got - want) <= DYN_RTOL * scale), f"ticks={ticks}: {np.abs(got - want).max()}"
+        assert np.abs(got - want).max() < 1e-9          # in practice ~1e-13: same equations, same op order
+    env.close()
+
+
+# ---------------------------------------------------------------------------------------------- a5 occupancy
+def test_occupancy_vs_golden_and_oracle(torch_cuda, golden_dir):
+    torch = torch_cuda
+    g = np.load(golden_dir / "occupancy_golden.npz")
+    names = [str(n) for n in g["track_names"]]
+    env = make_env(torch, tracks=tuple(names), n_envs=8, obs_type="lidar_occupancy")
+    got = env.occupancy_obs(torch.from_numpy(g["poses"]), g["track"]).cpu().numpy()
+    want = np.unpackbits(g["images"], axis=2)[:, :, :64]
+    assert np.array_equal(got, want), f"{(got != want).sum()} px differ from the reference's OccupancyMapObs"
+    orc = make_oracle(env)
+    rng = np.random.RandomState(21)
+    poses = np.concatenate([random_poses(t, 100, rng) for t in env.tracks])
+    ids = np.repeat(np.arange(3, dtype=np.int32), 100)
+    got = env.occupancy_obs(torch.from_numpy(poses), ids).cpu().numpy()
+    assert np.array_equal(got, orc.occupancy_obs(poses, ids))
+    env.close()
+
+
+# ---------------------------------------------------------------------------------------------- fused step
+def _gpu_step_fn(torch, env):
+    def step(a):
+        obs, rew, done, info = env.step(torch.from_numpy(np.ascontiguousarray(a)).cuda())
+        out = {"lidar": obs["lidar"], "pose": obs["pose"], "velocity": obs["velocity"], "speed": obs["speed"],
+               "reward": rew, "done": done.to(torch.uint8), "progress": info["progress"], "lap": info["lap"],
+               "time": info["time"], "flags": info["flags"]}
+        if "lidar_occupancy" in obs:
+            out["occupancy"] = obs["lidar_occupancy"][..., 0]
+        return {k: v.cpu().numpy() for k, v in out.items()}
+    return step
+
+
+def test_dreamer_stack_golden_replay(torch_cuda, golden_dir):
+    """BASELINE config 1 through the CUDA path == the reference wrapper stack, step for step."""
+    torch = torch_cuda
+    from racing_dreamer_b200 import BatchedRaceEnv
+    g = np.load(golden_dir / "dreamer_stack_golden.npz")
+    cfg = helpers.fused_dreamer_config(_abi.default_config(), int(g["action_repeat"]), int(g["duration"]))
+    env = BatchedRaceEnv(tracks=("columbia",), raw_config=cfg, device="cuda:0")
+    rec = helpers.replay(lambda: env.reset(mode="grid"), _gpu_step_fn(torch, env), g["actions"], g["reset_before"])
+    helpers.assert_matches_dreamer_golden(rec, g, lidar_tol=LIDAR_TOL_M, float_tol=DYN_RTOL)
+    env.close()
+
+
+def test_baselines_stack_golden_replay(torch_cuda, golden_dir):
+    torch = torch_cuda
+    from racing_dreamer_b200 import BatchedRaceEnv
+    g = np.load(golden_dir / "baselines_stack_golden.npz")
+    cfg = helpers.fused_baselines_config(_abi.default_config(), int(g["repeat"]))
+    env = BatchedRaceEnv(tracks=("austria",), raw_config=cfg, device="cuda:0")
+    rec = helpers.replay(lambda: env.reset(mode="grid"), _gpu_step_fn(torch, env), g["actions"], g["reset_before"])
+    helpers.assert_matches_baselines_golden(rec, g, float_tol=DYN_RTOL, lidar_tol=LIDAR_TOL_M)
+    env.close()
+
+
+def _compare_state(env, orc, step_idx):
+    f, i = env.get_state()
+    f, i = f.cpu().numpy(), i.cpu().numpy()
+    assert np.array_equal(i, orc.i32), f"integer state (lap/checkpoint/flags/...) differs at step {step_idx}"
+    scale = np.maximum(np.abs(orc.f64), 1.0)
+    assert np.all(np.abs(f - orc.f64) <= DYN_RTOL * scale), f"float64 state differs at step {step_idx}"
+
+
+@pytest.mark.parametrize("track,n,repeat,mode", [("treitlstrasse_v2", 4096, 8, "random"), ("austria", 1024, 4, "grid")])
+def test_closed_loop_vs_oracle_with_auto_reset(torch_cuda, track, n, repeat, mode):
+    """BASELINE config 4 subsample: random actions so that collisions / time limits fire; auto-reset on; the whole
+    integer state (lap, checkpoint, flags, counters) must stay bit-identical, flags/done bit-exact every step."""
+    torch = torch_cuda
+    env = make_env(torch, tracks=(track,), n_envs=n, action_repeat=repeat, auto_reset=True, reset_mode=mode,
+                   time_limit_steps=40, seed=4, laps=1)
+    orc = make_oracle(env)
+    env.reset()
+    orc.reset(mode=int(env.cfg.reset_mode))
+    _compare_state(env, orc, -1)
+    rng = np.random.RandomState(4)
+    dones = 0
+    for k in range(60):
+        a = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+        a[:, 0] = np.abs(a[:, 0])
+        obs, rew, done, info = env.step(torch.from_numpy(a).cuda())
+        ref = orc.step(a)
+        assert np.array_equal(done.cpu().numpy().astype(np.uint8), ref["done"])
+        assert np.array_equal(info["flags"].cpu().numpy(), ref["flags"])
+        assert np.array_equal(info["lap"].cpu().numpy(), ref["lap"])
+        assert np.allclose(rew.cpu().numpy(), ref["reward"], rtol=DYN_RTOL, atol=1e-6)
+        assert np.abs(obs["lidar"].cpu().numpy() - ref["lidar"]).max() <= LIDAR_TOL_M
+        assert np.allclose(obs["speed"].cpu().numpy(), ref["speed"], rtol=DYN_RTOL, atol=1e-7)
+        _compare_state(env, orc, k)
+        dones += int(ref["done"].sum())
+    assert dones > n // 4, "the scenario is supposed to exercise terminations"
+    gs, os_ = env.read_stats(), orc.stats.as_dict()
+    for key in gs:
+        assert abs(gs[key] - os_[key]) <= 1e-6 * max(1.0, abs(os_[key])), key
+    env.close()
+
+
+def test_mixed_maps_step_and_occupancy(torch_cuda):
+    """BASELINE config 5 layout: Barcelona/Austria alternating by env index; plus the occupancy obs in the step."""
+    torch = torch_cuda
+    n = 96
+    env = make_env(torch, tracks=("barcelona", "austria"), n_envs=n, action_repeat=8, obs_type="lidar_occupancy",
+                   auto_reset=True, reset_mode="random", seed=3)
+    assert np.array_equal(env.map_ids, np.arange(n) % 2)
+    orc = make_oracle(env)
+    o = env.reset()
+    r = orc.reset(mode=int(env.cfg.reset_mode))
+    assert not o["lidar_occupancy"].any()                        # reset obs is zeros [REF dreamer/wrappers.py:410-414]
+    assert np.abs(o["lidar"].cpu().numpy() - r["lidar"]).max() <= LIDAR_TOL_M
+    rng = np.random.RandomState(9)
+    for k in range(12):
+        a = np.stack([rng.uniform(0.2, 1.0, n), rng.uniform(-0.5, 0.5, n)], 1).astype(np.float32)
+        obs, rew, done, info = env.step(torch.from_numpy(a).cuda())
+        ref = orc.step(a)
+        assert np.array_equal(obs["lidar_occupancy"].cpu().numpy()[..., 0], ref["occupancy"])
+        assert np.abs(obs["lidar"].cpu().numpy() - ref["lidar"]).max() <= LIDAR_TOL_M
+        assert np.array_equal(done.cpu().numpy().astype(np.uint8), ref["done"])
+    env.close()
+
+
+def test_manual_reset_mask_frozen_envs_and_state_roundtrip(torch_cuda):
+    torch = torch_cuda
+    n = 64
+    env = make_env(torch, tracks=("columbia",), n_envs=n, action_repeat=4, auto_reset=False, time_limit_steps=5)
+    orc = make_oracle(env)
+    env.reset(mode="random")
+    orc.reset(mode=_abi.RESET_RANDOM)
+    a = np.tile(np.array([[0.5, 0.1]], np.float32), (n, 1))
+    for k in range(7):                                           # TimeLimit fires at step 5, then envs are frozen
+        obs, rew, done, info = env.step(torch.from_numpy(a).cuda())
+        ref = orc.step(a)
+        assert np.array_equal(done.cpu().numpy().astype(np.uint8), ref["done"])
+        assert np.allclose(rew.cpu().numpy(), ref["reward"], rtol=DYN_RTOL, atol=1e-6)
+    assert done.all()
+    mask = np.zeros(n, np.uint8)
+    mask[::3] = 1
+    env.reset(mask=torch.from_numpy(mask).cuda(), mode="grid")
+    orc.reset(mask=mask, mode=_abi.RESET_GRID)
+    _compare_state(env, orc, 100)
+    obs, rew, done, info = env.step(torch.from_numpy(a).cuda())
+    ref = orc.step(a)
+    assert np.array_equal(done.cpu().numpy().astype(np.uint8), ref["done"]) and done.cpu().numpy()[1]
+    f, i = env.get_state()
+    env2 = make_env(torch, tracks=("columbia",), n_envs=n, action_repeat=4, auto_reset=False, time_limit_steps=5)
+    env2.set_state(f, i)                                          # checkpoint / resume
+    o1 = env.step(torch.from_numpy(a).cuda())
+    r1 = o1[1].clone()
+    o2 = env2.step(torch.from_numpy(a).cuda())
+    assert torch.equal(r1, o2[1]) and torch.equal(env.get_state()[0], env2.get_state()[0])
+    env.close()
+    env2.close()
+
+
+def test_step_before_reset_is_an_error(torch_cuda):
+    torch = torch_cuda
+    env = make_env(torch, tracks=("austria",), n_envs=4)
+    with pytest.raises(RuntimeError, match="Must reset environment"):   # [REF dreamer/wrappers.py:148]
+        env.step(torch.zeros((4, 2), device="cuda"))
+    env.close()
+
+
+def test_max_speed_task(torch_cuda):
+    """In-tree task MaximizeSpeed [REF baselines/racing/environment/tasks.py:4-22]: never done, -exp(|steer| - v_x)."""
+    torch = torch_cuda
+    n = 128
+    env = make_env(torch, tracks=("austria",), n_envs=n, action_repeat=1, task="max_speed", auto_reset=False,
+                   rescale_actions=False)
+    orc = make_oracle(env)
+    env.reset()
+    orc.reset()
+    rng = np.random.RandomState(1)
+    for k in range(30):
+        a = np.stack([rng.uniform(0.0, 1.0, n), rng.uniform(-0.3, 0.3, n)], 1).astype(np.float32)
+        obs, rew, done, info = env.step(torch.from_numpy(a).cuda())
+        ref = orc.step(a)
+        assert not done.any()
+        assert np.allclose(rew.cpu().numpy(), ref["reward"], rtol=1e-5, atol=1e-6)
+    v = obs["velocity"].cpu().numpy()[:, 0].astype(np.float64)
+    col = info["wall_collision"].cpu().numpy()
+    want = np.where(col, -1.0, -np.exp(np.abs(a[:, 1].astype(np.float64)) - v))
+    assert np.allclose(rew.cpu().numpy(), want, rtol=1e-4, atol=1e-5)
+    env.close()
