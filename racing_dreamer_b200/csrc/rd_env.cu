@@ -456,8 +456,9 @@ RD_API int rd_step(rd_env* env, const float* actions_dev, const rd_outputs* out,
 
 RD_API int rd_lidar_cast(rd_env* env, const double* poses_dev, const int32_t* map_ids_host, int n, float* ranges_dev,
                          void* stream) {
-  if (!env || !poses_dev || !ranges_dev || n < 0) return fail(env, RD_ERR_INVALID, "bad argument");
-  if (n == 0) return RD_OK;
+  if (!env || n < 0) return fail(env, RD_ERR_INVALID, "bad argument");
+  if (n == 0) return RD_OK;  // empty batch: nothing to do (pointers may be null)
+  if (!poses_dev || !ranges_dev) return fail(env, RD_ERR_INVALID, "null pointer");
   cudaStream_t s = (cudaStream_t)stream;
   int rc = sync_maps(env);
   if (rc) return rc;
@@ -479,8 +480,9 @@ RD_API int rd_lidar_cast(rd_env* env, const double* poses_dev, const int32_t* ma
 
 RD_API int rd_occupancy_obs(rd_env* env, const double* poses_dev, const int32_t* map_ids_host, int n, uint8_t* out_dev,
                             void* stream) {
-  if (!env || !poses_dev || !out_dev || n < 0) return fail(env, RD_ERR_INVALID, "bad argument");
+  if (!env || n < 0) return fail(env, RD_ERR_INVALID, "bad argument");
   if (n == 0) return RD_OK;
+  if (!poses_dev || !out_dev) return fail(env, RD_ERR_INVALID, "null pointer");
   cudaStream_t s = (cudaStream_t)stream;
   int rc = sync_maps(env);
   if (rc) return rc;
@@ -497,8 +499,9 @@ RD_API int rd_occupancy_obs(rd_env* env, const double* poses_dev, const int32_t*
 }
 
 RD_API int rd_dynamics(rd_env* env, double* state_dev, const double* commands_dev, int n, int n_ticks, void* stream) {
-  if (!env || !state_dev || !commands_dev || n < 0 || n_ticks < 0) return fail(env, RD_ERR_INVALID, "bad argument");
+  if (!env || n < 0 || n_ticks < 0) return fail(env, RD_ERR_INVALID, "bad argument");
   if (n == 0) return RD_OK;
+  if (!state_dev || !commands_dev) return fail(env, RD_ERR_INVALID, "null pointer");
   k_dynamics<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(env->cfg, state_dev, commands_dev, n, n_ticks);
   env->launches++;
   CUDA_TRY(env, cudaGetLastError());
