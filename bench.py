@@ -270,12 +270,8 @@ def main():
     e2e_value = world * n * e2e_steps / float(te[0])
 
     # ---- the only collective of the system: episode statistics gathered across ranks at log cadence ----
-    st = torch.tensor([stats[k] for k in sorted(stats)], dtype=torch.float64, device=dev)
-    if world > 1:
-        gathered = [torch.zeros_like(st) for _ in range(world)]
-        dist.all_gather(gathered, st)
-        st = torch.stack(gathered).sum(0)
-    stats_all = dict(zip(sorted(stats), st.tolist()))
+    from racing_dreamer_b200.stats import gather_stats
+    stats_all, _ = gather_stats(stats, device=dev)
 
     if rank == 0:
         value = world * n * args.steps / (gpu_ms_max / 1e3)

@@ -143,6 +143,13 @@ class Oracle:
                           C.byref(self.stats), C.c_int(self.n_threads))
         return self.out
 
+    def read_stats(self, reset: bool = False):
+        """Episode statistics accumulated by step() (same fields as rd_read_stats)."""
+        d = self.stats.as_dict()
+        if reset:
+            self.stats = _abi.RdStats()
+        return d
+
     # -- stage functions --
     def lidar_cast(self, poses: np.ndarray, map_ids: Optional[np.ndarray] = None) -> np.ndarray:
         p = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 3)

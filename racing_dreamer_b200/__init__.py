@@ -14,7 +14,7 @@ def __getattr__(name):
     if name in ("BatchedRaceEnv", "EnvConfig"):
         from . import env as _env
         return getattr(_env, name)
-    if name in ("RaceCarGymCompat", "make_reference_env"):
+    if name in ("RaceCarGymCompat", "ReferenceEnv", "make_reference_env", "load_scenario"):
         from . import compat as _compat
         return getattr(_compat, name)
     raise AttributeError(name)

@@ -1,0 +1,91 @@
+"""The reference-facing dict API (racing_dreamer_b200/compat.py) on the GPU, against the golden trajectory recorded from
+the UNMODIFIED reference wrapper stack (tests/golden/make_golden.py) -- BASELINE config 1 through the drop-in boundary."""
+import numpy as np
+import pytest
+
+import helpers
+from racing_dreamer_b200 import _abi
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    torch.cuda.set_device(0)
+    return torch
+
+
+def test_reference_env_replays_dreamer_golden(torch_cuda, golden_dir):
+    from racing_dreamer_b200.compat import ReferenceEnv
+    g = np.load(golden_dir / "dreamer_stack_golden.npz")
+    env = ReferenceEnv("columbia", "max_progress", action_repeat=int(g["action_repeat"]),
+                       time_limit_steps=int(g["duration"]), reset_mode="grid", device="cuda:0")
+    assert env.agent_ids == ["A"] and env.n_agents == 1
+    assert env.action_space["A"].shape == (2,)
+    assert env.observation_space["A"]["lidar"].shape == (1080,)
+    assert env.observation_space["A"]["lidar_occupancy"].shape == (64, 64, 1)
+    with pytest.raises(AssertionError, match="Must reset environment"):   # [REF dreamer/wrappers.py:148]
+        env.step({"A": np.zeros(2, np.float32)})
+    rec = {k: [] for k in ("lidar", "pose", "velocity", "speed", "reward", "done", "progress", "lap", "time", "flags",
+                           "occupancy")}
+    for t in range(g["actions"].shape[0]):
+        if g["reset_before"][t]:
+            obs = env.reset()
+            assert obs["A"]["speed"] == 0.0 and not obs["A"]["lidar_occupancy"].any()   # [REF wrappers.py:74,410-414]
+            assert obs["A"]["lidar_occupancy"].shape == (64, 64, 1) and obs["A"]["lidar"].dtype == np.float32
+        obs, rew, done, info = env.step({"A": g["actions"][t].reshape(2)})
+        o, i = obs["A"], info["A"]
+        rec["lidar"].append(o["lidar"]); rec["pose"].append(o["pose"]); rec["velocity"].append(o["velocity"])
+        rec["speed"].append(o["speed"]); rec["occupancy"].append(o["lidar_occupancy"][..., 0])
+        rec["reward"].append(np.float32(rew["A"])); rec["done"].append(done["A"])
+        rec["progress"].append(np.float32(i["progress"])); rec["lap"].append(i["lap"]); rec["time"].append(np.float32(i["time"]))
+        rec["flags"].append((_abi.F_WRONG_WAY if i["wrong_way"] else 0) | (_abi.F_COLLISION if i["wall_collision"] else 0))
+    rec = {k: np.stack([np.asarray(x) for x in v]) for k, v in rec.items()}
+    helpers.assert_matches_dreamer_golden(rec, g, lidar_tol=1e-3, float_tol=1e-5)
+    # the scenario shim OccupancyMapObs reads [REF dreamer/wrappers.py:376,396-399]
+    occ = env.scenario.world._maps["occupancy"]
+    pr, pc = occ.to_pixel(info["A"]["pose"])
+    assert occ._map[pr, pc]                       # the car sits on a drivable pixel
+    assert env.scenario.world._config.name
+    assert env.render(mode="birds_eye", agent="A").shape == (200, 200, 3)
+    assert env.launch_count > 0
+    env.close()
+
+
+def test_tick_env_composes_to_fused_step(torch_cuda):
+    """RaceCarGymCompat (one sim tick per step, racecar_gym's interface) driven by a hand-written ActionRepeat loop
+    [REF dreamer/wrappers.py:107-116] == one fused ReferenceEnv step."""
+    from racing_dreamer_b200.compat import RaceCarGymCompat, ReferenceEnv
+    R = 4
+    fused = ReferenceEnv("austria", "max_progress", action_repeat=R, time_limit_steps=10 ** 6, reset_mode="grid",
+                         occupancy=False, device="cuda:0")
+    tick = RaceCarGymCompat("austria", "max_progress", device="cuda:0")
+    assert set(tick.action_space["A"].spaces) == {"motor", "steering"}
+    fused.reset()
+    o = tick.reset(mode="grid")
+    assert o["A"]["lidar"].dtype == np.float64 and o["A"]["pose"].shape == (6,)
+    rng = np.random.RandomState(5)
+    low, high = np.array([0.005, -1.0]), np.array([1.0, 1.0])
+    for step in range(150):
+        a = rng.uniform(-1, 1, 2).astype(np.float32)
+        fo, fr, fd, fi = fused.step({"A": a})
+        cmd = (a + 1) / 2 * (high - low) + low          # ReduceActionSpace._normalize [REF dreamer/wrappers.py:129-130]
+        total, done = 0.0, False
+        for _ in range(R):
+            to, tr, td, ti = tick.step({"A": {"motor": cmd[0], "steering": cmd[1]}})
+            total += tr["A"]
+            done = td["A"]
+            if done:
+                break
+        assert done == fd["A"], step
+        assert abs(total - fr["A"]) <= 1e-5 * max(1.0, abs(total))
+        assert np.abs(to["A"]["lidar"] - fo["A"]["lidar"]).max() <= 1e-3
+        assert ti["A"]["lap"] == fi["A"]["lap"] and ti["A"]["wall_collision"] == fi["A"]["wall_collision"]
+        assert np.allclose(ti["A"]["pose"], fi["A"]["pose"], rtol=1e-5, atol=1e-5)
+        if done:
+            fused.reset()
+            tick.reset(mode="grid")
+    fused.close()
+    tick.close()
