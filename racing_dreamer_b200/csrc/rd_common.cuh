@@ -6,21 +6,22 @@
 #include "../../include/rd_env.h"
 
 #define RD_MAX_MAPS 8
-#define RD_SUB_BITS 12            // ray origin quantum: 2^-12 cell
-#define RD_SUB (1 << RD_SUB_BITS)
-#define RD_DIR_BITS 18            // ray direction quantum: 2^-18
+#include "rd_march.cuh"           // RD_SUB_BITS = 12 (origin quantum 2^-12 cell), RD_DIR_BITS = 18 (direction 2^-18)
+#define RD_COARSE_SHIFT 2         // clearance field block = 4 x 4 cells
 #define RD_OCC_IN 220             // OccupancyMapObs crop [REF dreamer/wrappers.py:398-399]
 #define RD_OCC_MID 200
 #define RD_OCC_OUT 64
 
 // One track on the device.  bits: y-up rows of rw u32 words, bit = drivable.  dist: y-up u16.
 struct DevMap {
-  const uint32_t* bits;
+  const uint32_t* bits;  // followed, at byte offset coarse_off, by the block clearance field (one allocation)
   const uint16_t* dist;
   const double* start;   // [n_start][3]
   const double* reset;   // [n_reset][3]
   int h, w, rw, col0, row0, full_h, dmax, n_start, n_reset;
-  int bits_bytes;        // h*rw*4 rounded up to 16 (bulk-copy granularity)
+  int bits_bytes;        // bytes of bits + clearance field, each rounded up to 16 (bulk-copy granularity)
+  int coarse_off;        // byte offset of the clearance field u8[ch][cw] (rd_march.cuh)
+  int cw, ch, cshift;
   double res, inv_res, ox, oy;
 };
 

@@ -44,31 +44,37 @@ __device__ __forceinline__ void st_rhs(const rd_vehicle& p, const double (&q)[7]
   else if (acc >= pos_limit) ac = pos_limit;
   else ac = acc;
   const double lwb = p.lf + p.lr;
-  if (fabs(v) < p.v_kinematic) {
-    double cs = cos(steer);
-    double tn = tan(steer);
-    f[0] = v * cos(yaw);
-    f[1] = v * sin(yaw);
-    f[2] = svc;
-    f[3] = ac;
-    f[4] = (v / lwb) * tn;
-    f[5] = (ac / lwb) * tn + (v / (lwb * (cs * cs))) * svc;
+  const double rl = 1.0 / lwb;
+  // one sincos serves both regimes (heading of the velocity vector); warps whose lanes sit in different regimes
+  // share it instead of paying for both trig sets
+  const bool kin = fabs(v) < p.v_kinematic;
+  const double ang = kin ? yaw : (slip + yaw);
+  double sn, cn;
+  sincos(ang, &sn, &cn);
+  f[0] = v * cn;
+  f[1] = v * sn;
+  f[2] = svc;
+  f[3] = ac;
+  if (kin) {
+    double ss, cs;
+    sincos(steer, &ss, &cs);
+    const double rc = 1.0 / cs;
+    const double tn = ss * rc;
+    f[4] = (v * rl) * tn;
+    f[5] = (ac * rl) * tn + ((v * rl) * (rc * rc)) * svc;
     f[6] = 0.0;
   } else {
+    const double rv = 1.0 / v;
+    const double c1 = p.mu * p.mass / (p.inertia * lwb);
+    const double c2 = p.mu * rl;
     double rear = g * p.lf + ac * p.h_cg;
     double front = g * p.lr - ac * p.h_cg;
-    double k_yr = (-p.mu * p.mass / (v * p.inertia * lwb)) *
-                  (p.lf * p.lf * p.c_sf * front + p.lr * p.lr * p.c_sr * rear);
-    double k_sl = (p.mu * p.mass / (p.inertia * lwb)) * (p.lr * p.c_sr * rear - p.lf * p.c_sf * front);
-    double k_st = (p.mu * p.mass / (p.inertia * lwb)) * (p.lf * p.c_sf * front);
-    double b_yr = (p.mu / (v * v * lwb)) * (p.c_sr * rear * p.lr - p.c_sf * front * p.lf) - 1.0;
-    double b_sl = (p.mu / (v * lwb)) * (p.c_sr * rear + p.c_sf * front);
-    double b_st = (p.mu / (v * lwb)) * (p.c_sf * front);
-    double ang = slip + yaw;
-    f[0] = v * cos(ang);
-    f[1] = v * sin(ang);
-    f[2] = svc;
-    f[3] = ac;
+    double k_yr = (-c1 * rv) * (p.lf * p.lf * p.c_sf * front + p.lr * p.lr * p.c_sr * rear);
+    double k_sl = c1 * (p.lr * p.c_sr * rear - p.lf * p.c_sf * front);
+    double k_st = c1 * (p.lf * p.c_sf * front);
+    double b_yr = (c2 * (rv * rv)) * (p.c_sr * rear * p.lr - p.c_sf * front * p.lf) - 1.0;
+    double b_sl = (c2 * rv) * (p.c_sr * rear + p.c_sf * front);
+    double b_st = (c2 * rv) * (p.c_sf * front);
     f[4] = yr;
     f[5] = (k_yr * yr + k_sl * slip) + k_st * steer;
     f[6] = (b_yr * yr - b_sl * slip) + b_st * steer;
@@ -111,7 +117,8 @@ __device__ __forceinline__ bool rd_progress_at(const DevMap& m, double x, double
 __device__ __forceinline__ bool rd_collides(const rd_config& cfg, const DevMap& m, double x, double y, double yaw) {
   int cx, cy;
   if (!rd_cell_of(m, x, y, cx, cy) || !rd_drivable_at(m, cx, cy)) return true;
-  double c = cos(yaw), s = sin(yaw);
+  double c, s;
+  sincos(yaw, &s, &c);
   double hl = 0.5 * cfg.vehicle.body_length, hw = 0.5 * cfg.vehicle.body_width;
   double ax = hl * c, ay = hl * s, bx = hw * s, by = hw * c;
   double px[4] = {(x + ax) - bx, (x + ax) + bx, (x - ax) - bx, (x - ax) + bx};

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -48,6 +49,7 @@ struct rd_env {
   double* d_beam_tab = nullptr;
   DevMap* d_maps = nullptr;
   int32_t* d_env_order = nullptr;  // env indices grouped by map
+  unsigned int* d_lidar_ctr = nullptr;  // [2] work counter + finish ticket of k_lidar (self re-arming)
   OccScratch occ{};
   HostMap maps[RD_MAX_MAPS];
   std::vector<int> order_offset;   // RD_MAX_MAPS + 1 offsets into d_env_order
@@ -82,7 +84,10 @@ int fail(rd_env* env, int code, const char* fmt, ...) {
 #define CUDA_TRY(env, expr)                                                                         \
   do {                                                                                              \
     cudaError_t _e = (expr);                                                                        \
-    if (_e != cudaSuccess) return fail(env, RD_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e));  \
+    if (_e != cudaSuccess) {                                                                        \
+      cudaGetLastError(); /* do not leave the error sticky for the caller's own CUDA calls */       \
+      return fail(env, RD_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e));                       \
+    }                                                                                               \
   } while (0)
 
 void default_config(rd_config* c) {
@@ -186,11 +191,12 @@ int launch_lidar_t(rd_env* env, int map_id, const OriginRec* recs, const int32_t
   CUDA_TRY(env, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
   if (per_sm < 1) return fail(env, RD_ERR_INVALID, "map %d (%zu B) does not fit in shared memory", map_id, smem);
   const long long items = (long long)n_env * lp.groups;
+  if (items >= (1ll << 31)) return fail(env, RD_ERR_INVALID, "too many (env, beam group) items for one launch");
   long long grid = std::min<long long>((items + WARPS - 1) / WARPS, (long long)env->sm_count * per_sm);
   if (grid < 1) return RD_OK;
   {
     ScopedTiming tm(env, s, T_LIDAR);
-    kern<<<(unsigned)grid, WARPS * 32, smem, s>>>(env->d_maps, map_id, recs, order, n_env, lp, env->d_beam_tab, out);
+    kern<<<(unsigned)grid, WARPS * 32, smem, s>>>(env->d_maps, map_id, recs, order, n_env, lp, env->d_beam_tab, out, env->d_lidar_ctr);
   }
   env->launches++;
   CUDA_TRY(env, cudaGetLastError());
@@ -322,6 +328,7 @@ RD_API int rd_create(const rd_config* cfg, rd_env** out) {
   alloc((void**)&env->d_beam_tab, sizeof(double) * 2 * (size_t)cfg->n_beams);
   alloc((void**)&env->d_maps, sizeof(DevMap) * RD_MAX_MAPS);
   alloc((void**)&env->d_env_order, sizeof(int32_t) * n);
+  alloc((void**)&env->d_lidar_ctr, sizeof(unsigned int) * 2);
   if (e != cudaSuccess) {
     int rc = fail(nullptr, e == cudaErrorMemoryAllocation ? RD_ERR_NOMEM : RD_ERR_CUDA, "allocation: %s", cudaGetErrorString(e));
     rd_destroy(env);
@@ -343,7 +350,7 @@ RD_API int rd_create(const rd_config* cfg, rd_env** out) {
 RD_API void rd_destroy(rd_env* env) {
   if (!env) return;
   cudaFree(env->d_f64); cudaFree(env->d_i32); cudaFree(env->d_stats); cudaFree(env->d_recs);
-  cudaFree(env->d_beam_tab); cudaFree(env->d_maps); cudaFree(env->d_env_order);
+  cudaFree(env->d_beam_tab); cudaFree(env->d_maps); cudaFree(env->d_env_order); cudaFree(env->d_lidar_ctr);
   cudaFree(env->d_stage_recs); cudaFree(env->d_stage_ids);
   occ_free(env->occ);
   for (auto& t : env->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
@@ -376,9 +383,19 @@ RD_API int rd_upload_map(rd_env* env, int map_id, const uint32_t* bits_host, int
   m = HostMap{};
   const size_t bits_bytes = (size_t)h * row_words * 4;
   const size_t bits_padded = (bits_bytes + 15) & ~(size_t)15;
-  CUDA_TRY(env, cudaMalloc(&m.d_bits, bits_padded));
-  CUDA_TRY(env, cudaMemset(m.d_bits, 0, bits_padded));
-  CUDA_TRY(env, cudaMemcpy(m.d_bits, bits_host, bits_bytes, cudaMemcpyHostToDevice));
+  // block clearance field for the ray march's empty-space skipping (rd_march.cuh), stored right behind the bits so
+  // that one bulk copy brings both into shared memory
+  std::vector<uint8_t> coarse;
+  int ch = 0, cw = 0;
+  int cshift = RD_COARSE_SHIFT;
+  if (const char* ev = std::getenv("RD_LIDAR_CSHIFT")) { int v = std::atoi(ev); if (v >= 0 && v <= 5) cshift = v; }  // tuning knob
+  rd_build_clearance(bits_host, h, w, row_words, cshift, coarse, ch, cw);
+  const size_t coarse_padded = (coarse.size() + 15) & ~(size_t)15;
+  std::vector<unsigned char> packed(bits_padded + coarse_padded, 0);
+  std::memcpy(packed.data(), bits_host, bits_bytes);
+  std::memcpy(packed.data() + bits_padded, coarse.data(), coarse.size());
+  CUDA_TRY(env, cudaMalloc(&m.d_bits, packed.size()));
+  CUDA_TRY(env, cudaMemcpy(m.d_bits, packed.data(), packed.size(), cudaMemcpyHostToDevice));
   CUDA_TRY(env, cudaMalloc(&m.d_dist, sizeof(uint16_t) * (size_t)h * w));
   CUDA_TRY(env, cudaMemcpy(m.d_dist, dist_host, sizeof(uint16_t) * (size_t)h * w, cudaMemcpyHostToDevice));
   CUDA_TRY(env, cudaMalloc(&m.d_start, sizeof(double) * 3 * (size_t)n_start));
@@ -393,7 +410,8 @@ RD_API int rd_upload_map(rd_env* env, int map_id, const uint32_t* bits_host, int
   d.bits = (const uint32_t*)m.d_bits; d.dist = (const uint16_t*)m.d_dist;
   d.start = (const double*)m.d_start; d.reset = (const double*)m.d_reset;
   d.h = h; d.w = w; d.rw = row_words; d.col0 = col0; d.row0 = row0_yup; d.full_h = full_h; d.dmax = dmax;
-  d.n_start = n_start; d.n_reset = n_reset; d.bits_bytes = (int)bits_padded;
+  d.n_start = n_start; d.n_reset = n_reset; d.bits_bytes = (int)packed.size();
+  d.coarse_off = (int)bits_padded; d.cw = cw; d.ch = ch; d.cshift = cshift;
   d.res = resolution; d.inv_res = 1.0 / resolution; d.ox = origin_x; d.oy = origin_y;
   m.present = true;
   env->maps_dirty = true;

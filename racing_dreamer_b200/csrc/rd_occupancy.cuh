@@ -6,23 +6,32 @@
 //     resampling with constant-0 outside, result rounded to uint8;
 //   centre crop 200x200; PIL.Image.resize((64,64)) -- bicubic, two fixed-point passes with a uint8 image between.
 //
-// One CTA per env (persistent loop).  Phases, all inside one kernel:
-//   B  column prefilter: thread = column, float64 recursion straight from the bit grid -> coefficient scratch
-//   C  row prefilter:    thread = row, in place on the scratch (L1/L2-resident, 387 KB per CTA)
-//   D  rotation:         32x32 output tiles; the tile's source bounding box is staged in shared memory,
-//                        each thread evaluates 4 pixels (4x4 B-spline taps, float64), thresholds to {0,1,..}
-//   E  Pillow resize:    integer 22-bit fixed point, horizontal then vertical, uint8 intermediate, in smem
-// float64 is required: interpolated values come within ~3e-5 of the 0.5 rounding threshold, float32 would
-// flip pixels (SURVEY.md §7 hard part 1).
+// One CTA per env (persistent loop), everything in shared memory (no global scratch):
+//   A  crop        220x220 bits of the drivable grid -> smem (funnel-shifted words)
+//   B  prefilter   columns then rows (scipy's order), one thread per line, float32 recursion, into a 223x223 float32
+//                  image whose 1+2 border rows/columns hold the mirrored values, so the 4x4 taps need no index math
+//   C  rotation    one pixel per thread, 32 consecutive pixels per warp (odd pitch => conflict-free taps for axis-aligned
+//                  headings); source coordinates in float64 with scipy's exact operation order (they decide floor() and
+//                  the inside test); value in float32; the rounded pixel is stored as two warp-ballot bit planes
+//   C' exactness   a pixel whose float32 value lies within OCC_EPS of a rounding threshold (k + 0.5) is re-evaluated in
+//                  float64 by the whole CTA from the banded prefilter operator H (coef = H X H^T), which reproduces
+//                  scipy's float64 result to ~1e-15.  float32 error is < 2e-6 (bound in DESIGN.md), OCC_EPS = 2e-5, and
+//                  about one image in 40 has such a pixel, so the output is the reference's, bit for bit.
+//   D  resize      Pillow's 22-bit fixed-point bicubic, horizontal then vertical, uint8 intermediate, in smem
 #pragma once
 #include "rd_common.cuh"
 
-#define OCC_THREADS 256
-#define OCC_TILE 32
-#define OCC_BOX 56          // max side of a tile's source bounding box (32*sqrt(2)+3+margins)
-#define OCC_BOX_PITCH 57    // odd pitch (in doubles) to spread banks
+#define OCC_THREADS 512
+#define OCC_PITCH 223       // 220 + mirrored border (index -1 and 220, 221); odd => rows fall in distinct banks
+#define OCC_XW 7            // 32-bit words per crop row
 #define OCC_KSIZE 15        // Pillow: ceil(2*3.125)*2+1 taps per output pixel
 #define OCC_PREC_BITS 22
+#define OCC_EPS 2.0e-5f
+#define OCC_BAND 40         // |H[r][k]| < 1.3e-23 beyond this distance from the diagonal
+#define OCC_BANDW (2 * OCC_BAND + 1)
+#define OCC_AMB_CAP 2048    // ambiguous pixels per group of OCC_AMB_ROUNDS rounds (cannot overflow: 4 * 512 pixels)
+#define OCC_AMB_ROUNDS 4
+#define OCC_TW 84           // columns of the float64 window of the exact evaluator (4 taps + 2 * band)
 
 struct OccTables {            // Pillow precompute_coeffs + normalize_coeffs_8bpc for 200 -> 64, bicubic
   int32_t kk[RD_OCC_OUT * OCC_KSIZE];
@@ -31,9 +40,9 @@ struct OccTables {            // Pillow precompute_coeffs + normalize_coeffs_8bp
 };
 
 struct OccScratch {
-  double* coef = nullptr;     // [ctas][220*220]
   OccTables* tables = nullptr;
-  int ctas = 0;
+  double* hband = nullptr;    // [220][OCC_BANDW] banded 1-D prefilter operator (float64)
+  float eps = OCC_EPS;        // RD_OCC_EPS overrides it (tests widen it to force pixels through the exact path)
 };
 
 struct OccGeom {              // per-env geometry, computed by one thread
@@ -42,15 +51,26 @@ struct OccGeom {              // per-env geometry, computed by one thread
   int pr, pc;
 };
 
+// smem carve-up (bytes)
+#define OCC_SM_COEF 0
+#define OCC_SM_COEF_BYTES ((OCC_PITCH * OCC_PITCH * 4 + 15) & ~15)     // 198,928
+#define OCC_SM_XBITS (OCC_SM_COEF + OCC_SM_COEF_BYTES)
+#define OCC_SM_XBITS_BYTES (RD_OCC_IN * OCC_XW * 4)                   // 6,160
+#define OCC_SM_PLANES (OCC_SM_XBITS + OCC_SM_XBITS_BYTES)
+#define OCC_SM_PLANES_BYTES (2 * (RD_OCC_MID * RD_OCC_MID / 32) * 4)  // 10,000
+#define OCC_SM_AMB (OCC_SM_PLANES + OCC_SM_PLANES_BYTES)
+#define OCC_SM_AMB_BYTES (OCC_AMB_CAP * 2)                            // 4,096
+#define OCC_SM_T (OCC_SM_AMB + OCC_SM_AMB_BYTES)                      // 16-byte aligned: all sizes above are multiples of 16
+#define OCC_SM_T_BYTES ((4 * OCC_TW + 16) * 8)                        // 2,816
+#define OCC_SM_TOTAL (OCC_SM_T + OCC_SM_T_BYTES)                      // 222,000
+// after the rotation the coefficient image is dead; its space holds the uint8 images and tables of the resize
+#define OCC_SM_MID8 0
+#define OCC_SM_TMP (RD_OCC_MID * RD_OCC_MID)
+#define OCC_SM_TAB (OCC_SM_TMP + RD_OCC_MID * RD_OCC_OUT)
+
 __device__ __forceinline__ int occ_mirror(int idx, int len) {
-  const int s2 = 2 * len - 2;
-  if (idx < 0) {
-    idx = s2 * (int)(-idx / s2) + idx;
-    idx = idx <= 1 - len ? idx + s2 : -idx;
-  } else if (idx >= len) {
-    idx -= s2 * (int)(idx / s2);
-    if (idx >= len) idx = s2 - idx;
-  }
+  if (idx < 0) idx = -idx;
+  if (idx >= len) idx = 2 * len - 2 - idx;
   return idx;
 }
 
@@ -62,47 +82,128 @@ __device__ __forceinline__ void occ_weights(double x, double (&w)[4]) {
   w[3] = 1.0 - w[0] - w[1] - w[2];
 }
 
-// in-place cubic B-spline prefilter of one line held at p[0], p[stride], ... (mirror boundary, pole sqrt(3)-2)
-__device__ __forceinline__ void occ_prefilter_line(double* p, int stride) {
+// float32 cubic B-spline prefilter of one line of 220 values held at p[0], p[stride], ... (mirror boundary,
+// pole sqrt(3)-2, gain 6), in place.  `first` = true: the input is read from the crop bits instead of p.
+template <bool FROM_BITS>
+__device__ __forceinline__ void occ_prefilter_f32(float* p, int stride, const uint32_t* xb, int col) {
   const int n = RD_OCC_IN;
-  const double z = -0.26794919243112270647;  // sqrt(3) - 2
-  const double gain = 6.0;                   // (1-z)(1-1/z)
-  // causal init: sum_{i<=n-2} z^i c_i (+ mirror terms of relative size z^(n-1) ~ 1e-125, below rounding)
-  double zi = 1.0, acc = 0.0;
+  const float z = -0.26794919243112270647f, gain = 6.0f;
+  auto in = [&](int i) -> float {
+    if (FROM_BITS) return (float)((xb[i * OCC_XW + (col >> 5)] >> (col & 31)) & 1u);
+    return p[i * stride];
+  };
+  float zi = 1.0f, acc = 0.0f;
 #pragma unroll 4
-  for (int i = 0; i < 48; ++i) { acc += zi * (gain * p[(size_t)i * stride]); zi *= z; }
-  double prev = acc;
+  for (int i = 0; i < 24; ++i) { acc = fmaf(zi, gain * in(i), acc); zi *= z; }  // z^24 ~ 2e-14
+  float prev = acc;
   p[0] = prev;
+#pragma unroll 4
   for (int i = 1; i < n; ++i) {
-    prev = gain * p[(size_t)i * stride] + z * prev;
-    p[(size_t)i * stride] = prev;
+    prev = fmaf(z, prev, gain * in(i));
+    p[i * stride] = prev;
   }
-  double cur = (z * p[(size_t)(n - 2) * stride] + p[(size_t)(n - 1) * stride]) * z / (z * z - 1.0);
-  p[(size_t)(n - 1) * stride] = cur;
+  float cur = (z * p[(n - 2) * stride] + p[(n - 1) * stride]) * (z / (z * z - 1.0f));
+  p[(n - 1) * stride] = cur;
+#pragma unroll 4
   for (int i = n - 2; i >= 0; --i) {
-    cur = z * (cur - p[(size_t)i * stride]);
-    p[(size_t)i * stride] = cur;
+    cur = z * (cur - p[i * stride]);
+    p[i * stride] = cur;
   }
 }
 
-__global__ void __launch_bounds__(OCC_THREADS)
+// source coordinates of mid pixel (a, b) with scipy's operation order (shift first, then one product per output axis)
+__device__ __forceinline__ void occ_coords(const OccGeom& g, int a, int b, double& c0, double& c1) {
+  const double o0 = (double)(g.o0_first + a), o1 = (double)(g.o1_first + b);
+  c0 = __dadd_rn(__dadd_rn(g.off0, __dmul_rn(o0, g.c)), __dmul_rn(o1, g.s));
+  c1 = __dadd_rn(__dadd_rn(g.off1, __dmul_rn(o0, -g.s)), __dmul_rn(o1, g.c));
+}
+
+// Exact float64 value of one rotated pixel, computed cooperatively by the CTA from coef = H X H^T.
+__device__ __noinline__ void occ_exact_pixel(const OccGeom& g, int pix, const uint32_t* xb, const double* __restrict__ hband,
+                                             double* T, uint32_t* planes) {
+  const int tid = threadIdx.x;
+  const int a = pix / RD_OCC_MID, b = pix - a * RD_OCC_MID;
+  double c0, c1;
+  occ_coords(g, a, b, c0, c1);
+  const int s0 = (int)floor(c0) - 1, s1 = (int)floor(c1) - 1;
+  int rp[4], cq[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { rp[k] = occ_mirror(s0 + k, RD_OCC_IN); cq[k] = occ_mirror(s1 + k, RD_OCC_IN); }
+  const int cmin = min(min(cq[0], cq[1]), min(cq[2], cq[3])), cmax = max(max(cq[0], cq[1]), max(cq[2], cq[3]));
+  const int L0 = max(0, cmin - OCC_BAND), L1 = min(RD_OCC_IN - 1, cmax + OCC_BAND);
+  const int W = L1 - L0 + 1;  // <= 84
+  double* cf = T + 4 * OCC_TW;
+  // A: T[p][l] = sum_k H[rp][k] X[k][l]
+  for (int t = tid; t < 4 * W; t += OCC_THREADS) {
+    const int p = t / W, l = L0 + (t - p * W);
+    const int r = rp[p];
+    const double* h = hband + (size_t)r * OCC_BANDW;
+    double sum = 0.0;
+    const int k0 = max(0, r - OCC_BAND), k1 = min(RD_OCC_IN - 1, r + OCC_BAND);
+    for (int k = k0; k <= k1; ++k)
+      if ((xb[k * OCC_XW + (l >> 5)] >> (l & 31)) & 1u) sum += __ldg(h + (k - r + OCC_BAND));
+    T[p * OCC_TW + (l - L0)] = sum;
+  }
+  __syncthreads();
+  // B: coef[p][q] = sum_l H[cq][l] T[p][l]   (one warp per (p, q))
+  const int warp = tid >> 5, lane = tid & 31;
+  if (warp < 16) {
+    const int p = warp >> 2, q = warp & 3;
+    const int c = cq[q];
+    const double* h = hband + (size_t)c * OCC_BANDW;
+    double sum = 0.0;
+    for (int l = max(L0, c - OCC_BAND) + lane; l <= min(L1, c + OCC_BAND); l += 32)
+      sum += __ldg(h + (l - c + OCC_BAND)) * T[p * OCC_TW + (l - L0)];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    if (lane == 0) cf[warp] = sum;
+  }
+  __syncthreads();
+  // C: 4x4 taps in scipy's accumulation order, rounding, patch the bit planes
+  if (tid == 0) {
+    double w0[4], w1[4];
+    occ_weights(c0, w0);
+    occ_weights(c1, w1);
+    double t = 0.0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        double v = cf[p * 4 + q];
+        v *= w0[p];
+        v *= w1[q];
+        t += v;
+      }
+    double tv = t > 0.0 ? t + 0.5 : 0.0;
+    tv = tv > 255.0 ? 255.0 : tv;
+    const uint32_t val = (uint32_t)(uint8_t)tv;
+    const uint32_t bit = 1u << (pix & 31);
+    uint32_t* w = planes + (pix >> 5);
+    w[0] = (w[0] & ~bit) | ((val & 1u) ? bit : 0u);
+    w[RD_OCC_MID * RD_OCC_MID / 32] = (w[RD_OCC_MID * RD_OCC_MID / 32] & ~bit) | ((val & 2u) ? bit : 0u);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(OCC_THREADS, 1)
 k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict__ recs,
             const double* __restrict__ poses, const double* __restrict__ f64, int n_state,
-            const int32_t* __restrict__ order, int n_env, double* __restrict__ scratch_all,
-            const OccTables* __restrict__ tables, uint8_t* __restrict__ out) {
+            const int32_t* __restrict__ order, int n_env, const double* __restrict__ hband,
+            const OccTables* __restrict__ tables, float eps, uint8_t* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem[];
-  double* box = reinterpret_cast<double*>(smem);                                  // OCC_BOX * OCC_BOX_PITCH doubles
-  uint8_t* mid = smem + sizeof(double) * OCC_BOX * OCC_BOX_PITCH;                  // 200*200
-  uint8_t* tmp = mid + RD_OCC_MID * RD_OCC_MID;                                    // 200 rows * 64
-  OccTables* tb = reinterpret_cast<OccTables*>(tmp + RD_OCC_MID * RD_OCC_OUT);     // 4-byte aligned: sizes above are multiples of 8
+  float* coef = reinterpret_cast<float*>(smem + OCC_SM_COEF);
+  uint32_t* xb = reinterpret_cast<uint32_t*>(smem + OCC_SM_XBITS);
+  uint32_t* planes = reinterpret_cast<uint32_t*>(smem + OCC_SM_PLANES);
+  uint16_t* amb = reinterpret_cast<uint16_t*>(smem + OCC_SM_AMB);
+  double* T = reinterpret_cast<double*>(smem + OCC_SM_T);
+  uint8_t* mid = smem + OCC_SM_MID8;
+  uint8_t* tmp = smem + OCC_SM_TMP;
+  OccTables* tb = reinterpret_cast<OccTables*>(smem + OCC_SM_TAB);
   __shared__ OccGeom geom;
-  __shared__ int box_r0, box_c0, box_h, box_w;
+  __shared__ int amb_count;
 
   const DevMap& m = maps[map_id];
-  double* coef = scratch_all + (size_t)blockIdx.x * RD_OCC_IN * RD_OCC_IN;
-  const int tid = threadIdx.x;
-  for (int i = tid; i < (int)(sizeof(OccTables) / 4); i += OCC_THREADS)
-    reinterpret_cast<int32_t*>(tb)[i] = reinterpret_cast<const int32_t*>(tables)[i];
+  const int tid = threadIdx.x, lane = tid & 31;
 
   for (int slot = blockIdx.x; slot < n_env; slot += gridDim.x) {
     const int env = order ? __ldg(order + slot) : slot;
@@ -144,91 +245,118 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
       geom.off1 = ic - (-s * oc0 + c * oc1);
       geom.o0_first = oh / 2 - RD_OCC_MID / 2;
       geom.o1_first = ow / 2 - RD_OCC_MID / 2;
+      amb_count = 0;
     }
     __syncthreads();
 
-    // ---- B: crop + column prefilter (thread = column) ----
-    if (tid < RD_OCC_IN) {
-      const int cx = geom.pc - RD_OCC_IN / 2 + tid - m.col0;
-      const bool col_ok = cx >= 0 && cx < m.w;
-      for (int i = 0; i < RD_OCC_IN; ++i) {
-        const int r_img = geom.pr - RD_OCC_IN / 2 + i;
-        const int cy = (m.full_h - 1 - r_img) - m.row0;
-        uint32_t bit = 0;
-        if (col_ok && cy >= 0 && cy < m.h) bit = (__ldg(m.bits + (size_t)cy * m.rw + (cx >> 5)) >> (cx & 31)) & 1u;
-        coef[(size_t)i * RD_OCC_IN + tid] = (double)bit;
+    // ---- A: crop bits -> smem.  word (i, j) = crop columns 32j..32j+31 of crop row i ----
+    for (int t = tid; t < RD_OCC_IN * OCC_XW; t += OCC_THREADS) {
+      const int i = t / OCC_XW, j = t - i * OCC_XW;
+      const int r_img = geom.pr - RD_OCC_IN / 2 + i;
+      const int cy = (m.full_h - 1 - r_img) - m.row0;
+      const int cx = geom.pc - RD_OCC_IN / 2 + 32 * j - m.col0;      // map column of bit 0 of this word
+      uint32_t w = 0u;
+      if (cy >= 0 && cy < m.h && cx > -32 && cx < m.rw * 32) {
+        const uint32_t* row = m.bits + (size_t)cy * m.rw;
+        const int wi = cx >> 5, sh = cx & 31;                        // arithmetic shift: floor for negative cx
+        const uint32_t lo = (wi >= 0 && wi < m.rw) ? __ldg(row + wi) : 0u;
+        const uint32_t hi = (wi + 1 >= 0 && wi + 1 < m.rw) ? __ldg(row + wi + 1) : 0u;
+        w = __funnelshift_r(lo, hi, sh);
       }
-      occ_prefilter_line(coef + tid, RD_OCC_IN);
+      if (j == OCC_XW - 1) w &= (1u << (RD_OCC_IN - 32 * (OCC_XW - 1))) - 1u;  // only 28 columns in the last word
+      xb[t] = w;
     }
     __syncthreads();
-    // ---- C: row prefilter (thread = row) ----
-    if (tid < RD_OCC_IN) occ_prefilter_line(coef + (size_t)tid * RD_OCC_IN, 1);
+    // ---- B: prefilter, axis 0 (columns) then axis 1 (rows), float32; image stored at padded index (r+1, c+1) ----
+    if (tid < RD_OCC_IN) occ_prefilter_f32<true>(coef + OCC_PITCH + 1 + tid, OCC_PITCH, xb, tid);
+    __syncthreads();
+    if (tid < RD_OCC_IN) occ_prefilter_f32<false>(coef + (tid + 1) * OCC_PITCH + 1, 1, nullptr, 0);
+    __syncthreads();
+    // mirrored border: columns -1, 220, 221 of rows 0..219, then rows -1, 220, 221 of all 223 columns
+    for (int t = tid; t < RD_OCC_IN * 3; t += OCC_THREADS) {
+      const int r = t / 3, k = t - r * 3;
+      float* row = coef + (r + 1) * OCC_PITCH;
+      if (k == 0) row[0] = row[2];                                   // col -1 <- col 1
+      else if (k == 1) row[RD_OCC_IN + 1] = row[RD_OCC_IN - 1];      // col 220 <- col 218
+      else row[RD_OCC_IN + 2] = row[RD_OCC_IN - 2];                  // col 221 <- col 217
+    }
+    __syncthreads();
+    for (int t = tid; t < OCC_PITCH * 3; t += OCC_THREADS) {
+      const int c = t / 3, k = t - c * 3;
+      if (k == 0) coef[c] = coef[2 * OCC_PITCH + c];                                        // row -1 <- row 1
+      else if (k == 1) coef[(RD_OCC_IN + 1) * OCC_PITCH + c] = coef[(RD_OCC_IN - 1) * OCC_PITCH + c];  // 220 <- 218
+      else coef[(RD_OCC_IN + 2) * OCC_PITCH + c] = coef[(RD_OCC_IN - 2) * OCC_PITCH + c];              // 221 <- 217
+    }
     __syncthreads();
 
-    // ---- D: rotation, tile by tile ----
-    const double c = geom.c, s = geom.s, off0 = geom.off0, off1 = geom.off1;
-    const int ntile = (RD_OCC_MID + OCC_TILE - 1) / OCC_TILE;
-    for (int tile = 0; tile < ntile * ntile; ++tile) {
-      const int ta = (tile / ntile) * OCC_TILE, tb0 = (tile % ntile) * OCC_TILE;
-      const int th = min(OCC_TILE, RD_OCC_MID - ta), tw = min(OCC_TILE, RD_OCC_MID - tb0);
-      if (tid == 0) {
-        double lo0 = 1e30, hi0 = -1e30, lo1 = 1e30, hi1 = -1e30;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const double o0 = (double)(geom.o0_first + ta + ((k & 1) ? th - 1 : 0));
-          const double o1 = (double)(geom.o1_first + tb0 + ((k & 2) ? tw - 1 : 0));
-          const double c0 = off0 + o0 * c + o1 * s, c1 = off1 + o0 * -s + o1 * c;
-          lo0 = fmin(lo0, c0); hi0 = fmax(hi0, c0); lo1 = fmin(lo1, c1); hi1 = fmax(hi1, c1);
-        }
-        int r0 = max((int)floor(lo0) - 3, 0), r1 = min((int)floor(hi0) + 4, RD_OCC_IN - 1);
-        int q0 = max((int)floor(lo1) - 3, 0), q1 = min((int)floor(hi1) + 4, RD_OCC_IN - 1);
-        box_r0 = r0; box_c0 = q0;
-        box_h = max(min(r1 - r0 + 1, OCC_BOX), 0);
-        box_w = max(min(q1 - q0 + 1, OCC_BOX), 0);
-      }
-      __syncthreads();
-      const int bh = box_h, bw = box_w, br0 = box_r0, bc0 = box_c0;
-      for (int i = tid; i < bh * bw; i += OCC_THREADS) {
-        const int r = i / bw, q = i - r * bw;
-        box[r * OCC_BOX_PITCH + q] = coef[(size_t)(br0 + r) * RD_OCC_IN + bc0 + q];
-      }
-      __syncthreads();
-      for (int i = tid; i < th * tw; i += OCC_THREADS) {
-        const int a = i / tw, b = i - a * tw;
-        const double o0 = (double)(geom.o0_first + ta + a), o1 = (double)(geom.o1_first + tb0 + b);
-        // scipy accumulates shift first, then one product per output axis (no contraction)
-        double c0 = __dadd_rn(__dadd_rn(off0, __dmul_rn(o0, c)), __dmul_rn(o1, s));
-        double c1 = __dadd_rn(__dadd_rn(off1, __dmul_rn(o0, -s)), __dmul_rn(o1, c));
-        double t = 0.0;
+    // ---- C: rotation, one pixel per thread and round ----
+    const int n_pix = RD_OCC_MID * RD_OCC_MID;
+    const int n_rounds = (n_pix + OCC_THREADS - 1) / OCC_THREADS;
+    for (int round = 0; round < n_rounds; ++round) {
+      const int pix = round * OCC_THREADS + tid;
+      if (pix - lane < n_pix) {            // whole warps only (n_pix is a multiple of 32)
+        const int a = pix / RD_OCC_MID, b = pix - a * RD_OCC_MID;
+        double c0, c1;
+        occ_coords(geom, a, b, c0, c1);
+        uint32_t val = 0u;
         if (!(c0 < 0.0 || c0 > (double)(RD_OCC_IN - 1) || c1 < 0.0 || c1 > (double)(RD_OCC_IN - 1))) {
-          const int s0 = (int)floor(c0) - 1, s1 = (int)floor(c1) - 1;
-          double w0[4], w1[4];
-          occ_weights(c0, w0);
-          occ_weights(c1, w1);
-          int jj[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) jj[q] = occ_mirror(s1 + q, RD_OCC_IN) - bc0;
+          const double f0 = floor(c0), f1 = floor(c1);
+          const float y0 = (float)(c0 - f0), y1 = (float)(c1 - f1);
+          const float z0 = 1.0f - y0, z1 = 1.0f - y1;
+          float w0[4], w1[4];
+          w0[1] = (y0 * y0 * (y0 - 2.0f) * 3.0f + 4.0f) * (1.0f / 6.0f);
+          w0[2] = (z0 * z0 * (z0 - 2.0f) * 3.0f + 4.0f) * (1.0f / 6.0f);
+          w0[0] = z0 * z0 * z0 * (1.0f / 6.0f);
+          w0[3] = y0 * y0 * y0 * (1.0f / 6.0f);
+          w1[1] = (y1 * y1 * (y1 - 2.0f) * 3.0f + 4.0f) * (1.0f / 6.0f);
+          w1[2] = (z1 * z1 * (z1 - 2.0f) * 3.0f + 4.0f) * (1.0f / 6.0f);
+          w1[0] = z1 * z1 * z1 * (1.0f / 6.0f);
+          w1[3] = y1 * y1 * y1 * (1.0f / 6.0f);
+          // taps rows f0-1..f0+2 -> padded rows f0..f0+3; same for columns
+          const float* base = coef + (int)f0 * OCC_PITCH + (int)f1;
+          float v = 0.0f;
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
-            const int ii = occ_mirror(s0 + p, RD_OCC_IN) - br0;
-            const double* row = box + ii * OCC_BOX_PITCH;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              double cf = row[jj[q]];
-              cf *= w0[p];
-              cf *= w1[q];
-              t += cf;
-            }
+            const float* row = base + p * OCC_PITCH;
+            float r = row[0] * w1[0];
+            r = fmaf(row[1], w1[1], r);
+            r = fmaf(row[2], w1[2], r);
+            r = fmaf(row[3], w1[3], r);
+            v = fmaf(r, w0[p], v);
+          }
+          const float t = v + 0.5f;
+          const float k = floorf(t);
+          const float d = t - k;
+          val = t >= 1.0f ? (uint32_t)fminf(k, 3.0f) : 0u;      // (uint8)(v + 0.5) for v > 0, else 0; provably <= 3
+          if ((d < eps || d > 1.0f - eps) && t > 0.5f) {  // too close to a rounding threshold for float32
+            const int slot_a = atomicAdd(&amb_count, 1);
+            amb[slot_a] = (uint16_t)pix;
           }
         }
-        double tv = t > 0.0 ? t + 0.5 : 0.0;
-        tv = tv > 255.0 ? 255.0 : tv;
-        mid[(ta + a) * RD_OCC_MID + tb0 + b] = (uint8_t)tv;
+        const uint32_t b0 = __ballot_sync(0xffffffffu, val & 1u), b1 = __ballot_sync(0xffffffffu, val & 2u);
+        if (lane == 0) { planes[pix >> 5] = b0; planes[(n_pix >> 5) + (pix >> 5)] = b1; }
       }
-      __syncthreads();
+      if ((round % OCC_AMB_ROUNDS) == OCC_AMB_ROUNDS - 1 || round == n_rounds - 1) {
+        __syncthreads();
+        const int n_amb = amb_count;
+        __syncthreads();                   // everyone has read the count before anyone can add to it again
+        if (n_amb > 0) {
+          for (int e = 0; e < n_amb; ++e) occ_exact_pixel(geom, (int)amb[e], xb, hband, T, planes);
+          if (tid == 0) amb_count = 0;
+          __syncthreads();
+        }
+      }
     }
+    __syncthreads();
 
-    // ---- E: Pillow bicubic 200 -> 64: horizontal pass to uint8, then vertical ----
+    // ---- D: Pillow bicubic 200 -> 64.  The coefficient image is dead: expand the bit planes into it ----
+    for (int i = tid; i < n_pix; i += OCC_THREADS) {
+      const uint32_t lo = (planes[i >> 5] >> (i & 31)) & 1u, hi = (planes[(n_pix >> 5) + (i >> 5)] >> (i & 31)) & 1u;
+      mid[i] = (uint8_t)(lo | (hi << 1));
+    }
+    for (int i = tid; i < (int)(sizeof(OccTables) / 4); i += OCC_THREADS)
+      reinterpret_cast<int32_t*>(tb)[i] = __ldg(reinterpret_cast<const int32_t*>(tables) + i);
+    __syncthreads();
     for (int i = tid; i < RD_OCC_MID * RD_OCC_OUT; i += OCC_THREADS) {
       const int yy = i / RD_OCC_OUT, xx = i - yy * RD_OCC_OUT;
       int32_t ss = 1 << (OCC_PREC_BITS - 1);
@@ -285,9 +413,36 @@ static inline void occ_build_tables(OccTables& t) {
   }
 }
 
+// float64 1-D prefilter (scipy's recursion: gain 6, pole sqrt(3)-2, mirror boundary), host copy used to tabulate H
+static inline void occ_prefilter_host(double* p, int n) {
+  const double z = -0.26794919243112270647, gain = 6.0;
+  double zi = 1.0, acc = 0.0;
+  for (int i = 0; i < 48 && i < n; ++i) { acc += zi * (gain * p[i]); zi *= z; }
+  double prev = acc;
+  p[0] = prev;
+  for (int i = 1; i < n; ++i) { prev = gain * p[i] + z * prev; p[i] = prev; }
+  double cur = (z * p[n - 2] + p[n - 1]) * z / (z * z - 1.0);
+  p[n - 1] = cur;
+  for (int i = n - 2; i >= 0; --i) { cur = z * (cur - p[i]); p[i] = cur; }
+}
+
+// hband[r][k - r + OCC_BAND] = H[r][k], H = the prefilter as a linear operator on length-220 lines (column k of H is
+// the prefilter's response to the unit impulse e_k)
+static inline void occ_build_hband(std::vector<double>& hb) {
+  const int n = RD_OCC_IN;
+  hb.assign((size_t)n * OCC_BANDW, 0.0);
+  std::vector<double> e(n);
+  for (int k = 0; k < n; ++k) {
+    std::fill(e.begin(), e.end(), 0.0);
+    e[k] = 1.0;
+    occ_prefilter_host(e.data(), n);
+    for (int r = std::max(0, k - OCC_BAND); r <= std::min(n - 1, k + OCC_BAND); ++r) hb[(size_t)r * OCC_BANDW + (k - r + OCC_BAND)] = e[r];
+  }
+}
+
 static inline void occ_free(OccScratch& sc) {
-  cudaFree(sc.coef);
   cudaFree(sc.tables);
+  cudaFree(sc.hband);
   sc = OccScratch{};
 }
 
@@ -296,14 +451,9 @@ static inline int occ_launch(OccScratch& sc, const DevMap* d_maps, int map_id, c
                              const double* poses, const double* f64, int n_state, const int32_t* order, int n_env,
                              uint8_t* out, int sm_count, cudaStream_t s, int64_t* launches) {
   (void)hm;
-  const size_t smem = sizeof(double) * OCC_BOX * OCC_BOX_PITCH + RD_OCC_MID * RD_OCC_MID + RD_OCC_MID * RD_OCC_OUT + sizeof(OccTables);
+  const size_t smem = OCC_SM_TOTAL;
   cudaError_t e = cudaFuncSetAttribute(k_occupancy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_occupancy, OCC_THREADS, smem);
-  if (e != cudaSuccess) return (int)e;
-  if (per_sm < 1) per_sm = 1;
-  const int max_ctas = sm_count * per_sm;
   if (!sc.tables) {
     OccTables t;
     occ_build_tables(t);
@@ -312,17 +462,18 @@ static inline int occ_launch(OccScratch& sc, const DevMap* d_maps, int map_id, c
     e = cudaMemcpy(sc.tables, &t, sizeof(OccTables), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return (int)e;
   }
-  if (sc.ctas < max_ctas) {
-    cudaFree(sc.coef);
-    sc.coef = nullptr;
-    sc.ctas = 0;
-    e = cudaMalloc(&sc.coef, sizeof(double) * RD_OCC_IN * RD_OCC_IN * (size_t)max_ctas);
+  if (!sc.hband) {
+    if (const char* ev = std::getenv("RD_OCC_EPS")) { const float v = (float)std::atof(ev); if (v >= OCC_EPS && v <= 0.49f) sc.eps = v; }
+    std::vector<double> hb;
+    occ_build_hband(hb);
+    e = cudaMalloc(&sc.hband, sizeof(double) * hb.size());
     if (e != cudaSuccess) return (int)e;
-    sc.ctas = max_ctas;
+    e = cudaMemcpy(sc.hband, hb.data(), sizeof(double) * hb.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return (int)e;
   }
-  const int grid = n_env < max_ctas ? n_env : max_ctas;
+  const int grid = n_env < sm_count ? n_env : sm_count;  // one CTA per SM (221 KB of shared memory each)
   if (grid < 1) return 0;
-  k_occupancy<<<grid, OCC_THREADS, smem, s>>>(d_maps, map_id, recs, poses, f64, n_state, order, n_env, sc.coef, sc.tables, out);
+  k_occupancy<<<grid, OCC_THREADS, smem, s>>>(d_maps, map_id, recs, poses, f64, n_state, order, n_env, sc.hband, sc.tables, sc.eps, out);
   (*launches)++;
   return (int)cudaGetLastError();
 }

@@ -98,8 +98,12 @@ class BatchedRaceEnv:
     """
 
     def __init__(self, config: Optional[EnvConfig] = None, device: Union[str, torch.device, None] = None,
-                 raw_config: Optional[_abi.RdConfig] = None, **kwargs):
+                 raw_config: Optional[_abi.RdConfig] = None, out_buffers: Optional[Dict[str, torch.Tensor]] = None,
+                 **kwargs):
+        """out_buffers: optional caller-owned result tensors (keys of OUT_SPEC) the kernels write into -- e.g. slices
+        of one larger allocation (HostSteppedEnv); anything not given is allocated here."""
         self.lib = _abi.load_library()
+        self._out_buffers = out_buffers
         if not torch.cuda.is_available():
             raise _abi.NativeLibraryError("BatchedRaceEnv needs a CUDA device: the env step has no CPU fallback")
         ec = config if config is not None else EnvConfig(**kwargs)
@@ -138,22 +142,28 @@ class BatchedRaceEnv:
             self._alloc()
 
     # ------------------------------------------------------------------ buffers
+    OUT_SPEC = (  # key, per-env shape, dtype  [REF dreamer/wrappers.py:62-69,210-226: obs + what Collect records]
+        ("lidar", None, torch.float32), ("occupancy", (64, 64, 1), torch.uint8), ("pose", (6,), torch.float32),
+        ("velocity", (6,), torch.float32), ("speed", (), torch.float32), ("reward", (), torch.float32),
+        ("done", (), torch.uint8), ("progress", (), torch.float32), ("lap", (), torch.int32), ("time", (), torch.float32),
+        ("flags", (), torch.uint8))
+
     def _alloc(self):
         n, dev = self.n, self.device
         occ = bool(self.cfg.obs_flags & _abi.OBS_OCCUPANCY)
-        self.buf: Dict[str, Optional[torch.Tensor]] = dict(
-            lidar=torch.zeros((n, self.n_beams), dtype=torch.float32, device=dev),
-            occupancy=torch.zeros((n, 64, 64, 1), dtype=torch.uint8, device=dev) if occ else None,
-            pose=torch.zeros((n, 6), dtype=torch.float32, device=dev),
-            velocity=torch.zeros((n, 6), dtype=torch.float32, device=dev),
-            speed=torch.zeros((n,), dtype=torch.float32, device=dev),
-            reward=torch.zeros((n,), dtype=torch.float32, device=dev),
-            done=torch.zeros((n,), dtype=torch.uint8, device=dev),
-            progress=torch.zeros((n,), dtype=torch.float32, device=dev),
-            lap=torch.zeros((n,), dtype=torch.int32, device=dev),
-            time=torch.zeros((n,), dtype=torch.float32, device=dev),
-            flags=torch.zeros((n,), dtype=torch.uint8, device=dev),
-        )
+        given = self._out_buffers or {}
+        self.buf: Dict[str, Optional[torch.Tensor]] = {}
+        for key, shape, dtype in self.OUT_SPEC:
+            if key == "occupancy" and not occ:
+                self.buf[key] = None
+                continue
+            full = (n,) + ((self.n_beams,) if key == "lidar" else tuple(shape))
+            t = given.get(key)
+            if t is None:
+                t = torch.zeros(full, dtype=dtype, device=dev)
+            elif tuple(t.shape) != full or t.dtype != dtype or t.device != dev or not t.is_contiguous():
+                raise ValueError(f"out_buffers[{key!r}] must be a contiguous {dtype} tensor of shape {full} on {dev}")
+            self.buf[key] = t
         o = _abi.RdOutputs()
         for k, f in (("lidar", "lidar_dev"), ("occupancy", "occupancy_dev"), ("pose", "pose_dev"),
                      ("velocity", "velocity_dev"), ("speed", "speed_dev"), ("reward", "reward_dev"),

@@ -89,3 +89,38 @@ def test_tick_env_composes_to_fused_step(torch_cuda):
             tick.reset(mode="grid")
     fused.close()
     tick.close()
+
+
+@pytest.mark.parametrize("obs_type,n_shards", [("lidar", 4), ("lidar_occupancy", 3)])
+def test_host_stepped_env_equals_batched(torch_cuda, obs_type, n_shards):
+    """HostSteppedEnv (numpy in / numpy out, sharded streams, slab copies -- the `e2e` call of bench.py) returns exactly
+    what one BatchedRaceEnv over the same global env ids returns."""
+    torch = torch_cuda
+    from racing_dreamer_b200 import BatchedRaceEnv, EnvConfig
+    from racing_dreamer_b200.host import HostSteppedEnv
+    n = 203                                            # ragged shards
+    ec = EnvConfig(tracks=("austria", "treitlstrasse_v2"), n_envs=n, action_repeat=4, obs_type=obs_type, auto_reset=True,
+                   reset_mode="random", seed=11, time_limit_steps=7)
+    ref = BatchedRaceEnv(ec, device="cuda:0")
+    host = HostSteppedEnv(ec, device="cuda:0", n_shards=n_shards)
+    ro = ref.reset()
+    ho = host.reset()
+    assert np.array_equal(ho["lidar"], ro["lidar"].cpu().numpy())
+    rng = np.random.RandomState(2)
+    for step in range(12):
+        a = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+        obs, rew, done, info = ref.step(torch.from_numpy(a).cuda())
+        out = host.step(a)
+        assert np.array_equal(out["lidar"], obs["lidar"].cpu().numpy()), step
+        assert np.array_equal(out["reward"], rew.cpu().numpy())
+        assert np.array_equal(out["done"].astype(bool), done.cpu().numpy())
+        assert np.array_equal(out["pose"], obs["pose"].cpu().numpy())
+        assert np.array_equal(out["lap"], info["lap"].cpu().numpy())
+        assert np.array_equal(out["flags"], info["flags"].cpu().numpy())
+        if obs_type == "lidar_occupancy":
+            assert np.array_equal(out["occupancy"], obs["lidar_occupancy"].cpu().numpy())
+    assert host.d2h_bytes_per_step >= n * 1080 * 4
+    s_ref, s_host = ref.read_stats(), host.read_stats()
+    assert s_ref["episodes"] == s_host["episodes"] and s_ref["env_steps"] == s_host["env_steps"] == n * 12
+    ref.close()
+    host.close()

@@ -159,6 +159,39 @@ def test_occupancy_vs_golden_and_oracle(torch_cuda, golden_dir):
     env.close()
 
 
+def test_occupancy_exact_path_forced(torch_cuda, golden_dir, monkeypatch):
+    """k_occupancy evaluates pixels in float32 and re-evaluates, in float64, the ones that land within eps of a rounding
+    threshold.  Widening eps to 0.05 (RD_OCC_EPS) pushes every edge pixel through that float64 path: the images must
+    still be the reference's, bit for bit -- this pins the exact evaluator, which the default eps exercises only about
+    once in 40 images."""
+    torch = torch_cuda
+    monkeypatch.setenv("RD_OCC_EPS", "0.05")
+    g = np.load(golden_dir / "occupancy_golden.npz")
+    names = [str(n) for n in g["track_names"]]
+    env = make_env(torch, tracks=tuple(names), n_envs=8, obs_type="lidar_occupancy")
+    got = env.occupancy_obs(torch.from_numpy(g["poses"]), g["track"]).cpu().numpy()
+    want = np.unpackbits(g["images"], axis=2)[:, :, :64]
+    assert np.array_equal(got, want), f"{(got != want).sum()} px differ from the reference's OccupancyMapObs"
+    env.close()
+
+
+def test_occupancy_many_poses_vs_oracle(torch_cuda):
+    """4096 random poses per track (incl. map-edge crops and the four axis-aligned headings) against the float64 oracle."""
+    torch = torch_cuda
+    env = make_env(torch, tracks=("austria", "treitlstrasse_v2"), n_envs=8, obs_type="lidar_occupancy")
+    orc = make_oracle(env)
+    rng = np.random.RandomState(33)
+    poses = np.concatenate([random_poses(t, 2048, rng, jitter=0.3) for t in env.tracks])
+    poses[:4, 2] = (0.0, np.pi / 2, np.pi, -np.pi / 2)
+    poses[4] = (1e4, 1e4, 0.1)                       # crop entirely outside the map -> all zeros
+    ids = np.repeat(np.arange(2, dtype=np.int32), 2048)
+    got = env.occupancy_obs(torch.from_numpy(poses), ids).cpu().numpy()
+    want = orc.occupancy_obs(poses, ids)
+    assert np.array_equal(got, want), f"{(got != want).any(axis=(1, 2)).sum()} of {len(poses)} images differ"
+    assert not got[4].any()
+    env.close()
+
+
 # ---------------------------------------------------------------------------------------------- fused step
 def _gpu_step_fn(torch, env):
     def step(a):
