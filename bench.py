@@ -32,21 +32,38 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-TRACK = "austria"
+TRACKS = ("austria",)
 N_ENVS = 4096
 N_BEAMS = 1080
 ACTION_REPEAT = 8
 PERIOD = 50
+ACTIONS = "scripted"   # or "random"
+SEED = 1
+# BASELINE.json configs[1..4] (SURVEY.md §8-d).  The driver's bench line is config 2; the others are measured with
+# `--config N` for DESIGN.md / profiles and exercised by the parity tests.
+CONFIGS = {
+    2: dict(tracks=("austria",), envs=4096, obs="lidar", actions="scripted", seed=1),
+    3: dict(tracks=("columbia",), envs=16384, obs="lidar_occupancy", actions="scripted", seed=3),
+    4: dict(tracks=("treitlstrasse_v2",), envs=65536, obs="lidar", actions="random", seed=4),
+    5: dict(tracks=("barcelona", "austria"), envs=131072, obs="lidar", actions="scripted", seed=5),
+}
 # SURVEY.md §8-d: state r/w 224 + action 8 + lidar 4320 + scalars 24 + pose/velocity 48
 ALGO_BYTES_PER_ENV_STEP = 4624
 # k_lidar alone: 1080 f32 ranges written + one 48-byte origin record read per env
 LIDAR_BYTES_PER_ENV = N_BEAMS * 4 + 48
-WORKLOAD = f"config2: {TRACK} {N_BEAMS}-beam lidar, {N_ENVS} envs/GPU, action_repeat={ACTION_REPEAT}, obs=lidar f32"
+
+
+def workload(n, obs, cfg_id):
+    return (f"config{cfg_id}: {'+'.join(TRACKS)} {N_BEAMS}-beam lidar, {n} envs/GPU, action_repeat={ACTION_REPEAT}, "
+            f"obs={obs}, {ACTIONS} actions")
 
 
 def scripted_actions(n, rank=0):
-    """[PERIOD, n, 2] float32: motor +0.6, steering 0.8*sin(2*pi*k/50 + phi_i), phi_i from a seeded stream."""
+    """[PERIOD, n, 2] float32: motor +0.6, steering 0.8*sin(2*pi*k/50 + phi_i), phi_i from a seeded stream
+    (config 4: uniform random U(-1,1)^2 instead, so that collisions / laps / time limits fire)."""
     rng = np.random.Generator(np.random.Philox(key=2 + 1000 * rank))
+    if ACTIONS == "random":
+        return rng.uniform(-1.0, 1.0, (PERIOD, n, 2)).astype(np.float32)
     phi = rng.uniform(0.0, 2.0 * np.pi, n)
     k = np.arange(PERIOD)[:, None]
     a = np.empty((PERIOD, n, 2), np.float32)
@@ -57,8 +74,8 @@ def scripted_actions(n, rank=0):
 
 def env_config(n_envs, rank=0, obs_type="lidar"):
     from racing_dreamer_b200 import EnvConfig
-    return EnvConfig(tracks=(TRACK,), n_envs=n_envs, action_repeat=ACTION_REPEAT, obs_type=obs_type, auto_reset=True,
-                     reset_mode="random", seed=1, env_id_offset=rank * n_envs, time_limit_steps=2000 // ACTION_REPEAT)
+    return EnvConfig(tracks=TRACKS, n_envs=n_envs, action_repeat=ACTION_REPEAT, obs_type=obs_type, auto_reset=True,
+                     reset_mode="random", seed=SEED, env_id_offset=rank * n_envs, time_limit_steps=2000 // ACTION_REPEAT)
 
 
 class ClockSampler:
@@ -118,15 +135,16 @@ def measured_peak_gbs():
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
-def cpu_oracle_run(n_envs, steps, warmup, threads, rank=0):
+def cpu_oracle_run(n_envs, steps, warmup, threads, rank=0, obs="lidar"):
     """Times the oracle port on `threads` host threads: `steps` env.step() calls of `n_envs` envs."""
     from oracle import Oracle
     from racing_dreamer_b200 import _abi, load_track
     from racing_dreamer_b200.env import _fill_config
     from oracle import default_config
     cfg = default_config()
-    _fill_config(cfg, env_config(n_envs, rank))
-    orc = Oracle(cfg, [load_track(TRACK)], n_threads=threads)
+    _fill_config(cfg, env_config(n_envs, rank, obs))
+    ids = (np.arange(n_envs) % len(TRACKS)).astype(np.int32)
+    orc = Oracle(cfg, [load_track(t) for t in TRACKS], ids, n_threads=threads)
     orc.reset(mode=_abi.RESET_RANDOM)
     acts = scripted_actions(n_envs, rank)
     for k in range(warmup):
@@ -147,16 +165,16 @@ def reference_arm(args):
         return 0
     threads = os.cpu_count() or 1
     # size each step (env sample) so that steps+warmup finish in about two minutes
-    rate, _ = cpu_oracle_run(256, 2, 1, threads)
+    rate, _ = cpu_oracle_run(256, 2, 1, threads, obs=args.obs)
     total_steps = max(1, args.steps + args.warmup)
     n_sample = int(min(N_ENVS, max(threads, rate * 110.0 / total_steps)))
-    value, dt = cpu_oracle_run(n_sample, args.steps, args.warmup, threads)
+    value, dt = cpu_oracle_run(n_sample, args.steps, args.warmup, threads, obs=args.obs)
     line = {
         "metric": "env_steps_per_s", "value": value, "unit": "env-steps/s", "impl": "reference", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "beams_per_s": value * N_BEAMS,
-        "config": {"workload": WORKLOAD, "sample": f"{n_sample} of {N_ENVS} envs per step"},
+        "config": {"workload": workload(N_ENVS, args.obs, args.config), "sample": f"{n_sample} of {N_ENVS} envs per step"},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port",
                          "sample": f"{n_sample} envs x {args.steps} steps, oracle/rd_oracle.c, {threads} OpenMP threads"},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -173,12 +191,20 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs", type=int, default=N_ENVS, help="envs per GPU (bench default = BASELINE config 2)")
-    ap.add_argument("--obs", default="lidar", choices=["lidar", "lidar_occupancy"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config (default 2)")
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (0 = the config's)")
+    ap.add_argument("--obs", default="", choices=["", "lidar", "lidar_occupancy"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 200)")
+    ap.add_argument("--e2e-shards", type=int, default=8, help="stream shards of the host-facing env")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    global TRACKS, N_ENVS, ACTIONS, SEED
+    c = CONFIGS[args.config]
+    TRACKS, ACTIONS, SEED = c["tracks"], c["actions"], c["seed"]
+    N_ENVS = args.envs or c["envs"]
+    args.envs = N_ENVS
+    args.obs = args.obs or c["obs"]
     if args.impl == "reference":
         return reference_arm(args)
 
@@ -252,7 +278,7 @@ def main():
 
     # ---- e2e: host numpy actions -> pinned -> H2D -> step -> D2H of all results -> numpy ----
     e2e_steps = args.e2e_steps or min(args.steps, 200)
-    henv = HostSteppedEnv(env_config(n, rank, args.obs), device=dev, n_shards=4)
+    henv = HostSteppedEnv(env_config(n, rank, args.obs), device=dev, n_shards=args.e2e_shards)
     hacts = scripted_actions(n, rank)
     henv.reset()
     for k in range(5):
@@ -264,6 +290,17 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     assert out["lidar"].shape == (n, N_BEAMS) and np.isfinite(out["reward"]).all()
+    # pinned device->host copy rate of this box: the floor of any host-facing step is d2h_bytes / this
+    probe_d = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+    probe_h = torch.empty(64 << 20, dtype=torch.uint8, pin_memory=True)
+    probe_h.copy_(probe_d, non_blocking=True)
+    torch.cuda.synchronize()
+    tp = time.perf_counter()
+    for _ in range(5):
+        probe_h.copy_(probe_d, non_blocking=True)
+    torch.cuda.synchronize()
+    d2h_gbs = 5 * (64 << 20) / (time.perf_counter() - tp) / 1e9
+    del probe_d, probe_h
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -284,9 +321,7 @@ def main():
             "vs_baseline": None, "dtype": "f64 dynamics / i32 ray march / f32 ranges", "data": "synthetic",
             "beams_per_s": value * N_BEAMS,
             "sim_ticks_per_s": value * ACTION_REPEAT,
-            "config": {"workload": WORKLOAD if (n == N_ENVS and args.obs == "lidar") else
-                       f"{TRACK} {N_BEAMS}-beam, {n} envs/GPU, action_repeat={ACTION_REPEAT}, obs={args.obs}",
-                       "envs_per_gpu": n, "l2": "flushed between steps (256 MiB memset outside the per-step events)",
+            "config": {"workload": workload(n, args.obs, args.config), "envs_per_gpu": n, "l2": "flushed between steps (256 MiB memset outside the per-step events)",
                        "parallelism": f"env-sharded x{world}, no collective in step"},
             "ms_per_step_back_to_back": b2b_ms_max / args.steps,
             "wall_s_timed_region": wall,
@@ -299,17 +334,19 @@ def main():
             "kernel_ms": {"k_step": timing["step_ms"] / max(1, timing["step_launches"]), "k_lidar": lidar_ms,
                           "k_occupancy": timing["occupancy_ms"] / max(1, timing["occupancy_launches"])},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": henv.h2d_bytes_per_step,
-                    "d2h_bytes_per_step": henv.d2h_bytes_per_step, "steps": e2e_steps, "shards": len(henv.shards)},
+                    "d2h_bytes_per_step": henv.d2h_bytes_per_step, "steps": e2e_steps, "shards": len(henv.shards),
+                    "ms_per_step": float(te[0]) / e2e_steps * 1e3, "pinned_d2h_gbs": d2h_gbs,
+                    "d2h_floor_ms": henv.d2h_bytes_per_step / d2h_gbs / 1e6},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "episode_stats": stats_all,
         }
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
-            rate, _ = cpu_oracle_run(256, 2, 1, threads)
+            rate, _ = cpu_oracle_run(256, 2, 1, threads, obs=args.obs)
             n_s = int(min(N_ENVS, max(threads, rate * 1.0)))     # ~1 s per step
             steps_s = 12
-            v, dt = cpu_oracle_run(n_s, steps_s, 2, threads)
+            v, dt = cpu_oracle_run(n_s, steps_s, 2, threads, obs=args.obs)
             line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
                                     "sample": f"{n_s} envs x {steps_s} steps of the same workload, oracle/rd_oracle.c, "
                                               f"{threads} OpenMP threads, {dt:.1f} s"}

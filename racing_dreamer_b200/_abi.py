@@ -101,7 +101,7 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = Path(os.environ.get("RD_ENV_LIB", LIB_PATH))
+    path = Path(os.environ.get("RD_ENV_LIB") or LIB_PATH)   # RD_ENV_LIB: a prebuilt variant (tuning sweeps)
     if not path.exists():
         raise NativeLibraryError(
             f"{path} is missing: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'). "

@@ -21,7 +21,9 @@
 #pragma once
 #include "rd_common.cuh"
 
+#ifndef OCC_THREADS
 #define OCC_THREADS 512
+#endif
 #define OCC_PITCH 223       // 220 + mirrored border (index -1 and 220, 221); odd => rows fall in distinct banks
 #define OCC_XW 7            // 32-bit words per crop row
 #define OCC_KSIZE 15        // Pillow: ceil(2*3.125)*2+1 taps per output pixel
@@ -30,13 +32,17 @@
 #define OCC_BAND 40         // |H[r][k]| < 1.3e-23 beyond this distance from the diagonal
 #define OCC_BANDW (2 * OCC_BAND + 1)
 #define OCC_AMB_CAP 2048    // ambiguous pixels per group of OCC_AMB_ROUNDS rounds (cannot overflow: 4 * 512 pixels)
-#define OCC_AMB_ROUNDS 4
+#define OCC_AMB_ROUNDS (OCC_AMB_CAP / OCC_THREADS)
 #define OCC_TW 84           // columns of the float64 window of the exact evaluator (4 taps + 2 * band)
 
 struct OccTables {            // Pillow precompute_coeffs + normalize_coeffs_8bpc for 200 -> 64, bicubic
   int32_t kk[RD_OCC_OUT * OCC_KSIZE];
   int32_t xmin[RD_OCC_OUT];
   int32_t xnum[RD_OCC_OUT];
+  // horizontal pass on BINARY rows: lut[g][m][xx] = sum of kk[xx][5g + j] over the set bits j of the 5-bit mask m, so the
+  // 15-tap sum of one output pixel is three table reads on the window's bit mask (exact integer arithmetic); xx is the
+  // fastest index so that a warp (32 consecutive xx) reads 32 consecutive words when its lanes see the same mask
+  int32_t lut[3 * 32 * RD_OCC_OUT];
 };
 
 struct OccScratch {
@@ -62,10 +68,11 @@ struct OccGeom {              // per-env geometry, computed by one thread
 #define OCC_SM_AMB_BYTES (OCC_AMB_CAP * 2)                            // 4,096
 #define OCC_SM_T (OCC_SM_AMB + OCC_SM_AMB_BYTES)                      // 16-byte aligned: all sizes above are multiples of 16
 #define OCC_SM_T_BYTES ((4 * OCC_TW + 16) * 8)                        // 2,816
-#define OCC_SM_TOTAL (OCC_SM_T + OCC_SM_T_BYTES)                      // 222,000
+#define OCC_SM_RC (OCC_SM_T + OCC_SM_T_BYTES)                         // per-row / per-column coordinate terms (float64)
+#define OCC_SM_RC_BYTES (4 * RD_OCC_MID * 8)                          // 6,400
+#define OCC_SM_TOTAL (OCC_SM_RC + OCC_SM_RC_BYTES)                    // 228,400
 // after the rotation the coefficient image is dead; its space holds the uint8 images and tables of the resize
-#define OCC_SM_MID8 0
-#define OCC_SM_TMP (RD_OCC_MID * RD_OCC_MID)
+#define OCC_SM_TMP 0
 #define OCC_SM_TAB (OCC_SM_TMP + RD_OCC_MID * RD_OCC_OUT)
 
 __device__ __forceinline__ int occ_mirror(int idx, int len) {
@@ -111,20 +118,29 @@ __device__ __forceinline__ void occ_prefilter_f32(float* p, int stride, const ui
   }
 }
 
-// source coordinates of mid pixel (a, b) with scipy's operation order (shift first, then one product per output axis)
-__device__ __forceinline__ void occ_coords(const OccGeom& g, int a, int b, double& c0, double& c1) {
-  const double o0 = (double)(g.o0_first + a), o1 = (double)(g.o1_first + b);
-  c0 = __dadd_rn(__dadd_rn(g.off0, __dmul_rn(o0, g.c)), __dmul_rn(o1, g.s));
-  c1 = __dadd_rn(__dadd_rn(g.off1, __dmul_rn(o0, -g.s)), __dmul_rn(o1, g.c));
+// Source coordinates of mid pixel (a, b) with scipy's operation order (shift first, then one product per output axis):
+//   c0 = (off0 + o0*c) + o1*s ,  c1 = (off1 + o0*(-s)) + o1*c .
+// The per-row terms (off + o0*..) and per-column terms (o1*..) are tabulated once per env: rc[0..199] row term of c0,
+// rc[200..399] row term of c1, rc[400..599] column term of c0, rc[600..799] column term of c1 -- same operations, same bits.
+__device__ __forceinline__ void occ_coord_tables(const OccGeom& g, double* rc, int i) {
+  const double o0 = (double)(g.o0_first + i), o1 = (double)(g.o1_first + i);
+  rc[i] = __dadd_rn(g.off0, __dmul_rn(o0, g.c));
+  rc[RD_OCC_MID + i] = __dadd_rn(g.off1, __dmul_rn(o0, -g.s));
+  rc[2 * RD_OCC_MID + i] = __dmul_rn(o1, g.s);
+  rc[3 * RD_OCC_MID + i] = __dmul_rn(o1, g.c);
+}
+__device__ __forceinline__ void occ_coords(const double* rc, int a, int b, double& c0, double& c1) {
+  c0 = __dadd_rn(rc[a], rc[2 * RD_OCC_MID + b]);
+  c1 = __dadd_rn(rc[RD_OCC_MID + a], rc[3 * RD_OCC_MID + b]);
 }
 
 // Exact float64 value of one rotated pixel, computed cooperatively by the CTA from coef = H X H^T.
-__device__ __noinline__ void occ_exact_pixel(const OccGeom& g, int pix, const uint32_t* xb, const double* __restrict__ hband,
+__device__ __noinline__ void occ_exact_pixel(const double* rc, int pix, const uint32_t* xb, const double* __restrict__ hband,
                                              double* T, uint32_t* planes) {
   const int tid = threadIdx.x;
   const int a = pix / RD_OCC_MID, b = pix - a * RD_OCC_MID;
   double c0, c1;
-  occ_coords(g, a, b, c0, c1);
+  occ_coords(rc, a, b, c0, c1);
   const int s0 = (int)floor(c0) - 1, s1 = (int)floor(c1) - 1;
   int rp[4], cq[4];
 #pragma unroll
@@ -196,11 +212,11 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
   uint32_t* planes = reinterpret_cast<uint32_t*>(smem + OCC_SM_PLANES);
   uint16_t* amb = reinterpret_cast<uint16_t*>(smem + OCC_SM_AMB);
   double* T = reinterpret_cast<double*>(smem + OCC_SM_T);
-  uint8_t* mid = smem + OCC_SM_MID8;
+  double* rc = reinterpret_cast<double*>(smem + OCC_SM_RC);
   uint8_t* tmp = smem + OCC_SM_TMP;
   OccTables* tb = reinterpret_cast<OccTables*>(smem + OCC_SM_TAB);
   __shared__ OccGeom geom;
-  __shared__ int amb_count;
+  __shared__ int amb_count, any_hi;
 
   const DevMap& m = maps[map_id];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -246,8 +262,10 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
       geom.o0_first = oh / 2 - RD_OCC_MID / 2;
       geom.o1_first = ow / 2 - RD_OCC_MID / 2;
       amb_count = 0;
+      any_hi = 0;
     }
     __syncthreads();
+    if (tid < RD_OCC_MID) occ_coord_tables(geom, rc, tid);
 
     // ---- A: crop bits -> smem.  word (i, j) = crop columns 32j..32j+31 of crop row i ----
     for (int t = tid; t < RD_OCC_IN * OCC_XW; t += OCC_THREADS) {
@@ -297,21 +315,23 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
       if (pix - lane < n_pix) {            // whole warps only (n_pix is a multiple of 32)
         const int a = pix / RD_OCC_MID, b = pix - a * RD_OCC_MID;
         double c0, c1;
-        occ_coords(geom, a, b, c0, c1);
+        occ_coords(rc, a, b, c0, c1);
         uint32_t val = 0u;
         if (!(c0 < 0.0 || c0 > (double)(RD_OCC_IN - 1) || c1 < 0.0 || c1 > (double)(RD_OCC_IN - 1))) {
           const double f0 = floor(c0), f1 = floor(c1);
           const float y0 = (float)(c0 - f0), y1 = (float)(c1 - f1);
           const float z0 = 1.0f - y0, z1 = 1.0f - y1;
+          const float y02 = y0 * y0, z02 = z0 * z0, y12 = y1 * y1, z12 = z1 * z1;
           float w0[4], w1[4];
-          w0[1] = (y0 * y0 * (y0 - 2.0f) * 3.0f + 4.0f) * (1.0f / 6.0f);
-          w0[2] = (z0 * z0 * (z0 - 2.0f) * 3.0f + 4.0f) * (1.0f / 6.0f);
-          w0[0] = z0 * z0 * z0 * (1.0f / 6.0f);
-          w0[3] = y0 * y0 * y0 * (1.0f / 6.0f);
-          w1[1] = (y1 * y1 * (y1 - 2.0f) * 3.0f + 4.0f) * (1.0f / 6.0f);
-          w1[2] = (z1 * z1 * (z1 - 2.0f) * 3.0f + 4.0f) * (1.0f / 6.0f);
-          w1[0] = z1 * z1 * z1 * (1.0f / 6.0f);
-          w1[3] = y1 * y1 * y1 * (1.0f / 6.0f);
+          // cubic B-spline weights: (3t^3 - 6t^2 + 4)/6 = t^2 (t/2 - 1) + 2/3 ;  t^3/6
+          w0[1] = fmaf(y02, fmaf(0.5f, y0, -1.0f), 2.0f / 3.0f);
+          w0[2] = fmaf(z02, fmaf(0.5f, z0, -1.0f), 2.0f / 3.0f);
+          w0[0] = z02 * z0 * (1.0f / 6.0f);
+          w0[3] = y02 * y0 * (1.0f / 6.0f);
+          w1[1] = fmaf(y12, fmaf(0.5f, y1, -1.0f), 2.0f / 3.0f);
+          w1[2] = fmaf(z12, fmaf(0.5f, z1, -1.0f), 2.0f / 3.0f);
+          w1[0] = z12 * z1 * (1.0f / 6.0f);
+          w1[3] = y12 * y1 * (1.0f / 6.0f);
           // taps rows f0-1..f0+2 -> padded rows f0..f0+3; same for columns
           const float* base = coef + (int)f0 * OCC_PITCH + (int)f1;
           float v = 0.0f;
@@ -334,14 +354,18 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
           }
         }
         const uint32_t b0 = __ballot_sync(0xffffffffu, val & 1u), b1 = __ballot_sync(0xffffffffu, val & 2u);
-        if (lane == 0) { planes[pix >> 5] = b0; planes[(n_pix >> 5) + (pix >> 5)] = b1; }
+        if (lane == 0) {
+          planes[pix >> 5] = b0;
+          planes[(n_pix >> 5) + (pix >> 5)] = b1;
+          if (b1) any_hi = 1;
+        }
       }
       if ((round % OCC_AMB_ROUNDS) == OCC_AMB_ROUNDS - 1 || round == n_rounds - 1) {
         __syncthreads();
         const int n_amb = amb_count;
         __syncthreads();                   // everyone has read the count before anyone can add to it again
         if (n_amb > 0) {
-          for (int e = 0; e < n_amb; ++e) occ_exact_pixel(geom, (int)amb[e], xb, hband, T, planes);
+          for (int e = 0; e < n_amb; ++e) occ_exact_pixel(rc, (int)amb[e], xb, hband, T, planes);
           if (tid == 0) amb_count = 0;
           __syncthreads();
         }
@@ -349,23 +373,32 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
     }
     __syncthreads();
 
-    // ---- D: Pillow bicubic 200 -> 64.  The coefficient image is dead: expand the bit planes into it ----
-    for (int i = tid; i < n_pix; i += OCC_THREADS) {
-      const uint32_t lo = (planes[i >> 5] >> (i & 31)) & 1u, hi = (planes[(n_pix >> 5) + (i >> 5)] >> (i & 31)) & 1u;
-      mid[i] = (uint8_t)(lo | (hi << 1));
-    }
+    // ---- D: Pillow bicubic 200 -> 64.  The coefficient image is dead: its space takes the tables and the uint8
+    // intermediate.  Horizontal pass straight on the bit planes: the <= 15-tap window of an output pixel is a bit mask,
+    // its fixed-point sum three table reads (plane 1, the "value >= 2" plane, is empty for every real map; if any
+    // pixel set it, its windows are added with weight 2).
     for (int i = tid; i < (int)(sizeof(OccTables) / 4); i += OCC_THREADS)
       reinterpret_cast<int32_t*>(tb)[i] = __ldg(reinterpret_cast<const int32_t*>(tables) + i);
     __syncthreads();
-    for (int i = tid; i < RD_OCC_MID * RD_OCC_OUT; i += OCC_THREADS) {
-      const int yy = i / RD_OCC_OUT, xx = i - yy * RD_OCC_OUT;
-      int32_t ss = 1 << (OCC_PREC_BITS - 1);
-      const int x0 = tb->xmin[xx], xn = tb->xnum[xx];
-      const uint8_t* src = mid + yy * RD_OCC_MID + x0;
-      const int32_t* k = tb->kk + xx * OCC_KSIZE;
-      for (int t = 0; t < xn; ++t) ss += (int32_t)src[t] * k[t];
-      ss >>= OCC_PREC_BITS;
-      tmp[yy * RD_OCC_OUT + xx] = (uint8_t)(ss < 0 ? 0 : (ss > 255 ? 255 : ss));
+    {
+      const bool hi_plane = any_hi != 0;
+      for (int i = tid; i < RD_OCC_MID * RD_OCC_OUT; i += OCC_THREADS) {
+        const int yy = i / RD_OCC_OUT, xx = i - yy * RD_OCC_OUT;
+        const int x0 = tb->xmin[xx], xn = tb->xnum[xx];
+        const int bitpos = yy * RD_OCC_MID + x0;
+        const uint32_t mask = (1u << xn) - 1u;
+        const int32_t* lut = tb->lut + xx;
+        const uint32_t m0 = __funnelshift_r(planes[bitpos >> 5], planes[(bitpos >> 5) + 1], bitpos & 31) & mask;
+        int32_t ss = (1 << (OCC_PREC_BITS - 1)) + lut[(m0 & 31u) * RD_OCC_OUT] + lut[(32 + ((m0 >> 5) & 31u)) * RD_OCC_OUT] +
+                     lut[(64 + (m0 >> 10)) * RD_OCC_OUT];
+        if (hi_plane) {
+          const uint32_t* p1 = planes + (n_pix >> 5);
+          const uint32_t m1 = __funnelshift_r(p1[bitpos >> 5], p1[min((bitpos >> 5) + 1, (n_pix >> 5) - 1)], bitpos & 31) & mask;
+          ss += 2 * (lut[(m1 & 31u) * RD_OCC_OUT] + lut[(32 + ((m1 >> 5) & 31u)) * RD_OCC_OUT] + lut[(64 + (m1 >> 10)) * RD_OCC_OUT]);
+        }
+        ss >>= OCC_PREC_BITS;
+        tmp[yy * RD_OCC_OUT + xx] = (uint8_t)(ss < 0 ? 0 : (ss > 255 ? 255 : ss));
+      }
     }
     __syncthreads();
     for (int i = tid; i < RD_OCC_OUT * RD_OCC_OUT; i += OCC_THREADS) {
@@ -410,6 +443,13 @@ static inline void occ_build_tables(OccTables& t) {
       t.kk[xx * OCC_KSIZE + x] = k[x] < 0 ? (int32_t)(-0.5 + k[x] * (1 << OCC_PREC_BITS)) : (int32_t)(0.5 + k[x] * (1 << OCC_PREC_BITS));
     t.xmin[xx] = xmin;
     t.xnum[xx] = xmax;
+    for (int g = 0; g < 3; ++g)
+      for (int m = 0; m < 32; ++m) {
+        int32_t acc = 0;
+        for (int j = 0; j < 5; ++j)
+          if ((m >> j) & 1) acc += t.kk[xx * OCC_KSIZE + 5 * g + j];
+        t.lut[(g * 32 + m) * RD_OCC_OUT + xx] = acc;
+      }
   }
 }
 
