@@ -165,6 +165,17 @@ int rd_reset(rd_env* env, const uint8_t* mask_dev, int mode, const rd_outputs* o
  *      actions_dev: f32 [N,2] = [motor, steering] agent-facing ([-1,1] when rescale_actions). ---- */
 int rd_step(rd_env* env, const float* actions_dev, const rd_outputs* out, void* stream);
 
+/* ---- host-facing step: replaces `obs, reward, done, info = env.step(actions)` for callers whose actions and
+ *      observations are HOST arrays (numpy), which is how the reference's driver loop calls the env
+ *      [REF dreamer/tools.py:178-195 simulate()].  rd_host_init allocates, once, device result buffers and pinned
+ *      host mirrors owned by the library and returns the HOST pointers in `host_out` (valid until rd_destroy).
+ *      rd_step_host copies the actions in, steps the batch in `n_chunks` env-chunks pipelined over internal streams
+ *      (chunk k's device->host copy overlaps chunk k+1's kernels) and returns when every result is in the host
+ *      buffers.  Results are identical to rd_step's. ---- */
+int rd_host_init(rd_env* env, int n_chunks, rd_outputs* host_out);
+int rd_reset_host(rd_env* env, const uint8_t* mask_host, int mode);
+int rd_step_host(rd_env* env, const float* actions_host);
+
 /* ---- stage entry points (teacher-forced parity tests; each is one kernel of the step) ---- */
 /* a2 LiDAR [REF dreamer/scenarios/max_progress/austria.yml:7 'lidar' sensor]: poses f64 [n,3]=(x,y,yaw),
  * map_ids i32[n] sorted ascending or NULL (= map 0), ranges f32 [n, n_beams]. */

@@ -86,6 +86,7 @@ EXPORTS = (
     "rd_default_config", "rd_create", "rd_destroy", "rd_last_error", "rd_abi_version", "rd_upload_map",
     "rd_assign_maps", "rd_reset", "rd_step", "rd_lidar_cast", "rd_occupancy_obs", "rd_dynamics",
     "rd_get_state", "rd_set_state", "rd_read_stats", "rd_launch_count", "rd_enable_timing", "rd_read_timing",
+    "rd_host_init", "rd_reset_host", "rd_step_host",
 )
 
 LIB_PATH = Path(__file__).resolve().parent / "librd_env.so"
@@ -130,6 +131,12 @@ def load_library() -> C.CDLL:
     lib.rd_reset.restype = i32
     lib.rd_step.argtypes = [vp, vp, C.POINTER(RdOutputs), vp]
     lib.rd_step.restype = i32
+    lib.rd_host_init.argtypes = [vp, i32, C.POINTER(RdOutputs)]
+    lib.rd_host_init.restype = i32
+    lib.rd_reset_host.argtypes = [vp, vp, i32]
+    lib.rd_reset_host.restype = i32
+    lib.rd_step_host.argtypes = [vp, vp]
+    lib.rd_step_host.restype = i32
     lib.rd_lidar_cast.argtypes = [vp, vp, vp, i32, vp, vp]
     lib.rd_lidar_cast.restype = i32
     lib.rd_occupancy_obs.argtypes = [vp, vp, vp, i32, vp, vp]

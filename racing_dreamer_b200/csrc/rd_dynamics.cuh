@@ -242,12 +242,13 @@ __global__ void __launch_bounds__(128) k_reset(StepParams P, OutPtrs o, const ui
   }
 }
 
-__global__ void __launch_bounds__(128) k_step(StepParams P, OutPtrs o, const float* __restrict__ actions) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+// envs [e0, e1) of the batch (the host-facing path steps the batch in chunks on several streams)
+__global__ void __launch_bounds__(128) k_step(StepParams P, OutPtrs o, const float* __restrict__ actions, int e0, int e1) {
+  const int e = e0 + blockIdx.x * blockDim.x + threadIdx.x;
   const int n = P.n;
   const rd_config& cfg = P.cfg;
   double st[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // rd_stats contributions of this env
-  if (e < n) {
+  if (e < e1) {
     double* f = P.f64;
     int32_t* I = P.i32;
     int flags = I[(size_t)RD_I_FLAGS * n + e];

@@ -33,6 +33,7 @@ struct HostMap {
   void* d_start = nullptr;
   void* d_reset = nullptr;
   bool present = false;
+  int lidar_per_sm = -1;   // resident k_lidar CTAs per SM for this map (cached launch configuration)
 };
 
 }  // namespace
@@ -41,6 +42,8 @@ struct rd_env {
   rd_config cfg{};
   int device = 0;
   int sm_count = 0;
+  int smem_optin = 0;             // max dynamic shared memory per CTA (opt-in), bytes
+  bool lidar_attr_set[2] = {false, false};  // k_lidar<16>, k_lidar<32> opted in to smem_optin
   int n = 0;
   double* d_f64 = nullptr;
   int32_t* d_i32 = nullptr;
@@ -59,6 +62,23 @@ struct rd_env {
   int32_t* d_stage_ids = nullptr;
   int stage_cap = 0;
   int64_t launches = 0;
+  std::vector<int32_t> h_order;     // host copy of d_env_order (chunk -> per-map sub-ranges)
+  // host-facing path (rd_host_init / rd_step_host)
+  struct HostPath {
+    bool ready = false;
+    int n_chunks = 0;
+    std::vector<int> bounds;                 // n_chunks + 1 env indices
+    std::vector<cudaStream_t> streams;
+    std::vector<cudaEvent_t> ev_done;
+    cudaEvent_t ev_act = nullptr;
+    float* act_host = nullptr; float* act_dev = nullptr;
+    uint8_t* mask_dev = nullptr;
+    unsigned char* small_dev = nullptr; unsigned char* small_host = nullptr; size_t small_bytes = 0;
+    float* lidar_dev = nullptr; float* lidar_host = nullptr;
+    uint8_t* occ_dev = nullptr; uint8_t* occ_host = nullptr;
+    unsigned int* ctr = nullptr;             // [n_chunks][2] k_lidar work counters, one pair per stream
+    rd_outputs dev_out{}, host_out{};
+  } hp;
   // optional per-kernel timing (rd_enable_timing)
   bool timing = false;
   struct Timed { cudaEvent_t a, b; int kind; };
@@ -180,23 +200,32 @@ LidarParams lidar_params(const rd_env* env, const DevMap& m) {
 // LiDAR launch for the envs of one map: persistent CTAs, grid = resident CTAs on all SMs.
 template <int WARPS>
 int launch_lidar_t(rd_env* env, int map_id, const OriginRec* recs, const int32_t* order, int n_env, float* out,
-                   cudaStream_t s) {
+                   cudaStream_t s, unsigned int* ctr) {
   const DevMap& m = env->maps[map_id].dev;
   LidarParams lp = lidar_params(env, m);
   const size_t tab_bytes = ((size_t)2 * lp.n_beams * 8 + 15) & ~(size_t)15;
   const size_t smem = 16 + tab_bytes + (size_t)m.bits_bytes;
   auto kern = k_lidar<WARPS>;
-  CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  CUDA_TRY(env, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
-  if (per_sm < 1) return fail(env, RD_ERR_INVALID, "map %d (%zu B) does not fit in shared memory", map_id, smem);
+  int& per_sm = env->maps[map_id].lidar_per_sm;
+  if (per_sm < 0) {  // once per map: ask how many CTAs fit on an SM (the kernel is opted in to the device maximum)
+    bool& attr = env->lidar_attr_set[WARPS == 32 ? 1 : 0];
+    if (!attr) {
+      CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_optin));
+      attr = true;
+    }
+    if (smem > (size_t)env->smem_optin) return fail(env, RD_ERR_INVALID, "map %d (%zu B) does not fit in shared memory", map_id, smem);
+    int q = 0;
+    CUDA_TRY(env, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, WARPS * 32, smem));
+    if (q < 1) return fail(env, RD_ERR_INVALID, "map %d (%zu B) does not fit in shared memory", map_id, smem);
+    per_sm = q;
+  }
   const long long items = (long long)n_env * lp.groups;
   if (items >= (1ll << 31)) return fail(env, RD_ERR_INVALID, "too many (env, beam group) items for one launch");
   long long grid = std::min<long long>((items + WARPS - 1) / WARPS, (long long)env->sm_count * per_sm);
   if (grid < 1) return RD_OK;
   {
     ScopedTiming tm(env, s, T_LIDAR);
-    kern<<<(unsigned)grid, WARPS * 32, smem, s>>>(env->d_maps, map_id, recs, order, n_env, lp, env->d_beam_tab, out, env->d_lidar_ctr);
+    kern<<<(unsigned)grid, WARPS * 32, smem, s>>>(env->d_maps, map_id, recs, order, n_env, lp, env->d_beam_tab, out, ctr);
   }
   env->launches++;
   CUDA_TRY(env, cudaGetLastError());
@@ -204,11 +233,12 @@ int launch_lidar_t(rd_env* env, int map_id, const OriginRec* recs, const int32_t
 }
 
 int launch_lidar(rd_env* env, int map_id, const OriginRec* recs, const int32_t* order, int n_env, float* out,
-                 cudaStream_t s) {
+                 cudaStream_t s, unsigned int* ctr = nullptr) {
   const DevMap& m = env->maps[map_id].dev;
+  if (!ctr) ctr = env->d_lidar_ctr;
   // small maps: 16-warp CTAs (several per SM); large maps: 32-warp CTAs so one resident copy feeds 32 warps
-  if (m.bits_bytes > 72 * 1024) return launch_lidar_t<32>(env, map_id, recs, order, n_env, out, s);
-  return launch_lidar_t<16>(env, map_id, recs, order, n_env, out, s);
+  if (m.bits_bytes > 72 * 1024) return launch_lidar_t<32>(env, map_id, recs, order, n_env, out, s, ctr);
+  return launch_lidar_t<16>(env, map_id, recs, order, n_env, out, s, ctr);
 }
 
 int launch_occupancy(rd_env* env, int map_id, const OriginRec* recs, const double* poses_xyyaw,
@@ -238,14 +268,19 @@ StepParams step_params(rd_env* env) {
   return P;
 }
 
-int observe(rd_env* env, const rd_outputs* out, cudaStream_t s) {
+// LiDAR / occupancy launches for the envs [e0, e1) (grouped by map; each map's env list is ascending)
+int observe(rd_env* env, const rd_outputs* out, cudaStream_t s, int e0 = 0, int e1 = -1, unsigned int* ctr = nullptr) {
   if (!out) return RD_OK;
+  if (e1 < 0) e1 = env->n;
   for (int mid = 0; mid < RD_MAX_MAPS; ++mid) {
-    const int n_env = env->order_offset[mid + 1] - env->order_offset[mid];
+    const int32_t* hb = env->h_order.data() + env->order_offset[mid];
+    const int32_t* he = env->h_order.data() + env->order_offset[mid + 1];
+    const int first = (int)(std::lower_bound(hb, he, e0) - hb), last = (int)(std::lower_bound(hb, he, e1) - hb);
+    const int n_env = last - first;
     if (n_env == 0) continue;
-    const int32_t* order = env->d_env_order + env->order_offset[mid];
+    const int32_t* order = env->d_env_order + env->order_offset[mid] + first;
     if (out->lidar_dev && (env->cfg.obs_flags & RD_OBS_LIDAR)) {
-      int rc = launch_lidar(env, mid, env->d_recs, order, n_env, out->lidar_dev, s);
+      int rc = launch_lidar(env, mid, env->d_recs, order, n_env, out->lidar_dev, s, ctr);
       if (rc) return rc;
     }
     if (out->occupancy_dev && (env->cfg.obs_flags & RD_OBS_OCCUPANCY)) {
@@ -316,6 +351,7 @@ RD_API int rd_create(const rd_config* cfg, rd_env** out) {
   env->cfg = *cfg;
   env->device = dev;
   env->sm_count = prop.multiProcessorCount;
+  env->smem_optin = (int)prop.sharedMemPerBlockOptin;
   env->n = cfg->n_envs;
   env->order_offset.assign(RD_MAX_MAPS + 1, 0);
   const size_t n = (size_t)env->n;
@@ -353,6 +389,14 @@ RD_API void rd_destroy(rd_env* env) {
   cudaFree(env->d_beam_tab); cudaFree(env->d_maps); cudaFree(env->d_env_order); cudaFree(env->d_lidar_ctr);
   cudaFree(env->d_stage_recs); cudaFree(env->d_stage_ids);
   occ_free(env->occ);
+  {
+    auto& h = env->hp;
+    for (auto st : h.streams) cudaStreamDestroy(st);
+    for (auto ev : h.ev_done) cudaEventDestroy(ev);
+    if (h.ev_act) cudaEventDestroy(h.ev_act);
+    cudaFreeHost(h.act_host); cudaFree(h.act_dev); cudaFree(h.mask_dev); cudaFree(h.small_dev); cudaFreeHost(h.small_host);
+    cudaFree(h.lidar_dev); cudaFreeHost(h.lidar_host); cudaFree(h.occ_dev); cudaFreeHost(h.occ_host); cudaFree(h.ctr);
+  }
   for (auto& t : env->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (auto& e : env->event_pool) cudaEventDestroy(e);
   for (auto& m : env->maps) { cudaFree(m.d_bits); cudaFree(m.d_dist); cudaFree(m.d_start); cudaFree(m.d_reset); }
@@ -434,6 +478,7 @@ RD_API int rd_assign_maps(rd_env* env, const int32_t* ids) {
   std::vector<int32_t> order(n);
   for (int e = 0; e < n; ++e) order[cursor[id[e]]++] = e;
   CUDA_TRY(env, cudaMemcpy(env->d_env_order, order.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice));
+  env->h_order = order;
   CUDA_TRY(env, cudaMemcpy(env->d_i32 + (size_t)RD_I_MAP * n, id.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice));
   int rc = sync_maps(env);
   if (rc) return rc;
@@ -465,11 +510,165 @@ RD_API int rd_step(rd_env* env, const float* actions_dev, const rd_outputs* out,
   cudaStream_t s = (cudaStream_t)stream;
   {
     ScopedTiming tm(env, s, T_STEP);
-    k_step<<<(env->n + 127) / 128, 128, 0, s>>>(step_params(env), out_ptrs(out), actions_dev);
+    k_step<<<(env->n + 127) / 128, 128, 0, s>>>(step_params(env), out_ptrs(out), actions_dev, 0, env->n);
   }
   env->launches++;
   CUDA_TRY(env, cudaGetLastError());
   return observe(env, out, s);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-facing path
+RD_API int rd_host_init(rd_env* env, int n_chunks, rd_outputs* host_out) {
+  if (!env || !host_out) return fail(env, RD_ERR_INVALID, "null argument");
+  if (!env->assigned) return fail(env, RD_ERR_STATE, "rd_assign_maps has not been called");
+  auto& h = env->hp;
+  if (h.ready) { *host_out = h.host_out; return RD_OK; }
+  const int n = env->n;
+  n_chunks = std::max(1, std::min(n_chunks, n));
+  h.n_chunks = n_chunks;
+  h.bounds.resize(n_chunks + 1);
+  // progressive chunk sizes (1 : 2 : 4 : ... capped at 8x): the first chunk is small so that the copy engine starts
+  // early; from then on it is the bottleneck and each chunk's ray casting hides behind the previous chunk's copy
+  {
+    std::vector<double> w(n_chunks);
+    double tot = 0.0;
+    for (int c = 0; c < n_chunks; ++c) { w[c] = (double)(1 << std::min(c, 3)); tot += w[c]; }
+    double acc = 0.0;
+    h.bounds[0] = 0;
+    for (int c = 0; c < n_chunks; ++c) { acc += w[c]; h.bounds[c + 1] = (int)std::llround((double)n * acc / tot); }
+    h.bounds[n_chunks] = n;
+  }
+  // small arrays share one slab (one device->host copy per step); offsets 256-byte aligned
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_pose = take(sizeof(float) * 6 * n), o_vel = take(sizeof(float) * 6 * n), o_speed = take(sizeof(float) * n);
+  const size_t o_rew = take(sizeof(float) * n), o_prog = take(sizeof(float) * n), o_time = take(sizeof(float) * n);
+  const size_t o_lap = take(sizeof(int32_t) * n), o_done = take((size_t)n), o_flags = take((size_t)n);
+  h.small_bytes = off;
+  const size_t lidar_bytes = sizeof(float) * (size_t)n * env->cfg.n_beams;
+  const bool occ = (env->cfg.obs_flags & RD_OBS_OCCUPANCY) != 0;
+  CUDA_TRY(env, cudaMalloc(&h.small_dev, h.small_bytes));
+  CUDA_TRY(env, cudaMemset(h.small_dev, 0, h.small_bytes));
+  CUDA_TRY(env, cudaHostAlloc(&h.small_host, h.small_bytes, cudaHostAllocDefault));
+  std::memset(h.small_host, 0, h.small_bytes);
+  CUDA_TRY(env, cudaMalloc(&h.lidar_dev, lidar_bytes));
+  CUDA_TRY(env, cudaMemset(h.lidar_dev, 0, lidar_bytes));
+  CUDA_TRY(env, cudaHostAlloc(&h.lidar_host, lidar_bytes, cudaHostAllocDefault));
+  std::memset(h.lidar_host, 0, lidar_bytes);
+  if (occ) {
+    CUDA_TRY(env, cudaMalloc(&h.occ_dev, (size_t)n * 4096));
+    CUDA_TRY(env, cudaMemset(h.occ_dev, 0, (size_t)n * 4096));
+    CUDA_TRY(env, cudaHostAlloc(&h.occ_host, (size_t)n * 4096, cudaHostAllocDefault));
+    std::memset(h.occ_host, 0, (size_t)n * 4096);
+  }
+  CUDA_TRY(env, cudaHostAlloc(&h.act_host, sizeof(float) * 2 * n, cudaHostAllocDefault));
+  CUDA_TRY(env, cudaMalloc(&h.act_dev, sizeof(float) * 2 * n));
+  CUDA_TRY(env, cudaMalloc(&h.mask_dev, (size_t)n));
+  CUDA_TRY(env, cudaMalloc(&h.ctr, sizeof(unsigned int) * 2 * n_chunks));
+  CUDA_TRY(env, cudaMemset(h.ctr, 0, sizeof(unsigned int) * 2 * n_chunks));
+  h.streams.resize(n_chunks);
+  h.ev_done.resize(n_chunks);
+  for (int c = 0; c < n_chunks; ++c) {
+    CUDA_TRY(env, cudaStreamCreateWithFlags(&h.streams[c], cudaStreamNonBlocking));
+    CUDA_TRY(env, cudaEventCreateWithFlags(&h.ev_done[c], cudaEventDisableTiming));
+  }
+  CUDA_TRY(env, cudaEventCreateWithFlags(&h.ev_act, cudaEventDisableTiming));
+  auto fill = [&](rd_outputs& o, unsigned char* base, float* lidar, uint8_t* occp) {
+    o.lidar_dev = lidar; o.occupancy_dev = occp;
+    o.pose_dev = (float*)(base + o_pose); o.velocity_dev = (float*)(base + o_vel); o.speed_dev = (float*)(base + o_speed);
+    o.reward_dev = (float*)(base + o_rew); o.progress_dev = (float*)(base + o_prog); o.time_dev = (float*)(base + o_time);
+    o.lap_dev = (int32_t*)(base + o_lap); o.done_dev = (uint8_t*)(base + o_done); o.flags_dev = (uint8_t*)(base + o_flags);
+  };
+  fill(h.dev_out, h.small_dev, h.lidar_dev, h.occ_dev);
+  fill(h.host_out, h.small_host, h.lidar_host, h.occ_host);
+  h.ready = true;
+  *host_out = h.host_out;
+  return RD_OK;
+}
+
+namespace {
+// makes the handle's device current for the duration of a host-facing call
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+// device->host copies of the chunk's big rows on its stream; the last step of the call gathers the small slab
+int host_copy_back(rd_env* env, int c) {
+  auto& h = env->hp;
+  const size_t e0 = (size_t)h.bounds[c], cnt = (size_t)(h.bounds[c + 1] - h.bounds[c]);
+  const size_t nb = (size_t)env->cfg.n_beams;
+  CUDA_TRY(env, cudaMemcpyAsync(h.lidar_host + e0 * nb, h.lidar_dev + e0 * nb, sizeof(float) * cnt * nb, cudaMemcpyDeviceToHost, h.streams[c]));
+  if (h.occ_dev) CUDA_TRY(env, cudaMemcpyAsync(h.occ_host + e0 * 4096, h.occ_dev + e0 * 4096, cnt * 4096, cudaMemcpyDeviceToHost, h.streams[c]));
+  return RD_OK;
+}
+int host_finish(rd_env* env, bool small_copied) {
+  auto& h = env->hp;
+  for (int c = 1; c < h.n_chunks; ++c) {
+    CUDA_TRY(env, cudaEventRecord(h.ev_done[c], h.streams[c]));
+    CUDA_TRY(env, cudaStreamWaitEvent(h.streams[0], h.ev_done[c], 0));
+  }
+  if (!small_copied) CUDA_TRY(env, cudaMemcpyAsync(h.small_host, h.small_dev, h.small_bytes, cudaMemcpyDeviceToHost, h.streams[0]));
+  CUDA_TRY(env, cudaStreamSynchronize(h.streams[0]));
+  return RD_OK;
+}
+}  // namespace
+
+RD_API int rd_reset_host(rd_env* env, const uint8_t* mask_host, int mode) {
+  if (!env) return fail(nullptr, RD_ERR_INVALID, "null handle");
+  auto& h = env->hp;
+  if (!h.ready) return fail(env, RD_ERR_STATE, "rd_host_init has not been called");
+  DeviceGuard guard(env->device);
+  cudaStream_t s0 = h.streams[0];
+  if (mask_host) CUDA_TRY(env, cudaMemcpyAsync(h.mask_dev, mask_host, (size_t)env->n, cudaMemcpyHostToDevice, s0));
+  int rc = rd_reset(env, mask_host ? h.mask_dev : nullptr, mode, &h.dev_out, s0);
+  if (rc) return rc;
+  const int saved = h.n_chunks;   // everything ran on stream 0: copy it back as one chunk
+  const size_t nb = (size_t)env->cfg.n_beams, n = (size_t)env->n;
+  CUDA_TRY(env, cudaMemcpyAsync(h.lidar_host, h.lidar_dev, sizeof(float) * n * nb, cudaMemcpyDeviceToHost, s0));
+  if (h.occ_dev) CUDA_TRY(env, cudaMemcpyAsync(h.occ_host, h.occ_dev, n * 4096, cudaMemcpyDeviceToHost, s0));
+  CUDA_TRY(env, cudaMemcpyAsync(h.small_host, h.small_dev, h.small_bytes, cudaMemcpyDeviceToHost, s0));
+  CUDA_TRY(env, cudaStreamSynchronize(s0));
+  (void)saved;
+  return RD_OK;
+}
+
+RD_API int rd_step_host(rd_env* env, const float* actions_host) {
+  if (!env || !actions_host) return fail(env, RD_ERR_INVALID, "null argument");
+  auto& h = env->hp;
+  if (!h.ready) return fail(env, RD_ERR_STATE, "rd_host_init has not been called");
+  if (!env->was_reset) return fail(env, RD_ERR_STATE, "Must reset environment.");  // [REF dreamer/wrappers.py:148]
+  DeviceGuard guard(env->device);
+  const int n = env->n;
+  std::memcpy(h.act_host, actions_host, sizeof(float) * 2 * (size_t)n);   // caller memory may be pageable
+  CUDA_TRY(env, cudaMemcpyAsync(h.act_dev, h.act_host, sizeof(float) * 2 * (size_t)n, cudaMemcpyHostToDevice, h.streams[0]));
+  // k_step is bound by the latency of one env's float64 dependency chain, not by the batch size, so it runs ONCE
+  // over the whole batch; the observation kernels then go chunk by chunk so that chunk k's device->host copy
+  // overlaps chunk k+1's ray casting.  The small result slab is copied right behind k_step.
+  cudaStream_t s0 = h.streams[0];
+  {
+    ScopedTiming tm(env, s0, T_STEP);
+    k_step<<<(n + 127) / 128, 128, 0, s0>>>(step_params(env), out_ptrs(&h.dev_out), h.act_dev, 0, n);
+  }
+  env->launches++;
+  CUDA_TRY(env, cudaGetLastError());
+  CUDA_TRY(env, cudaEventRecord(h.ev_act, s0));   // marks "state advanced"
+  bool small_copied = false;
+  for (int c = 0; c < h.n_chunks; ++c) {
+    cudaStream_t s = h.streams[c];
+    const int e0 = h.bounds[c], e1 = h.bounds[c + 1];
+    if (e1 <= e0) continue;
+    if (c > 0) CUDA_TRY(env, cudaStreamWaitEvent(s, h.ev_act, 0));
+    if (c == 1) {  // the small slab is final once k_step is done: copy it while chunk 0 is ray casting
+      CUDA_TRY(env, cudaMemcpyAsync(h.small_host, h.small_dev, h.small_bytes, cudaMemcpyDeviceToHost, s));
+      small_copied = true;
+    }
+    int rc = observe(env, &h.dev_out, s, e0, e1, h.ctr + 2 * c);
+    if (rc) return rc;
+    if ((rc = host_copy_back(env, c))) return rc;
+  }
+  return host_finish(env, small_copied);
 }
 
 RD_API int rd_lidar_cast(rd_env* env, const double* poses_dev, const int32_t* map_ids_host, int n, float* ranges_dev,

@@ -8,13 +8,14 @@
 //
 // One CTA per env (persistent loop), everything in shared memory (no global scratch):
 //   A  crop        220x220 bits of the drivable grid -> smem (funnel-shifted words)
-//   B  prefilter   columns then rows (scipy's order), one thread per line, float32 recursion, into a 223x223 float32
+//   B  prefilter   columns then rows (scipy's order), float32 recursion, lines cut into 2-4 segments, into a 223x227 float32
 //                  image whose 1+2 border rows/columns hold the mirrored values, so the 4x4 taps need no index math
-//   C  rotation    one pixel per thread, 32 consecutive pixels per warp (odd pitch => conflict-free taps for axis-aligned
-//                  headings); source coordinates in float64 with scipy's exact operation order (they decide floor() and
+//   A' uniform map  8x8-cell blocks that are, with their 8 neighbours, all drivable / all not: pixels landing there are
+//                  that constant exactly and skip the taps (about 60-70 % of the pixels of a track crop)
+//   C  rotation    one pixel per thread, an 8x4 pixel tile per warp; source coordinates in float64 with scipy's exact operation order (they decide floor() and
 //                  the inside test); value in float32; the rounded pixel is stored as two warp-ballot bit planes
 //   C' exactness   a pixel whose float32 value lies within OCC_EPS of a rounding threshold (k + 0.5) is re-evaluated in
-//                  float64 by the whole CTA from the banded prefilter operator H (coef = H X H^T), which reproduces
+//                  float64 by its warp from the banded prefilter operator H (coef = H X H^T), which reproduces
 //                  scipy's float64 result to ~1e-15.  float32 error is < 2e-6 (bound in DESIGN.md), OCC_EPS = 2e-5, and
 //                  about one image in 40 has such a pixel, so the output is the reference's, bit for bit.
 //   D  resize      Pillow's 22-bit fixed-point bicubic, horizontal then vertical, uint8 intermediate, in smem
@@ -24,16 +25,15 @@
 #ifndef OCC_THREADS
 #define OCC_THREADS 512
 #endif
-#define OCC_PITCH 223       // 220 + mirrored border (index -1 and 220, 221); odd => rows fall in distinct banks
+#define OCC_ROWS 223        // 220 + mirrored border (index -1 and 220, 221)
+#define OCC_PITCH 227       // row pitch in floats: odd (row pass conflict-free) and = 3 mod 32 (rotated 8x4 tiles spread over the banks)
 #define OCC_XW 7            // 32-bit words per crop row
 #define OCC_KSIZE 15        // Pillow: ceil(2*3.125)*2+1 taps per output pixel
 #define OCC_PREC_BITS 22
 #define OCC_EPS 2.0e-5f
 #define OCC_BAND 40         // |H[r][k]| < 1.3e-23 beyond this distance from the diagonal
 #define OCC_BANDW (2 * OCC_BAND + 1)
-#define OCC_AMB_CAP 2048    // ambiguous pixels per group of OCC_AMB_ROUNDS rounds (cannot overflow: 4 * 512 pixels)
-#define OCC_AMB_ROUNDS (OCC_AMB_CAP / OCC_THREADS)
-#define OCC_TW 84           // columns of the float64 window of the exact evaluator (4 taps + 2 * band)
+#define OCC_NB 28           // 8x8-cell blocks per crop side (uniform-region map)
 
 struct OccTables {            // Pillow precompute_coeffs + normalize_coeffs_8bpc for 200 -> 64, bicubic
   int32_t kk[RD_OCC_OUT * OCC_KSIZE];
@@ -59,18 +59,16 @@ struct OccGeom {              // per-env geometry, computed by one thread
 
 // smem carve-up (bytes)
 #define OCC_SM_COEF 0
-#define OCC_SM_COEF_BYTES ((OCC_PITCH * OCC_PITCH * 4 + 15) & ~15)     // 198,928
+#define OCC_SM_COEF_BYTES ((OCC_ROWS * OCC_PITCH * 4 + 15) & ~15)      // 202,496
 #define OCC_SM_XBITS (OCC_SM_COEF + OCC_SM_COEF_BYTES)
 #define OCC_SM_XBITS_BYTES (RD_OCC_IN * OCC_XW * 4)                   // 6,160
 #define OCC_SM_PLANES (OCC_SM_XBITS + OCC_SM_XBITS_BYTES)
 #define OCC_SM_PLANES_BYTES (2 * (RD_OCC_MID * RD_OCC_MID / 32) * 4)  // 10,000
-#define OCC_SM_AMB (OCC_SM_PLANES + OCC_SM_PLANES_BYTES)
-#define OCC_SM_AMB_BYTES (OCC_AMB_CAP * 2)                            // 4,096
-#define OCC_SM_T (OCC_SM_AMB + OCC_SM_AMB_BYTES)                      // 16-byte aligned: all sizes above are multiples of 16
-#define OCC_SM_T_BYTES ((4 * OCC_TW + 16) * 8)                        // 2,816
-#define OCC_SM_RC (OCC_SM_T + OCC_SM_T_BYTES)                         // per-row / per-column coordinate terms (float64)
+#define OCC_SM_RC (OCC_SM_PLANES + OCC_SM_PLANES_BYTES)               // per-row / per-column coordinate terms (float64); 16-byte aligned
 #define OCC_SM_RC_BYTES (4 * RD_OCC_MID * 8)                          // 6,400
-#define OCC_SM_TOTAL (OCC_SM_RC + OCC_SM_RC_BYTES)                    // 228,400
+#define OCC_SM_UNI (OCC_SM_RC + OCC_SM_RC_BYTES)                      // block class maps (2 x 28 x 28 bytes)
+#define OCC_SM_UNI_BYTES (2 * OCC_NB * OCC_NB)                        // 1,568
+#define OCC_SM_TOTAL (OCC_SM_UNI + OCC_SM_UNI_BYTES)                  // 226,624 of 232,448
 // after the rotation the coefficient image is dead; its space holds the uint8 images and tables of the resize
 #define OCC_SM_TMP 0
 #define OCC_SM_TAB (OCC_SM_TMP + RD_OCC_MID * RD_OCC_OUT)
@@ -89,33 +87,71 @@ __device__ __forceinline__ void occ_weights(double x, double (&w)[4]) {
   w[3] = 1.0 - w[0] - w[1] - w[2];
 }
 
-// float32 cubic B-spline prefilter of one line of 220 values held at p[0], p[stride], ... (mirror boundary,
-// pole sqrt(3)-2, gain 6), in place.  `first` = true: the input is read from the crop bits instead of p.
+// float32 cubic B-spline prefilter of the 220 lines of one axis (mirror boundary, pole z = sqrt(3)-2, gain 6), in place,
+// by the whole CTA.  Element i of line L lives at img[L * line_stride + i * elem_stride].  FROM_BITS: the input is the
+// crop bit (i, L) instead of the image (the column pass reads the binary crop directly).
+// Each line is cut into OCC_NSEG segments handled by different threads: the recursion's memory decays like |z|^k, so a
+// segment that starts 24 samples early from zero reproduces the full-line recursion to |z|^24 = 2e-14 relative -- far
+// below float32 resolution -- and the serial chain per thread is 4x (2x) shorter.  Warm-ups only read; barriers
+// separate them from the in-place main loops.
+#define OCC_NSEG (OCC_THREADS / 256)
+#define OCC_SEG (RD_OCC_IN / OCC_NSEG)
+#define OCC_WARM 24
 template <bool FROM_BITS>
-__device__ __forceinline__ void occ_prefilter_f32(float* p, int stride, const uint32_t* xb, int col) {
+__device__ __forceinline__ void occ_prefilter_axis(float* img, int line_stride, int elem_stride, const uint32_t* xb) {
   const int n = RD_OCC_IN;
   const float z = -0.26794919243112270647f, gain = 6.0f;
+  const int tid = threadIdx.x;
+  const int seg = tid / RD_OCC_IN, L = tid - seg * RD_OCC_IN;
+  const bool active = seg < OCC_NSEG;
+  const int i0 = seg * OCC_SEG, i1 = i0 + OCC_SEG;
+  float* p = img + L * line_stride;
   auto in = [&](int i) -> float {
-    if (FROM_BITS) return (float)((xb[i * OCC_XW + (col >> 5)] >> (col & 31)) & 1u);
-    return p[i * stride];
+    if (FROM_BITS) return (float)((xb[i * OCC_XW + (L >> 5)] >> (L & 31)) & 1u);
+    return p[i * elem_stride];
   };
-  float zi = 1.0f, acc = 0.0f;
+  float prev = 0.0f;
+  if (active) {
+    if (seg == 0) {  // scipy's mirror initialisation: sum_i z^i c[i] (z^24 ~ 2e-14 truncation)
+      float zi = 1.0f;
 #pragma unroll 4
-  for (int i = 0; i < 24; ++i) { acc = fmaf(zi, gain * in(i), acc); zi *= z; }  // z^24 ~ 2e-14
-  float prev = acc;
-  p[0] = prev;
+      for (int i = 0; i < OCC_WARM; ++i) { prev = fmaf(zi, gain * in(i), prev); zi *= z; }
+    } else {
 #pragma unroll 4
-  for (int i = 1; i < n; ++i) {
-    prev = fmaf(z, prev, gain * in(i));
-    p[i * stride] = prev;
+      for (int i = i0 - OCC_WARM; i < i0; ++i) prev = fmaf(z, prev, gain * in(i));
+    }
   }
-  float cur = (z * p[(n - 2) * stride] + p[(n - 1) * stride]) * (z / (z * z - 1.0f));
-  p[(n - 1) * stride] = cur;
+  __syncthreads();
+  if (active) {
+    int i = i0;
+    if (seg == 0) { p[0] = prev; i = 1; }
 #pragma unroll 4
-  for (int i = n - 2; i >= 0; --i) {
-    cur = z * (cur - p[i * stride]);
-    p[i * stride] = cur;
+    for (; i < i1; ++i) {
+      prev = fmaf(z, prev, gain * in(i));
+      p[i * elem_stride] = prev;
+    }
   }
+  __syncthreads();
+  float cur = 0.0f;
+  if (active) {
+    if (seg == OCC_NSEG - 1) {
+      cur = (z * p[(n - 2) * elem_stride] + p[(n - 1) * elem_stride]) * (z / (z * z - 1.0f));
+    } else {
+#pragma unroll 4
+      for (int i = i1 + OCC_WARM - 1; i >= i1; --i) cur = z * (cur - p[i * elem_stride]);
+    }
+  }
+  __syncthreads();
+  if (active) {
+    int i = i1 - 1;
+    if (seg == OCC_NSEG - 1) { p[(n - 1) * elem_stride] = cur; i = n - 2; }
+#pragma unroll 4
+    for (; i >= i0; --i) {
+      cur = z * (cur - p[i * elem_stride]);
+      p[i * elem_stride] = cur;
+    }
+  }
+  __syncthreads();
 }
 
 // Source coordinates of mid pixel (a, b) with scipy's operation order (shift first, then one product per output axis):
@@ -134,11 +170,16 @@ __device__ __forceinline__ void occ_coords(const double* rc, int a, int b, doubl
   c1 = __dadd_rn(rc[RD_OCC_MID + a], rc[3 * RD_OCC_MID + b]);
 }
 
-// Exact float64 value of one rotated pixel, computed cooperatively by the CTA from coef = H X H^T.
-__device__ __noinline__ void occ_exact_pixel(const double* rc, int pix, const uint32_t* xb, const double* __restrict__ hband,
-                                             double* T, uint32_t* planes) {
-  const int tid = threadIdx.x;
-  const int a = pix / RD_OCC_MID, b = pix - a * RD_OCC_MID;
+// Exact float64 value of one rotated pixel (a, b), computed by ONE WARP from coef = H X H^T; every lane returns the
+// rounded pixel.  Lane l owns crop columns L0 + l, L0 + l + 32, L0 + l + 64 of the <= 84-column window:
+//   A: T[p][col] = sum_k H[rp][k] X[k][col]      (4 tap rows x 81 band entries, X from the crop bits)
+//   B: coef[p][q] = sum_col H[cq][col] T[p][col]  (warp reduction)
+//   C: the 4x4 taps in scipy's accumulation order and its rounding.
+// No shared scratch, no CTA barrier: about one image in 40 needs it, so its cost (~10k instructions) is irrelevant, but
+// it must not make the other warps wait.
+__device__ __noinline__ uint32_t occ_exact_pixel(const double* rc, int a, int b, const uint32_t* xb,
+                                                 const double* __restrict__ hband) {
+  const int lane = threadIdx.x & 31;
   double c0, c1;
   occ_coords(rc, a, b, c0, c1);
   const int s0 = (int)floor(c0) - 1, s1 = (int)floor(c1) - 1;
@@ -146,59 +187,59 @@ __device__ __noinline__ void occ_exact_pixel(const double* rc, int pix, const ui
 #pragma unroll
   for (int k = 0; k < 4; ++k) { rp[k] = occ_mirror(s0 + k, RD_OCC_IN); cq[k] = occ_mirror(s1 + k, RD_OCC_IN); }
   const int cmin = min(min(cq[0], cq[1]), min(cq[2], cq[3])), cmax = max(max(cq[0], cq[1]), max(cq[2], cq[3]));
-  const int L0 = max(0, cmin - OCC_BAND), L1 = min(RD_OCC_IN - 1, cmax + OCC_BAND);
-  const int W = L1 - L0 + 1;  // <= 84
-  double* cf = T + 4 * OCC_TW;
-  // A: T[p][l] = sum_k H[rp][k] X[k][l]
-  for (int t = tid; t < 4 * W; t += OCC_THREADS) {
-    const int p = t / W, l = L0 + (t - p * W);
+  const int L0 = max(0, cmin - OCC_BAND), L1 = min(RD_OCC_IN - 1, cmax + OCC_BAND);  // L1 - L0 + 1 <= 84 < 96
+  double T[4][3];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
     const int r = rp[p];
-    const double* h = hband + (size_t)r * OCC_BANDW;
-    double sum = 0.0;
+    const double* h = hband + (size_t)r * OCC_BANDW + (OCC_BAND - r);
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
     const int k0 = max(0, r - OCC_BAND), k1 = min(RD_OCC_IN - 1, r + OCC_BAND);
-    for (int k = k0; k <= k1; ++k)
-      if ((xb[k * OCC_XW + (l >> 5)] >> (l & 31)) & 1u) sum += __ldg(h + (k - r + OCC_BAND));
-    T[p * OCC_TW + (l - L0)] = sum;
+    for (int k = k0; k <= k1; ++k) {
+      const double hk = __ldg(h + k);
+      const uint32_t* row = xb + k * OCC_XW;
+      const int l0 = L0 + lane, l1 = l0 + 32, l2 = l0 + 64;
+      if (l0 <= L1 && ((row[l0 >> 5] >> (l0 & 31)) & 1u)) t0 += hk;
+      if (l1 <= L1 && ((row[l1 >> 5] >> (l1 & 31)) & 1u)) t1 += hk;
+      if (l2 <= L1 && ((row[l2 >> 5] >> (l2 & 31)) & 1u)) t2 += hk;
+    }
+    T[p][0] = t0; T[p][1] = t1; T[p][2] = t2;
   }
-  __syncthreads();
-  // B: coef[p][q] = sum_l H[cq][l] T[p][l]   (one warp per (p, q))
-  const int warp = tid >> 5, lane = tid & 31;
-  if (warp < 16) {
-    const int p = warp >> 2, q = warp & 3;
+  double cf[4][4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
     const int c = cq[q];
-    const double* h = hband + (size_t)c * OCC_BANDW;
-    double sum = 0.0;
-    for (int l = max(L0, c - OCC_BAND) + lane; l <= min(L1, c + OCC_BAND); l += 32)
-      sum += __ldg(h + (l - c + OCC_BAND)) * T[p * OCC_TW + (l - L0)];
+    const double* h = hband + (size_t)c * OCC_BANDW + (OCC_BAND - c);
+    double hq[3];
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-    if (lane == 0) cf[warp] = sum;
+    for (int j = 0; j < 3; ++j) {
+      const int l = L0 + lane + 32 * j;
+      hq[j] = (l <= L1 && l >= c - OCC_BAND && l <= c + OCC_BAND) ? __ldg(h + l) : 0.0;
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      double sum = hq[0] * T[p][0] + hq[1] * T[p][1] + hq[2] * T[p][2];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+      cf[p][q] = sum;
+    }
   }
-  __syncthreads();
-  // C: 4x4 taps in scipy's accumulation order, rounding, patch the bit planes
-  if (tid == 0) {
-    double w0[4], w1[4];
-    occ_weights(c0, w0);
-    occ_weights(c1, w1);
-    double t = 0.0;
+  double w0[4], w1[4];
+  occ_weights(c0, w0);
+  occ_weights(c1, w1);
+  double t = 0.0;
 #pragma unroll
-    for (int p = 0; p < 4; ++p)
+  for (int p = 0; p < 4; ++p)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        double v = cf[p * 4 + q];
-        v *= w0[p];
-        v *= w1[q];
-        t += v;
-      }
-    double tv = t > 0.0 ? t + 0.5 : 0.0;
-    tv = tv > 255.0 ? 255.0 : tv;
-    const uint32_t val = (uint32_t)(uint8_t)tv;
-    const uint32_t bit = 1u << (pix & 31);
-    uint32_t* w = planes + (pix >> 5);
-    w[0] = (w[0] & ~bit) | ((val & 1u) ? bit : 0u);
-    w[RD_OCC_MID * RD_OCC_MID / 32] = (w[RD_OCC_MID * RD_OCC_MID / 32] & ~bit) | ((val & 2u) ? bit : 0u);
-  }
-  __syncthreads();
+    for (int q = 0; q < 4; ++q) {
+      double v = cf[p][q];
+      v *= w0[p];
+      v *= w1[q];
+      t += v;
+    }
+  double tv = t > 0.0 ? t + 0.5 : 0.0;
+  tv = tv > 255.0 ? 255.0 : tv;
+  return (uint32_t)(uint8_t)tv;
 }
 
 __global__ void __launch_bounds__(OCC_THREADS, 1)
@@ -210,13 +251,13 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
   float* coef = reinterpret_cast<float*>(smem + OCC_SM_COEF);
   uint32_t* xb = reinterpret_cast<uint32_t*>(smem + OCC_SM_XBITS);
   uint32_t* planes = reinterpret_cast<uint32_t*>(smem + OCC_SM_PLANES);
-  uint16_t* amb = reinterpret_cast<uint16_t*>(smem + OCC_SM_AMB);
-  double* T = reinterpret_cast<double*>(smem + OCC_SM_T);
   double* rc = reinterpret_cast<double*>(smem + OCC_SM_RC);
+  uint8_t* cls = smem + OCC_SM_UNI;                 // per 8x8 block: 0 all non-drivable, 1 all drivable, 2 mixed
+  uint8_t* uni = cls + OCC_NB * OCC_NB;             // same, but only if the 8 neighbouring blocks agree (else 2)
   uint8_t* tmp = smem + OCC_SM_TMP;
   OccTables* tb = reinterpret_cast<OccTables*>(smem + OCC_SM_TAB);
   __shared__ OccGeom geom;
-  __shared__ int amb_count, any_hi;
+  __shared__ int any_hi;
 
   const DevMap& m = maps[map_id];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -261,7 +302,6 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
       geom.off1 = ic - (-s * oc0 + c * oc1);
       geom.o0_first = oh / 2 - RD_OCC_MID / 2;
       geom.o1_first = ow / 2 - RD_OCC_MID / 2;
-      amb_count = 0;
       any_hi = 0;
     }
     __syncthreads();
@@ -285,11 +325,39 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
       xb[t] = w;
     }
     __syncthreads();
+    // ---- A': uniform-region map.  A rotated pixel whose source cell lies in a block that is, together with its eight
+    // neighbours, entirely drivable (or entirely not) sees a constant crop within >= 8 cells; the spline there equals
+    // that constant to < 1e-3 (|pole|^7 tail), so the pixel is exactly that constant and needs no taps. ----
+    for (int t = tid; t < OCC_NB * OCC_NB; t += OCC_THREADS) {
+      const int bi = t / OCC_NB, bj = t - bi * OCC_NB;
+      const uint32_t valid = bj == OCC_NB - 1 ? 0x0Fu : 0xFFu;   // crop columns 220..223 do not exist
+      uint32_t all_and = valid, all_or = 0u;
+      for (int rr = 0; rr < 8; ++rr) {
+        const int r = 8 * bi + rr;
+        if (r >= RD_OCC_IN) break;
+        const uint32_t byte = (xb[r * OCC_XW + (bj >> 2)] >> ((bj & 3) * 8)) & valid;
+        all_and &= byte;
+        all_or |= byte;
+      }
+      cls[t] = all_or == 0u ? 0 : (all_and == valid ? 1 : 2);
+    }
+    __syncthreads();
+    for (int t = tid; t < OCC_NB * OCC_NB; t += OCC_THREADS) {
+      const int bi = t / OCC_NB, bj = t - bi * OCC_NB;
+      const uint8_t c = cls[t];
+      bool same = c != 2;
+      for (int di = -1; di <= 1 && same; ++di)
+        for (int dj = -1; dj <= 1; ++dj) {
+          const int i = bi + di, j = bj + dj;
+          if (i < 0 || i >= OCC_NB || j < 0 || j >= OCC_NB) continue;   // beyond the crop the prefilter mirrors the block itself
+          if (cls[i * OCC_NB + j] != c) same = false;
+        }
+      uni[t] = same ? c : 2;
+    }
     // ---- B: prefilter, axis 0 (columns) then axis 1 (rows), float32; image stored at padded index (r+1, c+1) ----
-    if (tid < RD_OCC_IN) occ_prefilter_f32<true>(coef + OCC_PITCH + 1 + tid, OCC_PITCH, xb, tid);
     __syncthreads();
-    if (tid < RD_OCC_IN) occ_prefilter_f32<false>(coef + (tid + 1) * OCC_PITCH + 1, 1, nullptr, 0);
-    __syncthreads();
+    occ_prefilter_axis<true>(coef + OCC_PITCH + 1, 1, OCC_PITCH, xb);       // axis 0: line = column
+    occ_prefilter_axis<false>(coef + OCC_PITCH + 1, OCC_PITCH, 1, nullptr);  // axis 1: line = row
     // mirrored border: columns -1, 220, 221 of rows 0..219, then rows -1, 220, 221 of all 223 columns
     for (int t = tid; t < RD_OCC_IN * 3; t += OCC_THREADS) {
       const int r = t / 3, k = t - r * 3;
@@ -299,7 +367,7 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
       else row[RD_OCC_IN + 2] = row[RD_OCC_IN - 2];                  // col 221 <- col 217
     }
     __syncthreads();
-    for (int t = tid; t < OCC_PITCH * 3; t += OCC_THREADS) {
+    for (int t = tid; t < OCC_ROWS * 3; t += OCC_THREADS) {
       const int c = t / 3, k = t - c * 3;
       if (k == 0) coef[c] = coef[2 * OCC_PITCH + c];                                        // row -1 <- row 1
       else if (k == 1) coef[(RD_OCC_IN + 1) * OCC_PITCH + c] = coef[(RD_OCC_IN - 1) * OCC_PITCH + c];  // 220 <- 218
@@ -307,18 +375,29 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
     }
     __syncthreads();
 
-    // ---- C: rotation, one pixel per thread and round ----
+    // ---- C: rotation.  One pixel per thread and round; a warp owns an 8-wide x 4-high tile of the mid image ----
     const int n_pix = RD_OCC_MID * RD_OCC_MID;
-    const int n_rounds = (n_pix + OCC_THREADS - 1) / OCC_THREADS;
-    for (int round = 0; round < n_rounds; ++round) {
-      const int pix = round * OCC_THREADS + tid;
-      if (pix - lane < n_pix) {            // whole warps only (n_pix is a multiple of 32)
-        const int a = pix / RD_OCC_MID, b = pix - a * RD_OCC_MID;
+    const int n_tiles = n_pix / 32;                                  // 50 x 25 tiles
+    const int warps = OCC_THREADS / 32;
+    const int n_rounds = (n_tiles + warps - 1) / warps;
+    uint8_t* plane0 = reinterpret_cast<uint8_t*>(planes);
+    uint8_t* plane1 = plane0 + n_pix / 8;
+    int ty = (tid >> 5) / (RD_OCC_MID / 8), tx = (tid >> 5) % (RD_OCC_MID / 8);   // tile of round 0; advanced incrementally
+    for (int round = 0; round < n_rounds; ++round, tx += warps) {
+      while (tx >= RD_OCC_MID / 8) { tx -= RD_OCC_MID / 8; ++ty; }
+      if (ty < RD_OCC_MID / 4) {
+        const int a = ty * 4 + (lane >> 3), b = tx * 8 + (lane & 7);
         double c0, c1;
         occ_coords(rc, a, b, c0, c1);
         uint32_t val = 0u;
-        if (!(c0 < 0.0 || c0 > (double)(RD_OCC_IN - 1) || c1 < 0.0 || c1 > (double)(RD_OCC_IN - 1))) {
-          const double f0 = floor(c0), f1 = floor(c1);
+        bool ambiguous = false;
+        const bool inside = !(c0 < 0.0 || c0 > (double)(RD_OCC_IN - 1) || c1 < 0.0 || c1 > (double)(RD_OCC_IN - 1));
+        const double f0 = floor(c0), f1 = floor(c1);
+        const int i0 = inside ? (int)f0 : 0, i1 = inside ? (int)f1 : 0;
+        const uint32_t u = inside ? (uint32_t)uni[(i0 >> 3) * OCC_NB + (i1 >> 3)] : 0u;
+        if (u != 2u) {
+          val = u;                                                   // constant neighbourhood (or outside the crop: 0)
+        } else {
           const float y0 = (float)(c0 - f0), y1 = (float)(c1 - f1);
           const float z0 = 1.0f - y0, z1 = 1.0f - y1;
           const float y02 = y0 * y0, z02 = z0 * z0, y12 = y1 * y1, z12 = z1 * z1;
@@ -333,7 +412,7 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
           w1[0] = z12 * z1 * (1.0f / 6.0f);
           w1[3] = y12 * y1 * (1.0f / 6.0f);
           // taps rows f0-1..f0+2 -> padded rows f0..f0+3; same for columns
-          const float* base = coef + (int)f0 * OCC_PITCH + (int)f1;
+          const float* base = coef + i0 * OCC_PITCH + i1;
           float v = 0.0f;
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
@@ -348,27 +427,22 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
           const float k = floorf(t);
           const float d = t - k;
           val = t >= 1.0f ? (uint32_t)fminf(k, 3.0f) : 0u;      // (uint8)(v + 0.5) for v > 0, else 0; provably <= 3
-          if ((d < eps || d > 1.0f - eps) && t > 0.5f) {  // too close to a rounding threshold for float32
-            const int slot_a = atomicAdd(&amb_count, 1);
-            amb[slot_a] = (uint16_t)pix;
-          }
+          ambiguous = (d < eps || d > 1.0f - eps) && t > 0.5f;    // too close to a rounding threshold for float32
         }
+        // float64 re-evaluation of the (rare) ambiguous pixels, one after the other, by the whole warp
+        for (uint32_t todo = __ballot_sync(0xffffffffu, ambiguous); todo; todo &= todo - 1u) {
+          const int src = __ffs(todo) - 1;
+          const uint32_t exact = occ_exact_pixel(rc, __shfl_sync(0xffffffffu, a, src), __shfl_sync(0xffffffffu, b, src), xb, hband);
+          if (lane == src) val = exact > 3u ? 3u : exact;
+        }
+        // tile row i (8 pixels) is one byte of the row-major bit planes
         const uint32_t b0 = __ballot_sync(0xffffffffu, val & 1u), b1 = __ballot_sync(0xffffffffu, val & 2u);
-        if (lane == 0) {
-          planes[pix >> 5] = b0;
-          planes[(n_pix >> 5) + (pix >> 5)] = b1;
-          if (b1) any_hi = 1;
+        if ((lane & 7) == 0) {
+          const int byte = (a * RD_OCC_MID + tx * 8) >> 3;
+          plane0[byte] = (uint8_t)(b0 >> (lane & 24));
+          plane1[byte] = (uint8_t)(b1 >> (lane & 24));
         }
-      }
-      if ((round % OCC_AMB_ROUNDS) == OCC_AMB_ROUNDS - 1 || round == n_rounds - 1) {
-        __syncthreads();
-        const int n_amb = amb_count;
-        __syncthreads();                   // everyone has read the count before anyone can add to it again
-        if (n_amb > 0) {
-          for (int e = 0; e < n_amb; ++e) occ_exact_pixel(rc, (int)amb[e], xb, hband, T, planes);
-          if (tid == 0) amb_count = 0;
-          __syncthreads();
-        }
+        if (lane == 0 && b1) any_hi = 1;
       }
     }
     __syncthreads();

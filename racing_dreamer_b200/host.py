@@ -1,136 +1,89 @@
 """HostSteppedEnv -- the env step for callers whose actions and observations live in HOST memory.
 
 This is the call a reference user makes: numpy actions in, numpy observation dict out
-[REF dreamer/tools.py:178-195 simulate(): obs = env.step(actions) with numpy arrays].  The batch is split into
-`n_shards` independent BatchedRaceEnv handles, each on its own CUDA stream, so that the device->host copy of shard k's
-observations overlaps with the kernels of the other shards.  Pinned staging buffers are allocated once.  Shards keep global env ids (env_id_offset), so results are identical
-to one big batch.
+[REF dreamer/tools.py:178-195 simulate(): obs = env.step(actions) with numpy arrays].  It is a thin wrapper over the
+C ABI's host-facing entry points (include/rd_env.h: rd_host_init / rd_reset_host / rd_step_host): the library owns the
+device result buffers and their pinned host mirrors, copies the actions in, runs k_step once over the batch, then the
+observation kernels chunk by chunk on internal streams so that chunk k's device->host copy overlaps chunk k+1's ray
+casting, and returns when every result is in host memory.  The arrays handed back are zero-copy numpy views of the
+pinned mirrors (valid until the next call).
 """
 from __future__ import annotations
 
-import dataclasses
-from typing import Dict, List, Optional
+import ctypes as C
+from typing import Dict, Optional
 
 import numpy as np
 import torch
 
+from . import _abi
 from .env import BatchedRaceEnv, EnvConfig
 
 _OUT_KEYS = ("lidar", "occupancy", "pose", "velocity", "speed", "reward", "done", "progress", "lap", "time", "flags")
+_FIELDS = {"lidar": ("lidar_dev", np.float32), "occupancy": ("occupancy_dev", np.uint8), "pose": ("pose_dev", np.float32),
+           "velocity": ("velocity_dev", np.float32), "speed": ("speed_dev", np.float32), "reward": ("reward_dev", np.float32),
+           "done": ("done_dev", np.uint8), "progress": ("progress_dev", np.float32), "lap": ("lap_dev", np.int32),
+           "time": ("time_dev", np.float32), "flags": ("flags_dev", np.uint8)}
 
 
 class HostSteppedEnv:
-    """See module docstring.  Device results live in ONE key-major allocation per key for the whole batch; each shard's
-    kernels write their slice of it.  Per step the host issues one H2D copy (all actions), per shard two kernels and one
-    D2H copy of its LiDAR rows (plus its occupancy rows), and one D2H copy of the slab that holds every small array."""
-
-    _BIG = ("lidar", "occupancy")
-
-    def __init__(self, config: EnvConfig, device=None, n_shards: int = 4, copy_back=_OUT_KEYS):
-        n = int(config.n_envs)
-        n_shards = max(1, min(int(n_shards), n))
-        bounds = np.linspace(0, n, n_shards + 1).astype(np.int64)
-        self.n = n
-        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
-        ntr = len(config.tracks)
-        all_ids = np.asarray(config.map_ids, np.int32) if config.map_ids is not None else (np.arange(n) % ntr).astype(np.int32)
-        occ = config.obs_type == "lidar_occupancy"
-        nb = int(config.n_beams)
-        # ---- device + pinned host storage, key-major over the whole batch ----
-        self.dev: Dict[str, torch.Tensor] = {}
-        self.host: Dict[str, torch.Tensor] = {}
-        small = [(k, sh, dt) for k, sh, dt in BatchedRaceEnv.OUT_SPEC if k not in self._BIG]
-        offs, total = {}, 0
-        for k, sh, dt in small:
-            nbytes = n * int(np.prod(sh, dtype=np.int64)) * torch.empty((), dtype=dt).element_size()
-            offs[k] = (total, nbytes)
-            total = (total + nbytes + 255) & ~255
-        self._small_dev = torch.zeros(total, dtype=torch.uint8, device=self.device)
-        self._small_host = torch.zeros(total, dtype=torch.uint8, pin_memory=True)
-        for k, sh, dt in small:
-            o, nbytes = offs[k]
-            self.dev[k] = self._small_dev[o:o + nbytes].view(dt).view((n,) + tuple(sh))
-            self.host[k] = self._small_host[o:o + nbytes].view(dt).view((n,) + tuple(sh))
-        self.dev["lidar"] = torch.zeros((n, nb), dtype=torch.float32, device=self.device)
-        self.host["lidar"] = torch.zeros((n, nb), dtype=torch.float32, pin_memory=True)
-        if occ:
-            self.dev["occupancy"] = torch.zeros((n, 64, 64, 1), dtype=torch.uint8, device=self.device)
-            self.host["occupancy"] = torch.zeros((n, 64, 64, 1), dtype=torch.uint8, pin_memory=True)
-        self.copy_back = tuple(k for k in copy_back if k in self.host)
-        self._copy_small = any(k not in self._BIG for k in self.copy_back)
-        self._big_keys = tuple(k for k in self._BIG if k in self.copy_back)
-        # ---- shards ----
-        self.shards: List[BatchedRaceEnv] = []
-        self.slices = []
-        for k in range(n_shards):
-            a, b = int(bounds[k]), int(bounds[k + 1])
-            ec = dataclasses.replace(config, n_envs=b - a, env_id_offset=int(config.env_id_offset) + a,
-                                     map_ids=all_ids[a:b].tolist())
-            bufs = {key: t[a:b] for key, t in self.dev.items()}
-            self.shards.append(BatchedRaceEnv(ec, device=self.device, out_buffers=bufs))
-            self.slices.append(slice(a, b))
-        self.streams = [torch.cuda.Stream(device=self.device) for _ in self.shards]
-        self._ev_act = torch.cuda.Event()
-        self._ev_done = [torch.cuda.Event() for _ in self.shards]
-        self.host_np = {k: self.host[k].numpy() for k in self.copy_back}
-        self.actions_pinned = torch.empty((n, 2), dtype=torch.float32, pin_memory=True)
-        self.actions_dev = torch.empty((n, 2), dtype=torch.float32, device=self.device)
+    def __init__(self, config: EnvConfig, device=None, n_shards: int = 8):
+        """n_shards: env-chunks the observation kernels and their device->host copies are pipelined over."""
+        self.env = BatchedRaceEnv(config, device=device)
+        self.n = self.env.n
+        self.device = self.env.device
+        self.lib = self.env.lib
+        ho = _abi.RdOutputs()
+        with torch.cuda.device(self.device):
+            self.env._check(self.lib.rd_host_init(self.env._handle, int(n_shards), C.byref(ho)))
+        n, nb = self.n, self.env.n_beams
+        shapes = {"lidar": (n, nb), "occupancy": (n, 64, 64, 1), "pose": (n, 6), "velocity": (n, 6)}
+        self.host_np: Dict[str, np.ndarray] = {}
+        for key in _OUT_KEYS:
+            field, dt = _FIELDS[key]
+            ptr = getattr(ho, field)
+            if not ptr:
+                continue
+            shape = shapes.get(key, (n,))
+            nbytes = int(np.prod(shape)) * np.dtype(dt).itemsize
+            buf = (C.c_char * nbytes).from_address(ptr)
+            self.host_np[key] = np.frombuffer(buf, dtype=dt).reshape(shape)
+        self.n_shards = max(1, min(int(n_shards), n))
         self.h2d_bytes_per_step = n * 2 * 4
-        self.d2h_bytes_per_step = int(sum(self.host[k].numel() * self.host[k].element_size() for k in self._big_keys)
-                                      + (self._small_host.numel() if self._copy_small else 0))
+        self.d2h_bytes_per_step = int(sum(v.nbytes for v in self.host_np.values()))
 
-    # ------------------------------------------------------------------
-    def _run(self, launch) -> Dict[str, np.ndarray]:
-        """launch(k, env): enqueue shard k's kernels on the current stream."""
-        for k, env in enumerate(self.shards):
-            st = self.streams[k]
-            with torch.cuda.stream(st):
-                if k > 0:
-                    st.wait_event(self._ev_act)
-                launch(k, env)
-                sl = self.slices[k]
-                for key in self._big_keys:
-                    self.host[key][sl].copy_(self.dev[key][sl], non_blocking=True)
-                if k > 0:
-                    self._ev_done[k].record(st)
-        st0 = self.streams[0]
-        with torch.cuda.stream(st0):
-            for k in range(1, len(self.shards)):
-                st0.wait_event(self._ev_done[k])
-            if self._copy_small:
-                self._small_host.copy_(self._small_dev, non_blocking=True)
-        st0.synchronize()
+    def reset(self, mask: Optional[np.ndarray] = None, mode: Optional[str] = None) -> Dict[str, np.ndarray]:
+        m = _abi.RESET_MODES[mode] if mode is not None else int(self.env.cfg.reset_mode)
+        mp = None
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.uint8)
+            if mask.shape != (self.n,):
+                raise ValueError("mask must have shape (n_envs,)")
+            mp = mask.ctypes.data
+        with torch.cuda.device(self.device):
+            self.env._check(self.lib.rd_reset_host(self.env._handle, mp, m))
         return self.host_np
-
-    def reset(self, mode: Optional[str] = None) -> Dict[str, np.ndarray]:
-        with torch.cuda.stream(self.streams[0]):
-            self._ev_act.record(self.streams[0])
-        return self._run(lambda k, env: env.reset(mode=mode))
 
     def step(self, actions: np.ndarray) -> Dict[str, np.ndarray]:
         """actions: float32 [n_envs, 2] in host memory.  Returns numpy views of the pinned result buffers
         (valid until the next call): lidar, pose, velocity, speed, reward, done, progress, lap, time, flags
         (+ occupancy for obs_type='lidar_occupancy')."""
-        self.actions_pinned.numpy()[...] = actions
-        st0 = self.streams[0]
-        with torch.cuda.stream(st0):
-            self.actions_dev.copy_(self.actions_pinned, non_blocking=True)
-            self._ev_act.record(st0)
-        base = self.actions_dev.data_ptr()
-        return self._run(lambda k, env: env.step_raw(base + self.slices[k].start * 8))
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        if a.shape != (self.n, 2):
+            raise ValueError(f"actions must have shape ({self.n}, 2), got {a.shape}")
+        self.env._check(self.lib.rd_step_host(self.env._handle, a.ctypes.data))
+        return self.host_np
 
     @property
     def launch_count(self) -> int:
-        return sum(e.launch_count for e in self.shards)
+        return self.env.launch_count
+
+    @property
+    def shards(self):
+        return range(self.n_shards)
 
     def read_stats(self, reset: bool = False) -> Dict[str, float]:
-        tot: Dict[str, float] = {}
-        for k, e in enumerate(self.shards):
-            with torch.cuda.stream(self.streams[k]):
-                for key, v in e.read_stats(reset).items():
-                    tot[key] = tot.get(key, 0.0) + v
-        return tot
+        return self.env.read_stats(reset)
 
     def close(self):
-        for e in self.shards:
-            e.close()
+        self.env.close()
