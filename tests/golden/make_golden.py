@@ -154,8 +154,48 @@ def baselines_stack_golden(n_steps=400, repeat=4):
     print("baselines_stack_golden: episodes", int(np.sum(rec["done"])))
 
 
+def episodes_golden(n_steps=160, action_repeat=4, duration=45):
+    """Episode store wire format: what the reference's Collect wrapper hands to callbacks.save_episodes
+    [REF dreamer/wrappers.py:198-250; dreamer/callbacks.py:41-53], captured through a callback on the unmodified
+    wrapper stack (Treitlstrasse, reset 'grid', random actions -> collisions and a few time-limit episodes)."""
+    from oracle import ref_env
+    W = ref_stubs.reference_wrappers()
+    tm = load_track("treitlstrasse_v2")
+    captured = []
+    env = ref_env.OracleRaceEnv(tm)
+    env = W.RaceCarWrapper(env, agent_id="A")
+    env = W.ActionRepeat(env, action_repeat)
+    env = W.ReduceActionSpace(env, low=[0.005, -1.0], high=[1.0, 1.0])
+    env = W.OccupancyMapObs(env)
+    env = W.FixedResetMode(env, "grid")
+    env = W.TimeLimit(env, duration)
+    env = W.Collect(env, callbacks=[lambda eps: captured.append({k: np.array(v) for k, v in eps[0].items()})], precision=32)
+    actions = np.random.RandomState(9).uniform(-1, 1, (n_steps, 2)).astype(np.float32)
+    actions[:, 1] = actions[:, 1] * 0.6 + 0.25      # biased steering: some episodes end in the wall, some at the limit
+    reset_before, need_reset = [], True
+    for t in range(n_steps):
+        reset_before.append(need_reset)
+        if need_reset:
+            env.reset()
+        _, _, done, _ = env.step({"A": actions[t]})
+        need_reset = bool(done["A"])
+    keys = sorted(captured[0])
+    out = {"actions": actions, "reset_before": np.asarray(reset_before), "action_repeat": action_repeat,
+           "duration": duration, "n_episodes": len(captured), "keys": np.array(keys)}
+    for i, ep in enumerate(captured):
+        for k in keys:
+            v = ep[k]
+            if k == "lidar_occupancy":
+                v = np.packbits(v[..., 0], axis=2)
+            out[f"ep{i}_{k}"] = v
+    np.savez_compressed(OUT / "episodes_golden.npz", **out)
+    print("episodes_golden:", len(captured), "episodes, lengths", [len(e["reward"]) for e in captured], "keys", keys,
+          "dtypes", {k: str(captured[0][k].dtype) for k in keys})
+
+
 if __name__ == "__main__":
     assert ref_stubs.available(), "/root/reference is required to regenerate the golden fixtures"
     occupancy_golden()
     dreamer_stack_golden()
     baselines_stack_golden()
+    episodes_golden()

@@ -86,3 +86,46 @@ def assert_matches_baselines_golden(rec, g, float_tol=0.0, lidar_tol=0.0):
         else:
             assert np.all(np.abs(a - b) <= float_tol * np.maximum(1.0, np.abs(b))), k
     assert np.abs(rec["lidar"].sum(1, dtype=np.float64) - g["lidar_sum"]).max() <= lidar_tol * 1080
+
+
+class OracleHostEnv:
+    """The CPU oracle behind the host-facing env interface (reset(mask, mode) / step(actions) -> dict of numpy arrays),
+    so that host-side logic written for HostSteppedEnv (e.g. the episode recorder) can be tested without a GPU."""
+
+    def __init__(self, cfg, tracks, map_ids=None, n_threads=1):
+        from oracle import Oracle
+        self.orc = Oracle(cfg, tracks, map_ids, n_threads=n_threads)
+        self.cfg = self.orc.cfg
+        self.n = self.orc.n
+
+    def _out(self, out):
+        d = {k: v for k, v in out.items() if v is not None and k != "reward64"}
+        if "occupancy" in d:
+            d["occupancy"] = d["occupancy"][..., None]
+        return d
+
+    def reset(self, mask=None, mode=None):
+        m = _abi.RESET_MODES[mode] if mode is not None else int(self.cfg.reset_mode)
+        return self._out(self.orc.reset(mask=mask, mode=m))
+
+    def step(self, actions):
+        return self._out(self.orc.step(actions))
+
+
+def assert_episodes_match_golden(episodes, g, tol=1e-6, lidar_tol=1e-3):
+    """episodes: list of dicts as handed to Collect's callbacks; g: tests/golden/episodes_golden.npz."""
+    assert len(episodes) == int(g["n_episodes"])
+    keys = [str(k) for k in g["keys"]]
+    for i, ep in enumerate(episodes):
+        assert sorted(ep) == keys, (sorted(ep), keys)
+        for k in keys:
+            want = g[f"ep{i}_{k}"]
+            got = ep[k]
+            if k == "lidar_occupancy":
+                assert got.dtype == np.uint8 and got.shape[1:] == (64, 64, 1)
+                assert np.array_equal(np.packbits(got[..., 0], axis=2), want), f"episode {i} {k}"
+                continue
+            assert got.dtype == want.dtype and got.shape == want.shape, f"episode {i} {k}: {got.dtype}{got.shape} vs {want.dtype}{want.shape}"
+            t = lidar_tol if k == "lidar" else tol
+            d = np.abs(got.astype(np.float64) - want.astype(np.float64))
+            assert np.all(d <= t * np.maximum(1.0, np.abs(want))), f"episode {i} {k}: max diff {d.max()}"

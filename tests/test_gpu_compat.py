@@ -124,3 +124,23 @@ def test_host_stepped_env_equals_batched(torch_cuda, obs_type, n_shards):
     assert s_ref["episodes"] == s_host["episodes"] and s_ref["env_steps"] == s_host["env_steps"] == n * 12
     ref.close()
     host.close()
+
+
+def test_episode_recorder_on_gpu_matches_reference_collect(torch_cuda, golden_dir, tmp_path):
+    """episodes recorded from the CUDA env == the ones the reference's Collect wrapper produced."""
+    from racing_dreamer_b200 import EnvConfig
+    from racing_dreamer_b200.episodes import EpisodeRecorder, count_episodes, save_episodes
+    from racing_dreamer_b200.host import HostSteppedEnv
+    g = np.load(golden_dir / "episodes_golden.npz")
+    ec = EnvConfig(tracks=("treitlstrasse_v2",), n_envs=1, action_repeat=int(g["action_repeat"]), obs_type="lidar_occupancy",
+                   auto_reset=False, reset_mode="grid", time_limit_steps=int(g["duration"]))
+    env = HostSteppedEnv(ec, device="cuda:0", n_shards=1)
+    captured = []
+    rec = EpisodeRecorder(env, max_len=int(g["duration"]), reset_mode="grid",
+                          callbacks=[lambda eps: captured.append(eps[0]), lambda eps: save_episodes(tmp_path, eps)])
+    rec.reset()
+    for t in range(g["actions"].shape[0]):
+        rec.step(g["actions"][t:t + 1])
+    helpers.assert_episodes_match_golden(captured, g, tol=1e-5, lidar_tol=1e-3)
+    assert count_episodes(tmp_path)[0] == int(g["n_episodes"])
+    env.close()
