@@ -135,6 +135,19 @@ def measured_peak_gbs():
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
+def ncu_traffic(config_id, n_envs, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/ncu_traffic.json), or None when no
+    capture matches this workload."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
+            ent = json.load(f).get(f"config{config_id}", {}).get(kernel)
+        if ent and int(ent["envs"]) == int(n_envs):
+            return int(ent["dram_read_bytes"]) + int(ent["dram_write_bytes"])
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 def cpu_oracle_run(n_envs, steps, warmup, threads, rank=0, obs="lidar"):
     """Times the oracle port on `threads` host threads: `steps` env.step() calls of `n_envs` envs."""
     from oracle import Oracle
@@ -326,7 +339,7 @@ def main():
             "ms_per_step_back_to_back": b2b_ms_max / args.steps,
             "wall_s_timed_region": wall,
             "roofline": {"bound": "hbm", "kernel": "k_lidar", "achieved": lidar_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": lidar_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": lidar_gbs / peak, "traffic": ncu_traffic(args.config, n, "k_lidar"), "peak_source": peak_src,
                          "kernel_ms": lidar_ms, "kernel_share_of_step": timing["lidar_ms"] / max(gpu_ms, 1e-9),
                          "algorithmic_bytes_per_launch": LIDAR_BYTES_PER_ENV * n,
                          "step_algorithmic_gbs": ALGO_BYTES_PER_ENV_STEP * value / world / 1e9,
