@@ -176,6 +176,51 @@ int rd_host_init(rd_env* env, int n_chunks, rd_outputs* host_out);
 int rd_reset_host(rd_env* env, const uint8_t* mask_host, int mode);
 int rd_step_host(rd_env* env, const float* actions_host);
 
+/* ---- on-device policies (policy-in-the-loop rollouts without a host round trip) ----
+ * Follow-the-gap controller: replaces AgentNode.laserscan_callback + publish_drive_from_heading + PID.calculate
+ * [REF ros_agent/agents/follow_the_gap/src/agent.py:128-193, 200-238, 45-55], one controller per env, state kept by
+ * the handle and cleared whenever the env is reset (rd_reset, auto-reset inside rd_step).  The env's `lidar` row
+ * (index 0 = left) is read in ROS order (index 0 = angle_min = -fov/2), i.e. reversed
+ * [REF ros_agent/agents/dreamer/src/agent.py:65 np.flip]. */
+typedef struct rd_gap_follower {
+  /* controller constants [REF agent.py:73-104] */
+  double lookahead;            /* 2 * max_speed^2 / (2 * max_decel) */
+  double vehicle_width;        /* 0.3302 * 1.2 */
+  double minimum_gap_length;   /* 0.2 m */
+  double median_dev_threshold; /* 9.0 */
+  double kp, ki, kd;           /* 1.4, 0.0, 0.1 */
+  double max_vehicle_speed;    /* 6.0 */
+  double max_steering_angle;   /* deg2rad(24) */
+  double speed_limit_angle;    /* deg2rad(5) */
+  double scan_dt;              /* seconds between scans = action_repeat * dt */
+  /* scan geometry, derived the way the reference derives it from the LaserScan message */
+  double angle_min, angle_increment, range_max;
+  double pct_gamma;            /* np.percentile(q): fractional part of the virtual index */
+  int32_t arc_first, arc_last; /* get_lidar_scan_arc(-90 deg, +90 deg) [REF agent.py:117-126], ROS order */
+  int32_t filter_width;        /* int(deg2rad(10) / angle_increment) */
+  int32_t pct_lo, pct_hi;      /* np.percentile(q): the two order statistics that are interpolated */
+  int32_t reserved;
+  /* drive command -> env action [NEW-SPEC: the reference publishes (steering_angle, speed) to a VESC]:
+   * steering = steering_angle / (steer_gain * steer_max); motor = v*.c_drag/a_drive + speed_gain * (v* - v) with
+   * v* = speed * speed_scale, both clipped to the sim-facing action range, then mapped back to the agent-facing
+   * [-1, 1] when cfg.rescale_actions. */
+  double speed_scale, speed_gain;
+} rd_gap_follower;
+
+/* Fills `g` with the reference node's constants and the geometry of `cfg`'s LiDAR. */
+void rd_gap_follower_defaults(const rd_config* cfg, rd_gap_follower* g);
+/* Allocates the per-env controller state (idempotent; replaces the parameters on a second call). */
+int rd_policy_gap_follower_init(rd_env* env, const rd_gap_follower* g_or_null);
+/* One controller update per env: lidar_dev f32 [N, n_beams] metres (an rd_step/rd_reset output), speed_dev f32 [N]
+ * longitudinal speed or NULL (= the env's own state), actions_dev f32 [N,2] agent-facing (what rd_step takes),
+ * debug_dev f64 [N,4] = (steering_angle, vehicle_speed, heading, heading_distance) or NULL. */
+int rd_policy_gap_follower(rd_env* env, const float* lidar_dev, const float* speed_dev, float* actions_dev,
+                           double* debug_dev, void* stream);
+/* n_steps x (controller update -> rd_step) enqueued on `stream` with no host synchronisation; `out->lidar_dev` must
+ * hold the current observation (rd_reset / previous rd_step with the same `out`).  The actions of the last step are
+ * left in actions_dev (f32 [N,2], may be NULL). */
+int rd_rollout_gap_follower(rd_env* env, int n_steps, const rd_outputs* out, float* actions_dev, void* stream);
+
 /* ---- stage entry points (teacher-forced parity tests; each is one kernel of the step) ---- */
 /* a2 LiDAR [REF dreamer/scenarios/max_progress/austria.yml:7 'lidar' sensor]: poses f64 [n,3]=(x,y,yaw),
  * map_ids i32[n] sorted ascending or NULL (= map 0), ranges f32 [n, n_beams]. */
@@ -203,6 +248,8 @@ int64_t rd_launch_count(const rd_env* env);
 typedef struct rd_timing {
   double step_ms, lidar_ms, occupancy_ms, reset_ms;
   int64_t step_launches, lidar_launches, occupancy_launches, reset_launches;
+  double policy_ms;
+  int64_t policy_launches;
 } rd_timing;
 int rd_enable_timing(rd_env* env, int enable);
 int rd_read_timing(rd_env* env, rd_timing* out_host, int reset);

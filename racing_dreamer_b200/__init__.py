@@ -17,4 +17,7 @@ def __getattr__(name):
     if name in ("RaceCarGymCompat", "ReferenceEnv", "make_reference_env", "load_scenario"):
         from . import compat as _compat
         return getattr(_compat, name)
+    if name == "GapFollowerPolicy":
+        from . import policy as _policy
+        return _policy.GapFollowerPolicy
     raise AttributeError(name)

@@ -76,7 +76,21 @@ class RdStats(C.Structure):
 class RdTiming(C.Structure):
     _fields_ = [("step_ms", C.c_double), ("lidar_ms", C.c_double), ("occupancy_ms", C.c_double),
                 ("reset_ms", C.c_double), ("step_launches", C.c_int64), ("lidar_launches", C.c_int64),
-                ("occupancy_launches", C.c_int64), ("reset_launches", C.c_int64)]
+                ("occupancy_launches", C.c_int64), ("reset_launches", C.c_int64),
+                ("policy_ms", C.c_double), ("policy_launches", C.c_int64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class RdGapFollower(C.Structure):
+    """rd_gap_follower (include/rd_env.h): the follow-the-gap controller's constants + scan geometry."""
+    _fields_ = [(n, C.c_double) for n in (
+        "lookahead", "vehicle_width", "minimum_gap_length", "median_dev_threshold", "kp", "ki", "kd",
+        "max_vehicle_speed", "max_steering_angle", "speed_limit_angle", "scan_dt",
+        "angle_min", "angle_increment", "range_max", "pct_gamma")] + [(n, C.c_int32) for n in (
+        "arc_first", "arc_last", "filter_width", "pct_lo", "pct_hi", "reserved")] + [
+        ("speed_scale", C.c_double), ("speed_gain", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -87,6 +101,7 @@ EXPORTS = (
     "rd_assign_maps", "rd_reset", "rd_step", "rd_lidar_cast", "rd_occupancy_obs", "rd_dynamics",
     "rd_get_state", "rd_set_state", "rd_read_stats", "rd_launch_count", "rd_enable_timing", "rd_read_timing",
     "rd_host_init", "rd_reset_host", "rd_step_host",
+    "rd_gap_follower_defaults", "rd_policy_gap_follower_init", "rd_policy_gap_follower", "rd_rollout_gap_follower",
 )
 
 LIB_PATH = Path(__file__).resolve().parent / "librd_env.so"
@@ -155,6 +170,14 @@ def load_library() -> C.CDLL:
     lib.rd_enable_timing.restype = i32
     lib.rd_read_timing.argtypes = [vp, C.POINTER(RdTiming), i32]
     lib.rd_read_timing.restype = i32
+    lib.rd_gap_follower_defaults.argtypes = [C.POINTER(RdConfig), C.POINTER(RdGapFollower)]
+    lib.rd_gap_follower_defaults.restype = None
+    lib.rd_policy_gap_follower_init.argtypes = [vp, C.POINTER(RdGapFollower)]
+    lib.rd_policy_gap_follower_init.restype = i32
+    lib.rd_policy_gap_follower.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.rd_policy_gap_follower.restype = i32
+    lib.rd_rollout_gap_follower.argtypes = [vp, i32, C.POINTER(RdOutputs), vp, vp]
+    lib.rd_rollout_gap_follower.restype = i32
     if lib.rd_abi_version() != ABI_VERSION:
         raise NativeLibraryError(f"{path}: ABI version {lib.rd_abi_version()} != {ABI_VERSION}")
     _lib = lib

@@ -13,6 +13,7 @@
 #pragma once
 #include "rd_common.cuh"
 #include "rd_lidar.cuh"
+#include "rd_policy.cuh"
 
 struct StepParams {
   rd_config cfg;
@@ -21,6 +22,7 @@ struct StepParams {
   double* stats;    // [8] accumulators (rd_stats order)
   OriginRec* recs;  // [n]
   const DevMap* maps;
+  PolicyState pol;  // on-device controller state, cleared with the env (null pointers: no policy attached)
   int n;
 };
 
@@ -192,6 +194,7 @@ __device__ __forceinline__ void rd_reset_one(const StepParams& P, int e, int mod
   I[(size_t)RD_I_FLAGS * n + e] = 0;
   I[(size_t)RD_I_AGENT_STEP * n + e] = 0;
   I[(size_t)RD_I_EPISODE * n + e] = (int32_t)(episode + 1u);
+  if (P.pol.i32) rd_policy_clear(P.pol, n, e);
 }
 
 // observation scalars + the origin record for the LiDAR / occupancy kernels, from the committed state

@@ -19,6 +19,7 @@
 #include "rd_dynamics.cuh"
 #include "rd_lidar.cuh"
 #include "rd_occupancy.cuh"
+#include "rd_policy.cuh"
 
 #define RD_API extern "C" __attribute__((visibility("default")))
 
@@ -80,6 +81,13 @@ struct rd_env {
     bool zero_copy = false;                  // k_lidar stores straight into the pinned host mirror (no staging copy)
     rd_outputs dev_out{}, host_out{};
   } hp;
+  // on-device follow-the-gap controller (rd_policy_gap_follower_init)
+  struct Policy {
+    bool ready = false;
+    rd_gap_follower g{};
+    PolicyState st{};
+    float* d_actions = nullptr;   // [n][2] rollout scratch
+  } pol;
   // optional per-kernel timing (rd_enable_timing)
   bool timing = false;
   struct Timed { cudaEvent_t a, b; int kind; };
@@ -163,7 +171,7 @@ int sync_maps(rd_env* env) {
   return RD_OK;
 }
 
-enum { T_STEP = 0, T_LIDAR = 1, T_OCC = 2, T_RESET = 3 };
+enum { T_STEP = 0, T_LIDAR = 1, T_OCC = 2, T_RESET = 3, T_POLICY = 4 };
 
 cudaEvent_t take_event(rd_env* env) {
   if (!env->event_pool.empty()) { cudaEvent_t e = env->event_pool.back(); env->event_pool.pop_back(); return e; }
@@ -265,6 +273,7 @@ StepParams step_params(rd_env* env) {
   StepParams P{};
   P.cfg = env->cfg;
   P.f64 = env->d_f64; P.i32 = env->d_i32; P.stats = env->d_stats; P.recs = env->d_recs; P.maps = env->d_maps;
+  P.pol = env->pol.st;
   P.n = env->n;
   return P;
 }
@@ -389,6 +398,7 @@ RD_API void rd_destroy(rd_env* env) {
   cudaFree(env->d_f64); cudaFree(env->d_i32); cudaFree(env->d_stats); cudaFree(env->d_recs);
   cudaFree(env->d_beam_tab); cudaFree(env->d_maps); cudaFree(env->d_env_order); cudaFree(env->d_lidar_ctr);
   cudaFree(env->d_stage_recs); cudaFree(env->d_stage_ids);
+  cudaFree(env->pol.st.f64); cudaFree(env->pol.st.i32); cudaFree(env->pol.d_actions);
   occ_free(env->occ);
   {
     auto& h = env->hp;
@@ -685,6 +695,123 @@ RD_API int rd_step_host(rd_env* env, const float* actions_host) {
   return host_finish(env, small_copied);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// on-device policies
+RD_API void rd_gap_follower_defaults(const rd_config* cfg, rd_gap_follower* g) {
+  if (!cfg || !g) return;
+  std::memset(g, 0, sizeof(*g));
+  const double deg = 3.14159265358979323846 / 180.0;
+  // constants of the node [REF ros_agent/agents/follow_the_gap/src/agent.py:73-104]
+  const double max_speed = 7.0, max_decel = 8.26;
+  g->lookahead = 2.0 * ((max_speed * max_speed) / (2.0 * max_decel));
+  g->vehicle_width = 0.3302 * 1.2;
+  g->minimum_gap_length = 0.2;
+  g->median_dev_threshold = 9.0;
+  g->kp = 1.4; g->ki = 0.0; g->kd = 0.1;
+  g->max_vehicle_speed = 6.0;
+  g->max_steering_angle = 24.0 * deg;
+  g->speed_limit_angle = 5.0 * deg;
+  g->scan_dt = (double)cfg->action_repeat * cfg->dt;
+  // the scan as a LaserScan message: angle_min = -fov/2, increment = fov/(n-1) [REF dreamer/tools.py:84-86]
+  g->angle_min = -0.5 * cfg->lidar_fov;
+  g->angle_increment = cfg->n_beams > 1 ? cfg->lidar_fov / (double)(cfg->n_beams - 1) : 1.0;
+  g->range_max = cfg->lidar_range_max;
+  // get_lidar_scan_arc(-90 deg, +90 deg): int((angle - angle_min) / increment) [REF agent.py:117-126]
+  const double a0 = -90.0 * deg, a1 = 90.0 * deg;
+  g->arc_first = (int32_t)((a0 - g->angle_min) / g->angle_increment);
+  g->arc_last = (int32_t)((a1 - g->angle_min) / g->angle_increment);
+  g->filter_width = (int32_t)((10.0 * deg) / g->angle_increment);
+  // np.percentile(adjusted, q = 100 * (1 - deg2rad(30) / (a1 - a0))), method 'linear'
+  const double q = 100.0 * (1.0 - ((30.0 * deg) / (a1 - a0)));
+  const double quant = q / 100.0;
+  const int m = g->arc_last - g->arc_first + 1;
+  const double vi = (double)m * quant + (1.0 + quant * (1.0 - 1.0 - 1.0)) - 1.0;
+  int lo = (int)std::floor(vi);
+  g->pct_gamma = vi - (double)lo;
+  g->pct_lo = std::min(std::max(lo, 0), m - 1);
+  g->pct_hi = std::min(std::max(lo + 1, 0), m - 1);
+  g->speed_scale = 0.5;
+  g->speed_gain = 1.0;
+}
+
+RD_API int rd_policy_gap_follower_init(rd_env* env, const rd_gap_follower* g_or_null) {
+  if (!env) return fail(nullptr, RD_ERR_INVALID, "null handle");
+  rd_gap_follower g;
+  if (g_or_null) g = *g_or_null; else rd_gap_follower_defaults(&env->cfg, &g);
+  const int m = g.arc_last - g.arc_first + 1;
+  if (g.arc_first < 0 || g.arc_last >= env->cfg.n_beams || m < 8 || g.filter_width < 1 || 2 * g.filter_width >= m ||
+      g.pct_lo < 0 || g.pct_hi < g.pct_lo || g.pct_hi >= m || !(g.scan_dt > 0.0) || !(g.angle_increment > 0.0))
+    return fail(env, RD_ERR_INVALID, "bad gap-follower parameters (arc %d..%d of %d beams, filter width %d)", g.arc_first,
+                g.arc_last, env->cfg.n_beams, g.filter_width);
+  if (env->cfg.obs_flags & RD_OBS_LIDAR_NORM) return fail(env, RD_ERR_INVALID, "the gap follower reads ranges in metres (RD_OBS_LIDAR_NORM is set)");
+  auto& p = env->pol;
+  const size_t n = (size_t)env->n;
+  if (!p.st.f64) {
+    CUDA_TRY(env, cudaMalloc(&p.st.f64, sizeof(double) * RD_NP_F64 * n));
+    CUDA_TRY(env, cudaMalloc(&p.st.i32, sizeof(int32_t) * RD_NP_I32 * n));
+    CUDA_TRY(env, cudaMalloc(&p.d_actions, sizeof(float) * 2 * n));
+    CUDA_TRY(env, cudaMemset(p.d_actions, 0, sizeof(float) * 2 * n));
+  }
+  std::vector<double> f(RD_NP_F64 * n, 0.0);
+  for (size_t e = 0; e < n; ++e) f[(size_t)RD_P_PREV * n + e] = std::nan("");
+  CUDA_TRY(env, cudaMemcpy(p.st.f64, f.data(), sizeof(double) * f.size(), cudaMemcpyHostToDevice));
+  CUDA_TRY(env, cudaMemset(p.st.i32, 0, sizeof(int32_t) * RD_NP_I32 * n));
+  p.g = g;
+  p.ready = true;
+  return RD_OK;
+}
+
+namespace {
+int launch_gap_follower(rd_env* env, const float* lidar_dev, const float* speed_dev, float* actions_dev, double* debug_dev,
+                        cudaStream_t s) {
+  constexpr int WARPS = 4;
+  auto& p = env->pol;
+  GapArgs A{};
+  A.g = p.g; A.ps = p.st; A.lidar = lidar_dev; A.speed = speed_dev; A.state_v = env->d_f64 + (size_t)RD_S_V * env->n;
+  A.actions = actions_dev; A.debug = debug_dev; A.n = env->n; A.n_beams = env->cfg.n_beams;
+  const int m = p.g.arc_last - p.g.arc_first + 1;
+  A.m_pad = (m + 1) | 1;   // odd number of doubles per row: the warps' rows start in different banks
+  A.rescale = env->cfg.rescale_actions;
+  for (int k = 0; k < 2; ++k) { A.low[k] = env->cfg.action_low[k]; A.high[k] = env->cfg.action_high[k]; }
+  A.a_drive = env->cfg.vehicle.a_drive; A.c_drag = env->cfg.vehicle.c_drag;
+  A.steer_scale = env->cfg.vehicle.steer_gain * env->cfg.vehicle.steer_max;
+  const size_t smem = sizeof(double) * 2 * (size_t)A.m_pad * WARPS;
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    CUDA_TRY(env, cudaFuncSetAttribute(k_gap_follower<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_optin));
+    attr_set = true;
+  }
+  if (smem > (size_t)env->smem_optin) return fail(env, RD_ERR_INVALID, "scan arc of %d beams does not fit in shared memory", m);
+  {
+    ScopedTiming tm(env, s, T_POLICY);
+    k_gap_follower<WARPS><<<(env->n + WARPS - 1) / WARPS, WARPS * 32, smem, s>>>(A);
+  }
+  env->launches++;
+  CUDA_TRY(env, cudaGetLastError());
+  return RD_OK;
+}
+}  // namespace
+
+RD_API int rd_policy_gap_follower(rd_env* env, const float* lidar_dev, const float* speed_dev, float* actions_dev,
+                                  double* debug_dev, void* stream) {
+  if (!env || !lidar_dev || !actions_dev) return fail(env, RD_ERR_INVALID, "null argument");
+  if (!env->pol.ready) return fail(env, RD_ERR_STATE, "rd_policy_gap_follower_init has not been called");
+  return launch_gap_follower(env, lidar_dev, speed_dev, actions_dev, debug_dev, (cudaStream_t)stream);
+}
+
+RD_API int rd_rollout_gap_follower(rd_env* env, int n_steps, const rd_outputs* out, float* actions_dev, void* stream) {
+  if (!env || !out || !out->lidar_dev || n_steps < 0) return fail(env, RD_ERR_INVALID, "bad argument (the rollout needs out->lidar_dev)");
+  if (!env->pol.ready) return fail(env, RD_ERR_STATE, "rd_policy_gap_follower_init has not been called");
+  if (!env->was_reset) return fail(env, RD_ERR_STATE, "Must reset environment.");
+  float* act = actions_dev ? actions_dev : env->pol.d_actions;
+  for (int k = 0; k < n_steps; ++k) {
+    int rc = launch_gap_follower(env, out->lidar_dev, nullptr, act, nullptr, (cudaStream_t)stream);
+    if (rc) return rc;
+    if ((rc = rd_step(env, act, out, stream))) return rc;
+  }
+  return RD_OK;
+}
+
 RD_API int rd_lidar_cast(rd_env* env, const double* poses_dev, const int32_t* map_ids_host, int n, float* ranges_dev,
                          void* stream) {
   if (!env || n < 0) return fail(env, RD_ERR_INVALID, "bad argument");
@@ -790,6 +917,7 @@ RD_API int rd_read_timing(rd_env* env, rd_timing* out_host, int reset) {
       case T_STEP: env->acc.step_ms += ms; env->acc.step_launches++; break;
       case T_LIDAR: env->acc.lidar_ms += ms; env->acc.lidar_launches++; break;
       case T_OCC: env->acc.occupancy_ms += ms; env->acc.occupancy_launches++; break;
+      case T_POLICY: env->acc.policy_ms += ms; env->acc.policy_launches++; break;
       default: env->acc.reset_ms += ms; env->acc.reset_launches++; break;
     }
     env->event_pool.push_back(t.a);

@@ -13,7 +13,11 @@ committed so that the parity tests can run where /root/reference does not exist 
   baselines_stack_golden.npz  the model-free chain's action path: Flatten(clip) -> ActionRepeat(4) with the
                            baselines edge semantics [REF baselines/racing/environment/single_agent.py:31-62].
 
-usage: python tests/golden/make_golden.py
+  gap_follower_golden.npz  the UNMODIFIED follow-the-gap node [REF ros_agent/agents/follow_the_gap/src/agent.py]
+                           (rospy stubbed, oracle/ref_ftg.py) fed scan sequences of the oracle env: the drive
+                           commands it publishes (steering angle, speed, heading) per scan.
+
+usage: python tests/golden/make_golden.py [name ...]
 """
 import sys
 from pathlib import Path
@@ -193,8 +197,68 @@ def episodes_golden(n_steps=160, action_repeat=4, duration=45):
           "dtypes", {k: str(captured[0][k].dtype) for k in keys})
 
 
+def gap_follower_golden():
+    """Three scan sequences (two closed loops driven by the numpy restatement with steering noise, one of unrelated
+    random poses) -> what the reference node publishes after each scan.  Only the forward arc the node reads is stored;
+    beams outside it are zero in the reconstructed message."""
+    from oracle import Oracle, default_config
+    from oracle.gap_follower import GapFollowerOracle, GapFollowerParams
+    from oracle.ref_ftg import ReferenceGapFollower
+    from racing_dreamer_b200 import _abi
+    out = {}
+    specs = (("austria", 4, 100, "loop"), ("treitlstrasse_v2", 8, 80, "loop"), ("columbia", 4, 60, "random"))
+    for si, (track, R, n_scans, kind) in enumerate(specs):
+        tm = load_track(track)
+        cfg = default_config()
+        cfg.n_envs, cfg.action_repeat, cfg.rescale_actions = 1, R, 0
+        orc = Oracle(cfg, [tm], n_threads=1)
+        p = GapFollowerParams(dt=R * 0.01)
+        s0, s1 = p.arc()
+        ref = ReferenceGapFollower(p.angle_min, p.angle_increment, p.n_beams, p.range_max, p.dt)
+        mine = GapFollowerOracle(p)
+        rng = np.random.RandomState(100 + si)
+        scans, cmds = [], []
+        if kind == "loop":
+            o = orc.reset(mode=_abi.RESET_GRID)
+        else:
+            poses = tm.reset_poses[rng.randint(0, len(tm.reset_poses), n_scans)].copy()
+            poses[:, 2] += rng.uniform(-1.2, 1.2, n_scans)
+            poses[:, :2] += rng.uniform(-0.25, 0.25, (n_scans, 2))
+            all_scans = orc.lidar_cast(poses)
+        veh = cfg.vehicle
+        for k in range(n_scans):
+            lidar = o["lidar"][0].copy() if kind == "loop" else all_scans[k]
+            ros = lidar[::-1].astype(np.float64)
+            full = np.zeros_like(ros)
+            full[s0:s1 + 1] = ros[s0:s1 + 1]
+            pub, sa, sp, hd = ref(full)
+            m = mine(full)
+            assert m[0] == pub and max(abs(m[1] - sa), abs(m[2] - sp), abs(m[3] - hd)) < 1e-12
+            scans.append(lidar[::-1][s0:s1 + 1].astype(np.float32))
+            cmds.append((float(pub), sa, sp, hd))
+            if kind == "loop":
+                v = orc.f64[_abi.S_V, 0]
+                vt = sp * 0.5
+                motor = min(max(vt * veh.c_drag / veh.a_drive + (vt - v), 0.005), 1.0)
+                steer = min(max(sa / (veh.steer_gain * veh.steer_max) + rng.uniform(-0.5, 0.5), -1), 1)
+                o = orc.step(commands=np.array([[motor, steer]]))
+                if o["done"][0]:
+                    break
+        out[f"seq{si}_arc_ros"] = np.asarray(scans, np.float32)
+        out[f"seq{si}_cmd"] = np.asarray(cmds, np.float64)
+        out[f"seq{si}_meta"] = np.array([R, s0, s1, p.n_beams], np.int64)
+        print(f"gap_follower_golden: {track} R={R} {len(scans)} scans, published {int(sum(c[0] for c in cmds))}, "
+              f"|steer| max {max(abs(c[1]) for c in cmds):.3f}")
+    np.savez_compressed(OUT / "gap_follower_golden.npz", n_seq=len(specs), tracks=np.array([s[0] for s in specs]), **out)
+
+
 if __name__ == "__main__":
     assert ref_stubs.available(), "/root/reference is required to regenerate the golden fixtures"
+    todo = sys.argv[1:]
+    if todo:
+        for name in todo:
+            globals()[name]()
+        sys.exit(0)
     occupancy_golden()
     dreamer_stack_golden()
     baselines_stack_golden()
