@@ -208,6 +208,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (0 = the config's)")
     ap.add_argument("--obs", default="", choices=["", "lidar", "lidar_occupancy"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-closed-loop", action="store_true", help="skip the on-device policy rollout leg")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 200)")
     ap.add_argument("--e2e-shards", type=int, default=8, help="stream shards of the host-facing env")
     args = ap.parse_args()
@@ -319,6 +320,38 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * n * e2e_steps / float(te[0])
 
+    # ---- closed loop: the on-device follow-the-gap controller drives every env, no host round trip per step ----
+    closed = None
+    if not args.no_closed_loop:
+        from racing_dreamer_b200 import GapFollowerPolicy
+        cenv = BatchedRaceEnv(env_config(n, rank, args.obs), device=dev)
+        pol = GapFollowerPolicy(cenv)
+        cenv.reset()
+        pol.rollout(args.warmup)
+        cenv.read_stats(reset=True)
+        cenv.enable_timing(True)
+        cenv.read_timing(reset=True)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cl_steps = min(args.steps, 500)
+        barrier()
+        c0.record()
+        pol.rollout(cl_steps)
+        c1.record()
+        barrier()
+        tc = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        ct = cenv.read_timing(reset=True)
+        cstats = cenv.read_stats()
+        closed = {"value": world * n * cl_steps / (float(tc[0]) / 1e3), "unit": "env-steps/s", "steps": cl_steps,
+                  "policy": "follow_the_gap on device (k_gap_follower), back-to-back steps",
+                  "ms_per_step": float(tc[0]) / cl_steps,
+                  "kernel_ms": {"k_gap_follower": ct["policy_ms"] / max(1, ct["policy_launches"]),
+                                "k_step": ct["step_ms"] / max(1, ct["step_launches"]),
+                                "k_lidar": ct["lidar_ms"] / max(1, ct["lidar_launches"])},
+                  "episode_stats_rank0": cstats}
+        cenv.close()
+
     # ---- the only collective of the system: episode statistics gathered across ranks at log cadence ----
     from racing_dreamer_b200.stats import gather_stats
     stats_all, _ = gather_stats(stats, device=dev)
@@ -353,6 +386,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "episode_stats": stats_all,
+            "closed_loop": closed,
         }
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1

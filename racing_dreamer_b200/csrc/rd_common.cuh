@@ -75,6 +75,50 @@ __device__ __forceinline__ int rd_drivable_at(const DevMap& m, int cx, int cy) {
   return (__ldg(m.bits + (size_t)cy * m.rw + (cx >> 5)) >> (cx & 31)) & 1u;
 }
 
+// ---- float64 helpers for the dynamics integrator (k_step): short, branch-free, no slow paths ----
+// sin/cos on [-pi/4, pi/4] (fdlibm __kernel_sin / __kernel_cos minimax polynomials, < 1 ulp)
+__device__ __forceinline__ void rd_sincos_kernel(double r, double& s, double& c) {
+  const double z = r * r;
+  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  ps = fma(z, ps, 2.75573137070700676789e-06);
+  pc = fma(z, pc, -2.75573143513906633035e-07);
+  ps = fma(z, ps, -1.98412698298579493134e-04);
+  pc = fma(z, pc, 2.48015872894767294178e-05);
+  ps = fma(z, ps, 8.33333333332248946124e-03);
+  pc = fma(z, pc, -1.38888888888741095749e-03);
+  ps = fma(z, ps, -1.66666666666666324348e-01);
+  pc = fma(z, pc, 4.16666666666666019037e-02);
+  s = fma(r * z, ps, r);
+  c = fma(z * z, pc, fma(z, -0.5, 1.0));
+}
+// sincos for |x| < ~1e5 rad (three-term Cody-Waite reduction by pi/2, then the kernels; quadrant fix-up by selects).
+// Larger arguments (a car that has spun thousands of times) take the library path.
+__device__ __forceinline__ void rd_sincos(double x, double* sn, double* cs) {
+  if (!(fabs(x) < 1.0e5)) { sincos(x, sn, cs); return; }
+  const double k = rint(x * 6.36619772367581382433e-01);
+  double r = fma(-k, 1.57079632679489655800e+00, x);
+  r = fma(-k, 6.12323399573676603587e-17, r);
+  r = fma(-k, -1.49738490485916983294e-33, r);
+  double s, c;
+  rd_sincos_kernel(r, s, c);
+  const int q = (int)k;
+  const double s1 = (q & 1) ? c : s, c1 = (q & 1) ? s : c;
+  *sn = (q & 2) ? -s1 : s1;
+  *cs = ((q + 1) & 2) ? -c1 : c1;
+}
+// 1/x for normal, finite x (speeds, cosines of small angles): hardware seed + three Newton steps, <= 1 ulp
+__device__ __forceinline__ double rd_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+
 // ---- mbarrier / bulk-copy (TMA, 1-D) wrappers ----
 __device__ __forceinline__ uint32_t rd_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void rd_mbar_init(uint64_t* bar, uint32_t count) {

@@ -39,7 +39,9 @@ __device__ __forceinline__ void st_rhs(const rd_vehicle& p, const double (&q)[7]
   else if (sv <= -p.steer_vel_max) svc = -p.steer_vel_max;
   else if (sv >= p.steer_vel_max) svc = p.steer_vel_max;
   else svc = sv;
-  double pos_limit = (v > p.v_switch) ? (p.a_max * p.v_switch / v) : p.a_max;
+  // the division only exists for vehicles that can exceed v_switch (uniform test: no work for the default car)
+  double pos_limit = p.a_max;
+  if (p.v_max + 1.0 > p.v_switch) { if (v > p.v_switch) pos_limit = p.a_max * p.v_switch / v; }
   double ac;
   if ((v <= p.v_min && acc <= 0.0) || (v >= p.v_max && acc >= 0.0)) ac = 0.0;
   else if (acc <= -p.a_max) ac = -p.a_max;
@@ -52,21 +54,21 @@ __device__ __forceinline__ void st_rhs(const rd_vehicle& p, const double (&q)[7]
   const bool kin = fabs(v) < p.v_kinematic;
   const double ang = kin ? yaw : (slip + yaw);
   double sn, cn;
-  sincos(ang, &sn, &cn);
+  rd_sincos(ang, &sn, &cn);
   f[0] = v * cn;
   f[1] = v * sn;
   f[2] = svc;
   f[3] = ac;
   if (kin) {
-    double ss, cs;
-    sincos(steer, &ss, &cs);
-    const double rc = 1.0 / cs;
+    double ss, cs;   // |steer| <= steer_max (+ an RK4 stage's overshoot) < pi/4: no range reduction needed
+    if (fabs(steer) < 0.78) rd_sincos_kernel(steer, ss, cs); else rd_sincos(steer, &ss, &cs);
+    const double rc = rd_rcp(cs);
     const double tn = ss * rc;
     f[4] = (v * rl) * tn;
     f[5] = (ac * rl) * tn + ((v * rl) * (rc * rc)) * svc;
     f[6] = 0.0;
   } else {
-    const double rv = 1.0 / v;
+    const double rv = rd_rcp(v);   // |v| >= v_kinematic here
     const double c1 = p.mu * p.mass / (p.inertia * lwb);
     const double c2 = p.mu * rl;
     double rear = g * p.lf + ac * p.h_cg;
@@ -83,11 +85,11 @@ __device__ __forceinline__ void st_rhs(const rd_vehicle& p, const double (&q)[7]
   }
 }
 
-__device__ __forceinline__ void st_tick(const rd_config& cfg, double (&q)[7], double motor, double steering) {
+__device__ __forceinline__ void st_tick(const rd_config& cfg, double (&q)[7], double motor, double steering, double inv_dt) {
   const rd_vehicle& p = cfg.vehicle;
   const double dt = cfg.dt;
   double target = steering * p.steer_gain * p.steer_max;
-  double sv = (target - q[2]) / dt;
+  double sv = (target - q[2]) * inv_dt;
   double acc = (motor >= 0.0) ? (motor * p.a_drive - p.c_drag * q[3]) : (motor * p.a_brake - p.c_drag * q[3]);
   double k1[7], k2[7], k3[7], k4[7], t[7];
   const double h2 = 0.5 * dt, h6 = dt / 6.0;
@@ -138,7 +140,7 @@ __device__ __forceinline__ bool rd_collides(const rd_config& cfg, const DevMap& 
 __device__ __forceinline__ void rd_probe(const rd_config& cfg, const DevMap& m, double x, double y, double yaw,
                                          bool& col, bool& inside, double& p) {
   double c, s;
-  sincos(yaw, &s, &c);
+  rd_sincos(yaw, &s, &c);
   const double hl = 0.5 * cfg.vehicle.body_length, hw = 0.5 * cfg.vehicle.body_width;
   const double ax = hl * c, ay = hl * s, bx = hw * s, by = hw * c;
   const double px[5] = {x, (x + ax) - bx, (x + ax) + bx, (x - ax) - bx, (x - ax) + bx};
@@ -288,8 +290,9 @@ __global__ void __launch_bounds__(128) k_step(StepParams P, OutPtrs o, const flo
       double total = 0.0;
       int done = 0;
       const int ncp = cfg.n_checkpoints;
+      const double inv_dt = 1.0 / cfg.dt;
       for (int t = 0; t < cfg.action_repeat; ++t) {  // ActionRepeat [REF dreamer/wrappers.py:107-116]
-        st_tick(cfg, q, a[0], a[1]);
+        st_tick(cfg, q, a[0], a[1], inv_dt);
         time = time + cfg.dt;
         bool col, inside;
         rd_probe(cfg, m, q[0], q[1], q[4], col, inside, p);
@@ -371,7 +374,8 @@ __global__ void __launch_bounds__(128) k_dynamics(rd_config cfg, double* __restr
 #pragma unroll
   for (int k = 0; k < 7; ++k) q[k] = state[(size_t)k * n + e];
   const double motor = commands[2 * e], steering = commands[2 * e + 1];
-  for (int t = 0; t < n_ticks; ++t) st_tick(cfg, q, motor, steering);
+  const double inv_dt = 1.0 / cfg.dt;
+  for (int t = 0; t < n_ticks; ++t) st_tick(cfg, q, motor, steering, inv_dt);
 #pragma unroll
   for (int k = 0; k < 7; ++k) state[(size_t)k * n + e] = q[k];
 }

@@ -46,6 +46,7 @@ struct rd_env {
   int smem_optin = 0;             // max dynamic shared memory per CTA (opt-in), bytes
   bool lidar_attr_set[2] = {false, false};  // k_lidar<16>, k_lidar<32> opted in to smem_optin
   int n = 0;
+  int step_block = 128;           // k_step threads per CTA (small batches: fewer, so that every SM gets a warp)
   double* d_f64 = nullptr;
   int32_t* d_i32 = nullptr;
   double* d_stats = nullptr;
@@ -87,6 +88,7 @@ struct rd_env {
     rd_gap_follower g{};
     PolicyState st{};
     float* d_actions = nullptr;   // [n][2] rollout scratch
+    bool attr_set = false;        // kernel opted in to > 48 KB of dynamic shared memory
   } pol;
   // optional per-kernel timing (rd_enable_timing)
   bool timing = false;
@@ -364,6 +366,10 @@ RD_API int rd_create(const rd_config* cfg, rd_env** out) {
   env->smem_optin = (int)prop.sharedMemPerBlockOptin;
   env->n = cfg->n_envs;
   env->order_offset.assign(RD_MAX_MAPS + 1, 0);
+  // k_step is one long float64 instruction stream per warp: spread the warps over as many SM sub-partitions as the
+  // batch allows (RD_STEP_BLOCK overrides, tuning)
+  env->step_block = (env->n >= 128 * 4 * env->sm_count) ? 128 : ((env->n >= 64 * 4 * env->sm_count) ? 64 : 32);
+  if (const char* ev = std::getenv("RD_STEP_BLOCK")) { int v = std::atoi(ev); if (v == 32 || v == 64 || v == 128) env->step_block = v; }
   const size_t n = (size_t)env->n;
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc(p, bytes); if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes); } };
@@ -527,7 +533,8 @@ RD_API int rd_step(rd_env* env, const float* actions_dev, const rd_outputs* out,
   cudaStream_t s = (cudaStream_t)stream;
   {
     ScopedTiming tm(env, s, T_STEP);
-    k_step<<<(env->n + 127) / 128, 128, 0, s>>>(step_params(env), out_ptrs(out), actions_dev, 0, env->n);
+    const int tb = env->step_block;
+    k_step<<<(env->n + tb - 1) / tb, tb, 0, s>>>(step_params(env), out_ptrs(out), actions_dev, 0, env->n);
   }
   env->launches++;
   CUDA_TRY(env, cudaGetLastError());
@@ -673,7 +680,8 @@ RD_API int rd_step_host(rd_env* env, const float* actions_host) {
   cudaStream_t s0 = h.streams[0];
   {
     ScopedTiming tm(env, s0, T_STEP);
-    k_step<<<(n + 127) / 128, 128, 0, s0>>>(step_params(env), out_ptrs(&h.dev_out), h.act_dev, 0, n);
+    const int tb = env->step_block;
+    k_step<<<(n + tb - 1) / tb, tb, 0, s0>>>(step_params(env), out_ptrs(&h.dev_out), h.act_dev, 0, n);
   }
   env->launches++;
   CUDA_TRY(env, cudaGetLastError());
@@ -764,27 +772,29 @@ RD_API int rd_policy_gap_follower_init(rd_env* env, const rd_gap_follower* g_or_
 namespace {
 int launch_gap_follower(rd_env* env, const float* lidar_dev, const float* speed_dev, float* actions_dev, double* debug_dev,
                         cudaStream_t s) {
-  constexpr int WARPS = 4;
+  constexpr int WARPS = 8;
   auto& p = env->pol;
   GapArgs A{};
   A.g = p.g; A.ps = p.st; A.lidar = lidar_dev; A.speed = speed_dev; A.state_v = env->d_f64 + (size_t)RD_S_V * env->n;
   A.actions = actions_dev; A.debug = debug_dev; A.n = env->n; A.n_beams = env->cfg.n_beams;
   const int m = p.g.arc_last - p.g.arc_first + 1;
-  A.m_pad = (m + 1) | 1;   // odd number of doubles per row: the warps' rows start in different banks
+  A.m_pad = (m + 1) | 1;   // odd number of floats per row: the warps' rows start in different banks
   A.rescale = env->cfg.rescale_actions;
   for (int k = 0; k < 2; ++k) { A.low[k] = env->cfg.action_low[k]; A.high[k] = env->cfg.action_high[k]; }
   A.a_drive = env->cfg.vehicle.a_drive; A.c_drag = env->cfg.vehicle.c_drag;
   A.steer_scale = env->cfg.vehicle.steer_gain * env->cfg.vehicle.steer_max;
-  const size_t smem = sizeof(double) * 2 * (size_t)A.m_pad * WARPS;
-  static bool attr_set = false;
-  if (smem > 48 * 1024 && !attr_set) {
-    CUDA_TRY(env, cudaFuncSetAttribute(k_gap_follower<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_optin));
-    attr_set = true;
+  const size_t smem = sizeof(float) * 2 * (size_t)A.m_pad * WARPS;
+  if (smem > (size_t)env->smem_optin || m > 32 * 64) return fail(env, RD_ERR_INVALID, "scan arc of %d beams is too long for the gap follower (max 2048)", m);
+  const unsigned grid = (unsigned)((env->n + WARPS - 1) / WARPS);
+  auto kern = (m <= 32 * 23) ? k_gap_follower<WARPS, 23>          // 1080 beams: 721 in the arc
+              : (m <= 32 * 32) ? k_gap_follower<WARPS, 32> : k_gap_follower<WARPS, 64>;
+  if (smem > 48 * 1024 && !env->pol.attr_set) {
+    CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_optin));
+    env->pol.attr_set = true;
   }
-  if (smem > (size_t)env->smem_optin) return fail(env, RD_ERR_INVALID, "scan arc of %d beams does not fit in shared memory", m);
   {
     ScopedTiming tm(env, s, T_POLICY);
-    k_gap_follower<WARPS><<<(env->n + WARPS - 1) / WARPS, WARPS * 32, smem, s>>>(A);
+    kern<<<grid, WARPS * 32, smem, s>>>(A);
   }
   env->launches++;
   CUDA_TRY(env, cudaGetLastError());

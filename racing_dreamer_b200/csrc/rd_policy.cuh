@@ -11,8 +11,8 @@
 //   percentile of the adjusted ranges (np.percentile's linear rule) -> heading = mean angle of the beams at or above
 //   it, heading distance = their mean range -> PID -> steering angle, speed -> env action.
 // The median test needs no sort: d > 9*median  <=>  at least w/2+1 window elements x satisfy 9*x < d.
-// The percentile needs two order statistics of ~721 non-negative doubles: bisection on their bit patterns (monotone
-// for non-negative IEEE doubles) with warp-wide counts.
+// The percentile needs two order statistics of ~721 values: bisection on the bit patterns of their float32 codes
+// (monotone for non-negative floats) with warp-wide counts, skipped when both are the lookahead distance itself.
 // All arithmetic is float64 in the reference's operation order (translation unit compiled with -fmad=false); the only
 // differences to NumPy are the summation order of the two means and acos() vs libm (<= 2 ulp).
 #pragma once
@@ -42,7 +42,7 @@ struct GapArgs {
   const double* state_v;  // env state row RD_S_V (used when speed is null)
   float* actions;         // [n][2]
   double* debug;          // [n][4] or null
-  int n, n_beams, m_pad;  // m_pad: doubles per shared-memory row
+  int n, n_beams, m_pad;  // m_pad: floats per shared-memory row
   int rescale;
   double low[2], high[2];
   double a_drive, c_drag, steer_scale;   // steer_scale = steer_gain * steer_max
@@ -62,17 +62,27 @@ __device__ __forceinline__ int rd_trunc_clip(double x, int hi) {
   return k < 0 ? 0 : (k > hi ? hi : (int)k);
 }
 
-template <int WARPS>
+// Ranges are kept in shared memory as float32 codes: the LiDAR's float32 value itself, or +inf for "clipped to the
+// lookahead distance" (which is not a float32 number).  The code order equals the value order, so min() and the
+// percentile selection work on the codes; rd_decode() gives back the exact float64 the reference computes with.
+#define RD_CLIP_CODE 0x7f800000u
+__device__ __forceinline__ double rd_decode(float f, double lookahead) {
+  return (__float_as_uint(f) == RD_CLIP_CODE) ? lookahead : (double)f;
+}
+
+// ITEMS: adjusted ranges per lane held in registers for the percentile selection (32 * ITEMS >= beams in the arc)
+template <int WARPS, int ITEMS>
 __global__ void __launch_bounds__(WARPS * 32) k_gap_follower(GapArgs A) {
-  extern __shared__ double sm_pol[];
+  extern __shared__ float sm_pol[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.x * WARPS + warp;
   if (e >= A.n) return;   // warps are independent: no block-wide barrier below
   const rd_gap_follower& g = A.g;
   const int n = A.n;
-  double* rng = sm_pol + (size_t)warp * 2 * A.m_pad;
-  double* adj = rng + A.m_pad;
+  float* rng = sm_pol + (size_t)warp * 2 * A.m_pad;
+  float* adj = rng + A.m_pad;
   const int M = g.arc_last - g.arc_first + 1;
+  const double look = g.lookahead;
   int scans = A.ps.i32[(size_t)RD_P_SCANS * n + e] + 1;
   int headings = A.ps.i32[(size_t)RD_P_HEADINGS * n + e];
   double steering_angle = A.ps.f64[(size_t)RD_P_STEER * n + e];
@@ -81,9 +91,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_gap_follower(GapArgs A) {
   if (scans >= 2) {   // the first scan after a reset only arms the node's timestamp [REF agent.py:132-134]
     const float* row = A.lidar + (size_t)e * A.n_beams;
     for (int j = lane; j < M; j += 32) {
-      double r = (double)row[(A.n_beams - 1) - (g.arc_first + j)];
-      r = r < 0.0 ? 0.0 : r;
-      r = r > g.lookahead ? g.lookahead : r;   // np.clip(ranges, 0, lookahead_distance)
+      float r = row[(A.n_beams - 1) - (g.arc_first + j)];
+      r = r < 0.0f ? 0.0f : r;
+      if ((double)r >= look) r = __uint_as_float(RD_CLIP_CODE);   // np.clip(ranges, 0, lookahead_distance)
       rng[j] = r;
       adj[j] = r;
     }
@@ -96,7 +106,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_gap_follower(GapArgs A) {
       const int i = base + lane;
       bool cand = false;
       if (i < nd) {
-        const double d = fabs(rng[i + 1] - rng[i]);
+        const double d = fabs(rd_decode(rng[i + 1], look) - rd_decode(rng[i], look));
         if (d > g.minimum_gap_length) {
           bool ismax = true;
           int below = 0;
@@ -104,8 +114,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_gap_follower(GapArgs A) {
             const int j = i - half + k;
             const int jr = j < 0 ? -j - 1 : (j >= nd ? 2 * nd - j - 1 : j);   // maximum_filter1d: mode 'reflect'
             const int jc = j < 0 ? 0 : (j >= nd ? nd - 1 : j);                // median_filter: mode 'nearest'
-            const double dr = fabs(rng[jr + 1] - rng[jr]);
-            const double dc = (jc == jr) ? dr : fabs(rng[jc + 1] - rng[jc]);
+            const double dr = fabs(rd_decode(rng[jr + 1], look) - rd_decode(rng[jr], look));
+            const double dc = (jc == jr) ? dr : fabs(rd_decode(rng[jc + 1], look) - rd_decode(rng[jc], look));
             if (dr > d) ismax = false;
             if (dc * g.median_dev_threshold < d) ++below;
           }
@@ -116,64 +126,76 @@ __global__ void __launch_bounds__(WARPS * 32) k_gap_follower(GapArgs A) {
       while (bal) {   // every lane handles the same candidate: its chord lowers a run of adjusted ranges
         const int ii = base + (__ffs(bal) - 1);
         bal &= bal - 1;
-        double L = rng[ii];
-        if (ii > 0) L = fmin(L, rng[ii - 1]);   // the reference's slice is empty (and raises) for ii == 0
-        L = fmin(L, rng[ii + 1]);
+        float Lc = rng[ii];
+        if (ii > 0) Lc = fminf(Lc, rng[ii - 1]);   // the reference's slice is empty (and raises) for ii == 0
+        Lc = fminf(Lc, rng[ii + 1]);
+        const double L = rd_decode(Lc, look);
         const double theta = (double)(g.arc_first + ii) * inc + amin;
         const double L2 = L * L;
         const double beta = acos((2.0 * L2 - w2) / (2.0 * L2));
         const int k0 = rd_trunc_clip(((theta - beta) - ang0) / inc, M - 1);
         const int k1 = rd_trunc_clip(((theta + beta) - ang0) / inc, M - 1);
-        for (int k = k0 + lane; k <= k1; k += 32) adj[k] = fmin(adj[k], L);
+        for (int k = k0 + lane; k <= k1; k += 32) adj[k] = fminf(adj[k], Lc);
       }
     }
     __syncwarp();
-    // two order statistics of adj[0..M) by bisection on the bit patterns
-    long long lo = 0x7fffffffffffffffll, hi = 0;
-    for (int j = lane; j < M; j += 32) {
-      const long long b = __double_as_longlong(adj[j]);
-      lo = b < lo ? b : lo;
-      hi = b > hi ? b : hi;
-    }
+    // two order statistics of adj[0..M): when enough beams are still clipped both are the lookahead distance itself
+    // (open track ahead); otherwise bisection on the codes' bit patterns (monotone for non-negative floats)
+    double x, y;
+    unsigned key[ITEMS];   // codes of this lane's adjusted ranges; slots past the arc hold the maximum code
+    unsigned n_clip = 0;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const long long l2 = __shfl_xor_sync(0xffffffffu, lo, off), h2 = __shfl_xor_sync(0xffffffffu, hi, off);
-      lo = l2 < lo ? l2 : lo;
-      hi = h2 > hi ? h2 : hi;
+    for (int t = 0; t < ITEMS; ++t) {
+      const int j = lane + 32 * t;
+      key[t] = (j < M) ? __float_as_uint(adj[j]) : 0xffffffffu;
+      n_clip += (key[t] == RD_CLIP_CODE) ? 1u : 0u;
     }
-    while (lo < hi) {
-      const long long mid = lo + ((hi - lo) >> 1);
-      unsigned c = 0;
-      for (int j = lane; j < M; j += 32) c += (__double_as_longlong(adj[j]) <= mid) ? 1u : 0u;
-      c = __reduce_add_sync(0xffffffffu, c);
-      if ((int)c >= g.pct_lo + 1) hi = mid; else lo = mid + 1;
-    }
-    const double x = __longlong_as_double(lo);
-    double y = x;
-    if (g.pct_hi > g.pct_lo) {
-      unsigned c = 0;
-      long long nxt = 0x7fffffffffffffffll;
-      for (int j = lane; j < M; j += 32) {
-        const long long b = __double_as_longlong(adj[j]);
-        c += (b <= lo) ? 1u : 0u;
-        if (b > lo && b < nxt) nxt = b;
-      }
-      c = __reduce_add_sync(0xffffffffu, c);
+    n_clip = __reduce_add_sync(0xffffffffu, n_clip);
+    if ((int)n_clip >= M - g.pct_lo) {
+      x = y = look;
+    } else {
+      unsigned lo = 0xffffffffu, hi = 0;
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const long long o2 = __shfl_xor_sync(0xffffffffu, nxt, off);
-        nxt = o2 < nxt ? o2 : nxt;
+      for (int t = 0; t < ITEMS; ++t) {
+        lo = key[t] < lo ? key[t] : lo;
+        if (key[t] != 0xffffffffu) hi = key[t] > hi ? key[t] : hi;
       }
-      if ((int)c < g.pct_hi + 1) y = __longlong_as_double(nxt);
+      lo = __reduce_min_sync(0xffffffffu, lo);
+      hi = __reduce_max_sync(0xffffffffu, hi);
+      while (lo < hi) {
+        const unsigned mid = lo + ((hi - lo) >> 1);
+        unsigned c = 0;
+#pragma unroll
+        for (int t = 0; t < ITEMS; ++t) c += (key[t] <= mid) ? 1u : 0u;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if ((int)c >= g.pct_lo + 1) hi = mid; else lo = mid + 1;
+      }
+      unsigned nxt = lo;
+      if (g.pct_hi > g.pct_lo) {
+        unsigned c = 0, up = 0xffffffffu;
+#pragma unroll
+        for (int t = 0; t < ITEMS; ++t) {
+          c += (key[t] <= lo) ? 1u : 0u;
+          if (key[t] > lo && key[t] < up) up = key[t];
+        }
+        c = __reduce_add_sync(0xffffffffu, c);
+        up = __reduce_min_sync(0xffffffffu, up);
+        if ((int)c < g.pct_hi + 1) nxt = up;
+      }
+      x = rd_decode(__uint_as_float(lo), look);
+      y = rd_decode(__uint_as_float(nxt), look);
     }
     const double dxy = y - x;   // numpy _lerp
     const double pct = (g.pct_gamma >= 0.5) ? (y - dxy * (1.0 - g.pct_gamma)) : (x + dxy * g.pct_gamma);
     double sa = 0.0, sr = 0.0, cnt = 0.0;
-    for (int j = lane; j < M; j += 32) {
-      const double a = adj[j];
+#pragma unroll
+    for (int t = 0; t < ITEMS; ++t) {
+      const int j = lane + 32 * t;
+      if (j >= M) break;
+      const double a = rd_decode(__uint_as_float(key[t]), look);
       if (a >= pct && a < g.range_max) {   // np.digitize(adjusted, [0, pct, range_max]) == 2
         sa += (double)(g.arc_first + j) * inc + amin;
-        sr += rng[j];
+        sr += rd_decode(rng[j], look);
         cnt += 1.0;
       }
     }

@@ -74,8 +74,9 @@ def test_policy_matches_reference_golden(torch_cuda, golden_dir):
         env.close()
 
 
-@pytest.mark.parametrize("track,R", [("austria", 4), ("treitlstrasse_v2", 8)])
-def test_closed_loop_vs_oracle(torch_cuda, track, R):
+@pytest.mark.parametrize("track,R,nb", [("austria", 4, 1080), ("treitlstrasse_v2", 8, 1080), ("columbia", 4, 2048),
+                                        ("austria", 4, 1440)])
+def test_closed_loop_vs_oracle(torch_cuda, track, R, nb):
     """GPU env + GPU policy; the numpy controller sees the GPU's scans, the CPU oracle env is stepped with the GPU's
     actions: controller outputs within TOL every step, env results at the usual parity bars, resets clear the PID."""
     torch = torch_cuda
@@ -83,10 +84,10 @@ def test_closed_loop_vs_oracle(torch_cuda, track, R):
     from oracle import Oracle
     n = 48
     env = make_env(tracks=(track,), n_envs=n, action_repeat=R, auto_reset=True, reset_mode="random", seed=21,
-                   time_limit_steps=25)
+                   time_limit_steps=25, n_beams=nb)
     orc = Oracle(env.cfg, env.tracks, env.map_ids, n_threads=THREADS)
     pol = GapFollowerPolicy(env)
-    ctl = [GapFollowerOracle(GapFollowerParams(dt=R * 0.01)) for _ in range(n)]
+    ctl = [GapFollowerOracle(GapFollowerParams(n_beams=nb, dt=R * 0.01)) for _ in range(n)]
     obs = env.reset()
     orc.reset(mode=int(env.cfg.reset_mode))
     resets = 0
