@@ -39,6 +39,11 @@ TRACK_FILES: Dict[str, str] = {
     "treitlstrasse_v2": "Treitlstrasse_3-U_v2",
     "columbia": "columbia_small",
     "circle_cw": "circle",
+    # further TU-Wien redraws in docs/maps/maps [REF docs/maps/README.md:22-46] (not racecar_gym scene names)
+    "monaco": "f1_mco",
+    "austria_wide": "f1_aut_wide",
+    "treitlstrasse_v1": "Treitlstrasse_3-U_v1",
+    "treitlstrasse_v3": "Treitlstrasse_3-U_v3",
 }
 
 
@@ -196,8 +201,16 @@ def _wavefront(free: np.ndarray, seed_rc) -> np.ndarray:
     return dist
 
 
+# The generator clears one hard-coded pixel of EVERY map it processes ("extra for optimized spline at
+# Treitlstrasse_3-U_v3") [REF generate-costmap.py:45-46].  On Treitlstrasse_3-U_v2 that pixel lies on the track, where it
+# would be a 5 cm phantom wall for the ray caster, so the shipped tracks are compiled without it; pass
+# reference_quirks=True to reproduce the generator's arrays bit for bit (tests/test_cpu_maps.py does).
+REFERENCE_CLEARED_PIXEL = (987, 1294)
+
+
 def compile_track(yaml_path: os.PathLike, name: Optional[str] = None, start_xy=(0.0, 0.0),
-                  reset_clearance_m: float = 0.4, max_reset_poses: int = 4096) -> TrackMap:
+                  reset_clearance_m: float = 0.4, max_reset_poses: int = 4096,
+                  reference_quirks: bool = False) -> TrackMap:
     import yaml
     from scipy import ndimage
 
@@ -209,6 +222,8 @@ def compile_track(yaml_path: os.PathLike, name: Optional[str] = None, start_xy=(
     gray = _read_gray(yaml_path.parent / props["image"])
     H, W = gray.shape
     binary = (gray / np.amax(gray)) > float(props["occupied_thresh"])     # [REF :42-43]
+    if reference_quirks and H > REFERENCE_CLEARED_PIXEL[0] and W > REFERENCE_CLEARED_PIXEL[1]:
+        binary[REFERENCE_CLEARED_PIXEL] = False
 
     # start pixel [REF :49-52]; the reference mixes shape[1] with the row axis (square images only) --
     # here the row flip uses the row count.

@@ -17,6 +17,10 @@ committed so that the parity tests can run where /root/reference does not exist 
                            (rospy stubbed, oracle/ref_ftg.py) fed scan sequences of the oracle env: the drive
                            commands it publishes (steering angle, speed, heading) per scan.
 
+  costmap_golden.npz       the UNMODIFIED map generator [REF docs/maps/costmaps/generate-costmap.py] (skimage/cmapy
+                           stubbed over scipy.ndimage, oracle/ref_costmap.py) run on two of the reference's maps:
+                           drivable_area, norm_distance_from_start, norm_distance_to_obstacle.
+
 usage: python tests/golden/make_golden.py [name ...]
 """
 import sys
@@ -250,6 +254,30 @@ def gap_follower_golden():
         print(f"gap_follower_golden: {track} R={R} {len(scans)} scans, published {int(sum(c[0] for c in cmds))}, "
               f"|steer| max {max(abs(c[1]) for c in cmds):.3f}")
     np.savez_compressed(OUT / "gap_follower_golden.npz", n_seq=len(specs), tracks=np.array([s[0] for s in specs]), **out)
+
+
+def costmap_golden():
+    """The generator's three consumed layers for Treitlstrasse_3-U_v2 (where its hard-coded cleared pixel lies ON the
+    track) and f1_aut (where it does not).  Stored in the compiled-track layout (crop, integer wavefront distance,
+    squared EDT) after checking that this layout reproduces the generator's float arrays bit for bit."""
+    from oracle.ref_costmap import reference_layers
+    from racing_dreamer_b200 import TRACK_FILES, maps
+    out = {"tracks": np.array(["treitlstrasse_v2", "austria"])}
+    for name in ("treitlstrasse_v2", "austria"):
+        y = ref_stubs.REFERENCE_ROOT / "docs" / "maps" / "maps" / f"{TRACK_FILES[name]}.yaml"
+        ref = reference_layers(y)
+        tm = maps.compile_track(y, reference_quirks=True)
+        assert np.array_equal(ref["drivable_area"], tm.full_drivable())
+        assert np.array_equal(ref["norm_distance_from_start"], tm.full_norm_distance_from_start())
+        assert np.array_equal(ref["norm_distance_to_obstacle"], tm.full_norm_distance_to_obstacle())
+        out[f"{name}_r0c0hw"] = np.array([tm.r0, tm.c0, tm.h, tm.w], np.int64)
+        out[f"{name}_drivable"] = np.packbits(tm.drivable, axis=1)
+        out[f"{name}_dist"] = tm.dist
+        out[f"{name}_dmax"] = tm.dmax
+        out[f"{name}_edt_sq"] = tm.edt_sq
+        out[f"{name}_start_px"] = np.asarray(ref["grid_starting_position"], np.int64)
+        print(f"costmap_golden: {name} crop {tm.h}x{tm.w} dmax {tm.dmax} drivable {int(tm.drivable.sum())} px")
+    np.savez_compressed(OUT / "costmap_golden.npz", **out)
 
 
 if __name__ == "__main__":

@@ -66,3 +66,48 @@ def test_recompile_matches_stored_and_dilation_wavefront():
         mask |= new
     assert cur == tm.dmax
     assert np.array_equal(dist[free], tm.dist[free].astype(np.int32))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# a6 / §8-f4: pinned against the UNMODIFIED generator (tests/golden/costmap_golden.npz, oracle/ref_costmap.py)
+def _golden_layers(golden_dir, name):
+    g = np.load(golden_dir / "costmap_golden.npz")
+    r0, c0, h, w = (int(v) for v in g[f"{name}_r0c0hw"])
+    drv = np.unpackbits(g[f"{name}_drivable"], axis=1)[:, :w].astype(bool)
+    return (r0, c0, h, w), drv, g[f"{name}_dist"], int(g[f"{name}_dmax"]), g[f"{name}_edt_sq"]
+
+
+def test_shipped_austria_equals_reference_generator(golden_dir):
+    """f1_aut: the generator's cleared pixel is off the track, so the shipped track IS the generator's output"""
+    (r0, c0, h, w), drv, dist, dmax, edt = _golden_layers(golden_dir, "austria")
+    tm = load_track("austria")
+    assert (tm.r0, tm.c0, tm.h, tm.w, tm.dmax) == (r0, c0, h, w, dmax)
+    assert np.array_equal(tm.drivable, drv) and np.array_equal(tm.dist, dist) and np.array_equal(tm.edt_sq, edt)
+
+
+def test_shipped_treitlstrasse_differs_only_by_the_cleared_pixel(golden_dir):
+    """Treitlstrasse_3-U_v2: the generator clears pixel (987, 1294) of every map [REF generate-costmap.py:45-46]; it is
+    on this track.  The shipped track keeps it drivable (no phantom 5 cm wall for the ray caster); everything else is
+    the generator's output, up to the detour the wavefront takes around the hole."""
+    (r0, c0, h, w), drv, dist, dmax, edt = _golden_layers(golden_dir, "treitlstrasse_v2")
+    tm = load_track("treitlstrasse_v2")
+    assert (tm.r0, tm.c0, tm.h, tm.w, tm.dmax) == (r0, c0, h, w, dmax)
+    pr, pc = maps.REFERENCE_CLEARED_PIXEL[0] - r0, maps.REFERENCE_CLEARED_PIXEL[1] - c0
+    diff = np.argwhere(tm.drivable != drv)
+    assert diff.tolist() == [[pr, pc]] and tm.drivable[pr, pc] and not drv[pr, pc]
+    rr, cc = np.mgrid[0:h, 0:w]
+    far = np.maximum(np.abs(rr - pr), np.abs(cc - pc)) > 40
+    dd = np.abs(tm.dist.astype(np.int64) - dist.astype(np.int64))
+    assert dd[far].max() == 0 and dd[(~far) & drv].max() <= 1        # one-cell detour right behind the hole
+    assert np.array_equal(tm.edt_sq[far], edt[far])
+
+
+@pytest.mark.skipif(not ref_stubs.available(), reason="/root/reference not present (GPU box)")
+def test_compile_with_reference_quirks_reproduces_golden(golden_dir):
+    """compile_track(reference_quirks=True) == the generator's arrays, bit for bit (fixture made by running the
+    unmodified script; see tests/golden/make_golden.py::costmap_golden)"""
+    for name in ("treitlstrasse_v2", "austria"):
+        (r0, c0, h, w), drv, dist, dmax, edt = _golden_layers(golden_dir, name)
+        tm = maps.compile_track(ref_stubs.REFERENCE_ROOT / "docs/maps/maps" / f"{TRACK_FILES[name]}.yaml", reference_quirks=True)
+        assert (tm.r0, tm.c0, tm.h, tm.w, tm.dmax) == (r0, c0, h, w, dmax)
+        assert np.array_equal(tm.drivable, drv) and np.array_equal(tm.dist, dist) and np.array_equal(tm.edt_sq, edt)
