@@ -1,0 +1,469 @@
+// rd_gemm.cuh -- the dense layers of the Dreamer agent on the 5th-generation tensor cores.
+//
+// One kernel, k_dense<EPI, NSLAB, NACC>, computes a 128 x 64 tile of  act(A @ W + b)  for a batch of envs:
+//   * A (activations, [envs][K] float32, K contiguous) and W (weights, stored transposed [N][K], K contiguous) are
+//     streamed through a 4-stage shared-memory ring by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle, out-of-bounds
+//     rows/columns zero-filled by the copy engine, so no padded copies of anything exist in HBM);
+//   * one elected thread issues tcgen05.mma.kind::tf32 (M = 128, N = 64, K = 8 per instruction; float32 operands are
+//     read as TF32, accumulation in float32) into tensor memory; tcgen05.commit hands each ring slot back to the
+//     producer and, after the last K block, hands the accumulators to the epilogue warps;
+//   * four epilogue warps read their 32 TMEM lanes (one env per thread) with tcgen05.ld and apply the layer's
+//     epilogue in registers: bias + ELU, the Keras GRU cell gates, the RSSM posterior sample, or the actor head with
+//     SampleDist.mode() -- so no pre-activation ever reaches HBM.
+// A layer is described by up to two "phases" (K ranges with their own A source: concat([deter, embed]) @ W is two
+// phases over one W) and up to three weight slabs per phase feeding up to four accumulators (the GRU's z, r and the
+// two halves of the candidate gate).
+//
+// Replaces tf.keras Dense / GRUCell calls inside RSSM.obs_step / img_step and ActionDecoder.__call__
+// [REF ros_agent/models/dreamer/models.py:63-90, 307-332].
+#pragma once
+#include <cuda.h>
+
+#include "rd_common.cuh"
+
+#define GM_BM 128
+#define GM_BN 64
+#define GM_BK 32                      // float32 elements per K block = one 128-byte swizzle row
+#define GM_STAGES 4
+#define GM_A_BYTES (GM_BM * 128)      // 16 KB
+#define GM_W_BYTES (GM_BN * 128)      // 8 KB
+#define GM_THREADS 192                // warp 0: TMA producer, warp 1: TMEM allocator + MMA issuer, warps 2-5: epilogue
+#define GM_STOCH 30                   // RSSM stochastic state size of the shipped agents [REF racing_dreamer.py:20]
+
+struct GemmPhase {
+  int k_blocks;     // number of 32-wide K blocks of this phase
+  int a_k0;         // first K element in the phase's A tensor map
+  int w_k0;         // first K element in the phase's W tensor map
+  int nb;           // weight slabs per block (1..3)
+  int w_row0[3];    // first W row of each slab (the CTA's n0 is added)
+  int acc[3];       // accumulator fed by each slab
+};
+
+enum { EPI_DENSE = 0, EPI_GRU = 1, EPI_STOCH = 2, EPI_ACTOR = 3 };
+enum { GM_NOISE_ZERO = 0, GM_NOISE_PHILOX = 1, GM_NOISE_EXPLICIT = 2 };
+#define RD_STREAM_STOCH 0x53544f43u
+#define RD_STREAM_ACTOR 0x41435452u
+
+struct GemmArgs {
+  int M, N;                 // rows (envs), valid output columns
+  int n_phases;
+  GemmPhase ph[2];
+  const float* bias;        // [N]; GRU: [2][3N] (input side, recurrent side; gates z, r, h)
+  float* out; int ldo;      // DENSE / GRU: output rows (TF32-rounded: they are only ever read as MMA operands)
+  int act;                  // DENSE: 1 = ELU, 0 = linear
+  const float* hold; int ldh;   // GRU: previous deterministic state
+  // STOCH / ACTOR
+  int noise;                // GM_NOISE_*
+  const float* eps; int ld_eps;   // explicit standard-normal draws: STOCH [M][30], ACTOR [M][n_samples*2]
+  uint32_t key0, key1, step, gid0;
+  float* dbg;               // STOCH: [M][60] mean | std; ACTOR: [M][8] mean0 mean1 std0 std1 a0 a1 logp index
+  float* actions;           // ACTOR: [M][2] agent-facing action (what rd_step reads)
+  float* feat; int ldf;     // STOCH: stoch -> feat[row][0..29]; ACTOR: action -> feat[row][30..31]
+  const float* bn;          // ACTOR "normalized" head: [4][4] gamma, beta, moving_mean, moving_variance (or null)
+  float raw_init_std, min_std, mean_scale, bn_eps;
+  int n_samples;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gm_tma_2d(uint32_t dst_smem, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          dst_smem),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(rd_smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void gm_prefetch_map(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+// bounded wait: a broken pipeline traps (the launch fails) instead of hanging the device
+__device__ __forceinline__ void gm_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = rd_smem_u32(bar);
+  for (uint32_t spins = 0;; ++spins) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (spins > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void gm_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void gm_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void gm_tmem_alloc(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(rd_smem_u32(slot)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void gm_tmem_free(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void gm_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(rd_smem_u32(bar))
+               : "memory");
+}
+// K-major operand tile in shared memory, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start >> 4 | LBO 1 << 16 | SBO 64 << 32 | version 1 << 46 | SWIZZLE_128B 2 << 61)
+__device__ __forceinline__ uint64_t gm_smem_desc(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// cute::UMMA::InstrDescriptor: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), both K-major, N >> 3 at bit 17, M >> 4 at 24
+#define GM_IDESC ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GM_BN >> 3) << 17) | ((uint32_t)(GM_BM >> 4) << 24))
+__device__ __forceinline__ void gm_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(GM_IDESC), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 bit x N columns: thread i of the warp receives TMEM lane (lane_base + i), N consecutive columns
+__device__ __forceinline__ void gm_tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void gm_tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float gm_round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float gm_elu(float x) { return x > 0.f ? x : expm1f(x); }
+__device__ __forceinline__ float gm_softplus(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float gm_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+// four standard normals from one Philox block (Box-Muller on (0,1] uniforms)
+__device__ __forceinline__ void gm_normal4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                           float (&z)[4]) {
+  uint32_t c[4] = {c0, c1, c2, c3};
+  philox4x32_10(c, k0, k1);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float u1 = ((float)(c[2 * h] >> 8) + 1.0f) * (1.0f / 16777216.0f);   // (0, 1]
+    const float u2 = (float)(c[2 * h + 1] >> 8) * (1.0f / 16777216.0f);        // [0, 1)
+    const float r = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    z[2 * h] = r * cs;
+    z[2 * h + 1] = r * sn;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------------------
+template <int EPI, int NSLAB, int NACC>
+__global__ void __launch_bounds__(GM_THREADS, 1)
+    k_dense(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+            const __grid_constant__ CUtensorMap mapW0, const __grid_constant__ CUtensorMap mapW1, const GemmArgs g) {
+  extern __shared__ uint8_t gm_smem_raw[];
+  __shared__ uint64_t full_bar[GM_STAGES], empty_bar[GM_STAGES], acc_bar;
+  __shared__ uint32_t tmem_slot;
+  constexpr uint32_t STAGE_BYTES = GM_A_BYTES + NSLAB * GM_W_BYTES;
+  constexpr uint32_t TM_COLS = (NACC * GM_BN <= 64) ? 64 : (NACC * GM_BN <= 128 ? 128 : 256);
+  const uint32_t smem_base = (rd_smem_u32(gm_smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles: 1024-byte aligned
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * GM_BM, n0 = blockIdx.y * GM_BN;
+
+  if (threadIdx.x == 0) {
+    gm_prefetch_map(&mapA0);
+    gm_prefetch_map(&mapW0);
+    if (g.n_phases > 1) { gm_prefetch_map(&mapA1); gm_prefetch_map(&mapW1); }
+#pragma unroll
+    for (int s = 0; s < GM_STAGES; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(rd_smem_u32(&full_bar[s])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(rd_smem_u32(&empty_bar[s])));
+    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(rd_smem_u32(&acc_bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) gm_tmem_alloc(&tmem_slot, TM_COLS);
+  gm_tc_fence_before();
+  __syncthreads();
+  gm_tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ===== TMA producer =====
+      uint32_t it = 0;
+      for (int p = 0; p < g.n_phases; ++p) {
+        const GemmPhase& ph = g.ph[p];
+        const CUtensorMap* ma = p == 0 ? &mapA0 : &mapA1;
+        const CUtensorMap* mw = p == 0 ? &mapW0 : &mapW1;
+        for (int kb = 0; kb < ph.k_blocks; ++kb, ++it) {
+          const uint32_t s = it % GM_STAGES, par = (it / GM_STAGES) & 1u;
+          gm_mbar_wait(&empty_bar[s], par ^ 1u);
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          rd_mbar_expect_tx(&full_bar[s], GM_A_BYTES + ph.nb * GM_W_BYTES);
+          gm_tma_2d(sa, ma, ph.a_k0 + kb * GM_BK, m0, &full_bar[s]);
+          for (int i = 0; i < ph.nb; ++i)
+            gm_tma_2d(sa + GM_A_BYTES + i * GM_W_BYTES, mw, ph.w_k0 + kb * GM_BK, ph.w_row0[i] + n0, &full_bar[s]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {   // ===== MMA issuer =====
+      uint32_t it = 0, touched = 0;
+      for (int p = 0; p < g.n_phases; ++p) {
+        const GemmPhase& ph = g.ph[p];
+        for (int kb = 0; kb < ph.k_blocks; ++kb, ++it) {
+          const uint32_t s = it % GM_STAGES, par = (it / GM_STAGES) & 1u;
+          gm_mbar_wait(&full_bar[s], par);
+          gm_tc_fence_after();
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          for (int i = 0; i < ph.nb; ++i) {
+            const uint32_t d = tmem + (uint32_t)(ph.acc[i] * GM_BN);
+            const uint32_t sw = sa + GM_A_BYTES + i * GM_W_BYTES;
+#pragma unroll
+            for (int k = 0; k < GM_BK / 8; ++k)   // UMMA_K = 8 TF32 = 32 bytes along the swizzled row
+              gm_mma_tf32(d, gm_smem_desc(sa + k * 32), gm_smem_desc(sw + k * 32), ((touched >> ph.acc[i]) & 1u) | (uint32_t)(k > 0));
+            touched |= 1u << ph.acc[i];
+          }
+          gm_commit(&empty_bar[s]);   // the slot is free once these MMAs have read it
+        }
+      }
+      gm_commit(&acc_bar);            // accumulators complete
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 = tile rows =====
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+    gm_mbar_wait(&acc_bar, 0);
+    gm_tc_fence_after();
+    const bool live = row < g.M;
+    if constexpr (EPI == EPI_DENSE) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < GM_BN; c0 += 16) {
+        if (n0 + c0 >= g.N) break;   // warp-uniform
+        float v[16];
+        gm_tmem_ld16(tl + c0, v);
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const int col = n0 + c0 + j;
+          if (live && col < g.N) {   // N % 4 == 0
+            float4 o;
+            float* po = &o.x;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              float x = v[j + t] + __ldg(g.bias + col + t);
+              if (g.act) x = gm_elu(x);
+              po[t] = gm_round_tf32(x);
+            }
+            *reinterpret_cast<float4*>(g.out + (size_t)row * g.ldo + col) = o;
+          }
+        }
+      }
+    } else if constexpr (EPI == EPI_GRU) {
+      // tf.keras GRUCell (reset_after=True): z, r, h gates; bias[0] input side, bias[1] recurrent side
+      const int H = g.N;
+      const float* bx = g.bias;
+      const float* bh = g.bias + 3 * H;
+#pragma unroll 1
+      for (int c0 = 0; c0 < GM_BN; c0 += 8) {
+        if (n0 + c0 >= H) break;
+        float az[8], ar[8], axh[8], arh[8];
+        gm_tmem_ld8(tl + 0 * GM_BN + c0, az);
+        gm_tmem_ld8(tl + 1 * GM_BN + c0, ar);
+        gm_tmem_ld8(tl + 2 * GM_BN + c0, axh);
+        gm_tmem_ld8(tl + 3 * GM_BN + c0, arh);
+#pragma unroll
+        for (int j = 0; j < 8; j += 4) {
+          const int col = n0 + c0 + j;
+          if (live && col < H) {
+            const float4 hp = *reinterpret_cast<const float4*>(g.hold + (size_t)row * g.ldh + col);
+            const float* ph_ = &hp.x;
+            float4 o;
+            float* po = &o.x;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int c = col + t;
+              const float z = gm_sigmoid((az[j + t] + __ldg(bx + c)) + __ldg(bh + c));
+              const float r = gm_sigmoid((ar[j + t] + __ldg(bx + H + c)) + __ldg(bh + H + c));
+              const float hh = tanhf((axh[j + t] + __ldg(bx + 2 * H + c)) + r * (arh[j + t] + __ldg(bh + 2 * H + c)));
+              po[t] = gm_round_tf32(z * ph_[t] + (1.f - z) * hh);
+            }
+            *reinterpret_cast<float4*>(g.out + (size_t)row * g.ldo + col) = o;
+          }
+        }
+      }
+    } else if constexpr (EPI == EPI_STOCH) {
+      // RSSM posterior [REF models.py:69-73]: mean, std = split(x); std = softplus(std) + 0.1; stoch = mean + std * eps
+      float lo[32], hi[32];
+      {
+        float t[16];
+        gm_tmem_ld16(tl + 0, t);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) lo[i] = t[i];
+        gm_tmem_ld16(tl + 16, t);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) lo[16 + i] = t[i];
+        gm_tmem_ld16(tl + 32, t);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hi[i] = t[i];
+        gm_tmem_ld16(tl + 48, t);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hi[16 + i] = t[i];
+      }
+      if (live) {
+        float* frow = g.feat + (size_t)row * g.ldf;
+        const uint32_t gid = g.gid0 + (uint32_t)row;
+#pragma unroll
+        for (int j0 = 0; j0 < 32; j0 += 4) {
+          float z[4] = {0.f, 0.f, 0.f, 0.f};
+          if (g.noise == GM_NOISE_PHILOX) gm_normal4(gid, g.step, (uint32_t)j0, RD_STREAM_STOCH, g.key0, g.key1, z);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int j = j0 + t;
+            if (j < GM_STOCH) {
+              const float mean = lo[j] + __ldg(g.bias + j);
+              const float sraw = (j + GM_STOCH < 32 ? lo[(j + GM_STOCH) & 31] : hi[(j + GM_STOCH - 32) & 31]) + __ldg(g.bias + GM_STOCH + j);
+              const float sd = gm_softplus(sraw) + 0.1f;
+              float e = z[t];
+              if (g.noise == GM_NOISE_EXPLICIT) e = g.eps[(size_t)row * g.ld_eps + j];
+              frow[j] = gm_round_tf32(mean + sd * e);
+              if (g.dbg) { g.dbg[(size_t)row * 2 * GM_STOCH + j] = mean; g.dbg[(size_t)row * 2 * GM_STOCH + GM_STOCH + j] = sd; }
+            }
+          }
+        }
+      }
+    } else {
+      // ActionDecoder head [REF models.py:323-346] + SampleDist.mode() [REF ros_agent/helpers/tools.py:70-73]
+      float v[8];
+      gm_tmem_ld8(tl, v);
+      if (live) {
+        float x[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) x[t] = v[t] + __ldg(g.bias + t);
+        float mean[2], sd[2];
+        if (g.bn) {   // 'normalized_tanhtransformed_normal': BatchNormalization in inference mode, linear mean
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            x[t] = (x[t] - __ldg(g.bn + 8 + t)) * (__ldg(g.bn + t) * rsqrtf(__ldg(g.bn + 12 + t) + g.bn_eps)) + __ldg(g.bn + 4 + t);
+          mean[0] = x[0]; mean[1] = x[1];
+          sd[0] = gm_softplus(x[2]) + g.min_std; sd[1] = gm_softplus(x[3]) + g.min_std;
+        } else {      // 'tanh_normal'
+          mean[0] = g.mean_scale * tanhf(x[0] / g.mean_scale); mean[1] = g.mean_scale * tanhf(x[1] / g.mean_scale);
+          sd[0] = gm_softplus(x[2] + g.raw_init_std) + g.min_std; sd[1] = gm_softplus(x[3] + g.raw_init_std) + g.min_std;
+        }
+        // mode(): argmax over n_samples draws of log_prob(tanh(u)), u ~ N(mean, sd): the Normal's log density minus
+        // the tanh bijector's forward log-det-Jacobian 2 (log 2 - u - softplus(-2u)), summed over the two actions
+        const float log2f_ = 0.69314718f, half_log_2pi = 0.91893853f;
+        const uint32_t gid = g.gid0 + (uint32_t)row;
+        float best = -INFINITY, bu0 = mean[0], bu1 = mean[1];
+        int bi = -1;
+        if (g.noise == GM_NOISE_ZERO) {
+          bi = 0;
+          best = 0.f;
+#pragma unroll
+          for (int d = 0; d < 2; ++d) {
+            const float u = mean[d];
+            best += (-logf(sd[d]) - half_log_2pi) - 2.f * ((log2f_ - u) - gm_softplus(-2.f * u));
+          }
+        } else {
+          for (int s0 = 0; s0 < g.n_samples; s0 += 2) {
+            float z[4] = {0.f, 0.f, 0.f, 0.f};
+            if (g.noise == GM_NOISE_PHILOX) gm_normal4(gid, g.step, (uint32_t)s0, RD_STREAM_ACTOR, g.key0, g.key1, z);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int s = s0 + h;
+              if (s >= g.n_samples) break;
+              float lp = 0.f, u[2];
+#pragma unroll
+              for (int d = 0; d < 2; ++d) {
+                const float e = (g.noise == GM_NOISE_EXPLICIT) ? g.eps[(size_t)row * g.ld_eps + 2 * s + d] : z[2 * h + d];
+                u[d] = mean[d] + sd[d] * e;
+                lp += ((-0.5f * e * e - logf(sd[d])) - half_log_2pi) - 2.f * ((log2f_ - u[d]) - gm_softplus(-2.f * u[d]));
+              }
+              if (lp > best) { best = lp; bu0 = u[0]; bu1 = u[1]; bi = s; }   // tf.argmax: first maximum
+            }
+          }
+        }
+        const float a0 = tanhf(bu0), a1 = tanhf(bu1);
+        g.actions[2 * (size_t)row] = a0;
+        g.actions[2 * (size_t)row + 1] = a1;
+        float* frow = g.feat + (size_t)row * g.ldf;
+        frow[GM_STOCH] = gm_round_tf32(a0);
+        frow[GM_STOCH + 1] = gm_round_tf32(a1);
+        if (g.dbg) {
+          float* d = g.dbg + (size_t)row * 8;
+          d[0] = mean[0]; d[1] = mean[1]; d[2] = sd[0]; d[3] = sd[1]; d[4] = a0; d[5] = a1; d[6] = best; d[7] = (float)bi;
+        }
+      }
+    }
+    gm_tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    gm_tc_fence_after();
+    gm_tmem_free(tmem, TM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side: tensor maps and launches
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*gm_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point: the library keeps no link-time dependency on
+// libcuda, so it still loads (and exports its symbols) on a machine without a driver.
+static inline gm_encode_fn gm_get_encoder() {
+  static gm_encode_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (gm_encode_fn)p;
+  }
+  return fn;
+}
+
+// float32 matrix [rows][inner] with row pitch ld (elements); box = 32 x box_rows, 128-byte swizzle, zero fill
+static inline bool gm_make_map(CUtensorMap* m, const float* base, uint64_t inner, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+  gm_encode_fn enc = gm_get_encoder();
+  if (!enc) return false;
+  if (((uintptr_t)base & 15u) || ((ld * 4) & 15u)) return false;
+  cuuint64_t gdim[2] = {inner, rows};
+  cuuint64_t gstr[1] = {ld * 4};
+  cuuint32_t box[2] = {GM_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int EPI, int NSLAB, int NACC>
+static inline cudaError_t gm_launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w0, const CUtensorMap& w1,
+                                    const GemmArgs& g, cudaStream_t s) {
+  constexpr size_t smem = (size_t)GM_STAGES * (GM_A_BYTES + NSLAB * GM_W_BYTES) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_dense<EPI, NSLAB, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  dim3 grid((unsigned)((g.M + GM_BM - 1) / GM_BM), (unsigned)((g.N + GM_BN - 1) / GM_BN));
+  k_dense<EPI, NSLAB, NACC><<<grid, GM_THREADS, smem, s>>>(a0, a1, w0, w1, g);
+  return cudaGetLastError();
+}
