@@ -78,7 +78,8 @@ typedef struct rd_vehicle {
   double v_switch, a_max, v_min, v_max;       /* CommonRoad acceleration constraint */
   double v_kinematic;                         /* |v| below this: kinematic model */
   double a_drive, a_brake, c_drag;            /* motor>=0: a = motor*a_drive - c_drag*v ; motor<0: braking */
-  double steer_gain;                          /* steer target = steering * steer_gain * steer_max */
+  double steer_gain;                          /* steer target = steering * steer_gain * steer_max; default -1: a positive
+                                               * steering action turns right [REF ros_agent/agents/dreamer/src/agent.py:111] */
   double body_length, body_width;             /* collision footprint (centred on the pose) */
 } rd_vehicle;
 
@@ -220,6 +221,51 @@ int rd_policy_gap_follower(rd_env* env, const float* lidar_dev, const float* spe
  * hold the current observation (rd_reset / previous rd_step with the same `out`).  The actions of the last step are
  * left in actions_dev (f32 [N,2], may be NULL). */
 int rd_rollout_gap_follower(rd_env* env, int n_steps, const rd_outputs* out, float* actions_dev, void* stream);
+
+/* Dreamer agent: replaces RacingDreamer.action [REF ros_agent/models/dreamer/racing_dreamer.py:62-82] =
+ * _preprocess_lidar -> RSSM.obs_step [REF ros_agent/models/dreamer/models.py:63-90] -> ActionDecoder(feat)
+ * [REF models.py:307-346] -> SampleDist.mode() [REF ros_agent/helpers/tools.py:70-73], one agent per env, the recurrent
+ * state (stoch, deter, previous action) kept by the handle and zeroed whenever the env is reset (`state is None`
+ * [REF racing_dreamer.py:66-68]).  Every Dense / GRUCell is one launch of the tcgen05 kernel k_dense (TF32 tensor-core
+ * products of hi/lo split float32 operands, float32 accumulation, csrc/rd_gemm.cuh).  Weights are HOST pointers in the checkpoint's own layout (Keras kernels
+ * [in][out], the pickled `variables` of rssm.pkl / actor.pkl [REF ros_agent/helpers/tools.py:25-33]). */
+typedef struct rd_dreamer_weights {
+  int32_t stoch, deter, hidden, embed, actor_units, actor_layers;   /* 30, 200, 200, n_beams, 400, 4 */
+  const float* gru_kernel;      /* [hidden][3*deter]  gates z | r | h  (tf.keras GRUCell, reset_after=True) */
+  const float* gru_recurrent;   /* [deter][3*deter] */
+  const float* gru_bias;        /* [2][3*deter]: input side, recurrent side */
+  const float* img1_w; const float* img1_b;   /* [stoch+2][hidden], [hidden] */
+  const float* obs1_w; const float* obs1_b;   /* [deter+embed][hidden], [hidden] */
+  const float* obs2_w; const float* obs2_b;   /* [hidden][2*stoch], [2*stoch] */
+  const float* actor_w[8]; const float* actor_b[8];   /* h0..h{L-1} then hout: [stoch+deter][units], [units][units].., [units][4] */
+  const float* bn;              /* NULL ('tanh_normal') or [4][4] gamma, beta, moving_mean, moving_variance ('normalized_...') */
+  float init_std, min_std, mean_scale, bn_eps;   /* 5, 1e-4, 5, 1e-3 */
+  int32_t n_samples;            /* SampleDist samples: 100 */
+  int32_t precision;            /* RD_PRECISION_* */
+} rd_dreamer_weights;
+/* arithmetic of the Dense / GRU products (accumulation is float32 either way) */
+enum { RD_PRECISION_TF32X3 = 0,  /* hi/lo split operands, three tensor-core passes: float32-grade (the reference computes in float32) */
+       RD_PRECISION_TF32 = 1     /* one TF32 pass (10-bit operand mantissas): ~1e-3 relative per layer, fastest */ };
+/* noise: where the standard-normal draws of the posterior sample and of SampleDist come from */
+enum { RD_NOISE_ZERO = 0,      /* none: stoch = mean, action = tanh(actor mean)  [NEW-SPEC, deterministic evaluation] */
+       RD_NOISE_PHILOX = 1,    /* Philox(cfg.seed; env id, policy step)          [NEW-SPEC, the reference uses TF's RNG] */
+       RD_NOISE_EXPLICIT = 2   /* caller-provided draws (teacher-forced parity tests) */ };
+#define RD_DREAMER_DEBUG_FLOATS 68   /* per env: posterior mean[30] std[30] | actor mean[2] std[2] action[2] log_prob index */
+/* Uploads the weights (transposed to K-major, lidar normalisation x/15 - 0.5 folded into obs1 unless the env emits
+ * normalised scans) and allocates the per-env latent state; idempotent (a second call replaces weights, clears state). */
+int rd_policy_dreamer_init(rd_env* env, const rd_dreamer_weights* w);
+/* One agent step per env.  lidar_dev f32 [N, n_beams] (an rd_step / rd_reset output), actions_dev f32 [N,2]
+ * agent-facing (what rd_step takes; its rescale is postprocess_action [REF racing_dreamer.py:54-60]).
+ * eps_stoch_dev f32 [N,30] and eps_actor_dev f32 [N, n_samples, 2] are read when noise == RD_NOISE_EXPLICIT.
+ * debug_dev: NULL or f32 [N*60] posterior (mean|std) followed by [N*8] actor diagnostics. */
+int rd_policy_dreamer(rd_env* env, const float* lidar_dev, float* actions_dev, int noise, const float* eps_stoch_dev,
+                      const float* eps_actor_dev, float* debug_dev, void* stream);
+/* latent state access: stoch f32 [N,30], deter f32 [N,deter], action f32 [N,2] (any may be NULL) */
+int rd_policy_dreamer_get_state(rd_env* env, float* stoch_dev, float* deter_dev, float* action_dev, void* stream);
+int rd_policy_dreamer_set_state(rd_env* env, const float* stoch_dev, const float* deter_dev, const float* action_dev,
+                                void* stream);
+/* n_steps x (agent step -> rd_step) enqueued on `stream` with no host synchronisation (see rd_rollout_gap_follower). */
+int rd_rollout_dreamer(rd_env* env, int n_steps, const rd_outputs* out, float* actions_dev, int noise, void* stream);
 
 /* ---- stage entry points (teacher-forced parity tests; each is one kernel of the step) ---- */
 /* a2 LiDAR [REF dreamer/scenarios/max_progress/austria.yml:7 'lidar' sensor]: poses f64 [n,3]=(x,y,yaw),

@@ -85,7 +85,7 @@ ORC_API void orc_default_config(rd_config* c) {
   v->v_switch = 7.319; v->a_max = 9.51; v->v_min = 0.0; v->v_max = 5.0;
   v->v_kinematic = 0.5;
   v->a_drive = 6.0; v->a_brake = 8.26; v->c_drag = 1.0;
-  v->steer_gain = 1.0;
+  v->steer_gain = -1.0;  /* positive steering action = right turn [REF ros_agent/agents/dreamer/src/agent.py:111] */
   v->body_length = 0.50; v->body_width = 0.27;
 }
 

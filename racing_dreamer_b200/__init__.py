@@ -17,7 +17,7 @@ def __getattr__(name):
     if name in ("RaceCarGymCompat", "ReferenceEnv", "make_reference_env", "load_scenario"):
         from . import compat as _compat
         return getattr(_compat, name)
-    if name == "GapFollowerPolicy":
+    if name in ("GapFollowerPolicy", "DreamerPolicy", "load_dreamer_checkpoint", "save_dreamer_checkpoint"):
         from . import policy as _policy
-        return _policy.GapFollowerPolicy
+        return getattr(_policy, name)
     raise AttributeError(name)

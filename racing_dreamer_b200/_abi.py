@@ -96,12 +96,28 @@ class RdGapFollower(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class RdDreamerWeights(C.Structure):
+    """rd_dreamer_weights (include/rd_env.h): host pointers to a Dreamer checkpoint's arrays, Keras layout."""
+    _fields_ = [(n, C.c_int32) for n in ("stoch", "deter", "hidden", "embed", "actor_units", "actor_layers")] + [
+        (n, C.c_void_p) for n in ("gru_kernel", "gru_recurrent", "gru_bias", "img1_w", "img1_b", "obs1_w", "obs1_b",
+                                  "obs2_w", "obs2_b")] + [
+        ("actor_w", C.c_void_p * 8), ("actor_b", C.c_void_p * 8), ("bn", C.c_void_p),
+        ("init_std", C.c_float), ("min_std", C.c_float), ("mean_scale", C.c_float), ("bn_eps", C.c_float),
+        ("n_samples", C.c_int32), ("precision", C.c_int32)]
+
+
+RD_NOISE_ZERO, RD_NOISE_PHILOX, RD_NOISE_EXPLICIT = 0, 1, 2
+RD_DREAMER_DEBUG_FLOATS = 68
+RD_PRECISION_TF32X3, RD_PRECISION_TF32 = 0, 1
+
 EXPORTS = (
     "rd_default_config", "rd_create", "rd_destroy", "rd_last_error", "rd_abi_version", "rd_upload_map",
     "rd_assign_maps", "rd_reset", "rd_step", "rd_lidar_cast", "rd_occupancy_obs", "rd_dynamics",
     "rd_get_state", "rd_set_state", "rd_read_stats", "rd_launch_count", "rd_enable_timing", "rd_read_timing",
     "rd_host_init", "rd_reset_host", "rd_step_host",
     "rd_gap_follower_defaults", "rd_policy_gap_follower_init", "rd_policy_gap_follower", "rd_rollout_gap_follower",
+    "rd_policy_dreamer_init", "rd_policy_dreamer", "rd_policy_dreamer_get_state", "rd_policy_dreamer_set_state",
+    "rd_rollout_dreamer",
 )
 
 LIB_PATH = Path(__file__).resolve().parent / "librd_env.so"
@@ -178,6 +194,16 @@ def load_library() -> C.CDLL:
     lib.rd_policy_gap_follower.restype = i32
     lib.rd_rollout_gap_follower.argtypes = [vp, i32, C.POINTER(RdOutputs), vp, vp]
     lib.rd_rollout_gap_follower.restype = i32
+    lib.rd_policy_dreamer_init.argtypes = [vp, C.POINTER(RdDreamerWeights)]
+    lib.rd_policy_dreamer_init.restype = i32
+    lib.rd_policy_dreamer.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
+    lib.rd_policy_dreamer.restype = i32
+    lib.rd_policy_dreamer_get_state.argtypes = [vp, vp, vp, vp, vp]
+    lib.rd_policy_dreamer_get_state.restype = i32
+    lib.rd_policy_dreamer_set_state.argtypes = [vp, vp, vp, vp, vp]
+    lib.rd_policy_dreamer_set_state.restype = i32
+    lib.rd_rollout_dreamer.argtypes = [vp, i32, C.POINTER(RdOutputs), vp, i32, vp]
+    lib.rd_rollout_dreamer.restype = i32
     if lib.rd_abi_version() != ABI_VERSION:
         raise NativeLibraryError(f"{path}: ABI version {lib.rd_abi_version()} != {ABI_VERSION}")
     _lib = lib

@@ -196,7 +196,7 @@ __device__ __forceinline__ void rd_reset_one(const StepParams& P, int e, int mod
   I[(size_t)RD_I_FLAGS * n + e] = 0;
   I[(size_t)RD_I_AGENT_STEP * n + e] = 0;
   I[(size_t)RD_I_EPISODE * n + e] = (int32_t)(episode + 1u);
-  if (P.pol.i32) rd_policy_clear(P.pol, n, e);
+  if (P.pol.i32 || P.pol.dr_feat) rd_policy_clear(P.pol, n, e);
 }
 
 // observation scalars + the origin record for the LiDAR / occupancy kernels, from the committed state

@@ -20,6 +20,7 @@
 #include "rd_lidar.cuh"
 #include "rd_occupancy.cuh"
 #include "rd_policy.cuh"
+#include "rd_dreamer.cuh"
 
 #define RD_API extern "C" __attribute__((visibility("default")))
 
@@ -90,6 +91,7 @@ struct rd_env {
     float* d_actions = nullptr;   // [n][2] rollout scratch
     bool attr_set = false;        // kernel opted in to > 48 KB of dynamic shared memory
   } pol;
+  DreamerPolicy dr;   // on-device Dreamer agent (rd_policy_dreamer_init)
   // optional per-kernel timing (rd_enable_timing)
   bool timing = false;
   struct Timed { cudaEvent_t a, b; int kind; };
@@ -160,7 +162,10 @@ void default_config(rd_config* c) {
   v->v_switch = 7.319; v->a_max = 9.51; v->v_min = 0.0; v->v_max = 5.0;  // [REF racing_dreamer.py:16]
   v->v_kinematic = 0.5;
   v->a_drive = 6.0; v->a_brake = 8.26; v->c_drag = 1.0;  // [REF ros_agent/agents/follow_the_gap/src/agent.py:74]
-  v->steer_gain = 1.0;
+  // sign: a positive steering action turns RIGHT, as in the reference's simulator (racecar_gym drives the steering joint to
+  // -steering * max_angle); in-tree evidence: the ROS node negates the agent's steering for the left-positive Ackermann
+  // message [REF ros_agent/agents/dreamer/src/agent.py:111], and the shipped Dreamer agents only drive with this sign.
+  v->steer_gain = -1.0;
   v->body_length = 0.50; v->body_width = 0.27;
 }
 
@@ -276,6 +281,7 @@ StepParams step_params(rd_env* env) {
   P.cfg = env->cfg;
   P.f64 = env->d_f64; P.i32 = env->d_i32; P.stats = env->d_stats; P.recs = env->d_recs; P.maps = env->d_maps;
   P.pol = env->pol.st;
+  if (env->dr.ready) { P.pol.dr_feat = env->dr.feat[env->dr.cur].p[0]; P.pol.dr_feat_lo = env->dr.feat[env->dr.cur].p[1]; P.pol.dr_ld = env->dr.ldf; }
   P.n = env->n;
   return P;
 }
@@ -405,6 +411,7 @@ RD_API void rd_destroy(rd_env* env) {
   cudaFree(env->d_beam_tab); cudaFree(env->d_maps); cudaFree(env->d_env_order); cudaFree(env->d_lidar_ctr);
   cudaFree(env->d_stage_recs); cudaFree(env->d_stage_ids);
   cudaFree(env->pol.st.f64); cudaFree(env->pol.st.i32); cudaFree(env->pol.d_actions);
+  dreamer_free(env->dr);
   occ_free(env->occ);
   {
     auto& h = env->hp;
@@ -816,6 +823,74 @@ RD_API int rd_rollout_gap_follower(rd_env* env, int n_steps, const rd_outputs* o
   float* act = actions_dev ? actions_dev : env->pol.d_actions;
   for (int k = 0; k < n_steps; ++k) {
     int rc = launch_gap_follower(env, out->lidar_dev, nullptr, act, nullptr, (cudaStream_t)stream);
+    if (rc) return rc;
+    if ((rc = rd_step(env, act, out, stream))) return rc;
+  }
+  return RD_OK;
+}
+
+RD_API int rd_policy_dreamer_init(rd_env* env, const rd_dreamer_weights* w) {
+  if (!env) return fail(nullptr, RD_ERR_INVALID, "null handle");
+  const int rc = dreamer_init(env->dr, env->n, env->cfg.n_beams, (env->cfg.obs_flags & RD_OBS_LIDAR_NORM) != 0, w);
+  if (rc) return fail(env, rc, "rd_policy_dreamer_init: %s", env->dr.err.c_str());
+  if (!env->pol.d_actions) {
+    CUDA_TRY(env, cudaMalloc(&env->pol.d_actions, sizeof(float) * 2 * (size_t)env->n));
+    CUDA_TRY(env, cudaMemset(env->pol.d_actions, 0, sizeof(float) * 2 * (size_t)env->n));
+  }
+  return RD_OK;
+}
+
+namespace {
+int launch_dreamer(rd_env* env, const float* lidar_dev, float* actions_dev, int noise, const float* eps_stoch_dev,
+                   const float* eps_actor_dev, float* debug_dev, cudaStream_t s) {
+  int launched = 0, rc;
+  {
+    ScopedTiming tm(env, s, T_POLICY);
+    rc = dreamer_step(env->dr, lidar_dev, actions_dev, noise, eps_stoch_dev, eps_actor_dev, debug_dev, env->cfg.seed,
+                      (uint32_t)env->cfg.env_id_offset, s, &launched);
+  }
+  env->launches += launched;
+  if (rc) return fail(env, rc, "rd_policy_dreamer: %s", env->dr.err.c_str());
+  return RD_OK;
+}
+}  // namespace
+
+RD_API int rd_policy_dreamer(rd_env* env, const float* lidar_dev, float* actions_dev, int noise, const float* eps_stoch_dev,
+                             const float* eps_actor_dev, float* debug_dev, void* stream) {
+  if (!env || !lidar_dev || !actions_dev) return fail(env, RD_ERR_INVALID, "null argument");
+  if (!env->dr.ready) return fail(env, RD_ERR_STATE, "rd_policy_dreamer_init has not been called");
+  if (noise < RD_NOISE_ZERO || noise > RD_NOISE_EXPLICIT) return fail(env, RD_ERR_INVALID, "bad noise mode %d", noise);
+  if (noise == RD_NOISE_EXPLICIT && (!eps_stoch_dev || !eps_actor_dev))
+    return fail(env, RD_ERR_INVALID, "RD_NOISE_EXPLICIT needs eps_stoch_dev and eps_actor_dev");
+  return launch_dreamer(env, lidar_dev, actions_dev, noise, eps_stoch_dev, eps_actor_dev, debug_dev, (cudaStream_t)stream);
+}
+
+RD_API int rd_policy_dreamer_get_state(rd_env* env, float* stoch_dev, float* deter_dev, float* action_dev, void* stream) {
+  if (!env) return fail(nullptr, RD_ERR_INVALID, "null handle");
+  if (!env->dr.ready) return fail(env, RD_ERR_STATE, "rd_policy_dreamer_init has not been called");
+  const int rc = dreamer_state_io(env->dr, stoch_dev, deter_dev, action_dev, 0, (cudaStream_t)stream);
+  if (rc) return fail(env, rc, "rd_policy_dreamer_get_state: %s", env->dr.err.c_str());
+  return RD_OK;
+}
+
+RD_API int rd_policy_dreamer_set_state(rd_env* env, const float* stoch_dev, const float* deter_dev, const float* action_dev,
+                                       void* stream) {
+  if (!env) return fail(nullptr, RD_ERR_INVALID, "null handle");
+  if (!env->dr.ready) return fail(env, RD_ERR_STATE, "rd_policy_dreamer_init has not been called");
+  const int rc = dreamer_state_io(env->dr, const_cast<float*>(stoch_dev), const_cast<float*>(deter_dev),
+                                  const_cast<float*>(action_dev), 1, (cudaStream_t)stream);
+  if (rc) return fail(env, rc, "rd_policy_dreamer_set_state: %s", env->dr.err.c_str());
+  return RD_OK;
+}
+
+RD_API int rd_rollout_dreamer(rd_env* env, int n_steps, const rd_outputs* out, float* actions_dev, int noise, void* stream) {
+  if (!env || !out || !out->lidar_dev || n_steps < 0) return fail(env, RD_ERR_INVALID, "bad argument (the rollout needs out->lidar_dev)");
+  if (!env->dr.ready) return fail(env, RD_ERR_STATE, "rd_policy_dreamer_init has not been called");
+  if (noise != RD_NOISE_ZERO && noise != RD_NOISE_PHILOX) return fail(env, RD_ERR_INVALID, "a rollout draws its own noise (RD_NOISE_ZERO or RD_NOISE_PHILOX)");
+  if (!env->was_reset) return fail(env, RD_ERR_STATE, "Must reset environment.");
+  float* act = actions_dev ? actions_dev : env->pol.d_actions;
+  for (int k = 0; k < n_steps; ++k) {
+    int rc = launch_dreamer(env, out->lidar_dev, act, noise, nullptr, nullptr, nullptr, (cudaStream_t)stream);
     if (rc) return rc;
     if ((rc = rd_step(env, act, out, stream))) return rc;
   }

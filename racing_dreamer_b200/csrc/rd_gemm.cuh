@@ -1,6 +1,6 @@
 // rd_gemm.cuh -- the dense layers of the Dreamer agent on the 5th-generation tensor cores.
 //
-// One kernel, k_dense<EPI, NSLAB, NACC>, computes a 128 x 64 tile of  act(A @ W + b)  for a batch of envs:
+// One kernel, k_dense<EPI, NSLAB, NACC, STAGES>, computes a 128 x 64 tile of  act(A @ W + b)  for a batch of envs:
 //   * A (activations, [envs][K] float32, K contiguous) and W (weights, stored transposed [N][K], K contiguous) are
 //     streamed through a 4-stage shared-memory ring by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle, out-of-bounds
 //     rows/columns zero-filled by the copy engine, so no padded copies of anything exist in HBM);
@@ -10,7 +10,16 @@
 //   * four epilogue warps read their 32 TMEM lanes (one env per thread) with tcgen05.ld and apply the layer's
 //     epilogue in registers: bias + ELU, the Keras GRU cell gates, the RSSM posterior sample, or the actor head with
 //     SampleDist.mode() -- so no pre-activation ever reaches HBM.
-// A layer is described by up to two "phases" (K ranges with their own A source: concat([deter, embed]) @ W is two
+// Precision.  kind::tf32 reads 10 mantissa bits of each operand.  With GemmArgs-level "x3" operation every product is
+// evaluated as  hi*hi + lo*hi + hi*lo  (hi = the TF32 rounding of the float32 value, lo = the TF32 rounding of the
+// remainder; weights are split once at upload, activations by the epilogue that produces them): three passes over K
+// into the same float32 accumulator, ~2^-21 relative error per product instead of 2^-11 -- float32-grade results,
+// which is what the reference's TensorFlow computes in.
+// The tensor core adds each instruction's products into the float32 accumulator with truncation, so a long K chain
+// drifts by ~(chain length) x 2^-24 x |partial sum| (measured: 2e-3 on the 1280-term obs1 layer).  The K range of a
+// layer is therefore cut into groups that accumulate in separate TMEM columns, and the epilogue adds the partial
+// sums in round-to-nearest float32; the lo*hi / hi*lo passes get an accumulator of their own.
+// A layer is described by up to twelve "phases" (K ranges with their own A source: concat([deter, embed]) @ W is two
 // phases over one W) and up to three weight slabs per phase feeding up to four accumulators (the GRU's z, r and the
 // two halves of the candidate gate).
 //
@@ -24,13 +33,18 @@
 #define GM_BM 128
 #define GM_BN 64
 #define GM_BK 32                      // float32 elements per K block = one 128-byte swizzle row
-#define GM_STAGES 4
 #define GM_A_BYTES (GM_BM * 128)      // 16 KB
 #define GM_W_BYTES (GM_BN * 128)      // 8 KB
 #define GM_THREADS 192                // warp 0: TMA producer, warp 1: TMEM allocator + MMA issuer, warps 2-5: epilogue
 #define GM_STOCH 30                   // RSSM stochastic state size of the shipped agents [REF racing_dreamer.py:20]
 
+#define GM_MAX_PHASES 12
+struct GemmMaps {   // tensor maps of one launch: A sources and weight matrices, hi parts and (x3 mode) lo parts
+  CUtensorMap a[4];
+  CUtensorMap w[4];
+};
 struct GemmPhase {
+  int a_map, w_map; // indices into GemmMaps
   int k_blocks;     // number of 32-wide K blocks of this phase
   int a_k0;         // first K element in the phase's A tensor map
   int w_k0;         // first K element in the phase's W tensor map
@@ -47,18 +61,20 @@ enum { GM_NOISE_ZERO = 0, GM_NOISE_PHILOX = 1, GM_NOISE_EXPLICIT = 2 };
 struct GemmArgs {
   int M, N;                 // rows (envs), valid output columns
   int n_phases;
-  GemmPhase ph[2];
+  int n_acc;                // accumulators (64 TMEM columns each) per output: the epilogue adds them up (GRU: per gate)
+  GemmPhase ph[GM_MAX_PHASES];
   const float* bias;        // [N]; GRU: [2][3N] (input side, recurrent side; gates z, r, h)
-  float* out; int ldo;      // DENSE / GRU: output rows (TF32-rounded: they are only ever read as MMA operands)
+  float* out; int ldo;      // DENSE / GRU: output rows, TF32-rounded (they are only ever read as MMA operands)
+  float* out_lo;            // x3 mode: TF32-rounded remainder of the same rows (same pitch), or null
   int act;                  // DENSE: 1 = ELU, 0 = linear
-  const float* hold; int ldh;   // GRU: previous deterministic state
+  const float* hold; const float* hold_lo; int ldh;   // GRU: previous deterministic state (hi [+ lo])
   // STOCH / ACTOR
   int noise;                // GM_NOISE_*
   const float* eps; int ld_eps;   // explicit standard-normal draws: STOCH [M][30], ACTOR [M][n_samples*2]
   uint32_t key0, key1, step, gid0;
   float* dbg;               // STOCH: [M][60] mean | std; ACTOR: [M][8] mean0 mean1 std0 std1 a0 a1 logp index
   float* actions;           // ACTOR: [M][2] agent-facing action (what rd_step reads)
-  float* feat; int ldf;     // STOCH: stoch -> feat[row][0..29]; ACTOR: action -> feat[row][30..31]
+  float* feat; float* feat_lo; int ldf;   // STOCH: stoch -> feat[row][0..29]; ACTOR: action -> feat[row][30..31]
   const float* bn;          // ACTOR "normalized" head: [4][4] gamma, beta, moving_mean, moving_variance (or null)
   float raw_init_std, min_std, mean_scale, bn_eps;
   int n_samples;
@@ -141,6 +157,25 @@ __device__ __forceinline__ void gm_tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// the same columns of n_acc accumulators (GM_BN * stride columns apart), added in round-to-nearest float32
+__device__ __forceinline__ void gm_tmem_sum16(uint32_t taddr, int n_acc, int stride, float (&v)[16]) {
+  gm_tmem_ld16(taddr, v);
+  for (int a = 1; a < n_acc; ++a) {
+    float t[16];
+    gm_tmem_ld16(taddr + (uint32_t)(a * stride * GM_BN), t);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += t[i];
+  }
+}
+__device__ __forceinline__ void gm_tmem_sum8(uint32_t taddr, int n_acc, int stride, float (&v)[8]) {
+  gm_tmem_ld8(taddr, v);
+  for (int a = 1; a < n_acc; ++a) {
+    float t[8];
+    gm_tmem_ld8(taddr + (uint32_t)(a * stride * GM_BN), t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += t[i];
+  }
+}
 __device__ __forceinline__ float gm_round_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -169,23 +204,20 @@ __device__ __forceinline__ void gm_normal4(uint32_t c0, uint32_t c1, uint32_t c2
 // ---------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------
-template <int EPI, int NSLAB, int NACC>
+template <int EPI, int NSLAB, int NACC, int GM_STAGES>
 __global__ void __launch_bounds__(GM_THREADS, 1)
-    k_dense(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-            const __grid_constant__ CUtensorMap mapW0, const __grid_constant__ CUtensorMap mapW1, const GemmArgs g) {
+    k_dense(const __grid_constant__ GemmMaps maps, const GemmArgs g) {
   extern __shared__ uint8_t gm_smem_raw[];
   __shared__ uint64_t full_bar[GM_STAGES], empty_bar[GM_STAGES], acc_bar;
   __shared__ uint32_t tmem_slot;
   constexpr uint32_t STAGE_BYTES = GM_A_BYTES + NSLAB * GM_W_BYTES;
-  constexpr uint32_t TM_COLS = (NACC * GM_BN <= 64) ? 64 : (NACC * GM_BN <= 128 ? 128 : 256);
+  constexpr uint32_t TM_COLS = (NACC * GM_BN <= 64) ? 64 : (NACC * GM_BN <= 128 ? 128 : (NACC * GM_BN <= 256 ? 256 : 512));
   const uint32_t smem_base = (rd_smem_u32(gm_smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles: 1024-byte aligned
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * GM_BM, n0 = blockIdx.y * GM_BN;
 
   if (threadIdx.x == 0) {
-    gm_prefetch_map(&mapA0);
-    gm_prefetch_map(&mapW0);
-    if (g.n_phases > 1) { gm_prefetch_map(&mapA1); gm_prefetch_map(&mapW1); }
+    for (int p = 0; p < g.n_phases; ++p) { gm_prefetch_map(&maps.a[g.ph[p].a_map]); gm_prefetch_map(&maps.w[g.ph[p].w_map]); }
 #pragma unroll
     for (int s = 0; s < GM_STAGES; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(rd_smem_u32(&full_bar[s])));
@@ -205,8 +237,8 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
       uint32_t it = 0;
       for (int p = 0; p < g.n_phases; ++p) {
         const GemmPhase& ph = g.ph[p];
-        const CUtensorMap* ma = p == 0 ? &mapA0 : &mapA1;
-        const CUtensorMap* mw = p == 0 ? &mapW0 : &mapW1;
+        const CUtensorMap* ma = &maps.a[ph.a_map];
+        const CUtensorMap* mw = &maps.w[ph.w_map];
         for (int kb = 0; kb < ph.k_blocks; ++kb, ++it) {
           const uint32_t s = it % GM_STAGES, par = (it / GM_STAGES) & 1u;
           gm_mbar_wait(&empty_bar[s], par ^ 1u);
@@ -256,20 +288,23 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
       for (int c0 = 0; c0 < GM_BN; c0 += 16) {
         if (n0 + c0 >= g.N) break;   // warp-uniform
         float v[16];
-        gm_tmem_ld16(tl + c0, v);
+        gm_tmem_sum16(tl + c0, g.n_acc, 1, v);
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
           const int col = n0 + c0 + j;
           if (live && col < g.N) {   // N % 4 == 0
-            float4 o;
+            float4 o, ol;
             float* po = &o.x;
+            float* pl = &ol.x;
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               float x = v[j + t] + __ldg(g.bias + col + t);
               if (g.act) x = gm_elu(x);
               po[t] = gm_round_tf32(x);
+              pl[t] = gm_round_tf32(x - po[t]);
             }
             *reinterpret_cast<float4*>(g.out + (size_t)row * g.ldo + col) = o;
+            if (g.out_lo) *reinterpret_cast<float4*>(g.out_lo + (size_t)row * g.ldo + col) = ol;
           }
         }
       }
@@ -282,27 +317,35 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
       for (int c0 = 0; c0 < GM_BN; c0 += 8) {
         if (n0 + c0 >= H) break;
         float az[8], ar[8], axh[8], arh[8];
-        gm_tmem_ld8(tl + 0 * GM_BN + c0, az);
-        gm_tmem_ld8(tl + 1 * GM_BN + c0, ar);
-        gm_tmem_ld8(tl + 2 * GM_BN + c0, axh);
-        gm_tmem_ld8(tl + 3 * GM_BN + c0, arh);
+        gm_tmem_sum8(tl + 0 * GM_BN + c0, g.n_acc, 4, az);    // accumulator a of gate q sits at column (4 a + q) * 64
+        gm_tmem_sum8(tl + 1 * GM_BN + c0, g.n_acc, 4, ar);
+        gm_tmem_sum8(tl + 2 * GM_BN + c0, g.n_acc, 4, axh);
+        gm_tmem_sum8(tl + 3 * GM_BN + c0, g.n_acc, 4, arh);
 #pragma unroll
         for (int j = 0; j < 8; j += 4) {
           const int col = n0 + c0 + j;
           if (live && col < H) {
-            const float4 hp = *reinterpret_cast<const float4*>(g.hold + (size_t)row * g.ldh + col);
+            float4 hp = *reinterpret_cast<const float4*>(g.hold + (size_t)row * g.ldh + col);
+            if (g.hold_lo) {
+              const float4 hl = *reinterpret_cast<const float4*>(g.hold_lo + (size_t)row * g.ldh + col);
+              hp.x += hl.x; hp.y += hl.y; hp.z += hl.z; hp.w += hl.w;
+            }
             const float* ph_ = &hp.x;
-            float4 o;
+            float4 o, ol;
             float* po = &o.x;
+            float* pl = &ol.x;
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               const int c = col + t;
               const float z = gm_sigmoid((az[j + t] + __ldg(bx + c)) + __ldg(bh + c));
               const float r = gm_sigmoid((ar[j + t] + __ldg(bx + H + c)) + __ldg(bh + H + c));
               const float hh = tanhf((axh[j + t] + __ldg(bx + 2 * H + c)) + r * (arh[j + t] + __ldg(bh + 2 * H + c)));
-              po[t] = gm_round_tf32(z * ph_[t] + (1.f - z) * hh);
+              const float hn = z * ph_[t] + (1.f - z) * hh;
+              po[t] = gm_round_tf32(hn);
+              pl[t] = gm_round_tf32(hn - po[t]);
             }
             *reinterpret_cast<float4*>(g.out + (size_t)row * g.ldo + col) = o;
+            if (g.out_lo) *reinterpret_cast<float4*>(g.out_lo + (size_t)row * g.ldo + col) = ol;
           }
         }
       }
@@ -311,16 +354,16 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
       float lo[32], hi[32];
       {
         float t[16];
-        gm_tmem_ld16(tl + 0, t);
+        gm_tmem_sum16(tl + 0, g.n_acc, 1, t);
 #pragma unroll
         for (int i = 0; i < 16; ++i) lo[i] = t[i];
-        gm_tmem_ld16(tl + 16, t);
+        gm_tmem_sum16(tl + 16, g.n_acc, 1, t);
 #pragma unroll
         for (int i = 0; i < 16; ++i) lo[16 + i] = t[i];
-        gm_tmem_ld16(tl + 32, t);
+        gm_tmem_sum16(tl + 32, g.n_acc, 1, t);
 #pragma unroll
         for (int i = 0; i < 16; ++i) hi[i] = t[i];
-        gm_tmem_ld16(tl + 48, t);
+        gm_tmem_sum16(tl + 48, g.n_acc, 1, t);
 #pragma unroll
         for (int i = 0; i < 16; ++i) hi[16 + i] = t[i];
       }
@@ -340,7 +383,10 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
               const float sd = gm_softplus(sraw) + 0.1f;
               float e = z[t];
               if (g.noise == GM_NOISE_EXPLICIT) e = g.eps[(size_t)row * g.ld_eps + j];
-              frow[j] = gm_round_tf32(mean + sd * e);
+              const float sv = mean + sd * e;
+              const float sh = gm_round_tf32(sv);
+              frow[j] = sh;
+              if (g.feat_lo) g.feat_lo[(size_t)row * g.ldf + j] = gm_round_tf32(sv - sh);
               if (g.dbg) { g.dbg[(size_t)row * 2 * GM_STOCH + j] = mean; g.dbg[(size_t)row * 2 * GM_STOCH + GM_STOCH + j] = sd; }
             }
           }
@@ -349,7 +395,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
     } else {
       // ActionDecoder head [REF models.py:323-346] + SampleDist.mode() [REF ros_agent/helpers/tools.py:70-73]
       float v[8];
-      gm_tmem_ld8(tl, v);
+      gm_tmem_sum8(tl, g.n_acc, 1, v);
       if (live) {
         float x[4];
 #pragma unroll
@@ -402,8 +448,13 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
         g.actions[2 * (size_t)row] = a0;
         g.actions[2 * (size_t)row + 1] = a1;
         float* frow = g.feat + (size_t)row * g.ldf;
-        frow[GM_STOCH] = gm_round_tf32(a0);
-        frow[GM_STOCH + 1] = gm_round_tf32(a1);
+        const float h0 = gm_round_tf32(a0), h1 = gm_round_tf32(a1);
+        frow[GM_STOCH] = h0;
+        frow[GM_STOCH + 1] = h1;
+        if (g.feat_lo) {
+          g.feat_lo[(size_t)row * g.ldf + GM_STOCH] = gm_round_tf32(a0 - h0);
+          g.feat_lo[(size_t)row * g.ldf + GM_STOCH + 1] = gm_round_tf32(a1 - h1);
+        }
         if (g.dbg) {
           float* d = g.dbg + (size_t)row * 8;
           d[0] = mean[0]; d[1] = mean[1]; d[2] = sd[0]; d[3] = sd[1]; d[4] = a0; d[5] = a1; d[6] = best; d[7] = (float)bi;
@@ -416,6 +467,47 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
   if (warp == 1) {
     gm_tc_fence_after();
     gm_tmem_free(tmem, TM_COLS);
+  }
+}
+
+// RacingDreamer._preprocess_lidar [REF ros_agent/models/dreamer/racing_dreamer.py:45-52] in its own float32 arithmetic
+// (clip to [0, 15], / 15, - 0.5; `normalise` = 0 when the env already emits that), then the TF32 split (hi, lo) the
+// tensor-core passes read; lo may be null (single-pass mode).  count % 4 == 0.
+__global__ void __launch_bounds__(256) k_embed_lidar(const float4* __restrict__ src, float4* __restrict__ hi,
+                                                     float4* __restrict__ lo, size_t count4, int normalise) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 x4 = src[i];
+    const float* x = &x4.x;
+    float4 h4, l4;
+    float* h = &h4.x;
+    float* l = &l4.x;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float v = x[t];
+      if (normalise) {
+        v = fminf(fmaxf(v, 0.0f), 15.0f);
+        v = __fsub_rn(__fdiv_rn(__fsub_rn(v, 0.0f), 15.0f), 0.5f);
+      }
+      h[t] = gm_round_tf32(v);
+      l[t] = gm_round_tf32(v - h[t]);
+    }
+    hi[i] = h4;
+    if (lo) lo[i] = l4;
+  }
+}
+// latent rows <-> the reference's state tuple.  dir 0: out = hi + lo; dir 1: (hi, lo) = split(in)
+__global__ void __launch_bounds__(256) k_latent_copy(float* __restrict__ feat, float* __restrict__ feat_lo, int ldf, int col0,
+                                                      int width, float* __restrict__ ext, int n, int dir) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * width) return;
+  const int e = (int)(i / width), c = (int)(i % width);
+  const size_t f = (size_t)e * ldf + col0 + c;
+  if (dir == 0) {
+    ext[i] = feat[f] + (feat_lo ? feat_lo[f] : 0.f);
+  } else {
+    const float x = ext[i], h = gm_round_tf32(x);
+    feat[f] = h;
+    if (feat_lo) feat_lo[f] = gm_round_tf32(x - h);
   }
 }
 
@@ -453,17 +545,16 @@ static inline bool gm_make_map(CUtensorMap* m, const float* base, uint64_t inner
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int EPI, int NSLAB, int NACC>
-static inline cudaError_t gm_launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w0, const CUtensorMap& w1,
-                                    const GemmArgs& g, cudaStream_t s) {
+template <int EPI, int NSLAB, int NACC, int GM_STAGES>
+static inline cudaError_t gm_launch(const GemmMaps& maps, const GemmArgs& g, cudaStream_t s) {
   constexpr size_t smem = (size_t)GM_STAGES * (GM_A_BYTES + NSLAB * GM_W_BYTES) + 1024;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_dense<EPI, NSLAB, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_dense<EPI, NSLAB, NACC, GM_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr = true;
   }
   dim3 grid((unsigned)((g.M + GM_BM - 1) / GM_BM), (unsigned)((g.N + GM_BN - 1) / GM_BN));
-  k_dense<EPI, NSLAB, NACC><<<grid, GM_THREADS, smem, s>>>(a0, a1, w0, w1, g);
+  k_dense<EPI, NSLAB, NACC, GM_STAGES><<<grid, GM_THREADS, smem, s>>>(maps, g);
   return cudaGetLastError();
 }

@@ -21,11 +21,23 @@
 struct PolicyState {
   double* f64;    // [4][n]: PID previous input (NaN = none), PID integral, steering_angle, vehicle_speed
   int32_t* i32;   // [2][n]: scans seen, headings seen (the two "first message" gates of the node)
+  float* dr_feat; // Dreamer agent: current latent rows [n][dr_ld] = stoch | previous action | deter (null: not attached)
+  float* dr_feat_lo;   // their TF32 remainder parts (null in single-pass mode)
+  int dr_ld;
 };
 enum { RD_P_PREV = 0, RD_P_INT, RD_P_STEER, RD_P_SPEED, RD_NP_F64 };
 enum { RD_P_SCANS = 0, RD_P_HEADINGS, RD_NP_I32 };
 
 __device__ __forceinline__ void rd_policy_clear(const PolicyState& ps, int n, int e) {
+  if (ps.dr_feat) {   // `state is None`: zero latent, zero previous action [REF ros_agent/models/dreamer/racing_dreamer.py:66-68]
+    float4* row = reinterpret_cast<float4*>(ps.dr_feat + (size_t)e * ps.dr_ld);
+    for (int k = 0; k < ps.dr_ld / 4; ++k) row[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ps.dr_feat_lo) {
+      float4* lo = reinterpret_cast<float4*>(ps.dr_feat_lo + (size_t)e * ps.dr_ld);
+      for (int k = 0; k < ps.dr_ld / 4; ++k) lo[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  if (!ps.i32) return;
   ps.f64[(size_t)RD_P_PREV * n + e] = __longlong_as_double(0x7ff8000000000000ll);
   ps.f64[(size_t)RD_P_INT * n + e] = 0.0;
   ps.f64[(size_t)RD_P_STEER * n + e] = 0.0;

@@ -38,10 +38,12 @@ int main() {
     CUtensorMap ma, mw;
     if (!gm_make_map(&ma, dA, K, M, K, GM_BM) || !gm_make_map(&mw, dW, K, N, K, GM_BN)) { printf("T1 map encode failed\n"); return 3; }
     GemmArgs g{};
-    g.M = M; g.N = N; g.n_phases = 1;
+    g.M = M; g.N = N; g.n_phases = 1; g.n_acc = 1;
     g.ph[0].k_blocks = (K + 31) / 32; g.ph[0].nb = 1; g.ph[0].w_row0[0] = 0; g.ph[0].acc[0] = 0;
     g.bias = db; g.out = dO; g.ldo = N; g.act = 1;
-    CK((gm_launch<EPI_DENSE, 1, 1>(ma, ma, mw, mw, g, 0)));
+    GemmMaps maps{};
+    maps.a[0] = ma; maps.w[0] = mw;
+    CK((gm_launch<EPI_DENSE, 1, 4, 4>(maps, g, 0)));
     CK(cudaDeviceSynchronize());
     std::vector<float> O((size_t)M * N);
     CK(cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost));
@@ -75,11 +77,13 @@ int main() {
     if (!gm_make_map(&ma0, dF + 32, K0, M, LD0, GM_BM) || !gm_make_map(&ma1, dL, K1, M, K1, GM_BM) ||
         !gm_make_map(&mw, dW, K0 + K1, N, K0 + K1, GM_BN)) { printf("T2 map encode failed\n"); return 3; }
     GemmArgs g{};
-    g.M = M; g.N = N; g.n_phases = 2;
+    g.M = M; g.N = N; g.n_phases = 2; g.n_acc = 1;
     g.ph[0].k_blocks = (K0 + 31) / 32; g.ph[0].nb = 1; g.ph[0].w_k0 = 0;
-    g.ph[1].k_blocks = (K1 + 31) / 32; g.ph[1].nb = 1; g.ph[1].w_k0 = K0;
+    g.ph[1].k_blocks = (K1 + 31) / 32; g.ph[1].nb = 1; g.ph[1].w_k0 = K0; g.ph[1].a_map = 1;
     g.bias = db; g.out = dO; g.ldo = N; g.act = 0;
-    CK((gm_launch<EPI_DENSE, 1, 1>(ma0, ma1, mw, mw, g, 0)));
+    GemmMaps maps{};
+    maps.a[0] = ma0; maps.a[1] = ma1; maps.w[0] = mw;
+    CK((gm_launch<EPI_DENSE, 1, 4, 4>(maps, g, 0)));
     CK(cudaDeviceSynchronize());
     std::vector<float> O((size_t)M * N);
     CK(cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost));
@@ -117,14 +121,16 @@ int main() {
     if (!gm_make_map(&mx, dX, H, M, H, GM_BM) || !gm_make_map(&mh, dF + 32, H, M, LD, GM_BM) ||
         !gm_make_map(&mwk, dWk, H, 3 * H, H, GM_BN) || !gm_make_map(&mwr, dWr, H, 3 * H, H, GM_BN)) { printf("T3 map encode failed\n"); return 3; }
     GemmArgs g{};
-    g.M = M; g.N = H; g.n_phases = 2;
+    g.M = M; g.N = H; g.n_phases = 2; g.n_acc = 1;
     for (int p = 0; p < 2; ++p) {
-      g.ph[p].k_blocks = (H + 31) / 32; g.ph[p].nb = 3;
+      g.ph[p].k_blocks = (H + 31) / 32; g.ph[p].nb = 3; g.ph[p].a_map = p; g.ph[p].w_map = p;
       g.ph[p].w_row0[0] = 0; g.ph[p].w_row0[1] = H; g.ph[p].w_row0[2] = 2 * H;
       g.ph[p].acc[0] = 0; g.ph[p].acc[1] = 1; g.ph[p].acc[2] = p == 0 ? 2 : 3;
     }
     g.bias = db; g.out = dO + 32; g.ldo = LD; g.hold = dF + 32; g.ldh = LD;
-    CK((gm_launch<EPI_GRU, 3, 4>(mx, mh, mwk, mwr, g, 0)));
+    GemmMaps maps{};
+    maps.a[0] = mx; maps.a[1] = mh; maps.w[0] = mwk; maps.w[1] = mwr;
+    CK((gm_launch<EPI_GRU, 3, 8, 4>(maps, g, 0)));
     CK(cudaDeviceSynchronize());
     std::vector<float> O((size_t)M * LD);
     CK(cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost));
