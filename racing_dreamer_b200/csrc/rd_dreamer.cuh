@@ -33,6 +33,7 @@ struct DreamerPolicy {
   float* b_act[8] = {};
   // activations.  feat[p]: latent rows; sa/det/all are views of the same rows (img1 input, deter, actor input)
   Operand feat[2], v_sa[2], v_det[2], x1, hobs, hid[2], lidar;
+  float* head_raw = nullptr;   // [n][4] hout pre-activations
   int cur = 0;           // feat[cur] holds the latest latent
   uint32_t step = 0;     // agent steps taken (Philox counter)
   std::string err;
@@ -162,6 +163,8 @@ static inline int dreamer_init(DreamerPolicy& d, int n, int n_beams, bool lidar_
     DR_TRY(dr_alloc(d, d.feat[p], N, d.ldf));
     DR_TRY(dr_alloc(d, d.hid[p], N, U));
   }
+  DR_TRY(cudaMalloc(&d.head_raw, N * 4 * sizeof(float)));
+  d.owned.push_back(d.head_raw);
   DR_TRY(dr_alloc(d, d.x1, N, H));
   DR_TRY(dr_alloc(d, d.hobs, N, H));
   DR_TRY(dr_alloc(d, d.lidar, N, E));   // the embedded scans (k_embed_lidar)
@@ -322,7 +325,11 @@ static inline int dreamer_step(DreamerPolicy& d, const float* lidar, float* acti
     g.bn = d.bn; g.raw_init_std = d.raw_init_std; g.min_std = d.min_std; g.mean_scale = d.mean_scale; g.bn_eps = d.bn_eps;
     g.n_samples = d.n_samples;
     g.dbg = debug ? debug + (size_t)d.n * 2 * GM_STOCH : nullptr;
+    g.out = d.head_raw;
     DR_TRY((gm_launch<EPI_ACTOR, 1, 4, 4>(maps, g, s)));
+    ++*launched;
+    k_actor_mode<<<(unsigned)((d.n + 7) / 8), 256, 0, s>>>(g);
+    DR_TRY(cudaGetLastError());
     ++*launched;
   }
   d.cur = nxt;

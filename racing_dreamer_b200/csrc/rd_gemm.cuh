@@ -181,7 +181,8 @@ __device__ __forceinline__ float gm_round_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
-__device__ __forceinline__ float gm_elu(float x) { return x > 0.f ? x : expm1f(x); }
+// tf.nn.elu; exp(x) - 1 instead of expm1: the absolute error (6e-8) is what matters for the next layer's dot products
+__device__ __forceinline__ float gm_elu(float x) { return x > 0.f ? x : expf(x) - 1.0f; }
 __device__ __forceinline__ float gm_softplus(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 __device__ __forceinline__ float gm_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 // four standard normals from one Philox block (Box-Muller on (0,1] uniforms)
@@ -231,9 +232,13 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
   __syncthreads();
   gm_tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  // Programmatic dependent launch: the next k_dense of the stream may start its own set-up (barriers, TMEM, tensor-map
+  // fetch) now; everything that touches global memory first waits for the previous kernel to have completed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     if (lane == 0) {   // ===== TMA producer =====
+      asm volatile("griddepcontrol.wait;" ::: "memory");
       uint32_t it = 0;
       for (int p = 0; p < g.n_phases; ++p) {
         const GemmPhase& ph = g.ph[p];
@@ -280,6 +285,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
     const int q = warp & 3;
     const int row = m0 + q * 32 + lane;
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     gm_mbar_wait(&acc_bar, 0);
     gm_tc_fence_after();
     const bool live = row < g.M;
@@ -393,72 +399,14 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
         }
       }
     } else {
-      // ActionDecoder head [REF models.py:323-346] + SampleDist.mode() [REF ros_agent/helpers/tools.py:70-73]
+      // hout: the four pre-activations of the ActionDecoder head, in full float32; the head itself and
+      // SampleDist.mode() need many more threads than this tile has rows (k_actor_mode)
       float v[8];
       gm_tmem_sum8(tl, g.n_acc, 1, v);
       if (live) {
-        float x[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) x[t] = v[t] + __ldg(g.bias + t);
-        float mean[2], sd[2];
-        if (g.bn) {   // 'normalized_tanhtransformed_normal': BatchNormalization in inference mode, linear mean
-#pragma unroll
-          for (int t = 0; t < 4; ++t)
-            x[t] = (x[t] - __ldg(g.bn + 8 + t)) * (__ldg(g.bn + t) * rsqrtf(__ldg(g.bn + 12 + t) + g.bn_eps)) + __ldg(g.bn + 4 + t);
-          mean[0] = x[0]; mean[1] = x[1];
-          sd[0] = gm_softplus(x[2]) + g.min_std; sd[1] = gm_softplus(x[3]) + g.min_std;
-        } else {      // 'tanh_normal'
-          mean[0] = g.mean_scale * tanhf(x[0] / g.mean_scale); mean[1] = g.mean_scale * tanhf(x[1] / g.mean_scale);
-          sd[0] = gm_softplus(x[2] + g.raw_init_std) + g.min_std; sd[1] = gm_softplus(x[3] + g.raw_init_std) + g.min_std;
-        }
-        // mode(): argmax over n_samples draws of log_prob(tanh(u)), u ~ N(mean, sd): the Normal's log density minus
-        // the tanh bijector's forward log-det-Jacobian 2 (log 2 - u - softplus(-2u)), summed over the two actions
-        const float log2f_ = 0.69314718f, half_log_2pi = 0.91893853f;
-        const uint32_t gid = g.gid0 + (uint32_t)row;
-        float best = -INFINITY, bu0 = mean[0], bu1 = mean[1];
-        int bi = -1;
-        if (g.noise == GM_NOISE_ZERO) {
-          bi = 0;
-          best = 0.f;
-#pragma unroll
-          for (int d = 0; d < 2; ++d) {
-            const float u = mean[d];
-            best += (-logf(sd[d]) - half_log_2pi) - 2.f * ((log2f_ - u) - gm_softplus(-2.f * u));
-          }
-        } else {
-          for (int s0 = 0; s0 < g.n_samples; s0 += 2) {
-            float z[4] = {0.f, 0.f, 0.f, 0.f};
-            if (g.noise == GM_NOISE_PHILOX) gm_normal4(gid, g.step, (uint32_t)s0, RD_STREAM_ACTOR, g.key0, g.key1, z);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int s = s0 + h;
-              if (s >= g.n_samples) break;
-              float lp = 0.f, u[2];
-#pragma unroll
-              for (int d = 0; d < 2; ++d) {
-                const float e = (g.noise == GM_NOISE_EXPLICIT) ? g.eps[(size_t)row * g.ld_eps + 2 * s + d] : z[2 * h + d];
-                u[d] = mean[d] + sd[d] * e;
-                lp += ((-0.5f * e * e - logf(sd[d])) - half_log_2pi) - 2.f * ((log2f_ - u[d]) - gm_softplus(-2.f * u[d]));
-              }
-              if (lp > best) { best = lp; bu0 = u[0]; bu1 = u[1]; bi = s; }   // tf.argmax: first maximum
-            }
-          }
-        }
-        const float a0 = tanhf(bu0), a1 = tanhf(bu1);
-        g.actions[2 * (size_t)row] = a0;
-        g.actions[2 * (size_t)row + 1] = a1;
-        float* frow = g.feat + (size_t)row * g.ldf;
-        const float h0 = gm_round_tf32(a0), h1 = gm_round_tf32(a1);
-        frow[GM_STOCH] = h0;
-        frow[GM_STOCH + 1] = h1;
-        if (g.feat_lo) {
-          g.feat_lo[(size_t)row * g.ldf + GM_STOCH] = gm_round_tf32(a0 - h0);
-          g.feat_lo[(size_t)row * g.ldf + GM_STOCH + 1] = gm_round_tf32(a1 - h1);
-        }
-        if (g.dbg) {
-          float* d = g.dbg + (size_t)row * 8;
-          d[0] = mean[0]; d[1] = mean[1]; d[2] = sd[0]; d[3] = sd[1]; d[4] = a0; d[5] = a1; d[6] = best; d[7] = (float)bi;
-        }
+        float4 o;
+        o.x = v[0] + __ldg(g.bias + 0); o.y = v[1] + __ldg(g.bias + 1); o.z = v[2] + __ldg(g.bias + 2); o.w = v[3] + __ldg(g.bias + 3);
+        *reinterpret_cast<float4*>(g.out + (size_t)row * 4) = o;
       }
     }
     gm_tc_fence_before();
@@ -467,6 +415,84 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
   if (warp == 1) {
     gm_tc_fence_after();
     gm_tmem_free(tmem, TM_COLS);
+  }
+}
+
+// ActionDecoder distribution head [REF models.py:323-346] + SampleDist.mode() [REF ros_agent/helpers/tools.py:70-73]:
+// one warp per env, lanes over pairs of draws (one Philox block = the four normals of two draws), warp arg-max.
+// `g.out` holds hout's pre-activations [M][4] (k_dense<EPI_ACTOR>); the other fields are the ACTOR ones of GemmArgs.
+__global__ void __launch_bounds__(256) k_actor_mode(const GemmArgs g) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= g.M) return;
+  const float4 x4 = *reinterpret_cast<const float4*>(g.out + (size_t)row * 4);
+  float x[4] = {x4.x, x4.y, x4.z, x4.w};
+  float mean[2], sd[2];
+  if (g.bn) {   // 'normalized_tanhtransformed_normal': BatchNormalization in inference mode, linear mean
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      x[t] = (x[t] - __ldg(g.bn + 8 + t)) * (__ldg(g.bn + t) * rsqrtf(__ldg(g.bn + 12 + t) + g.bn_eps)) + __ldg(g.bn + 4 + t);
+    mean[0] = x[0]; mean[1] = x[1];
+    sd[0] = gm_softplus(x[2]) + g.min_std; sd[1] = gm_softplus(x[3]) + g.min_std;
+  } else {      // 'tanh_normal'
+    mean[0] = g.mean_scale * tanhf(x[0] / g.mean_scale); mean[1] = g.mean_scale * tanhf(x[1] / g.mean_scale);
+    sd[0] = gm_softplus(x[2] + g.raw_init_std) + g.min_std; sd[1] = gm_softplus(x[3] + g.raw_init_std) + g.min_std;
+  }
+  // mode(): argmax over n_samples draws of log_prob(tanh(u)), u ~ N(mean, sd): the Normal's log density minus the tanh
+  // bijector's forward log-det-Jacobian 2 (log 2 - u - softplus(-2u)), summed over the two actions
+  const float log2f_ = 0.69314718f, half_log_2pi = 0.91893853f;
+  const uint32_t gid = g.gid0 + (uint32_t)row;
+  float best = -INFINITY, bu0 = mean[0], bu1 = mean[1];
+  int bi = 0x7fffffff;
+  if (g.noise == GM_NOISE_ZERO) {
+    bi = 0;
+    best = 0.f;
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      const float u = mean[d];
+      best += (-logf(sd[d]) - half_log_2pi) - 2.f * ((log2f_ - u) - gm_softplus(-2.f * u));
+    }
+  } else {
+    for (int s0 = 2 * lane; s0 < g.n_samples; s0 += 64) {
+      float z[4] = {0.f, 0.f, 0.f, 0.f};
+      if (g.noise == GM_NOISE_PHILOX) gm_normal4(gid, g.step, (uint32_t)s0, RD_STREAM_ACTOR, g.key0, g.key1, z);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int s = s0 + h;
+        if (s >= g.n_samples) break;
+        float lp = 0.f, u[2];
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          const float e = (g.noise == GM_NOISE_EXPLICIT) ? g.eps[(size_t)row * g.ld_eps + 2 * s + d] : z[2 * h + d];
+          u[d] = mean[d] + sd[d] * e;
+          lp += ((-0.5f * e * e - logf(sd[d])) - half_log_2pi) - 2.f * ((log2f_ - u[d]) - gm_softplus(-2.f * u[d]));
+        }
+        if (lp > best) { best = lp; bu0 = u[0]; bu1 = u[1]; bi = s; }   // ascending s per lane: first maximum
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {   // tf.argmax: the first maximum over all draws
+      const float ob = __shfl_xor_sync(0xffffffffu, best, off), o0 = __shfl_xor_sync(0xffffffffu, bu0, off),
+                  o1 = __shfl_xor_sync(0xffffffffu, bu1, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bu0 = o0; bu1 = o1; bi = oi; }
+    }
+  }
+  if (lane == 0) {
+    const float a0 = tanhf(bu0), a1 = tanhf(bu1);
+    g.actions[2 * (size_t)row] = a0;
+    g.actions[2 * (size_t)row + 1] = a1;
+    float* frow = g.feat + (size_t)row * g.ldf;
+    const float h0 = gm_round_tf32(a0), h1 = gm_round_tf32(a1);
+    frow[GM_STOCH] = h0;
+    frow[GM_STOCH + 1] = h1;
+    if (g.feat_lo) {
+      g.feat_lo[(size_t)row * g.ldf + GM_STOCH] = gm_round_tf32(a0 - h0);
+      g.feat_lo[(size_t)row * g.ldf + GM_STOCH + 1] = gm_round_tf32(a1 - h1);
+    }
+    if (g.dbg) {
+      float* d = g.dbg + (size_t)row * 8;
+      d[0] = mean[0]; d[1] = mean[1]; d[2] = sd[0]; d[3] = sd[1]; d[4] = a0; d[5] = a1; d[6] = best; d[7] = (float)bi;
+    }
   }
 }
 
@@ -554,7 +580,15 @@ static inline cudaError_t gm_launch(const GemmMaps& maps, const GemmArgs& g, cud
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  dim3 grid((unsigned)((g.M + GM_BM - 1) / GM_BM), (unsigned)((g.N + GM_BN - 1) / GM_BN));
-  k_dense<EPI, NSLAB, NACC, GM_STAGES><<<grid, GM_THREADS, smem, s>>>(maps, g);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((g.M + GM_BM - 1) / GM_BM), (unsigned)((g.N + GM_BN - 1) / GM_BN));
+  cfg.blockDim = dim3(GM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see griddepcontrol in k_dense
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k_dense<EPI, NSLAB, NACC, GM_STAGES>, maps, g);
 }
