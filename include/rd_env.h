@@ -22,7 +22,9 @@
 extern "C" {
 #endif
 
-#define RD_ABI_VERSION 1
+#define RD_ABI_VERSION 2
+#define RD_MAX_AGENTS 4   /* cars per world: agents A..D [REF baselines/scenarios/max_progress/austria.yml:3-34] */
+#define RD_MAX_NSTEP 32   /* longest n of the n_step_progress task */
 
 typedef struct rd_env rd_env; /* opaque */
 
@@ -36,9 +38,13 @@ typedef enum rd_status {
 } rd_status;
 
 /* reset modes [REF dreamer/wrappers.py:86-92 FixedResetMode; dreamer/dream.py:105-108,120] */
-enum { RD_RESET_GRID = 0, RD_RESET_RANDOM = 1, RD_RESET_RANDOM_BIDIRECTIONAL = 2 };
+enum { RD_RESET_GRID = 0, RD_RESET_RANDOM = 1, RD_RESET_RANDOM_BIDIRECTIONAL = 2,
+       RD_RESET_RANDOM_BALL = 3 /* multi-agent training: the cars of a world close to one random point
+                                   [REF dreamer/dream.py:105-106] */ };
 /* tasks [REF dreamer/scenarios/max_progress/austria.yml:8-10; baselines/racing/environment/tasks.py:4-22] */
-enum { RD_TASK_MAX_PROGRESS = 0, RD_TASK_MAX_SPEED = 1 };
+enum { RD_TASK_MAX_PROGRESS = 0, RD_TASK_MAX_SPEED = 1,
+       RD_TASK_N_STEP_PROGRESS = 2 /* agents B..D of the baselines' scenarios
+                                      [REF baselines/scenarios/max_progress/austria.yml:16-18] */ };
 /* observation outputs produced by rd_step/rd_reset */
 enum {
   RD_OBS_LIDAR = 1,          /* f32 [N, n_beams] metres */
@@ -61,13 +67,14 @@ enum {
 enum {
   RD_I_LAP = 0,     /* starts at 1 [REF dreamer/wrappers.py:218] */
   RD_I_CHECKPOINT,
-  RD_I_FLAGS,       /* bit0 wrong_way, bit1 wall_collision, bit2 needs_reset, bit3 left_map, bit4 nan */
+  RD_I_FLAGS,       /* bit0 wrong_way, bit1 wall_collision, bit2 needs_reset, bit3 left_map, bit4 nan, bit5 opponent */
   RD_I_AGENT_STEP,  /* TimeLimit counter [REF dreamer/wrappers.py:147-154] */
   RD_I_EPISODE,     /* episodes started (reset-sampling counter) */
   RD_I_MAP,         /* map id of this env */
   RD_NI32
 };
-enum { RD_F_WRONG_WAY = 1, RD_F_COLLISION = 2, RD_F_NEEDS_RESET = 4, RD_F_LEFT_MAP = 8, RD_F_NAN = 16 };
+enum { RD_F_WRONG_WAY = 1, RD_F_COLLISION = 2, RD_F_NEEDS_RESET = 4, RD_F_LEFT_MAP = 8, RD_F_NAN = 16,
+       RD_F_OPPONENT = 32 /* body overlaps another car of the same world (info['opponent_collisions'] non-empty) */ };
 
 /* Single-track (bicycle) vehicle model parameters, SURVEY.md Appendix C [NEW-SPEC; in-tree anchors:
  * wheelbase 0.3302 REF ros_agent/agents/follow_the_gap/src/agent.py:78, max steering 0.42 and
@@ -111,6 +118,16 @@ typedef struct rd_config {
   double lidar_offset;        /* sensor position ahead of the pose along the heading, metres */
   float lidar_noise;          /* multiplicative U(1-a,1+a); 0 = off */
   float reserved0;
+  /* ---- multi-agent worlds [REF baselines/scenarios/max_progress/austria.yml:3-34: four racecars
+   *      A..D in one world; dreamer/dream.py:105-106 n_agents > 1; dreamer/wrappers.py:107-116,147-154 dict-of-agents
+   *      step].  Env e is agent (e % agents_per_world) of world (e / agents_per_world); the agents of a world share its
+   *      map, see each other in their LiDAR scans, collide with each other, stop repeating / time out / reset together
+   *      (ActionRepeat: `not any(dones.values())` [REF wrappers.py:112]; tools.simulate: `if any(dones.values()):
+   *      env.reset()` [REF dreamer/tools.py:178-179]).  agents_per_world <= 1: single-agent envs, fields below unused. */
+  int32_t agents_per_world;   /* 1..RD_MAX_AGENTS; n_envs must be a multiple */
+  int32_t agent_task[RD_MAX_AGENTS]; /* RD_TASK_* of agent index 0..3 (used when agents_per_world > 1) */
+  int32_t n_step_progress;    /* n of n_step_progress, in sim ticks, 1..RD_MAX_NSTEP [REF .../austria.yml:18 n_steps: 10] */
+  double ball_spacing;        /* random_ball / multi-agent random reset: metres of track between consecutive cars */
   rd_vehicle vehicle;
 } rd_config;
 
@@ -131,6 +148,9 @@ typedef struct rd_outputs {
   int32_t* lap_dev;           /* [N]   info['lap'] */
   float* time_dev;            /* [N]   info['time'] */
   uint8_t* flags_dev;         /* [N]   RD_F_* bits of the (possibly terminal) state */
+  /* multi-agent worlds (NULL or left untouched when agents_per_world <= 1) */
+  int32_t* rank_dev;          /* [N]   info['rank']: 1 = leader of the world by lap + progress (ties: lower agent index) */
+  uint8_t* opponents_dev;     /* [N]   info['opponent_collisions'] as a bit mask over the world's agent indices */
 } rd_outputs;
 
 /* episode statistics accumulated on the device since the last rd_read_stats(reset=1)

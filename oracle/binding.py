@@ -32,13 +32,14 @@ class _Map(C.Structure):
         ("resolution", C.c_double), ("origin_x", C.c_double), ("origin_y", C.c_double),
         ("drivable", C.c_void_p), ("dist", C.c_void_p), ("start_poses", C.c_void_p), ("reset_poses", C.c_void_p),
         ("n_start", C.c_int32), ("n_reset", C.c_int32),
+        ("ball_next", C.c_void_p),
     ]
 
 
 class _Outputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "lidar", "occupancy", "pose", "velocity", "speed", "reward", "done", "progress", "lap", "time", "flags",
-        "reward64")]
+        "reward64", "rank", "opponents")]
 
 
 def _load():
@@ -69,7 +70,7 @@ class OracleMap:
         self.start = np.ascontiguousarray(tm.start_poses, dtype=np.float64)
         self.reset = np.ascontiguousarray(tm.reset_poses, dtype=np.float64)
 
-    def fill(self, m: _Map):
+    def fill(self, m: _Map, cfg=None):
         tm = self.tm
         m.h, m.w, m.col0, m.row0, m.full_h, m.dmax = tm.h, tm.w, tm.c0, tm.cy0, tm.full_shape[0], tm.dmax
         m.resolution, m.origin_x, m.origin_y = tm.resolution, tm.origin[0], tm.origin[1]
@@ -78,6 +79,11 @@ class OracleMap:
         m.start_poses = self.start.ctypes.data
         m.reset_poses = self.reset.ctypes.data
         m.n_start, m.n_reset = self.start.shape[0], self.reset.shape[0]
+        m.ball_next = None
+        if cfg is not None and self.reset.shape[0] > 0:   # random_ball chain (multi-agent resets)
+            self.ball_next = np.zeros(self.reset.shape[0], np.int32)
+            _load().orc_ball_next(C.byref(cfg), C.byref(m), C.c_void_p(self.ball_next.ctypes.data))
+            m.ball_next = self.ball_next.ctypes.data
 
 
 class Oracle:
@@ -93,11 +99,13 @@ class Oracle:
         self._maps: List[OracleMap] = [OracleMap(t) for t in tracks]
         self._cmaps = (_Map * len(self._maps))()
         for om, cm in zip(self._maps, self._cmaps):
-            om.fill(cm)
+            om.fill(cm, self.cfg)
         self.f64 = np.zeros((_abi.NF64, self.n), dtype=np.float64)
         self.i32 = np.zeros((_abi.NI32, self.n), dtype=np.int32)
         if env_map_ids is not None:
             self.i32[_abi.I_MAP] = np.asarray(env_map_ids, dtype=np.int32)
+        # ring of lap + progress per tick (n_step_progress task); harmless when unused
+        self.hist = np.zeros((max(1, int(cfg.n_step_progress)), self.n), dtype=np.float64)
         self.stats = _abi.RdStats()
         self.out = self._alloc_outputs()
 
@@ -111,7 +119,8 @@ class Oracle:
             pose=np.zeros((n, 6), np.float32), velocity=np.zeros((n, 6), np.float32),
             speed=np.zeros(n, np.float32), reward=np.zeros(n, np.float32), done=np.zeros(n, np.uint8),
             progress=np.zeros(n, np.float32), lap=np.zeros(n, np.int32), time=np.zeros(n, np.float32),
-            flags=np.zeros(n, np.uint8), reward64=np.zeros(n, np.float64))
+            flags=np.zeros(n, np.uint8), reward64=np.zeros(n, np.float64), rank=np.ones(n, np.int32),
+            opponents=np.zeros(n, np.uint8))
 
     def _c_outputs(self) -> _Outputs:
         o = _Outputs()
@@ -124,8 +133,8 @@ class Oracle:
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
         o = self._c_outputs()
         self.lib.orc_reset(C.byref(self.cfg), self._cmaps, C.c_void_p(self.f64.ctypes.data),
-                           C.c_void_p(self.i32.ctypes.data), C.c_void_p(m.ctypes.data if m is not None else None),
-                           C.c_int(mode), C.byref(o))
+                           C.c_void_p(self.i32.ctypes.data), C.c_void_p(self.hist.ctypes.data),
+                           C.c_void_p(m.ctypes.data if m is not None else None), C.c_int(mode), C.byref(o))
         return self.out
 
     def step(self, actions: np.ndarray = None, commands: np.ndarray = None):
@@ -138,7 +147,8 @@ class Oracle:
             a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.n, 2)
         o = self._c_outputs()
         self.lib.orc_step(C.byref(self.cfg), self._cmaps, C.c_void_p(self.f64.ctypes.data),
-                          C.c_void_p(self.i32.ctypes.data), C.c_void_p(a.ctypes.data if a is not None else None),
+                          C.c_void_p(self.i32.ctypes.data), C.c_void_p(self.hist.ctypes.data),
+                          C.c_void_p(a.ctypes.data if a is not None else None),
                           C.c_void_p(c.ctypes.data if c is not None else None), C.byref(o),
                           C.byref(self.stats), C.c_int(self.n_threads))
         return self.out

@@ -41,6 +41,7 @@ typedef struct orc_map {
   const double* start_poses; /* [n_start][3] */
   const double* reset_poses; /* [n_reset][3] */
   int32_t n_start, n_reset;
+  const int32_t* ball_next;  /* [n_reset] orc_ball_next(): the reset pose ball_spacing metres further along the lap */
 } orc_map;
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -78,6 +79,10 @@ ORC_API void orc_default_config(rd_config* c) {
   c->lidar_range_max = 15.0;
   c->lidar_offset = 0.0;
   c->lidar_noise = 0.0f;
+  c->agents_per_world = 1;
+  for (int a = 0; a < RD_MAX_AGENTS; ++a) c->agent_task[a] = RD_TASK_MAX_PROGRESS;
+  c->n_step_progress = 10; /* [REF baselines/scenarios/max_progress/austria.yml:18] */
+  c->ball_spacing = 1.5;
   rd_vehicle* v = &c->vehicle;
   v->mu = 1.0489; v->c_sf = 4.718; v->c_sr = 5.4562; v->lf = 0.15875; v->lr = 0.17145; v->h_cg = 0.074;
   v->mass = 3.74; v->inertia = 0.04712;
@@ -164,8 +169,77 @@ static float finish_range(const rd_config* cfg, float r, uint32_t gid, uint32_t 
   return r;
 }
 
+/* Another car of the same world as the scan sees it (multi-agent worlds): ITS sensor origin in
+ * 2^-12 cells and heading.  [NEW-SPEC: racecar_gym's rayTestBatch also hits the other racecars' collision shapes] */
+typedef struct orc_car { int32_t px, py; int has_pos; double c, s; } orc_car;
+
+/* sensor origin of a pose, quantised to 2^-12 cells relative to the crop; returns 1 when representable */
+static int sensor_origin(const rd_config* cfg, const orc_map* m, double x, double y, double yaw, int64_t* PX,
+                         int64_t* PY, double* c_out, double* s_out) {
+  const double inv_res = 1.0 / m->resolution;
+  const double c = cos(yaw), s = sin(yaw);
+  const double sx = x + cfg->lidar_offset * c;
+  const double sy = y + cfg->lidar_offset * s;
+  const double u = (sx - m->origin_x) * inv_res;
+  const double v = (sy - m->origin_y) * inv_res;
+  const double pu = floor(u * (double)SUB), pv = floor(v * (double)SUB);
+  *c_out = c; *s_out = s;
+  *PX = 0; *PY = 0;
+  if (!(pu > -1.0e12 && pu < 1.0e12 && pv > -1.0e12 && pv < 1.0e12)) return 0;
+  *PX = (int64_t)pu - (int64_t)m->col0 * SUB;
+  *PY = (int64_t)pv - (int64_t)m->row0 * SUB;
+  return (*PX > -((int64_t)1 << 30) && *PX < ((int64_t)1 << 30) && *PY > -((int64_t)1 << 30) && *PY < ((int64_t)1 << 30));
+}
+
+static orc_car car_of(const rd_config* cfg, const orc_map* m, double x, double y, double yaw) {
+  orc_car k;
+  int64_t PX, PY;
+  k.has_pos = sensor_origin(cfg, m, x, y, yaw, &PX, &PY, &k.c, &k.s);
+  k.px = k.has_pos ? (int32_t)PX : 0;
+  k.py = k.has_pos ? (int32_t)PY : 0;
+  return k;
+}
+
+/* Range (metres) at which the beam (DX, DY) * 2^-18 from (px, py) enters the body box of car q, or +inf: float32 slab
+ * test in q's sensor frame, one IEEE operation per step in this order (the kernel's rd_car_hit). */
+static float car_hit(const rd_config* cfg, const orc_map* m, int32_t px, int32_t py, int32_t DX, int32_t DY,
+                     const orc_car* q) {
+  const double inv_res = 1.0 / m->resolution;
+  const double hl = 0.5 * cfg->vehicle.body_length * inv_res, hw = 0.5 * cfg->vehicle.body_width * inv_res;
+  const double off = cfg->lidar_offset * inv_res;
+  const float ulo = (float)(-hl - off), uhi = (float)(hl - off), vhw = (float)hw, res = (float)m->resolution;
+  const int reach = (int)ceil((cfg->lidar_range_max * inv_res + 2.0 * (hl + hw + fabs(off)) + 2.0) * (double)SUB);
+  const int32_t rx = px - q->px, ry = py - q->py;
+  const int32_t arx = rx < 0 ? -rx : rx, ary = ry < 0 ? -ry : ry;
+  if (!q->has_pos || arx > reach || ary > reach) return INFINITY;
+  const float ox = (float)rx * (1.0f / (float)SUB), oy = (float)ry * (1.0f / (float)SUB);
+  const float c = (float)q->c, s = (float)q->s;
+  const float dxf = (float)DX * (1.0f / (float)(1 << DIR_BITS)), dyf = (float)DY * (1.0f / (float)(1 << DIR_BITS));
+  const float u0 = ox * c + oy * s;
+  const float v0 = oy * c - ox * s;
+  const float du = dxf * c + dyf * s;
+  const float dv = dyf * c - dxf * s;
+  float tmin = 0.0f, tmax = INFINITY;
+  if (du != 0.0f) {
+    float t1 = (ulo - u0) / du, t2 = (uhi - u0) / du;
+    tmin = fmaxf(tmin, fminf(t1, t2));
+    tmax = fminf(tmax, fmaxf(t1, t2));
+  } else if (u0 < ulo || u0 > uhi) {
+    return INFINITY;
+  }
+  if (dv != 0.0f) {
+    float t1 = (-vhw - v0) / dv, t2 = (vhw - v0) / dv;
+    tmin = fmaxf(tmin, fminf(t1, t2));
+    tmax = fminf(tmax, fmaxf(t1, t2));
+  } else if (v0 < -vhw || v0 > vhw) {
+    return INFINITY;
+  }
+  return tmin <= tmax ? tmin * res : INFINITY;
+}
+
 static void lidar_one(const rd_config* cfg, const orc_map* m, const double* ca, const double* sa, double x,
-                      double y, double yaw, uint32_t gid, uint32_t episode, uint32_t step, float* out) {
+                      double y, double yaw, uint32_t gid, uint32_t episode, uint32_t step, float* out,
+                      const orc_car* cars, int n_cars) {
   const int nb = cfg->n_beams;
   const double inv_res = 1.0 / m->resolution;
   const double c = cos(yaw), s = sin(yaw);
@@ -227,6 +301,7 @@ static void lidar_one(const rd_config* cfg, const orc_map* m, const double* ca, 
     } else {
       r = (float)cfg->lidar_range_max;
     }
+    for (int k = 0; k < n_cars; ++k) r = fminf(r, car_hit(cfg, m, (int32_t)PX, (int32_t)PY, DX, DY, &cars[k]));
     out[i] = finish_range(cfg, r, gid, episode, step, (uint32_t)i);
   }
 }
@@ -242,8 +317,13 @@ ORC_API void orc_lidar_cast(const rd_config* cfg, const orc_map* maps, const dou
 #pragma omp parallel for schedule(dynamic, 16) num_threads(n_threads)
   for (int e = 0; e < n; ++e) {
     const orc_map* m = &maps[map_ids ? map_ids[e] : 0];
+    orc_car cars[RD_MAX_AGENTS];
+    int n_cars = 0;
+    const int A = cfg->agents_per_world > 1 ? cfg->agents_per_world : 1;
+    for (int j = e - e % A; j < e - e % A + A && j < n && A > 1; ++j)
+      if (j != e) cars[n_cars++] = car_of(cfg, m, poses[3 * j], poses[3 * j + 1], poses[3 * j + 2]);
     lidar_one(cfg, m, ca, sa, poses[3 * e], poses[3 * e + 1], poses[3 * e + 2], (uint32_t)e, 0u, 0u,
-              ranges + (size_t)e * nb);
+              ranges + (size_t)e * nb, cars, n_cars);
   }
   free(ca);
 }
@@ -341,11 +421,12 @@ ORC_API void orc_dynamics(const rd_config* cfg, double* state, const double* com
 /* task parameters [REF dreamer/scenarios/max_progress/austria.yml:8-10].  Implementation in          */
 /* racecar_gym (not in tree) -> [NEW-SPEC], SURVEY.md §8 a7/a8.                                       */
 /* ------------------------------------------------------------------------------------------------ */
-typedef struct orc_view { double* f[RD_NF64]; int32_t* i[RD_NI32]; } orc_view;
+typedef struct orc_view { double* f[RD_NF64]; int32_t* i[RD_NI32]; double* hist; int n; } orc_view;
 static orc_view view_of(double* f64, int32_t* i32, int n) {
   orc_view v;
   for (int k = 0; k < RD_NF64; ++k) v.f[k] = f64 + (size_t)k * n;
   for (int k = 0; k < RD_NI32; ++k) v.i[k] = i32 + (size_t)k * n;
+  v.hist = NULL; v.n = n;
   return v;
 }
 
@@ -378,17 +459,59 @@ static int collides(const rd_config* cfg, const orc_map* m, double x, double y, 
   return 0;
 }
 
+/* random_ball / multi-agent random reset [REF dreamer/dream.py:105-106; sampler in racecar_gym -> NEW-SPEC]: the cars of
+ * a world line up behind one random anchor pose.  next[i] = the reset pose with the smallest wavefront distance that is
+ * at least ceil(ball_spacing / resolution) cells of progress beyond pose i (wrapping over the finish line); the
+ * wavefront distance is a Chebyshev path length, so consecutive cars stand at least ball_spacing metres apart. */
+typedef struct ball_key { int32_t d, i; } ball_key;
+static int ball_key_cmp(const void* a, const void* b) {
+  const ball_key* x = (const ball_key*)a; const ball_key* y = (const ball_key*)b;
+  if (x->d != y->d) return x->d < y->d ? -1 : 1;
+  return x->i < y->i ? -1 : (x->i > y->i ? 1 : 0);
+}
+static int ball_lower_bound(const ball_key* k, int n, int32_t d) { /* first entry with k.d >= d, or n */
+  int lo = 0, hi = n;
+  while (lo < hi) { int mid = (lo + hi) / 2; if (k[mid].d < d) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+ORC_API void orc_ball_next(const rd_config* cfg, const orc_map* m, int32_t* next) {
+  const int n = m->n_reset;
+  if (n <= 0) return;
+  ball_key* k = (ball_key*)malloc(sizeof(ball_key) * (size_t)n);
+  int32_t* d = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+  for (int i = 0; i < n; ++i) {
+    int cx, cy;
+    d[i] = cell_of(m, m->reset_poses[3 * i], m->reset_poses[3 * i + 1], &cx, &cy) ? (int32_t)m->dist[(size_t)cy * m->w + cx] : 0;
+    k[i].d = d[i]; k[i].i = i;
+  }
+  qsort(k, (size_t)n, sizeof(ball_key), ball_key_cmp);
+  const int32_t sc = (int32_t)ceil(cfg->ball_spacing / m->resolution);
+  for (int i = 0; i < n; ++i) {
+    int j = ball_lower_bound(k, n, d[i] + sc);
+    if (j == n) j = ball_lower_bound(k, n, d[i] + sc - m->dmax);
+    next[i] = j < n ? k[j].i : i;
+  }
+  free(d);
+  free(k);
+}
+
 static void reset_one(const rd_config* cfg, const orc_map* maps, orc_view* s, int e, int mode) {
   const orc_map* m = &maps[s->i[RD_I_MAP][e]];
   uint32_t episode = (uint32_t)s->i[RD_I_EPISODE][e];
-  uint64_t gid = (uint64_t)(cfg->env_id_offset + e);
+  /* multi-agent worlds: one anchor per world (counter = global id of its agent 0), the other cars follow the
+   * ball_next chain (cfg->ball_spacing metres of track apart); 'grid' = the staggered start slots */
+  const int A = cfg->agents_per_world > 1 ? cfg->agents_per_world : 1;
+  const int a = e % A;
+  uint64_t gid = (uint64_t)(cfg->env_id_offset + (e - a));
   double x, y, yaw;
   if (mode == RD_RESET_GRID || m->n_reset <= 0) {
-    x = m->start_poses[0]; y = m->start_poses[1]; yaw = m->start_poses[2];
+    int slot = a < m->n_start ? a : m->n_start - 1;
+    x = m->start_poses[3 * slot]; y = m->start_poses[3 * slot + 1]; yaw = m->start_poses[3 * slot + 2];
   } else {
     uint32_t c[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), episode, 0u};
     philox4x32_10(c, (uint32_t)cfg->seed, (uint32_t)(cfg->seed >> 32) ^ (uint32_t)STREAM_RESET);
     uint32_t idx = (uint32_t)(((uint64_t)c[0] * (uint64_t)m->n_reset) >> 32);
+    for (int k = 0; k < a && m->ball_next; ++k) idx = (uint32_t)m->ball_next[idx];
     x = m->reset_poses[3 * idx]; y = m->reset_poses[3 * idx + 1]; yaw = m->reset_poses[3 * idx + 2];
     if (mode == RD_RESET_RANDOM_BIDIRECTIONAL && (c[1] & 1u)) yaw = yaw + 3.14159265358979323846;
   }
@@ -406,6 +529,7 @@ static void reset_one(const rd_config* cfg, const orc_map* maps, orc_view* s, in
   s->i[RD_I_FLAGS][e] = 0;
   s->i[RD_I_AGENT_STEP][e] = 0;
   s->i[RD_I_EPISODE][e] = (int32_t)(episode + 1u);
+  if (s->hist) for (int k = 0; k < cfg->n_step_progress; ++k) s->hist[(size_t)k * s->n + e] = 1.0 + p;
 }
 
 /* outputs of one step, host arrays (any may be NULL) -- mirrors rd_outputs */
@@ -413,6 +537,7 @@ typedef struct orc_outputs {
   float* lidar; uint8_t* occupancy; float* pose; float* velocity; float* speed; float* reward;
   uint8_t* done; float* progress; int32_t* lap; float* time; uint8_t* flags;
   double* reward64; /* un-rounded step reward (the reference sums python floats [REF dreamer/wrappers.py:114]) */
+  int32_t* rank; uint8_t* opponents; /* multi-agent worlds */
 } orc_outputs;
 
 static void orc_occupancy_one(const orc_map* m, double x, double y, double yaw, uint8_t* out);
@@ -423,9 +548,15 @@ static void write_obs(const rd_config* cfg, const orc_map* maps, const double* c
   const orc_map* m = &maps[s->i[RD_I_MAP][e]];
   double x = s->f[RD_S_X][e], y = s->f[RD_S_Y][e], yaw = s->f[RD_S_YAW][e];
   double v = s->f[RD_S_V][e], slip = s->f[RD_S_SLIP][e];
-  if (o->lidar)
+  if (o->lidar) {
+    orc_car cars[RD_MAX_AGENTS];
+    int n_cars = 0;
+    const int A = cfg->agents_per_world > 1 ? cfg->agents_per_world : 1;
+    for (int j = e - e % A; j < e - e % A + A && A > 1; ++j)
+      if (j != e) cars[n_cars++] = car_of(cfg, m, s->f[RD_S_X][j], s->f[RD_S_Y][j], s->f[RD_S_YAW][j]);
     lidar_one(cfg, m, ca, sa, x, y, yaw, (uint32_t)(cfg->env_id_offset + e), (uint32_t)s->i[RD_I_EPISODE][e],
-              (uint32_t)s->i[RD_I_AGENT_STEP][e], o->lidar + (size_t)e * nb);
+              (uint32_t)s->i[RD_I_AGENT_STEP][e], o->lidar + (size_t)e * nb, cars, n_cars);
+  }
   if (o->occupancy) {
     if (zero_occupancy) memset(o->occupancy + (size_t)e * 4096, 0, 4096); /* [REF wrappers.py:410-414] */
     else orc_occupancy_one(m, x, y, yaw, o->occupancy + (size_t)e * 4096);
@@ -445,30 +576,38 @@ static void write_obs(const rd_config* cfg, const orc_map* maps, const double* c
 }
 
 /* env.reset(mode) [REF dreamer/wrappers.py:71-77,91-92,156-158] */
-ORC_API void orc_reset(const rd_config* cfg, const orc_map* maps, double* f64, int32_t* i32,
+ORC_API void orc_reset(const rd_config* cfg, const orc_map* maps, double* f64, int32_t* i32, double* hist,
                        const uint8_t* mask, int mode, const orc_outputs* out) {
   int n = cfg->n_envs, nb = cfg->n_beams;
   orc_view s = view_of(f64, i32, n);
+  s.hist = hist;
   double* ca = (double*)malloc(sizeof(double) * 2 * nb);
   double* sa = ca + nb;
   orc_beam_table(cfg, ca, sa);
-  for (int e = 0; e < n; ++e) {
-    int sel = (!mask || mask[e]);
-    if (sel) reset_one(cfg, maps, &s, e, mode);
-    if (out) {
-      orc_outputs o = *out;
-      if (!sel) o.occupancy = NULL; /* untouched for envs that were not reset */
-      write_obs(cfg, maps, ca, sa, &s, e, &o, 1);
-      if (sel) {
-        if (out->reward) out->reward[e] = 0.f;
-        if (out->done) out->done[e] = 0;
-        if (out->progress) out->progress[e] = (float)s.f[RD_S_PROGRESS][e];
-        if (out->lap) out->lap[e] = s.i[RD_I_LAP][e];
-        if (out->time) out->time[e] = 0.f;
-        if (out->flags) out->flags[e] = 0;
-      }
+  const int A = cfg->agents_per_world > 1 ? cfg->agents_per_world : 1;
+  uint8_t* sel = (uint8_t*)malloc((size_t)n);
+  for (int e = 0; e < n; ++e) { /* a world resets as a whole [REF dreamer/tools.py:178-179] */
+    int v = (!mask || mask[e]);
+    for (int j = e - e % A; j < e - e % A + A && mask && A > 1; ++j) v = v || mask[j];
+    sel[e] = (uint8_t)v;
+  }
+  for (int e = 0; e < n; ++e) if (sel[e]) reset_one(cfg, maps, &s, e, mode);
+  for (int e = 0; e < n && out; ++e) { /* observations after every car has its new pose (scans see the other cars) */
+    orc_outputs o = *out;
+    if (!sel[e]) o.occupancy = NULL; /* untouched for envs that were not reset */
+    write_obs(cfg, maps, ca, sa, &s, e, &o, 1);
+    if (sel[e]) {
+      if (out->reward) out->reward[e] = 0.f;
+      if (out->done) out->done[e] = 0;
+      if (out->progress) out->progress[e] = (float)s.f[RD_S_PROGRESS][e];
+      if (out->lap) out->lap[e] = s.i[RD_I_LAP][e];
+      if (out->time) out->time[e] = 0.f;
+      if (out->flags) out->flags[e] = 0;
+      if (out->rank) out->rank[e] = 1 + e % A;
+      if (out->opponents) out->opponents[e] = 0;
     }
   }
+  free(sel);
   free(ca);
 }
 
@@ -580,28 +719,220 @@ static void step_one(const rd_config* cfg, const orc_map* maps, orc_view* s, int
   if (done && cfg->auto_reset) { reset_one(cfg, maps, s, e, cfg->reset_mode); *was_reset = 1; }
 }
 
-/* env.step(actions) for the whole batch.  stats may be NULL.  n_threads >= 1. */
-ORC_API void orc_step(const rd_config* cfg, const orc_map* maps, double* f64, int32_t* i32,
+/* ---- multi-agent worlds --------------------------------------------------------------------- */
+/* Body-box overlap of two cars: separating-axis test on the four box axes [NEW-SPEC: racecar_gym reports Bullet
+ * contacts between racecars as info['opponent_collisions']]. */
+static int rect_overlap(double hl, double hw, double dx, double dy, double c1, double s1, double c2, double s2) {
+  const double cr = fabs(c1 * c2 + s1 * s2), sr = fabs(c1 * s2 - s1 * c2);
+  const double ex = hl + (hl * cr + hw * sr), ey = hw + (hl * sr + hw * cr);
+  if (fabs(dx * c1 + dy * s1) > ex) return 0;
+  if (fabs(dy * c1 - dx * s1) > ey) return 0;
+  if (fabs(dx * c2 + dy * s2) > ex) return 0;
+  if (fabs(dy * c2 - dx * s2) > ey) return 0;
+  return 1;
+}
+
+/* One agent step of one WORLD of A cars (env indices w*A .. w*A+A-1), the dict-of-agents semantics of the reference's
+ * wrappers: ActionRepeat stops at the first tick in which ANY car is done [REF dreamer/wrappers.py:112] (baselines
+ * multi-agent variant: every tick runs, dones are OR-ed [REF baselines/racing/environment/multi_agent.py:72-79]);
+ * TimeLimit sets every done [REF dreamer/wrappers.py:151-153]; the world is reset when any car is done
+ * [REF dreamer/tools.py:178-179]; statistics follow the first agent [REF dreamer/tools.py:162-165].  Tasks per car:
+ * cfg->agent_task[a] (A > 1) or cfg->task; n_step_progress rewards progress over the last n ticks [NEW-SPEC]. */
+static void step_world(const rd_config* cfg, const orc_map* maps, orc_view* s, int w, const float* actions,
+                       const orc_outputs* o, rd_stats* st, int* was_reset) {
+  const int A = cfg->agents_per_world > 1 ? cfg->agents_per_world : 1;
+  const int e0 = w * A, n = s->n;
+  const orc_map* m = &maps[s->i[RD_I_MAP][e0]];
+  *was_reset = 0;
+  if (s->i[RD_I_FLAGS][e0] & RD_F_NEEDS_RESET) {
+    for (int e = e0; e < e0 + A; ++e) {
+      if (o->reward) o->reward[e] = 0.f;
+      if (o->done) o->done[e] = 1;
+      if (o->progress) o->progress[e] = (float)s->f[RD_S_PROGRESS][e];
+      if (o->lap) o->lap[e] = s->i[RD_I_LAP][e];
+      if (o->time) o->time[e] = (float)s->f[RD_S_TIME][e];
+      if (o->flags) o->flags[e] = (uint8_t)s->i[RD_I_FLAGS][e];
+    }
+    return;
+  }
+  double act[RD_MAX_AGENTS][2], q[RD_MAX_AGENTS][7], time[RD_MAX_AGENTS], p[RD_MAX_AGENTS], last[RD_MAX_AGENTS];
+  double total[RD_MAX_AGENTS], cs[RD_MAX_AGENTS][2];
+  int lap[RD_MAX_AGENTS], cp[RD_MAX_AGENTS], flags[RD_MAX_AGENTS], opp[RD_MAX_AGENTS], done[RD_MAX_AGENTS];
+  int col[RD_MAX_AGENTS], inside[RD_MAX_AGENTS];
+  const int ncp = cfg->n_checkpoints;
+  const double hl = 0.5 * cfg->vehicle.body_length, hw = 0.5 * cfg->vehicle.body_width;
+  for (int a = 0; a < A; ++a) {
+    const int e = e0 + a;
+    for (int k = 0; k < 2; ++k) {
+      float af = actions[2 * e + k];
+      if (cfg->clip_actions) af = af < -1.0f ? -1.0f : (af > 1.0f ? 1.0f : af);
+      if (cfg->rescale_actions) {
+        float t = (af + 1.0f) / 2.0f;
+        act[a][k] = (double)t * (cfg->action_high[k] - cfg->action_low[k]) + cfg->action_low[k];
+      } else {
+        act[a][k] = (double)af;
+      }
+    }
+    for (int k = 0; k < 7; ++k) q[a][k] = s->f[k][e];
+    time[a] = s->f[RD_S_TIME][e]; p[a] = s->f[RD_S_PROGRESS][e]; last[a] = s->f[RD_S_LAST][e];
+    lap[a] = s->i[RD_I_LAP][e]; cp[a] = s->i[RD_I_CHECKPOINT][e]; flags[a] = s->i[RD_I_FLAGS][e];
+    total[a] = 0.0; opp[a] = 0; done[a] = 0;
+  }
+  const int agent_step0 = s->i[RD_I_AGENT_STEP][e0];
+  for (int tk = 0; tk < cfg->action_repeat; ++tk) {
+    for (int a = 0; a < A; ++a) {
+      st_tick(cfg, q[a], act[a][0], act[a][1]);
+      time[a] = time[a] + cfg->dt;
+      col[a] = collides(cfg, m, q[a][0], q[a][1], q[a][4]);
+      int cx, cy;
+      inside[a] = cell_of(m, q[a][0], q[a][1], &cx, &cy);
+      progress_at(m, q[a][0], q[a][1], &p[a]);
+      cs[a][0] = cos(q[a][4]); cs[a][1] = sin(q[a][4]);
+    }
+    int any = 0;
+    for (int a = 0; a < A; ++a) {
+      const int e = e0 + a;
+      opp[a] = 0;
+      for (int j = 0; j < A; ++j)
+        if (j != a && rect_overlap(hl, hw, q[j][0] - q[a][0], q[j][1] - q[a][1], cs[a][0], cs[a][1], cs[j][0], cs[j][1]))
+          opp[a] |= 1 << j;
+      flags[a] &= ~(RD_F_COLLISION | RD_F_LEFT_MAP | RD_F_OPPONENT);
+      if (col[a]) flags[a] |= RD_F_COLLISION;
+      if (opp[a]) flags[a] |= RD_F_OPPONENT;
+      if (!inside[a]) flags[a] |= RD_F_LEFT_MAP;
+      if (!(q[a][0] == q[a][0] && q[a][1] == q[a][1] && q[a][3] == q[a][3] && q[a][4] == q[a][4])) flags[a] |= RD_F_NAN;
+      const int hitc = col[a] || opp[a] != 0;
+      int cn = checkpoint_of(cfg, p[a]);
+      if (cn == cp[a] + 1) { cp[a] = cn; flags[a] &= ~RD_F_WRONG_WAY; }
+      else if (cp[a] == ncp - 1 && cn == 0 && ncp > 1) { lap[a] += 1; cp[a] = 0; flags[a] &= ~RD_F_WRONG_WAY; }
+      else if (cn == cp[a] - 1 || (cp[a] == 0 && cn == ncp - 1 && ncp > 1)) { flags[a] |= RD_F_WRONG_WAY; }
+      const double cur = (double)lap[a] + p[a];
+      const int task = A > 1 ? cfg->agent_task[a] : cfg->task;
+      double r;
+      int d;
+      if (task == RD_TASK_MAX_SPEED) {
+        r = hitc ? -1.0 : -exp(fabs(act[a][1]) - q[a][3] * cos(q[a][6]));
+        d = 0;
+      } else {
+        double ref = last[a];
+        if (task == RD_TASK_N_STEP_PROGRESS && s->hist) {
+          int slot = (agent_step0 * cfg->action_repeat + tk) % cfg->n_step_progress;
+          ref = s->hist[(size_t)slot * n + e];
+          s->hist[(size_t)slot * n + e] = cur;
+        }
+        double delta = cur - ref;
+        if (delta > 0.5) delta = delta - 1.0;
+        if (delta < -0.5) delta = delta + 1.0;
+        if (cfg->progress_abs) delta = fabs(delta);
+        r = cfg->frame_reward + cfg->progress_reward * delta;
+        if (hitc) r = r + cfg->collision_reward;
+        d = (cfg->terminate_on_collision && hitc) || (lap[a] > cfg->laps) || (time[a] > cfg->time_limit);
+      }
+      last[a] = cur;
+      total[a] = total[a] + r;
+      if (cfg->repeat_semantics == RD_REPEAT_BASELINES) done[a] |= d; else done[a] = d;
+      any |= d;
+    }
+    if (any && cfg->repeat_semantics != RD_REPEAT_BASELINES) break;
+  }
+  int wdone = 0;
+  for (int a = 0; a < A; ++a) wdone |= done[a];
+  const int agent_step = agent_step0 + 1;
+  int timeout = 0;
+  if (cfg->time_limit_steps > 0 && agent_step >= cfg->time_limit_steps) {
+    timeout = !wdone; wdone = 1;
+    for (int a = 0; a < A; ++a) done[a] = 1;
+  }
+  for (int a = 0; a < A; ++a) {
+    const int e = e0 + a;
+    int rank = 1;
+    const double mine = (double)lap[a] + p[a];
+    for (int j = 0; j < A; ++j) {
+      if (j == a) continue;
+      const double other = (double)lap[j] + p[j];
+      if (other > mine || (other == mine && j < a)) rank += 1;
+    }
+    const double ret = s->f[RD_S_RETURN][e] + total[a];
+    for (int k = 0; k < 7; ++k) s->f[k][e] = q[a][k];
+    s->f[RD_S_TIME][e] = time[a]; s->f[RD_S_PROGRESS][e] = p[a]; s->f[RD_S_LAST][e] = last[a];
+    s->f[RD_S_RETURN][e] = ret;
+    s->i[RD_I_LAP][e] = lap[a]; s->i[RD_I_CHECKPOINT][e] = cp[a]; s->i[RD_I_AGENT_STEP][e] = agent_step;
+    if (wdone && !cfg->auto_reset) flags[a] |= RD_F_NEEDS_RESET;
+    s->i[RD_I_FLAGS][e] = flags[a];
+    if (o->reward) o->reward[e] = (float)total[a];
+    if (o->reward64) o->reward64[e] = total[a];
+    if (o->done) o->done[e] = (uint8_t)done[a];
+    if (o->progress) o->progress[e] = (float)p[a];
+    if (o->lap) o->lap[e] = lap[a];
+    if (o->time) o->time[e] = (float)time[a];
+    if (o->flags) o->flags[e] = (uint8_t)flags[a];
+    if (o->rank) o->rank[e] = rank;
+    if (o->opponents) o->opponents[e] = (uint8_t)opp[a];
+    if (st) {
+      st->env_steps += 1.0;
+      if (wdone && a == 0) {
+        st->episodes += 1.0;
+        st->return_sum += ret;
+        st->progress_sum += ((double)lap[a] + p[a]) - s->f[RD_S_START][e];
+        st->length_sum += (double)agent_step;
+        st->collisions += (flags[a] & (RD_F_COLLISION | RD_F_OPPONENT)) ? 1.0 : 0.0;
+        st->laps_completed += (double)(lap[a] - 1);
+        st->timeouts += timeout ? 1.0 : 0.0;
+      }
+    }
+  }
+  if (wdone && cfg->auto_reset) {
+    for (int e = e0; e < e0 + A; ++e) reset_one(cfg, maps, s, e, cfg->reset_mode);
+    *was_reset = 1;
+  }
+}
+
+static int uses_worlds(const rd_config* cfg) {
+  if (cfg->agents_per_world > 1) return 1;
+  return cfg->task == RD_TASK_N_STEP_PROGRESS;
+}
+
+/* env.step(actions) for the whole batch.  stats may be NULL.  n_threads >= 1.  hist: [n_step_progress][n] ring of the
+ * n_step_progress task or NULL. */
+ORC_API void orc_step(const rd_config* cfg, const orc_map* maps, double* f64, int32_t* i32, double* hist,
                       const float* actions, const double* commands, const orc_outputs* out, rd_stats* stats,
                       int n_threads) {
   int n = cfg->n_envs, nb = cfg->n_beams;
   orc_view s = view_of(f64, i32, n);
+  s.hist = hist;
   double* ca = (double*)malloc(sizeof(double) * 2 * nb);
   double* sa = ca + nb;
   orc_beam_table(cfg, ca, sa);
   if (n_threads < 1) n_threads = 1;
   rd_stats acc;
   memset(&acc, 0, sizeof(acc));
+  const int worlds = uses_worlds(cfg);
+  const int A = cfg->agents_per_world > 1 ? cfg->agents_per_world : 1;
+  uint8_t* mark = (uint8_t*)calloc((size_t)n, 1); /* bit0 frozen, bit1 was reset */
 #pragma omp parallel num_threads(n_threads)
   {
     rd_stats loc;
     memset(&loc, 0, sizeof(loc));
+    if (worlds) {
+      /* phase 1: every world advances; phase 2: observations (scans see the other cars' committed poses) */
 #pragma omp for schedule(dynamic, 8)
-    for (int e = 0; e < n; ++e) {
-      int was_reset = 0;
-      int frozen = (s.i[RD_I_FLAGS][e] & RD_F_NEEDS_RESET) != 0;
-      step_one(cfg, maps, &s, e, actions, commands, out, &loc, &was_reset);
-      if (!frozen) write_obs(cfg, maps, ca, sa, &s, e, out, was_reset);
+      for (int w = 0; w < n / A; ++w) {
+        int was_reset = 0;
+        int frozen = (s.i[RD_I_FLAGS][w * A] & RD_F_NEEDS_RESET) != 0;
+        step_world(cfg, maps, &s, w, actions, out, &loc, &was_reset);
+        for (int e = w * A; e < w * A + A; ++e) mark[e] = (uint8_t)((frozen ? 1 : 0) | (was_reset ? 2 : 0));
+      }
+#pragma omp for schedule(dynamic, 8)
+      for (int e = 0; e < n; ++e)
+        if (!(mark[e] & 1)) write_obs(cfg, maps, ca, sa, &s, e, out, (mark[e] & 2) != 0);
+    } else {
+#pragma omp for schedule(dynamic, 8)
+      for (int e = 0; e < n; ++e) {
+        int was_reset = 0;
+        int frozen = (s.i[RD_I_FLAGS][e] & RD_F_NEEDS_RESET) != 0;
+        step_one(cfg, maps, &s, e, actions, commands, out, &loc, &was_reset);
+        if (!frozen) write_obs(cfg, maps, ca, sa, &s, e, out, was_reset);
+      }
     }
 #pragma omp critical
     {
@@ -615,6 +946,7 @@ ORC_API void orc_step(const rd_config* cfg, const orc_map* maps, double* f64, in
     stats->length_sum += acc.length_sum; stats->collisions += acc.collisions;
     stats->laps_completed += acc.laps_completed; stats->env_steps += acc.env_steps; stats->timeouts += acc.timeouts;
   }
+  free(mark);
   free(ca);
 }
 

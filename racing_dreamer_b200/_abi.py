@@ -8,20 +8,23 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 1
+ABI_VERSION = 2
+MAX_AGENTS = 4   # RD_MAX_AGENTS
+MAX_NSTEP = 32   # RD_MAX_NSTEP
 
 # enums (include/rd_env.h)
-RESET_GRID, RESET_RANDOM, RESET_RANDOM_BIDIRECTIONAL = 0, 1, 2
-RESET_MODES = {"grid": RESET_GRID, "random": RESET_RANDOM, "random_bidirectional": RESET_RANDOM_BIDIRECTIONAL}
-TASK_MAX_PROGRESS, TASK_MAX_SPEED = 0, 1
+RESET_GRID, RESET_RANDOM, RESET_RANDOM_BIDIRECTIONAL, RESET_RANDOM_BALL = 0, 1, 2, 3
+RESET_MODES = {"grid": RESET_GRID, "random": RESET_RANDOM, "random_bidirectional": RESET_RANDOM_BIDIRECTIONAL,
+               "random_ball": RESET_RANDOM_BALL}
+TASK_MAX_PROGRESS, TASK_MAX_SPEED, TASK_N_STEP_PROGRESS = 0, 1, 2
 TASKS = {"maximize_progress": TASK_MAX_PROGRESS, "max_progress": TASK_MAX_PROGRESS,
-         "max_speed": TASK_MAX_SPEED, "maximize_speed": TASK_MAX_SPEED}
+         "max_speed": TASK_MAX_SPEED, "maximize_speed": TASK_MAX_SPEED, "n_step_progress": TASK_N_STEP_PROGRESS}
 OBS_LIDAR, OBS_OCCUPANCY, OBS_LIDAR_NORM = 1, 2, 4
 REPEAT_DREAMER, REPEAT_BASELINES = 0, 1
 
 S_X, S_Y, S_STEER, S_V, S_YAW, S_YAWRATE, S_SLIP, S_TIME, S_PROGRESS, S_LAST, S_RETURN, S_START, NF64 = range(13)
 I_LAP, I_CHECKPOINT, I_FLAGS, I_AGENT_STEP, I_EPISODE, I_MAP, NI32 = range(7)
-F_WRONG_WAY, F_COLLISION, F_NEEDS_RESET, F_LEFT_MAP, F_NAN = 1, 2, 4, 8, 16
+F_WRONG_WAY, F_COLLISION, F_NEEDS_RESET, F_LEFT_MAP, F_NAN, F_OPPONENT = 1, 2, 4, 8, 16, 32
 
 
 class RdVehicle(C.Structure):
@@ -49,6 +52,8 @@ class RdConfig(C.Structure):
         ("lidar_fov", C.c_double), ("lidar_range_min", C.c_double), ("lidar_range_max", C.c_double),
         ("lidar_offset", C.c_double),
         ("lidar_noise", C.c_float), ("reserved0", C.c_float),
+        ("agents_per_world", C.c_int32), ("agent_task", C.c_int32 * MAX_AGENTS), ("n_step_progress", C.c_int32),
+        ("ball_spacing", C.c_double),
         ("vehicle", RdVehicle),
     ]
 
@@ -61,7 +66,7 @@ class RdConfig(C.Structure):
 class RdOutputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "lidar_dev", "occupancy_dev", "pose_dev", "velocity_dev", "speed_dev", "reward_dev", "done_dev",
-        "progress_dev", "lap_dev", "time_dev", "flags_dev")]
+        "progress_dev", "lap_dev", "time_dev", "flags_dev", "rank_dev", "opponents_dev")]
 
 
 class RdStats(C.Structure):

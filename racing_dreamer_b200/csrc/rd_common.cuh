@@ -18,6 +18,7 @@ struct DevMap {
   const uint16_t* dist;
   const double* start;   // [n_start][3]
   const double* reset;   // [n_reset][3]
+  const int32_t* ball_next;  // [n_reset] the reset pose cfg.ball_spacing metres further along the lap (multi-agent resets)
   int h, w, rw, col0, row0, full_h, dmax, n_start, n_reset;
   int bits_bytes;        // bytes of bits + clearance field, each rounded up to 16 (bulk-copy granularity)
   int coarse_off;        // byte offset of the clearance field u8[ch][cw] (rd_march.cuh)
@@ -27,8 +28,8 @@ struct DevMap {
 
 // Per-env record handed from the dynamics/reset kernel to the LiDAR and occupancy kernels (48 B, 16-B aligned).
 struct __align__(16) OriginRec {
-  int32_t px, py;        // sensor origin in 2^-12 cells relative to the crop (valid only if `valid`)
-  int32_t valid;         // origin inside a drivable cell
+  int32_t px, py;        // sensor origin in 2^-12 cells relative to the crop
+  int32_t valid;         // bit0: origin inside a drivable cell; bit1: px/py hold the position
   uint32_t gid;          // global env id (noise counter)
   uint32_t episode, step;
   int32_t was_reset;     // env was reset in this call (occupancy obs = zeros) ; 2 = frozen (leave outputs)
@@ -44,6 +45,11 @@ struct LidarParams {
   float scale;           // metres per (sub-cell / direction unit) = 2^(DIR-SUB) * resolution
   int64_t rsub;          // range_max in sub-cells
   uint32_t key0, key1;   // Philox key of the noise stream
+  // multi-agent worlds: the other cars of the world are seen by the scan (agents <= 1: off)
+  int agents;            // cars per world; env e belongs to world e / agents
+  int car_reach;         // |origin difference| (sub-cells, per axis) beyond which a car cannot be within range
+  float car_ulo, car_uhi, car_hw;  // body box in the OTHER car's sensor frame, cells: u in [ulo, uhi], |v| <= hw
+  float res;             // metres per cell
 };
 
 // ---- Philox4x32-10 (counter-based RNG; identical integer arithmetic in the oracle) ----

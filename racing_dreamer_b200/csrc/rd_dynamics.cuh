@@ -23,12 +23,13 @@ struct StepParams {
   OriginRec* recs;  // [n]
   const DevMap* maps;
   PolicyState pol;  // on-device controller state, cleared with the env (null pointers: no policy attached)
+  double* hist;     // [n_step_progress][n] ring of lap + progress per sim tick (n_step_progress task), or null
   int n;
 };
 
 struct OutPtrs {
   float* pose; float* velocity; float* speed; float* reward; uint8_t* done; float* progress; int32_t* lap;
-  float* time; uint8_t* flags; uint8_t* occupancy;
+  float* time; uint8_t* flags; uint8_t* occupancy; int32_t* rank; uint8_t* opponents;
 };
 
 __device__ __forceinline__ void st_rhs(const rd_vehicle& p, const double (&q)[7], double sv, double acc, double (&f)[7]) {
@@ -138,9 +139,11 @@ __device__ __forceinline__ bool rd_collides(const rd_config& cfg, const DevMap& 
 // loads (plus the centre's wavefront distance) issued together, instead of five dependent round trips.
 // Same results as rd_collides() + rd_cell_of() + rd_progress_at().
 __device__ __forceinline__ void rd_probe(const rd_config& cfg, const DevMap& m, double x, double y, double yaw,
-                                         bool& col, bool& inside, double& p) {
+                                         bool& col, bool& inside, double& p, double* c_out = nullptr,
+                                         double* s_out = nullptr) {
   double c, s;
   rd_sincos(yaw, &s, &c);
+  if (c_out) { *c_out = c; *s_out = s; }
   const double hl = 0.5 * cfg.vehicle.body_length, hw = 0.5 * cfg.vehicle.body_width;
   const double ax = hl * c, ay = hl * s, bx = hw * s, by = hw * c;
   const double px[5] = {x, (x + ax) - bx, (x + ax) + bx, (x - ax) - bx, (x - ax) + bx};
@@ -169,14 +172,20 @@ __device__ __forceinline__ void rd_reset_one(const StepParams& P, int e, int mod
   const int n = P.n;
   const DevMap& m = P.maps[P.i32[(size_t)RD_I_MAP * n + e]];
   const uint32_t episode = (uint32_t)P.i32[(size_t)RD_I_EPISODE * n + e];
-  const uint64_t gid = (uint64_t)(cfg.env_id_offset + e);
+  // multi-agent worlds: the cars of a world draw ONE anchor (counter = global id of the world's agent 0) and line up
+  // along the ball_next chain (cfg.ball_spacing metres of track apart); 'grid' hands out the staggered start slots
+  const int A = cfg.agents_per_world > 1 ? cfg.agents_per_world : 1;
+  const int a = e % A;
+  const uint64_t gid = (uint64_t)(cfg.env_id_offset + (e - a));
   double x, y, yaw;
   if (mode == RD_RESET_GRID || m.n_reset <= 0) {
-    x = m.start[0]; y = m.start[1]; yaw = m.start[2];
+    const int slot = a < m.n_start ? a : m.n_start - 1;
+    x = m.start[3 * slot]; y = m.start[3 * slot + 1]; yaw = m.start[3 * slot + 2];
   } else {
     uint32_t c[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), episode, 0u};
     philox4x32_10(c, (uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32) ^ RD_STREAM_RESET);
     uint32_t idx = __umulhi(c[0], (uint32_t)m.n_reset);
+    for (int k = 0; k < a && m.ball_next; ++k) idx = (uint32_t)__ldg(m.ball_next + idx);
     x = m.reset[3 * idx]; y = m.reset[3 * idx + 1]; yaw = m.reset[3 * idx + 2];
     if (mode == RD_RESET_RANDOM_BIDIRECTIONAL && (c[1] & 1u)) yaw = yaw + 3.14159265358979323846;
   }
@@ -196,6 +205,7 @@ __device__ __forceinline__ void rd_reset_one(const StepParams& P, int e, int mod
   I[(size_t)RD_I_FLAGS * n + e] = 0;
   I[(size_t)RD_I_AGENT_STEP * n + e] = 0;
   I[(size_t)RD_I_EPISODE * n + e] = (int32_t)(episode + 1u);
+  if (P.hist) for (int k = 0; k < cfg.n_step_progress; ++k) P.hist[(size_t)k * n + e] = 1.0 + p;
   if (P.pol.i32 || P.pol.dr_feat) rd_policy_clear(P.pol, n, e);
 }
 
@@ -234,7 +244,11 @@ __global__ void __launch_bounds__(128) k_reset(StepParams P, OutPtrs o, const ui
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= P.n) return;
   const int n = P.n;
-  const bool sel = (!mask || mask[e]);
+  bool sel = (!mask || mask[e]);
+  if (mask && P.cfg.agents_per_world > 1) {  // a world resets as a whole [REF dreamer/tools.py:178-179]
+    const int A = P.cfg.agents_per_world, b = e - e % A;
+    for (int j = 0; j < A; ++j) sel = sel || mask[b + j];
+  }
   if (sel) rd_reset_one(P, e, mode);
   rd_write_obs(P, o, e, sel ? 1 : 3);  // 3: not reset here -> occupancy output left untouched
   if (sel) {
@@ -244,6 +258,8 @@ __global__ void __launch_bounds__(128) k_reset(StepParams P, OutPtrs o, const ui
     if (o.lap) o.lap[e] = P.i32[(size_t)RD_I_LAP * n + e];
     if (o.time) o.time[e] = 0.f;
     if (o.flags) o.flags[e] = 0;
+    if (o.rank) o.rank[e] = 1 + (P.cfg.agents_per_world > 1 ? e % P.cfg.agents_per_world : 0);  // refined by the first step
+    if (o.opponents) o.opponents[e] = 0;
   }
 }
 
@@ -354,6 +370,199 @@ __global__ void __launch_bounds__(128) k_step(StepParams P, OutPtrs o, const flo
   }
   // K5 episode statistics: warp reduce, one atomic per warp and counter
   // [REF dreamer/tools.py:159-206 simulate(): per-episode return / progress lists]
+  const unsigned any_done = __ballot_sync(0xffffffffu, st[0] != 0.0);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (k != 6 && !any_done) continue;
+    double v = st[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(P.stats + k, v);
+  }
+}
+
+// ---- multi-agent worlds -----------------------------------------------------------------------
+// Overlap of two body boxes (half extents hl x hw, centres d apart, headings (c1,s1), (c2,s2)): separating-axis test on
+// the four box axes, float64, one IEEE operation per step in the order written (the oracle's rect_overlap).
+// [NEW-SPEC: racecar_gym reports Bullet contacts between racecars as info['opponent_collisions']]
+__device__ __forceinline__ bool rd_rect_overlap(double hl, double hw, double dx, double dy, double c1, double s1,
+                                                double c2, double s2) {
+  const double cr = fabs(c1 * c2 + s1 * s2), sr = fabs(c1 * s2 - s1 * c2);
+  const double ex = hl + (hl * cr + hw * sr), ey = hw + (hl * sr + hw * cr);
+  if (fabs(dx * c1 + dy * s1) > ex) return false;
+  if (fabs(dy * c1 - dx * s1) > ey) return false;
+  if (fabs(dx * c2 + dy * s2) > ex) return false;
+  if (fabs(dy * c2 - dx * s2) > ey) return false;
+  return true;
+}
+
+// k_step for worlds of A = cfg.agents_per_world cars (A = 1 allowed: single cars on the n_step_progress task).
+// One thread per car; the cars of a world are adjacent threads of one CTA (a CTA holds blockDim.x / A whole worlds) and
+// exchange poses / done flags through shared memory every tick:
+//   tick:  every car integrates its own dynamics and probes the walls            -> pose to shared memory
+//          body-box overlap with the other cars of the world (opponent mask), progress/lap machine, the car's own task
+//          reward and done                                                        -> done flag to shared memory
+//          dreamer ActionRepeat: the WORLD stops repeating at the first tick in which any car is done
+//          [REF dreamer/wrappers.py:112]; baselines multi-agent ActionRepeat: all ticks run, dones are OR-ed
+//          [REF baselines/racing/environment/multi_agent.py:72-79]
+//   then:  TimeLimit (one counter per world, all dones True [REF dreamer/wrappers.py:151-153]), rank, commit, auto-reset
+//          of the whole world when any car is done [REF dreamer/tools.py:178-179].
+// Episode statistics follow tools.simulate: the world's first agent only [REF dreamer/tools.py:162-165 main_id].
+__global__ void __launch_bounds__(128) k_step_ma(StepParams P, OutPtrs o, const float* __restrict__ actions) {
+  __shared__ double sh_pose[128 * 4];
+  __shared__ double sh_prog[128];
+  __shared__ int sh_flag[128];
+  const int n = P.n;
+  const rd_config& cfg = P.cfg;
+  const int A = cfg.agents_per_world > 1 ? cfg.agents_per_world : 1;
+  const int wpc = (int)blockDim.x / A;             // worlds per CTA
+  const int t = (int)threadIdx.x;
+  const int e = (int)blockIdx.x * wpc * A + t;
+  const bool live = t < wpc * A && e < n;
+  const int a = t % A, base = t - a;               // agent index, first thread of my world
+  double st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double* f = P.f64;
+  int32_t* I = P.i32;
+  int flags = live ? I[(size_t)RD_I_FLAGS * n + e] : 0;
+  const bool frozen = live && (flags & RD_F_NEEDS_RESET);
+  const bool run = live && !frozen;
+  const int task = A > 1 ? cfg.agent_task[a] : cfg.task;
+  const int ncp = cfg.n_checkpoints;
+  const double inv_dt = 1.0 / cfg.dt;
+  const double hl = 0.5 * cfg.vehicle.body_length, hw = 0.5 * cfg.vehicle.body_width;
+  const DevMap& m = P.maps[run ? I[(size_t)RD_I_MAP * n + e] : 0];
+  double act[2] = {0.0, 0.0};
+  double q[7] = {0, 0, 0, 0, 0, 0, 0};
+  double time = 0.0, p = 0.0, last = 0.0, total = 0.0;
+  int lap = 1, cp = 0, agent_step0 = 0, opp = 0, done = 0;
+  if (run) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {  // a4, as in k_step
+      float af = actions[2 * e + k];
+      if (cfg.clip_actions) af = af < -1.0f ? -1.0f : (af > 1.0f ? 1.0f : af);
+      if (cfg.rescale_actions) {
+        const float h = __fdiv_rn(__fadd_rn(af, 1.0f), 2.0f);
+        act[k] = (double)h * (cfg.action_high[k] - cfg.action_low[k]) + cfg.action_low[k];
+      } else {
+        act[k] = (double)af;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 7; ++k) q[k] = f[(size_t)k * n + e];
+    time = f[(size_t)RD_S_TIME * n + e]; p = f[(size_t)RD_S_PROGRESS * n + e]; last = f[(size_t)RD_S_LAST * n + e];
+    lap = I[(size_t)RD_I_LAP * n + e]; cp = I[(size_t)RD_I_CHECKPOINT * n + e];
+    agent_step0 = I[(size_t)RD_I_AGENT_STEP * n + e];
+  }
+  bool ticking = run;
+  for (int tk = 0; tk < cfg.action_repeat; ++tk) {
+    bool col = false, inside = true;
+    if (ticking) {
+      st_tick(cfg, q, act[0], act[1], inv_dt);
+      time = time + cfg.dt;
+      double c, s;
+      rd_probe(cfg, m, q[0], q[1], q[4], col, inside, p, &c, &s);
+      sh_pose[4 * t] = q[0]; sh_pose[4 * t + 1] = q[1]; sh_pose[4 * t + 2] = c; sh_pose[4 * t + 3] = s;
+    }
+    __syncthreads();
+    int d = 0;
+    if (ticking) {
+      opp = 0;
+      for (int j = 0; j < A; ++j) {
+        if (j == a) continue;
+        const double* w = sh_pose + 4 * (base + j);
+        if (rd_rect_overlap(hl, hw, w[0] - q[0], w[1] - q[1], sh_pose[4 * t + 2], sh_pose[4 * t + 3], w[2], w[3])) opp |= 1 << j;
+      }
+      flags &= ~(RD_F_COLLISION | RD_F_LEFT_MAP | RD_F_OPPONENT);
+      if (col) flags |= RD_F_COLLISION;
+      if (opp) flags |= RD_F_OPPONENT;
+      if (!inside) flags |= RD_F_LEFT_MAP;
+      if (!(q[0] == q[0] && q[1] == q[1] && q[3] == q[3] && q[4] == q[4])) flags |= RD_F_NAN;
+      const bool hitc = col || opp != 0;   // the task's collision: walls or other cars
+      const int cn = rd_checkpoint_of(cfg, p);
+      if (cn == cp + 1) { cp = cn; flags &= ~RD_F_WRONG_WAY; }
+      else if (cp == ncp - 1 && cn == 0 && ncp > 1) { lap += 1; cp = 0; flags &= ~RD_F_WRONG_WAY; }
+      else if (cn == cp - 1 || (cp == 0 && cn == ncp - 1 && ncp > 1)) { flags |= RD_F_WRONG_WAY; }
+      const double cur = (double)lap + p;
+      double r;
+      if (task == RD_TASK_MAX_SPEED) {
+        r = hitc ? -1.0 : -exp(fabs(act[1]) - q[3] * cos(q[6]));
+        d = 0;
+      } else {
+        double ref = last;
+        if (task == RD_TASK_N_STEP_PROGRESS && P.hist) {  // progress over the last n ticks
+          const int slot = (agent_step0 * cfg.action_repeat + tk) % cfg.n_step_progress;
+          ref = P.hist[(size_t)slot * n + e];
+          P.hist[(size_t)slot * n + e] = cur;
+        }
+        double delta = cur - ref;
+        if (delta > 0.5) delta = delta - 1.0;
+        if (delta < -0.5) delta = delta + 1.0;
+        if (cfg.progress_abs) delta = fabs(delta);
+        r = cfg.frame_reward + cfg.progress_reward * delta;
+        if (hitc) r = r + cfg.collision_reward;
+        d = ((cfg.terminate_on_collision && hitc) || (lap > cfg.laps) || (time > cfg.time_limit)) ? 1 : 0;
+      }
+      last = cur;
+      total = total + r;
+      if (cfg.repeat_semantics == RD_REPEAT_BASELINES) done |= d; else done = d;
+      sh_flag[t] = d;
+    }
+    __syncthreads();
+    if (ticking && cfg.repeat_semantics != RD_REPEAT_BASELINES) {
+      int any = 0;
+      for (int j = 0; j < A; ++j) any |= sh_flag[base + j];
+      if (any) ticking = false;
+    }
+  }
+  // world-level done, rank
+  __syncthreads();
+  if (run) { sh_flag[t] = done; sh_prog[t] = (double)lap + p; }
+  __syncthreads();
+  if (frozen) {  // frozen until reset [REF dreamer/wrappers.py:148]
+    if (o.reward) o.reward[e] = 0.f;
+    if (o.done) o.done[e] = 1;
+    if (o.progress) o.progress[e] = (float)f[(size_t)RD_S_PROGRESS * n + e];
+    if (o.lap) o.lap[e] = I[(size_t)RD_I_LAP * n + e];
+    if (o.time) o.time[e] = (float)f[(size_t)RD_S_TIME * n + e];
+    if (o.flags) o.flags[e] = (uint8_t)flags;
+    P.recs[e].was_reset = 2;
+  } else if (run) {
+    int wdone = 0, rank = 1;
+    const double mine = sh_prog[t];
+    for (int j = 0; j < A; ++j) {
+      wdone |= sh_flag[base + j];
+      if (j != a) { const double other = sh_prog[base + j]; if (other > mine || (other == mine && j < a)) rank += 1; }
+    }
+    const int agent_step = agent_step0 + 1;  // TimeLimit [REF dreamer/wrappers.py:147-154]
+    int timeout = 0;
+    if (cfg.time_limit_steps > 0 && agent_step >= cfg.time_limit_steps) { timeout = !wdone; done = 1; wdone = 1; }
+    const double ret = f[(size_t)RD_S_RETURN * n + e] + total;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) f[(size_t)k * n + e] = q[k];
+    f[(size_t)RD_S_TIME * n + e] = time; f[(size_t)RD_S_PROGRESS * n + e] = p;
+    f[(size_t)RD_S_LAST * n + e] = last; f[(size_t)RD_S_RETURN * n + e] = ret;
+    I[(size_t)RD_I_LAP * n + e] = lap; I[(size_t)RD_I_CHECKPOINT * n + e] = cp;
+    I[(size_t)RD_I_AGENT_STEP * n + e] = agent_step;
+    if (wdone && !cfg.auto_reset) flags |= RD_F_NEEDS_RESET;
+    I[(size_t)RD_I_FLAGS * n + e] = flags;
+    if (o.reward) o.reward[e] = (float)total;
+    if (o.done) o.done[e] = (uint8_t)done;
+    if (o.progress) o.progress[e] = (float)p;
+    if (o.lap) o.lap[e] = lap;
+    if (o.time) o.time[e] = (float)time;
+    if (o.flags) o.flags[e] = (uint8_t)flags;
+    if (o.rank) o.rank[e] = rank;
+    if (o.opponents) o.opponents[e] = (uint8_t)opp;
+    st[6] = 1.0;
+    if (wdone && a == 0) {
+      st[0] = 1.0; st[1] = ret; st[2] = ((double)lap + p) - f[(size_t)RD_S_START * n + e];
+      st[3] = (double)agent_step; st[4] = (flags & (RD_F_COLLISION | RD_F_OPPONENT)) ? 1.0 : 0.0; st[5] = (double)(lap - 1);
+      st[7] = timeout ? 1.0 : 0.0;
+    }
+    int was_reset = 0;
+    if (wdone && cfg.auto_reset) { rd_reset_one(P, e, cfg.reset_mode); was_reset = 1; }
+    rd_write_obs(P, o, e, was_reset);
+  }
   const unsigned any_done = __ballot_sync(0xffffffffu, st[0] != 0.0);
 #pragma unroll
   for (int k = 0; k < 8; ++k) {

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -13,6 +14,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "rd_common.cuh"
@@ -34,6 +36,7 @@ struct HostMap {
   void* d_dist = nullptr;
   void* d_start = nullptr;
   void* d_reset = nullptr;
+  void* d_next = nullptr;
   bool present = false;
   int lidar_per_sm = -1;   // resident k_lidar CTAs per SM for this map (cached launch configuration)
 };
@@ -51,6 +54,8 @@ struct rd_env {
   double* d_f64 = nullptr;
   int32_t* d_i32 = nullptr;
   double* d_stats = nullptr;
+  double* d_hist = nullptr;       // [n_step_progress][n] ring of lap + progress (n_step_progress task), else null
+  bool multi = false;             // k_step_ma steps the batch (agents_per_world > 1 or an n_step_progress task)
   OriginRec* d_recs = nullptr;
   double* d_beam_tab = nullptr;
   DevMap* d_maps = nullptr;
@@ -155,6 +160,10 @@ void default_config(rd_config* c) {
   c->lidar_range_max = 15.0;  // [REF dreamer/tools.py:274]
   c->lidar_offset = 0.0;
   c->lidar_noise = 0.0f;
+  c->agents_per_world = 1;
+  for (int a = 0; a < RD_MAX_AGENTS; ++a) c->agent_task[a] = RD_TASK_MAX_PROGRESS;
+  c->n_step_progress = 10;    // [REF baselines/scenarios/max_progress/austria.yml:18]
+  c->ball_spacing = 1.5;
   rd_vehicle* v = &c->vehicle;
   v->mu = 1.0489; v->c_sf = 4.718; v->c_sr = 5.4562; v->lf = 0.15875; v->lr = 0.17145; v->h_cg = 0.074;
   v->mass = 3.74; v->inertia = 0.04712;
@@ -210,6 +219,16 @@ LidarParams lidar_params(const rd_env* env, const DevMap& m) {
   lp.rsub = (int64_t)std::rint(c.lidar_range_max * m.inv_res * (double)RD_SUB);
   lp.key0 = (uint32_t)c.seed;
   lp.key1 = (uint32_t)(c.seed >> 32) ^ RD_STREAM_LIDAR;
+  lp.agents = c.agents_per_world > 1 ? c.agents_per_world : 1;
+  {  // body box of another car in ITS sensor frame (the record holds the sensor origin), in cells, as float32
+    const double hl = 0.5 * c.vehicle.body_length * m.inv_res, hw = 0.5 * c.vehicle.body_width * m.inv_res;
+    const double off = c.lidar_offset * m.inv_res;
+    lp.car_ulo = (float)(-hl - off);
+    lp.car_uhi = (float)(hl - off);
+    lp.car_hw = (float)hw;
+    lp.res = (float)m.res;
+    lp.car_reach = (int)std::ceil((c.lidar_range_max * m.inv_res + 2.0 * (hl + hw + std::fabs(off)) + 2.0) * (double)RD_SUB);
+  }
   return lp;
 }
 
@@ -271,7 +290,7 @@ OutPtrs out_ptrs(const rd_outputs* o) {
   if (o) {
     p.pose = o->pose_dev; p.velocity = o->velocity_dev; p.speed = o->speed_dev; p.reward = o->reward_dev;
     p.done = o->done_dev; p.progress = o->progress_dev; p.lap = o->lap_dev; p.time = o->time_dev;
-    p.flags = o->flags_dev; p.occupancy = o->occupancy_dev;
+    p.flags = o->flags_dev; p.occupancy = o->occupancy_dev; p.rank = o->rank_dev; p.opponents = o->opponents_dev;
   }
   return p;
 }
@@ -281,9 +300,28 @@ StepParams step_params(rd_env* env) {
   P.cfg = env->cfg;
   P.f64 = env->d_f64; P.i32 = env->d_i32; P.stats = env->d_stats; P.recs = env->d_recs; P.maps = env->d_maps;
   P.pol = env->pol.st;
+  P.hist = env->d_hist;
   if (env->dr.ready) { P.pol.dr_feat = env->dr.feat[env->dr.cur].p[0]; P.pol.dr_feat_lo = env->dr.feat[env->dr.cur].p[1]; P.pol.dr_ld = env->dr.ldf; }
   P.n = env->n;
   return P;
+}
+
+// the dynamics / reward / termination kernel over the whole batch: k_step (independent cars) or k_step_ma (worlds)
+int launch_step(rd_env* env, const rd_outputs* out, const float* actions_dev, cudaStream_t s) {
+  {
+    ScopedTiming tm(env, s, T_STEP);
+    if (env->multi) {
+      const int A = env->cfg.agents_per_world > 1 ? env->cfg.agents_per_world : 1;
+      const int tb = env->step_block, per_cta = (tb / A) * A;
+      k_step_ma<<<(env->n + per_cta - 1) / per_cta, tb, 0, s>>>(step_params(env), out_ptrs(out), actions_dev);
+    } else {
+      const int tb = env->step_block;
+      k_step<<<(env->n + tb - 1) / tb, tb, 0, s>>>(step_params(env), out_ptrs(out), actions_dev, 0, env->n);
+    }
+  }
+  env->launches++;
+  CUDA_TRY(env, cudaGetLastError());
+  return RD_OK;
 }
 
 // LiDAR / occupancy launches for the envs [e0, e1) (grouped by map; each map's env list is ascending)
@@ -354,6 +392,20 @@ RD_API int rd_create(const rd_config* cfg, rd_env** out) {
   if (cfg->n_envs < 1 || cfg->n_beams < 1 || cfg->n_beams > 8192 || cfg->action_repeat < 1 || cfg->n_checkpoints < 1 ||
       !(cfg->dt > 0.0) || !(cfg->lidar_range_max > 0.0))
     return fail(nullptr, RD_ERR_INVALID, "bad config (n_envs %d, n_beams %d, action_repeat %d)", cfg->n_envs, cfg->n_beams, cfg->action_repeat);
+  {
+    const int A = cfg->agents_per_world;
+    if (A > RD_MAX_AGENTS || (A > 1 && cfg->n_envs % A != 0))
+      return fail(nullptr, RD_ERR_INVALID, "agents_per_world %d: must be 1..%d and divide n_envs %d", A, RD_MAX_AGENTS, cfg->n_envs);
+    bool nstep = A > 1 ? false : cfg->task == RD_TASK_N_STEP_PROGRESS;
+    for (int a = 0; a < A && A > 1; ++a) {
+      if (cfg->agent_task[a] < RD_TASK_MAX_PROGRESS || cfg->agent_task[a] > RD_TASK_N_STEP_PROGRESS)
+        return fail(nullptr, RD_ERR_INVALID, "agent_task[%d] = %d is not an RD_TASK_*", a, cfg->agent_task[a]);
+      nstep = nstep || cfg->agent_task[a] == RD_TASK_N_STEP_PROGRESS;
+    }
+    if (nstep && (cfg->n_step_progress < 1 || cfg->n_step_progress > RD_MAX_NSTEP))
+      return fail(nullptr, RD_ERR_INVALID, "n_step_progress %d out of range [1,%d]", cfg->n_step_progress, RD_MAX_NSTEP);
+    if (A > 1 && !(cfg->ball_spacing > 0.0)) return fail(nullptr, RD_ERR_INVALID, "ball_spacing must be positive");
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
     cudaGetLastError();
@@ -383,6 +435,13 @@ RD_API int rd_create(const rd_config* cfg, rd_env** out) {
   alloc((void**)&env->d_i32, sizeof(int32_t) * RD_NI32 * n);
   alloc((void**)&env->d_stats, sizeof(double) * 8);
   alloc((void**)&env->d_recs, sizeof(OriginRec) * n);
+  {
+    const int A = cfg->agents_per_world > 1 ? cfg->agents_per_world : 1;
+    bool nstep = A > 1 ? false : cfg->task == RD_TASK_N_STEP_PROGRESS;
+    for (int a = 0; a < A && A > 1; ++a) nstep = nstep || cfg->agent_task[a] == RD_TASK_N_STEP_PROGRESS;
+    env->multi = A > 1 || nstep;
+    if (nstep) alloc((void**)&env->d_hist, sizeof(double) * (size_t)cfg->n_step_progress * n);
+  }
   alloc((void**)&env->d_beam_tab, sizeof(double) * 2 * (size_t)cfg->n_beams);
   alloc((void**)&env->d_maps, sizeof(DevMap) * RD_MAX_MAPS);
   alloc((void**)&env->d_env_order, sizeof(int32_t) * n);
@@ -407,7 +466,7 @@ RD_API int rd_create(const rd_config* cfg, rd_env** out) {
 
 RD_API void rd_destroy(rd_env* env) {
   if (!env) return;
-  cudaFree(env->d_f64); cudaFree(env->d_i32); cudaFree(env->d_stats); cudaFree(env->d_recs);
+  cudaFree(env->d_f64); cudaFree(env->d_i32); cudaFree(env->d_stats); cudaFree(env->d_hist); cudaFree(env->d_recs);
   cudaFree(env->d_beam_tab); cudaFree(env->d_maps); cudaFree(env->d_env_order); cudaFree(env->d_lidar_ctr);
   cudaFree(env->d_stage_recs); cudaFree(env->d_stage_ids);
   cudaFree(env->pol.st.f64); cudaFree(env->pol.st.i32); cudaFree(env->pol.d_actions);
@@ -424,7 +483,7 @@ RD_API void rd_destroy(rd_env* env) {
   }
   for (auto& t : env->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (auto& e : env->event_pool) cudaEventDestroy(e);
-  for (auto& m : env->maps) { cudaFree(m.d_bits); cudaFree(m.d_dist); cudaFree(m.d_start); cudaFree(m.d_reset); }
+  for (auto& m : env->maps) { cudaFree(m.d_bits); cudaFree(m.d_dist); cudaFree(m.d_start); cudaFree(m.d_reset); cudaFree(m.d_next); }
   delete env;
 }
 
@@ -448,7 +507,7 @@ RD_API int rd_upload_map(rd_env* env, int map_id, const uint32_t* bits_host, int
       if ((row[x >> 5] >> (x & 31)) & 1u) return fail(env, RD_ERR_INVALID, "map %d: padding bits set", map_id);
   }
   HostMap& m = env->maps[map_id];
-  cudaFree(m.d_bits); cudaFree(m.d_dist); cudaFree(m.d_start); cudaFree(m.d_reset);
+  cudaFree(m.d_bits); cudaFree(m.d_dist); cudaFree(m.d_start); cudaFree(m.d_reset); cudaFree(m.d_next);
   m = HostMap{};
   const size_t bits_bytes = (size_t)h * row_words * 4;
   const size_t bits_padded = (bits_bytes + 15) & ~(size_t)15;
@@ -487,6 +546,35 @@ RD_API int rd_upload_map(rd_env* env, int map_id, const uint32_t* bits_host, int
   d.n_start = n_start; d.n_reset = n_reset; d.bits_bytes = (int)packed.size();
   d.coarse_off = (int)bits_padded; d.cw = cw; d.ch = ch; d.cshift = cshift;
   d.res = resolution; d.inv_res = 1.0 / resolution; d.ox = origin_x; d.oy = origin_y;
+  if (n_reset > 0) {
+    // random_ball chain: next[i] = the reset pose with the smallest wavefront distance that is at least
+    // ceil(ball_spacing / resolution) cells of progress beyond pose i, wrapping over the finish line.  The wavefront
+    // distance is a Chebyshev path length, so consecutive cars of a world stand at least ball_spacing metres apart.
+    std::vector<int32_t> dpose(n_reset), next(n_reset);
+    std::vector<std::pair<int32_t, int32_t>> key(n_reset);
+    for (int i = 0; i < n_reset; ++i) {
+      const double u = (reset_poses_host[3 * i] - origin_x) * d.inv_res, v = (reset_poses_host[3 * i + 1] - origin_y) * d.inv_res;
+      const double fu = std::floor(u), fv = std::floor(v);
+      int32_t dv = 0;
+      if (fu > -1.0e9 && fu < 1.0e9 && fv > -1.0e9 && fv < 1.0e9) {
+        const int cx = (int)fu - col0, cy = (int)fv - row0_yup;
+        if (cx >= 0 && cx < w && cy >= 0 && cy < h) dv = (int32_t)dist_host[(size_t)cy * w + cx];
+      }
+      dpose[i] = dv;
+      key[i] = {dv, i};
+    }
+    std::sort(key.begin(), key.end());
+    const int32_t sc = (int32_t)std::ceil(env->cfg.ball_spacing / resolution);
+    auto first_at_least = [&](int32_t dv) { return (int)(std::lower_bound(key.begin(), key.end(), std::make_pair(dv, (int32_t)INT32_MIN)) - key.begin()); };
+    for (int i = 0; i < n_reset; ++i) {
+      int j = first_at_least(dpose[i] + sc);
+      if (j == n_reset) j = first_at_least(dpose[i] + sc - dmax);
+      next[i] = j < n_reset ? key[j].second : i;
+    }
+    CUDA_TRY(env, cudaMalloc(&m.d_next, sizeof(int32_t) * (size_t)n_reset));
+    CUDA_TRY(env, cudaMemcpy(m.d_next, next.data(), sizeof(int32_t) * (size_t)n_reset, cudaMemcpyHostToDevice));
+    d.ball_next = (const int32_t*)m.d_next;
+  }
   m.present = true;
   env->maps_dirty = true;
   return RD_OK;
@@ -501,6 +589,8 @@ RD_API int rd_assign_maps(rd_env* env, const int32_t* ids) {
   for (int e = 0; e < n; ++e) {
     if (id[e] < 0 || id[e] >= RD_MAX_MAPS || !env->maps[id[e]].present) return fail(env, RD_ERR_INVALID, "env %d: map id %d not uploaded", e, id[e]);
     count[id[e]]++;
+    const int A = env->cfg.agents_per_world;
+    if (A > 1 && id[e] != id[e - e % A]) return fail(env, RD_ERR_INVALID, "env %d: the cars of one world must share a map", e);
   }
   env->order_offset[0] = 0;
   for (int m = 0; m < RD_MAX_MAPS; ++m) env->order_offset[m + 1] = env->order_offset[m] + count[m];
@@ -519,7 +609,7 @@ RD_API int rd_assign_maps(rd_env* env, const int32_t* ids) {
 RD_API int rd_reset(rd_env* env, const uint8_t* mask_dev, int mode, const rd_outputs* out, void* stream) {
   if (!env) return fail(nullptr, RD_ERR_INVALID, "null handle");
   if (!env->assigned) return fail(env, RD_ERR_STATE, "rd_assign_maps has not been called");
-  if (mode < RD_RESET_GRID || mode > RD_RESET_RANDOM_BIDIRECTIONAL) return fail(env, RD_ERR_INVALID, "bad reset mode %d", mode);
+  if (mode < RD_RESET_GRID || mode > RD_RESET_RANDOM_BALL) return fail(env, RD_ERR_INVALID, "bad reset mode %d", mode);
   int rc = sync_maps(env);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
@@ -538,13 +628,8 @@ RD_API int rd_step(rd_env* env, const float* actions_dev, const rd_outputs* out,
   if (!env->assigned) return fail(env, RD_ERR_STATE, "rd_assign_maps has not been called");
   if (!env->was_reset) return fail(env, RD_ERR_STATE, "Must reset environment.");  // [REF dreamer/wrappers.py:148]
   cudaStream_t s = (cudaStream_t)stream;
-  {
-    ScopedTiming tm(env, s, T_STEP);
-    const int tb = env->step_block;
-    k_step<<<(env->n + tb - 1) / tb, tb, 0, s>>>(step_params(env), out_ptrs(out), actions_dev, 0, env->n);
-  }
-  env->launches++;
-  CUDA_TRY(env, cudaGetLastError());
+  int rc = launch_step(env, out, actions_dev, s);
+  if (rc) return rc;
   return observe(env, out, s);
 }
 
@@ -576,6 +661,7 @@ RD_API int rd_host_init(rd_env* env, int n_chunks, rd_outputs* host_out) {
   const size_t o_pose = take(sizeof(float) * 6 * n), o_vel = take(sizeof(float) * 6 * n), o_speed = take(sizeof(float) * n);
   const size_t o_rew = take(sizeof(float) * n), o_prog = take(sizeof(float) * n), o_time = take(sizeof(float) * n);
   const size_t o_lap = take(sizeof(int32_t) * n), o_done = take((size_t)n), o_flags = take((size_t)n);
+  const size_t o_rank = take(sizeof(int32_t) * n), o_opp = take((size_t)n);
   h.small_bytes = off;
   const size_t lidar_bytes = sizeof(float) * (size_t)n * env->cfg.n_beams;
   const bool occ = (env->cfg.obs_flags & RD_OBS_OCCUPANCY) != 0;
@@ -617,6 +703,7 @@ RD_API int rd_host_init(rd_env* env, int n_chunks, rd_outputs* host_out) {
     o.pose_dev = (float*)(base + o_pose); o.velocity_dev = (float*)(base + o_vel); o.speed_dev = (float*)(base + o_speed);
     o.reward_dev = (float*)(base + o_rew); o.progress_dev = (float*)(base + o_prog); o.time_dev = (float*)(base + o_time);
     o.lap_dev = (int32_t*)(base + o_lap); o.done_dev = (uint8_t*)(base + o_done); o.flags_dev = (uint8_t*)(base + o_flags);
+    o.rank_dev = (int32_t*)(base + o_rank); o.opponents_dev = (uint8_t*)(base + o_opp);
   };
   fill(h.dev_out, h.small_dev, h.lidar_dev, h.occ_dev);
   fill(h.host_out, h.small_host, h.lidar_host, h.occ_host);
@@ -685,13 +772,7 @@ RD_API int rd_step_host(rd_env* env, const float* actions_host) {
   // over the whole batch; the observation kernels then go chunk by chunk so that chunk k's device->host copy
   // overlaps chunk k+1's ray casting.  The small result slab is copied right behind k_step.
   cudaStream_t s0 = h.streams[0];
-  {
-    ScopedTiming tm(env, s0, T_STEP);
-    const int tb = env->step_block;
-    k_step<<<(n + tb - 1) / tb, tb, 0, s0>>>(step_params(env), out_ptrs(&h.dev_out), h.act_dev, 0, n);
-  }
-  env->launches++;
-  CUDA_TRY(env, cudaGetLastError());
+  if (int rc = launch_step(env, &h.dev_out, h.act_dev, s0)) return rc;
   CUDA_TRY(env, cudaEventRecord(h.ev_act, s0));   // marks "state advanced"
   bool small_copied = false;
   for (int c = 0; c < h.n_chunks; ++c) {
@@ -969,6 +1050,10 @@ RD_API int rd_set_state(rd_env* env, const double* f64_dev, const int32_t* i32_d
   if (i32_dev) {
     // everything but the map row: map assignment is owned by rd_assign_maps (the env grouping depends on it)
     CUDA_TRY(env, cudaMemcpyAsync(env->d_i32, i32_dev, sizeof(int32_t) * (size_t)RD_I_MAP * n, cudaMemcpyDeviceToDevice, s));
+  }
+  if (env->d_hist) {  // the n-step ring is not part of the state layout: restart it from the restored lap + progress
+    for (int k = 0; k < env->cfg.n_step_progress; ++k)
+      CUDA_TRY(env, cudaMemcpyAsync(env->d_hist + (size_t)k * n, env->d_f64 + (size_t)RD_S_LAST * n, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
   }
   env->was_reset = true;
   return RD_OK;

@@ -28,6 +28,42 @@ __device__ __forceinline__ float rd_finish_range(const LidarParams& lp, float r,
   return r;
 }
 
+// Range (metres) at which the beam (DX, DY) * 2^-18 from (px, py) enters the body box of another car of the world, or
+// +inf.  float32 slab test in the other car's sensor frame; every operand is an exactly representable integer (or a
+// per-launch constant) and every operation a single IEEE operation in a fixed order, so the CPU oracle's float32
+// restatement produces the same bits.  [NEW-SPEC: racecar_gym's rayTestBatch hits the other racecars' collision
+// shapes; SURVEY.md §8-f3 "rays hitting cars"]
+__device__ __forceinline__ float rd_car_hit(const LidarParams& lp, int px, int py, int DX, int DY, const OriginRec& q) {
+  const float inf = __int_as_float(0x7f800000);
+  const int rx = px - q.px, ry = py - q.py;
+  const int arx = rx < 0 ? -rx : rx, ary = ry < 0 ? -ry : ry;
+  if (!(q.valid & 2) || arx > lp.car_reach || ary > lp.car_reach) return inf;
+  const float ox = __fmul_rn((float)rx, 1.0f / (float)RD_SUB), oy = __fmul_rn((float)ry, 1.0f / (float)RD_SUB);
+  const float c = (float)q.c, s = (float)q.s;
+  const float dxf = __fmul_rn((float)DX, 1.0f / (float)(1 << RD_DIR_BITS));
+  const float dyf = __fmul_rn((float)DY, 1.0f / (float)(1 << RD_DIR_BITS));
+  const float u0 = __fadd_rn(__fmul_rn(ox, c), __fmul_rn(oy, s));
+  const float v0 = __fsub_rn(__fmul_rn(oy, c), __fmul_rn(ox, s));
+  const float du = __fadd_rn(__fmul_rn(dxf, c), __fmul_rn(dyf, s));
+  const float dv = __fsub_rn(__fmul_rn(dyf, c), __fmul_rn(dxf, s));
+  float tmin = 0.0f, tmax = inf;
+  if (du != 0.0f) {
+    const float t1 = __fdiv_rn(__fsub_rn(lp.car_ulo, u0), du), t2 = __fdiv_rn(__fsub_rn(lp.car_uhi, u0), du);
+    tmin = fmaxf(tmin, fminf(t1, t2));
+    tmax = fminf(tmax, fmaxf(t1, t2));
+  } else if (u0 < lp.car_ulo || u0 > lp.car_uhi) {
+    return inf;
+  }
+  if (dv != 0.0f) {
+    const float t1 = __fdiv_rn(__fsub_rn(-lp.car_hw, v0), dv), t2 = __fdiv_rn(__fsub_rn(lp.car_hw, v0), dv);
+    tmin = fmaxf(tmin, fminf(t1, t2));
+    tmax = fminf(tmax, fmaxf(t1, t2));
+  } else if (v0 < -lp.car_hw || v0 > lp.car_hw) {
+    return inf;
+  }
+  return tmin <= tmax ? __fmul_rn(tmin, lp.res) : inf;
+}
+
 // smem layout: [0,16) mbarrier | beam table 2*n_beams f64 (cos then sin) | bit grid | block clearance field
 // The tail of the item list is handed out through a global counter (ctr[0]); the last CTA to finish (ticket ctr[1])
 // re-arms both for the next launch on the stream.
@@ -91,7 +127,7 @@ k_lidar(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict
       const int beam = g * 32 + lane;
       if (rec.was_reset != 2 && beam < lp.n_beams) {  // was_reset == 2: frozen env, outputs stay as they are
         float r;
-        if (!rec.valid) {
+        if (!(rec.valid & 1)) {
           r = 0.0f;
         } else {
           const double ca = tab[beam], sa = tab[lp.n_beams + beam];
@@ -101,6 +137,13 @@ k_lidar(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict
           const int DY = __double2int_rn(dy * (double)(1 << RD_DIR_BITS));
           const MarchResult mr = rd_march(grid, rec.px, rec.py, DX, DY, (long long)lp.rsub, nullptr);
           r = mr.hit ? __fmul_rn(__fdiv_rn((float)mr.num, (float)mr.den), lp.scale) : lp.range_max;
+          if (lp.agents > 1) {  // the other cars of this world (their records sit next to this one)
+            const int base = env - env % lp.agents;
+            for (int j = 0; j < lp.agents; ++j) {
+              if (base + j == env) continue;
+              r = fminf(r, rd_car_hit(lp, rec.px, rec.py, DX, DY, recs[base + j]));
+            }
+          }
         }
         out[(size_t)env * lp.n_beams + beam] = rd_finish_range(lp, r, rec, (uint32_t)beam);
       }
@@ -126,15 +169,17 @@ __device__ __forceinline__ void rd_make_origin(const DevMap& m, double x, double
   const double pu = floor(u * (double)RD_SUB), pv = floor(v * (double)RD_SUB);
   bool ok = (pu > -1.0e12 && pu < 1.0e12 && pv > -1.0e12 && pv < 1.0e12);
   long long PX = 0, PY = 0;
+  bool pos = false;   // px/py representable (other cars of the world need them even when the sensor left the track)
   if (ok) {
     PX = (long long)pu - (long long)m.col0 * RD_SUB;
     PY = (long long)pv - (long long)m.row0 * RD_SUB;
+    pos = PX > -(1ll << 30) && PX < (1ll << 30) && PY > -(1ll << 30) && PY < (1ll << 30);
     ok = PX >= 0 && PY >= 0 && (PX >> RD_SUB_BITS) < m.w && (PY >> RD_SUB_BITS) < m.h;
   }
   if (ok) ok = rd_drivable_at(m, (int)(PX >> RD_SUB_BITS), (int)(PY >> RD_SUB_BITS)) != 0;
-  rec.px = ok ? (int32_t)PX : 0;
-  rec.py = ok ? (int32_t)PY : 0;
-  rec.valid = ok ? 1 : 0;
+  rec.px = pos ? (int32_t)PX : 0;
+  rec.py = pos ? (int32_t)PY : 0;
+  rec.valid = (ok ? 1 : 0) | (pos ? 2 : 0);   // bit0: origin inside a drivable cell; bit1: px/py hold the position
   rec.c = c;
   rec.s = s;
 }

@@ -53,6 +53,12 @@ class EnvConfig:
     seed: int = 0
     env_id_offset: int = 0
     map_ids: Optional[Sequence[int]] = None     # per-env index into `tracks`; default: env i -> track i % len
+    # multi-agent worlds [REF baselines/scenarios/max_progress/austria.yml:3-34; dreamer/dream.py:105-106]:
+    # env e = agent (e % agents_per_world) of world (e // agents_per_world); n_envs counts CARS
+    agents_per_world: int = 1
+    agent_tasks: Optional[Sequence[str]] = None  # task of agent A, B, ...; default: `task` for every agent
+    n_step_progress: int = 10                   # [REF baselines/scenarios/max_progress/austria.yml:18]
+    ball_spacing: float = 1.5                   # metres of track between the cars of a world after a random reset
 
 
 def _fill_config(cfg: _abi.RdConfig, ec: EnvConfig) -> None:
@@ -88,6 +94,19 @@ def _fill_config(cfg: _abi.RdConfig, ec: EnvConfig) -> None:
         cfg.action_low[k] = float(ec.action_low[k])
         cfg.action_high[k] = float(ec.action_high[k])
     cfg.lidar_noise = float(ec.lidar_noise)
+    A = int(ec.agents_per_world)
+    if not 1 <= A <= _abi.MAX_AGENTS:
+        raise ValueError(f"agents_per_world {A}: expected 1..{_abi.MAX_AGENTS}")
+    tasks = list(ec.agent_tasks) if ec.agent_tasks is not None else [ec.task] * A
+    if len(tasks) != A:
+        raise ValueError("agent_tasks must name one task per agent of a world")
+    cfg.agents_per_world = A
+    for a in range(_abi.MAX_AGENTS):
+        cfg.agent_task[a] = _abi.TASKS[tasks[a]] if a < A else _abi.TASK_MAX_PROGRESS
+    if A == 1:
+        cfg.task = _abi.TASKS[tasks[0]]
+    cfg.n_step_progress = int(ec.n_step_progress)
+    cfg.ball_spacing = float(ec.ball_spacing)
 
 
 class BatchedRaceEnv:
@@ -133,8 +152,9 @@ class BatchedRaceEnv:
                     start.ctypes.data, start.shape[0], rst.ctypes.data, rst.shape[0]))
             if ec.map_ids is not None:
                 ids = np.ascontiguousarray(ec.map_ids, dtype=np.int32)
-            else:
-                ids = (np.arange(self.n, dtype=np.int32) % len(self.tracks)).astype(np.int32)
+            else:  # worlds (not cars) alternate over the tracks
+                A = max(1, int(cfg.agents_per_world))
+                ids = ((np.arange(self.n, dtype=np.int32) // A) % len(self.tracks)).astype(np.int32)
             if ids.shape != (self.n,):
                 raise ValueError("map_ids must have one entry per env")
             self.map_ids = ids
@@ -146,7 +166,7 @@ class BatchedRaceEnv:
         ("lidar", None, torch.float32), ("occupancy", (64, 64, 1), torch.uint8), ("pose", (6,), torch.float32),
         ("velocity", (6,), torch.float32), ("speed", (), torch.float32), ("reward", (), torch.float32),
         ("done", (), torch.uint8), ("progress", (), torch.float32), ("lap", (), torch.int32), ("time", (), torch.float32),
-        ("flags", (), torch.uint8))
+        ("flags", (), torch.uint8), ("rank", (), torch.int32), ("opponents", (), torch.uint8))
 
     def _alloc(self):
         n, dev = self.n, self.device
@@ -168,7 +188,7 @@ class BatchedRaceEnv:
         for k, f in (("lidar", "lidar_dev"), ("occupancy", "occupancy_dev"), ("pose", "pose_dev"),
                      ("velocity", "velocity_dev"), ("speed", "speed_dev"), ("reward", "reward_dev"),
                      ("done", "done_dev"), ("progress", "progress_dev"), ("lap", "lap_dev"), ("time", "time_dev"),
-                     ("flags", "flags_dev")):
+                     ("flags", "flags_dev"), ("rank", "rank_dev"), ("opponents", "opponents_dev")):
             t = self.buf[k]
             setattr(o, f, t.data_ptr() if t is not None else None)
         self._out = o
@@ -195,7 +215,10 @@ class BatchedRaceEnv:
         fl = self.buf["flags"]
         return {"progress": self.buf["progress"], "lap": self.buf["lap"], "time": self.buf["time"],
                 "wrong_way": (fl & _abi.F_WRONG_WAY) != 0, "wall_collision": (fl & _abi.F_COLLISION) != 0,
-                "flags": fl, "pose": self.buf["pose"], "velocity": self.buf["velocity"]}
+                "flags": fl, "pose": self.buf["pose"], "velocity": self.buf["velocity"],
+                # multi-agent worlds: position in the world (1 = leader) and a bit mask over the world's agent
+                # indices the car is in contact with (racecar_gym: info['rank'], info['opponent_collisions'])
+                "rank": self.buf["rank"], "opponent_collisions": self.buf["opponents"]}
 
     def reset(self, mask: Optional[torch.Tensor] = None, mode: Optional[str] = None) -> Dict[str, torch.Tensor]:
         m = _abi.RESET_MODES[mode] if mode is not None else int(self.cfg.reset_mode)

@@ -19,11 +19,13 @@ import torch
 from . import _abi
 from .env import BatchedRaceEnv, EnvConfig
 
-_OUT_KEYS = ("lidar", "occupancy", "pose", "velocity", "speed", "reward", "done", "progress", "lap", "time", "flags")
+_OUT_KEYS = ("lidar", "occupancy", "pose", "velocity", "speed", "reward", "done", "progress", "lap", "time", "flags",
+             "rank", "opponents")
 _FIELDS = {"lidar": ("lidar_dev", np.float32), "occupancy": ("occupancy_dev", np.uint8), "pose": ("pose_dev", np.float32),
            "velocity": ("velocity_dev", np.float32), "speed": ("speed_dev", np.float32), "reward": ("reward_dev", np.float32),
            "done": ("done_dev", np.uint8), "progress": ("progress_dev", np.float32), "lap": ("lap_dev", np.int32),
-           "time": ("time_dev", np.float32), "flags": ("flags_dev", np.uint8)}
+           "time": ("time_dev", np.float32), "flags": ("flags_dev", np.uint8),
+           "rank": ("rank_dev", np.int32), "opponents": ("opponents_dev", np.uint8)}
 
 
 class HostSteppedEnv:
