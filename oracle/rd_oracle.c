@@ -739,7 +739,7 @@ static int rect_overlap(double hl, double hw, double dx, double dy, double c1, d
  * [REF dreamer/tools.py:178-179]; statistics follow the first agent [REF dreamer/tools.py:162-165].  Tasks per car:
  * cfg->agent_task[a] (A > 1) or cfg->task; n_step_progress rewards progress over the last n ticks [NEW-SPEC]. */
 static void step_world(const rd_config* cfg, const orc_map* maps, orc_view* s, int w, const float* actions,
-                       const orc_outputs* o, rd_stats* st, int* was_reset) {
+                       const double* commands, const orc_outputs* o, rd_stats* st, int* was_reset) {
   const int A = cfg->agents_per_world > 1 ? cfg->agents_per_world : 1;
   const int e0 = w * A, n = s->n;
   const orc_map* m = &maps[s->i[RD_I_MAP][e0]];
@@ -764,6 +764,7 @@ static void step_world(const rd_config* cfg, const orc_map* maps, orc_view* s, i
   for (int a = 0; a < A; ++a) {
     const int e = e0 + a;
     for (int k = 0; k < 2; ++k) {
+      if (commands) { act[a][k] = commands[2 * e + k]; continue; } /* sim-facing float64: racecar_gym's own step() */
       float af = actions[2 * e + k];
       if (cfg->clip_actions) af = af < -1.0f ? -1.0f : (af > 1.0f ? 1.0f : af);
       if (cfg->rescale_actions) {
@@ -919,7 +920,7 @@ ORC_API void orc_step(const rd_config* cfg, const orc_map* maps, double* f64, in
       for (int w = 0; w < n / A; ++w) {
         int was_reset = 0;
         int frozen = (s.i[RD_I_FLAGS][w * A] & RD_F_NEEDS_RESET) != 0;
-        step_world(cfg, maps, &s, w, actions, out, &loc, &was_reset);
+        step_world(cfg, maps, &s, w, actions, commands, out, &loc, &was_reset);
         for (int e = w * A; e < w * A + A; ++e) mark[e] = (uint8_t)((frozen ? 1 : 0) | (was_reset ? 2 : 0));
       }
 #pragma omp for schedule(dynamic, 8)

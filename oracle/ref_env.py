@@ -34,13 +34,19 @@ class GridMapShim:
         return self._tm.to_pixel(float(pose[0]), float(pose[1]))
 
 
+AGENT_IDS = ("A", "B", "C", "D")
+
+
 class OracleRaceEnv:
+    """n_agents = 1: the single-car world of the dreamer scenarios; n_agents > 1: one world of cars 'A', 'B', ... that
+    see and hit each other [REF baselines/scenarios/max_progress/austria.yml:3-34], `tasks` = task name per agent."""
+
     def __init__(self, tm: TrackMap, laps=10, time_limit=180.0, terminate_on_collision=True, collision_reward=-1.0,
-                 reset_mode="grid", seed=0):
+                 reset_mode="grid", seed=0, n_agents=1, tasks=None, n_step_progress=10, ball_spacing=1.5):
         ref_stubs.install()
         import gym
         cfg = default_config()
-        cfg.n_envs = 1
+        cfg.n_envs = n_agents
         cfg.action_repeat = 1          # one sim tick per step; the reference's ActionRepeat wrapper loops
         cfg.rescale_actions = 0        # the reference's ReduceActionSpace wrapper rescales
         cfg.auto_reset = 0
@@ -49,54 +55,69 @@ class OracleRaceEnv:
         cfg.terminate_on_collision = int(terminate_on_collision)
         cfg.collision_reward = collision_reward
         cfg.seed = seed
+        cfg.agents_per_world = n_agents
+        tasks = list(tasks) if tasks is not None else ["maximize_progress"] * n_agents
+        for a in range(n_agents):
+            cfg.agent_task[a] = _abi.TASKS[tasks[a]]
+        if n_agents == 1:
+            cfg.task = _abi.TASKS[tasks[0]]
+        cfg.n_step_progress = n_step_progress
+        cfg.ball_spacing = ball_spacing
         self.cfg = cfg
         self.tm = tm
+        self.ids = list(AGENT_IDS[:n_agents])
         self._orc = Oracle(cfg, [tm])
         self._mode = _abi.RESET_MODES[reset_mode]
         self.scenario = types.SimpleNamespace(world=types.SimpleNamespace(
             _maps={"occupancy": GridMapShim(tm)}, _config=types.SimpleNamespace(name=tm.name)))
         box = gym.spaces.Box
-        self.observation_space = gym.spaces.Dict({"A": gym.spaces.Dict({
+        self.observation_space = gym.spaces.Dict({i: gym.spaces.Dict({
             "lidar": box(0.0, 15.0, shape=(1080,), dtype=np.float64),
             "pose": box(-100.0, 100.0, shape=(6,), dtype=np.float64),
-            "velocity": box(-10.0, 10.0, shape=(6,), dtype=np.float64)})})
-        self.action_space = gym.spaces.Dict({"A": gym.spaces.Dict({
+            "velocity": box(-10.0, 10.0, shape=(6,), dtype=np.float64)}) for i in self.ids})
+        self.action_space = gym.spaces.Dict({i: gym.spaces.Dict({
             "motor": box(-1.0, 1.0, shape=(1,), dtype=np.float64),
-            "steering": box(-1.0, 1.0, shape=(1,), dtype=np.float64)})})
+            "steering": box(-1.0, 1.0, shape=(1,), dtype=np.float64)}) for i in self.ids})
 
     # -- racecar_gym API --
     def _obs(self, out):
-        return {"A": {"lidar": out["lidar"][0].astype(np.float64), "pose": self._pose(), "velocity": self._velocity()}}
+        return {i: {"lidar": out["lidar"][k].astype(np.float64), "pose": self._pose(k), "velocity": self._velocity(k)}
+                for k, i in enumerate(self.ids)}
 
-    def _pose(self):
+    def _pose(self, k=0):
         f = self._orc.f64
-        yaw = f[_abi.S_YAW, 0]
+        yaw = f[_abi.S_YAW, k]
         two_pi = 6.283185307179586
-        return np.array([f[_abi.S_X, 0], f[_abi.S_Y, 0], 0.0, 0.0, 0.0, yaw - np.rint(yaw / two_pi) * two_pi])
+        return np.array([f[_abi.S_X, k], f[_abi.S_Y, k], 0.0, 0.0, 0.0, yaw - np.rint(yaw / two_pi) * two_pi])
 
-    def _velocity(self):
+    def _velocity(self, k=0):
         f = self._orc.f64
-        v, b = f[_abi.S_V, 0], f[_abi.S_SLIP, 0]
-        return np.array([v * np.cos(b), v * np.sin(b), 0.0, 0.0, 0.0, f[_abi.S_YAWRATE, 0]])
+        v, b = f[_abi.S_V, k], f[_abi.S_SLIP, k]
+        return np.array([v * np.cos(b), v * np.sin(b), 0.0, 0.0, 0.0, f[_abi.S_YAWRATE, k]])
 
     def _info(self, out):
-        fl = int(out["flags"][0])
-        return {"A": {"pose": self._pose(), "velocity": self._velocity(),
-                      "progress": float(self._orc.f64[_abi.S_PROGRESS, 0]), "lap": int(out["lap"][0]),
-                      "time": float(self._orc.f64[_abi.S_TIME, 0]), "wrong_way": bool(fl & _abi.F_WRONG_WAY),
-                      "wall_collision": bool(fl & _abi.F_COLLISION)}}
+        info = {}
+        for k, i in enumerate(self.ids):
+            fl = int(out["flags"][k])
+            info[i] = {"pose": self._pose(k), "velocity": self._velocity(k),
+                       "progress": float(self._orc.f64[_abi.S_PROGRESS, k]), "lap": int(out["lap"][k]),
+                       "time": float(self._orc.f64[_abi.S_TIME, k]), "wrong_way": bool(fl & _abi.F_WRONG_WAY),
+                       "wall_collision": bool(fl & _abi.F_COLLISION),
+                       "opponent_collisions": [self.ids[j] for j in range(len(self.ids)) if int(out["opponents"][k]) >> j & 1],
+                       "rank": int(out["rank"][k])}
+        return info
 
     def reset(self, mode="grid"):
         out = self._orc.reset(mode=_abi.RESET_MODES[mode])
         return self._obs(out)
 
     def step(self, action):
-        a = action["A"]
-        cmd = np.array([[float(np.asarray(a["motor"]).reshape(-1)[0]), float(np.asarray(a["steering"]).reshape(-1)[0])]],
-                       dtype=np.float64)
-        self._orc.i32[_abi.I_FLAGS, 0] &= ~_abi.F_NEEDS_RESET  # racecar_gym keeps stepping after done
+        cmd = np.array([[float(np.asarray(action[i]["motor"]).reshape(-1)[0]),
+                         float(np.asarray(action[i]["steering"]).reshape(-1)[0])] for i in self.ids], dtype=np.float64)
+        self._orc.i32[_abi.I_FLAGS] &= ~_abi.F_NEEDS_RESET  # racecar_gym keeps stepping after done
         out = self._orc.step(commands=cmd)
-        return self._obs(out), {"A": float(out["reward64"][0])}, {"A": bool(out["done"][0])}, self._info(out)
+        return (self._obs(out), {i: float(out["reward64"][k]) for k, i in enumerate(self.ids)},
+                {i: bool(out["done"][k]) for k, i in enumerate(self.ids)}, self._info(out))
 
     def render(self, **kwargs):
         return np.zeros((8, 8, 3), np.uint8)

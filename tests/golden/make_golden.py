@@ -21,6 +21,13 @@ committed so that the parity tests can run where /root/reference does not exist 
                            stubbed over scipy.ndimage, oracle/ref_costmap.py) run on two of the reference's maps:
                            drivable_area, norm_distance_from_start, norm_distance_to_obstacle.
 
+  multi_agent_stack_golden.npz  one world of four cars (A maximize_progress, B..D n_step_progress as in the baselines'
+                           scenario files [REF baselines/scenarios/max_progress/austria.yml]) under the UNMODIFIED
+                           dict-of-agents wrapper stack of dream.py (RaceCarWrapper -> ActionRepeat -> ReduceActionSpace
+                           -> OccupancyMapObs -> FixedResetMode('random_ball') -> TimeLimit -> Collect)
+                           [REF dreamer/dream.py:103-140; dreamer/wrappers.py:107-116,147-154,210-226], reset whenever
+                           any agent is done [REF dreamer/tools.py:178-179].
+
 usage: python tests/golden/make_golden.py [name ...]
 """
 import sys
@@ -280,6 +287,59 @@ def costmap_golden():
     np.savez_compressed(OUT / "costmap_golden.npz", **out)
 
 
+def multi_agent_stack_golden(n_steps=600, action_repeat=4, duration=18, n_agents=4):
+    """the reference wrappers' dict-of-agents semantics (ActionRepeat stops when ANY agent is done and sums
+    per agent, TimeLimit sets every done, Collect's casts) over the one-tick multi-car oracle world."""
+    tm = load_track("austria")
+    tasks = ["maximize_progress"] + ["n_step_progress"] * (n_agents - 1)
+    env = make_reference_stack(tm, action_repeat=action_repeat, time_limit_steps=duration, reset_mode="random_ball",
+                               n_agents=n_agents, tasks=tasks, seed=17, ball_spacing=0.8)
+    ids = ["A", "B", "C", "D"][:n_agents]
+    rng = np.random.RandomState(17)
+    actions = rng.uniform(-1, 1, (n_steps, n_agents, 2)).astype(np.float32)
+    # the car at the back (A) is the fastest, gentle steering: rear-end contacts as well as wall hits and time-outs
+    gain = np.array([1.0, 0.15, 0.6, 0.05][:n_agents], np.float32)
+    actions[:, :, 0] = ((np.abs(actions[:, :, 0]) * 0.5 + 0.5) * gain) * 2 - 1
+    actions[:, :, 1] *= 0.3
+    keys = ("reward", "done", "progress", "lap", "time", "speed", "pose", "velocity", "lidar_sum", "occ_popcount",
+            "wrong_way", "collision", "opponents", "rank")
+    rec = {k: [] for k in keys}
+    reset_before, lidar_full, occ_full = [], [], []
+    need_reset = True
+    for t in range(n_steps):
+        reset_before.append(need_reset)
+        if need_reset:
+            obs = env.reset()
+            assert all(obs[i]["speed"] == 0.0 and not obs[i]["lidar_occupancy"].any() for i in ids)
+        obs, rew, done, info = env.step({i: actions[t, k] for k, i in enumerate(ids)})
+        row = {k: [] for k in keys}
+        for k, i in enumerate(ids):
+            o, f = obs[i], info[i]
+            row["reward"].append(rew[i]); row["done"].append(done[i]); row["progress"].append(f["progress"])
+            row["lap"].append(f["lap"]); row["time"].append(f["time"]); row["wrong_way"].append(f["wrong_way"])
+            row["collision"].append(f["wall_collision"]); row["rank"].append(f["rank"])
+            row["opponents"].append(sum(1 << ids.index(j) for j in f["opponent_collisions"]))
+            row["speed"].append(o["speed"]); row["pose"].append(o["pose"]); row["velocity"].append(o["velocity"])
+            row["lidar_sum"].append(np.sum(o["lidar"], dtype=np.float64))
+            row["occ_popcount"].append(int(o["lidar_occupancy"].sum()))
+        for k in keys:
+            rec[k].append(row[k])
+        if t % 20 == 0:
+            lidar_full.append([obs[i]["lidar"] for i in ids])
+            occ_full.append([np.packbits(obs[i]["lidar_occupancy"][..., 0], axis=1) for i in ids])
+        need_reset = any(done.values())          # [REF dreamer/tools.py:178]
+    out = {k: np.asarray(v) for k, v in rec.items()}
+    assert out["speed"].dtype == np.float32 and out["pose"].dtype == np.float32
+    np.savez_compressed(OUT / "multi_agent_stack_golden.npz", actions=actions, action_repeat=action_repeat,
+                        duration=duration, n_agents=n_agents, tasks=np.array(tasks), seed=17, ball_spacing=0.8,
+                        reset_before=np.asarray(reset_before), lidar_every20=np.asarray(lidar_full),
+                        occ_every20=np.asarray(occ_full), reward=out["reward"].astype(np.float64),
+                        **{k: v for k, v in out.items() if k != "reward"})
+    print("multi_agent_stack_golden: world episodes", int(out["done"].any(1).sum()), "car contacts",
+          int((out["opponents"] != 0).sum()), "wall hits", int(out["collision"].sum()),
+          "time-outs", int(out["done"].all(1).sum()))
+
+
 if __name__ == "__main__":
     assert ref_stubs.available(), "/root/reference is required to regenerate the golden fixtures"
     todo = sys.argv[1:]
@@ -291,3 +351,4 @@ if __name__ == "__main__":
     dreamer_stack_golden()
     baselines_stack_golden()
     episodes_golden()
+    multi_agent_stack_golden()

@@ -129,3 +129,69 @@ def assert_episodes_match_golden(episodes, g, tol=1e-6, lidar_tol=1e-3):
             t = lidar_tol if k == "lidar" else tol
             d = np.abs(got.astype(np.float64) - want.astype(np.float64))
             assert np.all(d <= t * np.maximum(1.0, np.abs(want))), f"episode {i} {k}: max diff {d.max()}"
+
+
+# ---------------------------------------------------------------------------------------------- multi-agent worlds
+def fused_world_config(cfg, g, occupancy=True):
+    """rd_config equivalent of the reference's dict-of-agents stack recorded in multi_agent_stack_golden.npz: ONE world of
+    n_agents cars, manual reset whenever any car is done [REF dreamer/tools.py:178-179]."""
+    A = int(g["n_agents"])
+    cfg.n_envs = A
+    cfg.agents_per_world = A
+    for a, name in enumerate(g["tasks"]):
+        cfg.agent_task[a] = _abi.TASKS[str(name)]
+    cfg.action_repeat = int(g["action_repeat"])
+    cfg.repeat_semantics = _abi.REPEAT_DREAMER
+    cfg.rescale_actions = 1
+    cfg.clip_actions = 0
+    cfg.time_limit_steps = int(g["duration"])
+    cfg.auto_reset = 0
+    cfg.reset_mode = _abi.RESET_RANDOM_BALL
+    cfg.seed = int(g["seed"])
+    cfg.ball_spacing = float(g["ball_spacing"])
+    cfg.obs_flags = _abi.OBS_LIDAR | (_abi.OBS_OCCUPANCY if occupancy else 0)
+    return cfg
+
+
+def replay_world(reset_fn, step_fn, actions, reset_before):
+    """step_fn(a[A,2] f32) -> dict of numpy arrays with leading dim A.  Returns dict of [T, A, ...] records."""
+    rec = {}
+    for t in range(actions.shape[0]):
+        if reset_before[t]:
+            reset_fn()
+        out = step_fn(actions[t])
+        for k, v in out.items():
+            if v is not None:
+                rec.setdefault(k, []).append(np.array(v))
+    return {k: np.stack(v) for k, v in rec.items()}
+
+
+def assert_matches_multi_agent_golden(rec, g, lidar_tol=0.0, float_tol=0.0):
+    def close(a, b, tol, what):
+        a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+        if tol == 0.0:
+            assert np.array_equal(a, b), f"{what}: max |diff| {np.abs(a - b).max()}"
+        else:
+            assert np.all(np.abs(a - b) <= tol * np.maximum(1.0, np.abs(b))), f"{what}: max |diff| {np.abs(a - b).max()}"
+    T, A = g["done"].shape
+    assert np.array_equal(rec["done"].astype(bool), g["done"])
+    assert np.array_equal(rec["lap"], g["lap"])
+    assert np.array_equal(rec["rank"], g["rank"])
+    assert np.array_equal(rec["opponents"], g["opponents"])
+    fl = rec["flags"]
+    assert np.array_equal((fl & _abi.F_COLLISION) != 0, g["collision"])
+    assert np.array_equal((fl & _abi.F_WRONG_WAY) != 0, g["wrong_way"])
+    assert np.array_equal((fl & _abi.F_OPPONENT) != 0, g["opponents"] != 0)
+    occ = rec["occupancy"].reshape(T, A, 64, 64)
+    assert np.array_equal(occ.reshape(T, A, -1).sum(2), g["occ_popcount"])
+    assert np.array_equal(np.packbits(occ[::20], axis=3), g["occ_every20"])
+    close(rec["reward"], g["reward"].astype(np.float32), float_tol, "reward")
+    close(rec["progress"], g["progress"].astype(np.float32), float_tol, "progress")
+    close(rec["time"], g["time"].astype(np.float32), float_tol, "time")
+    for k in ("speed", "pose", "velocity"):
+        close(rec[k], g[k], float_tol, k)
+    if lidar_tol == 0.0:
+        assert np.array_equal(rec["lidar"][::20], g["lidar_every20"])
+    else:
+        assert np.abs(rec["lidar"][::20] - g["lidar_every20"]).max() <= lidar_tol
+    assert np.abs(rec["lidar"].sum(2, dtype=np.float64) - g["lidar_sum"]).max() <= max(lidar_tol * 1080, 0.0)

@@ -175,3 +175,17 @@ def test_single_agent_path_is_untouched_by_the_world_fields():
             rec.append(np.concatenate([o["lidar"].ravel(), o["reward"], o["done"], o["progress"]]))
         outs.append(np.stack(rec))
     assert np.array_equal(outs[0], outs[1])
+
+
+def test_fused_world_matches_the_reference_wrapper_stack(golden_dir):
+    """The fused per-world step == the UNMODIFIED dict-of-agents wrappers of the reference (RaceCarWrapper, ActionRepeat
+    `not any(dones.values())`, ReduceActionSpace, OccupancyMapObs, TimeLimit, Collect [REF dreamer/wrappers.py:55-250])
+    run tick by tick over the one-tick multi-car world (tests/golden/make_golden.py::multi_agent_stack_golden)."""
+    import helpers
+    g = np.load(golden_dir / "multi_agent_stack_golden.npz")
+    cfg = helpers.fused_world_config(default_config(), g)
+    orc = Oracle(cfg, [load_track("austria")])
+    rec = helpers.replay_world(lambda: orc.reset(mode=_abi.RESET_RANDOM_BALL), lambda a: orc.step(a), g["actions"],
+                               g["reset_before"])
+    helpers.assert_matches_multi_agent_golden(rec, g)
+    assert (g["opponents"] != 0).sum() > 20 and g["done"].all(1).sum() >= 3   # contacts and time-outs are in the fixture

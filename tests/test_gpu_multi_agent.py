@@ -204,3 +204,26 @@ def test_bad_world_configs_are_rejected(torch_cuda):
         make_env(tracks=("austria", "barcelona"), n_envs=8, agents_per_world=2, map_ids=[0, 1, 0, 0, 1, 1, 0, 0])
     with pytest.raises(RuntimeError, match="n_step_progress"):
         make_env(tracks=("austria",), n_envs=8, task="n_step_progress", n_step_progress=1000)
+
+
+def test_world_golden_replay_of_the_reference_wrapper_stack(torch_cuda, golden_dir):
+    """One world of four cars through the CUDA path == the UNMODIFIED dict-of-agents wrapper stack of the reference run
+    over the one-tick oracle world, step for step (tests/golden/multi_agent_stack_golden.npz)."""
+    torch = torch_cuda
+    import helpers
+    from racing_dreamer_b200 import BatchedRaceEnv
+    g = np.load(golden_dir / "multi_agent_stack_golden.npz")
+    cfg = helpers.fused_world_config(_abi.default_config(), g)
+    env = BatchedRaceEnv(tracks=("austria",), raw_config=cfg, device="cuda:0")
+
+    def step(a):
+        obs, rew, done, info = env.step(torch.from_numpy(np.ascontiguousarray(a)).cuda())
+        out = {"lidar": obs["lidar"], "pose": obs["pose"], "velocity": obs["velocity"], "speed": obs["speed"],
+               "reward": rew, "done": done.to(torch.uint8), "progress": info["progress"], "lap": info["lap"],
+               "time": info["time"], "flags": info["flags"], "rank": info["rank"],
+               "opponents": info["opponent_collisions"], "occupancy": obs["lidar_occupancy"][..., 0]}
+        return {k: v.cpu().numpy() for k, v in out.items()}
+
+    rec = helpers.replay_world(lambda: env.reset(mode="random_ball"), step, g["actions"], g["reset_before"])
+    helpers.assert_matches_multi_agent_golden(rec, g, lidar_tol=LIDAR_TOL_M, float_tol=DYN_RTOL)
+    env.close()
