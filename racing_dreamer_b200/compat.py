@@ -11,8 +11,10 @@ Two views of the same kernels:
   ``{'A': {'motor','steering'}}`` actions, ``reset(mode=...)``) [REF dreamer/wrappers.py:14-15,62-77,92], for
   callers that want to stack the reference's own unmodified wrapper classes on top.
 
-Both are single-agent (agent id ``'A'``) views of a ``BatchedRaceEnv`` with ``n_envs = 1``; results come from the
-same kernels as the batched path.  Training-scale callers should use ``BatchedRaceEnv`` directly.
+Both are views of ONE world of a ``BatchedRaceEnv``: a single car ``'A'`` (the dreamer scenarios) or up to four cars
+``'A'..'D'`` that see and hit each other (``n_agents`` / a multi-agent scenario YAML
+[REF baselines/scenarios/max_progress/austria.yml:3-34; dreamer/dream.py:105-106]); results come from the same kernels
+as the batched path.  Training-scale callers should use ``BatchedRaceEnv`` directly.
 """
 from __future__ import annotations
 
@@ -39,22 +41,36 @@ SCENARIO_DEFAULTS = {
 }
 
 
+AGENT_IDS = ("A", "B", "C", "D")
+
+
 def load_scenario(path: Union[str, Path], agent_id: str = "A") -> dict:
-    """Parse a reference scenario YAML [REF dreamer/scenarios/max_progress/austria.yml:1-10] into
-    ``{'track': world.name, 'task': ..., 'laps': ..., ...}`` (the keys ``EnvConfig`` understands)."""
+    """Parse a reference scenario YAML [REF dreamer/scenarios/max_progress/austria.yml:1-10;
+    baselines/scenarios/max_progress/austria.yml:1-34] into the keys ``EnvConfig`` understands:
+    ``{'track': world.name, 'task': ..., 'laps': ..., ...}`` from agent ``agent_id``'s task, plus, for files with several
+    agents, ``agents_per_world``, ``agent_tasks`` (one task name per agent, file order) and ``n_step_progress``."""
     import yaml
     spec = yaml.safe_load(Path(path).read_text())
     out = {"track": spec["world"]["name"]}
-    for agent in spec.get("agents", []):
+    agents = spec.get("agents", [])
+    for agent in agents:
+        task = agent.get("task", {})
+        if task.get("task_name") == "n_step_progress" and "n_steps" in (task.get("params") or {}):
+            out["n_step_progress"] = int(task["params"]["n_steps"])
         if agent.get("id") != agent_id:
             continue
-        task = agent.get("task", {})
         out["task"] = task.get("task_name", "maximize_progress")
         for k, v in (task.get("params") or {}).items():
             if k in ("laps", "time_limit", "terminate_on_collision", "collision_reward", "progress_reward",
                      "frame_reward"):
                 out[k] = v
         out["sensors"] = list(agent.get("vehicle", {}).get("sensors", []))
+    if len(agents) > 1:
+        if len(agents) > _abi.MAX_AGENTS:
+            raise ValueError(f"{path}: {len(agents)} agents, at most {_abi.MAX_AGENTS} cars per world are supported")
+        out["agents_per_world"] = len(agents)
+        out["agent_tasks"] = [a.get("task", {}).get("task_name", "maximize_progress") for a in agents]
+        out["agent_ids"] = [str(a.get("id", AGENT_IDS[i])) for i, a in enumerate(agents)]
     return out
 
 
@@ -86,48 +102,59 @@ def _scenario_of(tm: TrackMap):
 
 
 class _SingleAgentBase:
+    """One world: a single car 'A' or n_agents cars 'A', 'B', ... (the name predates the multi-car worlds)."""
     agent_id = "A"
+    _ids = ("A",)
 
-    def _make(self, track, n_envs=1, **cfg_kw):
+    def _make(self, track, n_agents=1, agent_ids=None, **cfg_kw):
         self._tm = track if isinstance(track, TrackMap) else load_track(track)
-        self._env = BatchedRaceEnv(EnvConfig(tracks=(self._tm,), n_envs=n_envs, auto_reset=False, **cfg_kw),
+        n_agents = int(cfg_kw.get("agents_per_world", n_agents))
+        cfg_kw["agents_per_world"] = n_agents
+        self._ids = tuple(agent_ids) if agent_ids is not None else AGENT_IDS[:n_agents]
+        if len(self._ids) != n_agents:
+            raise ValueError("agent_ids must name every car of the world")
+        self.agent_id = self._ids[0]
+        self._env = BatchedRaceEnv(EnvConfig(tracks=(self._tm,), n_envs=n_agents, auto_reset=False, **cfg_kw),
                                    device=self._device)
         self.scenario = _scenario_of(self._tm)
 
     @property
     def agent_ids(self):
-        return [self.agent_id]
+        return list(self._ids)
 
     @property
     def n_agents(self):
-        return 1
+        return len(self._ids)
 
     def _host(self) -> TDict[str, np.ndarray]:
-        """One device->host read of every (tiny) result buffer of env 0."""
+        """One device->host read of every (tiny) result buffer of the world: arrays with leading dim n_agents."""
         buf = self._env.buf
         torch.cuda.current_stream(self._env.device).synchronize()
-        return {k: v[0].cpu().numpy() for k, v in buf.items() if v is not None}
+        return {k: v.cpu().numpy() for k, v in buf.items() if v is not None}
 
-    def _info(self, h, f64=None) -> dict:
-        fl = int(h["flags"])
-        pose = h["pose"].astype(np.float64)
-        vel = h["velocity"].astype(np.float64)
+    def _info(self, h, f64=None, k: int = 0) -> dict:
+        fl = int(h["flags"][k])
+        pose = h["pose"][k].astype(np.float64)
+        vel = h["velocity"][k].astype(np.float64)
         if f64 is not None:  # float64 pose straight from the state (racecar_gym reports float64)
-            yaw = f64[_abi.S_YAW]
-            pose = np.array([f64[_abi.S_X], f64[_abi.S_Y], 0.0, 0.0, 0.0, yaw - np.rint(yaw / (2 * np.pi)) * 2 * np.pi])
-            v, b = f64[_abi.S_V], f64[_abi.S_SLIP]
-            vel = np.array([v * np.cos(b), v * np.sin(b), 0.0, 0.0, 0.0, f64[_abi.S_YAWRATE]])
-        return {"pose": pose, "velocity": vel, "progress": float(h["progress"]), "lap": int(h["lap"]),
-                "time": float(h["time"]), "wrong_way": bool(fl & _abi.F_WRONG_WAY),
-                "wall_collision": bool(fl & _abi.F_COLLISION), "opponent_collisions": [],
-                "left_map": bool(fl & _abi.F_LEFT_MAP)}
+            yaw = f64[_abi.S_YAW, k]
+            pose = np.array([f64[_abi.S_X, k], f64[_abi.S_Y, k], 0.0, 0.0, 0.0, yaw - np.rint(yaw / (2 * np.pi)) * 2 * np.pi])
+            v, b = f64[_abi.S_V, k], f64[_abi.S_SLIP, k]
+            vel = np.array([v * np.cos(b), v * np.sin(b), 0.0, 0.0, 0.0, f64[_abi.S_YAWRATE, k]])
+        opp = int(h["opponents"][k])
+        return {"pose": pose, "velocity": vel, "progress": float(h["progress"][k]), "lap": int(h["lap"][k]),
+                "time": float(h["time"][k]), "wrong_way": bool(fl & _abi.F_WRONG_WAY),
+                "wall_collision": bool(fl & _abi.F_COLLISION),
+                "opponent_collisions": [self._ids[j] for j in range(len(self._ids)) if (opp >> j) & 1],
+                "rank": int(h["rank"][k]), "left_map": bool(fl & _abi.F_LEFT_MAP)}
 
     def render(self, mode: str = "birds_eye", agent: str = "A", **kwargs) -> np.ndarray:
         """Top-down RGB view of the drivable area around the car (the reference renders through PyBullet
         [REF dreamer/wrappers.py:178-195]; videos are not on the hot path, so this is a plain map crop)."""
         h = self._host()
         occ = self.scenario.world._maps["occupancy"]
-        pr, pc = occ.to_pixel(h["pose"])
+        k = self._ids.index(agent) if agent in self._ids else 0
+        pr, pc = occ.to_pixel(h["pose"][k])
         half = 100
         m = np.pad(occ._map, half, mode="constant")
         crop = m[pr:pr + 2 * half, pc:pc + 2 * half]
@@ -153,23 +180,33 @@ class ReferenceEnv(_SingleAgentBase):
     """
 
     def __init__(self, track="austria", task="max_progress", action_repeat=4, time_limit_steps=None,
-                 reset_mode="random", occupancy=True, device=None, scenario: Optional[str] = None, **overrides):
+                 reset_mode=None, occupancy=True, device=None, scenario: Optional[str] = None, n_agents: int = 1,
+                 **overrides):
+        """n_agents > 1 (or a scenario file with several agents): one world of cars 'A', 'B', ...; every dict below then
+        has one entry per car, ActionRepeat stops when ANY car is done, TimeLimit sets every done
+        [REF dreamer/wrappers.py:107-116,147-154]; reset_mode defaults to 'random_ball' for several cars and 'random'
+        for one [REF dreamer/dream.py:105-108]."""
         self._device = device
         params = dict(SCENARIO_DEFAULTS.get(task, SCENARIO_DEFAULTS["max_progress"]))
+        ids = None
         if scenario is not None:
             sc = load_scenario(scenario)
             track = sc.pop("track", track)
             sc.pop("sensors", None)
+            ids = sc.pop("agent_ids", None)
             params.update(sc)
         params.update(overrides)
+        n_agents = int(params.pop("agents_per_world", n_agents))
+        if reset_mode is None:
+            reset_mode = "random_ball" if n_agents > 1 else "random"
         if time_limit_steps is None:  # dream.py: time_limit_train 2000 sim ticks / action_repeat [REF dreamer/dream.py:57,109]
             time_limit_steps = 2000 // int(action_repeat)
-        self._make(track, action_repeat=int(action_repeat), reset_mode=reset_mode,
+        self._make(track, n_agents=n_agents, agent_ids=ids, action_repeat=int(action_repeat), reset_mode=reset_mode,
                    obs_type="lidar_occupancy" if occupancy else "lidar", time_limit_steps=int(time_limit_steps),
                    rescale_actions=True, **params)
         self._occupancy = occupancy
         self._needs_reset = True
-        self._action = torch.zeros((1, 2), dtype=torch.float32, device=self._env.device)
+        self._action = torch.zeros((self.n_agents, 2), dtype=torch.float32, device=self._env.device)
 
     @property
     def observation_space(self):
@@ -180,18 +217,22 @@ class ReferenceEnv(_SingleAgentBase):
               "speed": box(-np.inf, np.inf, shape=(1,), dtype=np.float32)}  # [REF dreamer/wrappers.py:50]
         if self._occupancy:
             sp["lidar_occupancy"] = box(0, 1, shape=(64, 64, 1), dtype=np.uint8)  # [REF dreamer/wrappers.py:380-385]
-        return spaces.Dict({self.agent_id: spaces.Dict(sp)})
+        return spaces.Dict({aid: spaces.Dict(dict(sp)) for aid in self._ids})
 
     @property
     def action_space(self):  # [REF dreamer/wrappers.py:55-60]: Box(append(motor.low, steering.low), ...)
-        return spaces.Dict({self.agent_id: spaces.Box(np.array([-1.0, -1.0], np.float32), np.array([1.0, 1.0], np.float32))})
+        return spaces.Dict({aid: spaces.Box(np.array([-1.0, -1.0], np.float32), np.array([1.0, 1.0], np.float32))
+                            for aid in self._ids})
 
     def _obs(self, h, reset: bool):
-        obs = {"lidar": h["lidar"], "pose": h["pose"], "velocity": h["velocity"],
-               "speed": np.float32(0.0) if reset else np.float32(h["speed"])}
-        if self._occupancy:
-            obs["lidar_occupancy"] = h["occupancy"]
-        return {self.agent_id: obs}
+        out = {}
+        for k, aid in enumerate(self._ids):
+            obs = {"lidar": h["lidar"][k], "pose": h["pose"][k], "velocity": h["velocity"][k],
+                   "speed": np.float32(0.0) if reset else np.float32(h["speed"][k])}
+            if self._occupancy:
+                obs["lidar_occupancy"] = h["occupancy"][k]
+            out[aid] = obs
+        return out
 
     def reset(self, mode: Optional[str] = None):
         self._env.reset(mode=mode)
@@ -200,62 +241,71 @@ class ReferenceEnv(_SingleAgentBase):
 
     def step(self, actions):
         assert not self._needs_reset, "Must reset environment."  # [REF dreamer/wrappers.py:148]
-        a = np.asarray(actions[self.agent_id], dtype=np.float32).reshape(1, 2)
+        a = np.stack([np.asarray(actions[aid], dtype=np.float32).reshape(2) for aid in self._ids])
         self._action.copy_(torch.from_numpy(a))
         self._env.step(self._action)
         h = self._host()
-        done = bool(h["done"])
-        self._needs_reset = done
-        aid = self.agent_id
-        return self._obs(h, reset=False), {aid: float(h["reward"])}, {aid: done}, {aid: self._info(h)}
+        dones = {aid: bool(h["done"][k]) for k, aid in enumerate(self._ids)}
+        self._needs_reset = any(dones.values())   # the world is over for everybody [REF dreamer/tools.py:178-179]
+        return (self._obs(h, reset=False), {aid: float(h["reward"][k]) for k, aid in enumerate(self._ids)}, dones,
+                {aid: self._info(h, k=k) for k, aid in enumerate(self._ids)})
 
 
 class RaceCarGymCompat(_SingleAgentBase):
     """``racecar_gym.envs.MultiAgentRaceEnv``-shaped view: one sim tick per ``step`` (see module docstring)."""
 
-    def __init__(self, track="austria", task="max_progress", device=None, scenario: Optional[str] = None, **overrides):
+    def __init__(self, track="austria", task="max_progress", device=None, scenario: Optional[str] = None,
+                 n_agents: int = 1, **overrides):
         self._device = device
         params = dict(SCENARIO_DEFAULTS.get(task, SCENARIO_DEFAULTS["max_progress"]))
+        ids = None
         if scenario is not None:
             sc = load_scenario(scenario)
             track = sc.pop("track", track)
             sc.pop("sensors", None)
+            ids = sc.pop("agent_ids", None)
             params.update(sc)
         params.update(overrides)
-        self._make(track, action_repeat=1, rescale_actions=False, obs_type="lidar", time_limit_steps=0, **params)
-        self._action = torch.zeros((1, 2), dtype=torch.float32, device=self._env.device)
+        n_agents = int(params.pop("agents_per_world", n_agents))
+        self._make(track, n_agents=n_agents, agent_ids=ids, action_repeat=1, rescale_actions=False, obs_type="lidar",
+                   time_limit_steps=0, **params)
+        self._action = torch.zeros((self.n_agents, 2), dtype=torch.float32, device=self._env.device)
 
     @property
     def observation_space(self):
         box = spaces.Box
-        return spaces.Dict({self.agent_id: spaces.Dict({
+        return spaces.Dict({aid: spaces.Dict({
             "lidar": box(0.0, 15.0, shape=(1080,), dtype=np.float64),
             "pose": box(-100.0, 100.0, shape=(6,), dtype=np.float64),
-            "velocity": box(-10.0, 10.0, shape=(6,), dtype=np.float64)})})
+            "velocity": box(-10.0, 10.0, shape=(6,), dtype=np.float64)}) for aid in self._ids})
 
     @property
     def action_space(self):
         box = spaces.Box
-        return spaces.Dict({self.agent_id: spaces.Dict({
+        return spaces.Dict({aid: spaces.Dict({
             "motor": box(-1.0, 1.0, shape=(1,), dtype=np.float64),
-            "steering": box(-1.0, 1.0, shape=(1,), dtype=np.float64)})})
+            "steering": box(-1.0, 1.0, shape=(1,), dtype=np.float64)}) for aid in self._ids})
 
     def _state(self):
         f, _ = self._env.get_state()
-        return f[:, 0].cpu().numpy()
+        return f.cpu().numpy()
 
-    def _obs(self, h, info):
-        return {self.agent_id: {"lidar": h["lidar"].astype(np.float64), "pose": info["pose"], "velocity": info["velocity"]}}
+    def _obs(self, h, infos):
+        return {aid: {"lidar": h["lidar"][k].astype(np.float64), "pose": infos[aid]["pose"],
+                      "velocity": infos[aid]["velocity"]} for k, aid in enumerate(self._ids)}
+
+    def _infos(self, h):
+        f64 = self._state()
+        return {aid: self._info(h, f64, k) for k, aid in enumerate(self._ids)}
 
     def reset(self, mode: str = "grid"):
         self._env.reset(mode=mode)
         h = self._host()
-        return self._obs(h, self._info(h, self._state()))
+        return self._obs(h, self._infos(h))
 
     def step(self, actions):
-        a = actions[self.agent_id]
-        cmd = np.array([[float(np.asarray(a["motor"]).reshape(-1)[0]), float(np.asarray(a["steering"]).reshape(-1)[0])]],
-                       dtype=np.float32)
+        cmd = np.array([[float(np.asarray(actions[aid]["motor"]).reshape(-1)[0]),
+                         float(np.asarray(actions[aid]["steering"]).reshape(-1)[0])] for aid in self._ids], dtype=np.float32)
         # racecar_gym keeps stepping after a terminal tick; the wrappers above decide when to reset
         f, i = self._env.get_state()
         i[_abi.I_FLAGS] &= ~_abi.F_NEEDS_RESET
@@ -263,17 +313,17 @@ class RaceCarGymCompat(_SingleAgentBase):
         self._action.copy_(torch.from_numpy(cmd))
         self._env.step(self._action)
         h = self._host()
-        info = self._info(h, self._state())
-        aid = self.agent_id
-        return self._obs(h, info), {aid: float(h["reward"])}, {aid: bool(h["done"])}, {aid: info}
+        infos = self._infos(h)
+        return (self._obs(h, infos), {aid: float(h["reward"][k]) for k, aid in enumerate(self._ids)},
+                {aid: bool(h["done"][k]) for k, aid in enumerate(self._ids)}, infos)
 
 
 def make_reference_env(track: str, task: str = "max_progress", action_repeat: int = 4, mode: str = "train",
                        device=None, **kw) -> ReferenceEnv:
     """``make_train_env`` / ``make_test_env`` of dream.py without the PyBullet sim [REF dreamer/dream.py:103-131]:
     train = reset mode 'random', TimeLimit 2000/action_repeat; test = 'grid', 4000/action_repeat."""
-    if mode == "train":
-        return ReferenceEnv(track, task, action_repeat, time_limit_steps=2000 // action_repeat, reset_mode="random",
+    if mode == "train":  # 'random' for one car, 'random_ball' for several [REF dreamer/dream.py:105-108]
+        return ReferenceEnv(track, task, action_repeat, time_limit_steps=2000 // action_repeat, reset_mode=None,
                             device=device, **kw)
     return ReferenceEnv(track, task, action_repeat, time_limit_steps=4000 // action_repeat, reset_mode="grid",
                         device=device, **kw)

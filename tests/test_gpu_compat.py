@@ -144,3 +144,107 @@ def test_episode_recorder_on_gpu_matches_reference_collect(torch_cuda, golden_di
     helpers.assert_episodes_match_golden(captured, g, tol=1e-5, lidar_tol=1e-3)
     assert count_episodes(tmp_path)[0] == int(g["n_episodes"])
     env.close()
+
+
+BASELINES_SCENARIO = """\
+world:
+  name: austria
+agents:
+  - id: A
+    vehicle: {name: racecar, sensors: [lidar, pose, velocity, acceleration]}
+    task:
+      task_name: maximize_progress
+      params: {laps: 10, time_limit: 180.0, terminate_on_collision: True, collision_reward: -1.0}
+  - id: B
+    vehicle: {name: racecar, sensors: [lidar, pose, velocity, acceleration], color: red}
+    task: {task_name: n_step_progress, params: {n_steps: 10}}
+  - id: C
+    vehicle: {name: racecar, sensors: [lidar, pose, velocity, acceleration], color: yellow}
+    task: {task_name: n_step_progress, params: {n_steps: 10}}
+  - id: D
+    vehicle: {name: racecar, sensors: [lidar, pose, velocity, acceleration], color: magenta}
+    task: {task_name: n_step_progress, params: {n_steps: 10}}
+"""
+
+
+def test_multi_agent_reference_env_replays_the_wrapper_stack_golden(torch_cuda, golden_dir, tmp_path):
+    """The four-car scenario of the baselines [REF baselines/scenarios/max_progress/austria.yml] through the dict API
+    == the reference's unmodified dict-of-agents wrapper stack (multi_agent_stack_golden.npz)."""
+    from racing_dreamer_b200.compat import ReferenceEnv
+    g = np.load(golden_dir / "multi_agent_stack_golden.npz")
+    yml = tmp_path / "austria.yml"
+    yml.write_text(BASELINES_SCENARIO)
+    env = ReferenceEnv(scenario=str(yml), action_repeat=int(g["action_repeat"]), time_limit_steps=int(g["duration"]),
+                       device="cuda:0", seed=int(g["seed"]), ball_spacing=float(g["ball_spacing"]))
+    ids = ["A", "B", "C", "D"]
+    assert env.agent_ids == ids and env.n_agents == 4
+    assert sorted(env.action_space.spaces) == ids and env.observation_space["C"]["lidar"].shape == (1080,)
+    assert env._env.config.reset_mode == "random_ball"          # [REF dreamer/dream.py:105-106]
+    keys = ("lidar", "pose", "velocity", "speed", "reward", "done", "progress", "lap", "time", "flags", "occupancy",
+            "rank", "opponents")
+    rec = {k: [] for k in keys}
+    for t in range(g["actions"].shape[0]):
+        if g["reset_before"][t]:
+            obs = env.reset()
+            assert all(obs[i]["speed"] == 0.0 and not obs[i]["lidar_occupancy"].any() for i in ids)
+        obs, rew, done, info = env.step({i: g["actions"][t, k] for k, i in enumerate(ids)})
+        row = {k: [] for k in keys}
+        for k, i in enumerate(ids):
+            o, f = obs[i], info[i]
+            row["lidar"].append(o["lidar"]); row["pose"].append(o["pose"]); row["velocity"].append(o["velocity"])
+            row["speed"].append(o["speed"]); row["occupancy"].append(o["lidar_occupancy"][..., 0])
+            row["reward"].append(np.float32(rew[i])); row["done"].append(done[i])
+            row["progress"].append(np.float32(f["progress"])); row["lap"].append(f["lap"]); row["time"].append(np.float32(f["time"]))
+            row["flags"].append((_abi.F_WRONG_WAY if f["wrong_way"] else 0) | (_abi.F_COLLISION if f["wall_collision"] else 0)
+                                | (_abi.F_OPPONENT if f["opponent_collisions"] else 0))
+            row["rank"].append(f["rank"])
+            row["opponents"].append(sum(1 << ids.index(j) for j in f["opponent_collisions"]))
+        for k in keys:
+            rec[k].append(np.stack([np.asarray(x) for x in row[k]]))
+        if any(done.values()):
+            with pytest.raises(AssertionError, match="Must reset environment"):
+                env.step({i: np.zeros(2, np.float32) for i in ids})
+    rec = {k: np.stack(v) for k, v in rec.items()}
+    helpers.assert_matches_multi_agent_golden(rec, g, lidar_tol=1e-3, float_tol=1e-5)
+    assert env.render(agent="C").shape == (200, 200, 3)
+    env.close()
+
+
+def test_multi_agent_tick_env_composes_to_fused_step(torch_cuda):
+    """RaceCarGymCompat with three cars, driven by the reference's ActionRepeat loop restated by hand
+    [REF dreamer/wrappers.py:107-116: stop when ANY agent is done, sum per agent] == the fused multi-car step."""
+    from racing_dreamer_b200.compat import RaceCarGymCompat, ReferenceEnv
+    R, ids = 4, ["A", "B", "C"]
+    kw = dict(n_agents=3, seed=9, ball_spacing=0.8)
+    fused = ReferenceEnv("treitlstrasse_v2", "max_progress", action_repeat=R, time_limit_steps=10 ** 6,
+                         reset_mode="random_ball", occupancy=False, device="cuda:0", **kw)
+    tick = RaceCarGymCompat("treitlstrasse_v2", "max_progress", device="cuda:0", **kw)
+    assert tick.agent_ids == ids
+    fused.reset()
+    tick.reset(mode="random_ball")
+    rng = np.random.RandomState(15)
+    low, high = np.array([0.005, -1.0]), np.array([1.0, 1.0])
+    contacts = 0
+    for step in range(200):
+        acts = {i: (rng.uniform(-1, 1, 2) * [1.0, 0.3]).astype(np.float32) for i in ids}
+        acts["A"][0] = 1.0
+        fo, fr, fd, fi = fused.step(acts)
+        cmds = {i: (a + 1) / 2 * (high - low) + low for i, a in acts.items()}
+        total, dones = {i: 0.0 for i in ids}, {i: False for i in ids}
+        for _ in range(R):
+            to, tr, dones, ti = tick.step({i: {"motor": c[0], "steering": c[1]} for i, c in cmds.items()})
+            total = {i: total[i] + tr[i] for i in ids}
+            if any(dones.values()):
+                break
+        for i in ids:
+            assert dones[i] == fd[i], (step, i)
+            assert abs(total[i] - fr[i]) <= 1e-5 * max(1.0, abs(total[i]))
+            assert np.abs(to[i]["lidar"] - fo[i]["lidar"]).max() <= 1e-3
+            assert ti[i]["opponent_collisions"] == fi[i]["opponent_collisions"] and ti[i]["rank"] == fi[i]["rank"]
+            contacts += len(fi[i]["opponent_collisions"])
+        if any(dones.values()):
+            fused.reset()
+            tick.reset(mode="random_ball")   # same seed, same episode counters -> the same world
+    assert contacts > 0
+    fused.close()
+    tick.close()
