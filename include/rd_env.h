@@ -299,7 +299,8 @@ int rd_occupancy_obs(rd_env* env, const double* poses_dev, const int32_t* map_id
  * commands f64 [n,2] = sim-facing (motor, steering), n_ticks ticks of cfg.dt. */
 int rd_dynamics(rd_env* env, double* state_dev, const double* commands_dev, int n, int n_ticks, void* stream);
 
-/* ---- state access (checkpoint/resume; teacher forcing) ---- */
+/* ---- state access (checkpoint/resume; teacher forcing); either pointer may be NULL.  The ring of the n_step_progress
+ *      task is not part of the layout: restoring the float64 part restarts it from the restored lap + progress ---- */
 int rd_get_state(rd_env* env, double* f64_dev, int32_t* i32_dev, void* stream);
 int rd_set_state(rd_env* env, const double* f64_dev, const int32_t* i32_dev, void* stream);
 

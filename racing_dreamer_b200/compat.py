@@ -106,17 +106,43 @@ class _SingleAgentBase:
     agent_id = "A"
     _ids = ("A",)
 
-    def _make(self, track, n_agents=1, agent_ids=None, **cfg_kw):
-        self._tm = track if isinstance(track, TrackMap) else load_track(track)
+    def _make(self, track, n_agents=1, agent_ids=None, order="manual", **cfg_kw):
+        """track: one track or a list of tracks (racecar_gym's ChangingTrack* envs [REF dreamer/evaluations/make_env.py:
+        6-11 order='manual'; baselines/racing/experiments/acme/experiment.py:90-93 order='sequential']): every map lives
+        on the device, ``set_next_env()`` switches the world to the next one."""
+        many = isinstance(track, (list, tuple))
+        self._tms = [t if isinstance(t, TrackMap) else load_track(t) for t in (track if many else [track])]
+        if order not in ("manual", "sequential"):
+            raise ValueError("order must be 'manual' or 'sequential'")
+        self._order = order
+        self._track_idx = 0
+        self._resets = 0
+        self._tm = self._tms[0]
         n_agents = int(cfg_kw.get("agents_per_world", n_agents))
         cfg_kw["agents_per_world"] = n_agents
         self._ids = tuple(agent_ids) if agent_ids is not None else AGENT_IDS[:n_agents]
         if len(self._ids) != n_agents:
             raise ValueError("agent_ids must name every car of the world")
         self.agent_id = self._ids[0]
-        self._env = BatchedRaceEnv(EnvConfig(tracks=(self._tm,), n_envs=n_agents, auto_reset=False, **cfg_kw),
-                                   device=self._device)
-        self.scenario = _scenario_of(self._tm)
+        self._env = BatchedRaceEnv(EnvConfig(tracks=tuple(self._tms), n_envs=n_agents, auto_reset=False,
+                                             map_ids=[0] * n_agents, **cfg_kw), device=self._device)
+        self._scenarios = [_scenario_of(tm) for tm in self._tms]
+        self.scenario = self._scenarios[0]
+
+    def set_next_env(self) -> None:
+        """Switch to the next track of the list [REF dreamer/evaluations/run_evaluation.py:48-49]; takes effect with the
+        next ``reset``, which the caller owes anyway."""
+        self._track_idx = (self._track_idx + 1) % len(self._tms)
+        self._tm = self._tms[self._track_idx]
+        self.scenario = self._scenarios[self._track_idx]
+        self._env.assign_maps([self._track_idx] * self.n_agents)
+        self._needs_reset = True
+
+    def _before_reset(self) -> None:
+        # order='sequential': every reset but the first moves on to the next track
+        if self._order == "sequential" and self._resets > 0 and len(self._tms) > 1:
+            self.set_next_env()
+        self._resets += 1
 
     @property
     def agent_ids(self):
@@ -149,17 +175,38 @@ class _SingleAgentBase:
                 "rank": int(h["rank"][k]), "left_map": bool(fl & _abi.F_LEFT_MAP)}
 
     def render(self, mode: str = "birds_eye", agent: str = "A", **kwargs) -> np.ndarray:
-        """Top-down RGB view of the drivable area around the car (the reference renders through PyBullet
-        [REF dreamer/wrappers.py:178-195]; videos are not on the hot path, so this is a plain map crop)."""
+        """RGB view (200, 200, 3) of the 10 m x 10 m around car ``agent``: 'birds_eye' = north up, 'follow' = the car's
+        heading up; drivable area white, the cars of the world as filled body boxes (``agent`` red, the others blue).
+        The reference renders these two views through PyBullet cameras [REF dreamer/wrappers.py:178-195; videos are
+        written by callbacks.save_videos]; frames are not on the hot path, so this is a host-side map crop."""
+        if mode not in ("birds_eye", "follow"):
+            raise ValueError(f"render mode {mode!r}: expected 'birds_eye' or 'follow'")
         h = self._host()
-        occ = self.scenario.world._maps["occupancy"]
-        k = self._ids.index(agent) if agent in self._ids else 0
-        pr, pc = occ.to_pixel(h["pose"][k])
-        half = 100
-        m = np.pad(occ._map, half, mode="constant")
-        crop = m[pr:pr + 2 * half, pc:pc + 2 * half]
-        img = np.repeat((crop.astype(np.uint8) * 255)[..., None], 3, axis=2)
-        img[half - 2:half + 3, half - 2:half + 3] = (255, 0, 0)
+        tm = self._tm
+        k0 = self._ids.index(agent) if agent in self._ids else 0
+        half, res = 100, tm.resolution
+        x0, y0, yaw0 = float(h["pose"][k0][0]), float(h["pose"][k0][1]), float(h["pose"][k0][5])
+        # world coordinates of every output pixel (row 0 = top)
+        jj, ii = np.meshgrid(np.arange(2 * half) - half + 0.5, half - np.arange(2 * half) - 0.5)
+        u, v = jj * res, ii * res
+        if mode == "follow":   # heading up: image +v axis = car's x axis
+            c, s = np.cos(yaw0), np.sin(yaw0)
+            wx, wy = x0 + v * c + u * s, y0 + v * s - u * c
+        else:
+            wx, wy = x0 + u, y0 + v
+        full = self.scenario.world._maps["occupancy"]._map
+        col = np.floor((wx - tm.origin[0]) / res).astype(np.int64)
+        row = full.shape[0] - 1 - np.floor((wy - tm.origin[1]) / res).astype(np.int64)
+        ok = (row >= 0) & (row < full.shape[0]) & (col >= 0) & (col < full.shape[1])
+        drv = np.zeros(wx.shape, bool)
+        drv[ok] = full[row[ok], col[ok]]
+        img = np.repeat((drv.astype(np.uint8) * 255)[..., None], 3, axis=2)
+        hl, hw = 0.5 * float(self._env.cfg.vehicle.body_length), 0.5 * float(self._env.cfg.vehicle.body_width)
+        for k in range(self.n_agents):
+            px, py, pyaw = float(h["pose"][k][0]), float(h["pose"][k][1]), float(h["pose"][k][5])
+            c, s = np.cos(pyaw), np.sin(pyaw)
+            lx, ly = (wx - px) * c + (wy - py) * s, (wy - py) * c - (wx - px) * s
+            img[(np.abs(lx) <= hl) & (np.abs(ly) <= hw)] = (255, 0, 0) if k == k0 else (0, 0, 255)
         return img
 
     def close(self):
@@ -181,7 +228,7 @@ class ReferenceEnv(_SingleAgentBase):
 
     def __init__(self, track="austria", task="max_progress", action_repeat=4, time_limit_steps=None,
                  reset_mode=None, occupancy=True, device=None, scenario: Optional[str] = None, n_agents: int = 1,
-                 **overrides):
+                 order: str = "manual", **overrides):
         """n_agents > 1 (or a scenario file with several agents): one world of cars 'A', 'B', ...; every dict below then
         has one entry per car, ActionRepeat stops when ANY car is done, TimeLimit sets every done
         [REF dreamer/wrappers.py:107-116,147-154]; reset_mode defaults to 'random_ball' for several cars and 'random'
@@ -201,7 +248,7 @@ class ReferenceEnv(_SingleAgentBase):
             reset_mode = "random_ball" if n_agents > 1 else "random"
         if time_limit_steps is None:  # dream.py: time_limit_train 2000 sim ticks / action_repeat [REF dreamer/dream.py:57,109]
             time_limit_steps = 2000 // int(action_repeat)
-        self._make(track, n_agents=n_agents, agent_ids=ids, action_repeat=int(action_repeat), reset_mode=reset_mode,
+        self._make(track, n_agents=n_agents, agent_ids=ids, order=order, action_repeat=int(action_repeat), reset_mode=reset_mode,
                    obs_type="lidar_occupancy" if occupancy else "lidar", time_limit_steps=int(time_limit_steps),
                    rescale_actions=True, **params)
         self._occupancy = occupancy
@@ -235,6 +282,7 @@ class ReferenceEnv(_SingleAgentBase):
         return out
 
     def reset(self, mode: Optional[str] = None):
+        self._before_reset()
         self._env.reset(mode=mode)
         self._needs_reset = False
         return self._obs(self._host(), reset=True)
@@ -255,7 +303,7 @@ class RaceCarGymCompat(_SingleAgentBase):
     """``racecar_gym.envs.MultiAgentRaceEnv``-shaped view: one sim tick per ``step`` (see module docstring)."""
 
     def __init__(self, track="austria", task="max_progress", device=None, scenario: Optional[str] = None,
-                 n_agents: int = 1, **overrides):
+                 n_agents: int = 1, order: str = "manual", **overrides):
         self._device = device
         params = dict(SCENARIO_DEFAULTS.get(task, SCENARIO_DEFAULTS["max_progress"]))
         ids = None
@@ -267,7 +315,7 @@ class RaceCarGymCompat(_SingleAgentBase):
             params.update(sc)
         params.update(overrides)
         n_agents = int(params.pop("agents_per_world", n_agents))
-        self._make(track, n_agents=n_agents, agent_ids=ids, action_repeat=1, rescale_actions=False, obs_type="lidar",
+        self._make(track, n_agents=n_agents, agent_ids=ids, order=order, action_repeat=1, rescale_actions=False, obs_type="lidar",
                    time_limit_steps=0, **params)
         self._action = torch.zeros((self.n_agents, 2), dtype=torch.float32, device=self._env.device)
 
@@ -299,6 +347,7 @@ class RaceCarGymCompat(_SingleAgentBase):
         return {aid: self._info(h, f64, k) for k, aid in enumerate(self._ids)}
 
     def reset(self, mode: str = "grid"):
+        self._before_reset()
         self._env.reset(mode=mode)
         h = self._host()
         return self._obs(h, self._infos(h))
@@ -307,9 +356,9 @@ class RaceCarGymCompat(_SingleAgentBase):
         cmd = np.array([[float(np.asarray(actions[aid]["motor"]).reshape(-1)[0]),
                          float(np.asarray(actions[aid]["steering"]).reshape(-1)[0])] for aid in self._ids], dtype=np.float32)
         # racecar_gym keeps stepping after a terminal tick; the wrappers above decide when to reset
-        f, i = self._env.get_state()
+        _, i = self._env.get_state()
         i[_abi.I_FLAGS] &= ~_abi.F_NEEDS_RESET
-        self._env.set_state(f, i)
+        self._env.set_state(None, i)
         self._action.copy_(torch.from_numpy(cmd))
         self._env.step(self._action)
         h = self._host()

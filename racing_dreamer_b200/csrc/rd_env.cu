@@ -1051,7 +1051,7 @@ RD_API int rd_set_state(rd_env* env, const double* f64_dev, const int32_t* i32_d
     // everything but the map row: map assignment is owned by rd_assign_maps (the env grouping depends on it)
     CUDA_TRY(env, cudaMemcpyAsync(env->d_i32, i32_dev, sizeof(int32_t) * (size_t)RD_I_MAP * n, cudaMemcpyDeviceToDevice, s));
   }
-  if (env->d_hist) {  // the n-step ring is not part of the state layout: restart it from the restored lap + progress
+  if (env->d_hist && f64_dev) {  // the n-step ring is not part of the state layout: restart it from the restored lap + progress
     for (int k = 0; k < env->cfg.n_step_progress; ++k)
       CUDA_TRY(env, cudaMemcpyAsync(env->d_hist + (size_t)k * n, env->d_f64 + (size_t)RD_S_LAST * n, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
   }

@@ -161,6 +161,18 @@ class BatchedRaceEnv:
             self._check(self.lib.rd_assign_maps(self._handle, ids.ctypes.data))
             self._alloc()
 
+    def assign_maps(self, map_ids: Sequence[int]) -> None:
+        """Re-assign the tracks (indices into ``tracks``) of the envs -- every track was uploaded at construction, so
+        switching is one small host->device copy (racecar_gym's ChangingTrack* envs [REF dreamer/evaluations/make_env.py:
+        6-11; baselines/racing/experiments/acme/experiment.py:90-93]).  The envs must be reset afterwards."""
+        ids = np.ascontiguousarray(map_ids, dtype=np.int32)
+        if ids.shape != (self.n,):
+            raise ValueError("map_ids must have one entry per env")
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream(self.device).synchronize()
+            self._check(self.lib.rd_assign_maps(self._handle, ids.ctypes.data))
+        self.map_ids = ids
+
     # ------------------------------------------------------------------ buffers
     OUT_SPEC = (  # key, per-env shape, dtype  [REF dreamer/wrappers.py:62-69,210-226: obs + what Collect records]
         ("lidar", None, torch.float32), ("occupancy", (64, 64, 1), torch.uint8), ("pose", (6,), torch.float32),
@@ -285,13 +297,15 @@ class BatchedRaceEnv:
             self._check(self.lib.rd_get_state(self._handle, f.data_ptr(), i.data_ptr(), self._stream()))
         return f, i
 
-    def set_state(self, f64: torch.Tensor, i32: torch.Tensor) -> None:
-        f = f64.to(device=self.device, dtype=torch.float64).contiguous()
-        i = i32.to(device=self.device, dtype=torch.int32).contiguous()
-        if f.shape != (_abi.NF64, self.n) or i.shape != (_abi.NI32, self.n):
+    def set_state(self, f64: Optional[torch.Tensor], i32: Optional[torch.Tensor]) -> None:
+        """Either part may be None (left as it is).  Restoring the float64 part restarts the n_step_progress ring."""
+        f = None if f64 is None else f64.to(device=self.device, dtype=torch.float64).contiguous()
+        i = None if i32 is None else i32.to(device=self.device, dtype=torch.int32).contiguous()
+        if (f is not None and f.shape != (_abi.NF64, self.n)) or (i is not None and i.shape != (_abi.NI32, self.n)):
             raise ValueError("state shapes must be [NF64, n] and [NI32, n]")
         with torch.cuda.device(self.device):
-            self._check(self.lib.rd_set_state(self._handle, f.data_ptr(), i.data_ptr(), self._stream()))
+            self._check(self.lib.rd_set_state(self._handle, f.data_ptr() if f is not None else None,
+                                              i.data_ptr() if i is not None else None, self._stream()))
             torch.cuda.current_stream(self.device).synchronize()  # f/i may be temporaries
 
     def read_stats(self, reset: bool = False) -> Dict[str, float]:

@@ -38,3 +38,20 @@ def test_reference_env_needs_gpu():
     from racing_dreamer_b200._abi import NativeLibraryError
     with pytest.raises((NativeLibraryError, RuntimeError)):
         compat.ReferenceEnv("austria")
+
+
+def test_load_multi_agent_scenario(tmp_path):
+    # the baselines' four-car files [REF baselines/scenarios/max_progress/austria.yml:1-34]
+    p = tmp_path / "austria.yml"
+    p.write_text("world:\n  name: austria\nagents:\n"
+                 "  - id: A\n    vehicle: {name: racecar, sensors: [lidar, pose]}\n"
+                 "    task: {task_name: maximize_progress, params: {laps: 10, time_limit: 180.0}}\n"
+                 "  - id: B\n    vehicle: {name: racecar, sensors: [lidar]}\n"
+                 "    task: {task_name: n_step_progress, params: {n_steps: 7}}\n")
+    sc = compat.load_scenario(p)
+    assert sc["agents_per_world"] == 2 and sc["agent_tasks"] == ["maximize_progress", "n_step_progress"]
+    assert sc["agent_ids"] == ["A", "B"] and sc["n_step_progress"] == 7 and sc["laps"] == 10
+    p.write_text("world:\n  name: austria\nagents:\n" + "".join(
+        f"  - id: {c}\n    task: {{task_name: maximize_progress}}\n" for c in "ABCDE"))
+    with pytest.raises(ValueError, match="at most"):
+        compat.load_scenario(p)

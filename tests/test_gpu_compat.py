@@ -248,3 +248,48 @@ def test_multi_agent_tick_env_composes_to_fused_step(torch_cuda):
     assert contacts > 0
     fused.close()
     tick.close()
+
+
+def test_changing_track_env_and_render(torch_cuda):
+    """racecar_gym's ChangingTrack envs [REF dreamer/evaluations/make_env.py:6-11; run_evaluation.py:48-49]: every map on
+    the device, set_next_env() until the wanted track is current; each track behaves exactly like its own env."""
+    from racing_dreamer_b200.compat import ReferenceEnv
+    tracks = ["austria", "columbia", "treitlstrasse_v2"]
+    multi = ReferenceEnv(tracks, "eval", action_repeat=8, time_limit_steps=50, reset_mode="grid", device="cuda:0")
+    rng = np.random.RandomState(1)
+    acts = (rng.uniform(-1, 1, (30, 2)) * [1.0, 0.3]).astype(np.float32)
+    for want in ["columbia", "treitlstrasse_v2", "austria"]:
+        while multi.scenario.world._config.name != multi._tms[tracks.index(want)].name:   # the loop of run_evaluation.py
+            multi.set_next_env()
+        with pytest.raises(AssertionError, match="Must reset environment"):
+            multi.step({"A": acts[0]})
+        single = ReferenceEnv(want, "eval", action_repeat=8, time_limit_steps=50, reset_mode="grid", device="cuda:0")
+        om, os_ = multi.reset(), single.reset()
+        assert np.array_equal(om["A"]["lidar"], os_["A"]["lidar"])
+        for a in acts:
+            m, s = multi.step({"A": a}), single.step({"A": a})
+            assert np.array_equal(m[0]["A"]["lidar"], s[0]["A"]["lidar"])
+            assert np.array_equal(m[0]["A"]["lidar_occupancy"], s[0]["A"]["lidar_occupancy"])
+            assert m[1] == s[1] and m[2] == s[2] and m[3]["A"]["progress"] == s[3]["A"]["progress"]
+            if m[2]["A"]:
+                break
+        occ = multi.scenario.world._maps["occupancy"]          # OccupancyMapObs would read the CURRENT track's map
+        pr, pc = occ.to_pixel(m[3]["A"]["pose"])
+        assert occ._map.shape == single.scenario.world._maps["occupancy"]._map.shape
+        single.close()
+    # order='sequential' [REF baselines/racing/experiments/acme/experiment.py:90-93]: next track at every reset
+    seq = ReferenceEnv(tracks[:2], "eval", action_repeat=4, reset_mode="grid", order="sequential", device="cuda:0")
+    names = []
+    for _ in range(4):
+        seq.reset()
+        names.append(seq.scenario.world._config.name)
+    assert names[0] == names[2] and names[1] == names[3] and names[0] != names[1]
+    # render: both views, the car in the middle (red), the track white under it
+    for mode in ("birds_eye", "follow"):
+        img = seq.render(mode=mode, agent="A")
+        assert img.shape == (200, 200, 3) and img.dtype == np.uint8
+        assert tuple(img[100, 100]) == (255, 0, 0) and (img == 255).all(axis=2).sum() > 500
+    with pytest.raises(ValueError):
+        seq.render(mode="nope")
+    seq.close()
+    multi.close()
