@@ -209,6 +209,7 @@ def main():
     ap.add_argument("--obs", default="", choices=["", "lidar", "lidar_occupancy"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-closed-loop", action="store_true", help="skip the on-device policy rollout leg")
+    ap.add_argument("--no-multi-agent", action="store_true", help="skip the four-cars-per-world leg (SURVEY §8-f3)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 200)")
     ap.add_argument("--e2e-shards", type=int, default=8, help="stream shards of the host-facing env")
     args = ap.parse_args()
@@ -375,6 +376,46 @@ def main():
             closed[pname] = leg
             cenv.close()
 
+    # ---- multi-agent worlds: the same car count as worlds of four cars that see and hit each other,
+    #      tasks of the baselines' scenario files (A maximize_progress, B..D n_step_progress), reset 'random_ball' ----
+    multi = None
+    if not args.no_multi_agent and n % 4 == 0:
+        from racing_dreamer_b200 import EnvConfig
+        mec = EnvConfig(tracks=TRACKS, n_envs=n, action_repeat=ACTION_REPEAT, obs_type=args.obs, auto_reset=True,
+                        reset_mode="random_ball", seed=SEED, env_id_offset=rank * n, time_limit_steps=2000 // ACTION_REPEAT,
+                        agents_per_world=4, agent_tasks=("maximize_progress",) + ("n_step_progress",) * 3)
+        menv = BatchedRaceEnv(mec, device=dev)
+        menv.reset()
+        ma_steps = min(args.steps, 300)
+        for k in range(args.warmup):
+            menv.step_raw(acts[k % PERIOD].data_ptr())
+        menv.read_stats(reset=True)
+        menv.enable_timing(True)
+        menv.read_timing(reset=True)
+        mev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ma_steps)]
+        barrier()
+        for k in range(ma_steps):
+            flush.zero_()
+            mev[k][0].record()
+            menv.step_raw(acts[(args.warmup + k) % PERIOD].data_ptr())
+            mev[k][1].record()
+        barrier()
+        tm_ = torch.tensor([float(sum(a.elapsed_time(b) for a, b in mev))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tm_, op=dist.ReduceOp.MAX)
+        mt = menv.read_timing(reset=True)
+        mstats = menv.read_stats()
+        contacts = int((menv.buf["opponents"] != 0).sum())
+        multi = {"value": world * n * ma_steps / (float(tm_[0]) / 1e3), "unit": "env-steps/s (cars)", "steps": ma_steps,
+                 "ms_per_step": float(tm_[0]) / ma_steps, "worlds_per_gpu": n // 4, "agents_per_world": 4,
+                 "kernel_ms": {"k_step_ma": mt["step_ms"] / max(1, mt["step_launches"]),
+                               "k_lidar": mt["lidar_ms"] / max(1, mt["lidar_launches"]),
+                               "k_occupancy": mt["occupancy_ms"] / max(1, mt["occupancy_launches"])},
+                 "cars_in_contact_last_step_rank0": contacts, "episode_stats_rank0": mstats,
+                 "note": "worlds of 4 cars (tasks A maximize_progress, B..D n_step_progress), scans see the other cars, "
+                         "world-level ActionRepeat/TimeLimit/reset; L2 flushed between steps"}
+        menv.close()
+
     # ---- the only collective of the system: episode statistics gathered across ranks at log cadence ----
     from racing_dreamer_b200.stats import gather_stats
     stats_all, _ = gather_stats(stats, device=dev)
@@ -410,6 +451,7 @@ def main():
             "clocks": clocks,
             "episode_stats": stats_all,
             "closed_loop": closed,
+            "multi_agent": multi,
         }
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1

@@ -15,6 +15,11 @@
  *     /root/reference and not installable offline; the reference has no tests or golden vectors.
  *     For those stages this file IS the specification (north_star: "a float64 ... rendition of the
  *     same model"), anchored on the reference's call sites and constants cited per function.
+ *   - multi-agent worlds: the dict-of-agents semantics (ActionRepeat stops when ANY agent is
+ *     done and sums per agent, TimeLimit sets every done, reset when any agent is done) are PINNED against the
+ *     unmodified reference wrappers (tests/golden/multi_agent_stack_golden.npz); car-car contact, the other
+ *     cars in the scans, rank, the n_step_progress task and the random_ball reset are racecar_gym arithmetic
+ *     -> **PARITY UNPINNED**, [NEW-SPEC] here.
  *
  * Build: gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC (oracle/Makefile).  No FMA contraction:
  * every floating-point operation below is one IEEE-754 operation in the order written.

@@ -241,6 +241,7 @@ __device__ __forceinline__ void rd_write_obs(const StepParams& P, const OutPtrs&
 }
 
 __global__ void __launch_bounds__(128) k_reset(StepParams P, OutPtrs o, const uint8_t* __restrict__ mask, int mode) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // k_lidar may start its set-up (see launch_lidar_t)
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= P.n) return;
   const int n = P.n;
@@ -265,6 +266,7 @@ __global__ void __launch_bounds__(128) k_reset(StepParams P, OutPtrs o, const ui
 
 // envs [e0, e1) of the batch (the host-facing path steps the batch in chunks on several streams)
 __global__ void __launch_bounds__(128) k_step(StepParams P, OutPtrs o, const float* __restrict__ actions, int e0, int e1) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // k_lidar may start its set-up (see launch_lidar_t)
   const int e = e0 + blockIdx.x * blockDim.x + threadIdx.x;
   const int n = P.n;
   const rd_config& cfg = P.cfg;
@@ -412,6 +414,7 @@ __global__ void __launch_bounds__(128) k_step_ma(StepParams P, OutPtrs o, const 
   __shared__ double sh_pose[128 * 4];
   __shared__ double sh_prog[128];
   __shared__ int sh_flag[128];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // k_lidar may start its set-up (see launch_lidar_t)
   const int n = P.n;
   const rd_config& cfg = P.cfg;
   const int A = cfg.agents_per_world > 1 ? cfg.agents_per_world : 1;

@@ -48,6 +48,7 @@ struct rd_env {
   int device = 0;
   int sm_count = 0;
   int smem_optin = 0;             // max dynamic shared memory per CTA (opt-in), bytes
+  bool lidar_pdl = true;          // k_lidar is launched as a programmatic dependent of the kernel in front of it (RD_LIDAR_PDL=0: off)
   bool lidar_attr_set[2] = {false, false};  // k_lidar<16>, k_lidar<32> opted in to smem_optin
   int n = 0;
   int step_block = 128;           // k_step threads per CTA (small batches: fewer, so that every SM gets a warp)
@@ -260,7 +261,19 @@ int launch_lidar_t(rd_env* env, int map_id, const OriginRec* recs, const int32_t
   if (grid < 1) return RD_OK;
   {
     ScopedTiming tm(env, s, T_LIDAR);
-    kern<<<(unsigned)grid, WARPS * 32, smem, s>>>(env->d_maps, map_id, recs, order, n_env, lp, env->d_beam_tab, out, ctr);
+    // Programmatic dependent launch: k_lidar's set-up (mbarrier, the bulk copy of the map into shared memory, the beam
+    // table, the first draw from the work counter) overlaps the tail of the kernel in front of it on the stream
+    // (k_step / k_reset trigger early with griddepcontrol.launch_dependents); k_lidar executes griddepcontrol.wait before
+    // it touches the origin records.
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(WARPS * 32); lc.dynamicSmemBytes = smem; lc.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = env->lidar_pdl ? 1 : 0;
+    const DevMap* a_maps = env->d_maps; const double* a_tab = env->d_beam_tab;
+    cudaError_t le = cudaLaunchKernelEx(&lc, kern, a_maps, map_id, recs, order, n_env, lp, a_tab, out, ctr);
+    if (le != cudaSuccess) { cudaGetLastError(); return fail(env, RD_ERR_CUDA, "k_lidar launch: %s", cudaGetErrorString(le)); }
   }
   env->launches++;
   CUDA_TRY(env, cudaGetLastError());
@@ -427,6 +440,7 @@ RD_API int rd_create(const rd_config* cfg, rd_env** out) {
   // k_step is one long float64 instruction stream per warp: spread the warps over as many SM sub-partitions as the
   // batch allows (RD_STEP_BLOCK overrides, tuning)
   env->step_block = (env->n >= 128 * 4 * env->sm_count) ? 128 : ((env->n >= 64 * 4 * env->sm_count) ? 64 : 32);
+  if (const char* ev = std::getenv("RD_LIDAR_PDL")) env->lidar_pdl = std::atoi(ev) != 0;
   if (const char* ev = std::getenv("RD_STEP_BLOCK")) { int v = std::atoi(ev); if (v == 32 || v == 64 || v == 128) env->step_block = v; }
   const size_t n = (size_t)env->n;
   cudaError_t e = cudaSuccess;

@@ -13,6 +13,13 @@
 #pragma once
 #include "rd_common.cuh"
 
+#ifndef RD_LIDAR_CHUNK
+#define RD_LIDAR_CHUNK 2   // work items a warp draws from the global counter at a time (see k_lidar)
+#endif
+#ifndef RD_LIDAR_PREFETCH
+#define RD_LIDAR_PREFETCH 0  // 1: draw the next chunk while the current one is marched; 2: the same, but not near the end
+#endif
+
 __device__ __forceinline__ float rd_finish_range(const LidarParams& lp, float r, const OriginRec& rec, uint32_t beam) {
   if (lp.noise > 0.0f) {
     uint32_t c[4] = {rec.gid, rec.episode, rec.step, beam};
@@ -92,6 +99,11 @@ k_lidar(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict
     }
   }
   for (int i = threadIdx.x; i < 2 * lp.n_beams; i += WARPS * 32) tab[i] = __ldg(beam_tab + i);
+  // first draw from the work counter: in flight while the map arrives
+  const int lane = threadIdx.x & 31;
+  unsigned ahead = 0;
+  bool have_ahead = true;
+  if (lane == 0) ahead = atomicAdd(ctr, (unsigned)RD_LIDAR_CHUNK);
   MarchGrid grid;
   grid.bits = bits;
   grid.coarse = reinterpret_cast<const uint8_t*>(bits) + m.coarse_off;
@@ -100,24 +112,30 @@ k_lidar(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict
   grid.cshift = m.cshift;
   __syncthreads();
   rd_mbar_wait(bar, 0);
+  // everything above only read launch-invariant data; the origin records come from the kernel in front of this one
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
-  const int lane = threadIdx.x & 31;
   const unsigned total_items = (unsigned)n_env * (unsigned)lp.groups;
   // Scheduling: items are handed out through a global counter, RD_LIDAR_CHUNK at a time, so warps that drew long rays
   // do not hold the kernel up.  Measured on B200 (Austria, 4096 envs): chunk 2 beats 4, 8, a guided (shrinking) chunk
   // and a static round-robin with a dynamic tail (profiles/r01_lidar_variants.txt).
-#ifndef RD_LIDAR_CHUNK
-#define RD_LIDAR_CHUNK 2
-#endif
+  // RD_LIDAR_PREFETCH (measured on B200, profiles/r01v_lidar_prefetch.txt): drawing the NEXT chunk while the current one
+  // is marched hides the atomic's L2 round trip but lets busy warps sit on work near the end of the launch; variant 2
+  // stops drawing ahead once the remaining items are fewer than one more round of draws by every warp.
   unsigned item = 0, last = 0;
+  const unsigned tail_margin = (unsigned)gridDim.x * WARPS * RD_LIDAR_CHUNK * 2u;
   for (;;) {
     if (item >= last) {
       const unsigned chunk = RD_LIDAR_CHUNK;
-      unsigned t = 0;
-      if (lane == 0) t = atomicAdd(ctr, chunk);
-      item = __shfl_sync(0xffffffffu, t, 0);
+      if (!have_ahead && lane == 0) ahead = atomicAdd(ctr, chunk);
+      item = __shfl_sync(0xffffffffu, ahead, 0);
+      have_ahead = false;
       if (item >= total_items) break;
       last = min(item + chunk, total_items);
+      if (RD_LIDAR_PREFETCH == 1 || (RD_LIDAR_PREFETCH == 2 && item + tail_margin < total_items)) {
+        if (lane == 0) ahead = atomicAdd(ctr, chunk);
+        have_ahead = true;
+      }
     }
     {
       const unsigned slot = item / (unsigned)lp.groups;

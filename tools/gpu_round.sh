@@ -12,14 +12,14 @@ echo "== bench reference"; timeout 600 python bench.py --impl reference --steps 
 echo "== bench occupancy (config 3 shape, 16384 envs)"; timeout 900 python bench.py --obs lidar_occupancy --envs 16384 --steps 50 --warmup 5 --no-cpu-baseline > $OUT/bench_occ.json 2> $OUT/bench_occ.err; echo "rc=$?"; cat $OUT/bench_occ.json; tail -3 $OUT/bench_occ.err
 echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
-   python bench.py --steps 20 --warmup 3 --no-cpu-baseline --e2e-steps 5 > $OUT/ncu_launches.log 2>&1; echo "rc=$?"
+   python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-closed-loop --no-multi-agent --e2e-steps 5 > $OUT/ncu_launches.log 2>&1; echo "rc=$?"
 echo "== ncu full k_lidar"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_lidar -s 5 -c 2 -o $OUT/prof_lidar -f \
-   python bench.py --steps 10 --warmup 3 --no-cpu-baseline --e2e-steps 2 > $OUT/ncu_lidar.log 2>&1; echo "rc=$?"
+   python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-closed-loop --no-multi-agent --e2e-steps 2 > $OUT/ncu_lidar.log 2>&1; echo "rc=$?"
 echo "== ncu full k_step"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_step -s 5 -c 2 -o $OUT/prof_step -f \
-   python bench.py --steps 10 --warmup 3 --no-cpu-baseline --e2e-steps 2 > $OUT/ncu_step.log 2>&1; echo "rc=$?"
+   python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-closed-loop --no-multi-agent --e2e-steps 2 > $OUT/ncu_step.log 2>&1; echo "rc=$?"
 echo "== ncu full k_occupancy"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_occupancy -s 2 -c 1 -o $OUT/prof_occ -f \
-   python bench.py --obs lidar_occupancy --envs 4096 --steps 4 --warmup 3 --no-cpu-baseline --e2e-steps 2 > $OUT/ncu_occ.log 2>&1; echo "rc=$?"
+   python bench.py --obs lidar_occupancy --envs 4096 --steps 4 --warmup 3 --no-cpu-baseline --no-closed-loop --no-multi-agent --e2e-steps 2 > $OUT/ncu_occ.log 2>&1; echo "rc=$?"
 ls -la $OUT
