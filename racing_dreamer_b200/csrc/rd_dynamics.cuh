@@ -86,14 +86,44 @@ __device__ __forceinline__ void st_rhs(const rd_vehicle& p, const double (&q)[7]
   }
 }
 
+#ifndef RD_STEP_MAP_LOCAL
+#define RD_STEP_MAP_LOCAL 1    // 1: the track descriptor is copied into registers once per step instead of being re-read
+#endif                         //    from global memory by every probe of the tick loop (long-scoreboard stalls)
+#if RD_STEP_MAP_LOCAL
+#define RD_STEP_MAP_T const DevMap
+#else
+#define RD_STEP_MAP_T const DevMap&
+#endif
+#ifndef RD_STEP_STAGE_LOOP
+#define RD_STEP_STAGE_LOOP 1   // 1: the four RK4 stages share ONE copy of the RHS code (rolled loop); 0: four inlined copies
+#endif
 __device__ __forceinline__ void st_tick(const rd_config& cfg, double (&q)[7], double motor, double steering, double inv_dt) {
   const rd_vehicle& p = cfg.vehicle;
   const double dt = cfg.dt;
   double target = steering * p.steer_gain * p.steer_max;
   double sv = (target - q[2]) * inv_dt;
   double acc = (motor >= 0.0) ? (motor * p.a_drive - p.c_drag * q[3]) : (motor * p.a_brake - p.c_drag * q[3]);
-  double k1[7], k2[7], k3[7], k4[7], t[7];
   const double h2 = 0.5 * dt, h6 = dt / 6.0;
+#if RD_STEP_STAGE_LOOP
+  // One RHS body executed four times instead of four inlined copies: the tick loop's code shrinks ~3.5x and stays in
+  // the instruction cache (k_step runs one warp per SM sub-partition; ncu showed 9 % no-instruction stalls).  Same
+  // operations in the same order as the unrolled form: stage input q + c*k with c = (0, h/2, h/2, h) and k = 0 before
+  // the first stage (q + 0*0 == q), sum ((1*k1 + 2*k2) + 2*k3) + 1*k4 (0 + 1*k1 == k1, products by 1 and 2 are exact).
+  double k[7] = {0, 0, 0, 0, 0, 0, 0}, sum[7] = {0, 0, 0, 0, 0, 0, 0}, t[7];
+#pragma unroll 1
+  for (int st = 0; st < 4; ++st) {
+    const double c = st == 0 ? 0.0 : (st == 3 ? dt : h2);
+    const double w = (st == 0 || st == 3) ? 1.0 : 2.0;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) t[i] = q[i] + c * k[i];
+    st_rhs(p, t, sv, acc, k);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) sum[i] = sum[i] + w * k[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 7; ++i) q[i] = q[i] + h6 * sum[i];
+#else
+  double k1[7], k2[7], k3[7], k4[7], t[7];
   st_rhs(p, q, sv, acc, k1);
 #pragma unroll
   for (int i = 0; i < 7; ++i) t[i] = q[i] + h2 * k1[i];
@@ -106,6 +136,7 @@ __device__ __forceinline__ void st_tick(const rd_config& cfg, double (&q)[7], do
   st_rhs(p, t, sv, acc, k4);
 #pragma unroll
   for (int i = 0; i < 7; ++i) q[i] = q[i] + h6 * (((k1[i] + 2.0 * k2[i]) + 2.0 * k3[i]) + k4[i]);
+#endif
 }
 
 __device__ __forceinline__ int rd_checkpoint_of(const rd_config& cfg, double p) {
@@ -284,7 +315,7 @@ __global__ void __launch_bounds__(128) k_step(StepParams P, OutPtrs o, const flo
       if (o.flags) o.flags[e] = (uint8_t)flags;
       P.recs[e].was_reset = 2;
     } else {
-      const DevMap& m = P.maps[I[(size_t)RD_I_MAP * n + e]];
+      RD_STEP_MAP_T m = P.maps[I[(size_t)RD_I_MAP * n + e]];
       // a4 [REF dreamer/wrappers.py:129-134; baselines single_agent.py:55-56]: numpy keeps (action+1)/2 of a
       // float32 policy output in float32 and promotes to float64 at `* (high-low)` (float64 arrays).
       double a[2];
@@ -433,7 +464,7 @@ __global__ void __launch_bounds__(128) k_step_ma(StepParams P, OutPtrs o, const 
   const int ncp = cfg.n_checkpoints;
   const double inv_dt = 1.0 / cfg.dt;
   const double hl = 0.5 * cfg.vehicle.body_length, hw = 0.5 * cfg.vehicle.body_width;
-  const DevMap& m = P.maps[run ? I[(size_t)RD_I_MAP * n + e] : 0];
+  RD_STEP_MAP_T m = P.maps[run ? I[(size_t)RD_I_MAP * n + e] : 0];
   double act[2] = {0.0, 0.0};
   double q[7] = {0, 0, 0, 0, 0, 0, 0};
   double time = 0.0, p = 0.0, last = 0.0, total = 0.0;
