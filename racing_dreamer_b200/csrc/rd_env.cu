@@ -49,7 +49,7 @@ struct rd_env {
   int sm_count = 0;
   int smem_optin = 0;             // max dynamic shared memory per CTA (opt-in), bytes
   bool lidar_pdl = true;          // k_lidar is launched as a programmatic dependent of the kernel in front of it (RD_LIDAR_PDL=0: off)
-  bool lidar_attr_set[2] = {false, false};  // k_lidar<16>, k_lidar<32> opted in to smem_optin
+  bool lidar_attr_set[4] = {false, false, false, false};  // k_lidar<16|32, ahead> opted in to smem_optin
   int n = 0;
   int step_block = 128;           // k_step threads per CTA (small batches: fewer, so that every SM gets a warp)
   double* d_f64 = nullptr;
@@ -234,17 +234,17 @@ LidarParams lidar_params(const rd_env* env, const DevMap& m) {
 }
 
 // LiDAR launch for the envs of one map: persistent CTAs, grid = resident CTAs on all SMs.
-template <int WARPS>
+template <int WARPS, bool AHEAD>
 int launch_lidar_t(rd_env* env, int map_id, const OriginRec* recs, const int32_t* order, int n_env, float* out,
                    cudaStream_t s, unsigned int* ctr) {
   const DevMap& m = env->maps[map_id].dev;
   LidarParams lp = lidar_params(env, m);
   const size_t tab_bytes = ((size_t)2 * lp.n_beams * 8 + 15) & ~(size_t)15;
   const size_t smem = 16 + tab_bytes + (size_t)m.bits_bytes;
-  auto kern = k_lidar<WARPS>;
+  auto kern = k_lidar<WARPS, AHEAD>;
   int& per_sm = env->maps[map_id].lidar_per_sm;
   if (per_sm < 0) {  // once per map: ask how many CTAs fit on an SM (the kernel is opted in to the device maximum)
-    bool& attr = env->lidar_attr_set[WARPS == 32 ? 1 : 0];
+    bool& attr = env->lidar_attr_set[(WARPS == 32 ? 1 : 0) + (AHEAD ? 2 : 0)];
     if (!attr) {
       CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_optin));
       attr = true;
@@ -284,9 +284,17 @@ int launch_lidar(rd_env* env, int map_id, const OriginRec* recs, const int32_t* 
                  cudaStream_t s, unsigned int* ctr = nullptr) {
   const DevMap& m = env->maps[map_id].dev;
   if (!ctr) ctr = env->d_lidar_ctr;
-  // small maps: 16-warp CTAs (several per SM); large maps: 32-warp CTAs so one resident copy feeds 32 warps
-  if (m.bits_bytes > 72 * 1024) return launch_lidar_t<32>(env, map_id, recs, order, n_env, out, s, ctr);
-  return launch_lidar_t<16>(env, map_id, recs, order, n_env, out, s, ctr);
+  // small maps: 16-warp CTAs (several per SM); large maps: 32-warp CTAs so one resident copy feeds 32 warps.
+  // Long launches (>= 128 work items per resident warp) draw their work one chunk ahead (see k_lidar).
+  const int warps = m.bits_bytes > 72 * 1024 ? 32 : 16;
+  const int per_sm = env->maps[map_id].lidar_per_sm > 0 ? env->maps[map_id].lidar_per_sm : 1;
+  const long long items = (long long)n_env * ((env->cfg.n_beams + 31) / 32);
+  bool ahead = items >= 128ll * env->sm_count * per_sm * warps;
+  if (const char* ev = std::getenv("RD_LIDAR_AHEAD")) ahead = std::atoi(ev) != 0;
+  if (warps == 32) return ahead ? launch_lidar_t<32, true>(env, map_id, recs, order, n_env, out, s, ctr)
+                                : launch_lidar_t<32, false>(env, map_id, recs, order, n_env, out, s, ctr);
+  return ahead ? launch_lidar_t<16, true>(env, map_id, recs, order, n_env, out, s, ctr)
+               : launch_lidar_t<16, false>(env, map_id, recs, order, n_env, out, s, ctr);
 }
 
 int launch_occupancy(rd_env* env, int map_id, const OriginRec* recs, const double* poses_xyyaw,

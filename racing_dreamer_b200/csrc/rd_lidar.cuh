@@ -16,9 +16,15 @@
 #ifndef RD_LIDAR_CHUNK
 #define RD_LIDAR_CHUNK 2   // work items a warp draws from the global counter at a time (see k_lidar)
 #endif
-#ifndef RD_LIDAR_PREFETCH
-#define RD_LIDAR_PREFETCH 0  // 1: draw the next chunk while the current one is marched; 2: the same, but not near the end
-#endif
+
+// atomicAdd whose result is NOT needed right away.  For an atomic on a provably warp-uniform address ptxas emits its
+// warp-aggregation pattern (leader ATOMG + SHFL of the result right behind it), which waits for the L2 round trip on the
+// spot and defeats drawing the next work chunk ahead of time; the (always zero) threadIdx.y offset hides the uniformity.
+__device__ __forceinline__ unsigned rd_atom_add(unsigned int* p, unsigned v) {
+  unsigned old;
+  asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p + threadIdx.y), "r"(v) : "memory");  // blockDim.y == 1
+  return old;
+}
 
 __device__ __forceinline__ float rd_finish_range(const LidarParams& lp, float r, const OriginRec& rec, uint32_t beam) {
   if (lp.noise > 0.0f) {
@@ -74,7 +80,7 @@ __device__ __forceinline__ float rd_car_hit(const LidarParams& lp, int px, int p
 // smem layout: [0,16) mbarrier | beam table 2*n_beams f64 (cos then sin) | bit grid | block clearance field
 // The tail of the item list is handed out through a global counter (ctr[0]); the last CTA to finish (ticket ctr[1])
 // re-arms both for the next launch on the stream.
-template <int WARPS>
+template <int WARPS, bool AHEAD>
 __global__ void __launch_bounds__(WARPS * 32)
 k_lidar(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict__ recs,
         const int32_t* __restrict__ env_order, int n_env, LidarParams lp, const double* __restrict__ beam_tab,
@@ -103,7 +109,7 @@ k_lidar(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict
   const int lane = threadIdx.x & 31;
   unsigned ahead = 0;
   bool have_ahead = true;
-  if (lane == 0) ahead = atomicAdd(ctr, (unsigned)RD_LIDAR_CHUNK);
+  if (lane == 0) ahead = rd_atom_add(ctr, (unsigned)RD_LIDAR_CHUNK);
   MarchGrid grid;
   grid.bits = bits;
   grid.coarse = reinterpret_cast<const uint8_t*>(bits) + m.coarse_off;
@@ -119,21 +125,21 @@ k_lidar(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict
   // Scheduling: items are handed out through a global counter, RD_LIDAR_CHUNK at a time, so warps that drew long rays
   // do not hold the kernel up.  Measured on B200 (Austria, 4096 envs): chunk 2 beats 4, 8, a guided (shrinking) chunk
   // and a static round-robin with a dynamic tail (profiles/r01_lidar_variants.txt).
-  // RD_LIDAR_PREFETCH (measured on B200, profiles/r01v_lidar_prefetch.txt): drawing the NEXT chunk while the current one
-  // is marched hides the atomic's L2 round trip but lets busy warps sit on work near the end of the launch; variant 2
-  // stops drawing ahead once the remaining items are fewer than one more round of draws by every warp.
+  // AHEAD: the next chunk is drawn while the current one is marched, so the atomic's L2 round trip (11 % of the warps'
+  // time in the ncu source view, profiles/r01x_ncu_k_lidar_lines.txt) is off the critical path -- but every warp then
+  // sits on one more chunk at the end of the launch.  Measured on B200 (profiles/r01y_lidar_prefetch.txt): +3.5 % at
+  // 470 items per warp (65536 envs), -4 % at 29 items per warp (4096 envs); the host picks per launch.
   unsigned item = 0, last = 0;
-  const unsigned tail_margin = (unsigned)gridDim.x * WARPS * RD_LIDAR_CHUNK * 2u;
   for (;;) {
     if (item >= last) {
       const unsigned chunk = RD_LIDAR_CHUNK;
-      if (!have_ahead && lane == 0) ahead = atomicAdd(ctr, chunk);
+      if (!have_ahead && lane == 0) ahead = rd_atom_add(ctr, chunk);
       item = __shfl_sync(0xffffffffu, ahead, 0);
       have_ahead = false;
       if (item >= total_items) break;
       last = min(item + chunk, total_items);
-      if (RD_LIDAR_PREFETCH == 1 || (RD_LIDAR_PREFETCH == 2 && item + tail_margin < total_items)) {
-        if (lane == 0) ahead = atomicAdd(ctr, chunk);
+      if (AHEAD) {
+        if (lane == 0) ahead = rd_atom_add(ctr, chunk);
         have_ahead = true;
       }
     }
