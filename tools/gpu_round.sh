@@ -17,8 +17,11 @@ echo "== ncu full k_lidar"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_lidar -s 5 -c 2 -o $OUT/prof_lidar -f \
    python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-closed-loop --no-multi-agent --e2e-steps 2 > $OUT/ncu_lidar.log 2>&1; echo "rc=$?"
 echo "== ncu full k_step"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_step -s 5 -c 2 -o $OUT/prof_step -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k k_step -s 5 -c 2 -o $OUT/prof_step -f \
    python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-closed-loop --no-multi-agent --e2e-steps 2 > $OUT/ncu_step.log 2>&1; echo "rc=$?"
+echo "== ncu full k_step_ma (worlds of 4 cars)"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_step_ma -s 5 -c 1 -o $OUT/prof_step_ma -f \
+   python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-closed-loop --e2e-steps 2 > $OUT/ncu_step_ma.log 2>&1; echo "rc=$?"
 echo "== ncu full k_occupancy"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_occupancy -s 2 -c 1 -o $OUT/prof_occ -f \
    python bench.py --obs lidar_occupancy --envs 4096 --steps 4 --warmup 3 --no-cpu-baseline --no-closed-loop --no-multi-agent --e2e-steps 2 > $OUT/ncu_occ.log 2>&1; echo "rc=$?"
