@@ -223,6 +223,12 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
 
+    # stdout carries exactly ONE JSON line: anything native libraries print on fd 1 meanwhile (NCCL's version banner
+    # when NCCL_DEBUG is set on the box) goes to stderr instead.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from racing_dreamer_b200 import BatchedRaceEnv
@@ -464,7 +470,8 @@ def main():
                                               f"{threads} OpenMP threads, {dt:.1f} s"}
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     henv.close()
     env.close()
     if world > 1:
