@@ -299,7 +299,7 @@ def main():
 
     # ---- e2e: host numpy actions -> pinned -> H2D -> step -> D2H of all results -> numpy ----
     e2e_steps = args.e2e_steps or min(args.steps, 200)
-    henv = HostSteppedEnv(env_config(n, rank, args.obs), device=dev, n_shards=args.e2e_shards)
+    henv = HostSteppedEnv(env_config(n, rank, args.obs), device=dev, n_shards=args.e2e_shards, bind_cpu=world > 1)
     hacts = scripted_actions(n, rank)
     henv.reset()
     for k in range(5):

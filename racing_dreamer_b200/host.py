@@ -11,6 +11,7 @@ pinned mirrors (valid until the next call).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -28,9 +29,36 @@ _FIELDS = {"lidar": ("lidar_dev", np.float32), "occupancy": ("occupancy_dev", np
            "rank": ("rank_dev", np.int32), "opponents": ("opponents_dev", np.uint8)}
 
 
+def bind_to_gpu_cpus(device_index: int) -> Optional[list]:
+    """Restrict this process to the CPU cores NVML reports as local to GPU `device_index` (same NUMA node / PCIe root),
+    so that the pinned result buffers allocated next are first-touched on that node and the device->host copies of one
+    rank do not cross the socket interconnect.  Returns the core list, or None when NVML / sched_setaffinity is missing
+    or the mask is empty (then nothing is changed)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 class HostSteppedEnv:
-    def __init__(self, config: EnvConfig, device=None, n_shards: int = 8):
-        """n_shards: env-chunks the observation kernels and their device->host copies are pipelined over."""
+    def __init__(self, config: EnvConfig, device=None, n_shards: int = 8, bind_cpu: bool = False):
+        """n_shards: env-chunks the observation kernels and their device->host copies are pipelined over.
+        bind_cpu: pin this PROCESS to the GPU's local cores first (multi-GPU boxes, one process per GPU)."""
+        self.cpus = None
+        if bind_cpu:
+            import torch as _t
+            d = _t.device(device if device is not None else f"cuda:{_t.cuda.current_device()}")
+            self.cpus = bind_to_gpu_cpus(d.index if d.index is not None else _t.cuda.current_device())
         self.env = BatchedRaceEnv(config, device=device)
         self.n = self.env.n
         self.device = self.env.device
