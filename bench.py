@@ -135,6 +135,23 @@ def measured_peak_gbs():
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
+def ncu_on_chip(config_id, n_envs, kernel, sm_count=148):
+    """The on-chip picture of `kernel` from the committed ncu capture (SURVEY.md §8-d asks for both): issue-slot
+    utilisation and the share of the shared-memory pipe its wavefronts use; None without a matching capture."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
+            ent = json.load(f).get(f"config{config_id}", {}).get(kernel)
+        if ent and int(ent["envs"]) == int(n_envs) and "issue_active_pct" in ent:
+            return {"bound": "issue slots", "issue_active_pct": ent["issue_active_pct"],
+                    "active_lanes_per_warp_inst": ent["active_lanes_per_inst"],
+                    "warp_inst_per_beam_group": ent["warp_inst_executed"] / (n_envs * ((N_BEAMS + 31) // 32)),
+                    "smem_pipe_frac": ent["smem_wavefronts"] / (sm_count * ent["sm_cycles_elapsed"]),
+                    "source": ent["source"] + " (ncu --set full, one launch)"}
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 def ncu_traffic(config_id, n_envs, kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/ncu_traffic.json), or None when no
     capture matches this workload."""
@@ -446,7 +463,8 @@ def main():
                          "kernel_ms": lidar_ms, "kernel_share_of_step": timing["lidar_ms"] / max(gpu_ms, 1e-9),
                          "algorithmic_bytes_per_launch": LIDAR_BYTES_PER_ENV * n,
                          "step_algorithmic_gbs": ALGO_BYTES_PER_ENV_STEP * value / world / 1e9,
-                         "note": "on-chip bound (shared-memory bit tests + issue slots), see DESIGN.md"},
+                         "on_chip": ncu_on_chip(args.config, n, "k_lidar"),
+                         "note": "on-chip bound (instruction issue; the map lives in shared memory), see DESIGN.md"},
             "kernel_ms": {"k_step": timing["step_ms"] / max(1, timing["step_launches"]), "k_lidar": lidar_ms,
                           "k_occupancy": timing["occupancy_ms"] / max(1, timing["occupancy_launches"])},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": henv.h2d_bytes_per_step,

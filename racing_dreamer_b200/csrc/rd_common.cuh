@@ -40,6 +40,7 @@ struct __align__(16) OriginRec {
 struct LidarParams {
   int n_beams;
   int groups;            // ceil(n_beams / 32)
+  unsigned groups_magic; // ceil(2^32 / groups): item / groups == umulhi(item, groups_magic) (k_lidar)
   int normalize;         // RD_OBS_LIDAR_NORM
   float range_min, range_max, noise;
   float scale;           // metres per (sub-cell / direction unit) = 2^(DIR-SUB) * resolution

@@ -212,6 +212,7 @@ LidarParams lidar_params(const rd_env* env, const DevMap& m) {
   LidarParams lp{};
   lp.n_beams = c.n_beams;
   lp.groups = (c.n_beams + 31) / 32;
+  lp.groups_magic = lp.groups > 1 ? (unsigned)(((1ull << 32) + (unsigned)lp.groups - 1) / (unsigned)lp.groups) : 0u;
   lp.normalize = (c.obs_flags & RD_OBS_LIDAR_NORM) ? 1 : 0;
   lp.range_min = (float)c.lidar_range_min;
   lp.range_max = (float)c.lidar_range_max;

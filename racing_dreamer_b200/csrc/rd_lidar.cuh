@@ -144,7 +144,10 @@ k_lidar(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict
       }
     }
     {
-      const unsigned slot = item / (unsigned)lp.groups;
+      // item / groups by a multiply: groups_magic = ceil(2^32 / groups) (exact for item < 2^32 / groups; one fix-up
+      // step covers the rest of the 31-bit range)
+      unsigned slot = lp.groups_magic ? __umulhi(item, lp.groups_magic) : item;   // magic 0: one group per env
+      if (item - slot * (unsigned)lp.groups >= (unsigned)lp.groups) --slot;      // the estimate never falls short
       const int g = (int)(item - slot * (unsigned)lp.groups);
       const int env = env_order ? __ldg(env_order + slot) : (int)slot;
       const OriginRec rec = recs[env];

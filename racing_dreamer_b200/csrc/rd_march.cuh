@@ -57,12 +57,15 @@ RD_HD MarchResult rd_march(const MarchGrid& g, int px, int py, int DX, int DY, l
 
   // ---- phase 1: clearance jumps in the ray parameter U (whole cells) ----
   const int ulim = (int)(rsub >> RD_SUB_BITS);
-  const int bxj = adx != 0 ? bx : 0x7fffffff;  // no x-crossings at all when adx == 0
-  const int byj = ady != 0 ? by : 0x7fffffff;
+  // crossing counts at parameter U: i(U) = #{m >= 0 : bx + m*4096 <= X} with X = floor(U*adx / 64).  Since 0 <= bx <= 4096
+  // and X >= 0, that is (X + 4096 - bx) >> 12 with no case split (for X < bx the sum stays in [0, 4095]); an axis the
+  // ray does not move along (adx == 0 -> X == 0) gets the offset 0 and therefore the count 0.
+  const int cxj = adx != 0 ? RD_SUB - bx : 0;
+  const int cyj = ady != 0 ? RD_SUB - by : 0;
   // crossing counts at U = 0: 1 when the origin lies exactly on the cell edge it is about to cross (b == 0), so that
   // (i, j) == (i(U), j(U)) holds from the start and a jump of D-1 never moves the cell index by more than D-1
   int U = 0, njump = 0;
-  int i = bxj == 0 ? 1 : 0, j = byj == 0 ? 1 : 0;
+  int i = cxj >> RD_SUB_BITS, j = cyj >> RD_SUB_BITS;
   int ix = ix0 + sx * i, iy = iy0 + sy * j;
   for (;;) {
     const int D = g.coarse[(iy >> g.cshift) * g.cw + (ix >> g.cshift)];
@@ -71,8 +74,8 @@ RD_HD MarchResult rd_march(const MarchGrid& g, int px, int py, int DX, int DY, l
     U = Un;
     const int X = (int)(((unsigned)U * (unsigned)adx) >> 6);  // U <= 2^13, adx <= 2^18: fits
     const int Y = (int)(((unsigned)U * (unsigned)ady) >> 6);
-    i = X >= bxj ? ((X - bxj) >> RD_SUB_BITS) + 1 : 0;
-    j = Y >= byj ? ((Y - byj) >> RD_SUB_BITS) + 1 : 0;
+    i = (X + cxj) >> RD_SUB_BITS;
+    j = (Y + cyj) >> RD_SUB_BITS;
     ix = ix0 + sx * i;
     iy = iy0 + sy * j;
     ++njump;
