@@ -196,6 +196,13 @@ int rd_step(rd_env* env, const float* actions_dev, const rd_outputs* out, void* 
 int rd_host_init(rd_env* env, int n_chunks, rd_outputs* host_out);
 int rd_reset_host(rd_env* env, const uint8_t* mask_host, int mode);
 int rd_step_host(rd_env* env, const float* actions_host);
+/* Split form for callers that keep several env groups in flight (one handle per group, e.g. two half-batches whose policy
+ * evaluations and copies overlap -- the asynchronous vector-env pattern): rd_step_host_begin copies the actions and
+ * enqueues the whole step (kernels + device->host copies) without waiting, rd_step_host_end blocks until that step's
+ * results are in the host buffers.  rd_step_host == begin + end.  One step may be pending per handle; the host buffers of
+ * a handle must not be read between its begin and end. */
+int rd_step_host_begin(rd_env* env, const float* actions_host);
+int rd_step_host_end(rd_env* env);
 
 /* ---- on-device policies (policy-in-the-loop rollouts without a host round trip) ----
  * Follow-the-gap controller: replaces AgentNode.laserscan_callback + publish_drive_from_heading + PID.calculate

@@ -119,7 +119,7 @@ EXPORTS = (
     "rd_default_config", "rd_create", "rd_destroy", "rd_last_error", "rd_abi_version", "rd_upload_map",
     "rd_assign_maps", "rd_reset", "rd_step", "rd_lidar_cast", "rd_occupancy_obs", "rd_dynamics",
     "rd_get_state", "rd_set_state", "rd_read_stats", "rd_launch_count", "rd_enable_timing", "rd_read_timing",
-    "rd_host_init", "rd_reset_host", "rd_step_host",
+    "rd_host_init", "rd_reset_host", "rd_step_host", "rd_step_host_begin", "rd_step_host_end",
     "rd_gap_follower_defaults", "rd_policy_gap_follower_init", "rd_policy_gap_follower", "rd_rollout_gap_follower",
     "rd_policy_dreamer_init", "rd_policy_dreamer", "rd_policy_dreamer_get_state", "rd_policy_dreamer_set_state",
     "rd_rollout_dreamer",
@@ -173,6 +173,10 @@ def load_library() -> C.CDLL:
     lib.rd_reset_host.restype = i32
     lib.rd_step_host.argtypes = [vp, vp]
     lib.rd_step_host.restype = i32
+    lib.rd_step_host_begin.argtypes = [vp, vp]
+    lib.rd_step_host_begin.restype = i32
+    lib.rd_step_host_end.argtypes = [vp]
+    lib.rd_step_host_end.restype = i32
     lib.rd_lidar_cast.argtypes = [vp, vp, vp, i32, vp, vp]
     lib.rd_lidar_cast.restype = i32
     lib.rd_occupancy_obs.argtypes = [vp, vp, vp, i32, vp, vp]

@@ -87,6 +87,7 @@ struct rd_env {
     uint8_t* occ_dev = nullptr; uint8_t* occ_host = nullptr;
     unsigned int* ctr = nullptr;             // [n_chunks][2] k_lidar work counters, one pair per stream
     bool zero_copy = false;                  // k_lidar stores straight into the pinned host mirror (no staging copy)
+    bool pending = false;                    // rd_step_host_begin enqueued a step whose results rd_step_host_end has not awaited
     rd_outputs dev_out{}, host_out{};
   } hp;
   // on-device follow-the-gap controller (rd_policy_gap_follower_init)
@@ -668,13 +669,26 @@ RD_API int rd_host_init(rd_env* env, int n_chunks, rd_outputs* host_out) {
   h.n_chunks = n_chunks;
   h.bounds.resize(n_chunks + 1);
   // progressive chunk sizes (1 : 2 : 4 : ... capped at 8x): the first chunk is small so that the copy engine starts
-  // early; from then on it is the bottleneck and each chunk's ray casting hides behind the previous chunk's copy
+  // early; from then on it is the bottleneck and each chunk's ray casting hides behind the previous chunk's copy.
+  // RD_HOST_CHUNKS="1,3,12" overrides the weights (and the chunk count) for tuning.
   {
-    std::vector<double> w(n_chunks);
-    double tot = 0.0;
-    for (int c = 0; c < n_chunks; ++c) { w[c] = (double)(1 << std::min(c, 3)); tot += w[c]; }
-    double acc = 0.0;
-    h.bounds[0] = 0;
+    std::vector<double> w;
+    if (const char* ev = std::getenv("RD_HOST_CHUNKS")) {
+      for (const char* p = ev; *p;) {
+        char* end = nullptr;
+        const double v = std::strtod(p, &end);
+        if (end == p) break;
+        if (v > 0.0) w.push_back(v);
+        p = (*end == ',') ? end + 1 : end;
+      }
+      if ((int)w.size() > n) w.resize(n);
+    }
+    if (w.empty()) { w.resize(n_chunks); for (int c = 0; c < n_chunks; ++c) w[c] = (double)(1 << std::min(c, 3)); }
+    n_chunks = (int)w.size();
+    h.n_chunks = n_chunks;
+    h.bounds.assign(n_chunks + 1, 0);
+    double tot = 0.0, acc = 0.0;
+    for (double v : w) tot += v;
     for (int c = 0; c < n_chunks; ++c) { acc += w[c]; h.bounds[c + 1] = (int)std::llround((double)n * acc / tot); }
     h.bounds[n_chunks] = n;
   }
@@ -751,14 +765,15 @@ int host_copy_back(rd_env* env, int c) {
   if (h.occ_dev) CUDA_TRY(env, cudaMemcpyAsync(h.occ_host + e0 * 4096, h.occ_dev + e0 * 4096, cnt * 4096, cudaMemcpyDeviceToHost, h.streams[c]));
   return RD_OK;
 }
-int host_finish(rd_env* env, bool small_copied) {
+// joins every chunk stream into stream 0 (and, `wait`, blocks until the results are in the host buffers)
+int host_finish(rd_env* env, bool small_copied, bool wait = true) {
   auto& h = env->hp;
   for (int c = 1; c < h.n_chunks; ++c) {
     CUDA_TRY(env, cudaEventRecord(h.ev_done[c], h.streams[c]));
     CUDA_TRY(env, cudaStreamWaitEvent(h.streams[0], h.ev_done[c], 0));
   }
   if (!small_copied) CUDA_TRY(env, cudaMemcpyAsync(h.small_host, h.small_dev, h.small_bytes, cudaMemcpyDeviceToHost, h.streams[0]));
-  CUDA_TRY(env, cudaStreamSynchronize(h.streams[0]));
+  if (wait) CUDA_TRY(env, cudaStreamSynchronize(h.streams[0]));
   return RD_OK;
 }
 }  // namespace
@@ -767,6 +782,7 @@ RD_API int rd_reset_host(rd_env* env, const uint8_t* mask_host, int mode) {
   if (!env) return fail(nullptr, RD_ERR_INVALID, "null handle");
   auto& h = env->hp;
   if (!h.ready) return fail(env, RD_ERR_STATE, "rd_host_init has not been called");
+  if (h.pending) return fail(env, RD_ERR_STATE, "rd_step_host_begin is pending: call rd_step_host_end first");
   DeviceGuard guard(env->device);
   cudaStream_t s0 = h.streams[0];
   if (mask_host) CUDA_TRY(env, cudaMemcpyAsync(h.mask_dev, mask_host, (size_t)env->n, cudaMemcpyHostToDevice, s0));
@@ -782,7 +798,32 @@ RD_API int rd_reset_host(rd_env* env, const uint8_t* mask_host, int mode) {
   return RD_OK;
 }
 
+namespace { int step_host_enqueue(rd_env* env, const float* actions_host, bool wait); }
+
 RD_API int rd_step_host(rd_env* env, const float* actions_host) {
+  if (env && env->hp.pending) return fail(env, RD_ERR_STATE, "rd_step_host_begin is pending: call rd_step_host_end first");
+  return step_host_enqueue(env, actions_host, true);
+}
+
+RD_API int rd_step_host_begin(rd_env* env, const float* actions_host) {
+  if (env && env->hp.pending) return fail(env, RD_ERR_STATE, "rd_step_host_begin is pending: call rd_step_host_end first");
+  int rc = step_host_enqueue(env, actions_host, false);
+  if (rc == RD_OK) env->hp.pending = true;
+  return rc;
+}
+
+RD_API int rd_step_host_end(rd_env* env) {
+  if (!env) return fail(nullptr, RD_ERR_INVALID, "null handle");
+  auto& h = env->hp;
+  if (!h.ready || !h.pending) return fail(env, RD_ERR_STATE, "no rd_step_host_begin is pending");
+  DeviceGuard guard(env->device);
+  h.pending = false;
+  CUDA_TRY(env, cudaStreamSynchronize(h.streams[0]));
+  return RD_OK;
+}
+
+namespace {
+int step_host_enqueue(rd_env* env, const float* actions_host, bool wait) {
   if (!env || !actions_host) return fail(env, RD_ERR_INVALID, "null argument");
   auto& h = env->hp;
   if (!h.ready) return fail(env, RD_ERR_STATE, "rd_host_init has not been called");
@@ -811,8 +852,9 @@ RD_API int rd_step_host(rd_env* env, const float* actions_host) {
     if (rc) return rc;
     if ((rc = host_copy_back(env, c))) return rc;
   }
-  return host_finish(env, small_copied);
+  return host_finish(env, small_copied, wait);
 }
+}  // namespace
 
 // ---------------------------------------------------------------------------------------------------------
 // on-device policies

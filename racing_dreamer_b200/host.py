@@ -104,6 +104,19 @@ class HostSteppedEnv:
         self.env._check(self.lib.rd_step_host(self.env._handle, a.ctypes.data))
         return self.host_np
 
+    def step_async(self, actions: np.ndarray) -> None:
+        """Enqueue one step (actions are copied now) and return without waiting -- ``step_wait()`` delivers the results.
+        With two HostSteppedEnv groups a caller overlaps group A's kernels and policy evaluation with group B's
+        device->host copy (the asynchronous vector-env pattern); ``step()`` == ``step_async()`` + ``step_wait()``."""
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        if a.shape != (self.n, 2):
+            raise ValueError(f"actions must have shape ({self.n}, 2), got {a.shape}")
+        self.env._check(self.lib.rd_step_host_begin(self.env._handle, a.ctypes.data))
+
+    def step_wait(self) -> Dict[str, np.ndarray]:
+        self.env._check(self.lib.rd_step_host_end(self.env._handle))
+        return self.host_np
+
     @property
     def launch_count(self) -> int:
         return self.env.launch_count

@@ -139,3 +139,42 @@ def test_host_facing_step_at_config2_size_equals_device_step(torch_cuda):
         assert np.array_equal(out["lidar"], obs["lidar"].cpu().numpy()), k
         assert np.array_equal(out["reward"], rew.cpu().numpy()) and np.array_equal(out["flags"], info["flags"].cpu().numpy())
     dev.close(); host.close()
+
+
+def test_two_groups_async_host_steps_equal_the_synchronous_call(torch_cuda):
+    """step_async/step_wait (rd_step_host_begin/_end) on two half-batches in flight == step() on each, bit for bit; a
+    second begin without end, or a reset while a step is pending, is refused."""
+    import dataclasses
+    from racing_dreamer_b200 import EnvConfig
+    from racing_dreamer_b200.host import HostSteppedEnv
+    half = 1024
+    base = EnvConfig(tracks=("austria",), n_envs=half, action_repeat=8, auto_reset=True, reset_mode="random", seed=2,
+                     time_limit_steps=30)
+    cfgs = [dataclasses.replace(base, env_id_offset=g * half) for g in range(2)]
+    sync = [HostSteppedEnv(c, device="cuda:0", n_shards=4) for c in cfgs]
+    asyn = [HostSteppedEnv(c, device="cuda:0", n_shards=4) for c in cfgs]
+    for e in sync + asyn:
+        e.reset()
+    rng = np.random.RandomState(3)
+    acts = rng.uniform(-1, 1, (40, 2, half, 2)).astype(np.float32)
+    asyn[0].step_async(acts[0, 0])
+    with pytest.raises(RuntimeError, match="pending"):
+        asyn[0].step_async(acts[0, 0])
+    with pytest.raises(RuntimeError, match="pending"):
+        asyn[0].reset()
+    for k in range(40):
+        asyn[1].step_async(acts[k, 1])
+        want0 = {key: v.copy() for key, v in sync[0].step(acts[k, 0]).items()}
+        got0 = asyn[0].step_wait()
+        for key in want0:
+            assert np.array_equal(got0[key], want0[key]), (key, k)
+        if k + 1 < 40:
+            asyn[0].step_async(acts[k + 1, 0])
+        want1 = sync[1].step(acts[k, 1])
+        got1 = asyn[1].step_wait()
+        for key in want1:
+            assert np.array_equal(got1[key], want1[key]), (key, k)
+    with pytest.raises(RuntimeError, match="pending"):
+        asyn[1].step_wait()
+    for e in sync + asyn:
+        e.close()
