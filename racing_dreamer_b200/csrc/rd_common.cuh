@@ -41,6 +41,8 @@ struct LidarParams {
   int n_beams;
   int groups;            // ceil(n_beams / 32)
   unsigned groups_magic; // ceil(2^32 / groups): item / groups == umulhi(item, groups_magic) (k_lidar)
+  unsigned envs_magic;   // ceil(2^32 / n_env of the launch), centre_first order
+  int centre_first;      // work order: beam groups from the centre of the scan outwards, envs innermost
   int normalize;         // RD_OBS_LIDAR_NORM
   float range_min, range_max, noise;
   float scale;           // metres per (sub-cell / direction unit) = 2^(DIR-SUB) * resolution

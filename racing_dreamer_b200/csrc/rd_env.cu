@@ -48,6 +48,7 @@ struct rd_env {
   int device = 0;
   int sm_count = 0;
   int smem_optin = 0;             // max dynamic shared memory per CTA (opt-in), bytes
+  bool lidar_centre_first = true; // k_lidar work order (RD_LIDAR_ORDER=0: env-major)
   bool lidar_pdl = true;          // k_lidar is launched as a programmatic dependent of the kernel in front of it (RD_LIDAR_PDL=0: off)
   bool lidar_attr_set[4] = {false, false, false, false};  // k_lidar<16|32, ahead> opted in to smem_optin
   int n = 0;
@@ -241,6 +242,8 @@ int launch_lidar_t(rd_env* env, int map_id, const OriginRec* recs, const int32_t
                    cudaStream_t s, unsigned int* ctr) {
   const DevMap& m = env->maps[map_id].dev;
   LidarParams lp = lidar_params(env, m);
+  lp.centre_first = env->lidar_centre_first ? 1 : 0;
+  lp.envs_magic = n_env > 1 ? (unsigned)(((1ull << 32) + (unsigned)n_env - 1) / (unsigned)n_env) : 0u;
   const size_t tab_bytes = ((size_t)2 * lp.n_beams * 8 + 15) & ~(size_t)15;
   const size_t smem = 16 + tab_bytes + (size_t)m.bits_bytes;
   auto kern = k_lidar<WARPS, AHEAD>;
@@ -451,6 +454,7 @@ RD_API int rd_create(const rd_config* cfg, rd_env** out) {
   // batch allows (RD_STEP_BLOCK overrides, tuning)
   env->step_block = (env->n >= 128 * 4 * env->sm_count) ? 128 : ((env->n >= 64 * 4 * env->sm_count) ? 64 : 32);
   if (const char* ev = std::getenv("RD_LIDAR_PDL")) env->lidar_pdl = std::atoi(ev) != 0;
+  if (const char* ev = std::getenv("RD_LIDAR_ORDER")) env->lidar_centre_first = std::atoi(ev) != 0;
   if (const char* ev = std::getenv("RD_STEP_BLOCK")) { int v = std::atoi(ev); if (v == 32 || v == 64 || v == 128) env->step_block = v; }
   const size_t n = (size_t)env->n;
   cudaError_t e = cudaSuccess;

@@ -144,11 +144,26 @@ k_lidar(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict
       }
     }
     {
-      // item / groups by a multiply: groups_magic = ceil(2^32 / groups) (exact for item < 2^32 / groups; one fix-up
-      // step covers the rest of the 31-bit range)
-      unsigned slot = lp.groups_magic ? __umulhi(item, lp.groups_magic) : item;   // magic 0: one group per env
-      if (item - slot * (unsigned)lp.groups >= (unsigned)lp.groups) --slot;      // the estimate never falls short
-      const int g = (int)(item - slot * (unsigned)lp.groups);
+      unsigned slot;
+      int g;
+      if (lp.centre_first) {
+        // Longest-first order: items are (beam group, env) with the groups taken from the centre of the scan outwards
+        // -- the beams that look along the track march furthest, the side beams end at the nearby wall -- so the items
+        // drawn last are the cheap ones and the warps finish closer together (the end-of-launch barrier held 11 % of the
+        // warps' time in the env-major order, profiles/r01x_ncu_k_lidar_lines.txt).
+        unsigned r = __umulhi(item, lp.envs_magic);          // item / n_env, envs_magic = ceil(2^32 / n_env) (0: n_env == 1)
+        if (!lp.envs_magic) r = item;
+        if (item - r * (unsigned)n_env >= (unsigned)n_env) --r;
+        slot = item - r * (unsigned)n_env;
+        const int c = lp.groups >> 1;
+        g = (r & 1u) ? c - (int)((r + 1u) >> 1) : c + (int)(r >> 1);
+      } else {
+        // item / groups by a multiply: groups_magic = ceil(2^32 / groups) (exact for item < 2^32 / groups; one fix-up
+        // step covers the rest of the 31-bit range)
+        slot = lp.groups_magic ? __umulhi(item, lp.groups_magic) : item;   // magic 0: one group per env
+        if (item - slot * (unsigned)lp.groups >= (unsigned)lp.groups) --slot;      // the estimate never falls short
+        g = (int)(item - slot * (unsigned)lp.groups);
+      }
       const int env = env_order ? __ldg(env_order + slot) : (int)slot;
       const OriginRec rec = recs[env];
       const int beam = g * 32 + lane;
