@@ -37,6 +37,7 @@ struct HostMap {
   void* d_start = nullptr;
   void* d_reset = nullptr;
   void* d_next = nullptr;
+  size_t hot_bytes = 0;    // bytes of the d_bits allocation (bits + clearance + distance): the L2-persisting window
   bool present = false;
   int lidar_per_sm = -1;   // resident k_lidar CTAs per SM for this map (cached launch configuration)
 };
@@ -48,6 +49,7 @@ struct rd_env {
   int device = 0;
   int sm_count = 0;
   int smem_optin = 0;             // max dynamic shared memory per CTA (opt-in), bytes
+  size_t l2_window_max = 0;       // > 0: L2 persistence is set up; the largest access-policy window the device takes
   bool lidar_centre_first = true; // k_lidar work order (RD_LIDAR_ORDER=0: env-major)
   bool lidar_pdl = true;          // k_lidar is launched as a programmatic dependent of the kernel in front of it (RD_LIDAR_PDL=0: off)
   bool lidar_attr_set[4] = {false, false, false, false};  // k_lidar<16|32, ahead> opted in to smem_optin
@@ -236,6 +238,30 @@ LidarParams lidar_params(const rd_env* env, const DevMap& m) {
   return lp;
 }
 
+// Launch attributes shared by the step and LiDAR kernels: (optionally) programmatic dependent launch, and an L2
+// access-policy window that marks the track's hot arrays (bit grid, clearance field, wavefront distance: 0.1-1.3 MB)
+// as PERSISTING, so that whatever runs between two env steps (a learner's GEMMs, bench.py's 256 MB flush) does not evict
+// the map [north_star: "L2 residency control on the map"].  rd_create sets aside the persisting share of L2 once.
+int launch_attrs(const rd_env* env, int map_id, bool pdl, cudaLaunchAttribute* at) {
+  int n = 0;
+  if (pdl) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (env->l2_window_max > 0 && map_id >= 0 && env->maps[map_id].present && env->maps[map_id].hot_bytes > 0) {
+    const HostMap& m = env->maps[map_id];
+    at[n].id = cudaLaunchAttributeAccessPolicyWindow;
+    at[n].val.accessPolicyWindow.base_ptr = m.d_bits;
+    at[n].val.accessPolicyWindow.num_bytes = std::min(m.hot_bytes, env->l2_window_max);
+    at[n].val.accessPolicyWindow.hitRatio = 1.0f;
+    at[n].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    at[n].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    ++n;
+  }
+  return n;
+}
+
 // LiDAR launch for the envs of one map: persistent CTAs, grid = resident CTAs on all SMs.
 template <int WARPS, bool AHEAD>
 int launch_lidar_t(rd_env* env, int map_id, const OriginRec* recs, const int32_t* order, int n_env, float* out,
@@ -272,10 +298,8 @@ int launch_lidar_t(rd_env* env, int map_id, const OriginRec* recs, const int32_t
     // it touches the origin records.
     cudaLaunchConfig_t lc{};
     lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(WARPS * 32); lc.dynamicSmemBytes = smem; lc.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    lc.attrs = at; lc.numAttrs = env->lidar_pdl ? 1 : 0;
+    cudaLaunchAttribute at[2];
+    lc.attrs = at; lc.numAttrs = launch_attrs(env, map_id, env->lidar_pdl, at);
     const DevMap* a_maps = env->d_maps; const double* a_tab = env->d_beam_tab;
     cudaError_t le = cudaLaunchKernelEx(&lc, kern, a_maps, map_id, recs, order, n_env, lp, a_tab, out, ctr);
     if (le != cudaSuccess) { cudaGetLastError(); return fail(env, RD_ERR_CUDA, "k_lidar launch: %s", cudaGetErrorString(le)); }
@@ -336,14 +360,29 @@ StepParams step_params(rd_env* env) {
 int launch_step(rd_env* env, const rd_outputs* out, const float* actions_dev, cudaStream_t s) {
   {
     ScopedTiming tm(env, s, T_STEP);
+    // the L2 window of the step kernel covers the track most envs drive on (one window per launch)
+    int hot = -1, most = 0;
+    for (int mid = 0; mid < RD_MAX_MAPS; ++mid) {
+      const int cnt = env->order_offset[mid + 1] - env->order_offset[mid];
+      if (cnt > most) { most = cnt; hot = mid; }
+    }
+    cudaLaunchAttribute at[2];
+    cudaLaunchConfig_t lc{};
+    lc.stream = s; lc.attrs = at; lc.numAttrs = launch_attrs(env, hot, false, at);
+    const int tb = env->step_block;
+    const StepParams P = step_params(env);
+    const OutPtrs o = out_ptrs(out);
+    cudaError_t le;
     if (env->multi) {
       const int A = env->cfg.agents_per_world > 1 ? env->cfg.agents_per_world : 1;
-      const int tb = env->step_block, per_cta = (tb / A) * A;
-      k_step_ma<<<(env->n + per_cta - 1) / per_cta, tb, 0, s>>>(step_params(env), out_ptrs(out), actions_dev);
+      const int per_cta = (tb / A) * A;
+      lc.gridDim = dim3((unsigned)((env->n + per_cta - 1) / per_cta)); lc.blockDim = dim3(tb);
+      le = cudaLaunchKernelEx(&lc, k_step_ma, P, o, actions_dev);
     } else {
-      const int tb = env->step_block;
-      k_step<<<(env->n + tb - 1) / tb, tb, 0, s>>>(step_params(env), out_ptrs(out), actions_dev, 0, env->n);
+      lc.gridDim = dim3((unsigned)((env->n + tb - 1) / tb)); lc.blockDim = dim3(tb);
+      le = cudaLaunchKernelEx(&lc, k_step, P, o, actions_dev, 0, env->n);
     }
+    if (le != cudaSuccess) { cudaGetLastError(); return fail(env, RD_ERR_CUDA, "k_step launch: %s", cudaGetErrorString(le)); }
   }
   env->launches++;
   CUDA_TRY(env, cudaGetLastError());
@@ -450,6 +489,20 @@ RD_API int rd_create(const rd_config* cfg, rd_env** out) {
   env->smem_optin = (int)prop.sharedMemPerBlockOptin;
   env->n = cfg->n_envs;
   env->order_offset.assign(RD_MAX_MAPS + 1, 0);
+  // L2 residency of the tracks (launch_attrs): set aside a slice of L2 for persisting lines, once per device; the
+  // slice only ever grows (another handle or the application may have asked for more).  RD_L2_PERSIST=0 turns it off.
+  {
+    bool on = prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0;
+    if (const char* ev = std::getenv("RD_L2_PERSIST")) on = on && std::atoi(ev) != 0;
+    if (on) {
+      size_t cur = 0;
+      const size_t want = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, (size_t)8 << 20);
+      if (cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize) == cudaSuccess &&
+          (cur >= want || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess))
+        env->l2_window_max = std::min<size_t>((size_t)prop.accessPolicyMaxWindowSize, std::max(cur, want));
+      cudaGetLastError();
+    }
+  }
   // k_step is one long float64 instruction stream per warp: spread the warps over as many SM sub-partitions as the
   // batch allows (RD_STEP_BLOCK overrides, tuning)
   env->step_block = (env->n >= 128 * 4 * env->sm_count) ? 128 : ((env->n >= 64 * 4 * env->sm_count) ? 64 : 32);
@@ -555,10 +608,14 @@ RD_API int rd_upload_map(rd_env* env, int map_id, const uint32_t* bits_host, int
   std::vector<unsigned char> packed(bits_padded + coarse_padded, 0);
   std::memcpy(packed.data(), bits_host, bits_bytes);
   std::memcpy(packed.data() + bits_padded, coarse.data(), coarse.size());
-  CUDA_TRY(env, cudaMalloc(&m.d_bits, packed.size()));
+  // the two arrays every step reads (bit grid + clearance field, wavefront distance) share ONE allocation, so that a
+  // single L2 access-policy window can keep the whole track resident (launch_attrs)
+  const size_t dist_off = (packed.size() + 255) & ~(size_t)255, dist_bytes = sizeof(uint16_t) * (size_t)h * w;
+  CUDA_TRY(env, cudaMalloc(&m.d_bits, dist_off + dist_bytes));
   CUDA_TRY(env, cudaMemcpy(m.d_bits, packed.data(), packed.size(), cudaMemcpyHostToDevice));
-  CUDA_TRY(env, cudaMalloc(&m.d_dist, sizeof(uint16_t) * (size_t)h * w));
-  CUDA_TRY(env, cudaMemcpy(m.d_dist, dist_host, sizeof(uint16_t) * (size_t)h * w, cudaMemcpyHostToDevice));
+  void* dist_dev = static_cast<unsigned char*>(m.d_bits) + dist_off;
+  CUDA_TRY(env, cudaMemcpy(dist_dev, dist_host, dist_bytes, cudaMemcpyHostToDevice));
+  m.hot_bytes = dist_off + dist_bytes;
   CUDA_TRY(env, cudaMalloc(&m.d_start, sizeof(double) * 3 * (size_t)n_start));
   CUDA_TRY(env, cudaMemcpy(m.d_start, start_poses_host, sizeof(double) * 3 * (size_t)n_start, cudaMemcpyHostToDevice));
   if (n_reset > 0 && reset_poses_host) {
@@ -568,7 +625,7 @@ RD_API int rd_upload_map(rd_env* env, int map_id, const uint32_t* bits_host, int
     n_reset = 0;
   }
   DevMap& d = m.dev;
-  d.bits = (const uint32_t*)m.d_bits; d.dist = (const uint16_t*)m.d_dist;
+  d.bits = (const uint32_t*)m.d_bits; d.dist = (const uint16_t*)dist_dev;
   d.start = (const double*)m.d_start; d.reset = (const double*)m.d_reset;
   d.h = h; d.w = w; d.rw = row_words; d.col0 = col0; d.row0 = row0_yup; d.full_h = full_h; d.dmax = dmax;
   d.n_start = n_start; d.n_reset = n_reset; d.bits_bytes = (int)packed.size();
