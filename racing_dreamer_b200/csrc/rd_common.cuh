@@ -51,6 +51,7 @@ struct LidarParams {
   // multi-agent worlds: the other cars of the world are seen by the scan (agents <= 1: off)
   int agents;            // cars per world; env e belongs to world e / agents
   int car_reach;         // |origin difference| (sub-cells, per axis) beyond which a car cannot be within range
+  int car_radius_sub;    // radius (sub-cells) of a disc around a car's SENSOR origin that contains its body box
   float car_ulo, car_uhi, car_hw;  // body box in the OTHER car's sensor frame, cells: u in [ulo, uhi], |v| <= hw
   float res;             // metres per cell
 };

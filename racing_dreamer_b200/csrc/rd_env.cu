@@ -52,7 +52,7 @@ struct rd_env {
   size_t l2_window_max = 0;       // > 0: L2 persistence is set up; the largest access-policy window the device takes
   bool lidar_centre_first = true; // k_lidar work order (RD_LIDAR_ORDER=0: env-major)
   bool lidar_pdl = true;          // k_lidar is launched as a programmatic dependent of the kernel in front of it (RD_LIDAR_PDL=0: off)
-  bool lidar_attr_set[4] = {false, false, false, false};  // k_lidar<16|32, ahead> opted in to smem_optin
+  bool lidar_attr_set[8] = {};    // k_lidar<16|32, ahead, cars> opted in to smem_optin
   int n = 0;
   int step_block = 128;           // k_step threads per CTA (small batches: fewer, so that every SM gets a warp)
   double* d_f64 = nullptr;
@@ -233,6 +233,7 @@ LidarParams lidar_params(const rd_env* env, const DevMap& m) {
     lp.car_uhi = (float)(hl - off);
     lp.car_hw = (float)hw;
     lp.res = (float)m.res;
+    lp.car_radius_sub = (int)std::ceil((hl + hw + std::fabs(off) + 1.0) * (double)RD_SUB);
     lp.car_reach = (int)std::ceil((c.lidar_range_max * m.inv_res + 2.0 * (hl + hw + std::fabs(off)) + 2.0) * (double)RD_SUB);
   }
   return lp;
@@ -263,7 +264,7 @@ int launch_attrs(const rd_env* env, int map_id, bool pdl, cudaLaunchAttribute* a
 }
 
 // LiDAR launch for the envs of one map: persistent CTAs, grid = resident CTAs on all SMs.
-template <int WARPS, bool AHEAD>
+template <int WARPS, bool AHEAD, bool CARS>
 int launch_lidar_t(rd_env* env, int map_id, const OriginRec* recs, const int32_t* order, int n_env, float* out,
                    cudaStream_t s, unsigned int* ctr) {
   const DevMap& m = env->maps[map_id].dev;
@@ -272,10 +273,10 @@ int launch_lidar_t(rd_env* env, int map_id, const OriginRec* recs, const int32_t
   lp.envs_magic = n_env > 1 ? (unsigned)(((1ull << 32) + (unsigned)n_env - 1) / (unsigned)n_env) : 0u;
   const size_t tab_bytes = ((size_t)2 * lp.n_beams * 8 + 15) & ~(size_t)15;
   const size_t smem = 16 + tab_bytes + (size_t)m.bits_bytes;
-  auto kern = k_lidar<WARPS, AHEAD>;
+  auto kern = k_lidar<WARPS, AHEAD, CARS>;
   int& per_sm = env->maps[map_id].lidar_per_sm;
   if (per_sm < 0) {  // once per map: ask how many CTAs fit on an SM (the kernel is opted in to the device maximum)
-    bool& attr = env->lidar_attr_set[(WARPS == 32 ? 1 : 0) + (AHEAD ? 2 : 0)];
+    bool& attr = env->lidar_attr_set[(WARPS == 32 ? 1 : 0) + (AHEAD ? 2 : 0) + (CARS ? 4 : 0)];
     if (!attr) {
       CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_optin));
       attr = true;
@@ -320,10 +321,16 @@ int launch_lidar(rd_env* env, int map_id, const OriginRec* recs, const int32_t* 
   const long long items = (long long)n_env * ((env->cfg.n_beams + 31) / 32);
   bool ahead = items >= 128ll * env->sm_count * per_sm * warps;
   if (const char* ev = std::getenv("RD_LIDAR_AHEAD")) ahead = std::atoi(ev) != 0;
-  if (warps == 32) return ahead ? launch_lidar_t<32, true>(env, map_id, recs, order, n_env, out, s, ctr)
-                                : launch_lidar_t<32, false>(env, map_id, recs, order, n_env, out, s, ctr);
-  return ahead ? launch_lidar_t<16, true>(env, map_id, recs, order, n_env, out, s, ctr)
-               : launch_lidar_t<16, false>(env, map_id, recs, order, n_env, out, s, ctr);
+  const bool cars = env->cfg.agents_per_world > 1;   // worlds: the scans also see the other cars (own instantiation, so
+                                                      // that the single-car kernel keeps its register budget)
+#define RD_LIDAR_GO(W, A, C) launch_lidar_t<W, A, C>(env, map_id, recs, order, n_env, out, s, ctr)
+  if (warps == 32) {
+    if (cars) return ahead ? RD_LIDAR_GO(32, true, true) : RD_LIDAR_GO(32, false, true);
+    return ahead ? RD_LIDAR_GO(32, true, false) : RD_LIDAR_GO(32, false, false);
+  }
+  if (cars) return ahead ? RD_LIDAR_GO(16, true, true) : RD_LIDAR_GO(16, false, true);
+  return ahead ? RD_LIDAR_GO(16, true, false) : RD_LIDAR_GO(16, false, false);
+#undef RD_LIDAR_GO
 }
 
 int launch_occupancy(rd_env* env, int map_id, const OriginRec* recs, const double* poses_xyyaw,

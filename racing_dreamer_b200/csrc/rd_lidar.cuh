@@ -80,7 +80,7 @@ __device__ __forceinline__ float rd_car_hit(const LidarParams& lp, int px, int p
 // smem layout: [0,16) mbarrier | beam table 2*n_beams f64 (cos then sin) | bit grid | block clearance field
 // The tail of the item list is handed out through a global counter (ctr[0]); the last CTA to finish (ticket ctr[1])
 // re-arms both for the next launch on the stream.
-template <int WARPS, bool AHEAD>
+template <int WARPS, bool AHEAD, bool CARS>
 __global__ void __launch_bounds__(WARPS * 32)
 k_lidar(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict__ recs,
         const int32_t* __restrict__ env_order, int n_env, LidarParams lp, const double* __restrict__ beam_tab,
@@ -179,11 +179,25 @@ k_lidar(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict
           const int DY = __double2int_rn(dy * (double)(1 << RD_DIR_BITS));
           const MarchResult mr = rd_march(grid, rec.px, rec.py, DX, DY, (long long)lp.rsub, nullptr);
           r = mr.hit ? __fmul_rn(__fdiv_rn((float)mr.num, (float)mr.den), lp.scale) : lp.range_max;
-          if (lp.agents > 1) {  // the other cars of this world (their records sit next to this one)
+          if (CARS) {  // worlds: the other cars of this world (their records sit next to this one)
+            // Warp-level rejection first: the group's beams fill the wedge between its first and last direction (W = the
+            // points clockwise of d_a and counter-clockwise of d_b, < 8 degrees wide); a car whose bounding disc lies
+            // entirely on the far side of either edge line cannot be hit by any beam of the group.  64-bit integers,
+            // conservative radius -- most groups skip every car, so worlds cost little more than single cars.
+            const unsigned act = __activemask();
+            const int la = __ffs(act) - 1, lb = 31 - __clz(act);
+            const int dax = __shfl_sync(act, DX, la), day = __shfl_sync(act, DY, la);
+            const int dbx = __shfl_sync(act, DX, lb), dby = __shfl_sync(act, DY, lb);
+            const long long rr = (long long)lp.car_radius_sub * ((1ll << RD_DIR_BITS) + 4);
             const int base = env - env % lp.agents;
             for (int j = 0; j < lp.agents; ++j) {
               if (base + j == env) continue;
-              r = fminf(r, rd_car_hit(lp, rec.px, rec.py, DX, DY, recs[base + j]));
+              const OriginRec q = recs[base + j];
+              const long long ox = (long long)q.px - rec.px, oy = (long long)q.py - rec.py;   // me -> the other car
+              const long long ca = (long long)dax * oy - (long long)day * ox;                // > 0: left of d_a
+              const long long cb = (long long)dbx * oy - (long long)dby * ox;                // < 0: right of d_b
+              if ((q.valid & 2) && (ca > rr || cb < -rr)) continue;
+              r = fminf(r, rd_car_hit(lp, rec.px, rec.py, DX, DY, q));
             }
           }
         }
