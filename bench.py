@@ -514,8 +514,8 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             rate, _ = cpu_oracle_run(256, 2, 1, threads, obs=args.obs)
-            n_s = int(min(N_ENVS, max(threads, rate * 1.0)))     # ~1 s per step
-            steps_s = 12
+            n_s = int(min(N_ENVS, max(threads, rate * 1.0)))     # <= ~1 s per step
+            steps_s = int(min(200, max(12, 1.5 * rate / n_s)))  # ~1.5 s of wall time on every host thread
             v, dt = cpu_oracle_run(n_s, steps_s, 2, threads, obs=args.obs)
             line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
                                     "sample": f"{n_s} envs x {steps_s} steps of the same workload, oracle/rd_oracle.c, "
