@@ -49,7 +49,11 @@ enum { RD_TASK_MAX_PROGRESS = 0, RD_TASK_MAX_SPEED = 1,
 enum {
   RD_OBS_LIDAR = 1,          /* f32 [N, n_beams] metres */
   RD_OBS_OCCUPANCY = 2,      /* u8 [N, 64, 64] 'lidar_occupancy' [REF dreamer/wrappers.py:372-414] */
-  RD_OBS_LIDAR_NORM = 4      /* lidar stored as r/15 - 0.5 [REF dreamer/tools.py:274] instead of metres */
+  RD_OBS_LIDAR_NORM = 4,     /* lidar stored as r/15 - 0.5 [REF dreamer/tools.py:274] instead of metres */
+  RD_OBS_LIDAR_F16 = 8       /* lidar stored as IEEE half (round to nearest even of the float32 value): what Collect hands on at
+                              * precision 16 [REF dreamer/wrappers.py:240-250 _convert; dreamer/dream.py:176-177].  lidar_dev then
+                              * points to uint16 [N, n_beams]; halves the device->host bytes of the host-facing step.  The
+                              * on-device policies read float32 scans and refuse this flag. */
 };
 /* action_repeat edge semantics [REF dreamer/wrappers.py:107-116 | baselines/.../single_agent.py:31-40] */
 enum { RD_REPEAT_DREAMER = 0, RD_REPEAT_BASELINES = 1 };
@@ -137,7 +141,7 @@ void rd_default_config(rd_config* cfg);
 /* Device pointers for one step's results.  Any pointer may be NULL = "do not produce".
  * [REF dreamer/wrappers.py:62-69 (obs dict + speed), :210-226 (Collect: f32 casts, progress, time)] */
 typedef struct rd_outputs {
-  float* lidar_dev;           /* [N, n_beams] */
+  float* lidar_dev;           /* [N, n_beams] float32 (IEEE half, i.e. uint16 storage, with RD_OBS_LIDAR_F16) */
   uint8_t* occupancy_dev;     /* [N, 64*64]   */
   float* pose_dev;            /* [N, 6] x,y,z,roll,pitch,yaw [REF dreamer/wrappers.py:395-401] */
   float* velocity_dev;        /* [N, 6] body-frame linear (vx,vy,0) + angular (0,0,yaw_rate) */

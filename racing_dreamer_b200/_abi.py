@@ -19,7 +19,7 @@ RESET_MODES = {"grid": RESET_GRID, "random": RESET_RANDOM, "random_bidirectional
 TASK_MAX_PROGRESS, TASK_MAX_SPEED, TASK_N_STEP_PROGRESS = 0, 1, 2
 TASKS = {"maximize_progress": TASK_MAX_PROGRESS, "max_progress": TASK_MAX_PROGRESS,
          "max_speed": TASK_MAX_SPEED, "maximize_speed": TASK_MAX_SPEED, "n_step_progress": TASK_N_STEP_PROGRESS}
-OBS_LIDAR, OBS_OCCUPANCY, OBS_LIDAR_NORM = 1, 2, 4
+OBS_LIDAR, OBS_OCCUPANCY, OBS_LIDAR_NORM, OBS_LIDAR_F16 = 1, 2, 4, 8
 REPEAT_DREAMER, REPEAT_BASELINES = 0, 1
 
 S_X, S_Y, S_STEER, S_V, S_YAW, S_YAWRATE, S_SLIP, S_TIME, S_PROGRESS, S_LAST, S_RETURN, S_START, NF64 = range(13)

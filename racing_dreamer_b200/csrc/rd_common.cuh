@@ -1,6 +1,7 @@
 // rd_common.cuh -- shared device-side types and helpers of librd_env.so (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #include "../../include/rd_env.h"
@@ -44,6 +45,7 @@ struct LidarParams {
   unsigned envs_magic;   // ceil(2^32 / n_env of the launch), centre_first order
   int centre_first;      // work order: beam groups from the centre of the scan outwards, envs innermost
   int normalize;         // RD_OBS_LIDAR_NORM
+  int f16;               // RD_OBS_LIDAR_F16: rows are stored as IEEE half
   float range_min, range_max, noise;
   float scale;           // metres per (sub-cell / direction unit) = 2^(DIR-SUB) * resolution
   int64_t rsub;          // range_max in sub-cells

@@ -86,7 +86,8 @@ struct rd_env {
     float* act_host = nullptr; float* act_dev = nullptr;
     uint8_t* mask_dev = nullptr;
     unsigned char* small_dev = nullptr; unsigned char* small_host = nullptr; size_t small_bytes = 0;
-    float* lidar_dev = nullptr; float* lidar_host = nullptr;
+    float* lidar_dev = nullptr; float* lidar_host = nullptr;   // float32 rows, or IEEE half rows (lidar_elem == 2)
+    size_t lidar_elem = 4;
     uint8_t* occ_dev = nullptr; uint8_t* occ_host = nullptr;
     unsigned int* ctr = nullptr;             // [n_chunks][2] k_lidar work counters, one pair per stream
     bool zero_copy = false;                  // k_lidar stores straight into the pinned host mirror (no staging copy)
@@ -218,6 +219,7 @@ LidarParams lidar_params(const rd_env* env, const DevMap& m) {
   lp.groups = (c.n_beams + 31) / 32;
   lp.groups_magic = lp.groups > 1 ? (unsigned)(((1ull << 32) + (unsigned)lp.groups - 1) / (unsigned)lp.groups) : 0u;
   lp.normalize = (c.obs_flags & RD_OBS_LIDAR_NORM) ? 1 : 0;
+  lp.f16 = (c.obs_flags & RD_OBS_LIDAR_F16) ? 1 : 0;
   lp.range_min = (float)c.lidar_range_min;
   lp.range_max = (float)c.lidar_range_max;
   lp.noise = c.lidar_noise;
@@ -768,7 +770,9 @@ RD_API int rd_host_init(rd_env* env, int n_chunks, rd_outputs* host_out) {
   const size_t o_lap = take(sizeof(int32_t) * n), o_done = take((size_t)n), o_flags = take((size_t)n);
   const size_t o_rank = take(sizeof(int32_t) * n), o_opp = take((size_t)n);
   h.small_bytes = off;
-  const size_t lidar_bytes = sizeof(float) * (size_t)n * env->cfg.n_beams;
+  const size_t lidar_elem = (env->cfg.obs_flags & RD_OBS_LIDAR_F16) ? 2 : 4;
+  h.lidar_elem = lidar_elem;
+  const size_t lidar_bytes = lidar_elem * (size_t)n * env->cfg.n_beams;
   const bool occ = (env->cfg.obs_flags & RD_OBS_OCCUPANCY) != 0;
   CUDA_TRY(env, cudaMalloc(&h.small_dev, h.small_bytes));
   CUDA_TRY(env, cudaMemset(h.small_dev, 0, h.small_bytes));
@@ -829,7 +833,11 @@ int host_copy_back(rd_env* env, int c) {
   auto& h = env->hp;
   const size_t e0 = (size_t)h.bounds[c], cnt = (size_t)(h.bounds[c + 1] - h.bounds[c]);
   const size_t nb = (size_t)env->cfg.n_beams;
-  if (!h.zero_copy) CUDA_TRY(env, cudaMemcpyAsync(h.lidar_host + e0 * nb, h.lidar_dev + e0 * nb, sizeof(float) * cnt * nb, cudaMemcpyDeviceToHost, h.streams[c]));
+  if (!h.zero_copy) {
+    const size_t off = e0 * nb * h.lidar_elem;
+    CUDA_TRY(env, cudaMemcpyAsync(reinterpret_cast<unsigned char*>(h.lidar_host) + off, reinterpret_cast<unsigned char*>(h.lidar_dev) + off,
+                                  h.lidar_elem * cnt * nb, cudaMemcpyDeviceToHost, h.streams[c]));
+  }
   if (h.occ_dev) CUDA_TRY(env, cudaMemcpyAsync(h.occ_host + e0 * 4096, h.occ_dev + e0 * 4096, cnt * 4096, cudaMemcpyDeviceToHost, h.streams[c]));
   return RD_OK;
 }
@@ -858,7 +866,7 @@ RD_API int rd_reset_host(rd_env* env, const uint8_t* mask_host, int mode) {
   if (rc) return rc;
   const int saved = h.n_chunks;   // everything ran on stream 0: copy it back as one chunk
   const size_t nb = (size_t)env->cfg.n_beams, n = (size_t)env->n;
-  if (!h.zero_copy) CUDA_TRY(env, cudaMemcpyAsync(h.lidar_host, h.lidar_dev, sizeof(float) * n * nb, cudaMemcpyDeviceToHost, s0));
+  if (!h.zero_copy) CUDA_TRY(env, cudaMemcpyAsync(h.lidar_host, h.lidar_dev, h.lidar_elem * n * nb, cudaMemcpyDeviceToHost, s0));
   if (h.occ_dev) CUDA_TRY(env, cudaMemcpyAsync(h.occ_host, h.occ_dev, n * 4096, cudaMemcpyDeviceToHost, s0));
   CUDA_TRY(env, cudaMemcpyAsync(h.small_host, h.small_dev, h.small_bytes, cudaMemcpyDeviceToHost, s0));
   CUDA_TRY(env, cudaStreamSynchronize(s0));
@@ -965,6 +973,7 @@ RD_API void rd_gap_follower_defaults(const rd_config* cfg, rd_gap_follower* g) {
 
 RD_API int rd_policy_gap_follower_init(rd_env* env, const rd_gap_follower* g_or_null) {
   if (!env) return fail(nullptr, RD_ERR_INVALID, "null handle");
+  if (env->cfg.obs_flags & RD_OBS_LIDAR_F16) return fail(env, RD_ERR_INVALID, "the on-device policies read float32 scans: RD_OBS_LIDAR_F16 is set");
   rd_gap_follower g;
   if (g_or_null) g = *g_or_null; else rd_gap_follower_defaults(&env->cfg, &g);
   const int m = g.arc_last - g.arc_first + 1;
@@ -1045,6 +1054,7 @@ RD_API int rd_rollout_gap_follower(rd_env* env, int n_steps, const rd_outputs* o
 
 RD_API int rd_policy_dreamer_init(rd_env* env, const rd_dreamer_weights* w) {
   if (!env) return fail(nullptr, RD_ERR_INVALID, "null handle");
+  if (env->cfg.obs_flags & RD_OBS_LIDAR_F16) return fail(env, RD_ERR_INVALID, "the on-device policies read float32 scans: RD_OBS_LIDAR_F16 is set");
   const int rc = dreamer_init(env->dr, env->n, env->cfg.n_beams, (env->cfg.obs_flags & RD_OBS_LIDAR_NORM) != 0, w);
   if (rc) return fail(env, rc, "rd_policy_dreamer_init: %s", env->dr.err.c_str());
   if (!env->pol.d_actions) {

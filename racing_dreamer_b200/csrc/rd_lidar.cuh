@@ -201,7 +201,9 @@ k_lidar(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict
             }
           }
         }
-        out[(size_t)env * lp.n_beams + beam] = rd_finish_range(lp, r, rec, (uint32_t)beam);
+        const float rf = rd_finish_range(lp, r, rec, (uint32_t)beam);
+        if (lp.f16) reinterpret_cast<__half*>(out)[(size_t)env * lp.n_beams + beam] = __float2half_rn(rf);   // Collect at precision 16
+        else out[(size_t)env * lp.n_beams + beam] = rf;
       }
     }
     ++item;

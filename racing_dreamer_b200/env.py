@@ -31,6 +31,7 @@ class EnvConfig:
     action_repeat: int = 4                      # [REF dreamer/dream.py:55]
     obs_type: str = "lidar"                     # 'lidar' | 'lidar_occupancy' [REF dreamer/dream.py:64-66]
     normalize_lidar: bool = False               # store r/15-0.5 [REF dreamer/tools.py:274]
+    lidar_dtype: str = "float32"                # 'float16' = what Collect hands on at precision 16 [REF dreamer/wrappers.py:240-250]
     task: str = "maximize_progress"
     laps: int = 10
     time_limit: float = 180.0
@@ -73,6 +74,10 @@ def _fill_config(cfg: _abi.RdConfig, ec: EnvConfig) -> None:
         raise ValueError(f"obs_type {ec.obs_type!r}: expected 'lidar' or 'lidar_occupancy'")
     if ec.normalize_lidar:
         flags |= _abi.OBS_LIDAR_NORM
+    if ec.lidar_dtype == "float16":
+        flags |= _abi.OBS_LIDAR_F16
+    elif ec.lidar_dtype != "float32":
+        raise ValueError(f"lidar_dtype {ec.lidar_dtype!r}: expected 'float32' or 'float16'")
     cfg.obs_flags = flags
     cfg.task = _abi.TASKS[ec.task]
     cfg.laps = int(ec.laps)
@@ -190,6 +195,8 @@ class BatchedRaceEnv:
                 self.buf[key] = None
                 continue
             full = (n,) + ((self.n_beams,) if key == "lidar" else tuple(shape))
+            if key == "lidar" and (self.cfg.obs_flags & _abi.OBS_LIDAR_F16):
+                dtype = torch.float16
             t = given.get(key)
             if t is None:
                 t = torch.zeros(full, dtype=dtype, device=dev)
@@ -262,7 +269,8 @@ class BatchedRaceEnv:
     # ------------------------------------------------------------------ stage entry points (parity tests)
     def lidar_cast(self, poses: torch.Tensor, map_ids: Optional[np.ndarray] = None) -> torch.Tensor:
         p = poses.to(device=self.device, dtype=torch.float64).contiguous().reshape(-1, 3)
-        out = torch.empty((p.shape[0], self.n_beams), dtype=torch.float32, device=self.device)
+        dt = torch.float16 if (self.cfg.obs_flags & _abi.OBS_LIDAR_F16) else torch.float32
+        out = torch.empty((p.shape[0], self.n_beams), dtype=dt, device=self.device)
         ids = None if map_ids is None else np.ascontiguousarray(map_ids, dtype=np.int32)
         with torch.cuda.device(self.device):
             self._check(self.lib.rd_lidar_cast(self._handle, p.data_ptr(), ids.ctypes.data if ids is not None else None,

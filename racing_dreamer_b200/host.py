@@ -71,6 +71,8 @@ class HostSteppedEnv:
         self.host_np: Dict[str, np.ndarray] = {}
         for key in _OUT_KEYS:
             field, dt = _FIELDS[key]
+            if key == "lidar" and (self.env.cfg.obs_flags & _abi.OBS_LIDAR_F16):
+                dt = np.float16
             ptr = getattr(ho, field)
             if not ptr:
                 continue

@@ -354,3 +354,37 @@ def test_max_speed_task(torch_cuda):
     want = np.where(col, -1.0, -np.exp(np.abs(a[:, 1].astype(np.float64)) - v))
     assert np.allclose(rew.cpu().numpy(), want, rtol=1e-4, atol=1e-5)
     env.close()
+
+
+def test_float16_scans_are_the_rounded_float32_scans(torch_cuda):
+    """lidar_dtype='float16' = Collect._convert at precision 16 [REF dreamer/wrappers.py:240-250; dream.py:176-177]: every
+    range is the float32 value rounded to nearest-even half, on the device path, the stage entry and the host-facing path;
+    the on-device policies (float32 readers) refuse such an env."""
+    torch = torch_cuda
+    from racing_dreamer_b200 import EnvConfig, GapFollowerPolicy
+    from racing_dreamer_b200.host import HostSteppedEnv
+    n = 300
+    kw = dict(tracks=("austria", "columbia"), n_envs=n, action_repeat=4, auto_reset=True, reset_mode="random", seed=8,
+              time_limit_steps=20, lidar_noise=0.03)
+    e32, e16 = make_env(torch, **kw), make_env(torch, lidar_dtype="float16", **kw)
+    h16 = HostSteppedEnv(EnvConfig(lidar_dtype="float16", **kw), device="cuda:0", n_shards=3)
+    orc = make_oracle(e32)
+    o32, o16 = e32.reset(), e16.reset()
+    ho = h16.reset()
+    ref = orc.reset(mode=int(e32.cfg.reset_mode))
+    assert o16["lidar"].dtype == torch.float16 and ho["lidar"].dtype == np.float16
+    rng = np.random.RandomState(1)
+    for k in range(25):
+        assert torch.equal(o16["lidar"], o32["lidar"].half()), k
+        assert np.array_equal(ho["lidar"], o16["lidar"].cpu().numpy()), k
+        assert np.array_equal(ho["lidar"], ref["lidar"].astype(np.float16)), k          # numpy's cast is the specification
+        a = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+        o32, o16 = e32.step(torch.from_numpy(a).cuda())[0], e16.step(torch.from_numpy(a).cuda())[0]
+        ho = h16.step(a)
+        ref = orc.step(a)
+    poses = random_poses(e32.tracks[0], 64, rng)
+    assert torch.equal(e16.lidar_cast(torch.from_numpy(poses)), e32.lidar_cast(torch.from_numpy(poses)).half())
+    assert h16.d2h_bytes_per_step < n * 1080 * 2 + n * 200
+    with pytest.raises(RuntimeError, match="float32 scans"):
+        GapFollowerPolicy(e16)
+    e32.close(); e16.close(); h16.close()

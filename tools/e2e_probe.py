@@ -49,3 +49,20 @@ for spec in ("", "1,15", "1,3,12", "1,4,11", "1,2,4,8", "2,6,8", "1,2,5,8", "1,3
         best = min(best, (time.perf_counter() - t0) / 200 * 1e3)
     print(f"chunks {spec or 'default(8)':12s}: e2e {best:.3f} ms/step", flush=True)
     env.close()
+
+for dt in ("float32", "float16"):
+    os.environ.pop("RD_HOST_CHUNKS", None)
+    ec = EnvConfig(tracks=("austria",), n_envs=n, action_repeat=8, auto_reset=True, reset_mode="random", seed=1,
+                   time_limit_steps=250, lidar_dtype=dt)
+    env = HostSteppedEnv(ec, device="cuda:0", n_shards=8)
+    env.reset()
+    for _ in range(30):
+        env.step(a)
+    best = 1e9
+    for rep in range(4):
+        t0 = time.perf_counter()
+        for _ in range(200):
+            env.step(a)
+        best = min(best, (time.perf_counter() - t0) / 200 * 1e3)
+    print(f"lidar_dtype {dt}: e2e {best:.3f} ms/step = {n / best / 1e3:.2f} M env-steps/s, {env.d2h_bytes_per_step / 1e6:.1f} MB d2h per step", flush=True)
+    env.close()
