@@ -114,9 +114,19 @@ class EpisodeRecorder:
     """
 
     def __init__(self, env, max_len: int, callbacks: Sequence[Callable] = (), precision: int = 32,
-                 reset_mode: Optional[str] = None, keep_obs: Sequence[str] = OBS_KEYS):
+                 reset_mode: Optional[str] = None, keep_obs: Sequence[str] = OBS_KEYS,
+                 agents_per_world: Optional[int] = None):
+        """agents_per_world (default: the env's own ``cfg.agents_per_world``): for worlds of several cars the episodes of
+        ALL cars of a world end at the step in which any of them is done -- the reference resets the world then
+        [REF dreamer/tools.py:178-179] -- and the callbacks get one list with the world's episodes, agent A first, exactly
+        what the reference's Collect passes for its single world [REF dreamer/wrappers.py:221-225]."""
         self.env = env
         self.n = int(env.n)
+        cfg = getattr(env, "cfg", None) or getattr(getattr(env, "env", None), "cfg", None)
+        A = agents_per_world if agents_per_world is not None else int(getattr(cfg, "agents_per_world", 1) or 1)
+        self.agents = max(1, int(A))
+        if self.n % self.agents:
+            raise ValueError("n_envs must be a multiple of agents_per_world")
         self.max_len = int(max_len)
         self.callbacks = tuple(callbacks)
         self.precision = precision
@@ -147,13 +157,17 @@ class EpisodeRecorder:
         self._len[envs] = t + 1
 
     def _flush(self, envs: np.ndarray) -> None:
-        for e in envs:
-            n = int(self._len[e])
-            episode = {k: self._store[k][:n, e].copy() for k in self._store}
-            self.episodes_done += 1
+        A = self.agents
+        for e in envs[::A] if A > 1 else envs:      # worlds: `envs` holds whole worlds, one callback per world
+            group = range(e, e + A) if A > 1 else (e,)
+            episodes = []
+            for c in group:
+                n = int(self._len[c])
+                episodes.append({k: self._store[k][:n, c].copy() for k in self._store})
+                self._len[c] = 0
+            self.episodes_done += len(episodes)
             for cb in self.callbacks:
-                cb([episode])
-            self._len[e] = 0
+                cb(episodes)
 
     # -- env API --
     def reset(self, mask: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
@@ -181,6 +195,8 @@ class EpisodeRecorder:
                     progress=out["lap"][live].astype(np.float64) + out["progress"][live].astype(np.float64) - 1.0,
                     time=out["time"][live])                                           # [REF dreamer/wrappers.py:214-219]
         self._put(rows, live)
+        if self.agents > 1:     # a world is over for all of its cars as soon as one is done
+            done = np.repeat(done.reshape(-1, self.agents).any(axis=1), self.agents)
         finished = live[done[live]]
         if finished.size:
             reward, done_flags = out["reward"].copy(), out["done"].copy()

@@ -287,6 +287,47 @@ def costmap_golden():
     np.savez_compressed(OUT / "costmap_golden.npz", **out)
 
 
+def multi_agent_episodes_golden(n_steps=120, action_repeat=4, duration=15, n_agents=3):
+    """SURVEY §8-f1 x f3: what the reference's Collect hands to its callbacks for a world of three cars -- ONE call per
+    world episode with a list of per-agent episodes that all end at the same step (discount 0 only for the cars that
+    were done themselves) [REF dreamer/wrappers.py:210-238]."""
+    from oracle import ref_env
+    W = ref_stubs.reference_wrappers()
+    tm = load_track("treitlstrasse_v2")
+    ids = ["A", "B", "C"][:n_agents]
+    captured = []
+    env = ref_env.OracleRaceEnv(tm, n_agents=n_agents, seed=23, ball_spacing=0.8)
+    env = W.RaceCarWrapper(env, agent_id="A")
+    env = W.ActionRepeat(env, action_repeat)
+    env = W.ReduceActionSpace(env, low=[0.005, -1.0], high=[1.0, 1.0])
+    env = W.FixedResetMode(env, "random_ball")
+    env = W.TimeLimit(env, duration)
+    env = W.Collect(env, callbacks=[lambda eps: captured.append([{k: np.array(v) for k, v in e.items()} for e in eps])],
+                    precision=32)
+    rng = np.random.RandomState(23)
+    actions = rng.uniform(-1, 1, (n_steps, n_agents, 2)).astype(np.float32)
+    actions[:, :, 0] = ((np.abs(actions[:, :, 0]) * 0.5 + 0.5) * np.array([1.0, 0.2, 0.5][:n_agents], np.float32)) * 2 - 1
+    actions[:, :, 1] *= 0.3
+    reset_before, need_reset = [], True
+    for t in range(n_steps):
+        reset_before.append(need_reset)
+        if need_reset:
+            env.reset()
+        _, _, done, _ = env.step({i: actions[t, k] for k, i in enumerate(ids)})
+        need_reset = any(done.values())
+    keys = sorted(captured[0][0])
+    out = {"actions": actions, "reset_before": np.asarray(reset_before), "action_repeat": action_repeat, "duration": duration,
+           "n_agents": n_agents, "seed": 23, "ball_spacing": 0.8, "n_episodes": len(captured), "keys": np.array(keys)}
+    for i, eps in enumerate(captured):
+        assert len(eps) == n_agents and len({len(e["reward"]) for e in eps}) == 1
+        for a, ep in enumerate(eps):
+            for k in keys:
+                out[f"ep{i}_{a}_{k}"] = ep[k]
+    np.savez_compressed(OUT / "multi_agent_episodes_golden.npz", **out)
+    print("multi_agent_episodes_golden:", len(captured), "world episodes, lengths", [len(e[0]["reward"]) for e in captured],
+          "terminal discounts", [[float(e["discount"][-1]) for e in eps] for eps in captured][:6])
+
+
 def multi_agent_stack_golden(n_steps=600, action_repeat=4, duration=18, n_agents=4):
     """the reference wrappers' dict-of-agents semantics (ActionRepeat stops when ANY agent is done and sums
     per agent, TimeLimit sets every done, Collect's casts) over the one-tick multi-car oracle world."""
@@ -352,3 +393,4 @@ if __name__ == "__main__":
     baselines_stack_golden()
     episodes_golden()
     multi_agent_stack_golden()
+    multi_agent_episodes_golden()

@@ -63,3 +63,36 @@ def test_batched_recorder_files_and_sampler(tmp_path):
         assert all(len(v) == 3 for v in c.values())
     a = [next(load_episodes(tmp_path, 4, length=3, seed=5))["reward"] for _ in range(2)]
     assert np.array_equal(a[0], a[1])                                   # same seed -> same stream
+
+
+def test_recorder_reproduces_reference_collect_for_a_world_of_cars(golden_dir):
+    """§8-f1 x f3: one world of three cars -- every car's episode ends when any car is done, one callback per world with
+    the list of per-agent episodes, discount 0 only for the cars that were done themselves
+    [REF dreamer/wrappers.py:210-238]; fixture recorded from the unmodified Collect (multi_agent_episodes_golden)."""
+    from oracle import default_config
+    g = np.load(golden_dir / "multi_agent_episodes_golden.npz")
+    A = int(g["n_agents"])
+    cfg = helpers.fused_dreamer_config(default_config(), int(g["action_repeat"]), int(g["duration"]), occupancy=False)
+    cfg.n_envs = A
+    cfg.agents_per_world = A
+    cfg.reset_mode = _abi.RESET_RANDOM_BALL
+    cfg.seed = int(g["seed"])
+    cfg.ball_spacing = float(g["ball_spacing"])
+    env = helpers.OracleHostEnv(cfg, [load_track("treitlstrasse_v2")])
+    captured = []
+    rec = EpisodeRecorder(env, max_len=int(g["duration"]), callbacks=[captured.append], reset_mode="random_ball")
+    assert rec.agents == A
+    rec.reset()
+    for t in range(g["actions"].shape[0]):
+        rec.step(g["actions"][t])
+    assert len(captured) == int(g["n_episodes"])
+    keys = [str(k) for k in g["keys"]]
+    for i, eps in enumerate(captured):
+        assert len(eps) == A
+        for a, ep in enumerate(eps):
+            assert sorted(ep) == keys
+            for k in keys:
+                want, got = g[f"ep{i}_{a}_{k}"], ep[k]
+                assert got.dtype == want.dtype and got.shape == want.shape, (i, a, k)
+                assert np.array_equal(got, want), (i, a, k)
+    assert any(eps[0]["discount"][-1] == 0 and eps[-1]["discount"][-1] == 1 for eps in captured)   # mixed endings occur

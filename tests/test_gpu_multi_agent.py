@@ -227,3 +227,32 @@ def test_world_golden_replay_of_the_reference_wrapper_stack(torch_cuda, golden_d
     rec = helpers.replay_world(lambda: env.reset(mode="random_ball"), step, g["actions"], g["reset_before"])
     helpers.assert_matches_multi_agent_golden(rec, g, lidar_tol=LIDAR_TOL_M, float_tol=DYN_RTOL)
     env.close()
+
+
+def test_episode_recorder_for_a_world_of_cars_on_gpu(torch_cuda, golden_dir):
+    """§8-f1 x f3 on the CUDA path: the recorder over the host-facing step of a three-car world == what the reference's
+    Collect handed to its callbacks (tests/golden/multi_agent_episodes_golden.npz)."""
+    from racing_dreamer_b200 import EnvConfig
+    from racing_dreamer_b200.episodes import EpisodeRecorder
+    from racing_dreamer_b200.host import HostSteppedEnv
+    g = np.load(golden_dir / "multi_agent_episodes_golden.npz")
+    A = int(g["n_agents"])
+    ec = EnvConfig(tracks=("treitlstrasse_v2",), n_envs=A, agents_per_world=A, action_repeat=int(g["action_repeat"]),
+                   auto_reset=False, reset_mode="random_ball", time_limit_steps=int(g["duration"]), seed=int(g["seed"]),
+                   ball_spacing=float(g["ball_spacing"]))
+    env = HostSteppedEnv(ec, device="cuda:0", n_shards=2)
+    captured = []
+    rec = EpisodeRecorder(env, max_len=int(g["duration"]), callbacks=[captured.append], reset_mode="random_ball")
+    rec.reset()
+    for t in range(g["actions"].shape[0]):
+        rec.step(g["actions"][t])
+    assert len(captured) == int(g["n_episodes"])
+    for i, eps in enumerate(captured):
+        for a, ep in enumerate(eps):
+            for k in (str(k) for k in g["keys"]):
+                want, got = g[f"ep{i}_{a}_{k}"], ep[k]
+                assert got.dtype == want.dtype and got.shape == want.shape, (i, a, k)
+                tol = LIDAR_TOL_M if k == "lidar" else DYN_RTOL
+                d = np.abs(got.astype(np.float64) - want.astype(np.float64))
+                assert np.all(d <= tol * np.maximum(1.0, np.abs(want))), (i, a, k, d.max())
+    env.close()
