@@ -156,3 +156,35 @@ def test_gap_follower_laps_without_collision(torch_cuda, track):
     assert float(total.max() - total.min()) == 0.0
     assert float(total[0]) > (0.4 if track == "barcelona" else 0.9)
     env.close()
+
+
+def test_policies_in_worlds_of_cars(torch_cuda):
+    """On-device policies with agents_per_world > 1: one controller / one latent per CAR, cleared when the car's world is
+    reset; the no-host rollout equals the host-driven loop bit for bit; the cars really interact (scans differ from the
+    single-car ones, contacts end worlds)."""
+    torch = torch_cuda
+    from racing_dreamer_b200 import DreamerPolicy, GapFollowerPolicy
+    kw = dict(tracks=("austria",), n_envs=512, agents_per_world=4, action_repeat=4, auto_reset=True, reset_mode="random_ball",
+              ball_spacing=0.9, seed=5, time_limit_steps=60)
+    for make_policy in (lambda e: GapFollowerPolicy(e), lambda e: DreamerPolicy(e, "austria_dreamer", noise="philox")):
+        outs = []
+        for mode in ("rollout", "stepwise"):
+            env = make_env(**kw)
+            pol = make_policy(env)
+            env.reset()
+            if mode == "rollout":
+                pol.rollout(50)
+            else:
+                for _ in range(50):
+                    env.step(pol.act())
+            f, i = env.get_state()
+            outs.append((f.cpu().numpy(), i.cpu().numpy(), env.buf["lidar"].cpu().numpy().copy(), env.read_stats()))
+            env.close()
+        assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+        assert np.array_equal(outs[0][2], outs[1][2])
+        for key in outs[0][3]:      # the statistics are float64 atomics: the order of the additions is not fixed
+            assert abs(outs[0][3][key] - outs[1][3][key]) <= 1e-9 * max(1.0, abs(outs[1][3][key])), key
+        st = outs[0][3]
+        assert st["episodes"] > 0 and st["env_steps"] == 512 * 50
+        ep = outs[0][1][_abi.I_EPISODE].reshape(-1, 4)
+        assert np.all(ep == ep[:, :1])          # worlds reset as a whole
