@@ -367,6 +367,49 @@ class RaceCarGymCompat(_SingleAgentBase):
                 {aid: bool(h["done"][k]) for k, aid in enumerate(self._ids)}, infos)
 
 
+class SingleAgentRaceCompat:
+    """``racecar_gym.envs.SingleAgentRaceEnv`` / ``ChangingTrackSingleAgentRaceEnv``-shaped view -- what the model-free
+    baselines build their wrapper chain on [REF baselines/racing/experiments/acme/experiment.py:66-93;
+    baselines/racing/experiments/sb3/sb_experiment.py:60-64]: one car, one sim tick per ``step``, observations / rewards /
+    dones NOT keyed by agent id, ``reset(mode=...)``; a list of tracks + ``order='sequential'`` moves to the next track at
+    every reset.  The reference's own ``FilterObservation -> Flatten -> NormalizeObservations -> FixedResetMode ->
+    TimeLimit -> ActionRepeat`` stack goes on top unchanged (``EnvConfig(clip_actions=True, rescale_actions=False,
+    repeat_semantics='baselines')`` is its fused form)."""
+
+    def __init__(self, track="austria", task="max_progress", device=None, scenario: Optional[str] = None,
+                 order: str = "sequential", **overrides):
+        self._env = RaceCarGymCompat(track, task, device=device, scenario=scenario, n_agents=1, order=order, **overrides)
+        self._id = self._env.agent_id
+
+    @property
+    def scenario(self):
+        return self._env.scenario
+
+    @property
+    def observation_space(self):
+        return self._env.observation_space[self._id]
+
+    @property
+    def action_space(self):
+        return self._env.action_space[self._id]
+
+    def reset(self, mode: str = "grid"):
+        return self._env.reset(mode=mode)[self._id]
+
+    def step(self, action):
+        obs, rew, done, info = self._env.step({self._id: action})
+        return obs[self._id], rew[self._id], done[self._id], info[self._id]
+
+    def set_next_env(self) -> None:
+        self._env.set_next_env()
+
+    def render(self, mode: str = "follow", **kwargs):
+        return self._env.render(mode=mode, agent=self._id)
+
+    def close(self):
+        self._env.close()
+
+
 def make_reference_env(track: str, task: str = "max_progress", action_repeat: int = 4, mode: str = "train",
                        device=None, **kw) -> ReferenceEnv:
     """``make_train_env`` / ``make_test_env`` of dream.py without the PyBullet sim [REF dreamer/dream.py:103-131]:

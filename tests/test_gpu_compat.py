@@ -293,3 +293,41 @@ def test_changing_track_env_and_render(torch_cuda):
         seq.render(mode="nope")
     seq.close()
     multi.close()
+
+
+def test_single_agent_env_shape_of_the_baselines(torch_cuda, golden_dir):
+    """SingleAgentRaceCompat (racecar_gym's SingleAgentRaceEnv surface) under the baselines' action chain restated by hand
+    -- Flatten's clip to [-1, 1] and ActionRepeat(4) that does not test the first tick's done
+    [REF baselines/racing/environment/single_agent.py:31-62] -- replays the fixture recorded from the unmodified classes;
+    with a list of tracks every reset moves on to the next one [REF baselines/racing/experiments/acme/experiment.py:90-93]."""
+    from racing_dreamer_b200 import SingleAgentRaceCompat
+    g = np.load(golden_dir / "baselines_stack_golden.npz")
+    R = int(g["repeat"])
+    env = SingleAgentRaceCompat("austria", "max_progress", device="cuda:0")
+    assert set(env.action_space.spaces) == {"motor", "steering"} and env.observation_space["lidar"].shape == (1080,)
+    rec = {k: [] for k in ("reward", "done", "progress", "lap", "time", "flags", "lidar")}
+    for t in range(g["actions"].shape[0]):
+        if g["reset_before"][t]:
+            env.reset(mode="grid")
+        a = np.clip(g["actions"][t], -1.0, 1.0)                                   # Flatten.step
+        act = {"motor": a[0], "steering": a[1]}
+        obs, total, done, info = env.step(act)                                   # ActionRepeat.step
+        for _ in range(R - 1):
+            obs, r, done, info = env.step(act)
+            total += r
+            if done:
+                break
+        rec["reward"].append(np.float32(total)); rec["done"].append(done); rec["progress"].append(np.float32(info["progress"]))
+        rec["lap"].append(info["lap"]); rec["time"].append(np.float32(info["time"]))
+        rec["flags"].append(_abi.F_COLLISION if info["wall_collision"] else 0)
+        rec["lidar"].append(obs["lidar"].astype(np.float32))
+    rec = {k: np.stack([np.asarray(x) for x in v]) for k, v in rec.items()}
+    helpers.assert_matches_baselines_golden(rec, g, float_tol=1e-5, lidar_tol=1e-3)
+    env.close()
+    seq = SingleAgentRaceCompat(["austria", "columbia"], "max_progress", device="cuda:0", order="sequential")
+    names = []
+    for _ in range(4):
+        seq.reset(mode="grid")
+        names.append(seq.scenario.world._config.name)
+    assert names[0] == names[2] != names[1] == names[3]
+    seq.close()
