@@ -300,7 +300,8 @@ int rd_rollout_dreamer(rd_env* env, int n_steps, const rd_outputs* out, float* a
 
 /* ---- stage entry points (teacher-forced parity tests; each is one kernel of the step) ---- */
 /* a2 LiDAR [REF dreamer/scenarios/max_progress/austria.yml:7 'lidar' sensor]: poses f64 [n,3]=(x,y,yaw),
- * map_ids i32[n] sorted ascending or NULL (= map 0), ranges f32 [n, n_beams]. */
+ * map_ids i32[n] sorted ascending or NULL (= map 0), ranges f32 [n, n_beams].  With agents_per_world = A > 1 consecutive
+ * poses form worlds (n must be a multiple of A, the cars of a world on one map) and see each other. */
 int rd_lidar_cast(rd_env* env, const double* poses_dev, const int32_t* map_ids_host, int n,
                   float* ranges_dev, void* stream);
 /* a5 OccupancyMapObs.step [REF dreamer/wrappers.py:390-408]: poses f64 [n,3], out u8 [n,64*64]. */

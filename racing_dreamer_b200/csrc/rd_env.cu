@@ -1126,6 +1126,12 @@ RD_API int rd_lidar_cast(rd_env* env, const double* poses_dev, const int32_t* ma
   if (!env || n < 0) return fail(env, RD_ERR_INVALID, "bad argument");
   if (n == 0) return RD_OK;  // empty batch: nothing to do (pointers may be null)
   if (!poses_dev || !ranges_dev) return fail(env, RD_ERR_INVALID, "null pointer");
+  if (env->cfg.agents_per_world > 1 && n % env->cfg.agents_per_world != 0)   // worlds = consecutive poses: whole worlds only
+    return fail(env, RD_ERR_INVALID, "rd_lidar_cast: %d poses are not whole worlds of %d cars", n, env->cfg.agents_per_world);
+  if (env->cfg.agents_per_world > 1 && map_ids_host)
+    for (int e = 0; e < n; ++e)
+      if (map_ids_host[e] != map_ids_host[e - e % env->cfg.agents_per_world])
+        return fail(env, RD_ERR_INVALID, "rd_lidar_cast: pose %d: the cars of one world must share a map", e);
   cudaStream_t s = (cudaStream_t)stream;
   int rc = sync_maps(env);
   if (rc) return rc;
