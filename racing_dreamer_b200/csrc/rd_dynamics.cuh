@@ -305,23 +305,36 @@ __global__ void __launch_bounds__(128) k_step(StepParams P, OutPtrs o, const flo
   if (e < e1) {
     double* f = P.f64;
     int32_t* I = P.i32;
+    // Every load of this env's state is issued up front, before the first branch: after a cold L2 (another kernel ran in
+    // between) each dependent round trip to HBM costs ~1 us of a ~40 us kernel -- the loads that used to sit behind the
+    // flags test and behind the tick loop (return, episode start, step counter) showed up as its top stall lines.
     int flags = I[(size_t)RD_I_FLAGS * n + e];
+    const int map_id = I[(size_t)RD_I_MAP * n + e];
+    const float act0 = actions[2 * e], act1 = actions[2 * e + 1];
+    double q[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) q[k] = f[(size_t)k * n + e];
+    double time = f[(size_t)RD_S_TIME * n + e], p = f[(size_t)RD_S_PROGRESS * n + e];
+    double last = f[(size_t)RD_S_LAST * n + e];
+    const double ret0 = f[(size_t)RD_S_RETURN * n + e], start0 = f[(size_t)RD_S_START * n + e];
+    int lap = I[(size_t)RD_I_LAP * n + e], cp = I[(size_t)RD_I_CHECKPOINT * n + e];
+    const int agent_step0 = I[(size_t)RD_I_AGENT_STEP * n + e];
     if (flags & RD_F_NEEDS_RESET) {  // frozen until reset [REF dreamer/wrappers.py:148]
       if (o.reward) o.reward[e] = 0.f;
       if (o.done) o.done[e] = 1;
-      if (o.progress) o.progress[e] = (float)f[(size_t)RD_S_PROGRESS * n + e];
-      if (o.lap) o.lap[e] = I[(size_t)RD_I_LAP * n + e];
-      if (o.time) o.time[e] = (float)f[(size_t)RD_S_TIME * n + e];
+      if (o.progress) o.progress[e] = (float)p;
+      if (o.lap) o.lap[e] = lap;
+      if (o.time) o.time[e] = (float)time;
       if (o.flags) o.flags[e] = (uint8_t)flags;
       P.recs[e].was_reset = 2;
     } else {
-      RD_STEP_MAP_T m = P.maps[I[(size_t)RD_I_MAP * n + e]];
+      RD_STEP_MAP_T m = P.maps[map_id];
       // a4 [REF dreamer/wrappers.py:129-134; baselines single_agent.py:55-56]: numpy keeps (action+1)/2 of a
       // float32 policy output in float32 and promotes to float64 at `* (high-low)` (float64 arrays).
       double a[2];
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        float af = actions[2 * e + k];
+        float af = k == 0 ? act0 : act1;
         if (cfg.clip_actions) af = af < -1.0f ? -1.0f : (af > 1.0f ? 1.0f : af);
         if (cfg.rescale_actions) {
           const float t = __fdiv_rn(__fadd_rn(af, 1.0f), 2.0f);
@@ -330,12 +343,6 @@ __global__ void __launch_bounds__(128) k_step(StepParams P, OutPtrs o, const flo
           a[k] = (double)af;
         }
       }
-      double q[7];
-#pragma unroll
-      for (int k = 0; k < 7; ++k) q[k] = f[(size_t)k * n + e];
-      double time = f[(size_t)RD_S_TIME * n + e], p = f[(size_t)RD_S_PROGRESS * n + e];
-      double last = f[(size_t)RD_S_LAST * n + e];
-      int lap = I[(size_t)RD_I_LAP * n + e], cp = I[(size_t)RD_I_CHECKPOINT * n + e];
       double total = 0.0;
       int done = 0;
       const int ncp = cfg.n_checkpoints;
@@ -372,10 +379,10 @@ __global__ void __launch_bounds__(128) k_step(StepParams P, OutPtrs o, const flo
         total = total + r;
         if (d && !(cfg.repeat_semantics == RD_REPEAT_BASELINES && t == 0 && cfg.action_repeat > 1)) { done = 1; break; }
       }
-      const int agent_step = I[(size_t)RD_I_AGENT_STEP * n + e] + 1;  // TimeLimit [REF dreamer/wrappers.py:147-154]
+      const int agent_step = agent_step0 + 1;  // TimeLimit [REF dreamer/wrappers.py:147-154]
       int timeout = 0;
       if (cfg.time_limit_steps > 0 && agent_step >= cfg.time_limit_steps) { timeout = !done; done = 1; }
-      const double ret = f[(size_t)RD_S_RETURN * n + e] + total;
+      const double ret = ret0 + total;
 #pragma unroll
       for (int k = 0; k < 7; ++k) f[(size_t)k * n + e] = q[k];
       f[(size_t)RD_S_TIME * n + e] = time; f[(size_t)RD_S_PROGRESS * n + e] = p;
@@ -392,7 +399,7 @@ __global__ void __launch_bounds__(128) k_step(StepParams P, OutPtrs o, const flo
       if (o.flags) o.flags[e] = (uint8_t)flags;
       st[6] = 1.0;
       if (done) {
-        st[0] = 1.0; st[1] = ret; st[2] = ((double)lap + p) - f[(size_t)RD_S_START * n + e];
+        st[0] = 1.0; st[1] = ret; st[2] = ((double)lap + p) - start0;
         st[3] = (double)agent_step; st[4] = (flags & RD_F_COLLISION) ? 1.0 : 0.0; st[5] = (double)(lap - 1);
         st[7] = timeout ? 1.0 : 0.0;
       }
@@ -467,7 +474,7 @@ __global__ void __launch_bounds__(128) k_step_ma(StepParams P, OutPtrs o, const 
   RD_STEP_MAP_T m = P.maps[run ? I[(size_t)RD_I_MAP * n + e] : 0];
   double act[2] = {0.0, 0.0};
   double q[7] = {0, 0, 0, 0, 0, 0, 0};
-  double time = 0.0, p = 0.0, last = 0.0, total = 0.0;
+  double time = 0.0, p = 0.0, last = 0.0, total = 0.0, ret0 = 0.0, start0 = 0.0;
   int lap = 1, cp = 0, agent_step0 = 0, opp = 0, done = 0;
   if (run) {
 #pragma unroll
@@ -486,6 +493,7 @@ __global__ void __launch_bounds__(128) k_step_ma(StepParams P, OutPtrs o, const 
     time = f[(size_t)RD_S_TIME * n + e]; p = f[(size_t)RD_S_PROGRESS * n + e]; last = f[(size_t)RD_S_LAST * n + e];
     lap = I[(size_t)RD_I_LAP * n + e]; cp = I[(size_t)RD_I_CHECKPOINT * n + e];
     agent_step0 = I[(size_t)RD_I_AGENT_STEP * n + e];
+    ret0 = f[(size_t)RD_S_RETURN * n + e]; start0 = f[(size_t)RD_S_START * n + e];
   }
   bool ticking = run;
   for (int tk = 0; tk < cfg.action_repeat; ++tk) {
@@ -570,7 +578,7 @@ __global__ void __launch_bounds__(128) k_step_ma(StepParams P, OutPtrs o, const 
     const int agent_step = agent_step0 + 1;  // TimeLimit [REF dreamer/wrappers.py:147-154]
     int timeout = 0;
     if (cfg.time_limit_steps > 0 && agent_step >= cfg.time_limit_steps) { timeout = !wdone; done = 1; wdone = 1; }
-    const double ret = f[(size_t)RD_S_RETURN * n + e] + total;
+    const double ret = ret0 + total;
 #pragma unroll
     for (int k = 0; k < 7; ++k) f[(size_t)k * n + e] = q[k];
     f[(size_t)RD_S_TIME * n + e] = time; f[(size_t)RD_S_PROGRESS * n + e] = p;
@@ -589,7 +597,7 @@ __global__ void __launch_bounds__(128) k_step_ma(StepParams P, OutPtrs o, const 
     if (o.opponents) o.opponents[e] = (uint8_t)opp;
     st[6] = 1.0;
     if (wdone && a == 0) {
-      st[0] = 1.0; st[1] = ret; st[2] = ((double)lap + p) - f[(size_t)RD_S_START * n + e];
+      st[0] = 1.0; st[1] = ret; st[2] = ((double)lap + p) - start0;
       st[3] = (double)agent_step; st[4] = (flags & (RD_F_COLLISION | RD_F_OPPONENT)) ? 1.0 : 0.0; st[5] = (double)(lap - 1);
       st[7] = timeout ? 1.0 : 0.0;
     }
