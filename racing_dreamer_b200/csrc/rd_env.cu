@@ -39,7 +39,8 @@ struct HostMap {
   void* d_next = nullptr;
   size_t hot_bytes = 0;    // bytes of the d_bits allocation (bits + clearance + distance): the L2-persisting window
   bool present = false;
-  int lidar_per_sm = -1;   // resident k_lidar CTAs per SM for this map (cached launch configuration)
+  int lidar_per_sm[8] = {-1, -1, -1, -1, -1, -1, -1, -1};   // resident k_lidar CTAs per SM for this map, per kernel
+                                                            // instantiation (cached launch configuration)
 };
 
 }  // namespace
@@ -276,13 +277,16 @@ int launch_lidar_t(rd_env* env, int map_id, const OriginRec* recs, const int32_t
   const size_t tab_bytes = ((size_t)2 * lp.n_beams * 8 + 15) & ~(size_t)15;
   const size_t smem = 16 + tab_bytes + (size_t)m.bits_bytes;
   auto kern = k_lidar<WARPS, AHEAD, CARS>;
-  int& per_sm = env->maps[map_id].lidar_per_sm;
-  if (per_sm < 0) {  // once per map: ask how many CTAs fit on an SM (the kernel is opted in to the device maximum)
-    bool& attr = env->lidar_attr_set[(WARPS == 32 ? 1 : 0) + (AHEAD ? 2 : 0) + (CARS ? 4 : 0)];
-    if (!attr) {
-      CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_optin));
-      attr = true;
-    }
+  // which instantiation runs depends on the map (warps), the handle (cars) AND the launch size (draw-ahead), so both
+  // the opt-in to the device's shared-memory maximum and the cached occupancy are kept per instantiation
+  const int variant = (WARPS == 32 ? 1 : 0) + (AHEAD ? 2 : 0) + (CARS ? 4 : 0);
+  bool& attr = env->lidar_attr_set[variant];
+  if (!attr) {
+    CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_optin));
+    attr = true;
+  }
+  int& per_sm = env->maps[map_id].lidar_per_sm[variant];
+  if (per_sm < 0) {  // once per map and instantiation: ask how many CTAs fit on an SM
     if (smem > (size_t)env->smem_optin) return fail(env, RD_ERR_INVALID, "map %d (%zu B) does not fit in shared memory", map_id, smem);
     int q = 0;
     CUDA_TRY(env, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, WARPS * 32, smem));
@@ -319,7 +323,8 @@ int launch_lidar(rd_env* env, int map_id, const OriginRec* recs, const int32_t* 
   // small maps: 16-warp CTAs (several per SM); large maps: 32-warp CTAs so one resident copy feeds 32 warps.
   // Long launches (>= 128 work items per resident warp) draw their work one chunk ahead (see k_lidar).
   const int warps = m.bits_bytes > 72 * 1024 ? 32 : 16;
-  const int per_sm = env->maps[map_id].lidar_per_sm > 0 ? env->maps[map_id].lidar_per_sm : 1;
+  int per_sm = 1;   // resident CTAs per SM as far as already known (any instantiation of this map: they differ by at most one)
+  for (int v = 0; v < 8; ++v) per_sm = std::max(per_sm, env->maps[map_id].lidar_per_sm[v]);
   const long long items = (long long)n_env * ((env->cfg.n_beams + 31) / 32);
   bool ahead = items >= 128ll * env->sm_count * per_sm * warps;
   if (const char* ev = std::getenv("RD_LIDAR_AHEAD")) ahead = std::atoi(ev) != 0;

@@ -388,3 +388,35 @@ def test_float16_scans_are_the_rounded_float32_scans(torch_cuda):
     with pytest.raises(RuntimeError, match="float32 scans"):
         GapFollowerPolicy(e16)
     e32.close(); e16.close(); h16.close()
+
+
+def test_lidar_kernel_variants_mix_on_one_handle(torch_cuda):
+    """One handle launches different k_lidar instantiations depending on the launch size (draw-ahead for long launches) --
+    e.g. the full batch in rd_step and small chunks in rd_step_host, or a large and a small rd_lidar_cast.  Every
+    instantiation must be opted in to the large shared-memory carve-out on its own (regression: 'invalid argument')."""
+    torch = torch_cuda
+    from racing_dreamer_b200 import EnvConfig
+    from racing_dreamer_b200.host import HostSteppedEnv
+    rng = np.random.RandomState(4)
+    for track in ("barcelona", "austria", "treitlstrasse_v2"):
+        env = make_env(torch, tracks=(track,), n_envs=8)
+        orc = make_oracle(env)
+        big = random_poses(env.tracks[0], 40000, rng)              # >= 128 items per resident warp: draw-ahead variant
+        small = big[:64]
+        a = env.lidar_cast(torch.from_numpy(small)).cpu().numpy()   # plain variant first ...
+        b = env.lidar_cast(torch.from_numpy(big)).cpu().numpy()     # ... then the other one on the same handle
+        c = env.lidar_cast(torch.from_numpy(small)).cpu().numpy()
+        assert np.array_equal(a, b[:64]) and np.array_equal(a, c)
+        assert np.abs(b[:2048] - orc.lidar_cast(big[:2048])).max() <= LIDAR_TOL_M
+        env.close()
+    # the host-facing path: k_step over 24576 envs, scans in chunks of very different sizes
+    ec = EnvConfig(tracks=("barcelona", "austria"), n_envs=24576, action_repeat=4, auto_reset=True, reset_mode="random", seed=2)
+    dev, host = make_env(torch, **{k: getattr(ec, k) for k in ("tracks", "n_envs", "action_repeat", "auto_reset", "reset_mode", "seed")}), \
+        HostSteppedEnv(ec, device="cuda:0", n_shards=8)
+    dev.reset(); host.reset()
+    for k in range(3):
+        a = rng.uniform(-1, 1, (24576, 2)).astype(np.float32)
+        obs = dev.step(torch.from_numpy(a).cuda())[0]
+        out = host.step(a)
+        assert np.array_equal(out["lidar"], obs["lidar"].cpu().numpy()), k
+    dev.close(); host.close()
