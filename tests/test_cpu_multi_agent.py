@@ -189,3 +189,31 @@ def test_fused_world_matches_the_reference_wrapper_stack(golden_dir):
                                g["reset_before"])
     helpers.assert_matches_multi_agent_golden(rec, g)
     assert (g["opponents"] != 0).sum() > 20 and g["done"].all(1).sum() >= 3   # contacts and time-outs are in the fixture
+
+
+def test_world_invariants_under_random_play():
+    """Laws of the world step that need no reference: contact is mutual, ranks are a permutation of 1..A per world, a car
+    never reports contact with itself, the cars of a world share time, step counter and episode counter."""
+    A, worlds = 4, 96
+    orc, tm = make(worlds=worlds, A=A, ball_spacing=0.7, time_limit_steps=25, seed=11)
+    orc.reset(mode=_abi.RESET_RANDOM_BALL)
+    rng = np.random.RandomState(3)
+    gain = np.tile(np.array([1.0, 0.15, 0.6, 0.05], np.float32), worlds)
+    contacts = 0
+    for k in range(60):
+        a = rng.uniform(-1, 1, (A * worlds, 2)).astype(np.float32)
+        a[:, 0] = ((np.abs(a[:, 0]) * 0.5 + 0.5) * gain) * 2 - 1
+        a[:, 1] *= 0.35
+        out = orc.step(a)
+        opp = out["opponents"].reshape(worlds, A)
+        for i in range(A):
+            assert not np.any(opp[:, i] >> i & 1)                               # never with itself
+            for j in range(A):
+                assert np.array_equal(opp[:, i] >> j & 1, opp[:, j] >> i & 1)   # mutual
+        assert np.array_equal(np.sort(out["rank"].reshape(worlds, A), axis=1), np.tile(np.arange(1, A + 1), (worlds, 1)))
+        assert np.array_equal((out["flags"] & _abi.F_OPPONENT) != 0, out["opponents"] != 0)
+        for row in (orc.f64[_abi.S_TIME], orc.i32[_abi.I_AGENT_STEP], orc.i32[_abi.I_EPISODE]):
+            w = row.reshape(worlds, A)
+            assert np.all(w == w[:, :1])
+        contacts += int((opp != 0).sum())
+    assert contacts > 50

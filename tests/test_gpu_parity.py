@@ -420,3 +420,27 @@ def test_lidar_kernel_variants_mix_on_one_handle(torch_cuda):
         out = host.step(a)
         assert np.array_equal(out["lidar"], obs["lidar"].cpu().numpy()), k
     dev.close(); host.close()
+
+
+@pytest.mark.parametrize("nb", [1, 31, 32, 33, 100, 1081])
+def test_lidar_ragged_beam_counts(torch_cuda, nb):
+    """Beam counts that are not multiples of the 32-beam work item (one group, a ragged last group, odd group counts in the
+    longest-first order) and the degenerate single beam, through the step and the stage entry."""
+    torch = torch_cuda
+    n = 160
+    env = make_env(torch, tracks=("treitlstrasse_v2", "austria"), n_envs=n, n_beams=nb, action_repeat=2, auto_reset=True,
+                   reset_mode="random", seed=nb, time_limit_steps=6)
+    orc = make_oracle(env)
+    o, r = env.reset(), orc.reset(mode=int(env.cfg.reset_mode))
+    assert o["lidar"].shape == (n, nb) and np.abs(o["lidar"].cpu().numpy() - r["lidar"]).max() <= LIDAR_TOL_M
+    rng = np.random.RandomState(nb)
+    for k in range(8):
+        a = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+        obs, rew, done, info = env.step(torch.from_numpy(a).cuda())
+        ref = orc.step(a)
+        assert np.abs(obs["lidar"].cpu().numpy() - ref["lidar"]).max() <= LIDAR_TOL_M
+        assert np.array_equal(done.cpu().numpy().astype(np.uint8), ref["done"])
+    poses = random_poses(env.tracks[1], 300, rng)
+    ids = np.ones(300, np.int32)
+    assert np.abs(env.lidar_cast(torch.from_numpy(poses), ids).cpu().numpy() - orc.lidar_cast(poses, ids)).max() <= LIDAR_TOL_M
+    env.close()
