@@ -25,9 +25,6 @@
 #ifndef OCC_THREADS
 #define OCC_THREADS 512
 #endif
-#ifndef RD_OCC_TILE_SHORTCUT
-#define RD_OCC_TILE_SHORTCUT 0   // 1: whole-tile uniform shortcut in the rotation stage (second-level block map)
-#endif
 #define OCC_ROWS 223        // 220 + mirrored border (index -1 and 220, 221)
 #define OCC_PITCH 227       // row pitch in floats: odd (row pass conflict-free) and = 3 mod 32 (rotated 8x4 tiles spread over the banks)
 #define OCC_XW 7            // 32-bit words per crop row
@@ -357,30 +354,6 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
         }
       uni[t] = same ? c : 2;
     }
-#if RD_OCC_TILE_SHORTCUT
-    __syncthreads();
-    // second level (into the storage of `cls`, which is dead now): the block AND its eight neighbours are uniform with
-    // the same constant.  A rotated 8x4 tile whose centre pixel's source falls into such a block lies within 4.5 cells
-    // of that source, i.e. inside the block or one of its neighbours, so the whole tile equals the constant and needs no
-    // per-pixel work.  Constant 1 requires all eight neighbours to exist and to be whole blocks (the last block row /
-    // column, 216..223, reaches beyond the crop's last sample 219, and a pixel there is "outside" = 0): every pixel of
-    // the tile is then inside the crop.  For constant 0 a neighbour beyond the crop counts as 0, which is what pixels
-    // outside the crop are.
-    uint8_t* uni2 = cls;
-    for (int t = tid; t < OCC_NB * OCC_NB; t += OCC_THREADS) {
-      const int bi = t / OCC_NB, bj = t - bi * OCC_NB;
-      const uint8_t c = uni[t];
-      bool same = c != 2;
-      for (int di = -1; di <= 1 && same; ++di)
-        for (int dj = -1; dj <= 1; ++dj) {
-          const int i = bi + di, j = bj + dj;
-          if (i < 0 || i >= OCC_NB || j < 0 || j >= OCC_NB) { if (c != 0) same = false; continue; }
-          if (c != 0 && (i == OCC_NB - 1 || j == OCC_NB - 1)) same = false;
-          if (uni[i * OCC_NB + j] != c) same = false;
-        }
-      uni2[t] = same ? c : 2;
-    }
-#endif
     // ---- B: prefilter, axis 0 (columns) then axis 1 (rows), float32; image stored at padded index (r+1, c+1) ----
     __syncthreads();
     occ_prefilter_axis<true>(coef + OCC_PITCH + 1, 1, OCC_PITCH, xb);       // axis 0: line = column
@@ -421,20 +394,6 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
         const bool inside = !(c0 < 0.0 || c0 > (double)(RD_OCC_IN - 1) || c1 < 0.0 || c1 > (double)(RD_OCC_IN - 1));
         const double f0 = floor(c0), f1 = floor(c1);
         const int i0 = inside ? (int)f0 : 0, i1 = inside ? (int)f1 : 0;
-#if RD_OCC_TILE_SHORTCUT
-        // whole-tile shortcut: lane 20 holds the tile's centre pixel (row 2, column 4)
-        uint32_t u2 = 2u;
-        if (lane == 20 && inside) u2 = (uint32_t)uni2[(i0 >> 3) * OCC_NB + (i1 >> 3)];
-        u2 = __shfl_sync(0xffffffffu, u2, 20);
-        if (u2 != 2u) {
-          if ((lane & 7) == 0) {
-            const int byte = (a * RD_OCC_MID + tx * 8) >> 3;
-            plane0[byte] = u2 ? (uint8_t)0xFF : (uint8_t)0;
-            plane1[byte] = 0;
-          }
-          continue;
-        }
-#endif
         const uint32_t u = inside ? (uint32_t)uni[(i0 >> 3) * OCC_NB + (i1 >> 3)] : 0u;
         if (u != 2u) {
           val = u;                                                   // constant neighbourhood (or outside the crop: 0)
