@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RD_ABI_VERSION 2
+#define RD_ABI_VERSION 3
 #define RD_MAX_AGENTS 4   /* cars per world: agents A..D [REF baselines/scenarios/max_progress/austria.yml:3-34] */
 #define RD_MAX_NSTEP 32   /* longest n of the n_step_progress task */
 
@@ -50,15 +50,23 @@ enum {
   RD_OBS_LIDAR = 1,          /* f32 [N, n_beams] metres */
   RD_OBS_OCCUPANCY = 2,      /* u8 [N, 64, 64] 'lidar_occupancy' [REF dreamer/wrappers.py:372-414] */
   RD_OBS_LIDAR_NORM = 4,     /* lidar stored as r/15 - 0.5 [REF dreamer/tools.py:274] instead of metres */
-  RD_OBS_LIDAR_F16 = 8       /* lidar stored as IEEE half (round to nearest even of the float32 value): what Collect hands on at
+  RD_OBS_LIDAR_F16 = 8,      /* lidar stored as IEEE half (round to nearest even of the float32 value): what Collect hands on at
                               * precision 16 [REF dreamer/wrappers.py:240-250 _convert; dreamer/dream.py:176-177].  lidar_dev then
                               * points to uint16 [N, n_beams]; halves the device->host bytes of the host-facing step.  The
                               * on-device policies read float32 scans and refuse this flag. */
+  RD_OBS_NORM_BASELINES = 16 /* the model-free chain's NormalizeObservations: lidar, pose and velocity stored as
+                              * (x - low) * (1 / (high - low)) per element, evaluated in float64 and rounded to float32
+                              * (SinglePrecisionWrapper) [REF baselines/racing/environment/single_agent.py:66-99;
+                              * baselines/racing/experiments/acme/experiment.py:66-75]; low/high = rd_config.obs_low/obs_high,
+                              * the Box bounds of the env's observation space.  Excludes RD_OBS_LIDAR_NORM. */
 };
+enum { RD_NORM_LIDAR = 0, RD_NORM_POSE = 1, RD_NORM_VELOCITY = 2 };   /* index into rd_config.obs_low / obs_high */
 /* action_repeat edge semantics [REF dreamer/wrappers.py:107-116 | baselines/.../single_agent.py:31-40] */
 enum { RD_REPEAT_DREAMER = 0, RD_REPEAT_BASELINES = 1 };
 
-/* state layout of rd_get_state / rd_set_state: f64 [RD_NF64][n_envs], i32 [RD_NI32][n_envs] (SoA) */
+/* state layout of rd_get_state / rd_set_state: f64 [RD_NF64][n_envs], i32 [RD_NI32][n_envs] (SoA).  Inside the library
+ * the fields are kept as SoA of 16-byte groups (double2 pairs / one int4 + one int2 per env) so that every state access
+ * of the step kernels is a 128-bit load or store; rd_get_state / rd_set_state convert. */
 enum {
   RD_S_X = 0, RD_S_Y, RD_S_STEER, RD_S_V, RD_S_YAW, RD_S_YAWRATE, RD_S_SLIP,
   RD_S_TIME,       /* seconds since reset */
@@ -66,6 +74,8 @@ enum {
   RD_S_LAST,       /* lap + progress at the previous tick (reward bookkeeping) */
   RD_S_RETURN,     /* episode return so far */
   RD_S_START,      /* lap + progress at the last reset (episode progress = lap + progress - start) */
+  RD_S_MAXPROG,    /* max over the episode's agent steps of lap + progress - 1, the per-episode statistic of tools.simulate
+                    * [REF dreamer/tools.py:181,195]; -1 right after a reset (lap + progress - 1 is never negative) */
   RD_NF64
 };
 enum {
@@ -132,6 +142,13 @@ typedef struct rd_config {
   int32_t agent_task[RD_MAX_AGENTS]; /* RD_TASK_* of agent index 0..3 (used when agents_per_world > 1) */
   int32_t n_step_progress;    /* n of n_step_progress, in sim ticks, 1..RD_MAX_NSTEP [REF .../austria.yml:18 n_steps: 10] */
   double ball_spacing;        /* random_ball / multi-agent random reset: metres of track between consecutive cars */
+  /* ---- the model-free (baselines) wrapper chain ---- */
+  int32_t time_limit_ticks;   /* gym TimeLimit(max_episode_steps) INSIDE ActionRepeat, i.e. counted in sim ticks: the tick
+                               * that brings the episode's tick count to this value is done, subject to the repeat
+                               * semantics like any task done [REF baselines/racing/experiments/acme/experiment.py:66-72;
+                               * gym 0.18.0 wrappers/time_limit.py]; 0 = off */
+  int32_t reserved1;
+  double obs_low[3], obs_high[3]; /* RD_OBS_NORM_BASELINES: Box bounds of lidar / pose / velocity (RD_NORM_*) */
   rd_vehicle vehicle;
 } rd_config;
 
@@ -155,12 +172,20 @@ typedef struct rd_outputs {
   /* multi-agent worlds (NULL or left untouched when agents_per_world <= 1) */
   int32_t* rank_dev;          /* [N]   info['rank']: 1 = leader of the world by lap + progress (ties: lower agent index) */
   uint8_t* opponents_dev;     /* [N]   info['opponent_collisions'] as a bit mask over the world's agent indices */
+  /* the two flags the reference's consumers read as booleans, ready-made (0 / 1) so that the host side decodes nothing
+   * [REF baselines/racing/environment/tasks.py:8 info['wall_collision']; baselines/racing/experiments/sb3/
+   * sb_experiment.py:82-88 info['wrong_way']] */
+  uint8_t* wrong_way_dev;     /* [N]   info['wrong_way'] */
+  uint8_t* wall_collision_dev;/* [N]   info['wall_collision'] */
 } rd_outputs;
 
 /* episode statistics accumulated on the device since the last rd_read_stats(reset=1)
  * [REF dreamer/tools.py:159-206 simulate(): per-episode return and max progress] */
 typedef struct rd_stats {
   double episodes, return_sum, progress_sum, length_sum, collisions, laps_completed, env_steps, timeouts;
+  double max_progress_sum;    /* sum over finished episodes of max_t (lap + progress - 1): what tools.simulate appends to
+                               * max_progresses per episode [REF dreamer/tools.py:181,195] (progress_sum is the FINAL
+                               * lap + progress - start instead); return_sum is its cum_reward [REF tools.py:182,194] */
 } rd_stats;
 
 /* ---- lifecycle: replaces RaceCarBaseEnv.__init__ -> MultiAgentScenario.from_spec + MultiAgentRaceEnv
@@ -310,6 +335,18 @@ int rd_occupancy_obs(rd_env* env, const double* poses_dev, const int32_t* map_id
 /* a1 dynamics only: state f64 [7][n] SoA (x,y,steer,v,yaw,yaw_rate,slip) in/out,
  * commands f64 [n,2] = sim-facing (motor, steering), n_ticks ticks of cfg.dt. */
 int rd_dynamics(rd_env* env, double* state_dev, const double* commands_dev, int n, int n_ticks, void* stream);
+
+/* a7/a8 one sim tick of progress / lap / wrong-way bookkeeping + task reward / done for teacher-forced poses (single-car
+ * rule, cfg.task) [REF consumers: dreamer/wrappers.py:218-219; dreamer/tools.py:195; baselines/racing/environment/
+ * tasks.py:4-22; task parameters dreamer/scenarios/max_progress/austria.yml:8-10]:
+ *   kin_dev      f64 [5][n] SoA (x, y, yaw, v, slip): the car AFTER the tick
+ *   steering_dev f64 [n] sim-facing steering command (max_speed reward) or NULL (= 0)
+ *   map_ids_host as rd_lidar_cast
+ *   book_f64_dev f64 [3][n] (time, progress, last = lap + progress of the previous tick), in/out
+ *   book_i32_dev i32 [3][n] (lap, checkpoint, flags), in/out
+ *   reward_dev   f64 [n] the tick's reward;  done_dev u8 [n] the task's done (no ActionRepeat / TimeLimit on top) */
+int rd_reward_done(rd_env* env, const double* kin_dev, const double* steering_dev, const int32_t* map_ids_host, int n,
+                   double* book_f64_dev, int32_t* book_i32_dev, double* reward_dev, uint8_t* done_dev, void* stream);
 
 /* ---- state access (checkpoint/resume; teacher forcing); either pointer may be NULL.  The ring of the n_step_progress
  *      task is not part of the layout: restoring the float64 part restarts it from the restored lap + progress ---- */

@@ -187,6 +187,26 @@ class Oracle:
                               C.c_int(s.shape[1]), C.c_int(n_ticks))
         return s
 
+    def reward_done(self, kin: np.ndarray, steering: Optional[np.ndarray], book_f64: np.ndarray, book_i32: np.ndarray,
+                    map_ids: Optional[np.ndarray] = None):
+        """One tick of a7/a8 bookkeeping for teacher-forced poses (mirrors rd_reward_done): kin [5, n] = (x, y, yaw, v,
+        slip) after the tick, book_f64 [3, n] = (time, progress, last), book_i32 [3, n] = (lap, checkpoint, flags).
+        Returns (book_f64', book_i32', reward f64[n], done u8[n])."""
+        k = np.ascontiguousarray(kin, dtype=np.float64)
+        n = k.shape[1]
+        st = None if steering is None else np.ascontiguousarray(steering, dtype=np.float64)
+        bf = np.ascontiguousarray(book_f64, dtype=np.float64).copy()
+        bi = np.ascontiguousarray(book_i32, dtype=np.int32).copy()
+        ids = None if map_ids is None else np.ascontiguousarray(map_ids, dtype=np.int32)
+        rew = np.zeros(n, np.float64)
+        done = np.zeros(n, np.uint8)
+        self.lib.orc_reward_done(C.byref(self.cfg), self._cmaps, C.c_void_p(k.ctypes.data),
+                                 C.c_void_p(st.ctypes.data if st is not None else None),
+                                 C.c_void_p(ids.ctypes.data if ids is not None else None), C.c_int(n),
+                                 C.c_void_p(bf.ctypes.data), C.c_void_p(bi.ctypes.data), C.c_void_p(rew.ctypes.data),
+                                 C.c_void_p(done.ctypes.data))
+        return bf, bi, rew, done
+
     def beam_table(self):
         ca = np.zeros(self.nb, np.float64)
         sa = np.zeros(self.nb, np.float64)

@@ -88,6 +88,11 @@ ORC_API void orc_default_config(rd_config* c) {
   for (int a = 0; a < RD_MAX_AGENTS; ++a) c->agent_task[a] = RD_TASK_MAX_PROGRESS;
   c->n_step_progress = 10; /* [REF baselines/scenarios/max_progress/austria.yml:18] */
   c->ball_spacing = 1.5;
+  c->time_limit_ticks = 0;
+  /* Box bounds of the observation space [NEW-SPEC: racecar_gym's sensor spaces are not in tree] */
+  c->obs_low[RD_NORM_LIDAR] = 0.0;      c->obs_high[RD_NORM_LIDAR] = 15.0;
+  c->obs_low[RD_NORM_POSE] = -100.0;    c->obs_high[RD_NORM_POSE] = 100.0;
+  c->obs_low[RD_NORM_VELOCITY] = -10.0; c->obs_high[RD_NORM_VELOCITY] = 10.0;
   rd_vehicle* v = &c->vehicle;
   v->mu = 1.0489; v->c_sf = 4.718; v->c_sr = 5.4562; v->lf = 0.15875; v->lr = 0.17145; v->h_cg = 0.074;
   v->mass = 3.74; v->inertia = 0.04712;
@@ -171,6 +176,10 @@ static float finish_range(const rd_config* cfg, float r, uint32_t gid, uint32_t 
   r = r < rmin ? rmin : r;
   r = r > rmax ? rmax : r;
   if (cfg->obs_flags & RD_OBS_LIDAR_NORM) r = r / rmax - 0.5f; /* [REF dreamer/tools.py:274] */
+  /* NormalizeObservations: (observation - low) * scaler, scaler = 1.0 / (high - low), float64 arrays
+   * [REF baselines/racing/environment/single_agent.py:66-99]; SinglePrecisionWrapper rounds to float32 afterwards */
+  else if (cfg->obs_flags & RD_OBS_NORM_BASELINES)
+    r = (float)(((double)r - cfg->obs_low[RD_NORM_LIDAR]) * (1.0 / (cfg->obs_high[RD_NORM_LIDAR] - cfg->obs_low[RD_NORM_LIDAR])));
   return r;
 }
 
@@ -529,6 +538,7 @@ static void reset_one(const rd_config* cfg, const orc_map* maps, orc_view* s, in
   s->f[RD_S_LAST][e] = 1.0 + p;
   s->f[RD_S_START][e] = 1.0 + p;
   s->f[RD_S_RETURN][e] = 0.0;
+  s->f[RD_S_MAXPROG][e] = -1.0; /* no step yet: lap + progress - 1 is never negative */
   s->i[RD_I_LAP][e] = 1;
   s->i[RD_I_CHECKPOINT][e] = checkpoint_of(cfg, p);
   s->i[RD_I_FLAGS][e] = 0;
@@ -569,14 +579,15 @@ static void write_obs(const rd_config* cfg, const orc_map* maps, const double* c
   const double two_pi = 6.283185307179586;
   double wy = yaw - rint(yaw / two_pi) * two_pi;
   double vx = v * cos(slip), vy = v * sin(slip);
-  if (o->pose) {
-    float* p = o->pose + (size_t)e * 6;
-    p[0] = (float)x; p[1] = (float)y; p[2] = 0.f; p[3] = 0.f; p[4] = 0.f; p[5] = (float)wy;
+  double pose[6] = {x, y, 0.0, 0.0, 0.0, wy};
+  double vel[6] = {vx, vy, 0.0, 0.0, 0.0, s->f[RD_S_YAWRATE][e]};
+  if (cfg->obs_flags & RD_OBS_NORM_BASELINES) { /* NormalizeObservations [REF baselines single_agent.py:92-99] */
+    const double pl = cfg->obs_low[RD_NORM_POSE], ps = 1.0 / (cfg->obs_high[RD_NORM_POSE] - cfg->obs_low[RD_NORM_POSE]);
+    const double vl = cfg->obs_low[RD_NORM_VELOCITY], vs = 1.0 / (cfg->obs_high[RD_NORM_VELOCITY] - cfg->obs_low[RD_NORM_VELOCITY]);
+    for (int k = 0; k < 6; ++k) { pose[k] = (pose[k] - pl) * ps; vel[k] = (vel[k] - vl) * vs; }
   }
-  if (o->velocity) {
-    float* q = o->velocity + (size_t)e * 6;
-    q[0] = (float)vx; q[1] = (float)vy; q[2] = 0.f; q[3] = 0.f; q[4] = 0.f; q[5] = (float)s->f[RD_S_YAWRATE][e];
-  }
+  if (o->pose) for (int k = 0; k < 6; ++k) o->pose[(size_t)e * 6 + k] = (float)pose[k];
+  if (o->velocity) for (int k = 0; k < 6; ++k) o->velocity[(size_t)e * 6 + k] = (float)vel[k];
   if (o->speed) o->speed[e] = (float)sqrt(vx * vx + vy * vy); /* [REF dreamer/wrappers.py:66] */
 }
 
@@ -654,7 +665,7 @@ static void step_one(const rd_config* cfg, const orc_map* maps, orc_view* s, int
   double time = s->f[RD_S_TIME][e], p = s->f[RD_S_PROGRESS][e], last = s->f[RD_S_LAST][e];
   int lap = s->i[RD_I_LAP][e], cp = s->i[RD_I_CHECKPOINT][e], flags = s->i[RD_I_FLAGS][e];
   double total = 0.0;
-  int done = 0;
+  int done = 0, tick_timeout = 0;
   const int ncp = cfg->n_checkpoints;
   for (int t = 0; t < cfg->action_repeat; ++t) {
     st_tick(cfg, q, a[0], a[1]);
@@ -686,6 +697,12 @@ static void step_one(const rd_config* cfg, const orc_map* maps, orc_view* s, int
       if (col) r = r + cfg->collision_reward;
       d = (cfg->terminate_on_collision && col) || (lap > cfg->laps) || (time > cfg->time_limit);
     }
+    /* gym TimeLimit inside ActionRepeat (the model-free chain): the tick that brings the episode's tick count to the
+     * limit is done [REF baselines/racing/experiments/acme/experiment.py:66-72; gym 0.18.0 wrappers/time_limit.py] */
+    tick_timeout = 0;
+    if (cfg->time_limit_ticks > 0 && s->i[RD_I_AGENT_STEP][e] * cfg->action_repeat + t + 1 >= cfg->time_limit_ticks) {
+      tick_timeout = !d; d = 1;
+    }
     last = cur;
     total = total + r;
     /* dreamer: stop at the first done [REF dreamer/wrappers.py:112]; baselines: the done of tick 0 is not
@@ -693,9 +710,13 @@ static void step_one(const rd_config* cfg, const orc_map* maps, orc_view* s, int
     if (d && !(cfg->repeat_semantics == RD_REPEAT_BASELINES && t == 0 && cfg->action_repeat > 1)) { done = 1; break; }
   }
   int agent_step = s->i[RD_I_AGENT_STEP][e] + 1;
-  int timeout = 0;
-  if (cfg->time_limit_steps > 0 && agent_step >= cfg->time_limit_steps) { timeout = !done; done = 1; }
+  int timeout = done ? tick_timeout : 0;
+  if (cfg->time_limit_steps > 0 && agent_step >= cfg->time_limit_steps) { timeout = timeout || !done; done = 1; }
   double ret = s->f[RD_S_RETURN][e] + total;
+  /* tools.simulate's per-episode statistic: max over the agent steps of lap + progress - 1 [REF dreamer/tools.py:181,195] */
+  double epi = ((double)lap + p) - 1.0;
+  double mp = epi > s->f[RD_S_MAXPROG][e] ? epi : s->f[RD_S_MAXPROG][e];
+  s->f[RD_S_MAXPROG][e] = mp;
   /* commit */
   for (int k = 0; k < 7; ++k) s->f[k][e] = q[k];
   s->f[RD_S_TIME][e] = time; s->f[RD_S_PROGRESS][e] = p; s->f[RD_S_LAST][e] = last; s->f[RD_S_RETURN][e] = ret;
@@ -719,6 +740,7 @@ static void step_one(const rd_config* cfg, const orc_map* maps, orc_view* s, int
       st->collisions += (flags & RD_F_COLLISION) ? 1.0 : 0.0;
       st->laps_completed += (double)(lap - 1);
       st->timeouts += timeout ? 1.0 : 0.0;
+      st->max_progress_sum += mp;
     }
   }
   if (done && cfg->auto_reset) { reset_one(cfg, maps, s, e, cfg->reset_mode); *was_reset = 1; }
@@ -763,6 +785,11 @@ static void step_world(const rd_config* cfg, const orc_map* maps, orc_view* s, i
   double act[RD_MAX_AGENTS][2], q[RD_MAX_AGENTS][7], time[RD_MAX_AGENTS], p[RD_MAX_AGENTS], last[RD_MAX_AGENTS];
   double total[RD_MAX_AGENTS], cs[RD_MAX_AGENTS][2];
   int lap[RD_MAX_AGENTS], cp[RD_MAX_AGENTS], flags[RD_MAX_AGENTS], opp[RD_MAX_AGENTS], done[RD_MAX_AGENTS];
+  int tick_timeout[RD_MAX_AGENTS];
+  /* baselines semantics: several cars -> multi_agent.py (every tick runs, dones are OR-ed); one car -> single_agent.py
+   * (the first tick's done is not tested, a later one stops the repeat), exactly as step_one */
+  const int ma_or = cfg->repeat_semantics == RD_REPEAT_BASELINES && A > 1;
+  const int sa_skip = cfg->repeat_semantics == RD_REPEAT_BASELINES && A == 1;
   int col[RD_MAX_AGENTS], inside[RD_MAX_AGENTS];
   const int ncp = cfg->n_checkpoints;
   const double hl = 0.5 * cfg->vehicle.body_length, hw = 0.5 * cfg->vehicle.body_width;
@@ -782,7 +809,7 @@ static void step_world(const rd_config* cfg, const orc_map* maps, orc_view* s, i
     for (int k = 0; k < 7; ++k) q[a][k] = s->f[k][e];
     time[a] = s->f[RD_S_TIME][e]; p[a] = s->f[RD_S_PROGRESS][e]; last[a] = s->f[RD_S_LAST][e];
     lap[a] = s->i[RD_I_LAP][e]; cp[a] = s->i[RD_I_CHECKPOINT][e]; flags[a] = s->i[RD_I_FLAGS][e];
-    total[a] = 0.0; opp[a] = 0; done[a] = 0;
+    total[a] = 0.0; opp[a] = 0; done[a] = 0; tick_timeout[a] = 0;
   }
   const int agent_step0 = s->i[RD_I_AGENT_STEP][e0];
   for (int tk = 0; tk < cfg->action_repeat; ++tk) {
@@ -834,19 +861,25 @@ static void step_world(const rd_config* cfg, const orc_map* maps, orc_view* s, i
         if (hitc) r = r + cfg->collision_reward;
         d = (cfg->terminate_on_collision && hitc) || (lap[a] > cfg->laps) || (time[a] > cfg->time_limit);
       }
+      int tto = 0;
+      if (cfg->time_limit_ticks > 0 && agent_step0 * cfg->action_repeat + tk + 1 >= cfg->time_limit_ticks) { tto = !d; d = 1; }
       last[a] = cur;
       total[a] = total[a] + r;
-      if (cfg->repeat_semantics == RD_REPEAT_BASELINES) done[a] |= d; else done[a] = d;
-      any |= d;
+      if (ma_or) { done[a] |= d; tick_timeout[a] |= tto; }
+      else {
+        d = d && !(sa_skip && tk == 0 && cfg->action_repeat > 1);
+        done[a] = d; tick_timeout[a] = d ? tto : 0;
+        any |= d;
+      }
     }
-    if (any && cfg->repeat_semantics != RD_REPEAT_BASELINES) break;
+    if (any) break;
   }
   int wdone = 0;
   for (int a = 0; a < A; ++a) wdone |= done[a];
   const int agent_step = agent_step0 + 1;
-  int timeout = 0;
+  int timeout = done[0] ? tick_timeout[0] : 0;
   if (cfg->time_limit_steps > 0 && agent_step >= cfg->time_limit_steps) {
-    timeout = !wdone; wdone = 1;
+    timeout = timeout || !wdone; wdone = 1;
     for (int a = 0; a < A; ++a) done[a] = 1;
   }
   for (int a = 0; a < A; ++a) {
@@ -859,6 +892,9 @@ static void step_world(const rd_config* cfg, const orc_map* maps, orc_view* s, i
       if (other > mine || (other == mine && j < a)) rank += 1;
     }
     const double ret = s->f[RD_S_RETURN][e] + total[a];
+    const double epi = ((double)lap[a] + p[a]) - 1.0;
+    const double mp = epi > s->f[RD_S_MAXPROG][e] ? epi : s->f[RD_S_MAXPROG][e];
+    s->f[RD_S_MAXPROG][e] = mp;
     for (int k = 0; k < 7; ++k) s->f[k][e] = q[a][k];
     s->f[RD_S_TIME][e] = time[a]; s->f[RD_S_PROGRESS][e] = p[a]; s->f[RD_S_LAST][e] = last[a];
     s->f[RD_S_RETURN][e] = ret;
@@ -884,6 +920,7 @@ static void step_world(const rd_config* cfg, const orc_map* maps, orc_view* s, i
         st->collisions += (flags[a] & (RD_F_COLLISION | RD_F_OPPONENT)) ? 1.0 : 0.0;
         st->laps_completed += (double)(lap[a] - 1);
         st->timeouts += timeout ? 1.0 : 0.0;
+        st->max_progress_sum += mp;
       }
     }
   }
@@ -944,16 +981,64 @@ ORC_API void orc_step(const rd_config* cfg, const orc_map* maps, double* f64, in
     {
       acc.episodes += loc.episodes; acc.return_sum += loc.return_sum; acc.progress_sum += loc.progress_sum;
       acc.length_sum += loc.length_sum; acc.collisions += loc.collisions; acc.laps_completed += loc.laps_completed;
-      acc.env_steps += loc.env_steps; acc.timeouts += loc.timeouts;
+      acc.env_steps += loc.env_steps; acc.timeouts += loc.timeouts; acc.max_progress_sum += loc.max_progress_sum;
     }
   }
   if (stats) {
     stats->episodes += acc.episodes; stats->return_sum += acc.return_sum; stats->progress_sum += acc.progress_sum;
     stats->length_sum += acc.length_sum; stats->collisions += acc.collisions;
     stats->laps_completed += acc.laps_completed; stats->env_steps += acc.env_steps; stats->timeouts += acc.timeouts;
+    stats->max_progress_sum += acc.max_progress_sum;
   }
   free(mark);
   free(ca);
+}
+
+/* a7/a8 stage entry (mirrors rd_reward_done): one sim tick of progress / lap / wrong-way bookkeeping + the task's reward
+ * and done for teacher-forced poses.  kin [5][n] = (x, y, yaw, v, slip) AFTER the tick; steering [n] or NULL;
+ * book_f64 [3][n] = (time, progress, last), book_i32 [3][n] = (lap, checkpoint, flags), both in/out. */
+ORC_API void orc_reward_done(const rd_config* cfg, const orc_map* maps, const double* kin, const double* steering,
+                             const int32_t* map_ids, int n, double* book_f64, int32_t* book_i32, double* reward,
+                             uint8_t* done) {
+  const int ncp = cfg->n_checkpoints;
+  for (int e = 0; e < n; ++e) {
+    const orc_map* m = &maps[map_ids ? map_ids[e] : 0];
+    const double x = kin[e], y = kin[(size_t)n + e], yaw = kin[(size_t)2 * n + e], v = kin[(size_t)3 * n + e];
+    const double slip = kin[(size_t)4 * n + e];
+    double time = book_f64[e] + cfg->dt, p = book_f64[(size_t)n + e], last = book_f64[(size_t)2 * n + e];
+    int lap = book_i32[e], cp = book_i32[(size_t)n + e], flags = book_i32[(size_t)2 * n + e];
+    int col = collides(cfg, m, x, y, yaw);
+    int cx, cy;
+    int inside = cell_of(m, x, y, &cx, &cy);
+    flags &= ~(RD_F_COLLISION | RD_F_LEFT_MAP);
+    if (col) flags |= RD_F_COLLISION;
+    if (!inside) flags |= RD_F_LEFT_MAP;
+    if (!(x == x && y == y && v == v && yaw == yaw)) flags |= RD_F_NAN;
+    progress_at(m, x, y, &p);
+    int cn = checkpoint_of(cfg, p);
+    if (cn == cp + 1) { cp = cn; flags &= ~RD_F_WRONG_WAY; }
+    else if (cp == ncp - 1 && cn == 0 && ncp > 1) { lap += 1; cp = 0; flags &= ~RD_F_WRONG_WAY; }
+    else if (cn == cp - 1 || (cp == 0 && cn == ncp - 1 && ncp > 1)) { flags |= RD_F_WRONG_WAY; }
+    const double cur = (double)lap + p;
+    double r;
+    int d;
+    if (cfg->task == RD_TASK_MAX_SPEED) { /* [REF baselines/racing/environment/tasks.py:6-18] */
+      r = col ? -1.0 : -exp(fabs(steering ? steering[e] : 0.0) - v * cos(slip));
+      d = 0;
+    } else {
+      double delta = cur - last;
+      if (delta > 0.5) delta = delta - 1.0;
+      if (delta < -0.5) delta = delta + 1.0;
+      if (cfg->progress_abs) delta = fabs(delta);
+      r = cfg->frame_reward + cfg->progress_reward * delta;
+      if (col) r = r + cfg->collision_reward;
+      d = (cfg->terminate_on_collision && col) || (lap > cfg->laps) || (time > cfg->time_limit);
+    }
+    book_f64[e] = time; book_f64[(size_t)n + e] = p; book_f64[(size_t)2 * n + e] = cur;
+    book_i32[e] = lap; book_i32[(size_t)n + e] = cp; book_i32[(size_t)2 * n + e] = flags;
+    reward[e] = r;
+    done[e] = (uint8_t)(d ? 1 : 0);
+  }
 }
 
 /* ------------------------------------------------------------------------------------------------ */

@@ -162,6 +162,98 @@ def reference_baselines_env():
     return _load("_ref_baselines_single_agent", "baselines/racing/environment/single_agent.py")
 
 
+def reference_baselines_common():
+    """The reference's baselines/racing/environment/common.py, unmodified (FixedResetMode, InfoToObservation)."""
+    install()
+    return _load("_ref_baselines_common", "baselines/racing/environment/common.py")
+
+
+class FilterObservation(ObservationWrapper):
+    """Restatement of gym.wrappers.FilterObservation (gym==0.18.0, pinned at baselines/docker/requirements_acme.txt:40;
+    gym itself is not in this image): keeps the `filter_keys` entries of a Dict observation and of its space.  Used by the
+    model-free wrap chains [REF baselines/racing/experiments/acme/experiment.py:67,78]."""
+
+    def __init__(self, env, filter_keys=None):
+        super().__init__(env)
+        keys = list(env.observation_space.spaces) if filter_keys is None else list(filter_keys)
+        self._filter_keys = keys
+        self.observation_space = Dict([(k, sp) for k, sp in env.observation_space.spaces.items() if k in keys])
+
+    def observation(self, observation):
+        return type(observation)([(k, v) for k, v in observation.items() if k in self._filter_keys])
+
+
+class GymTimeLimit(Wrapper):
+    """Restatement of gym.wrappers.TimeLimit (gym==0.18.0): counts env.step calls since reset; the step that reaches
+    max_episode_steps returns done=True and info['TimeLimit.truncated'] = not done
+    [REF baselines/racing/experiments/acme/experiment.py:71,83 TimeLimit(env, max_episode_steps=...)]."""
+
+    def __init__(self, env, max_episode_steps):
+        super().__init__(env)
+        self._max_episode_steps = max_episode_steps
+        self._elapsed_steps = None
+
+    def step(self, action):
+        assert self._elapsed_steps is not None, "Cannot call env.step() before calling reset()"
+        observation, reward, done, info = self.env.step(action)
+        self._elapsed_steps += 1
+        if self._elapsed_steps >= self._max_episode_steps:
+            info["TimeLimit.truncated"] = not done
+            done = True
+        return observation, reward, done, info
+
+    def reset(self, **kwargs):
+        self._elapsed_steps = 0
+        return self.env.reset(**kwargs)
+
+
+def reference_tools():
+    """The reference's dreamer/tools.py, unmodified, with tensorflow / tensorflow_probability / tfplot / imageio stubbed
+    (none of them is in this image): only the pure-Python driver loop `simulate` [REF dreamer/tools.py:154-206] is run."""
+    install()
+
+    class _Any:
+        """Permissive stand-in: any attribute is another stand-in, calling it returns a stand-in -- or the argument itself
+        when used as a decorator on a function."""
+        def __init__(self, name="stub"):
+            self.__name__ = name
+        def __getattr__(self, k):
+            if k.startswith("__"):
+                raise AttributeError(k)
+            return _Any(k)
+        def __call__(self, *a, **kw):
+            if len(a) == 1 and not kw and callable(a[0]) and not isinstance(a[0], _Any):
+                return a[0]
+            return _Any()
+        def __enter__(self):
+            return self
+        def __exit__(self, *exc):
+            return False
+
+    def module(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        m.__getattr__ = lambda k: _Any(k)   # PEP 562: anything else
+        sys.modules[name] = m
+        return m
+
+    class _Base:
+        pass
+
+    tfd = module("tensorflow_probability.distributions", MultivariateNormalDiag=type("MultivariateNormalDiag", (), {}),
+                 Categorical=type("Categorical", (), {}))
+    module("tensorflow_probability", distributions=tfd, bijectors=types.SimpleNamespace(Bijector=_Base))
+    tf1 = module("tensorflow.compat.v1")
+    module("tensorflow.compat", v1=tf1)
+    prec = module("tensorflow.keras.mixed_precision.experimental")
+    mp = module("tensorflow.keras.mixed_precision", experimental=prec)
+    keras = module("tensorflow.keras", mixed_precision=mp)
+    module("tensorflow", Module=_Base, compat=sys.modules["tensorflow.compat"], keras=keras)
+    module("tfplot", autowrap=lambda *a, **kw: (lambda f: f))
+    module("imageio")
+    return _load("_ref_dreamer_tools", "dreamer/tools.py")
+
+
 def reference_tasks():
     install()
     return _load("_ref_baselines_tasks", "baselines/racing/environment/tasks.py")

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_AGENTS = 4   # RD_MAX_AGENTS
 MAX_NSTEP = 32   # RD_MAX_NSTEP
 
@@ -19,10 +19,11 @@ RESET_MODES = {"grid": RESET_GRID, "random": RESET_RANDOM, "random_bidirectional
 TASK_MAX_PROGRESS, TASK_MAX_SPEED, TASK_N_STEP_PROGRESS = 0, 1, 2
 TASKS = {"maximize_progress": TASK_MAX_PROGRESS, "max_progress": TASK_MAX_PROGRESS,
          "max_speed": TASK_MAX_SPEED, "maximize_speed": TASK_MAX_SPEED, "n_step_progress": TASK_N_STEP_PROGRESS}
-OBS_LIDAR, OBS_OCCUPANCY, OBS_LIDAR_NORM, OBS_LIDAR_F16 = 1, 2, 4, 8
+OBS_LIDAR, OBS_OCCUPANCY, OBS_LIDAR_NORM, OBS_LIDAR_F16, OBS_NORM_BASELINES = 1, 2, 4, 8, 16
+NORM_LIDAR, NORM_POSE, NORM_VELOCITY = 0, 1, 2
 REPEAT_DREAMER, REPEAT_BASELINES = 0, 1
 
-S_X, S_Y, S_STEER, S_V, S_YAW, S_YAWRATE, S_SLIP, S_TIME, S_PROGRESS, S_LAST, S_RETURN, S_START, NF64 = range(13)
+S_X, S_Y, S_STEER, S_V, S_YAW, S_YAWRATE, S_SLIP, S_TIME, S_PROGRESS, S_LAST, S_RETURN, S_START, S_MAXPROG, NF64 = range(14)
 I_LAP, I_CHECKPOINT, I_FLAGS, I_AGENT_STEP, I_EPISODE, I_MAP, NI32 = range(7)
 F_WRONG_WAY, F_COLLISION, F_NEEDS_RESET, F_LEFT_MAP, F_NAN, F_OPPONENT = 1, 2, 4, 8, 16, 32
 
@@ -54,6 +55,8 @@ class RdConfig(C.Structure):
         ("lidar_noise", C.c_float), ("reserved0", C.c_float),
         ("agents_per_world", C.c_int32), ("agent_task", C.c_int32 * MAX_AGENTS), ("n_step_progress", C.c_int32),
         ("ball_spacing", C.c_double),
+        ("time_limit_ticks", C.c_int32), ("reserved1", C.c_int32),
+        ("obs_low", C.c_double * 3), ("obs_high", C.c_double * 3),
         ("vehicle", RdVehicle),
     ]
 
@@ -66,13 +69,14 @@ class RdConfig(C.Structure):
 class RdOutputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "lidar_dev", "occupancy_dev", "pose_dev", "velocity_dev", "speed_dev", "reward_dev", "done_dev",
-        "progress_dev", "lap_dev", "time_dev", "flags_dev", "rank_dev", "opponents_dev")]
+        "progress_dev", "lap_dev", "time_dev", "flags_dev", "rank_dev", "opponents_dev", "wrong_way_dev",
+        "wall_collision_dev")]
 
 
 class RdStats(C.Structure):
     _fields_ = [(n, C.c_double) for n in (
         "episodes", "return_sum", "progress_sum", "length_sum", "collisions", "laps_completed", "env_steps",
-        "timeouts")]
+        "timeouts", "max_progress_sum")]
 
     def as_dict(self):
         return {n: float(getattr(self, n)) for n, _ in self._fields_}
@@ -117,7 +121,7 @@ RD_PRECISION_TF32X3, RD_PRECISION_TF32 = 0, 1
 
 EXPORTS = (
     "rd_default_config", "rd_create", "rd_destroy", "rd_last_error", "rd_abi_version", "rd_upload_map",
-    "rd_assign_maps", "rd_reset", "rd_step", "rd_lidar_cast", "rd_occupancy_obs", "rd_dynamics",
+    "rd_assign_maps", "rd_reset", "rd_step", "rd_lidar_cast", "rd_occupancy_obs", "rd_dynamics", "rd_reward_done",
     "rd_get_state", "rd_set_state", "rd_read_stats", "rd_launch_count", "rd_enable_timing", "rd_read_timing",
     "rd_host_init", "rd_reset_host", "rd_step_host", "rd_step_host_begin", "rd_step_host_end",
     "rd_gap_follower_defaults", "rd_policy_gap_follower_init", "rd_policy_gap_follower", "rd_rollout_gap_follower",
@@ -183,6 +187,8 @@ def load_library() -> C.CDLL:
     lib.rd_occupancy_obs.restype = i32
     lib.rd_dynamics.argtypes = [vp, vp, vp, i32, i32, vp]
     lib.rd_dynamics.restype = i32
+    lib.rd_reward_done.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
+    lib.rd_reward_done.restype = i32
     lib.rd_get_state.argtypes = [vp, vp, vp, vp]
     lib.rd_get_state.restype = i32
     lib.rd_set_state.argtypes = [vp, vp, vp, vp]

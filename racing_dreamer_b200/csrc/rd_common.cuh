@@ -25,6 +25,7 @@ struct DevMap {
   int coarse_off;        // byte offset of the clearance field u8[ch][cw] (rd_march.cuh)
   int cw, ch, cshift;
   double res, inv_res, ox, oy;
+  double inv_dmax;       // RN(1 / dmax): progress = dist / dmax by one multiply + two fma (rdv_div_by, correctly rounded)
 };
 
 // Per-env record handed from the dynamics/reset kernel to the LiDAR and occupancy kernels (48 B, 16-B aligned).
@@ -44,7 +45,8 @@ struct LidarParams {
   unsigned groups_magic; // ceil(2^32 / groups): item / groups == umulhi(item, groups_magic) (k_lidar)
   unsigned envs_magic;   // ceil(2^32 / n_env of the launch), centre_first order
   int centre_first;      // work order: beam groups from the centre of the scan outwards, envs innermost
-  int normalize;         // RD_OBS_LIDAR_NORM
+  int normalize;         // 1: RD_OBS_LIDAR_NORM (r / range_max - 0.5); 2: RD_OBS_NORM_BASELINES ((r - norm_lo) * norm_sc)
+  double norm_lo, norm_sc;
   int f16;               // RD_OBS_LIDAR_F16: rows are stored as IEEE half
   float range_min, range_max, noise;
   float scale;           // metres per (sub-cell / direction unit) = 2^(DIR-SUB) * resolution

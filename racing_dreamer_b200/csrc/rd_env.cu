@@ -56,8 +56,13 @@ struct rd_env {
   bool lidar_attr_set[8] = {};    // k_lidar<16|32, ahead, cars> opted in to smem_optin
   int n = 0;
   int step_block = 128;           // k_step threads per CTA (small batches: fewer, so that every SM gets a warp)
-  double* d_f64 = nullptr;
-  int32_t* d_i32 = nullptr;
+  double2* d_f2 = nullptr;        // env state, SoA of 16-byte groups (rd_dynamics.cuh StateRef)
+  int4* d_i4 = nullptr;
+  int2* d_i2 = nullptr;
+  VehConst vk{};                  // vehicle constants of cfg.vehicle / cfg.dt (rd_vehicle.cuh)
+  VehAcc voff{};
+  VehConst* d_vk = nullptr;       // device copies of the two (rdv_tick's out-of-line general path reads them through pointers)
+  VehAcc* d_voff = nullptr;
   double* d_stats = nullptr;
   double* d_hist = nullptr;       // [n_step_progress][n] ring of lap + progress (n_step_progress task), else null
   bool multi = false;             // k_step_ma steps the batch (agents_per_world > 1 or an n_step_progress task)
@@ -65,7 +70,9 @@ struct rd_env {
   double* d_beam_tab = nullptr;
   DevMap* d_maps = nullptr;
   int32_t* d_env_order = nullptr;  // env indices grouped by map
-  unsigned int* d_lidar_ctr = nullptr;  // [2] work counter + finish ticket of k_lidar (self re-arming)
+  unsigned int* d_lidar_ctr = nullptr;  // [RD_CTR_RING][2] work counter + finish ticket of k_lidar (self re-arming); every
+  unsigned lidar_ctr_next = 0;          // launch takes the next pair of the ring, so launches that overlap (programmatic
+                                        // dependent launch, calls on different streams) never share a counter
   OccScratch occ{};
   HostMap maps[RD_MAX_MAPS];
   std::vector<int> order_offset;   // RD_MAX_MAPS + 1 offsets into d_env_order
@@ -90,7 +97,6 @@ struct rd_env {
     float* lidar_dev = nullptr; float* lidar_host = nullptr;   // float32 rows, or IEEE half rows (lidar_elem == 2)
     size_t lidar_elem = 4;
     uint8_t* occ_dev = nullptr; uint8_t* occ_host = nullptr;
-    unsigned int* ctr = nullptr;             // [n_chunks][2] k_lidar work counters, one pair per stream
     bool zero_copy = false;                  // k_lidar stores straight into the pinned host mirror (no staging copy)
     bool pending = false;                    // rd_step_host_begin enqueued a step whose results rd_step_host_end has not awaited
     rd_outputs dev_out{}, host_out{};
@@ -171,6 +177,12 @@ void default_config(rd_config* c) {
   for (int a = 0; a < RD_MAX_AGENTS; ++a) c->agent_task[a] = RD_TASK_MAX_PROGRESS;
   c->n_step_progress = 10;    // [REF baselines/scenarios/max_progress/austria.yml:18]
   c->ball_spacing = 1.5;
+  c->time_limit_ticks = 0;
+  // Box bounds of the env's observation space [NEW-SPEC: racecar_gym's sensor spaces are not in tree]: lidar [0, range],
+  // pose +-100 m (the maps span +-50 m), velocity +-10 (v_max = 5 m/s)
+  c->obs_low[RD_NORM_LIDAR] = 0.0;      c->obs_high[RD_NORM_LIDAR] = 15.0;
+  c->obs_low[RD_NORM_POSE] = -100.0;    c->obs_high[RD_NORM_POSE] = 100.0;
+  c->obs_low[RD_NORM_VELOCITY] = -10.0; c->obs_high[RD_NORM_VELOCITY] = 10.0;
   rd_vehicle* v = &c->vehicle;
   v->mu = 1.0489; v->c_sf = 4.718; v->c_sr = 5.4562; v->lf = 0.15875; v->lr = 0.17145; v->h_cg = 0.074;
   v->mass = 3.74; v->inertia = 0.04712;
@@ -184,6 +196,10 @@ void default_config(rd_config* c) {
   v->steer_gain = -1.0;
   v->body_length = 0.50; v->body_width = 0.27;
 }
+
+// k_lidar work-counter pairs: far more than the launches one handle can have in flight (the host-facing step enqueues at
+// most chunks x maps <= 24 x 8 launches before it waits)
+constexpr int RD_CTR_RING = 1024;
 
 int sync_maps(rd_env* env) {
   if (!env->maps_dirty) return RD_OK;
@@ -219,7 +235,9 @@ LidarParams lidar_params(const rd_env* env, const DevMap& m) {
   lp.n_beams = c.n_beams;
   lp.groups = (c.n_beams + 31) / 32;
   lp.groups_magic = lp.groups > 1 ? (unsigned)(((1ull << 32) + (unsigned)lp.groups - 1) / (unsigned)lp.groups) : 0u;
-  lp.normalize = (c.obs_flags & RD_OBS_LIDAR_NORM) ? 1 : 0;
+  lp.normalize = (c.obs_flags & RD_OBS_LIDAR_NORM) ? 1 : ((c.obs_flags & RD_OBS_NORM_BASELINES) ? 2 : 0);
+  lp.norm_lo = c.obs_low[RD_NORM_LIDAR];
+  lp.norm_sc = 1.0 / (c.obs_high[RD_NORM_LIDAR] - c.obs_low[RD_NORM_LIDAR]);
   lp.f16 = (c.obs_flags & RD_OBS_LIDAR_F16) ? 1 : 0;
   lp.range_min = (float)c.lidar_range_min;
   lp.range_max = (float)c.lidar_range_max;
@@ -319,7 +337,7 @@ int launch_lidar_t(rd_env* env, int map_id, const OriginRec* recs, const int32_t
 int launch_lidar(rd_env* env, int map_id, const OriginRec* recs, const int32_t* order, int n_env, float* out,
                  cudaStream_t s, unsigned int* ctr = nullptr) {
   const DevMap& m = env->maps[map_id].dev;
-  if (!ctr) ctr = env->d_lidar_ctr;
+  if (!ctr) ctr = env->d_lidar_ctr + 2 * (env->lidar_ctr_next++ % RD_CTR_RING);
   // small maps: 16-warp CTAs (several per SM); large maps: 32-warp CTAs so one resident copy feeds 32 warps.
   // Long launches (>= 128 work items per resident warp) draw their work one chunk ahead (see k_lidar).
   const int warps = m.bits_bytes > 72 * 1024 ? 32 : 16;
@@ -343,7 +361,7 @@ int launch_lidar(rd_env* env, int map_id, const OriginRec* recs, const int32_t* 
 int launch_occupancy(rd_env* env, int map_id, const OriginRec* recs, const double* poses_xyyaw,
                      const int32_t* order, int n_env, uint8_t* out, cudaStream_t s) {
   ScopedTiming tm(env, s, T_OCC);
-  int rc = occ_launch(env->occ, env->d_maps, map_id, env->maps[map_id].dev, recs, poses_xyyaw, env->d_f64, env->n,
+  int rc = occ_launch(env->occ, env->d_maps, map_id, env->maps[map_id].dev, recs, poses_xyyaw, env->d_f2, env->n,
                       order, n_env, out, env->sm_count, s, &env->launches);
   if (rc != 0) return fail(env, RD_ERR_CUDA, "occupancy launch: %s", cudaGetErrorString((cudaError_t)rc));
   return RD_OK;
@@ -355,6 +373,7 @@ OutPtrs out_ptrs(const rd_outputs* o) {
     p.pose = o->pose_dev; p.velocity = o->velocity_dev; p.speed = o->speed_dev; p.reward = o->reward_dev;
     p.done = o->done_dev; p.progress = o->progress_dev; p.lap = o->lap_dev; p.time = o->time_dev;
     p.flags = o->flags_dev; p.occupancy = o->occupancy_dev; p.rank = o->rank_dev; p.opponents = o->opponents_dev;
+    p.wrong_way = o->wrong_way_dev; p.wall_collision = o->wall_collision_dev;
   }
   return p;
 }
@@ -362,7 +381,14 @@ OutPtrs out_ptrs(const rd_outputs* o) {
 StepParams step_params(rd_env* env) {
   StepParams P{};
   P.cfg = env->cfg;
-  P.f64 = env->d_f64; P.i32 = env->d_i32; P.stats = env->d_stats; P.recs = env->d_recs; P.maps = env->d_maps;
+  P.vk = env->vk; P.off = env->voff; P.vk_g = env->d_vk; P.off_g = env->d_voff;
+  P.S.f2 = env->d_f2; P.S.i4 = env->d_i4; P.S.i2 = env->d_i2; P.S.n = env->n;
+  P.stats = env->d_stats; P.recs = env->d_recs; P.maps = env->d_maps;
+  P.norm = (env->cfg.obs_flags & RD_OBS_NORM_BASELINES) ? 1 : 0;
+  for (int k = 0; k < 3; ++k) {
+    P.norm_lo[k] = env->cfg.obs_low[k];
+    P.norm_sc[k] = P.norm ? 1.0 / (env->cfg.obs_high[k] - env->cfg.obs_low[k]) : 1.0;
+  }
   P.pol = env->pol.st;
   P.hist = env->d_hist;
   if (env->dr.ready) { P.pol.dr_feat = env->dr.feat[env->dr.cur].p[0]; P.pol.dr_feat_lo = env->dr.feat[env->dr.cur].p[1]; P.pol.dr_ld = env->dr.ldf; }
@@ -484,6 +510,12 @@ RD_API int rd_create(const rd_config* cfg, rd_env** out) {
     if (nstep && (cfg->n_step_progress < 1 || cfg->n_step_progress > RD_MAX_NSTEP))
       return fail(nullptr, RD_ERR_INVALID, "n_step_progress %d out of range [1,%d]", cfg->n_step_progress, RD_MAX_NSTEP);
     if (A > 1 && !(cfg->ball_spacing > 0.0)) return fail(nullptr, RD_ERR_INVALID, "ball_spacing must be positive");
+    if (cfg->time_limit_ticks < 0) return fail(nullptr, RD_ERR_INVALID, "time_limit_ticks must be >= 0");
+    if (cfg->obs_flags & RD_OBS_NORM_BASELINES) {
+      if (cfg->obs_flags & RD_OBS_LIDAR_NORM) return fail(nullptr, RD_ERR_INVALID, "RD_OBS_NORM_BASELINES excludes RD_OBS_LIDAR_NORM");
+      for (int k = 0; k < 3; ++k)
+        if (!(cfg->obs_high[k] > cfg->obs_low[k])) return fail(nullptr, RD_ERR_INVALID, "obs_high[%d] must exceed obs_low[%d]", k, k);
+    }
   }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
@@ -526,9 +558,16 @@ RD_API int rd_create(const rd_config* cfg, rd_env** out) {
   const size_t n = (size_t)env->n;
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc(p, bytes); if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes); } };
-  alloc((void**)&env->d_f64, sizeof(double) * RD_NF64 * n);
-  alloc((void**)&env->d_i32, sizeof(int32_t) * RD_NI32 * n);
-  alloc((void**)&env->d_stats, sizeof(double) * 8);
+  env->vk = rdv_make_const(cfg->vehicle, cfg->dt);
+  env->voff = rdv_acc_set(env->vk, 0.0);
+  alloc((void**)&env->d_vk, sizeof(VehConst));
+  alloc((void**)&env->d_voff, sizeof(VehAcc));
+  if (e == cudaSuccess) e = cudaMemcpy(env->d_vk, &env->vk, sizeof(VehConst), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(env->d_voff, &env->voff, sizeof(VehAcc), cudaMemcpyHostToDevice);
+  alloc((void**)&env->d_f2, sizeof(double2) * RD_NPAIR * n);
+  alloc((void**)&env->d_i4, sizeof(int4) * n);
+  alloc((void**)&env->d_i2, sizeof(int2) * n);
+  alloc((void**)&env->d_stats, sizeof(double) * 16);
   alloc((void**)&env->d_recs, sizeof(OriginRec) * n);
   {
     const int A = cfg->agents_per_world > 1 ? cfg->agents_per_world : 1;
@@ -540,7 +579,7 @@ RD_API int rd_create(const rd_config* cfg, rd_env** out) {
   alloc((void**)&env->d_beam_tab, sizeof(double) * 2 * (size_t)cfg->n_beams);
   alloc((void**)&env->d_maps, sizeof(DevMap) * RD_MAX_MAPS);
   alloc((void**)&env->d_env_order, sizeof(int32_t) * n);
-  alloc((void**)&env->d_lidar_ctr, sizeof(unsigned int) * 2);
+  alloc((void**)&env->d_lidar_ctr, sizeof(unsigned int) * 2 * RD_CTR_RING);
   if (e != cudaSuccess) {
     int rc = fail(nullptr, e == cudaErrorMemoryAllocation ? RD_ERR_NOMEM : RD_ERR_CUDA, "allocation: %s", cudaGetErrorString(e));
     rd_destroy(env);
@@ -561,7 +600,8 @@ RD_API int rd_create(const rd_config* cfg, rd_env** out) {
 
 RD_API void rd_destroy(rd_env* env) {
   if (!env) return;
-  cudaFree(env->d_f64); cudaFree(env->d_i32); cudaFree(env->d_stats); cudaFree(env->d_hist); cudaFree(env->d_recs);
+  cudaFree(env->d_vk); cudaFree(env->d_voff);
+  cudaFree(env->d_f2); cudaFree(env->d_i4); cudaFree(env->d_i2); cudaFree(env->d_stats); cudaFree(env->d_hist); cudaFree(env->d_recs);
   cudaFree(env->d_beam_tab); cudaFree(env->d_maps); cudaFree(env->d_env_order); cudaFree(env->d_lidar_ctr);
   cudaFree(env->d_stage_recs); cudaFree(env->d_stage_ids);
   cudaFree(env->pol.st.f64); cudaFree(env->pol.st.i32); cudaFree(env->pol.d_actions);
@@ -574,7 +614,7 @@ RD_API void rd_destroy(rd_env* env) {
     if (h.ev_act) cudaEventDestroy(h.ev_act);
     cudaFreeHost(h.act_host); cudaFree(h.act_dev); cudaFree(h.mask_dev); cudaFree(h.small_dev); cudaFreeHost(h.small_host);
     if (!h.zero_copy) cudaFree(h.lidar_dev);
-    cudaFreeHost(h.lidar_host); cudaFree(h.occ_dev); cudaFreeHost(h.occ_host); cudaFree(h.ctr);
+    cudaFreeHost(h.lidar_host); cudaFree(h.occ_dev); cudaFreeHost(h.occ_host);
   }
   for (auto& t : env->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (auto& e : env->event_pool) cudaEventDestroy(e);
@@ -645,6 +685,7 @@ RD_API int rd_upload_map(rd_env* env, int map_id, const uint32_t* bits_host, int
   d.n_start = n_start; d.n_reset = n_reset; d.bits_bytes = (int)packed.size();
   d.coarse_off = (int)bits_padded; d.cw = cw; d.ch = ch; d.cshift = cshift;
   d.res = resolution; d.inv_res = 1.0 / resolution; d.ox = origin_x; d.oy = origin_y;
+  d.inv_dmax = 1.0 / (double)dmax;
   if (n_reset > 0) {
     // random_ball chain: next[i] = the reset pose with the smallest wavefront distance that is at least
     // ceil(ball_spacing / resolution) cells of progress beyond pose i, wrapping over the finish line.  The wavefront
@@ -698,7 +739,8 @@ RD_API int rd_assign_maps(rd_env* env, const int32_t* ids) {
   for (int e = 0; e < n; ++e) order[cursor[id[e]]++] = e;
   CUDA_TRY(env, cudaMemcpy(env->d_env_order, order.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice));
   env->h_order = order;
-  CUDA_TRY(env, cudaMemcpy(env->d_i32 + (size_t)RD_I_MAP * n, id.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice));
+  CUDA_TRY(env, cudaMemcpy2D(reinterpret_cast<int32_t*>(env->d_i2) + 1, sizeof(int2), id.data(), sizeof(int32_t), sizeof(int32_t),
+                             (size_t)n, cudaMemcpyHostToDevice));   // the .y (map) column of the (episode, map) group
   int rc = sync_maps(env);
   if (rc) return rc;
   env->assigned = true;
@@ -774,6 +816,7 @@ RD_API int rd_host_init(rd_env* env, int n_chunks, rd_outputs* host_out) {
   const size_t o_rew = take(sizeof(float) * n), o_prog = take(sizeof(float) * n), o_time = take(sizeof(float) * n);
   const size_t o_lap = take(sizeof(int32_t) * n), o_done = take((size_t)n), o_flags = take((size_t)n);
   const size_t o_rank = take(sizeof(int32_t) * n), o_opp = take((size_t)n);
+  const size_t o_ww = take((size_t)n), o_wc = take((size_t)n);
   h.small_bytes = off;
   const size_t lidar_elem = (env->cfg.obs_flags & RD_OBS_LIDAR_F16) ? 2 : 4;
   h.lidar_elem = lidar_elem;
@@ -803,8 +846,6 @@ RD_API int rd_host_init(rd_env* env, int n_chunks, rd_outputs* host_out) {
   CUDA_TRY(env, cudaHostAlloc(&h.act_host, sizeof(float) * 2 * n, cudaHostAllocDefault));
   CUDA_TRY(env, cudaMalloc(&h.act_dev, sizeof(float) * 2 * n));
   CUDA_TRY(env, cudaMalloc(&h.mask_dev, (size_t)n));
-  CUDA_TRY(env, cudaMalloc(&h.ctr, sizeof(unsigned int) * 2 * n_chunks));
-  CUDA_TRY(env, cudaMemset(h.ctr, 0, sizeof(unsigned int) * 2 * n_chunks));
   h.streams.resize(n_chunks);
   h.ev_done.resize(n_chunks);
   for (int c = 0; c < n_chunks; ++c) {
@@ -818,6 +859,7 @@ RD_API int rd_host_init(rd_env* env, int n_chunks, rd_outputs* host_out) {
     o.reward_dev = (float*)(base + o_rew); o.progress_dev = (float*)(base + o_prog); o.time_dev = (float*)(base + o_time);
     o.lap_dev = (int32_t*)(base + o_lap); o.done_dev = (uint8_t*)(base + o_done); o.flags_dev = (uint8_t*)(base + o_flags);
     o.rank_dev = (int32_t*)(base + o_rank); o.opponents_dev = (uint8_t*)(base + o_opp);
+    o.wrong_way_dev = (uint8_t*)(base + o_ww); o.wall_collision_dev = (uint8_t*)(base + o_wc);
   };
   fill(h.dev_out, h.small_dev, h.lidar_dev, h.occ_dev);
   fill(h.host_out, h.small_host, h.lidar_host, h.occ_host);
@@ -929,7 +971,7 @@ int step_host_enqueue(rd_env* env, const float* actions_host, bool wait) {
       CUDA_TRY(env, cudaMemcpyAsync(h.small_host, h.small_dev, h.small_bytes, cudaMemcpyDeviceToHost, s));
       small_copied = true;
     }
-    int rc = observe(env, &h.dev_out, s, e0, e1, h.ctr + 2 * c);
+    int rc = observe(env, &h.dev_out, s, e0, e1);
     if (rc) return rc;
     if ((rc = host_copy_back(env, c))) return rc;
   }
@@ -1010,7 +1052,7 @@ int launch_gap_follower(rd_env* env, const float* lidar_dev, const float* speed_
   constexpr int WARPS = 8;
   auto& p = env->pol;
   GapArgs A{};
-  A.g = p.g; A.ps = p.st; A.lidar = lidar_dev; A.speed = speed_dev; A.state_v = env->d_f64 + (size_t)RD_S_V * env->n;
+  A.g = p.g; A.ps = p.st; A.lidar = lidar_dev; A.speed = speed_dev; A.state_sv = env->d_f2 + (size_t)RD_P_SV * env->n;
   A.actions = actions_dev; A.debug = debug_dev; A.n = env->n; A.n_beams = env->cfg.n_beams;
   const int m = p.g.arc_last - p.g.arc_first + 1;
   A.m_pad = (m + 1) | 1;   // odd number of floats per row: the warps' rows start in different banks
@@ -1180,7 +1222,25 @@ RD_API int rd_dynamics(rd_env* env, double* state_dev, const double* commands_de
   if (!env || n < 0 || n_ticks < 0) return fail(env, RD_ERR_INVALID, "bad argument");
   if (n == 0) return RD_OK;
   if (!state_dev || !commands_dev) return fail(env, RD_ERR_INVALID, "null pointer");
-  k_dynamics<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(env->cfg, state_dev, commands_dev, n, n_ticks);
+  k_dynamics<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(env->vk, env->voff, env->d_vk, env->d_voff, state_dev, commands_dev, n, n_ticks);
+  env->launches++;
+  CUDA_TRY(env, cudaGetLastError());
+  return RD_OK;
+}
+
+RD_API int rd_reward_done(rd_env* env, const double* kin_dev, const double* steering_dev, const int32_t* map_ids_host, int n,
+                          double* book_f64_dev, int32_t* book_i32_dev, double* reward_dev, uint8_t* done_dev, void* stream) {
+  if (!env || n < 0) return fail(env, RD_ERR_INVALID, "bad argument");
+  if (n == 0) return RD_OK;
+  if (!kin_dev || !book_f64_dev || !book_i32_dev || !reward_dev || !done_dev) return fail(env, RD_ERR_INVALID, "null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = sync_maps(env);
+  if (rc) return rc;
+  if ((rc = ensure_stage(env, n))) return rc;
+  int runs[RD_MAX_MAPS][2];
+  if ((rc = stage_runs(env, map_ids_host, n, runs, s))) return rc;
+  k_reward_done<<<(n + 127) / 128, 128, 0, s>>>(env->cfg, env->d_maps, map_ids_host ? env->d_stage_ids : nullptr, kin_dev,
+                                               steering_dev, n, book_f64_dev, book_i32_dev, reward_dev, done_dev);
   env->launches++;
   CUDA_TRY(env, cudaGetLastError());
   return RD_OK;
@@ -1190,8 +1250,12 @@ RD_API int rd_get_state(rd_env* env, double* f64_dev, int32_t* i32_dev, void* st
   if (!env) return fail(nullptr, RD_ERR_INVALID, "null handle");
   cudaStream_t s = (cudaStream_t)stream;
   const size_t n = (size_t)env->n;
-  if (f64_dev) CUDA_TRY(env, cudaMemcpyAsync(f64_dev, env->d_f64, sizeof(double) * RD_NF64 * n, cudaMemcpyDeviceToDevice, s));
-  if (i32_dev) CUDA_TRY(env, cudaMemcpyAsync(i32_dev, env->d_i32, sizeof(int32_t) * RD_NI32 * n, cudaMemcpyDeviceToDevice, s));
+  (void)n;
+  if (f64_dev || i32_dev) {
+    k_state_export<<<(env->n + 127) / 128, 128, 0, s>>>(step_params(env).S, f64_dev, i32_dev);
+    env->launches++;
+    CUDA_TRY(env, cudaGetLastError());
+  }
   return RD_OK;
 }
 
@@ -1200,14 +1264,13 @@ RD_API int rd_set_state(rd_env* env, const double* f64_dev, const int32_t* i32_d
   if (!env->assigned) return fail(env, RD_ERR_STATE, "rd_assign_maps has not been called");
   cudaStream_t s = (cudaStream_t)stream;
   const size_t n = (size_t)env->n;
-  if (f64_dev) CUDA_TRY(env, cudaMemcpyAsync(env->d_f64, f64_dev, sizeof(double) * RD_NF64 * n, cudaMemcpyDeviceToDevice, s));
-  if (i32_dev) {
-    // everything but the map row: map assignment is owned by rd_assign_maps (the env grouping depends on it)
-    CUDA_TRY(env, cudaMemcpyAsync(env->d_i32, i32_dev, sizeof(int32_t) * (size_t)RD_I_MAP * n, cudaMemcpyDeviceToDevice, s));
-  }
-  if (env->d_hist && f64_dev) {  // the n-step ring is not part of the state layout: restart it from the restored lap + progress
-    for (int k = 0; k < env->cfg.n_step_progress; ++k)
-      CUDA_TRY(env, cudaMemcpyAsync(env->d_hist + (size_t)k * n, env->d_f64 + (size_t)RD_S_LAST * n, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+  (void)n;
+  if (f64_dev || i32_dev) {
+    // everything but the map column (owned by rd_assign_maps: the env grouping depends on it); the n-step ring is not
+    // part of the state layout and restarts from the restored lap + progress
+    k_state_import<<<(env->n + 127) / 128, 128, 0, s>>>(step_params(env).S, f64_dev, i32_dev, env->d_hist, env->cfg.n_step_progress);
+    env->launches++;
+    CUDA_TRY(env, cudaGetLastError());
   }
   env->was_reset = true;
   return RD_OK;
@@ -1216,12 +1279,13 @@ RD_API int rd_set_state(rd_env* env, const double* f64_dev, const int32_t* i32_d
 RD_API int rd_read_stats(rd_env* env, rd_stats* out_host, int reset, void* stream) {
   if (!env || !out_host) return fail(env, RD_ERR_INVALID, "null argument");
   cudaStream_t s = (cudaStream_t)stream;
-  double h[8];
+  double h[RD_NSTAT];
   CUDA_TRY(env, cudaMemcpyAsync(h, env->d_stats, sizeof(h), cudaMemcpyDeviceToHost, s));
   if (reset) CUDA_TRY(env, cudaMemsetAsync(env->d_stats, 0, sizeof(h), s));
   CUDA_TRY(env, cudaStreamSynchronize(s));
   out_host->episodes = h[0]; out_host->return_sum = h[1]; out_host->progress_sum = h[2]; out_host->length_sum = h[3];
   out_host->collisions = h[4]; out_host->laps_completed = h[5]; out_host->env_steps = h[6]; out_host->timeouts = h[7];
+  out_host->max_progress_sum = h[8];
   return RD_OK;
 }
 

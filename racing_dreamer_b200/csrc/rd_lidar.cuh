@@ -37,7 +37,9 @@ __device__ __forceinline__ float rd_finish_range(const LidarParams& lp, float r,
   }
   r = r < lp.range_min ? lp.range_min : r;
   r = r > lp.range_max ? lp.range_max : r;
-  if (lp.normalize) r = __fsub_rn(__fdiv_rn(r, lp.range_max), 0.5f);  // [REF dreamer/tools.py:274]
+  if (lp.normalize == 1) r = __fsub_rn(__fdiv_rn(r, lp.range_max), 0.5f);  // [REF dreamer/tools.py:274]
+  // NormalizeObservations: (x - low) * (1 / (high - low)), float64, then float32 [REF baselines single_agent.py:92-99]
+  else if (lp.normalize == 2) r = (float)__dmul_rn(__dsub_rn((double)r, lp.norm_lo), lp.norm_sc);
   return r;
 }
 
@@ -215,11 +217,9 @@ k_lidar(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict
   }
 }
 
-// Sensor-origin record from a pose (stage entry rd_lidar_cast / rd_occupancy_obs, and the step kernels).
-__device__ __forceinline__ void rd_make_origin(const DevMap& m, double x, double y, double yaw, double lidar_offset,
-                                               OriginRec& rec) {
-  double s, c;
-  sincos(yaw, &s, &c);
+// Sensor-origin record from a pose and the cosine / sine of its heading (the step kernels already hold them).
+__device__ __forceinline__ void rd_make_origin_cs(const DevMap& m, double x, double y, double c, double s,
+                                                  double lidar_offset, OriginRec& rec) {
   const double sx = x + lidar_offset * c;
   const double sy = y + lidar_offset * s;
   const double u = (sx - m.ox) * m.inv_res;
@@ -240,6 +240,13 @@ __device__ __forceinline__ void rd_make_origin(const DevMap& m, double x, double
   rec.valid = (ok ? 1 : 0) | (pos ? 2 : 0);   // bit0: origin inside a drivable cell; bit1: px/py hold the position
   rec.c = c;
   rec.s = s;
+}
+// ... from a pose alone (stage entries rd_lidar_cast / rd_occupancy_obs)
+__device__ __forceinline__ void rd_make_origin(const DevMap& m, double x, double y, double yaw, double lidar_offset,
+                                               OriginRec& rec) {
+  double s, c;
+  sincos(yaw, &s, &c);
+  rd_make_origin_cs(m, x, y, c, s, lidar_offset, rec);
 }
 
 __global__ void k_origin_from_poses(const DevMap* __restrict__ maps, const int32_t* __restrict__ map_ids,

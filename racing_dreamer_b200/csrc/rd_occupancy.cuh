@@ -244,7 +244,7 @@ __device__ __noinline__ uint32_t occ_exact_pixel(const double* rc, int a, int b,
 
 __global__ void __launch_bounds__(OCC_THREADS, 1)
 k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict__ recs,
-            const double* __restrict__ poses, const double* __restrict__ f64, int n_state,
+            const double* __restrict__ poses, const double2* __restrict__ f2, int n_state,
             const int32_t* __restrict__ order, int n_env, const double* __restrict__ hband,
             const OccTables* __restrict__ tables, float eps, uint8_t* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -268,8 +268,9 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
     int mode = 0;
     if (poses) { x = poses[3 * slot]; y = poses[3 * slot + 1]; yaw = poses[3 * slot + 2]; }
     else {
-      x = f64[(size_t)RD_S_X * n_state + env]; y = f64[(size_t)RD_S_Y * n_state + env];
-      yaw = f64[(size_t)RD_S_YAW * n_state + env];
+      const double2 xy = f2[env];                                   // env state groups (rd_dynamics.cuh): 0 = (x, y),
+      x = xy.x; y = xy.y;
+      yaw = f2[(size_t)2 * n_state + env].x;                        // 2 = (yaw, yaw_rate)
       mode = recs[env].was_reset;
     }
     uint8_t* dst = out + (size_t)(poses ? slot : env) * (RD_OCC_OUT * RD_OCC_OUT);
@@ -562,7 +563,7 @@ static inline void occ_free(OccScratch& sc) {
 
 // returns a cudaError_t value (0 = ok)
 static inline int occ_launch(OccScratch& sc, const DevMap* d_maps, int map_id, const DevMap& hm, const OriginRec* recs,
-                             const double* poses, const double* f64, int n_state, const int32_t* order, int n_env,
+                             const double* poses, const double2* f2, int n_state, const int32_t* order, int n_env,
                              uint8_t* out, int sm_count, cudaStream_t s, int64_t* launches) {
   (void)hm;
   const size_t smem = OCC_SM_TOTAL;
@@ -587,7 +588,7 @@ static inline int occ_launch(OccScratch& sc, const DevMap* d_maps, int map_id, c
   }
   const int grid = n_env < sm_count ? n_env : sm_count;  // one CTA per SM (221 KB of shared memory each)
   if (grid < 1) return 0;
-  k_occupancy<<<grid, OCC_THREADS, smem, s>>>(d_maps, map_id, recs, poses, f64, n_state, order, n_env, sc.hband, sc.tables, sc.eps, out);
+  k_occupancy<<<grid, OCC_THREADS, smem, s>>>(d_maps, map_id, recs, poses, f2, n_state, order, n_env, sc.hband, sc.tables, sc.eps, out);
   (*launches)++;
   return (int)cudaGetLastError();
 }

@@ -51,7 +51,7 @@ struct GapArgs {
   PolicyState ps;
   const float* lidar;     // [n][n_beams], metres, index 0 = left
   const float* speed;     // [n] or null
-  const double* state_v;  // env state row RD_S_V (used when speed is null)
+  const double2* state_sv; // env state group (steer, v) (v is used when speed is null)
   float* actions;         // [n][2]
   double* debug;          // [n][4] or null
   int n, n_beams, m_pad;  // m_pad: floats per shared-memory row
@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_gap_follower(GapArgs A) {
         const int k0 = rd_trunc_clip(((theta - beta) - ang0) / inc, M - 1);
         const int k1 = rd_trunc_clip(((theta + beta) - ang0) / inc, M - 1);
         for (int k = k0 + lane; k <= k1; k += 32) adj[k] = fminf(adj[k], Lc);
+        __syncwarp();   // the next candidate's run overlaps this one's with a different lane -> element mapping
       }
     }
     __syncwarp();
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_gap_follower(GapArgs A) {
     A.ps.i32[(size_t)RD_P_SCANS * n + e] = scans;
     A.ps.i32[(size_t)RD_P_HEADINGS * n + e] = headings;
     // drive command -> env action
-    const double v = A.speed ? (double)A.speed[e] : A.state_v[e];
+    const double v = A.speed ? (double)A.speed[e] : A.state_sv[e].y;
     const double vt = vehicle_speed * g.speed_scale;
     double motor = vt * A.c_drag / A.a_drive + g.speed_gain * (vt - v);
     double steer = steering_angle / A.steer_scale;

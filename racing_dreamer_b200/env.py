@@ -31,6 +31,10 @@ class EnvConfig:
     action_repeat: int = 4                      # [REF dreamer/dream.py:55]
     obs_type: str = "lidar"                     # 'lidar' | 'lidar_occupancy' [REF dreamer/dream.py:64-66]
     normalize_lidar: bool = False               # store r/15-0.5 [REF dreamer/tools.py:274]
+    normalize_obs: Optional[str] = None         # 'baselines': lidar / pose / velocity as (x-low)/(high-low), the model-free
+                                                # chain's NormalizeObservations [REF baselines/racing/environment/single_agent.py:66-99]
+    obs_low: Sequence[float] = (0.0, -100.0, -10.0)    # Box bounds of lidar / pose / velocity (normalize_obs)
+    obs_high: Sequence[float] = (15.0, 100.0, 10.0)
     lidar_dtype: str = "float32"                # 'float16' = what Collect hands on at precision 16 [REF dreamer/wrappers.py:240-250]
     task: str = "maximize_progress"
     laps: int = 10
@@ -41,6 +45,8 @@ class EnvConfig:
     frame_reward: float = 0.0
     n_checkpoints: int = 20
     time_limit_steps: int = 0                   # TimeLimit(duration) in agent steps; 0 = off
+    time_limit_ticks: int = 0                   # gym TimeLimit inside ActionRepeat (baselines chain), in sim ticks; 0 = off
+                                                # [REF baselines/racing/experiments/acme/experiment.py:66-72]
     auto_reset: bool = True
     reset_mode: str = "grid"
     rescale_actions: bool = True                # ReduceActionSpace
@@ -74,6 +80,15 @@ def _fill_config(cfg: _abi.RdConfig, ec: EnvConfig) -> None:
         raise ValueError(f"obs_type {ec.obs_type!r}: expected 'lidar' or 'lidar_occupancy'")
     if ec.normalize_lidar:
         flags |= _abi.OBS_LIDAR_NORM
+    if ec.normalize_obs == "baselines":
+        if ec.normalize_lidar:
+            raise ValueError("normalize_obs='baselines' excludes normalize_lidar (dreamer's r/15 - 0.5)")
+        flags |= _abi.OBS_NORM_BASELINES
+        for k in range(3):
+            cfg.obs_low[k] = float(ec.obs_low[k])
+            cfg.obs_high[k] = float(ec.obs_high[k])
+    elif ec.normalize_obs is not None:
+        raise ValueError(f"normalize_obs {ec.normalize_obs!r}: expected None or 'baselines'")
     if ec.lidar_dtype == "float16":
         flags |= _abi.OBS_LIDAR_F16
     elif ec.lidar_dtype != "float32":
@@ -84,6 +99,7 @@ def _fill_config(cfg: _abi.RdConfig, ec: EnvConfig) -> None:
     cfg.terminate_on_collision = int(ec.terminate_on_collision)
     cfg.n_checkpoints = int(ec.n_checkpoints)
     cfg.time_limit_steps = int(ec.time_limit_steps)
+    cfg.time_limit_ticks = int(ec.time_limit_ticks)
     cfg.auto_reset = int(ec.auto_reset)
     cfg.reset_mode = _abi.RESET_MODES[ec.reset_mode]
     cfg.rescale_actions = int(ec.rescale_actions)
@@ -183,7 +199,8 @@ class BatchedRaceEnv:
         ("lidar", None, torch.float32), ("occupancy", (64, 64, 1), torch.uint8), ("pose", (6,), torch.float32),
         ("velocity", (6,), torch.float32), ("speed", (), torch.float32), ("reward", (), torch.float32),
         ("done", (), torch.uint8), ("progress", (), torch.float32), ("lap", (), torch.int32), ("time", (), torch.float32),
-        ("flags", (), torch.uint8), ("rank", (), torch.int32), ("opponents", (), torch.uint8))
+        ("flags", (), torch.uint8), ("rank", (), torch.int32), ("opponents", (), torch.uint8),
+        ("wrong_way", (), torch.bool), ("wall_collision", (), torch.bool), ("done_bool", (), torch.bool))
 
     def _alloc(self):
         n, dev = self.n, self.device
@@ -197,6 +214,9 @@ class BatchedRaceEnv:
             full = (n,) + ((self.n_beams,) if key == "lidar" else tuple(shape))
             if key == "lidar" and (self.cfg.obs_flags & _abi.OBS_LIDAR_F16):
                 dtype = torch.float16
+            if key == "done_bool":      # a bool VIEW of the kernel's 0/1 bytes: step() returns it without launching anything
+                self.buf[key] = self.buf["done"].view(torch.bool)
+                continue
             t = given.get(key)
             if t is None:
                 t = torch.zeros(full, dtype=dtype, device=dev)
@@ -207,7 +227,8 @@ class BatchedRaceEnv:
         for k, f in (("lidar", "lidar_dev"), ("occupancy", "occupancy_dev"), ("pose", "pose_dev"),
                      ("velocity", "velocity_dev"), ("speed", "speed_dev"), ("reward", "reward_dev"),
                      ("done", "done_dev"), ("progress", "progress_dev"), ("lap", "lap_dev"), ("time", "time_dev"),
-                     ("flags", "flags_dev"), ("rank", "rank_dev"), ("opponents", "opponents_dev")):
+                     ("flags", "flags_dev"), ("rank", "rank_dev"), ("opponents", "opponents_dev"),
+                     ("wrong_way", "wrong_way_dev"), ("wall_collision", "wall_collision_dev")):
             t = self.buf[k]
             setattr(o, f, t.data_ptr() if t is not None else None)
         self._out = o
@@ -231,10 +252,10 @@ class BatchedRaceEnv:
         return obs
 
     def _info(self) -> Dict[str, torch.Tensor]:
-        fl = self.buf["flags"]
+        # every value is a persistent buffer the kernels wrote (the two booleans included): no torch kernel runs here
         return {"progress": self.buf["progress"], "lap": self.buf["lap"], "time": self.buf["time"],
-                "wrong_way": (fl & _abi.F_WRONG_WAY) != 0, "wall_collision": (fl & _abi.F_COLLISION) != 0,
-                "flags": fl, "pose": self.buf["pose"], "velocity": self.buf["velocity"],
+                "wrong_way": self.buf["wrong_way"], "wall_collision": self.buf["wall_collision"],
+                "flags": self.buf["flags"], "pose": self.buf["pose"], "velocity": self.buf["velocity"],
                 # multi-agent worlds: position in the world (1 = leader) and a bit mask over the world's agent
                 # indices the car is in contact with (racecar_gym: info['rank'], info['opponent_collisions'])
                 "rank": self.buf["rank"], "opponent_collisions": self.buf["opponents"]}
@@ -260,7 +281,7 @@ class BatchedRaceEnv:
             a = self._actions
         with torch.cuda.device(self.device):
             self._check(self.lib.rd_step(self._handle, a.data_ptr(), C.byref(self._out), self._stream()))
-        return self._obs(), self.buf["reward"], self.buf["done"].bool(), self._info()
+        return self._obs(), self.buf["reward"], self.buf["done_bool"], self._info()
 
     def step_raw(self, actions_ptr: int) -> None:
         """rd_step on a raw device pointer; results land in ``self.buf`` (bench / tight loops)."""
@@ -296,6 +317,25 @@ class BatchedRaceEnv:
             self._check(self.lib.rd_dynamics(self._handle, s.data_ptr(), cmd.data_ptr(), s.shape[1], int(n_ticks),
                                              self._stream()))
         return s
+
+    def reward_done(self, kin: torch.Tensor, steering: Optional[torch.Tensor], book_f64: torch.Tensor,
+                    book_i32: torch.Tensor, map_ids: Optional[np.ndarray] = None):
+        """a7/a8 stage entry (rd_reward_done): one tick of progress / lap / wrong-way bookkeeping + task reward / done for
+        teacher-forced poses.  kin f64 [5, n] = (x, y, yaw, v, slip) after the tick, book_f64 [3, n] = (time, progress,
+        last), book_i32 [3, n] = (lap, checkpoint, flags).  Returns (book_f64', book_i32', reward f64[n], done u8[n])."""
+        k = kin.to(device=self.device, dtype=torch.float64).contiguous()
+        n = k.shape[1]
+        st = None if steering is None else steering.to(device=self.device, dtype=torch.float64).contiguous()
+        bf = book_f64.to(device=self.device, dtype=torch.float64).contiguous().clone()
+        bi = book_i32.to(device=self.device, dtype=torch.int32).contiguous().clone()
+        rew = torch.empty(n, dtype=torch.float64, device=self.device)
+        done = torch.empty(n, dtype=torch.uint8, device=self.device)
+        ids = None if map_ids is None else np.ascontiguousarray(map_ids, dtype=np.int32)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.rd_reward_done(self._handle, k.data_ptr(), st.data_ptr() if st is not None else None,
+                                                ids.ctypes.data if ids is not None else None, n, bf.data_ptr(),
+                                                bi.data_ptr(), rew.data_ptr(), done.data_ptr(), self._stream()))
+        return bf, bi, rew, done
 
     # ------------------------------------------------------------------ state / stats
     def get_state(self):

@@ -21,12 +21,14 @@ from . import _abi
 from .env import BatchedRaceEnv, EnvConfig
 
 _OUT_KEYS = ("lidar", "occupancy", "pose", "velocity", "speed", "reward", "done", "progress", "lap", "time", "flags",
-             "rank", "opponents")
+             "rank", "opponents", "wrong_way", "wall_collision")
 _FIELDS = {"lidar": ("lidar_dev", np.float32), "occupancy": ("occupancy_dev", np.uint8), "pose": ("pose_dev", np.float32),
            "velocity": ("velocity_dev", np.float32), "speed": ("speed_dev", np.float32), "reward": ("reward_dev", np.float32),
            "done": ("done_dev", np.uint8), "progress": ("progress_dev", np.float32), "lap": ("lap_dev", np.int32),
            "time": ("time_dev", np.float32), "flags": ("flags_dev", np.uint8),
-           "rank": ("rank_dev", np.int32), "opponents": ("opponents_dev", np.uint8)}
+           "rank": ("rank_dev", np.int32), "opponents": ("opponents_dev", np.uint8),
+           # the two info booleans the reference's consumers read, written as 0 / 1 bytes by the step kernel
+           "wrong_way": ("wrong_way_dev", np.bool_), "wall_collision": ("wall_collision_dev", np.bool_)}
 
 
 def bind_to_gpu_cpus(device_index: int) -> Optional[list]:

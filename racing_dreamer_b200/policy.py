@@ -65,7 +65,7 @@ class GapFollowerPolicy:
         with torch.cuda.device(env.device):
             env._check(env.lib.rd_rollout_gap_follower(env._handle, int(n_steps), C.byref(env._out),
                                                        self.actions.data_ptr(), env._stream()))
-        return env._obs(), env.buf["reward"], env.buf["done"].bool(), env._info()
+        return env._obs(), env.buf["reward"], env.buf["done_bool"], env._info()
 
     def drive_command(self) -> Dict[str, torch.Tensor]:
         """The node's last published command per env (valid after ``act(debug=True)``)."""
@@ -259,4 +259,4 @@ class DreamerPolicy:
         with torch.cuda.device(env.device):
             env._check(env.lib.rd_rollout_dreamer(env._handle, int(n_steps), C.byref(env._out), self.actions.data_ptr(),
                                                   mode, env._stream()))
-        return env._obs(), env.buf["reward"], env.buf["done"].bool(), env._info()
+        return env._obs(), env.buf["reward"], env.buf["done_bool"], env._info()

@@ -1,7 +1,7 @@
 """Episode statistics across ranks -- the ONLY collective of the system.
 
 Envs shard across GPUs with no exchange inside ``step``/``reset``; at log cadence each rank contributes the
-eight device-side accumulators of ``rd_read_stats`` (episodes, return_sum, progress_sum, ...) and every rank
+nine device-side accumulators of ``rd_read_stats`` (episodes, return_sum, progress_sum, ...) and every rank
 receives the per-rank table and its sum.  Mirrors what ``tools.simulate`` aggregates per episode on the host
 [REF dreamer/tools.py:159-206] and what ``callbacks.summarize_episode`` logs [REF dreamer/callbacks.py:74-100].
 """
@@ -13,7 +13,7 @@ import torch
 import torch.distributed as dist
 
 STAT_KEYS = ("episodes", "return_sum", "progress_sum", "length_sum", "collisions", "laps_completed", "env_steps",
-             "timeouts")
+             "timeouts", "max_progress_sum")
 
 
 def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
@@ -42,5 +42,7 @@ def summarize(total: Dict[str, float]) -> Dict[str, float]:
     n = max(total.get("episodes", 0.0), 1.0)
     return {"episodes": total.get("episodes", 0.0), "mean_return": total["return_sum"] / n,
             "mean_progress": total["progress_sum"] / n, "mean_length": total["length_sum"] / n,
+            # tools.simulate's per-episode statistic: max over the episode of lap + progress - 1 [REF dreamer/tools.py:181,195]
+            "mean_max_progress": total.get("max_progress_sum", 0.0) / n,
             "collision_rate": total["collisions"] / n, "timeout_rate": total["timeouts"] / n,
             "env_steps": total["env_steps"]}

@@ -28,6 +28,13 @@ committed so that the parity tests can run where /root/reference does not exist 
                            [REF dreamer/dream.py:103-140; dreamer/wrappers.py:107-116,147-154,210-226], reset whenever
                            any agent is done [REF dreamer/tools.py:178-179].
 
+  baselines_chain_golden.npz  the model-free wrap chains end to end: FilterObservation(['lidar']) -> Flatten ->
+                           NormalizeObservations (-> InfoToObservation) -> FixedResetMode -> TimeLimit(ticks) ->
+                           ActionRepeat [REF baselines/racing/experiments/acme/experiment.py:66-88] with the reference's
+                           own classes (gym's FilterObservation / TimeLimit restated in oracle/ref_stubs.py).
+  simulate_golden.npz      the reference's driver loop tools.simulate [REF dreamer/tools.py:154-206] (TensorFlow stubbed)
+                           over the unmodified dreamer wrapper stack: its per-episode `max_progresses` / `cum_rewards`.
+
 usage: python tests/golden/make_golden.py [name ...]
 """
 import sys
@@ -167,6 +174,106 @@ def baselines_stack_golden(n_steps=400, repeat=4):
     np.savez_compressed(OUT / "baselines_stack_golden.npz", actions=actions, repeat=repeat,
                         **{k: np.asarray(v) for k, v in rec.items()})
     print("baselines_stack_golden: episodes", int(np.sum(rec["done"])))
+
+
+class _Single:
+    """SingleAgentRaceEnv surface over the one-tick oracle env (racecar_gym's single-agent class is not in tree)."""
+
+    def __init__(self, env):
+        self.env = env
+        self.action_space = env.action_space["A"]
+        self.observation_space = env.observation_space["A"]
+
+    def step(self, action):
+        o, r, d, i = self.env.step({"A": action})
+        return o["A"], r["A"], d["A"], i["A"]
+
+    def reset(self, **kw):
+        return self.env.reset(**kw)["A"]
+
+
+def baselines_chain_golden(n_steps=300, repeat=4, limit_train=110, limit_test=170):
+    """Both model-free wrap chains [REF baselines/racing/experiments/acme/experiment.py:66-88 _wrap_training /
+    _wrap_test], every class the reference's own except gym's two (restated, see ref_stubs), over the one-tick oracle
+    env on Treitlstrasse (short episodes: collisions AND tick limits fire).  The float32 casts are acme's
+    SinglePrecisionWrapper [REF experiment.py:74,86]."""
+    B = ref_stubs.reference_baselines_env()
+    Cm = ref_stubs.reference_baselines_common()
+    tm = load_track("treitlstrasse_v2")
+    rng = np.random.RandomState(17)
+    actions = rng.uniform(-1.3, 1.3, (n_steps, 2)).astype(np.float32)
+    actions[:, 0] = np.abs(actions[:, 0]) * 0.7 + 0.3   # > 1 now and then: clipped by Flatten
+    actions[:, 1] *= 0.8
+    actions[60:170, 1] *= 0.05         # a stretch of near-straight driving: episodes long enough to hit the tick limit
+    out = {"actions": actions, "repeat": repeat, "limit_train": limit_train, "limit_test": limit_test}
+    for name, test in (("train", False), ("test", True)):
+        env = _Single(OracleRaceEnv(tm))
+        env = ref_stubs.FilterObservation(env, filter_keys=["lidar"])
+        env = B.Flatten(env, flatten_obs=not test, flatten_actions=True)
+        env = B.NormalizeObservations(env)
+        if test:
+            env = Cm.InfoToObservation(env)
+        env = Cm.FixedResetMode(env, mode="grid")
+        env = ref_stubs.GymTimeLimit(env, max_episode_steps=limit_test if test else limit_train)
+        env = B.ActionRepeat(env, n=repeat)
+        rec = {k: [] for k in ("lidar", "reward", "done", "reset_before", "truncated", "progress", "lap", "wrong_way",
+                               "wall_collision", "time")}
+        need_reset = True
+        for t in range(n_steps):
+            rec["reset_before"].append(need_reset)
+            if need_reset:
+                env.reset()
+            o, r, d, i = env.step(actions[t])
+            lid = o["lidar"] if test else o
+            rec["lidar"].append(np.asarray(lid, np.float64).astype(np.float32))
+            rec["reward"].append(r); rec["done"].append(d); rec["truncated"].append(bool(i.get("TimeLimit.truncated", False)))
+            if test:   # InfoToObservation: every info key shows up as obs['info_<key>'] [REF common.py:31-39]
+                assert sorted(k for k in o if k.startswith("info_")) == sorted(f"info_{k}" for k in i if k != "TimeLimit.truncated")
+                rec["progress"].append(o["info_progress"]); rec["lap"].append(o["info_lap"]); rec["time"].append(o["info_time"])
+                rec["wrong_way"].append(o["info_wrong_way"]); rec["wall_collision"].append(o["info_wall_collision"])
+            else:
+                rec["progress"].append(i["progress"]); rec["lap"].append(i["lap"]); rec["time"].append(i["time"])
+                rec["wrong_way"].append(i["wrong_way"]); rec["wall_collision"].append(i["wall_collision"])
+            need_reset = bool(d)
+        lid = np.asarray(rec.pop("lidar"))
+        out[f"{name}_lidar_every10"] = lid[::10]
+        out[f"{name}_lidar_sum"] = lid.sum(1, dtype=np.float64)
+        for k, v in rec.items():
+            out[f"{name}_{k}"] = np.asarray(v)
+        print(f"baselines_chain_golden[{name}]: episodes", int(np.sum(rec["done"])), "truncated", int(np.sum(rec["truncated"])),
+              "collisions", int(np.sum(rec["wall_collision"])))
+    np.savez_compressed(OUT / "baselines_chain_golden.npz", **out)
+
+
+def simulate_golden(n_episodes=9, action_repeat=4, duration=40):
+    """tools.simulate [REF dreamer/tools.py:154-206], unmodified (TensorFlow stubbed), driving the unmodified dreamer
+    wrapper stack over the one-tick oracle env with a scripted agent; what it hands to summarize_collection
+    (`max_progresses`, `cum_rewards`) is the per-episode statistic the device-side accumulators must reproduce."""
+    import tempfile
+    T = ref_stubs.reference_tools()
+    tm = load_track("treitlstrasse_v2")
+    env = make_reference_stack(tm, action_repeat=action_repeat, time_limit_steps=duration, reset_mode="grid")
+    rng = np.random.RandomState(23)
+    script = rng.uniform(-1, 1, (4000, 2)).astype(np.float32)
+    script[:, 0] = np.abs(script[:, 0]) * 0.6 + 0.2
+    script[:, 1] *= 0.3
+    used = []
+
+    def agent(obs, done, state):
+        a = script[len(used)]
+        used.append(a)
+        return np.stack([a]), state
+
+    captured = {}
+    T.summarize_collection = lambda metrics, *a, **kw: captured.update({k: list(v) for k, v in metrics.items()})
+    config = T.AttrDict(action_repeat=action_repeat)
+    with tempfile.TemporaryDirectory() as d:
+        T.simulate([agent], env, config, Path(d), writer=None, prefix="test", episodes=n_episodes)
+    np.savez_compressed(OUT / "simulate_golden.npz", actions=np.asarray(used), action_repeat=action_repeat,
+                        duration=duration, n_episodes=n_episodes, max_progresses=np.asarray(captured["progress"]),
+                        cum_rewards=np.asarray(captured["return"]))
+    print("simulate_golden: steps", len(used), "episodes recorded", len(captured["progress"]), "max_progresses",
+          np.round(captured["progress"], 3))
 
 
 def episodes_golden(n_steps=160, action_repeat=4, duration=45):
@@ -394,3 +501,5 @@ if __name__ == "__main__":
     episodes_golden()
     multi_agent_stack_golden()
     multi_agent_episodes_golden()
+    baselines_chain_golden()
+    simulate_golden()

@@ -34,8 +34,11 @@ def _case(seed):
         time_limit=float(r.choice([180.0, 0.35])), auto_reset=bool(r.rand() < 0.7),
         reset_mode=str(r.choice(["grid", "random", "random_bidirectional", "random_ball"])),
         lidar_noise=float(r.choice([0.0, 0.0, 0.03])), normalize_lidar=bool(r.rand() < 0.3),
+        time_limit_ticks=int(r.choice([0, 0, 13, 40])),
         obs_type=str(r.choice(["lidar", "lidar", "lidar_occupancy"])) if worlds * A <= 132 else "lidar",
         ball_spacing=float(r.choice([0.7, 1.5])), seed=int(r.randint(0, 2 ** 31)), env_id_offset=int(r.choice([0, 4096])) * A)
+    if not kw["normalize_lidar"] and r.rand() < 0.3:   # the model-free chain's NormalizeObservations
+        kw["normalize_obs"] = "baselines"
     return kw
 
 
@@ -50,7 +53,7 @@ def test_random_configuration_vs_oracle(seed):
     orc = Oracle(env.cfg, env.tracks, env.map_ids, n_threads=THREADS)
     n = env.n
     o, r = env.reset(), orc.reset(mode=int(env.cfg.reset_mode))
-    tol = 1e-3 if not kw["normalize_lidar"] else 1e-3 / 15.0
+    tol = 1e-3 if not (kw["normalize_lidar"] or kw.get("normalize_obs")) else 1e-3 / 15.0
     assert np.abs(o["lidar"].cpu().numpy() - r["lidar"]).max() <= tol, kw
     rng = np.random.RandomState(seed)
     for k in range(30):
@@ -65,6 +68,11 @@ def test_random_configuration_vs_oracle(seed):
         assert np.array_equal(done.cpu().numpy().astype(np.uint8), ref["done"]), (k, kw)
         assert np.array_equal(info["flags"].cpu().numpy(), ref["flags"]), (k, kw)
         assert np.array_equal(info["lap"].cpu().numpy(), ref["lap"]), (k, kw)
+        assert done.dtype == torch.bool and info["wrong_way"].dtype == torch.bool
+        assert np.array_equal(info["wrong_way"].cpu().numpy(), (ref["flags"] & _abi.F_WRONG_WAY) != 0), (k, kw)
+        assert np.array_equal(info["wall_collision"].cpu().numpy(), (ref["flags"] & _abi.F_COLLISION) != 0), (k, kw)
+        for key in ("pose", "velocity"):
+            assert np.allclose(obs[key].cpu().numpy(), ref[key], rtol=1e-5, atol=1e-6), (k, key, kw)
         assert np.array_equal(info["rank"].cpu().numpy(), ref["rank"]) or kw["agents_per_world"] == 1, (k, kw)
         assert np.allclose(rew.cpu().numpy(), ref["reward"], rtol=1e-5, atol=2e-5), (k, kw)
         assert np.abs(obs["lidar"].cpu().numpy() - ref["lidar"]).max() <= tol, (k, kw)
@@ -73,4 +81,9 @@ def test_random_configuration_vs_oracle(seed):
         f, i = env.get_state()
         assert np.array_equal(i.cpu().numpy(), orc.i32), (k, kw)
         assert np.all(np.abs(f.cpu().numpy() - orc.f64) <= 1e-5 * np.maximum(np.abs(orc.f64), 1.0)), (k, kw)
+    gs, os_ = env.read_stats(), orc.read_stats()
+    for key in ("episodes", "collisions", "laps_completed", "env_steps", "timeouts", "length_sum"):
+        assert gs[key] == os_[key], (key, gs, os_, kw)
+    for key in ("return_sum", "progress_sum", "max_progress_sum"):
+        assert abs(gs[key] - os_[key]) <= 1e-6 * max(1.0, abs(os_[key])), (key, gs, os_, kw)
     env.close()

@@ -444,3 +444,110 @@ def test_lidar_ragged_beam_counts(torch_cuda, nb):
     ids = np.ones(300, np.int32)
     assert np.abs(env.lidar_cast(torch.from_numpy(poses), ids).cpu().numpy() - orc.lidar_cast(poses, ids)).max() <= LIDAR_TOL_M
     env.close()
+
+
+# ---------------------------------------------------------------------------------------------- round-2 additions
+def test_dynamics_vs_independent_numpy_model(torch_cuda):
+    """north_star: "dynamics state after N steps must agree within 1e-5 relative, compared against a float64 NumPy
+    rendition of the same model" -- tests/np_single_track.py, the textbook form of SURVEY.md Appendix C that shares no
+    code or operation order with the kernel or the C oracle."""
+    from np_single_track import integrate, params_from_config, random_states
+    torch = torch_cuda
+    env = make_env(torch, tracks=("austria",), n_envs=8)
+    p = params_from_config(env.cfg)
+    for seed, (v_lo, v_hi), ticks in ((4, (0.0, 4.5), 400), (12, (0.3, 0.7), 60), (13, (0.0, 4.5), 8)):
+        state, cmd = random_states(4096, np.random.RandomState(seed), v_lo=v_lo, v_hi=v_hi)
+        got = env.dynamics(torch.from_numpy(state), torch.from_numpy(cmd), ticks).cpu().numpy()
+        want = integrate(p, state, cmd, ticks, dt=float(env.cfg.dt))
+        err = np.abs(got - want) / np.maximum(np.abs(want), 1.0)
+        assert err.max() <= DYN_RTOL, f"seed {seed}: {err.max():.3e}"      # the contract
+        assert err.max() < 1e-9, f"seed {seed}: {err.max():.3e}"           # in practice ~1e-13
+    env.close()
+
+
+def test_reward_done_stage_vs_oracle(torch_cuda):
+    """a7/a8 stage entry rd_reward_done: teacher-forced poses along and across the track, several ticks in a row so that
+    checkpoints advance, laps complete, cars leave the track; integer bookkeeping bit-exact, reward to rounding."""
+    torch = torch_cuda
+    for task, kw in (("maximize_progress", dict(laps=1, n_checkpoints=20)), ("max_speed", {}),
+                     ("maximize_progress", dict(progress_abs=True, terminate_on_collision=False, n_checkpoints=4, time_limit=0.05))):
+        env = make_env(torch, tracks=("treitlstrasse_v2", "austria"), n_envs=8, task=task, **kw)
+        orc = make_oracle(env)
+        rng = np.random.RandomState(31)
+        n = 3000
+        ids = np.sort(rng.randint(0, 2, n)).astype(np.int32)
+        bf = np.zeros((3, n)); bi = np.zeros((3, n), np.int32)
+        bi[0] = 1
+        idx = [rng.randint(0, len(env.tracks[m].reset_poses)) for m in ids]
+        bf[1] = rng.uniform(0, 1, n); bf[2] = 1.0 + bf[1]; bi[1] = (bf[1] * int(env.cfg.n_checkpoints)).astype(np.int32)
+        gbf, gbi = torch.from_numpy(bf), torch.from_numpy(bi)
+        for k in range(6):
+            stride = 40 * k                                   # walk along the lap: checkpoints and the finish line pass by
+            poses = np.stack([env.tracks[m].reset_poses[(i + stride) % len(env.tracks[m].reset_poses)] for m, i in zip(ids, idx)])
+            kin = np.zeros((5, n))
+            kin[0] = poses[:, 0] + rng.uniform(-0.4, 0.4, n); kin[1] = poses[:, 1] + rng.uniform(-0.4, 0.4, n)
+            kin[2] = poses[:, 2] + rng.uniform(-1, 1, n); kin[3] = rng.uniform(0, 4, n); kin[4] = rng.uniform(-0.3, 0.3, n)
+            kin[0, :5] = 1e7                                  # far outside the map
+            steer = rng.uniform(-1, 1, n)
+            gbf, gbi, grew, gdone = env.reward_done(torch.from_numpy(kin), torch.from_numpy(steer), gbf, gbi, ids)
+            bf, bi, rew, done = orc.reward_done(kin, steer, bf, bi, ids)
+            assert np.array_equal(gbi.cpu().numpy(), bi), (task, k)
+            assert np.array_equal(gdone.cpu().numpy(), done), (task, k)
+            assert np.array_equal(gbf.cpu().numpy(), bf), (task, k)          # time, progress, lap + progress: same operations
+            assert np.allclose(grew.cpu().numpy(), rew, rtol=1e-12, atol=1e-12), (task, k)
+        assert bi[0].max() >= 2 and (bi[2] & _abi.F_COLLISION).any() and (bi[2] & _abi.F_WRONG_WAY).any()
+        env.close()
+
+
+def test_baselines_normalize_observations(torch_cuda):
+    """RD_OBS_NORM_BASELINES: lidar / pose / velocity = (x - low) * (1 / (high - low)) in float64, then float32
+    [REF baselines/racing/environment/single_agent.py:66-99], fused into the stores of k_lidar and k_step."""
+    torch = torch_cuda
+    n = 256
+    kw = dict(tracks=("austria",), n_envs=n, action_repeat=4, auto_reset=True, reset_mode="random", seed=5,
+              clip_actions=True, rescale_actions=False, repeat_semantics="baselines", time_limit_ticks=50)
+    env = make_env(torch, normalize_obs="baselines", **kw)
+    raw = make_env(torch, **kw)
+    orc = make_oracle(env)
+    env.reset(); raw.reset(); orc.reset(mode=_abi.RESET_RANDOM)
+    rng = np.random.RandomState(3)
+    for k in range(20):
+        a = rng.uniform(-1.2, 1.2, (n, 2)).astype(np.float32)
+        obs, rew, done, info = env.step(torch.from_numpy(a).cuda())
+        robs, _, rdone, _ = raw.step(torch.from_numpy(a).cuda())
+        ref = orc.step(a)
+        assert np.array_equal(done.cpu().numpy().astype(np.uint8), ref["done"])
+        assert torch.equal(done, rdone)
+        for key in ("lidar", "pose", "velocity"):
+            got = obs[key].cpu().numpy()
+            assert np.abs(got - ref[key]).max() <= 1e-6, key
+            assert got.min() >= 0.0 and got.max() <= 1.0, key
+        # against the un-normalised run of the same kernels: exactly NormalizeObservations' arithmetic
+        want = ((robs["lidar"].cpu().numpy().astype(np.float64) - 0.0) * (1.0 / (15.0 - 0.0))).astype(np.float32)
+        assert np.array_equal(obs["lidar"].cpu().numpy(), want)
+    st = env.read_stats()
+    assert st["timeouts"] > 0                              # gym TimeLimit(50 ticks) inside ActionRepeat fired
+    env.close(); raw.close()
+
+
+def test_public_step_launches_only_the_env_kernels(torch_cuda):
+    """BatchedRaceEnv.step() -- the public API -- must not run eager PyTorch on the hot path: every tensor it returns is a
+    persistent buffer the CUDA kernels wrote (done and the two info flags as bool views of 0/1 bytes)."""
+    torch = torch_cuda
+    from torch.profiler import profile, ProfilerActivity
+    env = make_env(torch, tracks=("austria",), n_envs=512, action_repeat=8, auto_reset=True, reset_mode="random")
+    env.reset()
+    a = torch.zeros((512, 2), device="cuda")
+    env.step(a)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        for _ in range(3):
+            obs, rew, done, info = env.step(a)
+        torch.cuda.synchronize()
+    names = [e.name for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    kernels = [nm for nm in names if "memcpy" not in nm.lower() and "memset" not in nm.lower()]
+    assert kernels, "the profiler saw no kernels"
+    assert all(nm.startswith(("k_step", "k_lidar", "void k_lidar", "k_occupancy")) for nm in kernels), sorted(set(kernels))
+    assert done.dtype == torch.bool and done.data_ptr() == env.buf["done"].data_ptr()
+    assert info["wrong_way"].data_ptr() == env.buf["wrong_way"].data_ptr()
+    env.close()
