@@ -14,7 +14,8 @@ def __getattr__(name):
     if name in ("BatchedRaceEnv", "EnvConfig"):
         from . import env as _env
         return getattr(_env, name)
-    if name in ("RaceCarGymCompat", "ReferenceEnv", "SingleAgentRaceCompat", "make_reference_env", "load_scenario"):
+    if name in ("RaceCarGymCompat", "ReferenceEnv", "SingleAgentRaceCompat", "BaselinesEnv", "make_reference_env",
+                "load_scenario"):
         from . import compat as _compat
         return getattr(_compat, name)
     if name in ("GapFollowerPolicy", "DreamerPolicy", "load_dreamer_checkpoint", "save_dreamer_checkpoint"):

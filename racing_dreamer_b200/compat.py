@@ -247,7 +247,7 @@ class ReferenceEnv(_SingleAgentBase):
         if reset_mode is None:
             reset_mode = "random_ball" if n_agents > 1 else "random"
         if time_limit_steps is None:  # dream.py: time_limit_train 2000 sim ticks / action_repeat [REF dreamer/dream.py:57,109]
-            time_limit_steps = 2000 // int(action_repeat)
+            time_limit_steps = -(-2000 // int(action_repeat))   # TimeLimit(2000 / action_repeat) tests `step >= duration`: ceil
         self._make(track, n_agents=n_agents, agent_ids=ids, order=order, action_repeat=int(action_repeat), reset_mode=reset_mode,
                    obs_type="lidar_occupancy" if occupancy else "lidar", time_limit_steps=int(time_limit_steps),
                    rescale_actions=True, **params)
@@ -410,12 +410,99 @@ class SingleAgentRaceCompat:
         self._env.close()
 
 
+class BaselinesEnv(_SingleAgentBase):
+    """Fused equivalent of the model-free agents' wrap chains [REF baselines/racing/experiments/acme/experiment.py:66-88
+    _wrap_training / _wrap_test; baselines/racing/experiments/sb3/sb_experiment.py:42-58]:
+
+        ChangingTrackSingleAgentRaceEnv -> FilterObservation(['lidar']) -> Flatten -> NormalizeObservations
+        (-> InfoToObservation) -> FixedResetMode -> TimeLimit(max_episode_steps, in sim ticks) -> ActionRepeat(n)
+        (-> SinglePrecisionWrapper)
+
+    as ONE ``rd_step`` per agent step: the action clip of ``Flatten``, ``(x - low) / (high - low)`` of
+    ``NormalizeObservations`` [REF baselines/racing/environment/single_agent.py:55-56,66-99] and the tick-based time limit
+    run inside the kernels (``clip_actions``, ``normalize_obs='baselines'``, ``time_limit_ticks``,
+    ``repeat_semantics='baselines'``).
+
+    ``mode='train'``: ``reset() -> float32[1080]`` (the flattened, normalised scan), reset mode 'random', 2000 ticks.
+    ``mode='test'``:  ``reset() -> {'lidar': float32[1080]}``; after a step the dict also carries ``info_<key>`` for every
+    info key, as ``InfoToObservation`` adds them [REF baselines/racing/environment/common.py:31-39]; reset mode 'grid',
+    4000 ticks.  ``step(action[2]) -> (obs, reward, done, info)`` -- not keyed by agent id (``SingleAgentRaceEnv``);
+    ``info['TimeLimit.truncated']`` is set the way gym's TimeLimit does.  A list of tracks + ``order='sequential'`` moves
+    to the next track at every reset [REF acme/experiment.py:90-93]."""
+
+    def __init__(self, track="austria", task="max_progress", action_repeat: int = 4, mode: str = "train",
+                 time_limit: Optional[int] = None, device=None, scenario: Optional[str] = None,
+                 order: str = "sequential", **overrides):
+        if mode not in ("train", "test"):
+            raise ValueError("mode must be 'train' or 'test'")
+        self._device = device
+        self._test = mode == "test"
+        params = dict(SCENARIO_DEFAULTS.get(task, SCENARIO_DEFAULTS["max_progress"]))
+        if scenario is not None:
+            sc = load_scenario(scenario)
+            track = sc.pop("track", track)
+            for k in ("sensors", "agent_ids", "agents_per_world", "agent_tasks"):   # SingleAgentScenario: agent A only
+                sc.pop(k, None)
+            params.update(sc)
+        params.update(overrides)
+        self._limit = int(time_limit if time_limit is not None else (4000 if self._test else 2000))
+        self._reset_mode = "grid" if self._test else "random"
+        self._make(track, n_agents=1, order=order, action_repeat=int(action_repeat), reset_mode=self._reset_mode,
+                   obs_type="lidar", time_limit_steps=0, time_limit_ticks=self._limit, rescale_actions=False,
+                   clip_actions=True, repeat_semantics="baselines", normalize_obs="baselines", **params)
+        self._needs_reset = True
+        self._action = torch.zeros((1, 2), dtype=torch.float32, device=self._env.device)
+
+    @property
+    def observation_space(self):
+        lidar = spaces.Box(0.0, 1.0, shape=(1080,), dtype=np.float32)   # NormalizeObservations: zeros .. ones
+        return spaces.Dict({"lidar": lidar}) if self._test else lidar
+
+    @property
+    def action_space(self):  # Flatten: Box(-1, 1, shape (2,)) = [motor, steering] [REF single_agent.py:49-52]
+        return spaces.Box(np.array([-1.0, -1.0], np.float32), np.array([1.0, 1.0], np.float32))
+
+    def _obs(self, h, info=None):
+        lidar = h["lidar"][0]
+        if not self._test:
+            return lidar
+        obs = {"lidar": lidar}
+        for k, v in (info or {}).items():   # InfoToObservation sits inside TimeLimit: it never sees 'TimeLimit.truncated'
+            if k != "TimeLimit.truncated":
+                obs[f"info_{k}"] = v
+        return obs
+
+    def reset(self, mode: Optional[str] = None):
+        self._before_reset()
+        self._env.reset(mode=mode or self._reset_mode)
+        self._needs_reset = False
+        return self._obs(self._host())
+
+    def step(self, action):
+        assert not self._needs_reset, "Cannot call env.step() before calling reset()"   # gym TimeLimit's assertion
+        self._action.copy_(torch.from_numpy(np.asarray(action, dtype=np.float32).reshape(1, 2)))
+        self._env.step(self._action)
+        h = self._host()
+        done = bool(h["done"][0])
+        info = self._info(h)
+        # gym TimeLimit: the step that reaches max_episode_steps reports whether the env itself was done
+        ticks = int(round(float(h["time"][0]) / float(self._env.cfg.dt)))
+        if done and ticks >= self._limit:
+            task_done = bool(info["wall_collision"] and int(self._env.cfg.terminate_on_collision)) or \
+                info["lap"] > int(self._env.cfg.laps) or info["time"] > float(self._env.cfg.time_limit)
+            info["TimeLimit.truncated"] = not task_done
+        self._needs_reset = done
+        return self._obs(h, info), float(h["reward"][0]), done, info
+
+
 def make_reference_env(track: str, task: str = "max_progress", action_repeat: int = 4, mode: str = "train",
                        device=None, **kw) -> ReferenceEnv:
     """``make_train_env`` / ``make_test_env`` of dream.py without the PyBullet sim [REF dreamer/dream.py:103-131]:
-    train = reset mode 'random', TimeLimit 2000/action_repeat; test = 'grid', 4000/action_repeat."""
+    train = reset mode 'random', TimeLimit 2000/action_repeat; test = 'grid', 4000/action_repeat.  dream.py passes the
+    float quotient and TimeLimit ends the episode at `step >= duration` [REF dreamer/wrappers.py:150], i.e. after
+    ceil(limit / action_repeat) agent steps."""
     if mode == "train":  # 'random' for one car, 'random_ball' for several [REF dreamer/dream.py:105-108]
-        return ReferenceEnv(track, task, action_repeat, time_limit_steps=2000 // action_repeat, reset_mode=None,
+        return ReferenceEnv(track, task, action_repeat, time_limit_steps=-(-2000 // action_repeat), reset_mode=None,
                             device=device, **kw)
-    return ReferenceEnv(track, task, action_repeat, time_limit_steps=4000 // action_repeat, reset_mode="grid",
+    return ReferenceEnv(track, task, action_repeat, time_limit_steps=-(-4000 // action_repeat), reset_mode="grid",
                         device=device, **kw)

@@ -125,6 +125,12 @@ class EpisodeRecorder:
         cfg = getattr(env, "cfg", None) or getattr(getattr(env, "env", None), "cfg", None)
         A = agents_per_world if agents_per_world is not None else int(getattr(cfg, "agents_per_world", 1) or 1)
         self.agents = max(1, int(A))
+        # Collect stores the TERMINAL observation of an episode and resets afterwards [REF dreamer/wrappers.py:210-226]; an
+        # auto-resetting env has already replaced it with the first observation of the next episode (and advanced the
+        # reset counters) by the time the recorder sees the done flag.
+        if cfg is not None and int(getattr(cfg, "auto_reset", 0)):
+            raise ValueError("EpisodeRecorder needs an env created with auto_reset=False: it resets finished envs itself, "
+                             "after storing their terminal observation")
         if self.n % self.agents:
             raise ValueError("n_envs must be a multiple of agents_per_world")
         self.max_len = int(max_len)

@@ -195,3 +195,67 @@ def assert_matches_multi_agent_golden(rec, g, lidar_tol=0.0, float_tol=0.0):
     else:
         assert np.abs(rec["lidar"][::20] - g["lidar_every20"]).max() <= lidar_tol
     assert np.abs(rec["lidar"].sum(2, dtype=np.float64) - g["lidar_sum"]).max() <= max(lidar_tol * 1080, 0.0)
+
+
+# ---------------------------------------------------------------------------------------------- model-free chain (a11)
+def fused_baselines_chain_config(cfg, g, test: bool):
+    """rd_config equivalent of the model-free wrap chains [REF baselines/racing/experiments/acme/experiment.py:66-88]:
+    Flatten(clip) -> NormalizeObservations -> FixedResetMode('grid') -> TimeLimit(ticks) -> ActionRepeat."""
+    cfg.n_envs = 1
+    cfg.action_repeat = int(g["repeat"])
+    cfg.repeat_semantics = _abi.REPEAT_BASELINES
+    cfg.rescale_actions = 0
+    cfg.clip_actions = 1
+    cfg.time_limit_steps = 0
+    cfg.time_limit_ticks = int(g["limit_test"] if test else g["limit_train"])
+    cfg.auto_reset = 0
+    cfg.reset_mode = _abi.RESET_GRID
+    cfg.obs_flags = _abi.OBS_LIDAR | _abi.OBS_NORM_BASELINES
+    return cfg
+
+
+def assert_matches_baselines_chain_golden(rec, g, name, lidar_tol=0.0, float_tol=0.0):
+    """rec: replay() records of the fused env; g: baselines_chain_golden.npz; name: 'train' | 'test'."""
+    assert np.array_equal(rec["done"].astype(bool), g[f"{name}_done"])
+    assert np.array_equal(rec["lap"], g[f"{name}_lap"])
+    fl = rec["flags"]
+    assert np.array_equal((fl & _abi.F_COLLISION) != 0, g[f"{name}_wall_collision"])
+    assert np.array_equal((fl & _abi.F_WRONG_WAY) != 0, g[f"{name}_wrong_way"])
+    for k in ("reward", "progress", "time"):
+        a, b = rec[k].astype(np.float64), g[f"{name}_{k}"].astype(np.float32).astype(np.float64)
+        if float_tol == 0.0:
+            assert np.array_equal(a, b), k
+        else:
+            assert np.all(np.abs(a - b) <= float_tol * np.maximum(1.0, np.abs(b))), k
+    lid = rec["lidar"]
+    assert lid.dtype == np.float32 and lid.min() >= 0.0 and lid.max() <= 1.0     # NormalizeObservations: [0, 1]
+    if lidar_tol == 0.0:
+        assert np.array_equal(lid[::10], g[f"{name}_lidar_every10"])
+    else:
+        assert np.abs(lid[::10] - g[f"{name}_lidar_every10"]).max() <= lidar_tol
+    assert np.abs(lid.sum(1, dtype=np.float64) - g[f"{name}_lidar_sum"]).max() <= max(lidar_tol * 1080, 0.0)
+
+
+# ---------------------------------------------------------------------------------------------- tools.simulate (a12)
+def simulate_statistics(reset_fn, step_fn, read_stats_fn, g):
+    """Drives a fused single env (TimeLimit, ActionRepeat inside) through simulate_golden.npz's action script with
+    simulate's reset rule (reset when done) and turns the device-side per-episode statistics into the two lists
+    tools.simulate hands to summarize_collection [REF dreamer/tools.py:154-206]:
+      cum_rewards[i]    = return of episode i                                   -> rd_stats.return_sum per episode
+      max_progresses[i] = max(episode_progresses) at the reset after episode i; the reference never clears that list, so
+                          it is the running maximum over every step so far      -> cummax of rd_stats.max_progress_sum
+    Both lists are appended at the NEXT reset, so the last episode of a call is not in them."""
+    returns, maxima = [], []
+    need_reset = True
+    for a in g["actions"]:
+        if need_reset:
+            reset_fn()
+        out = step_fn(a[None])
+        need_reset = bool(out["done"][0])
+        if need_reset:
+            st = read_stats_fn()
+            assert st["episodes"] == 1.0
+            returns.append(st["return_sum"])
+            maxima.append(st["max_progress_sum"])
+    assert need_reset and len(returns) == int(g["n_episodes"])
+    return np.asarray(returns[:-1]), np.maximum.accumulate(np.asarray(maxima))[:-1]

@@ -77,3 +77,31 @@ def test_reference_wrapper_arithmetic_live():
         mine = t.astype(np.float64) * (np.array([1.0, 1.0]) - np.array([0.005, -1.0])) + np.array([0.005, -1.0])
         assert np.array_equal(d.last["A"], mine)
     assert cfg.action_low[0] == 0.005 and cfg.action_high[0] == 1.0
+
+
+@pytest.mark.parametrize("name", ["train", "test"])
+def test_baselines_chain_replay(golden_dir, name):
+    """a11 + the model-free chain end to end: FilterObservation(['lidar']) -> Flatten -> NormalizeObservations
+    (-> InfoToObservation) -> FixedResetMode -> gym TimeLimit (ticks, inside ActionRepeat) -> ActionRepeat of the
+    reference [REF baselines/racing/experiments/acme/experiment.py:66-88; baselines/racing/environment/
+    single_agent.py:31-99; common.py:22-39] == one fused step with RD_OBS_NORM_BASELINES + time_limit_ticks."""
+    g = np.load(golden_dir / "baselines_chain_golden.npz")
+    cfg = helpers.fused_baselines_chain_config(default_config(), g, test=(name == "test"))
+    orc = Oracle(cfg, [load_track("treitlstrasse_v2")])
+    rec = helpers.replay(lambda: orc.reset(mode=_abi.RESET_GRID), lambda a: orc.step(a), g["actions"],
+                         g[f"{name}_reset_before"])
+    helpers.assert_matches_baselines_chain_golden(rec, g, name)
+    assert g[f"{name}_truncated"].sum() > 0                      # the tick limit really fired in the recording
+
+
+def test_simulate_statistics(golden_dir):
+    """a12: the per-episode statistics of the reference's driver loop tools.simulate [REF dreamer/tools.py:154-206]
+    (max over the episode of lap + progress - 1, cumulative reward of the first agent) from the device-side accumulators'
+    CPU restatement."""
+    g = np.load(golden_dir / "simulate_golden.npz")
+    cfg = helpers.fused_dreamer_config(default_config(), int(g["action_repeat"]), int(g["duration"]), occupancy=False)
+    orc = Oracle(cfg, [load_track("treitlstrasse_v2")])
+    returns, maxima = helpers.simulate_statistics(lambda: orc.reset(mode=_abi.RESET_GRID), lambda a: orc.step(a),
+                                                  lambda: orc.read_stats(reset=True), g)
+    assert np.allclose(returns, g["cum_rewards"], rtol=1e-12, atol=1e-12)
+    assert np.allclose(maxima, g["max_progresses"], rtol=0, atol=1e-12)

@@ -551,3 +551,33 @@ def test_public_step_launches_only_the_env_kernels(torch_cuda):
     assert done.dtype == torch.bool and done.data_ptr() == env.buf["done"].data_ptr()
     assert info["wrong_way"].data_ptr() == env.buf["wrong_way"].data_ptr()
     env.close()
+
+
+@pytest.mark.parametrize("name", ["train", "test"])
+def test_baselines_chain_golden_replay(torch_cuda, golden_dir, name):
+    """The model-free wrap chains of the reference (recorded with its own classes, baselines_chain_golden.npz) through
+    the CUDA path: clip, NormalizeObservations, tick-based gym TimeLimit inside ActionRepeat, the baselines repeat rule."""
+    torch = torch_cuda
+    from racing_dreamer_b200 import BatchedRaceEnv
+    g = np.load(golden_dir / "baselines_chain_golden.npz")
+    cfg = helpers.fused_baselines_chain_config(_abi.default_config(), g, test=(name == "test"))
+    env = BatchedRaceEnv(tracks=("treitlstrasse_v2",), raw_config=cfg, device="cuda:0")
+    rec = helpers.replay(lambda: env.reset(mode="grid"), _gpu_step_fn(torch, env), g["actions"], g[f"{name}_reset_before"])
+    helpers.assert_matches_baselines_chain_golden(rec, g, name, lidar_tol=LIDAR_TOL_M / 15.0, float_tol=DYN_RTOL)
+    env.close()
+
+
+def test_simulate_statistics_on_device(torch_cuda, golden_dir):
+    """a12: rd_read_stats reproduces what the reference's tools.simulate collects per episode -- max over the episode of
+    lap + progress - 1 and the cumulative reward [REF dreamer/tools.py:178-199] (simulate_golden.npz, recorded from the
+    unmodified function)."""
+    torch = torch_cuda
+    from racing_dreamer_b200 import BatchedRaceEnv
+    g = np.load(golden_dir / "simulate_golden.npz")
+    cfg = helpers.fused_dreamer_config(_abi.default_config(), int(g["action_repeat"]), int(g["duration"]), occupancy=False)
+    env = BatchedRaceEnv(tracks=("treitlstrasse_v2",), raw_config=cfg, device="cuda:0")
+    returns, maxima = helpers.simulate_statistics(lambda: env.reset(mode="grid"), _gpu_step_fn(torch, env),
+                                                  lambda: env.read_stats(reset=True), g)
+    assert np.allclose(returns, g["cum_rewards"], rtol=1e-9, atol=1e-9)
+    assert np.allclose(maxima, g["max_progresses"], rtol=0, atol=1e-9)
+    env.close()
