@@ -12,6 +12,11 @@
 //                  image whose 1+2 border rows/columns hold the mirrored values, so the 4x4 taps need no index math
 //   A' uniform map  8x8-cell blocks that are, with their 8 neighbours, all drivable / all not: pixels landing there are
 //                  that constant exactly and skip the taps (about 60-70 % of the pixels of a track crop)
+//   A" tile classes  every 8x4 tile of the mid image is classified by ONE lane (32 tiles per warp instruction): its four
+//                  corners bound the source coordinates of its 32 pixels (each coordinate is a rounded sum of a monotone
+//                  function of the row and one of the column), so a tile whose bounding blocks are all uniform with
+//                  one class -- or that lies outside the crop -- is that constant for every pixel by the per-pixel
+//                  rule; its plane bytes are written on the spot.  Only the mixed tiles (about half) go to stage C.
 //   C  rotation    one pixel per thread, an 8x4 pixel tile per warp; source coordinates in float64 with scipy's exact operation order (they decide floor() and
 //                  the inside test); value in float32; the rounded pixel is stored as two warp-ballot bit planes
 //   C' exactness   a pixel whose float32 value lies within OCC_EPS of a rounding threshold (k + 0.5) is re-evaluated in
@@ -64,11 +69,14 @@ struct OccGeom {              // per-env geometry, computed by one thread
 #define OCC_SM_XBITS_BYTES (RD_OCC_IN * OCC_XW * 4)                   // 6,160
 #define OCC_SM_PLANES (OCC_SM_XBITS + OCC_SM_XBITS_BYTES)
 #define OCC_SM_PLANES_BYTES (2 * (RD_OCC_MID * RD_OCC_MID / 32) * 4)  // 10,000
-#define OCC_SM_RC (OCC_SM_PLANES + OCC_SM_PLANES_BYTES)               // per-row / per-column coordinate terms (float64); 16-byte aligned
-#define OCC_SM_RC_BYTES (4 * RD_OCC_MID * 8)                          // 6,400
-#define OCC_SM_UNI (OCC_SM_RC + OCC_SM_RC_BYTES)                      // block class maps (2 x 28 x 28 bytes)
-#define OCC_SM_UNI_BYTES (2 * OCC_NB * OCC_NB)                        // 1,568
-#define OCC_SM_TOTAL (OCC_SM_UNI + OCC_SM_UNI_BYTES)                  // 226,624 of 232,448
+#define OCC_SM_RC (OCC_SM_PLANES + OCC_SM_PLANES_BYTES)               // per-row coordinate terms (float64); 16-byte aligned
+#define OCC_SM_RC_BYTES (2 * RD_OCC_MID * 8)                          // 3,200
+#define OCC_SM_EDGE (OCC_SM_RC + OCC_SM_RC_BYTES)                     // near-edge bitmap, same layout as the crop bits
+#define OCC_SM_EDGE_BYTES (RD_OCC_IN * OCC_XW * 4)                    // 6,160
+#define OCC_SM_TLIST (OCC_SM_EDGE + OCC_SM_EDGE_BYTES)                // packed (ty, tx) of the mixed 8x4 tiles of the mid image (u16)
+#define OCC_N_TILES (RD_OCC_MID * RD_OCC_MID / 32)                    // 1250
+#define OCC_SM_TLIST_BYTES ((OCC_N_TILES * 2 + 15) & ~15)             // 2,512
+#define OCC_SM_TOTAL (OCC_SM_TLIST + OCC_SM_TLIST_BYTES)              // 230,528 of 232,448
 // after the rotation the coefficient image is dead; its space holds the uint8 images and tables of the resize
 #define OCC_SM_TMP 0
 #define OCC_SM_TAB (OCC_SM_TMP + RD_OCC_MID * RD_OCC_OUT)
@@ -87,87 +95,105 @@ __device__ __forceinline__ void occ_weights(double x, double (&w)[4]) {
   w[3] = 1.0 - w[0] - w[1] - w[2];
 }
 
-// float32 cubic B-spline prefilter of the 220 lines of one axis (mirror boundary, pole z = sqrt(3)-2, gain 6), in place,
-// by the whole CTA.  Element i of line L lives at img[L * line_stride + i * elem_stride].  FROM_BITS: the input is the
-// crop bit (i, L) instead of the image (the column pass reads the binary crop directly).
-// Each line is cut into OCC_NSEG segments handled by different threads: the recursion's memory decays like |z|^k, so a
-// segment that starts 24 samples early from zero reproduces the full-line recursion to |z|^24 = 2e-14 relative -- far
-// below float32 resolution -- and the serial chain per thread is 4x (2x) shorter.  Warm-ups only read; barriers
-// separate them from the in-place main loops.
-#define OCC_NSEG (OCC_THREADS / 256)
-#define OCC_SEG (RD_OCC_IN / OCC_NSEG)
-#define OCC_WARM 24
-template <bool FROM_BITS>
-__device__ __forceinline__ void occ_prefilter_axis(float* img, int line_stride, int elem_stride, const uint32_t* xb) {
-  const int n = RD_OCC_IN;
-  const float z = -0.26794919243112270647f, gain = 6.0f;
-  const int tid = threadIdx.x;
-  const int seg = tid / RD_OCC_IN, L = tid - seg * RD_OCC_IN;
-  const bool active = seg < OCC_NSEG;
-  const int i0 = seg * OCC_SEG, i1 = i0 + OCC_SEG;
-  float* p = img + L * line_stride;
-  auto in = [&](int i) -> float {
-    if (FROM_BITS) return (float)((xb[i * OCC_XW + (L >> 5)] >> (L & 31)) & 1u);
-    return p[i * elem_stride];
-  };
-  float prev = 0.0f;
-  if (active) {
-    if (seg == 0) {  // scipy's mirror initialisation: sum_i z^i c[i] (z^24 ~ 2e-14 truncation)
-      float zi = 1.0f;
-#pragma unroll 4
-      for (int i = 0; i < OCC_WARM; ++i) { prev = fmaf(zi, gain * in(i), prev); zi *= z; }
+// float32 cubic B-spline prefilter of the 220 lines of one axis (mirror boundary, pole z = sqrt(3)-2, gain 6), one WARP
+// per line, every sample in registers:
+//   scipy's recursion is  y[i] = 6 x[i] + z y[i-1]  (causal, y[0] = the mirror sum  sum_i z^i 6 x[i])  followed by
+//   w[n-1] = (z y[n-2] + y[n-1]) z / (z^2 - 1),  w[i] = z (w[i+1] - y[i])  (anticausal).
+// Lane l owns samples 7l .. 7l+6.  It runs both recursions on its seven samples with a zero incoming state, and the true
+// incoming state is restored from its neighbours' end values: the state decays by z^7 = -1e-4 per lane, so three
+// neighbours (z^21 = 1e-12) reproduce the full-line recursion far below float32 resolution.  Compared with one thread per
+// line this replaces two 134-step dependent chains per thread and axis by 7-step chains, reads and writes every sample
+// once per axis instead of twice, and needs one barrier per axis instead of four.
+// Element i of line L lives at img[L * LINE_STRIDE + i * ELEM_STRIDE].  FROM_BITS: the line is crop ROW L and its input
+// the crop bits (L, i) instead of the image -- the first pass reads the binary crop directly, seven bits of one funnel
+// shift per lane.  (scipy filters axis 0 first; the operator is separable, so the order only moves float32 rounding.)
+#define OCC_LANE_N 7
+template <bool FROM_BITS, int LINE_STRIDE, int ELEM_STRIDE>
+__device__ __forceinline__ void occ_prefilter_axis(float* img, const uint32_t* xb) {
+  constexpr int n = RD_OCC_IN;
+  constexpr float z = -0.26794919243112270647f, gain = 6.0f;
+  constexpr float z2 = z * z, z3 = z2 * z, z4 = z3 * z, z5 = z4 * z, z6 = z5 * z, z7 = z6 * z;
+  const float zp[OCC_LANE_N] = {z, z2, z3, z4, z5, z6, z7};
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i0 = lane * OCC_LANE_N;
+  for (int L = warp; L < n; L += OCC_THREADS / 32) {
+    float* p = img + L * LINE_STRIDE + i0 * ELEM_STRIDE;
+    float x[OCC_LANE_N];
+    if (FROM_BITS) {   // bits i0 .. i0+6 of crop row L (bits beyond column 219 are zero in the crop words)
+      const uint32_t* row = xb + L * OCC_XW;
+      const int wj = i0 >> 5;
+      const uint32_t w = __funnelshift_r(row[wj], wj + 1 < OCC_XW ? row[wj + 1] : 0u, i0 & 31);
+#pragma unroll
+      for (int j = 0; j < OCC_LANE_N; ++j) x[j] = ((w >> j) & 1u) ? gain : 0.0f;
     } else {
-#pragma unroll 4
-      for (int i = i0 - OCC_WARM; i < i0; ++i) prev = fmaf(z, prev, gain * in(i));
+#pragma unroll
+      for (int j = 0; j < OCC_LANE_N; ++j) x[j] = (i0 + j < n) ? gain * p[j * ELEM_STRIDE] : 0.0f;
     }
-  }
-  __syncthreads();
-  if (active) {
-    int i = i0;
-    if (seg == 0) { p[0] = prev; i = 1; }
-#pragma unroll 4
-    for (; i < i1; ++i) {
-      prev = fmaf(z, prev, gain * in(i));
-      p[i * elem_stride] = prev;
+    // ---- causal pass ----
+    float u[OCC_LANE_N];
+    u[0] = x[0];
+#pragma unroll
+    for (int j = 1; j < OCC_LANE_N; ++j) u[j] = fmaf(z, u[j - 1], x[j]);
+    // mirror initialisation y[0] = sum_i z^i x[i]: lanes 0..3 hold the first 28 terms (z^28 = 1e-16)
+    float poly = x[OCC_LANE_N - 1];
+#pragma unroll
+    for (int j = OCC_LANE_N - 2; j >= 0; --j) poly = fmaf(z, poly, x[j]);
+    const float p1 = __shfl_sync(0xffffffffu, poly, 1), p2 = __shfl_sync(0xffffffffu, poly, 2), p3 = __shfl_sync(0xffffffffu, poly, 3);
+    const float y0 = fmaf(z7, fmaf(z7, fmaf(z7, p3, p2), p1), __shfl_sync(0xffffffffu, poly, 0));
+    const float s0 = (y0 - __shfl_sync(0xffffffffu, x[0], 0)) * (1.0f / z);   // the state "before sample 0" that yields y[0]
+    // lanes 0..2 have fewer than three predecessors: the state before sample 0 (s0) stands in for "lane -1"
+    const bool first = lane == 0;
+    float c1 = __shfl_up_sync(0xffffffffu, u[OCC_LANE_N - 1], 1);
+    c1 = first ? s0 : c1;
+    float c2 = __shfl_up_sync(0xffffffffu, c1, 1);
+    c2 = first ? 0.0f : c2;
+    float c3 = __shfl_up_sync(0xffffffffu, c2, 1);
+    c3 = first ? 0.0f : c3;
+    const float sin_ = fmaf(z7, fmaf(z7, c3, c2), c1);
+    float y[OCC_LANE_N];
+#pragma unroll
+    for (int j = 0; j < OCC_LANE_N; ++j) y[j] = fmaf(zp[j], sin_, u[j]);
+    // ---- anticausal pass ----
+    constexpr int last_lane = (n - 1) / OCC_LANE_N, last_j = (n - 1) - last_lane * OCC_LANE_N;   // sample n-1 = lane 31, slot 2
+    static_assert(last_lane == 31 && last_j >= 1, "220 samples over 32 lanes of 7");
+    float v[OCC_LANE_N + 1];
+    v[OCC_LANE_N] = 0.0f;
+    const bool tail = lane == last_lane;
+    const float w_end = (z * y[last_j - 1] + y[last_j]) * (z / (z * z - 1.0f));
+#pragma unroll
+    for (int j = OCC_LANE_N - 1; j >= 0; --j) {
+      float t = z * (v[j + 1] - y[j]);
+      if (tail && j > last_j) t = 0.0f;       // samples beyond the line
+      if (tail && j == last_j) t = w_end;     // scipy's anticausal initialisation
+      v[j] = t;
     }
-  }
-  __syncthreads();
-  float cur = 0.0f;
-  if (active) {
-    if (seg == OCC_NSEG - 1) {
-      cur = (z * p[(n - 2) * elem_stride] + p[(n - 1) * elem_stride]) * (z / (z * z - 1.0f));
-    } else {
-#pragma unroll 4
-      for (int i = i1 + OCC_WARM - 1; i >= i1; --i) cur = z * (cur - p[i * elem_stride]);
-    }
-  }
-  __syncthreads();
-  if (active) {
-    int i = i1 - 1;
-    if (seg == OCC_NSEG - 1) { p[(n - 1) * elem_stride] = cur; i = n - 2; }
-#pragma unroll 4
-    for (; i >= i0; --i) {
-      cur = z * (cur - p[i * elem_stride]);
-      p[i * elem_stride] = cur;
-    }
+    float d1 = __shfl_down_sync(0xffffffffu, v[0], 1);
+    d1 = tail ? 0.0f : d1;
+    float d2 = __shfl_down_sync(0xffffffffu, d1, 1);
+    d2 = tail ? 0.0f : d2;
+    float d3 = __shfl_down_sync(0xffffffffu, d2, 1);
+    d3 = tail ? 0.0f : d3;
+    const float tin = fmaf(z7, fmaf(z7, d3, d2), d1);   // 0 for lane 31: its values are final already
+#pragma unroll
+    for (int j = 0; j < OCC_LANE_N; ++j)
+      if (i0 + j < n) p[j * ELEM_STRIDE] = fmaf(zp[OCC_LANE_N - 1 - j], tin, v[j]);
   }
   __syncthreads();
 }
 
 // Source coordinates of mid pixel (a, b) with scipy's operation order (shift first, then one product per output axis):
 //   c0 = (off0 + o0*c) + o1*s ,  c1 = (off1 + o0*(-s)) + o1*c .
-// The per-row terms (off + o0*..) and per-column terms (o1*..) are tabulated once per env: rc[0..199] row term of c0,
-// rc[200..399] row term of c1, rc[400..599] column term of c0, rc[600..799] column term of c1 -- same operations, same bits.
+// The per-row terms (off + o0*..) are tabulated once per env: rc[0..199] row term of c0, rc[200..399] row term of c1; the
+// per-column terms are one product each -- same operations, same bits.
 __device__ __forceinline__ void occ_coord_tables(const OccGeom& g, double* rc, int i) {
-  const double o0 = (double)(g.o0_first + i), o1 = (double)(g.o1_first + i);
+  const double o0 = (double)(g.o0_first + i);
   rc[i] = __dadd_rn(g.off0, __dmul_rn(o0, g.c));
   rc[RD_OCC_MID + i] = __dadd_rn(g.off1, __dmul_rn(o0, -g.s));
-  rc[2 * RD_OCC_MID + i] = __dmul_rn(o1, g.s);
-  rc[3 * RD_OCC_MID + i] = __dmul_rn(o1, g.c);
 }
-__device__ __forceinline__ void occ_coords(const double* rc, int a, int b, double& c0, double& c1) {
-  c0 = __dadd_rn(rc[a], rc[2 * RD_OCC_MID + b]);
-  c1 = __dadd_rn(rc[RD_OCC_MID + a], rc[3 * RD_OCC_MID + b]);
+__device__ __forceinline__ void occ_coords(const double* rc, const OccGeom& g, int a, int b, double& c0, double& c1) {
+  const double o1 = (double)(g.o1_first + b);
+  c0 = __dadd_rn(rc[a], __dmul_rn(o1, g.s));
+  c1 = __dadd_rn(rc[RD_OCC_MID + a], __dmul_rn(o1, g.c));
 }
 
 // Exact float64 value of one rotated pixel (a, b), computed by ONE WARP from coef = H X H^T; every lane returns the
@@ -177,11 +203,11 @@ __device__ __forceinline__ void occ_coords(const double* rc, int a, int b, doubl
 //   C: the 4x4 taps in scipy's accumulation order and its rounding.
 // No shared scratch, no CTA barrier: about one image in 40 needs it, so its cost (~10k instructions) is irrelevant, but
 // it must not make the other warps wait.
-__device__ __noinline__ uint32_t occ_exact_pixel(const double* rc, int a, int b, const uint32_t* xb,
+__device__ __noinline__ uint32_t occ_exact_pixel(const double* rc, const OccGeom& g, int a, int b, const uint32_t* xb,
                                                  const double* __restrict__ hband) {
   const int lane = threadIdx.x & 31;
   double c0, c1;
-  occ_coords(rc, a, b, c0, c1);
+  occ_coords(rc, g, a, b, c0, c1);
   const int s0 = (int)floor(c0) - 1, s1 = (int)floor(c1) - 1;
   int rp[4], cq[4];
 #pragma unroll
@@ -252,12 +278,13 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
   uint32_t* xb = reinterpret_cast<uint32_t*>(smem + OCC_SM_XBITS);
   uint32_t* planes = reinterpret_cast<uint32_t*>(smem + OCC_SM_PLANES);
   double* rc = reinterpret_cast<double*>(smem + OCC_SM_RC);
-  uint8_t* cls = smem + OCC_SM_UNI;                 // per 8x8 block: 0 all non-drivable, 1 all drivable, 2 mixed
-  uint8_t* uni = cls + OCC_NB * OCC_NB;             // same, but only if the 8 neighbouring blocks agree (else 2)
+  uint32_t* eb = reinterpret_cast<uint32_t*>(smem + OCC_SM_EDGE);   // near-edge bitmap (see stage A')
   uint8_t* tmp = smem + OCC_SM_TMP;
   OccTables* tb = reinterpret_cast<OccTables*>(smem + OCC_SM_TAB);
+  uint16_t* tlist = reinterpret_cast<uint16_t*>(smem + OCC_SM_TLIST);
   __shared__ OccGeom geom;
   __shared__ int any_hi;
+  __shared__ int n_mixed;
 
   const DevMap& m = maps[map_id];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -304,6 +331,7 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
       geom.o0_first = oh / 2 - RD_OCC_MID / 2;
       geom.o1_first = ow / 2 - RD_OCC_MID / 2;
       any_hi = 0;
+      n_mixed = 0;
     }
     __syncthreads();
     if (tid < RD_OCC_MID) occ_coord_tables(geom, rc, tid);
@@ -326,39 +354,97 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
       xb[t] = w;
     }
     __syncthreads();
-    // ---- A': uniform-region map.  A rotated pixel whose source cell lies in a block that is, together with its eight
-    // neighbours, entirely drivable (or entirely not) sees a constant crop within >= 8 cells; the spline there equals
-    // that constant to < 1e-3 (|pole|^7 tail), so the pixel is exactly that constant and needs no taps. ----
-    for (int t = tid; t < OCC_NB * OCC_NB; t += OCC_THREADS) {
-      const int bi = t / OCC_NB, bj = t - bi * OCC_NB;
-      const uint32_t valid = bj == OCC_NB - 1 ? 0x0Fu : 0xFFu;   // crop columns 220..223 do not exist
-      uint32_t all_and = valid, all_or = 0u;
-      for (int rr = 0; rr < 8; ++rr) {
-        const int r = 8 * bi + rr;
-        if (r >= RD_OCC_IN) break;
-        const uint32_t byte = (xb[r * OCC_XW + (bj >> 2)] >> ((bj & 3) * 8)) & valid;
-        all_and &= byte;
-        all_or |= byte;
+    // ---- A': near-edge bitmap.  Bit (i0, i1) = the 4x4 cells [i0-1, i0+2] x [i1-1, i1+2] around a source point with
+    // floor coordinates (i0, i1) -- exactly the cells its cubic-spline taps touch; cells beyond the crop mirror cells of the
+    // same window -- are NOT all equal.  Where the bit is clear the rotated pixel needs no arithmetic: the cardinal
+    // cubic spline has |eta| mass 0.0933 outside a window of this size and total mass 1.549 per axis, so the interpolated
+    // value lies within 1.549^2 - (1.549 - 0.0933)^2 = 0.28 of the window's constant c in {0, 1} and rounds to c
+    // ((uint8)(v + 0.5) = 1 for v in [0.72, 1.28], 0 for v <= 0.28).  Only a band of +-2 cells along the track walls has
+    // the bit set.  Row stage: AND / OR over columns c-1 .. c+2; column stage: over rows r-1 .. r+2. ----
+    for (int t = tid; t < RD_OCC_IN * OCC_XW; t += OCC_THREADS) {
+      const int i = t / OCC_XW, j = t - i * OCC_XW;
+      const uint32_t last_mask = (1u << (RD_OCC_IN - 32 * (OCC_XW - 1))) - 1u;       // 28 valid columns in the last word
+      uint32_t all1 = 0xffffffffu, any1 = 0u;
+#pragma unroll
+      for (int dr = -1; dr <= 2; ++dr) {
+        const int r = i + dr;
+        if (r < 0 || r >= RD_OCC_IN) continue;                                       // clipped window
+        const uint32_t* row = xb + r * OCC_XW;
+        const uint32_t w = row[j];
+        const uint32_t lo = j > 0 ? row[j - 1] : 0u, hi = j < OCC_XW - 1 ? row[j + 1] : 0u;
+        // neighbours of column c: c-1 (bit c of w << 1 | carry), c+1, c+2
+        const uint32_t m1 = (w << 1) | (lo >> 31), p1 = (w >> 1) | (hi << 31), p2 = (w >> 2) | (hi << 30);
+        // columns outside [0, 219] are not part of the window: neutral element of each reduction there
+        const uint32_t vw = j == OCC_XW - 1 ? last_mask : 0xffffffffu;                // valid columns of this word
+        const uint32_t vm1 = j == 0 ? 0xfffffffeu : 0xffffffffu;                      // column -1 does not exist
+        const uint32_t vp1 = j == OCC_XW - 1 ? (last_mask >> 1) : 0xffffffffu;        // column 220 does not exist
+        const uint32_t vp2 = j == OCC_XW - 1 ? (last_mask >> 2) : 0xffffffffu;        // columns 220, 221 do not exist
+        all1 &= (w | ~vw) & (m1 | ~vm1) & (p1 | ~vp1) & (p2 | ~vp2);
+        any1 |= (w & vw) | (m1 & vm1) | (p1 & vp1) | (p2 & vp2);
       }
-      cls[t] = all_or == 0u ? 0 : (all_and == valid ? 1 : 2);
+      uint32_t e = any1 & ~all1;
+      if (j == OCC_XW - 1) e &= last_mask;
+      eb[t] = e;
     }
     __syncthreads();
-    for (int t = tid; t < OCC_NB * OCC_NB; t += OCC_THREADS) {
-      const int bi = t / OCC_NB, bj = t - bi * OCC_NB;
-      const uint8_t c = cls[t];
-      bool same = c != 2;
-      for (int di = -1; di <= 1 && same; ++di)
-        for (int dj = -1; dj <= 1; ++dj) {
-          const int i = bi + di, j = bj + dj;
-          if (i < 0 || i >= OCC_NB || j < 0 || j >= OCC_NB) continue;   // beyond the crop the prefilter mirrors the block itself
-          if (cls[i * OCC_NB + j] != c) same = false;
+    // ---- A": tile classes (see the header).  One lane per tile; uniform / outside tiles get their plane bytes here,
+    // mixed tiles are appended to tlist (order irrelevant). ----
+    {
+      uint8_t* plane0 = reinterpret_cast<uint8_t*>(planes);
+      uint8_t* plane1 = plane0 + RD_OCC_MID * RD_OCC_MID / 8;
+      for (int base = 0; base < OCC_N_TILES; base += OCC_THREADS) {
+        const int t = base + tid;
+        int cls_t = 2;
+        const int ty = t / (RD_OCC_MID / 8), tx = t - ty * (RD_OCC_MID / 8);
+        if (t < OCC_N_TILES) {
+          const int a0 = 4 * ty, b0 = 8 * tx;
+          double lo0, hi0, lo1, hi1;
+          {
+            double p0, p1, q0, q1, r0, r1, s0, s1;
+            occ_coords(rc, geom, a0, b0, p0, p1);
+            occ_coords(rc, geom, a0, b0 + 7, q0, q1);
+            occ_coords(rc, geom, a0 + 3, b0, r0, r1);
+            occ_coords(rc, geom, a0 + 3, b0 + 7, s0, s1);
+            lo0 = fmin(fmin(p0, q0), fmin(r0, s0)); hi0 = fmax(fmax(p0, q0), fmax(r0, s0));
+            lo1 = fmin(fmin(p1, q1), fmin(r1, s1)); hi1 = fmax(fmax(p1, q1), fmax(r1, s1));
+          }
+          const double top = (double)(RD_OCC_IN - 1);
+          if (hi0 < 0.0 || lo0 > top || hi1 < 0.0 || lo1 > top) {
+            cls_t = 0;                                             // every pixel outside the crop: 0
+          } else if (lo0 >= 0.0 && hi0 <= top && lo1 >= 0.0 && hi1 <= top) {
+            // every pixel of the tile has its floor coordinates in [r0, r1] x [q0, q1] (<= 9 x 9 cells): no near-edge bit
+            // there means every pixel is the crop bit of its own cell, and those cells are all equal
+            const int r0 = (int)floor(lo0), r1 = (int)floor(hi0), q0 = (int)floor(lo1), q1 = (int)floor(hi1);
+            const uint32_t cmask = (q1 - q0 + 1 >= 32) ? 0xffffffffu : ((1u << (q1 - q0 + 1)) - 1u);
+            const int wj = q0 >> 5, sh = q0 & 31;
+            uint32_t any_e = 0u;
+            for (int r = r0; r <= r1; ++r) {
+              const uint32_t* row = eb + r * OCC_XW;
+              any_e |= __funnelshift_r(row[wj], wj + 1 < OCC_XW ? row[wj + 1] : 0u, sh) & cmask;
+            }
+            if (!any_e) cls_t = (int)((xb[r0 * OCC_XW + wj] >> sh) & 1u);
+          }
+          if (cls_t != 2) {
+            const uint8_t v = cls_t ? 0xFF : 0x00;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const int byte = ((a0 + r) * RD_OCC_MID + b0) >> 3;
+              plane0[byte] = v;
+              plane1[byte] = 0;
+            }
+          }
         }
-      uni[t] = same ? c : 2;
+        const uint32_t mixed = __ballot_sync(0xffffffffu, cls_t == 2 && t < OCC_N_TILES);
+        int pos = 0;
+        if (lane == 0 && mixed) pos = atomicAdd(&n_mixed, __popc(mixed));
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (cls_t == 2 && t < OCC_N_TILES) tlist[pos + __popc(mixed & ((1u << lane) - 1u))] = (uint16_t)((ty << 8) | tx);   // ty < 50, tx < 25
+      }
     }
     // ---- B: prefilter, axis 0 (columns) then axis 1 (rows), float32; image stored at padded index (r+1, c+1) ----
     __syncthreads();
-    occ_prefilter_axis<true>(coef + OCC_PITCH + 1, 1, OCC_PITCH, xb);       // axis 0: line = column
-    occ_prefilter_axis<false>(coef + OCC_PITCH + 1, OCC_PITCH, 1, nullptr);  // axis 1: line = row
+    occ_prefilter_axis<true, OCC_PITCH, 1>(coef + OCC_PITCH + 1, xb);        // lines = crop rows, from the bits
+    occ_prefilter_axis<false, 1, OCC_PITCH>(coef + OCC_PITCH + 1, nullptr);  // lines = columns, in place
     // mirrored border: columns -1, 220, 221 of rows 0..219, then rows -1, 220, 221 of all 223 columns
     for (int t = tid; t < RD_OCC_IN * 3; t += OCC_THREADS) {
       const int r = t / 3, k = t - r * 3;
@@ -378,26 +464,27 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
 
     // ---- C: rotation.  One pixel per thread and round; a warp owns an 8-wide x 4-high tile of the mid image ----
     const int n_pix = RD_OCC_MID * RD_OCC_MID;
-    const int n_tiles = n_pix / 32;                                  // 50 x 25 tiles
     const int warps = OCC_THREADS / 32;
-    const int n_rounds = (n_tiles + warps - 1) / warps;
     uint8_t* plane0 = reinterpret_cast<uint8_t*>(planes);
     uint8_t* plane1 = plane0 + n_pix / 8;
-    for (int round = 0; round < n_rounds; ++round) {
-      const int tile = round * warps + (tid >> 5);
-      const int ty = tile / (RD_OCC_MID / 8), tx = tile - ty * (RD_OCC_MID / 8);
-      if (ty < RD_OCC_MID / 4) {
+    const int n_list = n_mixed;
+    uint32_t hi_acc = 0u;
+    for (int k = tid >> 5; k < n_list; k += warps) {              // the mixed tiles only
+      const int tile = tlist[k];
+      const int ty = tile >> 8, tx = tile & 255;
+      {
         const int a = ty * 4 + (lane >> 3), b = tx * 8 + (lane & 7);
         double c0, c1;
-        occ_coords(rc, a, b, c0, c1);
+        occ_coords(rc, geom, a, b, c0, c1);
         uint32_t val = 0u;
         bool ambiguous = false;
         const bool inside = !(c0 < 0.0 || c0 > (double)(RD_OCC_IN - 1) || c1 < 0.0 || c1 > (double)(RD_OCC_IN - 1));
         const double f0 = floor(c0), f1 = floor(c1);
         const int i0 = inside ? (int)f0 : 0, i1 = inside ? (int)f1 : 0;
-        const uint32_t u = inside ? (uint32_t)uni[(i0 >> 3) * OCC_NB + (i1 >> 3)] : 0u;
-        if (u != 2u) {
-          val = u;                                                   // constant neighbourhood (or outside the crop: 0)
+        const int wpos = i0 * OCC_XW + (i1 >> 5);
+        const bool near_edge = inside && ((eb[wpos] >> (i1 & 31)) & 1u);
+        if (!near_edge) {
+          val = inside ? ((xb[wpos] >> (i1 & 31)) & 1u) : 0u;        // constant 4x4 neighbourhood (or outside the crop: 0)
         } else {
           const float y0 = (float)(c0 - f0), y1 = (float)(c1 - f1);
           const float z0 = 1.0f - y0, z1 = 1.0f - y1;
@@ -433,7 +520,7 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
         // float64 re-evaluation of the (rare) ambiguous pixels, one after the other, by the whole warp
         for (uint32_t todo = __ballot_sync(0xffffffffu, ambiguous); todo; todo &= todo - 1u) {
           const int src = __ffs(todo) - 1;
-          const uint32_t exact = occ_exact_pixel(rc, __shfl_sync(0xffffffffu, a, src), __shfl_sync(0xffffffffu, b, src), xb, hband);
+          const uint32_t exact = occ_exact_pixel(rc, geom, __shfl_sync(0xffffffffu, a, src), __shfl_sync(0xffffffffu, b, src), xb, hband);
           if (lane == src) val = exact > 3u ? 3u : exact;
         }
         // tile row i (8 pixels) is one byte of the row-major bit planes
@@ -443,9 +530,10 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
           plane0[byte] = (uint8_t)(b0 >> (lane & 24));
           plane1[byte] = (uint8_t)(b1 >> (lane & 24));
         }
-        if (lane == 0 && b1) any_hi = 1;
+        hi_acc |= b1;
       }
     }
+    if (hi_acc && lane == 0) any_hi = 1;
     __syncthreads();
 
     // ---- D: Pillow bicubic 200 -> 64.  The coefficient image is dead: its space takes the tables and the uint8
@@ -476,14 +564,26 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
       }
     }
     __syncthreads();
-    for (int i = tid; i < RD_OCC_OUT * RD_OCC_OUT; i += OCC_THREADS) {
-      const int yy = i / RD_OCC_OUT, xx = i - yy * RD_OCC_OUT;
-      int32_t ss = 1 << (OCC_PREC_BITS - 1);
+    // vertical pass: four adjacent output pixels per thread (one 32-bit read of the uint8 intermediate per tap, one
+    // 32-bit store of the result)
+    for (int i = tid; i < RD_OCC_OUT * RD_OCC_OUT / 4; i += OCC_THREADS) {
+      const int yy = i / (RD_OCC_OUT / 4), x4 = i - yy * (RD_OCC_OUT / 4);
+      int32_t s0 = 1 << (OCC_PREC_BITS - 1), s1 = s0, s2 = s0, s3 = s0;
       const int y0 = tb->xmin[yy], yn = tb->xnum[yy];
       const int32_t* k = tb->kk + yy * OCC_KSIZE;
-      for (int t = 0; t < yn; ++t) ss += (int32_t)tmp[(y0 + t) * RD_OCC_OUT + xx] * k[t];
-      ss >>= OCC_PREC_BITS;
-      dst[i] = (uint8_t)(ss < 0 ? 0 : (ss > 255 ? 255 : ss));
+      const uint32_t* col = reinterpret_cast<const uint32_t*>(tmp) + y0 * (RD_OCC_OUT / 4) + x4;
+      for (int t = 0; t < yn; ++t) {
+        const uint32_t w = col[t * (RD_OCC_OUT / 4)];
+        const int32_t kt = k[t];
+        s0 += (int32_t)(w & 255u) * kt;
+        s1 += (int32_t)((w >> 8) & 255u) * kt;
+        s2 += (int32_t)((w >> 16) & 255u) * kt;
+        s3 += (int32_t)(w >> 24) * kt;
+      }
+      s0 >>= OCC_PREC_BITS; s1 >>= OCC_PREC_BITS; s2 >>= OCC_PREC_BITS; s3 >>= OCC_PREC_BITS;
+      const uint32_t b0 = (uint32_t)(s0 < 0 ? 0 : (s0 > 255 ? 255 : s0)), b1 = (uint32_t)(s1 < 0 ? 0 : (s1 > 255 ? 255 : s1));
+      const uint32_t b2 = (uint32_t)(s2 < 0 ? 0 : (s2 > 255 ? 255 : s2)), b3 = (uint32_t)(s3 < 0 ? 0 : (s3 > 255 ? 255 : s3));
+      reinterpret_cast<uint32_t*>(dst)[i] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
     }
   }
 }

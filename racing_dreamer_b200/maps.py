@@ -174,7 +174,7 @@ def _read_gray(image_path: Path) -> np.ndarray:
     return rgb @ np.array([0.2125, 0.7154, 0.0721])
 
 
-def _wavefront(free: np.ndarray, seed_rc) -> np.ndarray:
+def _wavefront(free: np.ndarray, seed_rc, max_dist: Optional[int] = None) -> np.ndarray:
     """8-neighbour (Chebyshev) wavefront distance from the seed over ``free`` cells
     [REF generate-costmap.py:198-209: repeated 3x3 dilation, new pixels get the current distance].
     Returns int32 distances, -1 where unreached."""
@@ -185,7 +185,7 @@ def _wavefront(free: np.ndarray, seed_rc) -> np.ndarray:
     fc = np.array([seed_rc[1]], dtype=np.int64)
     d = 0
     offs = [(-1, -1), (-1, 0), (-1, 1), (0, -1), (0, 1), (1, -1), (1, 0), (1, 1)]
-    while fr.size:
+    while fr.size and (max_dist is None or d < max_dist):
         d += 1
         nr = np.concatenate([fr + a for a, _ in offs])
         nc = np.concatenate([fc + b for _, b in offs])
@@ -274,6 +274,88 @@ def compile_track(yaml_path: os.PathLike, name: Optional[str] = None, start_xy=(
     tm.start_poses = _grid_poses(tm, start_xy)
     tm.reset_poses = _random_reset_poses(tm, reset_clearance_m, max_reset_poses)
     return tm
+
+
+# The generator's per-map switch for the smoothing terms [REF generate-costmap.py:84-111]: maps with custom settings that
+# turn `use_blurred_factor` off keep the plain wavefront distance; every other map adds the two blurred fields.
+_NO_BLUR_MAPS = ("f1_aut", "columbia_small")
+
+
+def compile_distance_to_target(yaml_path: os.PathLike, start_xy=(0.0, 0.0), reference_quirks: bool = False,
+                               use_blurred_factor: Optional[bool] = None) -> Dict[str, np.ndarray]:
+    """The fourth layer of the reference's costmap files, ``norm_distance_to`` = normalised SMOOTHED distance to the
+    target (the finish line approached in driving direction) [REF docs/maps/costmaps/generate-costmap.py:227-276
+    compute_distance_transform_smoothed(forward_direction=False), saved at :405-420], full image size, float64.
+    SURVEY.md §8-f4.  No env-path function reads it (the env uses the forward progress map); it completes the map
+    compiler's output for tools that load the reference's ``maps.npz`` keys.  Returns ``{'drivable_area',
+    'norm_distance_to'}``.  The race-line image the generator also draws [REF :280-360] is exported as PNG only, never
+    stored, and is not built.
+
+    Restated steps: backward wavefront (the finish line is blocked one column AFTER the start [REF :160]); 'start' /
+    'target' areas = cells within 100 (small: 50) wavefront steps of the pixels two columns ahead of / behind the start
+    [REF :165-192]; two rounds of 'extend beyond the track by a 10-px maximum filter, blank the far side of the finish
+    line, Gaussian sigma 3, recombine' and one Gaussian sigma 5 of the distance padded with its maximum [REF :236-262];
+    distance + 0.08 blurred + 0.06 border-blurred when the map's `use_blurred_factor` is on [REF :270-271]."""
+    import yaml
+    from scipy import ndimage
+
+    yaml_path = Path(yaml_path)
+    with open(yaml_path) as f:
+        props = yaml.safe_load(f)
+    res = float(props["resolution"])
+    ox, oy = float(props["origin"][0]), float(props["origin"][1])
+    gray = _read_gray(yaml_path.parent / props["image"])
+    H, W = gray.shape
+    binary = (gray / np.amax(gray)) > float(props["occupied_thresh"])
+    if reference_quirks and H > REFERENCE_CLEARED_PIXEL[0] and W > REFERENCE_CLEARED_PIXEL[1]:
+        binary[REFERENCE_CLEARED_PIXEL] = False
+    if use_blurred_factor is None:
+        use_blurred_factor = yaml_path.stem not in _NO_BLUR_MAPS
+    gx = int((start_xy[0] - ox) / res)
+    gy = int(H - (start_xy[1] - oy) / res - 1)
+
+    free = binary.copy()
+    finish = np.zeros_like(free)
+    for r, step in ((gy, 1), (gy - 1, -1)):          # backward direction: the column one AHEAD of the start
+        while free[r, gx + 1]:
+            free[r, gx + 1] = False
+            finish[r, gx + 1] = True
+            r += step
+
+    def area(seed, steps):                           # the seed pixel itself + free cells within `steps` wavefront steps
+        d = _wavefront(free, seed, max_dist=steps)
+        return d >= 0
+
+    start_big = area((gy, gx + 2), 100) ^ finish
+    start_small = area((gy, gx + 2), 50) ^ finish
+    target_big = area((gy, gx - 2), 100)
+
+    d = _wavefront(free, (gy, gx))
+    reached = d >= 0
+    top = float(int(d.max()) + 1)                    # loop-exit value of the generator's counter
+    dist = np.where(reached, d, 0).astype(np.float64)
+    dist[finish] = top
+    drivable = reached | finish
+    drv = drivable.astype(np.float64)
+    tgt, st_s, st_b = target_big.astype(np.float64), start_small.astype(np.float64), start_big.astype(np.float64)
+
+    def split_blur(field, sigma):
+        """Gaussian of `field` computed twice -- once with the target side of the finish line blanked to the maximum, once
+        with the start side blanked to zero -- so that values do not leak across the line; recombined by side."""
+        a = top * tgt + field * (1.0 - tgt)
+        b = 0.0 * st_s + field * (1.0 - st_s)
+        ga = ndimage.gaussian_filter(a, sigma=sigma) * drv
+        gb = ndimage.gaussian_filter(b, sigma=sigma) * drv
+        return ga * st_b + gb * (1.0 - st_b)
+
+    blurred = dist
+    for _ in range(2):
+        extended = blurred * drv + ndimage.maximum_filter(blurred, size=10) * (1.0 - drv)
+        blurred = split_blur(extended, 3)
+    border = split_blur(dist * drv + top * (1.0 - drv), 5)
+    out = dist + blurred * 0.08 + border * 0.06 if use_blurred_factor else dist
+    out = out * res
+    return {"drivable_area": drivable, "norm_distance_to": out / np.amax(out)}
 
 
 def _heading_field(tm: TrackMap, rows: np.ndarray, cols: np.ndarray, k: int = 6) -> np.ndarray:
