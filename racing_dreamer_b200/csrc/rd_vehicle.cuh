@@ -225,12 +225,17 @@ RDV_HD VehCmd rdv_command(const VehConst& k, const double (&q)[7], double motor,
 
 RDV_NOINLINE void rdv_acc_set_slow(const VehConst* k, double ac, VehAcc* out) { *out = rdv_acc_set(*k, ac); }
 
-// dq/dt at state t (x, y, steer, v, yaw, yaw_rate, slip).  `off` = the coefficient set for ac = 0 (per handle).
+// dq/dt at state t (x, y, steer, v, yaw, yaw_rate, slip), split in two: the position (x, y) enters no derivative, so the
+// recurrence between the RK4 stages runs over (steer, v, yaw, yaw_rate, slip) only.  rdv_rhs_core returns those five
+// derivatives plus the heading `ang` of the velocity vector; the position derivative (v cos ang, v sin ang) -- the one
+// sine / cosine pair both regimes need -- is formed afterwards (rdv_tick_t), off the dependency chain between stages.
+// `off` = the coefficient set for ac = 0 (per handle).
 // FAST: the caller has checked, for the whole tick, that the angles stay where the short trigonometric paths are valid
-// (|heading| < 9e4 rad, |steer| < 0.7 rad) and that the vehicle cannot reach v_switch; then the RHS has no range guards
+// (|heading| < 9e4 rad, |steer| < 0.7 rad) and that the vehicle cannot reach v_switch; then there are no range guards
 // and no power-limit branch.  Same arithmetic either way.
 template <bool FAST>
-RDV_HD void rdv_rhs(const VehConst& k, const VehCmd& c, const VehAcc& off, const double (&t)[7], double (&f)[7]) {
+RDV_HD void rdv_rhs_core(const VehConst& k, const VehCmd& c, const VehAcc& off, const double (&t)[7], double (&f)[7],
+                         double& ang) {
   const double steer = t[2], v = t[3], yaw = t[4], yr = t[5], slip = t[6];
   const bool s_blocked = (steer <= k.steer_min && c.sv_neg) || (steer >= k.steer_max && c.sv_pos);
   const double svc = s_blocked ? 0.0 : c.sv_clip;
@@ -245,13 +250,7 @@ RDV_HD void rdv_rhs(const VehConst& k, const VehCmd& c, const VehAcc& off, const
     }
   }
   const bool kin = fabs(v) < k.v_kin;
-  const double ang = kin ? yaw : (slip + yaw);
-  double sn, cn;
-  if (FAST) rdv_sincos_reduced(ang, sn, cn);
-  else if (fabs(ang) < 1.0e5) rdv_sincos_reduced(ang, sn, cn);
-  else rdv_sincos_slow(ang, &sn, &cn);
-  f[0] = v * cn;
-  f[1] = v * sn;
+  ang = kin ? yaw : (slip + yaw);
   f[2] = svc;
   f[3] = ac;
   if (kin) {
@@ -279,6 +278,21 @@ RDV_HD void rdv_rhs(const VehConst& k, const VehCmd& c, const VehAcc& off, const
     f[6] = fma(c2rv * s.Sf, steer, fma(-(c2rv * s.S3), slip, b_yr * yr));
   }
 }
+template <bool FAST> RDV_HD void rdv_heading(double ang, double& sn, double& cn);
+template <bool FAST>
+RDV_HD void rdv_rhs(const VehConst& k, const VehCmd& c, const VehAcc& off, const double (&t)[7], double (&f)[7]) {
+  double ang, sn, cn;
+  rdv_rhs_core<FAST>(k, c, off, t, f, ang);
+  rdv_heading<FAST>(ang, sn, cn);
+  f[0] = t[3] * cn;
+  f[1] = t[3] * sn;
+}
+template <bool FAST>
+RDV_HD void rdv_heading(double ang, double& sn, double& cn) {
+  if (FAST) rdv_sincos_reduced(ang, sn, cn);
+  else if (fabs(ang) < 1.0e5) rdv_sincos_reduced(ang, sn, cn);
+  else rdv_sincos_slow(ang, &sn, &cn);
+}
 
 // one 10 ms tick under the sim-facing command (motor, steering): classical RK4.
 // RD_TICK_ROLLED = 1: the four stages share ONE copy of the RHS code (stage input q + c*k with c = (0, h/2, h/2, h), sum
@@ -305,19 +319,36 @@ RDV_HD void rdv_tick_t(const VehConst& k, const VehAcc& off, double (&q)[7], dou
 #pragma unroll
   for (int i = 0; i < 7; ++i) q[i] = fma(k.h6, acc[i], q[i]);
 #else
-  double k1[7], kk[7], acc[7], t[7];
-  rdv_rhs<FAST>(k, c, off, q, k1);
+  // The five coupled derivatives first, stage after stage; the four headings and speeds they leave behind feed four
+  // INDEPENDENT sine / cosine evaluations afterwards (one straight-line block the scheduler can interleave) -- the
+  // position never feeds back, so the values are those of the textbook stage-by-stage form, bit for bit.
+  double kk[7], acc[7], t[7], ang[4], vs[4];
 #pragma unroll
-  for (int i = 0; i < 7; ++i) { t[i] = fma(k.h2, k1[i], q[i]); acc[i] = k1[i]; }
-  rdv_rhs<FAST>(k, c, off, t, kk);
+  for (int i = 0; i < 7; ++i) t[i] = q[i];
+  vs[0] = t[3];
+  rdv_rhs_core<FAST>(k, c, off, t, kk, ang[0]);
 #pragma unroll
-  for (int i = 0; i < 7; ++i) { t[i] = fma(k.h2, kk[i], q[i]); acc[i] = fma(2.0, kk[i], acc[i]); }
-  rdv_rhs<FAST>(k, c, off, t, kk);
+  for (int i = 2; i < 7; ++i) { t[i] = fma(k.h2, kk[i], q[i]); acc[i] = kk[i]; }
+  vs[1] = t[3];
+  rdv_rhs_core<FAST>(k, c, off, t, kk, ang[1]);
 #pragma unroll
-  for (int i = 0; i < 7; ++i) { t[i] = fma(k.dt, kk[i], q[i]); acc[i] = fma(2.0, kk[i], acc[i]); }
-  rdv_rhs<FAST>(k, c, off, t, kk);
+  for (int i = 2; i < 7; ++i) { t[i] = fma(k.h2, kk[i], q[i]); acc[i] = fma(2.0, kk[i], acc[i]); }
+  vs[2] = t[3];
+  rdv_rhs_core<FAST>(k, c, off, t, kk, ang[2]);
 #pragma unroll
-  for (int i = 0; i < 7; ++i) q[i] = fma(k.h6, acc[i] + kk[i], q[i]);
+  for (int i = 2; i < 7; ++i) { t[i] = fma(k.dt, kk[i], q[i]); acc[i] = fma(2.0, kk[i], acc[i]); }
+  vs[3] = t[3];
+  rdv_rhs_core<FAST>(k, c, off, t, kk, ang[3]);
+#pragma unroll
+  for (int i = 2; i < 7; ++i) q[i] = fma(k.h6, acc[i] + kk[i], q[i]);
+  double sn[4], cn[4];
+#pragma unroll
+  for (int st = 0; st < 4; ++st) rdv_heading<FAST>(ang[st], sn[st], cn[st]);
+  // x, y: k_s = v_s (cos, sin)(ang_s);  q += h/6 (((k1 + 2 k2) + 2 k3) + k4)
+  const double ax = fma(2.0, vs[2] * cn[2], fma(2.0, vs[1] * cn[1], vs[0] * cn[0]));
+  const double ay = fma(2.0, vs[2] * sn[2], fma(2.0, vs[1] * sn[1], vs[0] * sn[0]));
+  q[0] = fma(k.h6, ax + vs[3] * cn[3], q[0]);
+  q[1] = fma(k.h6, ay + vs[3] * sn[3], q[1]);
 #endif
 }
 // the general tick, out of line: any heading, any steering angle, vehicles that reach v_switch
