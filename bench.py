@@ -239,7 +239,7 @@ def cpu_baseline_of(wl, budget_s=1.5):
     threads = os.cpu_count() or 1
     rate, _ = cpu_oracle_run(wl, 256 if wl.obs == "lidar" else 2 * threads, 2, 1, threads)
     n_s = int(min(wl.envs, max(threads, rate * 1.0)))          # <= ~1 s per step
-    steps_s = int(min(200, max(3, budget_s * rate / n_s)))
+    steps_s = int(min(200, max(12 if wl.obs == "lidar" else 3, budget_s * rate / n_s)))
     v, dt = cpu_oracle_run(wl, n_s, steps_s, 1, threads)
     return {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
             "sample": f"{n_s} envs x {steps_s} steps of the same workload, oracle/rd_oracle.c, {threads} OpenMP threads, {dt:.1f} s"}

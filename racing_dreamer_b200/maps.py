@@ -332,9 +332,10 @@ def compile_distance_to_target(yaml_path: os.PathLike, start_xy=(0.0, 0.0), refe
 
     d = _wavefront(free, (gy, gx))
     reached = d >= 0
-    top = float(int(d.max()) + 1)                    # loop-exit value of the generator's counter
     dist = np.where(reached, d, 0).astype(np.float64)
-    dist[finish] = top
+    dist[finish] = float(int(d.max()) + 1)           # loop-exit value of the generator's counter
+    dist = dist * res                                # the generator's distance transform already returns metres [REF :221]
+    top = np.amax(dist)
     drivable = reached | finish
     drv = drivable.astype(np.float64)
     tgt, st_s, st_b = target_big.astype(np.float64), start_small.astype(np.float64), start_big.astype(np.float64)
@@ -354,7 +355,7 @@ def compile_distance_to_target(yaml_path: os.PathLike, start_xy=(0.0, 0.0), refe
         blurred = split_blur(extended, 3)
     border = split_blur(dist * drv + top * (1.0 - drv), 5)
     out = dist + blurred * 0.08 + border * 0.06 if use_blurred_factor else dist
-    out = out * res
+    out = out * res                                  # ... and the smoothed variant scales once more [REF :273]; it cancels below
     return {"drivable_area": drivable, "norm_distance_to": out / np.amax(out)}
 
 

@@ -391,6 +391,20 @@ def costmap_golden():
         out[f"{name}_edt_sq"] = tm.edt_sq
         out[f"{name}_start_px"] = np.asarray(ref["grid_starting_position"], np.int64)
         print(f"costmap_golden: {name} crop {tm.h}x{tm.w} dmax {tm.dmax} drivable {int(tm.drivable.sum())} px")
+    # the fourth stored layer, norm_distance_to (smoothed distance to the target) [REF generate-costmap.py:227-276,405-420]:
+    # the generator's full run() on Treitlstrasse (default settings: use_blurred_factor on).  Stored as the sha256 of the
+    # full float64 array (bit-exactness) plus the crop in float32 (diagnostics when the hash differs).
+    import hashlib
+    y = ref_stubs.REFERENCE_ROOT / "docs" / "maps" / "maps" / f"{TRACK_FILES['treitlstrasse_v2']}.yaml"
+    full = reference_layers(y, full_run=True, out_path="/tmp/ref_full_costmap.npz")
+    mine = maps.compile_distance_to_target(y, reference_quirks=True)
+    assert np.array_equal(full["drivable_area"], mine["drivable_area"])
+    assert np.array_equal(full["norm_distance_to"], mine["norm_distance_to"])
+    r0, c0, h, w = (int(v) for v in out["treitlstrasse_v2_r0c0hw"])
+    ndt = np.ascontiguousarray(full["norm_distance_to"], dtype=np.float64)
+    out["treitlstrasse_v2_norm_distance_to_sha256"] = np.array(hashlib.sha256(ndt.tobytes()).hexdigest())
+    out["treitlstrasse_v2_norm_distance_to_crop_f32"] = ndt[r0:r0 + h, c0:c0 + w].astype(np.float32)
+    print("costmap_golden: norm_distance_to max", float(ndt.max()), "nonzero", int((ndt > 0).sum()))
     np.savez_compressed(OUT / "costmap_golden.npz", **out)
 
 

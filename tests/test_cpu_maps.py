@@ -111,3 +111,23 @@ def test_compile_with_reference_quirks_reproduces_golden(golden_dir):
         tm = maps.compile_track(ref_stubs.REFERENCE_ROOT / "docs/maps/maps" / f"{TRACK_FILES[name]}.yaml", reference_quirks=True)
         assert (tm.r0, tm.c0, tm.h, tm.w, tm.dmax) == (r0, c0, h, w, dmax)
         assert np.array_equal(tm.drivable, drv) and np.array_equal(tm.dist, dist) and np.array_equal(tm.edt_sq, edt)
+
+
+@pytest.mark.skipif(not ref_stubs.available(), reason="/root/reference not present (GPU box)")
+def test_distance_to_target_layer_reproduces_generator(golden_dir):
+    """§8-f4: the generator's fourth stored layer, `norm_distance_to` (smoothed distance to the target)
+    [REF docs/maps/costmaps/generate-costmap.py:227-276,405-420], restated in maps.compile_distance_to_target; the fixture
+    is the unmodified script's full run() on Treitlstrasse_3-U_v2 (tests/golden/make_golden.py::costmap_golden)."""
+    import hashlib
+    g = np.load(golden_dir / "costmap_golden.npz")
+    out = maps.compile_distance_to_target(ref_stubs.REFERENCE_ROOT / "docs/maps/maps/Treitlstrasse_3-U_v2.yaml", reference_quirks=True)
+    ndt = np.ascontiguousarray(out["norm_distance_to"], dtype=np.float64)
+    r0, c0, h, w = (int(v) for v in g["treitlstrasse_v2_r0c0hw"])
+    assert np.abs(ndt[r0:r0 + h, c0:c0 + w].astype(np.float32) - g["treitlstrasse_v2_norm_distance_to_crop_f32"]).max() == 0.0
+    assert hashlib.sha256(ndt.tobytes()).hexdigest() == str(g["treitlstrasse_v2_norm_distance_to_sha256"])
+    assert ndt.max() == 1.0 and (ndt[~out["drivable_area"]] == 0).all()
+    # maps with custom generator settings keep the plain wavefront distance (use_blurred_factor off) [REF :94-105]
+    plain = maps.compile_distance_to_target(ref_stubs.REFERENCE_ROOT / "docs/maps/maps/f1_aut.yaml")
+    d = plain["norm_distance_to"][plain["drivable_area"]]
+    steps = np.unique(np.round(d * d.size))          # a pure wavefront distance takes few distinct values per cell count
+    assert len(np.unique(d)) <= 2000 and steps.size > 10

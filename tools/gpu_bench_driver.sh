@@ -20,4 +20,4 @@ for k,v in (d.get('configs') or {}).items():
 print('cpu', d.get('cpu_baseline'))
 print('closed', {k:round(v['value']) for k,v in (d.get('closed_loop') or {}).items()}, 'multi', d['multi_agent'] and round(d['multi_agent']['value']))
 PY
-tail -3 $OUT/bench.err
+tail -3 $OUT/bench*.err 2>/dev/null | tail -3
