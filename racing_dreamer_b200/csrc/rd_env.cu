@@ -313,6 +313,10 @@ int launch_lidar_t(rd_env* env, int map_id, const OriginRec* recs, const int32_t
   }
   const long long items = (long long)n_env * lp.groups;
   if (items >= (1ll << 31)) return fail(env, RD_ERR_INVALID, "too many (env, beam group) items for one launch");
+  // rd_march keeps the ray position in 32-bit 2^-18 cells (rd_march.cuh)
+  if ((long long)std::max(m.w, m.h) + (lp.rsub >> RD_SUB_BITS) >= 8190)
+    return fail(env, RD_ERR_INVALID, "map %d (%d x %d cells) plus the LiDAR range (%lld cells) exceeds the ray march's 8190-cell span",
+                map_id, m.w, m.h, (long long)(lp.rsub >> RD_SUB_BITS));
   long long grid = std::min<long long>((items + WARPS - 1) / WARPS, (long long)env->sm_count * per_sm);
   if (grid < 1) return RD_OK;
   {

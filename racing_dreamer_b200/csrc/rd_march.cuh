@@ -57,30 +57,37 @@ RD_HD MarchResult rd_march(const MarchGrid& g, int px, int py, int DX, int DY, l
 
   // ---- phase 1: clearance jumps in the ray parameter U (whole cells) ----
   const int ulim = (int)(rsub >> RD_SUB_BITS);
-  // crossing counts at parameter U: i(U) = #{m >= 0 : bx + m*4096 <= X} with X = floor(U*adx / 64).  Since 0 <= bx <= 4096
-  // and X >= 0, that is (X + 4096 - bx) >> 12 with no case split (for X < bx the sum stays in [0, 4095]); an axis the
-  // ray does not move along (adx == 0 -> X == 0) gets the offset 0 and therefore the count 0.
-  const int cxj = adx != 0 ? RD_SUB - bx : 0;
-  const int cyj = ady != 0 ? RD_SUB - by : 0;
-  // crossing counts at U = 0: 1 when the origin lies exactly on the cell edge it is about to cross (b == 0), so that
-  // (i, j) == (i(U), j(U)) holds from the start and a jump of D-1 never moves the cell index by more than D-1
+  // Cell reached at parameter U.  The crossing counts have the closed form i(U) = #{m >= 0 : bx + m*4096 <= X} with
+  // X = floor(U*adx / 64), i.e. a crossing counts as soon as the ray REACHES the edge.  In 2^-18 cells that is one
+  // multiply-add and one arithmetic shift per axis:
+  //     ix(U) = (px*64 - [DX < 0] + U*DX) >> 18
+  // DX > 0: ix0 + ((fx*64 + U*adx) >> 18) = ix0 + ((fx + X) >> 12) = ix0 + i(U) (bx = 4096 - fx).
+  // DX < 0: with T = U*adx = 64*X + t (0 <= t < 64), floor((fx*64 - 1 - T) / 64) = fx - X - 1, so the shift gives
+  //         ix0 + floor((fx - X - 1) / 4096) = ix0 - (floor((X - fx) / 4096) + 1) = ix0 - ((X + 4096 - fx) >> 12)
+  //         = ix0 - i(U) (bx = fx); the "- 1" is what makes reaching the edge count (an origin exactly on the edge
+  //         it is about to cross, fx == 0, is already in the next cell at U = 0, as the counts say).
+  // DX == 0: the cell index never moves.
+  // 32-bit: px*64 < w * 2^18 and |U*DX| <= ulim * 2^18, so max(w, h) + ulim < 8192 is required (checked at launch).
+  // The clearance lookup needs only the block indices, (pos >> 18) >> cshift == pos >> (18 + cshift).
+  const int PX0 = (int)((unsigned)px << (RD_DIR_BITS - RD_SUB_BITS)) - (DX < 0 ? 1 : 0);
+  const int PY0 = (int)((unsigned)py << (RD_DIR_BITS - RD_SUB_BITS)) - (DY < 0 ? 1 : 0);
+  const int bsh = RD_DIR_BITS + g.cshift;
   int U = 0, njump = 0;
-  int i = cxj >> RD_SUB_BITS, j = cyj >> RD_SUB_BITS;
-  int ix = ix0 + sx * i, iy = iy0 + sy * j;
   for (;;) {
-    const int D = g.coarse[(iy >> g.cshift) * g.cw + (ix >> g.cshift)];
+    const int D = g.coarse[((PY0 + U * DY) >> bsh) * g.cw + ((PX0 + U * DX) >> bsh)];
     const int Un = U + D - 1;
     if (D < 2 || Un > ulim) break;
     U = Un;
-    const int X = (int)(((unsigned)U * (unsigned)adx) >> 6);  // U <= 2^13, adx <= 2^18: fits
-    const int Y = (int)(((unsigned)U * (unsigned)ady) >> 6);
-    i = (X + cxj) >> RD_SUB_BITS;
-    j = (Y + cyj) >> RD_SUB_BITS;
-    ix = ix0 + sx * i;
-    iy = iy0 + sy * j;
     ++njump;
   }
-  if (U == 0) { i = 0; j = 0; ix = ix0; iy = iy0; }  // no jump taken: only the origin cell is known to be drivable
+  // crossing counts (i, j) and cell at the parameter reached; no jump taken: only the origin cell is known to be drivable
+  int ix = ix0, iy = iy0, i = 0, j = 0;
+  if (U != 0) {
+    ix = (PX0 + U * DX) >> RD_DIR_BITS;
+    iy = (PY0 + U * DY) >> RD_DIR_BITS;
+    i = DX > 0 ? ix - ix0 : ix0 - ix;
+    j = DY > 0 ? iy - iy0 : iy0 - iy;
+  }
 
   // ---- phase 2: exact DDA from crossing counts (i, j) ----
   int n = n0 - (i + j);
@@ -91,19 +98,25 @@ RD_HD MarchResult rd_march(const MarchGrid& g, int px, int py, int DX, int DY, l
   const int rowbits = g.rw * 32;
   const int stepa_y = DY > 0 ? rowbits : -rowbits;
   int a = iy * rowbits + ix;  // bit address
-  bool hit = false, lastx = false;
   int xs = i;  // x-crossings taken so far
   const int n2 = n;
+  // The error update of a step is applied at the head of the NEXT one, so that after the loop the sign of e still tells
+  // through which side the last cell was entered; one loop exit (free cell AND crossings left) keeps the loop free of
+  // copies for the code behind it.
+  int de = 0;
+  uint32_t free_cell = 1u;
 #pragma unroll 1  // unrolling by 2 measured slower on B200 (more divergent tail code)
-  while (n > 0) {
-    lastx = e < 0;
-    e += lastx ? ex : -ey;
-    a += lastx ? sx : stepa_y;
-    xs += lastx ? 1 : 0;
-    const uint32_t word = g.bits[a >> 5];
+  while (n > 0 && free_cell) {
+    e += de;
+    const bool stepx = e < 0;
+    de = stepx ? ex : -ey;
+    a += stepx ? sx : stepa_y;
+    xs += stepx ? 1 : 0;
+    free_cell = g.bits[a >> 5] & (1u << (a & 31));
     --n;
-    if (!((word >> (a & 31)) & 1u)) { hit = true; break; }
   }
+  const bool hit = !free_cell;
+  const bool lastx = e < 0;
   if (steps) *steps = (njump << 16) | (n2 - n);
   MarchResult r;
   r.hit = hit ? 1 : 0;
