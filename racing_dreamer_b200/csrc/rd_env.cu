@@ -39,7 +39,7 @@ struct HostMap {
   void* d_next = nullptr;
   size_t hot_bytes = 0;    // bytes of the d_bits allocation (bits + clearance + distance): the L2-persisting window
   bool present = false;
-  int lidar_per_sm[8] = {-1, -1, -1, -1, -1, -1, -1, -1};   // resident k_lidar CTAs per SM for this map, per kernel
+  int lidar_per_sm[12] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};   // resident k_lidar CTAs per SM for this map, per kernel
                                                             // instantiation (cached launch configuration)
 };
 
@@ -50,10 +50,11 @@ struct rd_env {
   int device = 0;
   int sm_count = 0;
   int smem_optin = 0;             // max dynamic shared memory per CTA (opt-in), bytes
+  int smem_per_sm = 0;            // shared memory per SM, bytes
   size_t l2_window_max = 0;       // > 0: L2 persistence is set up; the largest access-policy window the device takes
   bool lidar_centre_first = true; // k_lidar work order (RD_LIDAR_ORDER=0: env-major)
   bool lidar_pdl = true;          // k_lidar is launched as a programmatic dependent of the kernel in front of it (RD_LIDAR_PDL=0: off)
-  bool lidar_attr_set[8] = {};    // k_lidar<16|32, ahead, cars> opted in to smem_optin
+  bool lidar_attr_set[12] = {};   // k_lidar<16|24|32, ahead, cars> opted in to smem_optin
   int n = 0;
   int step_block = 128;           // k_step threads per CTA (small batches: fewer, so that every SM gets a warp)
   double2* d_f2 = nullptr;        // env state, SoA of 16-byte groups (rd_dynamics.cuh StateRef)
@@ -297,7 +298,7 @@ int launch_lidar_t(rd_env* env, int map_id, const OriginRec* recs, const int32_t
   auto kern = k_lidar<WARPS, AHEAD, CARS>;
   // which instantiation runs depends on the map (warps), the handle (cars) AND the launch size (draw-ahead), so both
   // the opt-in to the device's shared-memory maximum and the cached occupancy are kept per instantiation
-  const int variant = (WARPS == 32 ? 1 : 0) + (AHEAD ? 2 : 0) + (CARS ? 4 : 0);
+  const int variant = (WARPS == 32 ? 2 : (WARPS == 24 ? 1 : 0)) + (AHEAD ? 3 : 0) + (CARS ? 6 : 0);
   bool& attr = env->lidar_attr_set[variant];
   if (!attr) {
     CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_optin));
@@ -342,23 +343,28 @@ int launch_lidar(rd_env* env, int map_id, const OriginRec* recs, const int32_t* 
                  cudaStream_t s, unsigned int* ctr = nullptr) {
   const DevMap& m = env->maps[map_id].dev;
   if (!ctr) ctr = env->d_lidar_ctr + 2 * (env->lidar_ctr_next++ % RD_CTR_RING);
-  // small maps: 16-warp CTAs (several per SM); large maps: 32-warp CTAs so one resident copy feeds 32 warps.
+  // 48 resident warps per SM wherever the shared-memory copies of the map allow it (the kernel is capped at 40
+  // registers for that): three 16-warp CTAs for small maps, two 24-warp CTAs for maps of which two copies fit, one
+  // 32-warp CTA otherwise.  RD_LIDAR_WARPS=16|24|32 overrides (tuning).
   // Long launches (>= 128 work items per resident warp) draw their work one chunk ahead (see k_lidar).
-  const int warps = m.bits_bytes > 72 * 1024 ? 32 : 16;
+  const size_t smem1 = 16 + (((size_t)2 * env->cfg.n_beams * 8 + 15) & ~(size_t)15) + (size_t)m.bits_bytes + 1024;   // + the per-CTA reserve
+  const size_t sm_total = (size_t)env->smem_per_sm;
+  int warps = 3 * smem1 <= sm_total ? 16 : (2 * smem1 <= sm_total ? 24 : 32);
+  if (const char* ev = std::getenv("RD_LIDAR_WARPS")) { const int w = std::atoi(ev); if (w == 16 || w == 24 || w == 32) warps = w; }
   int per_sm = 1;   // resident CTAs per SM as far as already known (any instantiation of this map: they differ by at most one)
-  for (int v = 0; v < 8; ++v) per_sm = std::max(per_sm, env->maps[map_id].lidar_per_sm[v]);
+  for (int v = 0; v < 12; ++v) per_sm = std::max(per_sm, env->maps[map_id].lidar_per_sm[v]);
   const long long items = (long long)n_env * ((env->cfg.n_beams + 31) / 32);
   bool ahead = items >= 128ll * env->sm_count * per_sm * warps;
   if (const char* ev = std::getenv("RD_LIDAR_AHEAD")) ahead = std::atoi(ev) != 0;
   const bool cars = env->cfg.agents_per_world > 1;   // worlds: the scans also see the other cars (own instantiation, so
                                                       // that the single-car kernel keeps its register budget)
 #define RD_LIDAR_GO(W, A, C) launch_lidar_t<W, A, C>(env, map_id, recs, order, n_env, out, s, ctr)
-  if (warps == 32) {
-    if (cars) return ahead ? RD_LIDAR_GO(32, true, true) : RD_LIDAR_GO(32, false, true);
-    return ahead ? RD_LIDAR_GO(32, true, false) : RD_LIDAR_GO(32, false, false);
-  }
-  if (cars) return ahead ? RD_LIDAR_GO(16, true, true) : RD_LIDAR_GO(16, false, true);
-  return ahead ? RD_LIDAR_GO(16, true, false) : RD_LIDAR_GO(16, false, false);
+#define RD_LIDAR_GO_W(W) (cars ? (ahead ? RD_LIDAR_GO(W, true, true) : RD_LIDAR_GO(W, false, true)) \
+                               : (ahead ? RD_LIDAR_GO(W, true, false) : RD_LIDAR_GO(W, false, false)))
+  if (warps == 32) return RD_LIDAR_GO_W(32);
+  if (warps == 24) return RD_LIDAR_GO_W(24);
+  return RD_LIDAR_GO_W(16);
+#undef RD_LIDAR_GO_W
 #undef RD_LIDAR_GO
 }
 
@@ -537,6 +543,7 @@ RD_API int rd_create(const rd_config* cfg, rd_env** out) {
   env->device = dev;
   env->sm_count = prop.multiProcessorCount;
   env->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  env->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
   env->n = cfg->n_envs;
   env->order_offset.assign(RD_MAX_MAPS + 1, 0);
   // L2 residency of the tracks (launch_attrs): set aside a slice of L2 for persisting lines, once per device; the

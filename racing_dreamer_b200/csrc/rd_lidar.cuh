@@ -83,7 +83,7 @@ __device__ __forceinline__ float rd_car_hit(const LidarParams& lp, int px, int p
 // The tail of the item list is handed out through a global counter (ctr[0]); the last CTA to finish (ticket ctr[1])
 // re-arms both for the next launch on the stream.
 template <int WARPS, bool AHEAD, bool CARS>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, CARS ? (WARPS == 16 ? 2 : 1) : (WARPS == 32 ? 1 : (WARPS == 24 ? 2 : 3)))
 k_lidar(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict__ recs,
         const int32_t* __restrict__ env_order, int n_env, LidarParams lp, const double* __restrict__ beam_tab,
         float* __restrict__ out, unsigned int* __restrict__ ctr) {

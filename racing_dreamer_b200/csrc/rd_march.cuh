@@ -28,6 +28,14 @@
 #define RD_DIR_BITS 18
 #endif
 
+RD_HD uint32_t rd_mulhi_u32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((unsigned long long)a * b) >> 32);
+#endif
+}
+
 struct MarchGrid {
   const uint32_t* bits;   // rows of rw words, bit = drivable (shared memory in the kernel)
   const uint8_t* coarse;  // [ch][cw] block clearance
@@ -49,9 +57,20 @@ RD_HD MarchResult rd_march(const MarchGrid& g, int px, int py, int DX, int DY, l
   const int fx = px & (RD_SUB - 1), fy = py & (RD_SUB - 1);
   const int bx = DX > 0 ? RD_SUB - fx : fx;
   const int by = DY > 0 ? RD_SUB - fy : fy;
-  const long long lx = (rsub * adx) >> RD_DIR_BITS, ly = (rsub * ady) >> RD_DIR_BITS;
-  const int nx = (adx != 0 && lx >= bx) ? (int)((lx - bx) >> RD_SUB_BITS) + 1 : 0;
-  const int ny = (ady != 0 && ly >= by) ? (int)((ly - by) >> RD_SUB_BITS) + 1 : 0;
+  // crossings no farther than range_max per axis: l = floor(rsub * |D| / 2^18) sub-cells of travel along the axis
+  int nx, ny;
+  if ((unsigned long long)rsub < (1ull << 21)) {
+    // ranges below 512 cells (every shipped configuration): (rsub * 2^11) * (|D| * 2^3) = rsub * |D| * 2^14 exactly, so
+    // the high word of one 32 x 32 multiply is the same floor as the 64-bit product shifted by 18
+    const uint32_t r11 = (uint32_t)rsub << 11;
+    const uint32_t lx = rd_mulhi_u32(r11, (uint32_t)adx << 3), ly = rd_mulhi_u32(r11, (uint32_t)ady << 3);
+    nx = (adx != 0 && lx >= (uint32_t)bx) ? (int)((lx - (uint32_t)bx) >> RD_SUB_BITS) + 1 : 0;
+    ny = (ady != 0 && ly >= (uint32_t)by) ? (int)((ly - (uint32_t)by) >> RD_SUB_BITS) + 1 : 0;
+  } else {
+    const long long lx = (rsub * adx) >> RD_DIR_BITS, ly = (rsub * ady) >> RD_DIR_BITS;
+    nx = (adx != 0 && lx >= bx) ? (int)((lx - bx) >> RD_SUB_BITS) + 1 : 0;
+    ny = (ady != 0 && ly >= by) ? (int)((ly - by) >> RD_SUB_BITS) + 1 : 0;
+  }
   const int n0 = nx + ny;
   const int sx = DX > 0 ? 1 : -1, sy = DY > 0 ? 1 : -1;
 
