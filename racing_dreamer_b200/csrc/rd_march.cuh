@@ -72,7 +72,7 @@ RD_HD MarchResult rd_march(const MarchGrid& g, int px, int py, int DX, int DY, l
     ny = (ady != 0 && ly >= by) ? (int)((ly - by) >> RD_SUB_BITS) + 1 : 0;
   }
   const int n0 = nx + ny;
-  const int sx = DX > 0 ? 1 : -1, sy = DY > 0 ? 1 : -1;
+  const int sx = DX > 0 ? 1 : -1;
 
   // ---- phase 1: clearance jumps in the ray parameter U (whole cells) ----
   const int ulim = (int)(rsub >> RD_SUB_BITS);

@@ -26,9 +26,10 @@
 //   D  resize      Pillow's 22-bit fixed-point bicubic, horizontal then vertical, uint8 intermediate, in smem
 #pragma once
 #include "rd_common.cuh"
+#include <cstring>
 
 #ifndef OCC_THREADS
-#define OCC_THREADS 512
+#define OCC_THREADS 640
 #endif
 #define OCC_ROWS 223        // 220 + mirrored border (index -1 and 220, 221)
 #define OCC_PITCH 227       // row pitch in floats: odd (row pass conflict-free) and = 3 mod 32 (rotated 8x4 tiles spread over the banks)
@@ -40,14 +41,22 @@
 #define OCC_BANDW (2 * OCC_BAND + 1)
 #define OCC_NB 28           // 8x8-cell blocks per crop side (uniform-region map)
 
-struct OccTables {            // Pillow precompute_coeffs + normalize_coeffs_8bpc for 200 -> 64, bicubic
-  int32_t kk[RD_OCC_OUT * OCC_KSIZE];
-  int32_t xmin[RD_OCC_OUT];
-  int32_t xnum[RD_OCC_OUT];
-  // horizontal pass on BINARY rows: lut[g][m][xx] = sum of kk[xx][5g + j] over the set bits j of the 5-bit mask m, so the
-  // 15-tap sum of one output pixel is three table reads on the window's bit mask (exact integer arithmetic); xx is the
-  // fastest index so that a warp (32 consecutive xx) reads 32 consecutive words when its lanes see the same mask
-  int32_t lut[3 * 32 * RD_OCC_OUT];
+// Pillow precompute_coeffs + normalize_coeffs_8bpc for 200 -> 64, bicubic.  25 input pixels map onto 8 output pixels
+// exactly (scale 3.125), so output pixel xx + 8 has the weights of xx with its window moved by 25: apart from the two
+// clipped windows at either end there are only 8 distinct weight sets -- OCC_NPH = 12 "phases" -- and the tables are
+// small enough (4.4 KB) to stay in shared memory for the whole launch instead of being copied in per env.
+#define OCC_NPH 12
+#define OCC_LUT_ROWS (32 + 32 + 8)   // 5-bit masks of taps 0..4 and 5..9, 3-bit mask of taps 10..12 (windows are <= 13 taps)
+struct OccTables {
+  // horizontal pass on BINARY rows: lut[row][ph] = sum of kk[ph][5g + j] over the set bits j of the mask m of tap group g
+  // (row = 32 g + m), so the <= 13-tap sum of one output pixel is three table reads on the window's bit mask (exact
+  // integer arithmetic); the phase is the fastest index: 32 consecutive output pixels with the same mask read 8
+  // consecutive words
+  int32_t lut[OCC_LUT_ROWS * OCC_NPH];
+  int32_t kk[OCC_NPH * OCC_KSIZE];
+  uint8_t xmin[RD_OCC_OUT];
+  uint8_t xnum[RD_OCC_OUT];
+  uint8_t phase[RD_OCC_OUT];
 };
 
 struct OccScratch {
@@ -69,17 +78,17 @@ struct OccGeom {              // per-env geometry, computed by one thread
 #define OCC_SM_XBITS_BYTES (RD_OCC_IN * OCC_XW * 4)                   // 6,160
 #define OCC_SM_PLANES (OCC_SM_XBITS + OCC_SM_XBITS_BYTES)
 #define OCC_SM_PLANES_BYTES (2 * (RD_OCC_MID * RD_OCC_MID / 32) * 4)  // 10,000
-#define OCC_SM_RC (OCC_SM_PLANES + OCC_SM_PLANES_BYTES)               // per-row coordinate terms (float64); 16-byte aligned
-#define OCC_SM_RC_BYTES (2 * RD_OCC_MID * 8)                          // 3,200
-#define OCC_SM_EDGE (OCC_SM_RC + OCC_SM_RC_BYTES)                     // near-edge bitmap, same layout as the crop bits
+#define OCC_SM_EDGE (OCC_SM_PLANES + OCC_SM_PLANES_BYTES)              // near-edge bitmap, same layout as the crop bits
 #define OCC_SM_EDGE_BYTES (RD_OCC_IN * OCC_XW * 4)                    // 6,160
 #define OCC_SM_TLIST (OCC_SM_EDGE + OCC_SM_EDGE_BYTES)                // packed (ty, tx) of the mixed 8x4 tiles of the mid image (u16)
 #define OCC_N_TILES (RD_OCC_MID * RD_OCC_MID / 32)                    // 1250
 #define OCC_SM_TLIST_BYTES ((OCC_N_TILES * 2 + 15) & ~15)             // 2,512
-#define OCC_SM_TOTAL (OCC_SM_TLIST + OCC_SM_TLIST_BYTES)              // 230,528 of 232,448
-// after the rotation the coefficient image is dead; its space holds the uint8 images and tables of the resize
+#define OCC_SM_TAB (OCC_SM_TLIST + OCC_SM_TLIST_BYTES)                // resize tables, resident for the whole launch
+#define OCC_SM_TAB_BYTES ((sizeof(OccTables) + 15) & ~15)             // 4,368
+#define OCC_SM_TOTAL (OCC_SM_TAB + OCC_SM_TAB_BYTES)                  // 231,696 of 232,448 (227 KB per CTA, 64 B static)
+static_assert(OCC_SM_TOTAL + 64 <= 232448, "k_occupancy shared memory");
+// after the rotation the coefficient image is dead; its space holds the uint8 intermediate of the resize
 #define OCC_SM_TMP 0
-#define OCC_SM_TAB (OCC_SM_TMP + RD_OCC_MID * RD_OCC_OUT)
 
 __device__ __forceinline__ int occ_mirror(int idx, int len) {
   if (idx < 0) idx = -idx;
@@ -96,104 +105,115 @@ __device__ __forceinline__ void occ_weights(double x, double (&w)[4]) {
 }
 
 // float32 cubic B-spline prefilter of the 220 lines of one axis (mirror boundary, pole z = sqrt(3)-2, gain 6), one WARP
-// per line, every sample in registers:
+// per PAIR of adjacent lines, every sample in registers, the two lines packed in float2 (FFMA2: one instruction, two
+// lines):
 //   scipy's recursion is  y[i] = 6 x[i] + z y[i-1]  (causal, y[0] = the mirror sum  sum_i z^i 6 x[i])  followed by
 //   w[n-1] = (z y[n-2] + y[n-1]) z / (z^2 - 1),  w[i] = z (w[i+1] - y[i])  (anticausal).
-// Lane l owns samples 7l .. 7l+6.  It runs both recursions on its seven samples with a zero incoming state, and the true
-// incoming state is restored from its neighbours' end values: the state decays by z^7 = -1e-4 per lane, so three
-// neighbours (z^21 = 1e-12) reproduce the full-line recursion far below float32 resolution.  Compared with one thread per
-// line this replaces two 134-step dependent chains per thread and axis by 7-step chains, reads and writes every sample
-// once per axis instead of twice, and needs one barrier per axis instead of four.
+// The inputs are scaled by -z (on top of the gain), so that the anticausal step is ONE fma, w[i] = z w[i+1] + y'[i]
+// with y' = -z y; every quantity of the causal pass carries that factor (the recursion is linear).
+// Lane l owns samples 7l-4 .. 7l+2: the line's last sample (219) is the last slot of lane 31, so the anticausal
+// initialisation touches one register; the four slots in front of sample 0 (lane 0) hold zeros and are never stored.
+// Each lane runs both recursions on its seven samples with a zero incoming state, and the true incoming state is
+// restored from its neighbours' end values: the state decays by z^7 = -1e-4 per lane, so three neighbours (z^21 = 1e-12)
+// reproduce the full-line recursion far below float32 resolution.  The mirror initialisation enters as the state c in
+// front of lane 0's slot 0 that makes the causal value at sample 0 equal the mirror sum M: four zero samples later the
+// state is z^4 c = (M - x0) / z.
 // Element i of line L lives at img[L * LINE_STRIDE + i * ELEM_STRIDE].  FROM_BITS: the line is crop ROW L and its input
 // the crop bits (L, i) instead of the image -- the first pass reads the binary crop directly, seven bits of one funnel
-// shift per lane.  (scipy filters axis 0 first; the operator is separable, so the order only moves float32 rounding.)
+// shift per lane and line.  (scipy filters axis 0 first; the operator is separable, so the order only moves float32
+// rounding, which the exactness stage C' bounds.)
 #define OCC_LANE_N 7
+#define OCC_LANE_LEAD 4
+__device__ __forceinline__ float2 occ_f2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 occ_shfl2(float2 v, int src) {
+  return make_float2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+__device__ __forceinline__ float2 occ_shfl2_up(float2 v) {
+  return make_float2(__shfl_up_sync(0xffffffffu, v.x, 1), __shfl_up_sync(0xffffffffu, v.y, 1));
+}
+__device__ __forceinline__ float2 occ_shfl2_down(float2 v) {
+  return make_float2(__shfl_down_sync(0xffffffffu, v.x, 1), __shfl_down_sync(0xffffffffu, v.y, 1));
+}
 template <bool FROM_BITS, int LINE_STRIDE, int ELEM_STRIDE>
 __device__ __forceinline__ void occ_prefilter_axis(float* img, const uint32_t* xb) {
   constexpr int n = RD_OCC_IN;
-  constexpr float z = -0.26794919243112270647f, gain = 6.0f;
+  static_assert(n % 2 == 0 && 32 * OCC_LANE_N - OCC_LANE_LEAD == n, "220 samples = 32 lanes of 7 minus 4 leading slots");
+  constexpr float z = -0.26794919243112270647f, gain = 6.0f, xg = -z * gain;
   constexpr float z2 = z * z, z3 = z2 * z, z4 = z3 * z, z5 = z4 * z, z6 = z5 * z, z7 = z6 * z;
+  constexpr float zm5 = 1.0f / z5, zm9 = 1.0f / (z5 * z4);
   const float zp[OCC_LANE_N] = {z, z2, z3, z4, z5, z6, z7};
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i0 = lane * OCC_LANE_N;
-  for (int L = warp; L < n; L += OCC_THREADS / 32) {
+  const int i0 = lane * OCC_LANE_N - OCC_LANE_LEAD;
+  const bool first = lane == 0, tail = lane == 31;
+  const float2 Z = occ_f2(z), Z7 = occ_f2(z7), zero = occ_f2(0.0f);
+  for (int L = 2 * warp; L < n; L += 2 * (OCC_THREADS / 32)) {
     float* p = img + L * LINE_STRIDE + i0 * ELEM_STRIDE;
-    float x[OCC_LANE_N];
-    if (FROM_BITS) {   // bits i0 .. i0+6 of crop row L (bits beyond column 219 are zero in the crop words)
-      const uint32_t* row = xb + L * OCC_XW;
-      const int wj = i0 >> 5;
-      const uint32_t w = __funnelshift_r(row[wj], wj + 1 < OCC_XW ? row[wj + 1] : 0u, i0 & 31);
+    float2 x[OCC_LANE_N];
+    if (FROM_BITS) {   // bits i0 .. i0+6 of crop rows L, L+1 (lane 0: four zero slots, then bits 0..2)
+      const uint32_t* ra = xb + L * OCC_XW;
+      const uint32_t* rb = ra + OCC_XW;
+      const int s = first ? 0 : i0, wj = s >> 5;
+      uint32_t wa = __funnelshift_r(ra[wj], wj + 1 < OCC_XW ? ra[wj + 1] : 0u, s & 31);
+      uint32_t wb = __funnelshift_r(rb[wj], wj + 1 < OCC_XW ? rb[wj + 1] : 0u, s & 31);
+      if (first) { wa <<= OCC_LANE_LEAD; wb <<= OCC_LANE_LEAD; }
 #pragma unroll
-      for (int j = 0; j < OCC_LANE_N; ++j) x[j] = ((w >> j) & 1u) ? gain : 0.0f;
+      for (int j = 0; j < OCC_LANE_N; ++j) x[j] = make_float2(((wa >> j) & 1u) ? xg : 0.0f, ((wb >> j) & 1u) ? xg : 0.0f);
     } else {
 #pragma unroll
-      for (int j = 0; j < OCC_LANE_N; ++j) x[j] = (i0 + j < n) ? gain * p[j * ELEM_STRIDE] : 0.0f;
+      for (int j = 0; j < OCC_LANE_N; ++j)
+        x[j] = (i0 + j >= 0) ? __fmul2_rn(make_float2(p[j * ELEM_STRIDE], p[j * ELEM_STRIDE + LINE_STRIDE]), occ_f2(xg)) : zero;
     }
-    // ---- causal pass ----
-    float u[OCC_LANE_N];
+    // ---- causal pass (zero incoming state) and the mirror sum ----
+    float2 u[OCC_LANE_N];
     u[0] = x[0];
 #pragma unroll
-    for (int j = 1; j < OCC_LANE_N; ++j) u[j] = fmaf(z, u[j - 1], x[j]);
-    // mirror initialisation y[0] = sum_i z^i x[i]: lanes 0..3 hold the first 28 terms (z^28 = 1e-16)
-    float poly = x[OCC_LANE_N - 1];
+    for (int j = 1; j < OCC_LANE_N; ++j) u[j] = __ffma2_rn(Z, u[j - 1], x[j]);
+    float2 poly = x[OCC_LANE_N - 1];
 #pragma unroll
-    for (int j = OCC_LANE_N - 2; j >= 0; --j) poly = fmaf(z, poly, x[j]);
-    const float p1 = __shfl_sync(0xffffffffu, poly, 1), p2 = __shfl_sync(0xffffffffu, poly, 2), p3 = __shfl_sync(0xffffffffu, poly, 3);
-    const float y0 = fmaf(z7, fmaf(z7, fmaf(z7, p3, p2), p1), __shfl_sync(0xffffffffu, poly, 0));
-    const float s0 = (y0 - __shfl_sync(0xffffffffu, x[0], 0)) * (1.0f / z);   // the state "before sample 0" that yields y[0]
-    // lanes 0..2 have fewer than three predecessors: the state before sample 0 (s0) stands in for "lane -1"
-    const bool first = lane == 0;
-    float c1 = __shfl_up_sync(0xffffffffu, u[OCC_LANE_N - 1], 1);
-    c1 = first ? s0 : c1;
-    float c2 = __shfl_up_sync(0xffffffffu, c1, 1);
-    c2 = first ? 0.0f : c2;
-    float c3 = __shfl_up_sync(0xffffffffu, c2, 1);
-    c3 = first ? 0.0f : c3;
-    const float sin_ = fmaf(z7, fmaf(z7, c3, c2), c1);
-    float y[OCC_LANE_N];
+    for (int j = OCC_LANE_N - 2; j >= 0; --j) poly = __ffma2_rn(Z, poly, x[j]);
+    // lanes 0..3 hold samples 0..23 behind four zeros: poly0 + z^7 (poly1 + z^7 (poly2 + z^7 poly3)) = z^4 M (z^24 = 2e-14)
+    const float2 p1 = occ_shfl2(poly, 1), p2 = occ_shfl2(poly, 2), p3 = occ_shfl2(poly, 3);
+    const float2 m4 = __ffma2_rn(Z7, __ffma2_rn(Z7, __ffma2_rn(Z7, p3, p2), p1), occ_shfl2(poly, 0));
+    // c = (M - x0) / z^5 = z^-9 (z^4 M) - z^-5 x0
+    const float2 c = __ffma2_rn(m4, occ_f2(zm9), __fmul2_rn(occ_shfl2(x[OCC_LANE_LEAD], 0), occ_f2(-zm5)));
+    float2 c1 = occ_shfl2_up(u[OCC_LANE_N - 1]);
+    c1 = first ? c : c1;
+    float2 c2 = occ_shfl2_up(c1);
+    c2 = first ? zero : c2;
+    float2 c3 = occ_shfl2_up(c2);
+    c3 = first ? zero : c3;
+    const float2 sin_ = __ffma2_rn(Z7, __ffma2_rn(Z7, c3, c2), c1);
+    float2 y[OCC_LANE_N];
 #pragma unroll
-    for (int j = 0; j < OCC_LANE_N; ++j) y[j] = fmaf(zp[j], sin_, u[j]);
-    // ---- anticausal pass ----
-    constexpr int last_lane = (n - 1) / OCC_LANE_N, last_j = (n - 1) - last_lane * OCC_LANE_N;   // sample n-1 = lane 31, slot 2
-    static_assert(last_lane == 31 && last_j >= 1, "220 samples over 32 lanes of 7");
-    float v[OCC_LANE_N + 1];
-    v[OCC_LANE_N] = 0.0f;
-    const bool tail = lane == last_lane;
-    const float w_end = (z * y[last_j - 1] + y[last_j]) * (z / (z * z - 1.0f));
+    for (int j = 0; j < OCC_LANE_N; ++j) y[j] = __ffma2_rn(occ_f2(zp[j]), sin_, u[j]);
+    // ---- anticausal pass: w[i] = z w[i+1] + y[i]; the line ends at slot 6 of lane 31 ----
+    const float2 w_end = __fmul2_rn(__ffma2_rn(Z, y[OCC_LANE_N - 2], y[OCC_LANE_N - 1]), occ_f2(-1.0f / (z * z - 1.0f)));
+    float2 v[OCC_LANE_N];
+    v[OCC_LANE_N - 1] = tail ? w_end : y[OCC_LANE_N - 1];
 #pragma unroll
-    for (int j = OCC_LANE_N - 1; j >= 0; --j) {
-      float t = z * (v[j + 1] - y[j]);
-      if (tail && j > last_j) t = 0.0f;       // samples beyond the line
-      if (tail && j == last_j) t = w_end;     // scipy's anticausal initialisation
-      v[j] = t;
+    for (int j = OCC_LANE_N - 2; j >= 0; --j) v[j] = __ffma2_rn(Z, v[j + 1], y[j]);
+    float2 d1 = occ_shfl2_down(v[0]);
+    d1 = tail ? zero : d1;
+    float2 d2 = occ_shfl2_down(d1);
+    d2 = tail ? zero : d2;
+    float2 d3 = occ_shfl2_down(d2);
+    d3 = tail ? zero : d3;
+    const float2 tin = __ffma2_rn(Z7, __ffma2_rn(Z7, d3, d2), d1);   // 0 for lane 31: its values are final already
+#pragma unroll
+    for (int j = 0; j < OCC_LANE_N; ++j) {
+      const float2 o = __ffma2_rn(occ_f2(zp[OCC_LANE_N - 1 - j]), tin, v[j]);
+      if (i0 + j >= 0) { p[j * ELEM_STRIDE] = o.x; p[j * ELEM_STRIDE + LINE_STRIDE] = o.y; }
     }
-    float d1 = __shfl_down_sync(0xffffffffu, v[0], 1);
-    d1 = tail ? 0.0f : d1;
-    float d2 = __shfl_down_sync(0xffffffffu, d1, 1);
-    d2 = tail ? 0.0f : d2;
-    float d3 = __shfl_down_sync(0xffffffffu, d2, 1);
-    d3 = tail ? 0.0f : d3;
-    const float tin = fmaf(z7, fmaf(z7, d3, d2), d1);   // 0 for lane 31: its values are final already
-#pragma unroll
-    for (int j = 0; j < OCC_LANE_N; ++j)
-      if (i0 + j < n) p[j * ELEM_STRIDE] = fmaf(zp[OCC_LANE_N - 1 - j], tin, v[j]);
   }
   __syncthreads();
 }
 
 // Source coordinates of mid pixel (a, b) with scipy's operation order (shift first, then one product per output axis):
 //   c0 = (off0 + o0*c) + o1*s ,  c1 = (off1 + o0*(-s)) + o1*c .
-// The per-row terms (off + o0*..) are tabulated once per env: rc[0..199] row term of c0, rc[200..399] row term of c1; the
-// per-column terms are one product each -- same operations, same bits.
-__device__ __forceinline__ void occ_coord_tables(const OccGeom& g, double* rc, int i) {
-  const double o0 = (double)(g.o0_first + i);
-  rc[i] = __dadd_rn(g.off0, __dmul_rn(o0, g.c));
-  rc[RD_OCC_MID + i] = __dadd_rn(g.off1, __dmul_rn(o0, -g.s));
-}
-__device__ __forceinline__ void occ_coords(const double* rc, const OccGeom& g, int a, int b, double& c0, double& c1) {
-  const double o1 = (double)(g.o1_first + b);
-  c0 = __dadd_rn(rc[a], __dmul_rn(o1, g.s));
-  c1 = __dadd_rn(rc[RD_OCC_MID + a], __dmul_rn(o1, g.c));
+__device__ __forceinline__ void occ_coords(const OccGeom& g, int a, int b, double& c0, double& c1) {
+  const double o0 = (double)(g.o0_first + a), o1 = (double)(g.o1_first + b);
+  c0 = __dadd_rn(__dadd_rn(g.off0, __dmul_rn(o0, g.c)), __dmul_rn(o1, g.s));
+  c1 = __dadd_rn(__dadd_rn(g.off1, __dmul_rn(o0, -g.s)), __dmul_rn(o1, g.c));
 }
 
 // Exact float64 value of one rotated pixel (a, b), computed by ONE WARP from coef = H X H^T; every lane returns the
@@ -203,11 +223,11 @@ __device__ __forceinline__ void occ_coords(const double* rc, const OccGeom& g, i
 //   C: the 4x4 taps in scipy's accumulation order and its rounding.
 // No shared scratch, no CTA barrier: about one image in 40 needs it, so its cost (~10k instructions) is irrelevant, but
 // it must not make the other warps wait.
-__device__ __noinline__ uint32_t occ_exact_pixel(const double* rc, const OccGeom& g, int a, int b, const uint32_t* xb,
+__device__ __noinline__ uint32_t occ_exact_pixel(const OccGeom& g, int a, int b, const uint32_t* xb,
                                                  const double* __restrict__ hband) {
   const int lane = threadIdx.x & 31;
   double c0, c1;
-  occ_coords(rc, g, a, b, c0, c1);
+  occ_coords(g, a, b, c0, c1);
   const int s0 = (int)floor(c0) - 1, s1 = (int)floor(c1) - 1;
   int rp[4], cq[4];
 #pragma unroll
@@ -277,7 +297,6 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
   float* coef = reinterpret_cast<float*>(smem + OCC_SM_COEF);
   uint32_t* xb = reinterpret_cast<uint32_t*>(smem + OCC_SM_XBITS);
   uint32_t* planes = reinterpret_cast<uint32_t*>(smem + OCC_SM_PLANES);
-  double* rc = reinterpret_cast<double*>(smem + OCC_SM_RC);
   uint32_t* eb = reinterpret_cast<uint32_t*>(smem + OCC_SM_EDGE);   // near-edge bitmap (see stage A')
   uint8_t* tmp = smem + OCC_SM_TMP;
   OccTables* tb = reinterpret_cast<OccTables*>(smem + OCC_SM_TAB);
@@ -288,6 +307,8 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
 
   const DevMap& m = maps[map_id];
   const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < (int)(sizeof(OccTables) / 4); i += OCC_THREADS)     // resident for every env of this CTA
+    reinterpret_cast<int32_t*>(tb)[i] = __ldg(reinterpret_cast<const int32_t*>(tables) + i);
 
   for (int slot = blockIdx.x; slot < n_env; slot += gridDim.x) {
     const int env = order ? __ldg(order + slot) : slot;
@@ -334,7 +355,6 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
       n_mixed = 0;
     }
     __syncthreads();
-    if (tid < RD_OCC_MID) occ_coord_tables(geom, rc, tid);
 
     // ---- A: crop bits -> smem.  word (i, j) = crop columns 32j..32j+31 of crop row i ----
     for (int t = tid; t < RD_OCC_IN * OCC_XW; t += OCC_THREADS) {
@@ -401,10 +421,10 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
           double lo0, hi0, lo1, hi1;
           {
             double p0, p1, q0, q1, r0, r1, s0, s1;
-            occ_coords(rc, geom, a0, b0, p0, p1);
-            occ_coords(rc, geom, a0, b0 + 7, q0, q1);
-            occ_coords(rc, geom, a0 + 3, b0, r0, r1);
-            occ_coords(rc, geom, a0 + 3, b0 + 7, s0, s1);
+            occ_coords(geom, a0, b0, p0, p1);
+            occ_coords(geom, a0, b0 + 7, q0, q1);
+            occ_coords(geom, a0 + 3, b0, r0, r1);
+            occ_coords(geom, a0 + 3, b0 + 7, s0, s1);
             lo0 = fmin(fmin(p0, q0), fmin(r0, s0)); hi0 = fmax(fmax(p0, q0), fmax(r0, s0));
             lo1 = fmin(fmin(p1, q1), fmin(r1, s1)); hi1 = fmax(fmax(p1, q1), fmax(r1, s1));
           }
@@ -475,7 +495,7 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
       {
         const int a = ty * 4 + (lane >> 3), b = tx * 8 + (lane & 7);
         double c0, c1;
-        occ_coords(rc, geom, a, b, c0, c1);
+        occ_coords(geom, a, b, c0, c1);
         uint32_t val = 0u;
         bool ambiguous = false;
         const bool inside = !(c0 < 0.0 || c0 > (double)(RD_OCC_IN - 1) || c1 < 0.0 || c1 > (double)(RD_OCC_IN - 1));
@@ -520,7 +540,7 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
         // float64 re-evaluation of the (rare) ambiguous pixels, one after the other, by the whole warp
         for (uint32_t todo = __ballot_sync(0xffffffffu, ambiguous); todo; todo &= todo - 1u) {
           const int src = __ffs(todo) - 1;
-          const uint32_t exact = occ_exact_pixel(rc, geom, __shfl_sync(0xffffffffu, a, src), __shfl_sync(0xffffffffu, b, src), xb, hband);
+          const uint32_t exact = occ_exact_pixel(geom, __shfl_sync(0xffffffffu, a, src), __shfl_sync(0xffffffffu, b, src), xb, hband);
           if (lane == src) val = exact > 3u ? 3u : exact;
         }
         // tile row i (8 pixels) is one byte of the row-major bit planes
@@ -536,28 +556,26 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
     if (hi_acc && lane == 0) any_hi = 1;
     __syncthreads();
 
-    // ---- D: Pillow bicubic 200 -> 64.  The coefficient image is dead: its space takes the tables and the uint8
-    // intermediate.  Horizontal pass straight on the bit planes: the <= 15-tap window of an output pixel is a bit mask,
-    // its fixed-point sum three table reads (plane 1, the "value >= 2" plane, is empty for every real map; if any
-    // pixel set it, its windows are added with weight 2).
-    for (int i = tid; i < (int)(sizeof(OccTables) / 4); i += OCC_THREADS)
-      reinterpret_cast<int32_t*>(tb)[i] = __ldg(reinterpret_cast<const int32_t*>(tables) + i);
-    __syncthreads();
+    // ---- D: Pillow bicubic 200 -> 64.  The coefficient image is dead: its space takes the uint8 intermediate.
+    // Horizontal pass straight on the bit planes: the <= 13-tap window of an output pixel is a bit mask, its fixed-point
+    // sum three table reads (plane 1, the "value >= 2" plane, is empty for every real map; if any pixel set it, its
+    // windows are added with weight 2).  A thread keeps its output column: window position and phase are loop constants.
     {
+      static_assert(OCC_THREADS % RD_OCC_OUT == 0, "one output column per thread");
       const bool hi_plane = any_hi != 0;
-      for (int i = tid; i < RD_OCC_MID * RD_OCC_OUT; i += OCC_THREADS) {
-        const int yy = i / RD_OCC_OUT, xx = i - yy * RD_OCC_OUT;
-        const int x0 = tb->xmin[xx], xn = tb->xnum[xx];
+      const int xx = tid & (RD_OCC_OUT - 1);
+      const int x0 = tb->xmin[xx], xn = tb->xnum[xx];
+      const uint32_t mask = (1u << xn) - 1u;
+      const int32_t* lut = tb->lut + tb->phase[xx];
+      for (int yy = tid / RD_OCC_OUT; yy < RD_OCC_MID; yy += OCC_THREADS / RD_OCC_OUT) {
         const int bitpos = yy * RD_OCC_MID + x0;
-        const uint32_t mask = (1u << xn) - 1u;
-        const int32_t* lut = tb->lut + xx;
         const uint32_t m0 = __funnelshift_r(planes[bitpos >> 5], planes[(bitpos >> 5) + 1], bitpos & 31) & mask;
-        int32_t ss = (1 << (OCC_PREC_BITS - 1)) + lut[(m0 & 31u) * RD_OCC_OUT] + lut[(32 + ((m0 >> 5) & 31u)) * RD_OCC_OUT] +
-                     lut[(64 + (m0 >> 10)) * RD_OCC_OUT];
+        int32_t ss = (1 << (OCC_PREC_BITS - 1)) + lut[(m0 & 31u) * OCC_NPH] + lut[(32 + ((m0 >> 5) & 31u)) * OCC_NPH] +
+                     lut[(64 + (m0 >> 10)) * OCC_NPH];
         if (hi_plane) {
           const uint32_t* p1 = planes + (n_pix >> 5);
           const uint32_t m1 = __funnelshift_r(p1[bitpos >> 5], p1[min((bitpos >> 5) + 1, (n_pix >> 5) - 1)], bitpos & 31) & mask;
-          ss += 2 * (lut[(m1 & 31u) * RD_OCC_OUT] + lut[(32 + ((m1 >> 5) & 31u)) * RD_OCC_OUT] + lut[(64 + (m1 >> 10)) * RD_OCC_OUT]);
+          ss += 2 * (lut[(m1 & 31u) * OCC_NPH] + lut[(32 + ((m1 >> 5) & 31u)) * OCC_NPH] + lut[(64 + (m1 >> 10)) * OCC_NPH]);
         }
         ss >>= OCC_PREC_BITS;
         tmp[yy * RD_OCC_OUT + xx] = (uint8_t)(ss < 0 ? 0 : (ss > 255 ? 255 : ss));
@@ -570,7 +588,7 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
       const int yy = i / (RD_OCC_OUT / 4), x4 = i - yy * (RD_OCC_OUT / 4);
       int32_t s0 = 1 << (OCC_PREC_BITS - 1), s1 = s0, s2 = s0, s3 = s0;
       const int y0 = tb->xmin[yy], yn = tb->xnum[yy];
-      const int32_t* k = tb->kk + yy * OCC_KSIZE;
+      const int32_t* k = tb->kk + tb->phase[yy] * OCC_KSIZE;
       const uint32_t* col = reinterpret_cast<const uint32_t*>(tmp) + y0 * (RD_OCC_OUT / 4) + x4;
       for (int t = 0; t < yn; ++t) {
         const uint32_t w = col[t * (RD_OCC_OUT / 4)];
@@ -597,11 +615,15 @@ static inline double occ_bicubic(double x) {
   return 0.0;
 }
 
-static inline void occ_build_tables(OccTables& t) {
+// returns false if the resize geometry does not have the expected structure (cannot happen for 200 -> 64)
+static inline bool occ_build_tables(OccTables& t) {
   const int in_size = RD_OCC_MID, out_size = RD_OCC_OUT;
   const double scale = (double)in_size / out_size, filterscale = scale < 1.0 ? 1.0 : scale;
   const double support = 2.0 * filterscale;
   double k[OCC_KSIZE];
+  int32_t kk[RD_OCC_OUT][OCC_KSIZE];
+  int n_phase = 0;
+  std::memset(&t, 0, sizeof(t));
   for (int xx = 0; xx < out_size; ++xx) {
     const double center = (xx + 0.5) * scale, ss = 1.0 / filterscale;
     double ww = 0.0;
@@ -615,17 +637,29 @@ static inline void occ_build_tables(OccTables& t) {
     for (x = 0; x < xmax; ++x) if (ww != 0.0) k[x] /= ww;
     for (; x < OCC_KSIZE; ++x) k[x] = 0;
     for (x = 0; x < OCC_KSIZE; ++x)
-      t.kk[xx * OCC_KSIZE + x] = k[x] < 0 ? (int32_t)(-0.5 + k[x] * (1 << OCC_PREC_BITS)) : (int32_t)(0.5 + k[x] * (1 << OCC_PREC_BITS));
-    t.xmin[xx] = xmin;
-    t.xnum[xx] = xmax;
-    for (int g = 0; g < 3; ++g)
-      for (int m = 0; m < 32; ++m) {
-        int32_t acc = 0;
-        for (int j = 0; j < 5; ++j)
-          if ((m >> j) & 1) acc += t.kk[xx * OCC_KSIZE + 5 * g + j];
-        t.lut[(g * 32 + m) * RD_OCC_OUT + xx] = acc;
-      }
+      kk[xx][x] = k[x] < 0 ? (int32_t)(-0.5 + k[x] * (1 << OCC_PREC_BITS)) : (int32_t)(0.5 + k[x] * (1 << OCC_PREC_BITS));
+    if (xmax > 13 || xmin > 255) return false;
+    t.xmin[xx] = (uint8_t)xmin;
+    t.xnum[xx] = (uint8_t)xmax;
+    // phase = index of the first output pixel with the same window length and weights
+    int ph = -1;
+    for (int q = 0; q < xx && ph < 0; ++q)
+      if (t.xnum[q] == t.xnum[xx] && std::memcmp(kk[q], kk[xx], sizeof(kk[q])) == 0) ph = t.phase[q];
+    if (ph < 0) {
+      if (n_phase == OCC_NPH) return false;
+      ph = n_phase++;
+      for (x = 0; x < OCC_KSIZE; ++x) t.kk[ph * OCC_KSIZE + x] = kk[xx][x];
+      for (int g = 0; g < 3; ++g)
+        for (int m = 0; m < (g < 2 ? 32 : 8); ++m) {
+          int32_t acc = 0;
+          for (int j = 0; j < 5; ++j)
+            if ((m >> j) & 1) acc += kk[xx][5 * g + j];
+          t.lut[(g * 32 + m) * OCC_NPH + ph] = acc;
+        }
+    }
+    t.phase[xx] = (uint8_t)ph;
   }
+  return true;
 }
 
 // float64 1-D prefilter (scipy's recursion: gain 6, pole sqrt(3)-2, mirror boundary), host copy used to tabulate H
@@ -671,7 +705,7 @@ static inline int occ_launch(OccScratch& sc, const DevMap* d_maps, int map_id, c
   if (e != cudaSuccess) return (int)e;
   if (!sc.tables) {
     OccTables t;
-    occ_build_tables(t);
+    if (!occ_build_tables(t)) return (int)cudaErrorInvalidValue;
     e = cudaMalloc(&sc.tables, sizeof(OccTables));
     if (e != cudaSuccess) return (int)e;
     e = cudaMemcpy(sc.tables, &t, sizeof(OccTables), cudaMemcpyHostToDevice);
