@@ -69,7 +69,15 @@ struct OccGeom {              // per-env geometry, computed by one thread
   double c, s, off0, off1;
   int o0_first, o1_first;     // output index of centre-crop pixel (0,0)
   int pr, pc;
+  int env, mode;              // env index; 0 = compute, 1 = reset observation (zeros), 2 = leave the buffer untouched
+  // float32 bounds of the source coordinates over an 8x4 tile (stage A"): c0 in [t0 + lo0, t0 + hi0] with
+  // t0 = fb0 + a0*fc + b0*fs for the tile's first pixel (a0, b0), likewise c1 with t1 = fb1 - a0*fs + b0*fc.  The four
+  // corners of the affine map give the extremes; OCC_TILE_MARGIN covers float32 rounding (< 1e-4 for |c| < 512) and
+  // the float64 roundings of the per-pixel rule, so a tile is only ever classified conservatively.
+  float fb0, fb1, fc, fs, lo0, hi0, lo1, hi1;
 };
+#define OCC_TILE_MARGIN 1.0e-3f
+struct OccPose { double x, y, yaw; int env, mode; };
 
 // smem carve-up (bytes)
 #define OCC_SM_COEF 0
@@ -86,7 +94,7 @@ struct OccGeom {              // per-env geometry, computed by one thread
 #define OCC_SM_TAB (OCC_SM_TLIST + OCC_SM_TLIST_BYTES)                // resize tables, resident for the whole launch
 #define OCC_SM_TAB_BYTES ((sizeof(OccTables) + 15) & ~15)             // 4,368
 #define OCC_SM_TOTAL (OCC_SM_TAB + OCC_SM_TAB_BYTES)                  // 231,696 of 232,448 (227 KB per CTA, 64 B static)
-static_assert(OCC_SM_TOTAL + 64 <= 232448, "k_occupancy shared memory");
+static_assert(OCC_SM_TOTAL + 256 <= 232448, "k_occupancy shared memory (dynamic + static)");
 // after the rotation the coefficient image is dead; its space holds the uint8 intermediate of the resize
 #define OCC_SM_TMP 0
 
@@ -288,6 +296,60 @@ __device__ __noinline__ uint32_t occ_exact_pixel(const OccGeom& g, int a, int b,
   return (uint32_t)(uint8_t)tv;
 }
 
+// The pose (and reset mode) of the env in work slot `slot`: three dependent global loads, issued one env ahead.
+__device__ __forceinline__ OccPose occ_load_pose(const OriginRec* __restrict__ recs, const double* __restrict__ poses,
+                                                 const double2* __restrict__ f2, int n_state,
+                                                 const int32_t* __restrict__ order, int slot) {
+  OccPose p;
+  p.env = order ? __ldg(order + slot) : slot;
+  p.mode = 0;
+  if (poses) { p.x = poses[3 * slot]; p.y = poses[3 * slot + 1]; p.yaw = poses[3 * slot + 2]; }
+  else {
+    const double2 xy = f2[p.env];                                   // env state groups (rd_dynamics.cuh): 0 = (x, y),
+    p.x = xy.x; p.y = xy.y;
+    p.yaw = f2[(size_t)2 * n_state + p.env].x;                      // 2 = (yaw, yaw_rate)
+    p.mode = recs[p.env].was_reset;
+  }
+  return p;
+}
+// crop position and scipy.ndimage.rotate's output geometry for one pose [REF dreamer/wrappers.py:396-403]
+__device__ __forceinline__ void occ_make_geom(const DevMap& m, const OccPose& p, OccGeom& g) {
+  const int col = (int)floor((p.x - m.ox) * m.inv_res);
+  const int rup = (int)floor((p.y - m.oy) * m.inv_res);
+  g.pr = m.full_h - 1 - rup;
+  g.pc = col;
+  const double ang = 2.0 * 3.141592653589793 - p.yaw;
+  double s, c;
+  sincos(ang, &s, &c);
+  const double N = (double)RD_OCC_IN;
+  const double b0[4] = {0.0, s * N, c * N, c * N + s * N};
+  const double b1[4] = {0.0, c * N, -s * N, -s * N + c * N};
+  double mn0 = b0[0], mx0 = b0[0], mn1 = b1[0], mx1 = b1[0];
+#pragma unroll
+  for (int k = 1; k < 4; ++k) {
+    mn0 = fmin(mn0, b0[k]); mx0 = fmax(mx0, b0[k]); mn1 = fmin(mn1, b1[k]); mx1 = fmax(mx1, b1[k]);
+  }
+  const int oh = (int)((mx0 - mn0) + 0.5), ow = (int)((mx1 - mn1) + 0.5);
+  const double oc0 = (oh - 1) / 2.0, oc1 = (ow - 1) / 2.0, ic = (N - 1.0) / 2.0;
+  g.c = c; g.s = s;
+  g.off0 = ic - (c * oc0 + s * oc1);
+  g.off1 = ic - (-s * oc0 + c * oc1);
+  g.o0_first = oh / 2 - RD_OCC_MID / 2;
+  g.o1_first = ow / 2 - RD_OCC_MID / 2;
+  g.env = p.env;
+  g.mode = p.mode;
+  const double f0 = (double)g.o0_first, f1 = (double)g.o1_first;
+  g.fb0 = (float)(g.off0 + f0 * c + f1 * s);
+  g.fb1 = (float)(g.off1 - f0 * s + f1 * c);
+  g.fc = (float)c;
+  g.fs = (float)s;
+  const float ac = 3.0f * g.fc, as = 3.0f * g.fs, bc = 7.0f * g.fc, bs = 7.0f * g.fs;   // rows a0..a0+3, columns b0..b0+7
+  g.lo0 = fminf(0.0f, ac) + fminf(0.0f, bs) - OCC_TILE_MARGIN;
+  g.hi0 = fmaxf(0.0f, ac) + fmaxf(0.0f, bs) + OCC_TILE_MARGIN;
+  g.lo1 = fminf(0.0f, -as) + fminf(0.0f, bc) - OCC_TILE_MARGIN;
+  g.hi1 = fmaxf(0.0f, -as) + fmaxf(0.0f, bc) + OCC_TILE_MARGIN;
+}
+
 __global__ void __launch_bounds__(OCC_THREADS, 1)
 k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict__ recs,
             const double* __restrict__ poses, const double2* __restrict__ f2, int n_state,
@@ -301,60 +363,43 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
   uint8_t* tmp = smem + OCC_SM_TMP;
   OccTables* tb = reinterpret_cast<OccTables*>(smem + OCC_SM_TAB);
   uint16_t* tlist = reinterpret_cast<uint16_t*>(smem + OCC_SM_TLIST);
-  __shared__ OccGeom geom;
+  // Geometry is double-buffered and computed ONE ENV AHEAD: the pose loads are issued at the top of an iteration by the
+  // first lane of the last warp, which turns them into the next env's geometry at the start of the prefilter stage (its
+  // warp has one line pair less than the first ten there), so neither the global-load latency nor the float64 sincos
+  // chain of a single thread holds the other 639 threads at a barrier.
+  __shared__ OccGeom gbuf[2];
   __shared__ int any_hi;
   __shared__ int n_mixed;
 
   const DevMap& m = maps[map_id];
   const int tid = threadIdx.x, lane = tid & 31;
+  const bool geom_thread = tid == OCC_THREADS - 32;
   for (int i = tid; i < (int)(sizeof(OccTables) / 4); i += OCC_THREADS)     // resident for every env of this CTA
     reinterpret_cast<int32_t*>(tb)[i] = __ldg(reinterpret_cast<const int32_t*>(tables) + i);
+  if (geom_thread && (int)blockIdx.x < n_env) occ_make_geom(m, occ_load_pose(recs, poses, f2, n_state, order, blockIdx.x), gbuf[0]);
+  __syncthreads();
 
-  for (int slot = blockIdx.x; slot < n_env; slot += gridDim.x) {
-    const int env = order ? __ldg(order + slot) : slot;
-    double x, y, yaw;
-    int mode = 0;
-    if (poses) { x = poses[3 * slot]; y = poses[3 * slot + 1]; yaw = poses[3 * slot + 2]; }
-    else {
-      const double2 xy = f2[env];                                   // env state groups (rd_dynamics.cuh): 0 = (x, y),
-      x = xy.x; y = xy.y;
-      yaw = f2[(size_t)2 * n_state + env].x;                        // 2 = (yaw, yaw_rate)
-      mode = recs[env].was_reset;
-    }
+  int it = 0;
+  for (int slot = blockIdx.x; slot < n_env; slot += gridDim.x, ++it) {
+    const OccGeom& geom = gbuf[it & 1];
+    OccGeom& geom_next = gbuf[(it + 1) & 1];
+    const bool have_next = geom_thread && slot + (int)gridDim.x < n_env;
+    OccPose next_pose;
+    if (have_next) next_pose = occ_load_pose(recs, poses, f2, n_state, order, slot + gridDim.x);   // in flight until stage B
+    const int env = geom.env, mode = geom.mode;
     uint8_t* dst = out + (size_t)(poses ? slot : env) * (RD_OCC_OUT * RD_OCC_OUT);
-    if (mode >= 2) continue;                 // frozen / not reset by this call: leave the buffer untouched
-    if (mode == 1) {                         // reset observation is all zeros [REF dreamer/wrappers.py:410-414]
-      for (int i = tid; i < RD_OCC_OUT * RD_OCC_OUT / 4; i += OCC_THREADS) reinterpret_cast<uint32_t*>(dst)[i] = 0u;
+    if (mode >= 1) {
+      // 2: frozen / not reset by this call: leave the buffer untouched; 1: the reset observation is all zeros
+      // [REF dreamer/wrappers.py:410-414]
+      if (mode == 1)
+        for (int i = tid; i < RD_OCC_OUT * RD_OCC_OUT / 4; i += OCC_THREADS) reinterpret_cast<uint32_t*>(dst)[i] = 0u;
+      __syncthreads();                       // nobody still reads the buffer the next geometry goes into
+      if (have_next) occ_make_geom(m, next_pose, geom_next);
+      __syncthreads();
       continue;
     }
     __syncthreads();  // previous env's smem fully consumed
-    if (tid == 0) {
-      const int col = (int)floor((x - m.ox) * m.inv_res);
-      const int rup = (int)floor((y - m.oy) * m.inv_res);
-      geom.pr = m.full_h - 1 - rup;
-      geom.pc = col;
-      const double ang = 2.0 * 3.141592653589793 - yaw;
-      double s, c;
-      sincos(ang, &s, &c);
-      const double N = (double)RD_OCC_IN;
-      const double b0[4] = {0.0, s * N, c * N, c * N + s * N};
-      const double b1[4] = {0.0, c * N, -s * N, -s * N + c * N};
-      double mn0 = b0[0], mx0 = b0[0], mn1 = b1[0], mx1 = b1[0];
-#pragma unroll
-      for (int k = 1; k < 4; ++k) {
-        mn0 = fmin(mn0, b0[k]); mx0 = fmax(mx0, b0[k]); mn1 = fmin(mn1, b1[k]); mx1 = fmax(mx1, b1[k]);
-      }
-      const int oh = (int)((mx0 - mn0) + 0.5), ow = (int)((mx1 - mn1) + 0.5);
-      const double oc0 = (oh - 1) / 2.0, oc1 = (ow - 1) / 2.0, ic = (N - 1.0) / 2.0;
-      geom.c = c; geom.s = s;
-      geom.off0 = ic - (c * oc0 + s * oc1);
-      geom.off1 = ic - (-s * oc0 + c * oc1);
-      geom.o0_first = oh / 2 - RD_OCC_MID / 2;
-      geom.o1_first = ow / 2 - RD_OCC_MID / 2;
-      any_hi = 0;
-      n_mixed = 0;
-    }
-    __syncthreads();
+    if (tid == 0) { any_hi = 0; n_mixed = 0; }   // first used two barriers further down
 
     // ---- A: crop bits -> smem.  word (i, j) = crop columns 32j..32j+31 of crop row i ----
     for (int t = tid; t < RD_OCC_IN * OCC_XW; t += OCC_THREADS) {
@@ -381,15 +426,14 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
     // value lies within 1.549^2 - (1.549 - 0.0933)^2 = 0.28 of the window's constant c in {0, 1} and rounds to c
     // ((uint8)(v + 0.5) = 1 for v in [0.72, 1.28], 0 for v <= 0.28).  Only a band of +-2 cells along the track walls has
     // the bit set.  Row stage: AND / OR over columns c-1 .. c+2; column stage: over rows r-1 .. r+2. ----
-    for (int t = tid; t < RD_OCC_IN * OCC_XW; t += OCC_THREADS) {
-      const int i = t / OCC_XW, j = t - i * OCC_XW;
+    // Two passes (the reductions are separable); the row results live in the not-yet-written coefficient image.
+    {
+      uint32_t* row_all = reinterpret_cast<uint32_t*>(coef);
+      uint32_t* row_any = row_all + RD_OCC_IN * OCC_XW;
       const uint32_t last_mask = (1u << (RD_OCC_IN - 32 * (OCC_XW - 1))) - 1u;       // 28 valid columns in the last word
-      uint32_t all1 = 0xffffffffu, any1 = 0u;
-#pragma unroll
-      for (int dr = -1; dr <= 2; ++dr) {
-        const int r = i + dr;
-        if (r < 0 || r >= RD_OCC_IN) continue;                                       // clipped window
-        const uint32_t* row = xb + r * OCC_XW;
+      for (int t = tid; t < RD_OCC_IN * OCC_XW; t += OCC_THREADS) {
+        const int i = t / OCC_XW, j = t - i * OCC_XW;
+        const uint32_t* row = xb + i * OCC_XW;
         const uint32_t w = row[j];
         const uint32_t lo = j > 0 ? row[j - 1] : 0u, hi = j < OCC_XW - 1 ? row[j + 1] : 0u;
         // neighbours of column c: c-1 (bit c of w << 1 | carry), c+1, c+2
@@ -399,12 +443,24 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
         const uint32_t vm1 = j == 0 ? 0xfffffffeu : 0xffffffffu;                      // column -1 does not exist
         const uint32_t vp1 = j == OCC_XW - 1 ? (last_mask >> 1) : 0xffffffffu;        // column 220 does not exist
         const uint32_t vp2 = j == OCC_XW - 1 ? (last_mask >> 2) : 0xffffffffu;        // columns 220, 221 do not exist
-        all1 &= (w | ~vw) & (m1 | ~vm1) & (p1 | ~vp1) & (p2 | ~vp2);
-        any1 |= (w & vw) | (m1 & vm1) | (p1 & vp1) | (p2 & vp2);
+        row_all[t] = (w | ~vw) & (m1 | ~vm1) & (p1 | ~vp1) & (p2 | ~vp2);
+        row_any[t] = (w & vw) | (m1 & vm1) | (p1 & vp1) | (p2 & vp2);
       }
-      uint32_t e = any1 & ~all1;
-      if (j == OCC_XW - 1) e &= last_mask;
-      eb[t] = e;
+      __syncthreads();
+      for (int t = tid; t < RD_OCC_IN * OCC_XW; t += OCC_THREADS) {
+        const int i = t / OCC_XW, j = t - i * OCC_XW;
+        uint32_t all1 = 0xffffffffu, any1 = 0u;
+#pragma unroll
+        for (int dr = -1; dr <= 2; ++dr) {
+          const int r = i + dr;
+          if (r < 0 || r >= RD_OCC_IN) continue;                                     // clipped window
+          all1 &= row_all[t + dr * OCC_XW];
+          any1 |= row_any[t + dr * OCC_XW];
+        }
+        uint32_t e = any1 & ~all1;
+        if (j == OCC_XW - 1) e &= last_mask;
+        eb[t] = e;
+      }
     }
     __syncthreads();
     // ---- A": tile classes (see the header).  One lane per tile; uniform / outside tiles get their plane bytes here,
@@ -418,23 +474,17 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
         const int ty = t / (RD_OCC_MID / 8), tx = t - ty * (RD_OCC_MID / 8);
         if (t < OCC_N_TILES) {
           const int a0 = 4 * ty, b0 = 8 * tx;
-          double lo0, hi0, lo1, hi1;
-          {
-            double p0, p1, q0, q1, r0, r1, s0, s1;
-            occ_coords(geom, a0, b0, p0, p1);
-            occ_coords(geom, a0, b0 + 7, q0, q1);
-            occ_coords(geom, a0 + 3, b0, r0, r1);
-            occ_coords(geom, a0 + 3, b0 + 7, s0, s1);
-            lo0 = fmin(fmin(p0, q0), fmin(r0, s0)); hi0 = fmax(fmax(p0, q0), fmax(r0, s0));
-            lo1 = fmin(fmin(p1, q1), fmin(r1, s1)); hi1 = fmax(fmax(p1, q1), fmax(r1, s1));
-          }
-          const double top = (double)(RD_OCC_IN - 1);
-          if (hi0 < 0.0 || lo0 > top || hi1 < 0.0 || lo1 > top) {
+          const float fa = (float)a0, fb = (float)b0;
+          const float t0 = fmaf(fa, geom.fc, fmaf(fb, geom.fs, geom.fb0));
+          const float t1 = fmaf(-fa, geom.fs, fmaf(fb, geom.fc, geom.fb1));
+          const float lo0 = t0 + geom.lo0, hi0 = t0 + geom.hi0, lo1 = t1 + geom.lo1, hi1 = t1 + geom.hi1;
+          const float top = (float)(RD_OCC_IN - 1);
+          if (hi0 < 0.0f || lo0 > top || hi1 < 0.0f || lo1 > top) {
             cls_t = 0;                                             // every pixel outside the crop: 0
-          } else if (lo0 >= 0.0 && hi0 <= top && lo1 >= 0.0 && hi1 <= top) {
+          } else if (lo0 >= 0.0f && hi0 <= top && lo1 >= 0.0f && hi1 <= top) {
             // every pixel of the tile has its floor coordinates in [r0, r1] x [q0, q1] (<= 9 x 9 cells): no near-edge bit
             // there means every pixel is the crop bit of its own cell, and those cells are all equal
-            const int r0 = (int)floor(lo0), r1 = (int)floor(hi0), q0 = (int)floor(lo1), q1 = (int)floor(hi1);
+            const int r0 = (int)floorf(lo0), r1 = (int)floorf(hi0), q0 = (int)floorf(lo1), q1 = (int)floorf(hi1);
             const uint32_t cmask = (q1 - q0 + 1 >= 32) ? 0xffffffffu : ((1u << (q1 - q0 + 1)) - 1u);
             const int wj = q0 >> 5, sh = q0 & 31;
             uint32_t any_e = 0u;
@@ -463,6 +513,7 @@ k_occupancy(const DevMap* __restrict__ maps, int map_id, const OriginRec* __rest
     }
     // ---- B: prefilter, axis 0 (columns) then axis 1 (rows), float32; image stored at padded index (r+1, c+1) ----
     __syncthreads();
+    if (have_next) occ_make_geom(m, next_pose, geom_next);                   // see gbuf
     occ_prefilter_axis<true, OCC_PITCH, 1>(coef + OCC_PITCH + 1, xb);        // lines = crop rows, from the bits
     occ_prefilter_axis<false, 1, OCC_PITCH>(coef + OCC_PITCH + 1, nullptr);  // lines = columns, in place
     // mirrored border: columns -1, 220, 221 of rows 0..219, then rows -1, 220, 221 of all 223 columns
