@@ -80,9 +80,14 @@ struct Probe {
   bool in0;          // centre inside the crop
   double c, s;       // cos / sin of the heading (reused for the observation record)
 };
+__device__ __forceinline__ void rd_probe_issue_cs(const rd_config& cfg, const DevMap& m, double x, double y, double c, double s, Probe& pr);
 __device__ __forceinline__ void rd_probe_issue(const rd_config& cfg, const DevMap& m, double x, double y, double yaw, Probe& pr) {
   double c, s;
   rdv_sincos(yaw, s, c);
+  rd_probe_issue_cs(cfg, m, x, y, c, s, pr);
+}
+// ... with the cosine / sine of the heading already known
+__device__ __forceinline__ void rd_probe_issue_cs(const rd_config& cfg, const DevMap& m, double x, double y, double c, double s, Probe& pr) {
   pr.c = c; pr.s = s;
   const double hl = 0.5 * cfg.vehicle.body_length, hw = 0.5 * cfg.vehicle.body_width;
   const double ax = hl * c, ay = hl * s, bx = hw * s, by = hw * c;
@@ -377,6 +382,209 @@ __global__ void __launch_bounds__(128) k_step(StepParams P, OutPtrs o, const flo
           for (int k = 0; k < 7; ++k) q[k] = qn[k];
           rd_probe_issue(cfg, m, q[0], q[1], q[4], pr);
         }
+      }
+      const int agent_step = agent_step0 + 1;  // TimeLimit [REF dreamer/wrappers.py:147-154]
+      int timeout = done ? tick_timeout : 0;
+      if (cfg.time_limit_steps > 0 && agent_step >= cfg.time_limit_steps) { timeout = timeout || !done; done = 1; }
+      const double ret = prs.x + total;
+      const double epi = ((double)lap + p) - 1.0;           // tools.simulate's per-step progress [REF dreamer/tools.py:195]
+      const double mp = epi > pmp.x ? epi : pmp.x;
+      if (done && !cfg.auto_reset) flags |= RD_F_NEEDS_RESET;
+      rd_write_scalars(o, e, (float)total, done, p, lap, time, flags);
+      st[6] = 1.0;
+      if (done) {
+        st[0] = 1.0; st[1] = ret; st[2] = ((double)lap + p) - prs.y;
+        st[3] = (double)agent_step; st[4] = (flags & RD_F_COLLISION) ? 1.0 : 0.0; st[5] = (double)(lap - 1);
+        st[7] = timeout ? 1.0 : 0.0; st[8] = mp;
+      }
+      if (done && cfg.auto_reset) {
+        double pz;
+        rd_reset_one(P, m, e, cfg.reset_mode, (uint32_t)jv.x, map_id, q, pz);
+        rd_write_obs(P, o, m, e, map_id, q, (uint32_t)jv.x + 1u, 0u, 1, false, 0.0, 0.0);
+      } else {
+        rd_stp(S, RD_P_XY, e, q[0], q[1]);
+        rd_stp(S, RD_P_SV, e, q[2], q[3]);
+        rd_stp(S, RD_P_YW, e, q[4], q[5]);
+        rd_stp(S, RD_P_ST, e, q[6], time);
+        rd_stp(S, RD_P_PL, e, p, last);
+        rd_stp(S, RD_P_RS, e, ret, prs.y);
+        rd_stp(S, RD_P_MP, e, mp, 0.0);
+        S.i4[e] = make_int4(lap, cp, flags, agent_step);
+        rd_write_obs(P, o, m, e, map_id, q, (uint32_t)jv.x, (uint32_t)agent_step, 0, true, hc, hs);
+      }
+    }
+  }
+  rd_stats_reduce(P.stats, st);
+}
+
+// k_step over THREE warps per 32 envs.  k_step's time is the latency of one env's in-order instruction stream (one warp
+// per SM sub-partition), and that stream holds three chains that only feed FORWARD: the five coupled vehicle states
+// (four dependent RK4 stages per tick); the position, i.e. four sine/cosine pairs per tick on the stage headings those
+// leave behind (plus the pair of the new heading for the footprint); and the footprint / progress probe, lap machine,
+// reward and termination on the resulting pose.  Warp 0 ("dynamics") integrates the coupled states of 32 envs for all R
+// ticks; warp 1 ("position") follows with the trigonometry and the position sums; warp 2 ("bookkeeping") follows with
+// k_step's own loop body -- the tick integration replaced by a read of the two shared-memory rings -- and does the
+// commit / observation / statistics epilogue.  One mbarrier per tick and ring, no back-pressure (the rings hold all
+// R <= RD_SPLIT_TICKS ticks).  Same arithmetic, operation for operation, as k_step (rdv_tick_core_t + rdv_tick_position
+// are what rdv_tick_t is made of); ticks integrated past a terminal one are simply never read.
+#define RD_SPLIT_TICKS 8
+#define RD_SPLIT_FIELDS 13   // ring 0: ang[4], vs[4], steer, v, yaw, yaw_rate, slip
+#define RD_SPLIT_POS 4       // ring 1: x, y, cos(yaw), sin(yaw) ...
+#define RD_SPLIT_PROBE 8     // ... and the footprint probe: five bit-grid words, the centre's wavefront distance, shifts + inside flag
+__device__ __forceinline__ void rd_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rd_smem_u32(bar)) : "memory");   // release.cta
+}
+__global__ void __launch_bounds__(96) k_step_split(StepParams P, OutPtrs o, const float* __restrict__ actions, int e0, int e1) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // k_lidar may start its set-up (see launch_lidar_t)
+  __shared__ __align__(16) double rg[RD_SPLIT_TICKS][RD_SPLIT_FIELDS][32];   // 26 KB
+  __shared__ __align__(16) double rp[RD_SPLIT_TICKS][RD_SPLIT_POS][32];      // 8 KB
+  __shared__ __align__(16) uint32_t rq[RD_SPLIT_TICKS][RD_SPLIT_PROBE][32];  // 8 KB
+  __shared__ __align__(8) uint64_t fb[2][RD_SPLIT_TICKS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e = e0 + blockIdx.x * 32 + lane;
+  const rd_config& cfg = P.cfg;
+  const StateRef& S = P.S;
+  const int R = cfg.action_repeat;
+  if (threadIdx.x < 2 * RD_SPLIT_TICKS) rd_mbar_init(&fb[0][0] + threadIdx.x, 32);
+  __syncthreads();
+  if (warp == 0) {
+    // ---- dynamics warp ----
+    bool live = false;
+    double q[7] = {0, 0, 0, 0, 0, 0, 0};
+    double a0 = 0.0, a1 = 0.0;
+    if (e < e1) {
+      const int4 iv = S.i4[e];
+      const float2 act = reinterpret_cast<const float2*>(actions)[e];
+      const double2 psv = rd_ldp(S, RD_P_SV, e), pyw = rd_ldp(S, RD_P_YW, e), pst = rd_ldp(S, RD_P_ST, e);
+      live = !(iv.z & RD_F_NEEDS_RESET);
+      a0 = rd_action(cfg, act.x, 0); a1 = rd_action(cfg, act.y, 1);
+      q[2] = psv.x; q[3] = psv.y; q[4] = pyw.x; q[5] = pyw.y; q[6] = pst.x;
+    }
+#pragma unroll 1
+    for (int t = 0; t < R; ++t) {
+      if (live) {
+        double ang[4], vs[4];
+        rdv_tick_core(P.vk, P.off, P.vk_g, P.off_g, q, a0, a1, ang, vs);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { rg[t][k][lane] = ang[k]; rg[t][4 + k][lane] = vs[k]; }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) rg[t][8 + k][lane] = q[2 + k];
+      }
+      rd_mbar_arrive(&fb[0][t]);
+    }
+    return;
+  }
+  if (warp == 1) {
+    // ---- position warp: x, y of every tick, the cosine / sine of the new heading, and the footprint probe's loads
+    // (issued for tick t, stored to the ring while tick t+1's trigonometry runs) ----
+    bool live = false;
+    double x = 0.0, y = 0.0;
+    int map_id = 0;
+    if (e < e1) {
+      const int4 iv = S.i4[e];
+      const int2 jv = S.i2[e];
+      const double2 pxy = rd_ldp(S, RD_P_XY, e);
+      live = !(iv.z & RD_F_NEEDS_RESET);
+      x = pxy.x; y = pxy.y;
+      map_id = jv.y;
+    }
+    const DevMap m = P.maps[map_id];
+    Probe pr{};
+    double px = 0.0, py = 0.0;
+    auto publish = [&](int t) {
+      if (live) {
+        rp[t][0][lane] = px; rp[t][1][lane] = py; rp[t][2][lane] = pr.c; rp[t][3][lane] = pr.s;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) rq[t][k][lane] = pr.w[k];
+        rq[t][5][lane] = pr.dval;
+        rq[t][6][lane] = (uint32_t)pr.sh[0] | ((uint32_t)pr.sh[1] << 5) | ((uint32_t)pr.sh[2] << 10) | ((uint32_t)pr.sh[3] << 15) |
+                         ((uint32_t)pr.sh[4] << 20) | (pr.in0 ? 0x80000000u : 0u);
+      }
+      rd_mbar_arrive(&fb[1][t]);
+    };
+#pragma unroll 1
+    for (int t = 0; t < R; ++t) {
+      rd_mbar_wait(&fb[0][t], 0);
+      double c = 1.0, s = 0.0;
+      if (live) {
+        double ang[4], vs[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { ang[k] = rg[t][k][lane]; vs[k] = rg[t][4 + k][lane]; }
+        const double yaw = rg[t][10][lane];
+        // the short trigonometric path for all five arguments when every one of them is in its range (always, unless a
+        // car has spun thousands of times): five independent chains in one straight-line block
+        const bool in_range = fabs(ang[0]) < 1.0e5 && fabs(ang[1]) < 1.0e5 && fabs(ang[2]) < 1.0e5 && fabs(ang[3]) < 1.0e5 &&
+                              fabs(yaw) < 1.0e5;
+        if (in_range) {
+          rdv_sincos_reduced(yaw, s, c);
+          rdv_tick_position<true>(P.vk, ang, vs, x, y);
+        } else {
+          rdv_sincos(yaw, s, c);
+          rdv_tick_position<false>(P.vk, ang, vs, x, y);
+        }
+      }
+      if (t > 0) publish(t - 1);          // tick t-1's loads have had this tick's trigonometry to arrive
+      if (live) rd_probe_issue_cs(cfg, m, x, y, c, s, pr);
+      px = x; py = y;
+    }
+    publish(R - 1);
+    return;
+  }
+  // ---- bookkeeping warp: k_step with the tick integration replaced by the ring ----
+  double st[RD_NSTAT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // rd_stats contributions of this env
+  if (e < e1) {
+    const int4 iv = S.i4[e];
+    const int2 jv = S.i2[e];
+    const float2 act = reinterpret_cast<const float2*>(actions)[e];
+    const double2 pxy = rd_ldp(S, RD_P_XY, e), psv = rd_ldp(S, RD_P_SV, e), pyw = rd_ldp(S, RD_P_YW, e);
+    const double2 pst = rd_ldp(S, RD_P_ST, e), ppl = rd_ldp(S, RD_P_PL, e), prs = rd_ldp(S, RD_P_RS, e);
+    const double2 pmp = rd_ldp(S, RD_P_MP, e);
+    int lap = iv.x, cp = iv.y, flags = iv.z;
+    const int agent_step0 = iv.w, map_id = jv.y;
+    double time = pst.y, p = ppl.x, last = ppl.y;
+    if (flags & RD_F_NEEDS_RESET) {  // frozen until reset [REF dreamer/wrappers.py:148]
+      rd_write_scalars(o, e, 0.f, 1, p, lap, time, flags);
+      P.recs[e].was_reset = 2;
+    } else {
+      const DevMap m = P.maps[map_id];   // the track descriptor lives in registers for the whole step
+      const double a1 = rd_action(cfg, act.y, 1);
+      double q[7] = {pxy.x, pxy.y, psv.x, psv.y, pyw.x, pyw.y, pst.x};
+      double total = 0.0;
+      int done = 0, tick_timeout = 0;
+      double hc = 0.0, hs = 0.0;
+#pragma unroll 1
+      for (int t = 1; t <= R; ++t) {      // t ticks done, as in k_step's bookkeeping half
+        rd_mbar_wait(&fb[1][t - 1], 0);   // acquire: the position warp's tick (and with it the dynamics warp's) is there
+        Probe pr;
+        q[0] = rp[t - 1][0][lane]; q[1] = rp[t - 1][1][lane]; pr.c = rp[t - 1][2][lane]; pr.s = rp[t - 1][3][lane];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) q[2 + k] = rg[t - 1][8 + k][lane];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) pr.w[k] = rq[t - 1][k][lane];
+        pr.dval = rq[t - 1][5][lane];
+        const uint32_t packed = rq[t - 1][6][lane];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) pr.sh[k] = (int)((packed >> (5 * k)) & 31u);
+        pr.in0 = (packed >> 31) != 0u;
+        time = time + cfg.dt;
+        bool col, inside;
+        rd_probe_finish(m, pr, col, inside, p);
+        hc = pr.c; hs = pr.s;
+        flags &= ~(RD_F_COLLISION | RD_F_LEFT_MAP);
+        if (col) flags |= RD_F_COLLISION;
+        if (!inside) flags |= RD_F_LEFT_MAP;
+        if (!(q[0] == q[0] && q[1] == q[1] && q[3] == q[3] && q[4] == q[4])) flags |= RD_F_NAN;
+        rd_lap_machine(cfg, p, lap, cp, flags);
+        const double cur = (double)lap + p;
+        bool d;
+        const double r = rd_task_reward(cfg, cfg.task, col, cur, last, a1, q[3], q[6], lap, time, d);
+        if (cfg.time_limit_ticks > 0 && agent_step0 * R + t >= cfg.time_limit_ticks) { tick_timeout = !d; d = true; }
+        last = cur;
+        total = total + r;
+        // dreamer: stop at the first done [REF dreamer/wrappers.py:112]; baselines: the done of the first tick is not
+        // tested when more ticks follow [REF baselines/racing/environment/single_agent.py:32-38]
+        if (d && !(cfg.repeat_semantics == RD_REPEAT_BASELINES && t == 1 && R > 1)) { done = 1; break; }
+        tick_timeout = 0;
       }
       const int agent_step = agent_step0 + 1;  // TimeLimit [REF dreamer/wrappers.py:147-154]
       int timeout = done ? tick_timeout : 0;

@@ -57,6 +57,7 @@ struct rd_env {
   bool lidar_attr_set[12] = {};   // k_lidar<16|24|32, ahead, cars> opted in to smem_optin
   int n = 0;
   int step_block = 128;           // k_step threads per CTA (small batches: fewer, so that every SM gets a warp)
+  bool step_split = true;         // k_step_split (two warps per 32 envs) while the batch is latency-bound; RD_STEP_SPLIT overrides
   double2* d_f2 = nullptr;        // env state, SoA of 16-byte groups (rd_dynamics.cuh StateRef)
   int4* d_i4 = nullptr;
   int2* d_i2 = nullptr;
@@ -428,6 +429,10 @@ int launch_step(rd_env* env, const rd_outputs* out, const float* actions_dev, cu
       const int per_cta = (tb / A) * A;
       lc.gridDim = dim3((unsigned)((env->n + per_cta - 1) / per_cta)); lc.blockDim = dim3(tb);
       le = cudaLaunchKernelEx(&lc, k_step_ma, P, o, actions_dev);
+    } else if (env->step_split && env->cfg.action_repeat <= RD_SPLIT_TICKS) {
+      // three warps per 32 envs (dynamics | position | bookkeeping): shortens the per-env latency chain k_step is bound by
+      lc.gridDim = dim3((unsigned)((env->n + 31) / 32)); lc.blockDim = dim3(96);
+      le = cudaLaunchKernelEx(&lc, k_step_split, P, o, actions_dev, 0, env->n);
     } else {
       lc.gridDim = dim3((unsigned)((env->n + tb - 1) / tb)); lc.blockDim = dim3(tb);
       le = cudaLaunchKernelEx(&lc, k_step, P, o, actions_dev, 0, env->n);
@@ -565,6 +570,8 @@ RD_API int rd_create(const rd_config* cfg, rd_env** out) {
   env->step_block = (env->n >= 128 * 4 * env->sm_count) ? 128 : ((env->n >= 64 * 4 * env->sm_count) ? 64 : 32);
   if (const char* ev = std::getenv("RD_LIDAR_PDL")) env->lidar_pdl = std::atoi(ev) != 0;
   if (const char* ev = std::getenv("RD_LIDAR_ORDER")) env->lidar_centre_first = std::atoi(ev) != 0;
+  env->step_split = env->n < 64 * 4 * env->sm_count;   // larger batches are throughput-bound: one warp per 32 envs does less work
+  if (const char* ev = std::getenv("RD_STEP_SPLIT")) env->step_split = std::atoi(ev) != 0;
   if (const char* ev = std::getenv("RD_STEP_BLOCK")) { int v = std::atoi(ev); if (v == 32 || v == 64 || v == 128) env->step_block = v; }
   const size_t n = (size_t)env->n;
   cudaError_t e = cudaSuccess;

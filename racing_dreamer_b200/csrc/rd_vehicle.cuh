@@ -294,35 +294,15 @@ RDV_HD void rdv_heading(double ang, double& sn, double& cn) {
   else rdv_sincos_slow(ang, &sn, &cn);
 }
 
-// one 10 ms tick under the sim-facing command (motor, steering): classical RK4.
-// RD_TICK_ROLLED = 1: the four stages share ONE copy of the RHS code (stage input q + c*k with c = (0, h/2, h/2, h), sum
-// of w*k with w = (1, 2, 2, 1): the same values, products by 0, 1 and 2 being exact) -- a quarter of the code for the
-// instruction cache at the price of a few selects per stage; 0: four inlined copies.
-#ifndef RD_TICK_ROLLED
-#define RD_TICK_ROLLED 0
-#endif
+// One tick of the five coupled states (steer, v, yaw, yaw_rate, slip), stage after stage; q[0], q[1] are not touched.
+// The four stage headings `ang` and speeds `vs` it leaves behind are all the position update needs (rdv_tick_position):
+// the position never feeds back, so the values are those of the textbook stage-by-stage form, bit for bit -- and the
+// two halves can run in different warps (k_step_split, rd_dynamics.cuh).
 template <bool FAST>
-RDV_HD void rdv_tick_t(const VehConst& k, const VehAcc& off, double (&q)[7], double motor, double steering) {
+RDV_HD void rdv_tick_core_t(const VehConst& k, const VehAcc& off, double (&q)[7], double motor, double steering,
+                            double (&ang)[4], double (&vs)[4]) {
   const VehCmd c = rdv_command(k, q, motor, steering);
-#if RD_TICK_ROLLED
-  double kk[7] = {0, 0, 0, 0, 0, 0, 0}, acc[7] = {0, 0, 0, 0, 0, 0, 0}, t[7];
-#pragma unroll 1
-  for (int st = 0; st < 4; ++st) {
-    const double cs = st == 0 ? 0.0 : (st == 3 ? k.dt : k.h2);
-    const double w = (st == 0 || st == 3) ? 1.0 : 2.0;
-#pragma unroll
-    for (int i = 0; i < 7; ++i) t[i] = fma(cs, kk[i], q[i]);
-    rdv_rhs<FAST>(k, c, off, t, kk);
-#pragma unroll
-    for (int i = 0; i < 7; ++i) acc[i] = fma(w, kk[i], acc[i]);
-  }
-#pragma unroll
-  for (int i = 0; i < 7; ++i) q[i] = fma(k.h6, acc[i], q[i]);
-#else
-  // The five coupled derivatives first, stage after stage; the four headings and speeds they leave behind feed four
-  // INDEPENDENT sine / cosine evaluations afterwards (one straight-line block the scheduler can interleave) -- the
-  // position never feeds back, so the values are those of the textbook stage-by-stage form, bit for bit.
-  double kk[7], acc[7], t[7], ang[4], vs[4];
+  double kk[7], acc[7], t[7];
 #pragma unroll
   for (int i = 0; i < 7; ++i) t[i] = q[i];
   vs[0] = t[3];
@@ -341,14 +321,49 @@ RDV_HD void rdv_tick_t(const VehConst& k, const VehAcc& off, double (&q)[7], dou
   rdv_rhs_core<FAST>(k, c, off, t, kk, ang[3]);
 #pragma unroll
   for (int i = 2; i < 7; ++i) q[i] = fma(k.h6, acc[i] + kk[i], q[i]);
+}
+// x, y: k_s = v_s (cos, sin)(ang_s);  q += h/6 (((k1 + 2 k2) + 2 k3) + k4).  Four INDEPENDENT sine / cosine evaluations
+// (one straight-line block the scheduler can interleave).  FAST = false guards each argument (|ang| < 1e5: the same
+// short path, same bits; beyond: the library).
+template <bool FAST>
+RDV_HD void rdv_tick_position(const VehConst& k, const double (&ang)[4], const double (&vs)[4], double& x, double& y) {
   double sn[4], cn[4];
 #pragma unroll
   for (int st = 0; st < 4; ++st) rdv_heading<FAST>(ang[st], sn[st], cn[st]);
-  // x, y: k_s = v_s (cos, sin)(ang_s);  q += h/6 (((k1 + 2 k2) + 2 k3) + k4)
   const double ax = fma(2.0, vs[2] * cn[2], fma(2.0, vs[1] * cn[1], vs[0] * cn[0]));
   const double ay = fma(2.0, vs[2] * sn[2], fma(2.0, vs[1] * sn[1], vs[0] * sn[0]));
-  q[0] = fma(k.h6, ax + vs[3] * cn[3], q[0]);
-  q[1] = fma(k.h6, ay + vs[3] * sn[3], q[1]);
+  x = fma(k.h6, ax + vs[3] * cn[3], x);
+  y = fma(k.h6, ay + vs[3] * sn[3], y);
+}
+
+// one 10 ms tick under the sim-facing command (motor, steering): classical RK4.
+// RD_TICK_ROLLED = 1: the four stages share ONE copy of the RHS code (stage input q + c*k with c = (0, h/2, h/2, h), sum
+// of w*k with w = (1, 2, 2, 1): the same values, products by 0, 1 and 2 being exact) -- a quarter of the code for the
+// instruction cache at the price of a few selects per stage; 0: four inlined copies.
+#ifndef RD_TICK_ROLLED
+#define RD_TICK_ROLLED 0
+#endif
+template <bool FAST>
+RDV_HD void rdv_tick_t(const VehConst& k, const VehAcc& off, double (&q)[7], double motor, double steering) {
+#if RD_TICK_ROLLED
+  const VehCmd c = rdv_command(k, q, motor, steering);
+  double kk[7] = {0, 0, 0, 0, 0, 0, 0}, acc[7] = {0, 0, 0, 0, 0, 0, 0}, t[7];
+#pragma unroll 1
+  for (int st = 0; st < 4; ++st) {
+    const double cs = st == 0 ? 0.0 : (st == 3 ? k.dt : k.h2);
+    const double w = (st == 0 || st == 3) ? 1.0 : 2.0;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) t[i] = fma(cs, kk[i], q[i]);
+    rdv_rhs<FAST>(k, c, off, t, kk);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) acc[i] = fma(w, kk[i], acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 7; ++i) q[i] = fma(k.h6, acc[i], q[i]);
+#else
+  double ang[4], vs[4];
+  rdv_tick_core_t<FAST>(k, off, q, motor, steering, ang, vs);
+  rdv_tick_position<FAST>(k, ang, vs, q[0], q[1]);
 #endif
 }
 // the general tick, out of line: any heading, any steering angle, vehicles that reach v_switch
@@ -367,4 +382,19 @@ RDV_HD void rdv_tick(const VehConst& k, const VehAcc& off, const VehConst* kg, c
   const bool fast = !k.has_switch && fabs(q[4]) < 9.0e4 && fabs(q[6]) < 1.0e3 && fabs(q[5]) < 1.0e3 && fabs(q[2]) < 0.6;
   if (fast) rdv_tick_t<true>(k, off, q, motor, steering);
   else rdv_tick_slow(kg, offg, q, motor, steering);
+}
+// The same tick without the position: the coupled states advance, the stage headings / speeds are handed out.
+RDV_NOINLINE void rdv_tick_core_slow(const VehConst* k, const VehAcc* off, double* q, double motor, double steering,
+                                     double* ang, double* vs) {
+  double r[7], a[4], v[4];
+  for (int i = 0; i < 7; ++i) r[i] = q[i];
+  rdv_tick_core_t<false>(*k, *off, r, motor, steering, a, v);
+  for (int i = 2; i < 7; ++i) q[i] = r[i];
+  for (int i = 0; i < 4; ++i) { ang[i] = a[i]; vs[i] = v[i]; }
+}
+RDV_HD void rdv_tick_core(const VehConst& k, const VehAcc& off, const VehConst* kg, const VehAcc* offg, double (&q)[7],
+                          double motor, double steering, double (&ang)[4], double (&vs)[4]) {
+  const bool fast = !k.has_switch && fabs(q[4]) < 9.0e4 && fabs(q[6]) < 1.0e3 && fabs(q[5]) < 1.0e3 && fabs(q[2]) < 0.6;
+  if (fast) rdv_tick_core_t<true>(k, off, q, motor, steering, ang, vs);
+  else rdv_tick_core_slow(kg, offg, q, motor, steering, ang, vs);
 }
