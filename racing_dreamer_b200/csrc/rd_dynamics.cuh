@@ -165,16 +165,16 @@ __device__ __forceinline__ double rd_action(const rd_config& cfg, float af, int 
 // reset of one env: pose from the map's tables (grid slot or a Philox-sampled candidate); writes the whole state and
 // returns the pose in q (all rates zero) [REF dreamer/wrappers.py:91-92 reset(mode=...); sampler itself is racecar_gym
 // -> NEW-SPEC]
-__device__ __forceinline__ void rd_reset_one(const StepParams& P, const DevMap& m, int e, int mode, uint32_t episode,
-                                             int map_id, double (&q)[7], double& p_out) {
+// ... the pose and its progress (reads only: the same (env, episode) always yields the same pose, so k_step_split looks
+// it up ahead of time for every env)
+__device__ __forceinline__ void rd_reset_pose(const StepParams& P, const DevMap& m, int e, int mode, uint32_t episode,
+                                              double& x, double& y, double& yaw, double& p) {
   const rd_config& cfg = P.cfg;
-  const int n = P.n;
   // multi-agent worlds: the cars of a world draw ONE anchor (counter = global id of the world's agent 0) and line up
   // along the ball_next chain (cfg.ball_spacing metres of track apart); 'grid' hands out the staggered start slots
   const int A = cfg.agents_per_world > 1 ? cfg.agents_per_world : 1;
   const int a = e % A;
   const uint64_t gid = (uint64_t)(cfg.env_id_offset + (e - a));
-  double x, y, yaw;
   if (mode == RD_RESET_GRID || m.n_reset <= 0) {
     const int slot = a < m.n_start ? a : m.n_start - 1;
     x = m.start[3 * slot]; y = m.start[3 * slot + 1]; yaw = m.start[3 * slot + 2];
@@ -186,8 +186,14 @@ __device__ __forceinline__ void rd_reset_one(const StepParams& P, const DevMap& 
     x = m.reset[3 * idx]; y = m.reset[3 * idx + 1]; yaw = m.reset[3 * idx + 2];
     if (mode == RD_RESET_RANDOM_BIDIRECTIONAL && (c[1] & 1u)) yaw = yaw + 3.14159265358979323846;
   }
-  double p = 0.0;
+  p = 0.0;
   rd_progress_at(m, x, y, p);
+}
+// ... and the state it leaves behind
+__device__ __forceinline__ void rd_reset_commit(const StepParams& P, int e, uint32_t episode, int map_id, double x, double y,
+                                                double yaw, double p, double (&q)[7]) {
+  const rd_config& cfg = P.cfg;
+  const int n = P.n;
   const StateRef& S = P.S;
   rd_stp(S, RD_P_XY, e, x, y);
   rd_stp(S, RD_P_SV, e, 0.0, 0.0);
@@ -201,24 +207,34 @@ __device__ __forceinline__ void rd_reset_one(const StepParams& P, const DevMap& 
   if (P.hist) for (int k = 0; k < cfg.n_step_progress; ++k) P.hist[(size_t)k * n + e] = 1.0 + p;
   if (P.pol.i32 || P.pol.dr_feat) rd_policy_clear(P.pol, n, e);
   q[0] = x; q[1] = y; q[2] = 0.0; q[3] = 0.0; q[4] = yaw; q[5] = 0.0; q[6] = 0.0;
+}
+__device__ __forceinline__ void rd_reset_one(const StepParams& P, const DevMap& m, int e, int mode, uint32_t episode,
+                                             int map_id, double (&q)[7], double& p_out) {
+  double x, y, yaw, p;
+  rd_reset_pose(P, m, e, mode, episode, x, y, yaw, p);
+  rd_reset_commit(P, e, episode, map_id, x, y, yaw, p, q);
   p_out = p;
 }
 
 // observation scalars + the origin record for the LiDAR / occupancy kernels, from the committed pose.
 // have_cs: (c, s) = cos / sin of q[4] are already known (the last tick's footprint probe)
-__device__ __forceinline__ void rd_write_obs(const StepParams& P, const OutPtrs& o, const DevMap& m, int e, int map_id,
-                                             const double (&q)[7], uint32_t episode, uint32_t agent_step, int was_reset,
-                                             bool have_cs, double c, double s) {
+struct ObsVals {            // what one env's step hands to the observation kernels and to the caller
+  OriginRec rec;
+  float pose[6], vel[6], speed;
+};
+#define RD_OBS_WORDS 25     // 12 (record) + 6 + 6 + 1 32-bit words
+__device__ __forceinline__ void rd_obs_compute(const StepParams& P, const DevMap& m, int e, int map_id, const double (&q)[7],
+                                               uint32_t episode, uint32_t agent_step, int was_reset, bool have_cs, double c,
+                                               double s, ObsVals& ov) {
   const double x = q[0], y = q[1], yaw = q[4], v = q[3], slip = q[6];
   if (!have_cs) rdv_sincos(yaw, s, c);
-  OriginRec rec;
+  OriginRec& rec = ov.rec;
   rd_make_origin_cs(m, x, y, c, s, P.cfg.lidar_offset, rec);
   rec.gid = (uint32_t)(P.cfg.env_id_offset + e);   // noise counter: the low 32 bits of the global env id
   rec.episode = episode;
   rec.step = agent_step;
   rec.was_reset = was_reset;
   rec.pad = map_id;
-  P.recs[e] = rec;
   const double two_pi = 6.283185307179586;
   const double wy = yaw - rint(yaw / two_pi) * two_pi;
   double ss, cs;
@@ -228,35 +244,35 @@ __device__ __forceinline__ void rd_write_obs(const StepParams& P, const OutPtrs&
   if (P.norm) {   // NormalizeObservations: (x - low) * scaler in float64, then float32 [REF baselines single_agent.py:92-99]
     const double pl = P.norm_lo[RD_NORM_POSE], psc = P.norm_sc[RD_NORM_POSE];
     const double vl = P.norm_lo[RD_NORM_VELOCITY], vsc = P.norm_sc[RD_NORM_VELOCITY];
-    if (o.pose) {
-      float2* p2 = reinterpret_cast<float2*>(o.pose + (size_t)e * 6);   // rows are 24 bytes: 8-byte aligned float2 stores
-      const float z = (float)((0.0 - pl) * psc);
-      p2[0] = make_float2((float)((x - pl) * psc), (float)((y - pl) * psc));
-      p2[1] = make_float2(z, z);
-      p2[2] = make_float2(z, (float)((wy - pl) * psc));
-    }
-    if (o.velocity) {
-      float2* q2 = reinterpret_cast<float2*>(o.velocity + (size_t)e * 6);
-      const float z = (float)((0.0 - vl) * vsc);
-      q2[0] = make_float2((float)((vx - vl) * vsc), (float)((vy - vl) * vsc));
-      q2[1] = make_float2(z, z);
-      q2[2] = make_float2(z, (float)((yr - vl) * vsc));
-    }
+    const float zp = (float)((0.0 - pl) * psc), zv = (float)((0.0 - vl) * vsc);
+    ov.pose[0] = (float)((x - pl) * psc); ov.pose[1] = (float)((y - pl) * psc);
+    ov.pose[2] = zp; ov.pose[3] = zp; ov.pose[4] = zp; ov.pose[5] = (float)((wy - pl) * psc);
+    ov.vel[0] = (float)((vx - vl) * vsc); ov.vel[1] = (float)((vy - vl) * vsc);
+    ov.vel[2] = zv; ov.vel[3] = zv; ov.vel[4] = zv; ov.vel[5] = (float)((yr - vl) * vsc);
   } else {
-    if (o.pose) {
-      float2* p2 = reinterpret_cast<float2*>(o.pose + (size_t)e * 6);
-      p2[0] = make_float2((float)x, (float)y);
-      p2[1] = make_float2(0.f, 0.f);
-      p2[2] = make_float2(0.f, (float)wy);
-    }
-    if (o.velocity) {
-      float2* q2 = reinterpret_cast<float2*>(o.velocity + (size_t)e * 6);
-      q2[0] = make_float2((float)vx, (float)vy);
-      q2[1] = make_float2(0.f, 0.f);
-      q2[2] = make_float2(0.f, (float)yr);
-    }
+    ov.pose[0] = (float)x; ov.pose[1] = (float)y; ov.pose[2] = 0.f; ov.pose[3] = 0.f; ov.pose[4] = 0.f; ov.pose[5] = (float)wy;
+    ov.vel[0] = (float)vx; ov.vel[1] = (float)vy; ov.vel[2] = 0.f; ov.vel[3] = 0.f; ov.vel[4] = 0.f; ov.vel[5] = (float)yr;
   }
-  if (o.speed) o.speed[e] = (float)sqrt(vx * vx + vy * vy);  // [REF dreamer/wrappers.py:66]
+  ov.speed = (float)sqrt(vx * vx + vy * vy);  // [REF dreamer/wrappers.py:66]
+}
+__device__ __forceinline__ void rd_obs_store(const StepParams& P, const OutPtrs& o, int e, const ObsVals& ov) {
+  P.recs[e] = ov.rec;
+  if (o.pose) {
+    float2* p2 = reinterpret_cast<float2*>(o.pose + (size_t)e * 6);   // rows are 24 bytes: 8-byte aligned float2 stores
+    p2[0] = make_float2(ov.pose[0], ov.pose[1]); p2[1] = make_float2(ov.pose[2], ov.pose[3]); p2[2] = make_float2(ov.pose[4], ov.pose[5]);
+  }
+  if (o.velocity) {
+    float2* q2 = reinterpret_cast<float2*>(o.velocity + (size_t)e * 6);
+    q2[0] = make_float2(ov.vel[0], ov.vel[1]); q2[1] = make_float2(ov.vel[2], ov.vel[3]); q2[2] = make_float2(ov.vel[4], ov.vel[5]);
+  }
+  if (o.speed) o.speed[e] = ov.speed;
+}
+__device__ __forceinline__ void rd_write_obs(const StepParams& P, const OutPtrs& o, const DevMap& m, int e, int map_id,
+                                             const double (&q)[7], uint32_t episode, uint32_t agent_step, int was_reset,
+                                             bool have_cs, double c, double s) {
+  ObsVals ov;
+  rd_obs_compute(P, m, e, map_id, q, episode, agent_step, was_reset, have_cs, c, s, ov);
+  rd_obs_store(P, o, e, ov);
 }
 
 __device__ __forceinline__ void rd_write_scalars(const OutPtrs& o, int e, float reward, int done, double p, int lap,
@@ -417,36 +433,77 @@ __global__ void __launch_bounds__(128) k_step(StepParams P, OutPtrs o, const flo
   rd_stats_reduce(P.stats, st);
 }
 
-// k_step over THREE warps per 32 envs.  k_step's time is the latency of one env's in-order instruction stream (one warp
-// per SM sub-partition), and that stream holds three chains that only feed FORWARD: the five coupled vehicle states
-// (four dependent RK4 stages per tick); the position, i.e. four sine/cosine pairs per tick on the stage headings those
-// leave behind (plus the pair of the new heading for the footprint); and the footprint / progress probe, lap machine,
-// reward and termination on the resulting pose.  Warp 0 ("dynamics") integrates the coupled states of 32 envs for all R
-// ticks; warp 1 ("position") follows with the trigonometry and the position sums; warp 2 ("bookkeeping") follows with
-// k_step's own loop body -- the tick integration replaced by a read of the two shared-memory rings -- and does the
-// commit / observation / statistics epilogue.  One mbarrier per tick and ring, no back-pressure (the rings hold all
-// R <= RD_SPLIT_TICKS ticks).  Same arithmetic, operation for operation, as k_step (rdv_tick_core_t + rdv_tick_position
-// are what rdv_tick_t is made of); ticks integrated past a terminal one are simply never read.
+// k_step over FOUR warps per 32 envs.  k_step's time is the latency of one env's in-order instruction stream (one warp
+// per SM sub-partition), and that stream holds chains that only feed FORWARD:
+//   warp 0 "dynamics"     the five coupled vehicle states, four dependent RK4 stages per tick, for all R ticks;
+//   warp 1 "position"     four sine/cosine pairs per tick on the stage headings those leave behind -> x, y;
+//   warp 2 "probe"        cosine/sine of the new heading, the footprint's five cells, their bit-grid / wavefront loads
+//                         (issued for tick t, stored while tick t+1's arithmetic runs); after the last tick it writes the
+//                         observation scalars and the LiDAR origin record of the state after R ticks -- what the step
+//                         returns unless the env finishes, which warp 3 then overwrites;
+//   warp 3 "bookkeeping"  k_step's own per-tick body (lap machine, reward, termination) on what the rings hold, then
+//                         scalars, commit, statistics, and the observation of the envs that finished or were reset;
+//   warp 4 "reset"        (auto-reset only) looks up, right at the start, the pose every env WOULD be reset to -- a
+//                         pure function of (env, episode) -- with its progress and its observation record: three
+//                         dependent map loads and a general sine/cosine that would otherwise sit, for the few lanes
+//                         that finish, at the very end of their whole warp's critical path (88 of 128 CTAs had such a
+//                         lane in a config-2 step; it cost them 3.6 us).
+// One mbarrier per tick and ring, no back-pressure (the rings hold all R <= RD_SPLIT_TICKS ticks).  Same arithmetic,
+// operation for operation, as k_step (rdv_tick_core_t + rdv_tick_position are what rdv_tick_t is made of); ticks
+// integrated past a terminal one are simply never read.
 #define RD_SPLIT_TICKS 8
 #define RD_SPLIT_FIELDS 13   // ring 0: ang[4], vs[4], steer, v, yaw, yaw_rate, slip
-#define RD_SPLIT_POS 4       // ring 1: x, y, cos(yaw), sin(yaw) ...
-#define RD_SPLIT_PROBE 8     // ... and the footprint probe: five bit-grid words, the centre's wavefront distance, shifts + inside flag
+#define RD_SPLIT_PROBE 8     // ring 2: five bit-grid words, the centre's wavefront distance, shifts + inside flag
 __device__ __forceinline__ void rd_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rd_smem_u32(bar)) : "memory");   // release.cta
 }
-__global__ void __launch_bounds__(96) k_step_split(StepParams P, OutPtrs o, const float* __restrict__ actions, int e0, int e1) {
+#ifdef RD_SPLIT_TRACE   // tuning: per-warp time stamps (cycles since the CTA started) of one CTA, printed at the end
+#define RD_TR(i) do { if (lane == 0 && blockIdx.x == 5 && (i) < 24) tr[warp][(i)] = clock64() - t_begin; } while (0)
+#define RD_TR_DUMP(n) do { if (lane == 0 && blockIdx.x == 5) { printf("[k_step_split warp %d]", warp); for (int i_ = 0; i_ < (n); ++i_) printf(" %lld", tr[warp][i_]); printf("\n"); } } while (0)
+#else
+#define RD_TR(i) do {} while (0)
+#define RD_TR_DUMP(n) do {} while (0)
+#endif
+__global__ void __launch_bounds__(160) k_step_split(StepParams P, OutPtrs o, const float* __restrict__ actions, int e0, int e1) {
+#ifdef RD_SPLIT_TRACE
+  __shared__ long long tr[4][24];
+  const long long t_begin = clock64();
+#endif
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // k_lidar may start its set-up (see launch_lidar_t)
-  __shared__ __align__(16) double rg[RD_SPLIT_TICKS][RD_SPLIT_FIELDS][32];   // 26 KB
-  __shared__ __align__(16) double rp[RD_SPLIT_TICKS][RD_SPLIT_POS][32];      // 8 KB
-  __shared__ __align__(16) uint32_t rq[RD_SPLIT_TICKS][RD_SPLIT_PROBE][32];  // 8 KB
-  __shared__ __align__(8) uint64_t fb[2][RD_SPLIT_TICKS];
+  __shared__ __align__(16) double rg[RD_SPLIT_TICKS][RD_SPLIT_FIELDS][32];   // 26 KB  warp 0 -> 1, 2, 3
+  __shared__ __align__(16) double rp[RD_SPLIT_TICKS][2][32];                 // 4 KB   warp 1 -> 2, 3: x, y
+  __shared__ __align__(16) double rc[RD_SPLIT_TICKS][2][32];                 // 4 KB   warp 2 -> 3: cos, sin of the heading
+  __shared__ __align__(16) uint32_t rq[RD_SPLIT_TICKS][RD_SPLIT_PROBE][32];  // 8 KB   warp 2 -> 3: the probe
+  __shared__ __align__(16) double rs[4][32];                                 // 1 KB   warp 4 -> 3: reset pose x, y, yaw, progress
+  __shared__ __align__(16) uint32_t ro[RD_OBS_WORDS][32];                    // 3 KB   warp 4 -> 3: its observation (ObsVals)
+  __shared__ __align__(8) uint64_t fb[3][RD_SPLIT_TICKS];
+  __shared__ __align__(8) uint64_t obs_bar, rst_bar;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = e0 + blockIdx.x * 32 + lane;
   const rd_config& cfg = P.cfg;
   const StateRef& S = P.S;
   const int R = cfg.action_repeat;
-  if (threadIdx.x < 2 * RD_SPLIT_TICKS) rd_mbar_init(&fb[0][0] + threadIdx.x, 32);
+  if (threadIdx.x < 3 * RD_SPLIT_TICKS) rd_mbar_init(&fb[0][0] + threadIdx.x, 32);
+  if (threadIdx.x == 3 * RD_SPLIT_TICKS) { rd_mbar_init(&obs_bar, 32); rd_mbar_init(&rst_bar, 32); }
   __syncthreads();
+  if (warp == 4) {
+    // ---- reset warp ----
+    if (cfg.auto_reset && e < e1) {
+      const int2 jv = S.i2[e];
+      const DevMap m = P.maps[jv.y];
+      double x, y, yaw, p;
+      rd_reset_pose(P, m, e, cfg.reset_mode, (uint32_t)jv.x, x, y, yaw, p);
+      const double q[7] = {x, y, 0.0, 0.0, yaw, 0.0, 0.0};
+      ObsVals ov;
+      rd_obs_compute(P, m, e, jv.y, q, (uint32_t)jv.x + 1u, 0u, 1, false, 0.0, 0.0, ov);
+      rs[0][lane] = x; rs[1][lane] = y; rs[2][lane] = yaw; rs[3][lane] = p;
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&ov);
+#pragma unroll
+      for (int k = 0; k < RD_OBS_WORDS; ++k) ro[k][lane] = w[k];
+    }
+    rd_mbar_arrive(&rst_bar);
+    return;
+  }
   if (warp == 0) {
     // ---- dynamics warp ----
     bool live = false;
@@ -460,6 +517,7 @@ __global__ void __launch_bounds__(96) k_step_split(StepParams P, OutPtrs o, cons
       a0 = rd_action(cfg, act.x, 0); a1 = rd_action(cfg, act.y, 1);
       q[2] = psv.x; q[3] = psv.y; q[4] = pyw.x; q[5] = pyw.y; q[6] = pst.x;
     }
+    RD_TR(0);
 #pragma unroll 1
     for (int t = 0; t < R; ++t) {
       if (live) {
@@ -471,63 +529,88 @@ __global__ void __launch_bounds__(96) k_step_split(StepParams P, OutPtrs o, cons
         for (int k = 0; k < 5; ++k) rg[t][8 + k][lane] = q[2 + k];
       }
       rd_mbar_arrive(&fb[0][t]);
+      RD_TR(1 + t);
     }
+    RD_TR_DUMP(1 + R);
     return;
   }
   if (warp == 1) {
-    // ---- position warp: x, y of every tick, the cosine / sine of the new heading, and the footprint probe's loads
-    // (issued for tick t, stored to the ring while tick t+1's trigonometry runs) ----
+    // ---- position warp ----
     bool live = false;
     double x = 0.0, y = 0.0;
-    int map_id = 0;
     if (e < e1) {
       const int4 iv = S.i4[e];
-      const int2 jv = S.i2[e];
       const double2 pxy = rd_ldp(S, RD_P_XY, e);
       live = !(iv.z & RD_F_NEEDS_RESET);
       x = pxy.x; y = pxy.y;
-      map_id = jv.y;
+    }
+#pragma unroll 1
+    for (int t = 0; t < R; ++t) {
+      rd_mbar_wait(&fb[0][t], 0);
+      if (live) {
+        double ang[4], vs[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { ang[k] = rg[t][k][lane]; vs[k] = rg[t][4 + k][lane]; }
+        // the short trigonometric path when every argument is in its range (always, unless a car has spun thousands of
+        // times): four independent chains in one straight-line block
+        const bool in_range = fabs(ang[0]) < 1.0e5 && fabs(ang[1]) < 1.0e5 && fabs(ang[2]) < 1.0e5 && fabs(ang[3]) < 1.0e5;
+        if (in_range) rdv_tick_position<true>(P.vk, ang, vs, x, y);
+        else rdv_tick_position<false>(P.vk, ang, vs, x, y);
+        rp[t][0][lane] = x; rp[t][1][lane] = y;
+      }
+      rd_mbar_arrive(&fb[1][t]);
+      RD_TR(1 + t);
+    }
+    RD_TR_DUMP(1 + R);
+    return;
+  }
+  if (warp == 2) {
+    // ---- probe warp ----
+    bool live = false;
+    int map_id = 0, episode = 0, agent_step0 = 0;
+    if (e < e1) {
+      const int4 iv = S.i4[e];
+      const int2 jv = S.i2[e];
+      live = !(iv.z & RD_F_NEEDS_RESET);
+      agent_step0 = iv.w; episode = jv.x; map_id = jv.y;
     }
     const DevMap m = P.maps[map_id];
     Probe pr{};
-    double px = 0.0, py = 0.0;
+    double qf[7] = {0, 0, 0, 0, 0, 0, 0};
     auto publish = [&](int t) {
       if (live) {
-        rp[t][0][lane] = px; rp[t][1][lane] = py; rp[t][2][lane] = pr.c; rp[t][3][lane] = pr.s;
+        rc[t][0][lane] = pr.c; rc[t][1][lane] = pr.s;
 #pragma unroll
         for (int k = 0; k < 5; ++k) rq[t][k][lane] = pr.w[k];
         rq[t][5][lane] = pr.dval;
         rq[t][6][lane] = (uint32_t)pr.sh[0] | ((uint32_t)pr.sh[1] << 5) | ((uint32_t)pr.sh[2] << 10) | ((uint32_t)pr.sh[3] << 15) |
                          ((uint32_t)pr.sh[4] << 20) | (pr.in0 ? 0x80000000u : 0u);
       }
-      rd_mbar_arrive(&fb[1][t]);
+      rd_mbar_arrive(&fb[2][t]);
     };
 #pragma unroll 1
     for (int t = 0; t < R; ++t) {
       rd_mbar_wait(&fb[0][t], 0);
+      RD_TR(1 + t);
       double c = 1.0, s = 0.0;
+      if (live) rdv_sincos(rg[t][10][lane], s, c);   // the new heading: in flight while the position warp finishes tick t
+      rd_mbar_wait(&fb[1][t], 0);
+      if (t > 0) publish(t - 1);                     // tick t-1's loads have had this tick's trigonometry to arrive
       if (live) {
-        double ang[4], vs[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { ang[k] = rg[t][k][lane]; vs[k] = rg[t][4 + k][lane]; }
-        const double yaw = rg[t][10][lane];
-        // the short trigonometric path for all five arguments when every one of them is in its range (always, unless a
-        // car has spun thousands of times): five independent chains in one straight-line block
-        const bool in_range = fabs(ang[0]) < 1.0e5 && fabs(ang[1]) < 1.0e5 && fabs(ang[2]) < 1.0e5 && fabs(ang[3]) < 1.0e5 &&
-                              fabs(yaw) < 1.0e5;
-        if (in_range) {
-          rdv_sincos_reduced(yaw, s, c);
-          rdv_tick_position<true>(P.vk, ang, vs, x, y);
-        } else {
-          rdv_sincos(yaw, s, c);
-          rdv_tick_position<false>(P.vk, ang, vs, x, y);
-        }
+        qf[0] = rp[t][0][lane]; qf[1] = rp[t][1][lane];
+        rd_probe_issue_cs(cfg, m, qf[0], qf[1], c, s, pr);
       }
-      if (t > 0) publish(t - 1);          // tick t-1's loads have had this tick's trigonometry to arrive
-      if (live) rd_probe_issue_cs(cfg, m, x, y, c, s, pr);
-      px = x; py = y;
     }
     publish(R - 1);
+    RD_TR(10);
+    if (live) {   // the observation of the state after R ticks (warp 3 overwrites it for the envs that finish)
+#pragma unroll
+      for (int k = 0; k < 5; ++k) qf[2 + k] = rg[R - 1][8 + k][lane];
+      rd_write_obs(P, o, m, e, map_id, qf, (uint32_t)episode, (uint32_t)(agent_step0 + 1), 0, true, pr.c, pr.s);
+    }
+    rd_mbar_arrive(&obs_bar);
+    RD_TR(11);
+    RD_TR_DUMP(12);
     return;
   }
   // ---- bookkeeping warp: k_step with the tick integration replaced by the ring ----
@@ -547,6 +630,7 @@ __global__ void __launch_bounds__(96) k_step_split(StepParams P, OutPtrs o, cons
       P.recs[e].was_reset = 2;
     } else {
       const DevMap m = P.maps[map_id];   // the track descriptor lives in registers for the whole step
+      RD_TR(0);
       const double a1 = rd_action(cfg, act.y, 1);
       double q[7] = {pxy.x, pxy.y, psv.x, psv.y, pyw.x, pyw.y, pst.x};
       double total = 0.0;
@@ -554,9 +638,9 @@ __global__ void __launch_bounds__(96) k_step_split(StepParams P, OutPtrs o, cons
       double hc = 0.0, hs = 0.0;
 #pragma unroll 1
       for (int t = 1; t <= R; ++t) {      // t ticks done, as in k_step's bookkeeping half
-        rd_mbar_wait(&fb[1][t - 1], 0);   // acquire: the position warp's tick (and with it the dynamics warp's) is there
+        rd_mbar_wait(&fb[2][t - 1], 0);   // acquire: the probe warp's tick (and with it the other two warps') is there
         Probe pr;
-        q[0] = rp[t - 1][0][lane]; q[1] = rp[t - 1][1][lane]; pr.c = rp[t - 1][2][lane]; pr.s = rp[t - 1][3][lane];
+        q[0] = rp[t - 1][0][lane]; q[1] = rp[t - 1][1][lane]; pr.c = rc[t - 1][0][lane]; pr.s = rc[t - 1][1][lane];
 #pragma unroll
         for (int k = 0; k < 5; ++k) q[2 + k] = rg[t - 1][8 + k][lane];
 #pragma unroll
@@ -585,6 +669,7 @@ __global__ void __launch_bounds__(96) k_step_split(StepParams P, OutPtrs o, cons
         // tested when more ticks follow [REF baselines/racing/environment/single_agent.py:32-38]
         if (d && !(cfg.repeat_semantics == RD_REPEAT_BASELINES && t == 1 && R > 1)) { done = 1; break; }
         tick_timeout = 0;
+        RD_TR(1 + t);
       }
       const int agent_step = agent_step0 + 1;  // TimeLimit [REF dreamer/wrappers.py:147-154]
       int timeout = done ? tick_timeout : 0;
@@ -600,10 +685,15 @@ __global__ void __launch_bounds__(96) k_step_split(StepParams P, OutPtrs o, cons
         st[3] = (double)agent_step; st[4] = (flags & RD_F_COLLISION) ? 1.0 : 0.0; st[5] = (double)(lap - 1);
         st[7] = timeout ? 1.0 : 0.0; st[8] = mp;
       }
+      if (done) rd_mbar_wait(&obs_bar, 0);   // the probe warp's observation of the R-tick state is out: what follows replaces it
       if (done && cfg.auto_reset) {
-        double pz;
-        rd_reset_one(P, m, e, cfg.reset_mode, (uint32_t)jv.x, map_id, q, pz);
-        rd_write_obs(P, o, m, e, map_id, q, (uint32_t)jv.x + 1u, 0u, 1, false, 0.0, 0.0);
+        rd_mbar_wait(&rst_bar, 0);           // the reset warp's pose and observation for this (env, episode)
+        rd_reset_commit(P, e, (uint32_t)jv.x, map_id, rs[0][lane], rs[1][lane], rs[2][lane], rs[3][lane], q);
+        ObsVals ov;
+        uint32_t* w = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+        for (int k = 0; k < RD_OBS_WORDS; ++k) w[k] = ro[k][lane];
+        rd_obs_store(P, o, e, ov);
       } else {
         rd_stp(S, RD_P_XY, e, q[0], q[1]);
         rd_stp(S, RD_P_SV, e, q[2], q[3]);
@@ -613,10 +703,16 @@ __global__ void __launch_bounds__(96) k_step_split(StepParams P, OutPtrs o, cons
         rd_stp(S, RD_P_RS, e, ret, prs.y);
         rd_stp(S, RD_P_MP, e, mp, 0.0);
         S.i4[e] = make_int4(lap, cp, flags, agent_step);
-        rd_write_obs(P, o, m, e, map_id, q, (uint32_t)jv.x, (uint32_t)agent_step, 0, true, hc, hs);
+        // not done: all R ticks ran and the probe warp has written exactly this observation already
+        if (done) rd_write_obs(P, o, m, e, map_id, q, (uint32_t)jv.x, (uint32_t)agent_step, 0, true, hc, hs);
       }
     }
   }
+  RD_TR(12);
+  RD_TR_DUMP(13);
+#ifdef RD_SPLIT_TRACE
+  { const unsigned dn = __ballot_sync(0xffffffffu, st[0] != 0.0); if (lane == 0) printf("[cta %d] end %lld done %08x\n", blockIdx.x, clock64() - t_begin, dn); }
+#endif
   rd_stats_reduce(P.stats, st);
 }
 

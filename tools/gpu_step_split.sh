@@ -9,6 +9,7 @@ for rep in 1 2; do
     RD_STEP_SPLIT=$sp python bench.py $B > $OUT/b_$sp.json 2>$OUT/err.log; show $OUT/b_$sp.json "config2 split=$sp"
     RD_STEP_SPLIT=$sp python bench.py --config 4 $B > $OUT/b4_$sp.json 2>>$OUT/err.log; show $OUT/b4_$sp.json "config4 split=$sp"
     RD_STEP_SPLIT=$sp python bench.py --envs 16384 $B > $OUT/b16_$sp.json 2>>$OUT/err.log; show $OUT/b16_$sp.json "16384 envs split=$sp"
+    RD_STEP_SPLIT=$sp python bench.py --envs 8192 $B > $OUT/b8_$sp.json 2>>$OUT/err.log; show $OUT/b8_$sp.json "8192 envs split=$sp"
   done
 done
 tail -3 $OUT/err.log
