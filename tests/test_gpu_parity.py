@@ -581,3 +581,51 @@ def test_simulate_statistics_on_device(torch_cuda, golden_dir):
     assert np.allclose(returns, g["cum_rewards"], rtol=1e-9, atol=1e-9)
     assert np.allclose(maxima, g["max_progresses"], rtol=0, atol=1e-9)
     env.close()
+
+
+@pytest.mark.parametrize("kw", [dict(auto_reset=True, reset_mode="random"), dict(auto_reset=False, reset_mode="grid"),
+                                dict(auto_reset=True, reset_mode="random_bidirectional", repeat_semantics="baselines",
+                                     time_limit_ticks=96, normalize="baselines")])
+def test_split_step_kernel_is_bitwise_the_single_warp_kernel(torch_cuda, monkeypatch, kw):
+    """k_step_split (five warps per 32 envs: dynamics | position | probe | bookkeeping | reset look-ahead) and k_step
+    (one warp) are the same arithmetic in a different instruction order: every output, the whole env state and the
+    episode statistics must agree bit for bit, step after step, through terminations, auto-resets, frozen envs and a
+    ragged last warp."""
+    torch = torch_cuda
+    kw = dict(kw)
+    if kw.pop("normalize", None) == "baselines":
+        kw["normalize_obs"] = "baselines"
+    n = 1000 + 13                                          # ragged: the last CTA has 21 live lanes
+    envs = []
+    for split in ("1", "0"):
+        monkeypatch.setenv("RD_STEP_SPLIT", split)
+        envs.append(make_env(torch, tracks=("austria",), n_envs=n, action_repeat=8, time_limit_steps=25, seed=9, laps=1, **kw))
+    for e in envs:
+        e.reset()
+    rng = np.random.RandomState(21)
+    finished = 0
+    for k in range(40):
+        a = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+        a[:, 0] = np.abs(a[:, 0])
+        outs = []
+        for e in envs:
+            obs, rew, done, info = e.step(torch.from_numpy(a).cuda())
+            f64, i32 = e.get_state()
+            outs.append(([obs[key].cpu().numpy() for key in sorted(obs)], rew.cpu().numpy(), done.cpu().numpy(),
+                         [info[key].cpu().numpy() for key in sorted(info)], f64.cpu().numpy(), i32.cpu().numpy()))
+        x, y = outs
+        for u, v in zip(x[0], y[0]):
+            assert np.array_equal(u, v), f"step {k}: observation differs"
+        assert np.array_equal(x[1].view(np.uint32), y[1].view(np.uint32)), f"step {k}: reward bits differ"
+        assert np.array_equal(x[2], y[2])
+        for u, v in zip(x[3], y[3]):
+            assert np.array_equal(u, v), f"step {k}: info differs"
+        assert np.array_equal(x[4].view(np.uint64), y[4].view(np.uint64)), f"step {k}: float64 state bits differ"
+        assert np.array_equal(x[5], y[5]), f"step {k}: integer state differs"
+        finished += int(x[2].sum())
+    assert finished > n // 8, "the scenario is supposed to exercise terminations"
+    sa, sb = envs[0].read_stats(), envs[1].read_stats()
+    for key in sa:
+        assert abs(sa[key] - sb[key]) <= 1e-9 * max(1.0, abs(sb[key])), key   # sums of the same terms in another order
+    for e in envs:
+        e.close()
