@@ -347,15 +347,14 @@ int launch_lidar(rd_env* env, int map_id, const OriginRec* recs, const int32_t* 
   // 48 resident warps per SM wherever the shared-memory copies of the map allow it (the kernel is capped at 40
   // registers for that): three 16-warp CTAs for small maps, two 24-warp CTAs for maps of which two copies fit, one
   // 32-warp CTA otherwise.  RD_LIDAR_WARPS=16|24|32 overrides (tuning).
-  // Long launches (>= 128 work items per resident warp) draw their work one chunk ahead (see k_lidar).
   const size_t smem1 = 16 + (((size_t)2 * env->cfg.n_beams * 8 + 15) & ~(size_t)15) + (size_t)m.bits_bytes + 1024;   // + the per-CTA reserve
   const size_t sm_total = (size_t)env->smem_per_sm;
   int warps = 3 * smem1 <= sm_total ? 16 : (2 * smem1 <= sm_total ? 24 : 32);
   if (const char* ev = std::getenv("RD_LIDAR_WARPS")) { const int w = std::atoi(ev); if (w == 16 || w == 24 || w == 32) warps = w; }
-  int per_sm = 1;   // resident CTAs per SM as far as already known (any instantiation of this map: they differ by at most one)
-  for (int v = 0; v < 12; ++v) per_sm = std::max(per_sm, env->maps[map_id].lidar_per_sm[v]);
-  const long long items = (long long)n_env * ((env->cfg.n_beams + 31) / 32);
-  bool ahead = items >= 128ll * env->sm_count * per_sm * warps;
+  // Drawing the next work chunk one item ahead (k_lidar<.., AHEAD = true, ..>) paid off for long launches in round 1
+  // (+3.5 % at 65 536 envs); with the round-2 march it no longer does at any size (profiles/r3l_lidar_chunk_ahead.txt),
+  // so it is off unless RD_LIDAR_AHEAD=1 asks for it.
+  bool ahead = false;
   if (const char* ev = std::getenv("RD_LIDAR_AHEAD")) ahead = std::atoi(ev) != 0;
   const bool cars = env->cfg.agents_per_world > 1;   // worlds: the scans also see the other cars (own instantiation, so
                                                       // that the single-car kernel keeps its register budget)
