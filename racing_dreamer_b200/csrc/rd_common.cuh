@@ -42,7 +42,9 @@ struct __align__(16) OriginRec {
 struct LidarParams {
   int n_beams;
   int groups;            // ceil(n_beams / 32)
-  unsigned groups_magic; // ceil(2^32 / groups): item / groups == umulhi(item, groups_magic) (k_lidar)
+  int gpi;               // beam groups per work item (1 or 2, see k_lidar)
+  int units;             // work items per env: ceil(groups / gpi)
+  unsigned groups_magic; // ceil(2^32 / units): item / units == umulhi(item, groups_magic) (k_lidar)
   unsigned envs_magic;   // ceil(2^32 / n_env of the launch), centre_first order
   int centre_first;      // work order: beam groups from the centre of the scan outwards, envs innermost
   int normalize;         // 1: RD_OBS_LIDAR_NORM (r / range_max - 0.5); 2: RD_OBS_NORM_BASELINES ((r - norm_lo) * norm_sc)

@@ -53,8 +53,10 @@ struct rd_env {
   int smem_per_sm = 0;            // shared memory per SM, bytes
   size_t l2_window_max = 0;       // > 0: L2 persistence is set up; the largest access-policy window the device takes
   bool lidar_centre_first = true; // k_lidar work order (RD_LIDAR_ORDER=0: env-major)
+  int lidar_gpi_min = 45;         // beam groups per resident warp from which a work item holds two groups (RD_LIDAR_GPI_MIN)
+  int lidar_gpi_force = 0;        // RD_LIDAR_GPI=1|2
   bool lidar_pdl = true;          // k_lidar is launched as a programmatic dependent of the kernel in front of it (RD_LIDAR_PDL=0: off)
-  bool lidar_attr_set[12] = {};   // k_lidar<16|24|32, ahead, cars> opted in to smem_optin
+  bool lidar_attr_set[12] = {};   // k_lidar<16|24|32, groups per item, cars> opted in to smem_optin
   int n = 0;
   int step_block = 128;           // k_step threads per CTA (small batches: fewer, so that every SM gets a warp)
   bool step_split = true;         // k_step_split (two warps per 32 envs) while the batch is latency-bound; RD_STEP_SPLIT overrides
@@ -236,7 +238,9 @@ LidarParams lidar_params(const rd_env* env, const DevMap& m) {
   LidarParams lp{};
   lp.n_beams = c.n_beams;
   lp.groups = (c.n_beams + 31) / 32;
-  lp.groups_magic = lp.groups > 1 ? (unsigned)(((1ull << 32) + (unsigned)lp.groups - 1) / (unsigned)lp.groups) : 0u;
+  lp.gpi = 1;
+  lp.units = lp.groups;
+  lp.groups_magic = lp.units > 1 ? (unsigned)(((1ull << 32) + (unsigned)lp.units - 1) / (unsigned)lp.units) : 0u;
   lp.normalize = (c.obs_flags & RD_OBS_LIDAR_NORM) ? 1 : ((c.obs_flags & RD_OBS_NORM_BASELINES) ? 2 : 0);
   lp.norm_lo = c.obs_low[RD_NORM_LIDAR];
   lp.norm_sc = 1.0 / (c.obs_high[RD_NORM_LIDAR] - c.obs_low[RD_NORM_LIDAR]);
@@ -287,7 +291,7 @@ int launch_attrs(const rd_env* env, int map_id, bool pdl, cudaLaunchAttribute* a
 }
 
 // LiDAR launch for the envs of one map: persistent CTAs, grid = resident CTAs on all SMs.
-template <int WARPS, bool AHEAD, bool CARS>
+template <int WARPS, int GPI, bool CARS>
 int launch_lidar_t(rd_env* env, int map_id, const OriginRec* recs, const int32_t* order, int n_env, float* out,
                    cudaStream_t s, unsigned int* ctr) {
   const DevMap& m = env->maps[map_id].dev;
@@ -296,10 +300,10 @@ int launch_lidar_t(rd_env* env, int map_id, const OriginRec* recs, const int32_t
   lp.envs_magic = n_env > 1 ? (unsigned)(((1ull << 32) + (unsigned)n_env - 1) / (unsigned)n_env) : 0u;
   const size_t tab_bytes = ((size_t)2 * lp.n_beams * 8 + 15) & ~(size_t)15;
   const size_t smem = 16 + tab_bytes + (size_t)m.bits_bytes;
-  auto kern = k_lidar<WARPS, AHEAD, CARS>;
-  // which instantiation runs depends on the map (warps), the handle (cars) AND the launch size (draw-ahead), so both
+  auto kern = k_lidar<WARPS, GPI, CARS>;
+  // which instantiation runs depends on the map (warps), the handle (cars) AND the launch size (groups per item), so both
   // the opt-in to the device's shared-memory maximum and the cached occupancy are kept per instantiation
-  const int variant = (WARPS == 32 ? 2 : (WARPS == 24 ? 1 : 0)) + (AHEAD ? 3 : 0) + (CARS ? 6 : 0);
+  const int variant = (WARPS == 32 ? 2 : (WARPS == 24 ? 1 : 0)) + (GPI == 2 ? 3 : 0) + (CARS ? 6 : 0);
   bool& attr = env->lidar_attr_set[variant];
   if (!attr) {
     CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, env->smem_optin));
@@ -313,7 +317,10 @@ int launch_lidar_t(rd_env* env, int map_id, const OriginRec* recs, const int32_t
     if (q < 1) return fail(env, RD_ERR_INVALID, "map %d (%zu B) does not fit in shared memory", map_id, smem);
     per_sm = q;
   }
-  const long long items = (long long)n_env * lp.groups;
+  lp.gpi = GPI;
+  lp.units = (lp.groups + GPI - 1) / GPI;
+  lp.groups_magic = lp.units > 1 ? (unsigned)(((1ull << 32) + (unsigned)lp.units - 1) / (unsigned)lp.units) : 0u;
+  const long long items = (long long)n_env * lp.units;
   if (items >= (1ll << 31)) return fail(env, RD_ERR_INVALID, "too many (env, beam group) items for one launch");
   // rd_march keeps the ray position in 32-bit 2^-18 cells (rd_march.cuh)
   if ((long long)std::max(m.w, m.h) + (lp.rsub >> RD_SUB_BITS) >= 8190)
@@ -351,16 +358,16 @@ int launch_lidar(rd_env* env, int map_id, const OriginRec* recs, const int32_t* 
   const size_t sm_total = (size_t)env->smem_per_sm;
   int warps = 3 * smem1 <= sm_total ? 16 : (2 * smem1 <= sm_total ? 24 : 32);
   if (const char* ev = std::getenv("RD_LIDAR_WARPS")) { const int w = std::atoi(ev); if (w == 16 || w == 24 || w == 32) warps = w; }
-  // Drawing the next work chunk one item ahead (k_lidar<.., AHEAD = true, ..>) paid off for long launches in round 1
-  // (+3.5 % at 65 536 envs); with the round-2 march it no longer does at any size (profiles/r3l_lidar_chunk_ahead.txt),
-  // so it is off unless RD_LIDAR_AHEAD=1 asks for it.
-  bool ahead = false;
-  if (const char* ev = std::getenv("RD_LIDAR_AHEAD")) ahead = std::atoi(ev) != 0;
+  // Two beam groups per work item once a resident warp gets enough of them (see k_lidar): 45 groups per warp is where
+  // the curves cross (profiles/r3o_lidar_groups_per_item.txt).  RD_LIDAR_GPI=1|2 overrides.
+  const long long resident_warps = (long long)env->sm_count * (warps == 32 ? 32 : 48);
+  int gpi = (long long)n_env * ((env->cfg.n_beams + 31) / 32) >= (long long)env->lidar_gpi_min * resident_warps ? 2 : 1;
+  if (env->lidar_gpi_force) gpi = env->lidar_gpi_force;
   const bool cars = env->cfg.agents_per_world > 1;   // worlds: the scans also see the other cars (own instantiation, so
                                                       // that the single-car kernel keeps its register budget)
-#define RD_LIDAR_GO(W, A, C) launch_lidar_t<W, A, C>(env, map_id, recs, order, n_env, out, s, ctr)
-#define RD_LIDAR_GO_W(W) (cars ? (ahead ? RD_LIDAR_GO(W, true, true) : RD_LIDAR_GO(W, false, true)) \
-                               : (ahead ? RD_LIDAR_GO(W, true, false) : RD_LIDAR_GO(W, false, false)))
+#define RD_LIDAR_GO(W, G, C) launch_lidar_t<W, G, C>(env, map_id, recs, order, n_env, out, s, ctr)
+#define RD_LIDAR_GO_W(W) (cars ? (gpi == 2 ? RD_LIDAR_GO(W, 2, true) : RD_LIDAR_GO(W, 1, true)) \
+                               : (gpi == 2 ? RD_LIDAR_GO(W, 2, false) : RD_LIDAR_GO(W, 1, false)))
   if (warps == 32) return RD_LIDAR_GO_W(32);
   if (warps == 24) return RD_LIDAR_GO_W(24);
   return RD_LIDAR_GO_W(16);
@@ -570,6 +577,8 @@ RD_API int rd_create(const rd_config* cfg, rd_env** out) {
   env->step_block = (env->n >= 128 * 4 * env->sm_count) ? 128 : ((env->n >= 64 * 4 * env->sm_count) ? 64 : 32);
   if (const char* ev = std::getenv("RD_LIDAR_PDL")) env->lidar_pdl = std::atoi(ev) != 0;
   if (const char* ev = std::getenv("RD_LIDAR_ORDER")) env->lidar_centre_first = std::atoi(ev) != 0;
+  if (const char* ev = std::getenv("RD_LIDAR_GPI")) { const int v = std::atoi(ev); if (v == 1 || v == 2) env->lidar_gpi_force = v; }
+  if (const char* ev = std::getenv("RD_LIDAR_GPI_MIN")) { const int v = std::atoi(ev); if (v > 0) env->lidar_gpi_min = v; }
   env->step_split = env->n <= 64 * env->sm_count;   // up to two CTAs per SM (measured: 22.9 vs 31.9 us at 8192 envs, 39.3 vs 33.1 us
                                                      // at 16384): larger batches are throughput-bound and one warp per 32 envs does less work
   if (const char* ev = std::getenv("RD_STEP_SPLIT")) env->step_split = std::atoi(ev) != 0;

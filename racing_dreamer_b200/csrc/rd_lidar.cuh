@@ -16,6 +16,10 @@
 #ifndef RD_LIDAR_CHUNK
 #define RD_LIDAR_CHUNK 2   // work items a warp draws from the global counter at a time (see k_lidar)
 #endif
+// GPI = beam groups (32 adjacent beams each) per work item: the item's decode, its env look-up and its origin
+// record are shared by gpi consecutive groups of one env.  Measured on B200 (profiles/r3o_lidar_groups_per_item.txt):
+// two groups per item are 4-8 % faster for long launches (fewer draws from the work counter, half the set-up) and 5 %
+// slower at 4096 envs, where a warp only gets ~20 groups and the coarser items leave a longer tail; the host picks.
 
 // atomicAdd whose result is NOT needed right away.  For an atomic on a provably warp-uniform address ptxas emits its
 // warp-aggregation pattern (leader ATOMG + SHFL of the result right behind it), which waits for the L2 round trip on the
@@ -82,7 +86,7 @@ __device__ __forceinline__ float rd_car_hit(const LidarParams& lp, int px, int p
 // smem layout: [0,16) mbarrier | beam table 2*n_beams f64 (cos then sin) | bit grid | block clearance field
 // The tail of the item list is handed out through a global counter (ctr[0]); the last CTA to finish (ticket ctr[1])
 // re-arms both for the next launch on the stream.
-template <int WARPS, bool AHEAD, bool CARS>
+template <int WARPS, int GPI, bool CARS>
 __global__ void __launch_bounds__(WARPS * 32, CARS ? (WARPS == 16 ? 2 : 1) : (WARPS == 32 ? 1 : (WARPS == 24 ? 2 : 3)))
 k_lidar(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict__ recs,
         const int32_t* __restrict__ env_order, int n_env, LidarParams lp, const double* __restrict__ beam_tab,
@@ -123,14 +127,10 @@ k_lidar(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict
   // everything above only read launch-invariant data; the origin records come from the kernel in front of this one
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
-  const unsigned total_items = (unsigned)n_env * (unsigned)lp.groups;
+  const unsigned total_items = (unsigned)n_env * (unsigned)lp.units;
   // Scheduling: items are handed out through a global counter, RD_LIDAR_CHUNK at a time, so warps that drew long rays
   // do not hold the kernel up.  Measured on B200 (Austria, 4096 envs): chunk 2 beats 4, 8, a guided (shrinking) chunk
   // and a static round-robin with a dynamic tail (profiles/r01_lidar_variants.txt).
-  // AHEAD: the next chunk is drawn while the current one is marched, so the atomic's L2 round trip (11 % of the warps'
-  // time in the ncu source view, profiles/r01x_ncu_k_lidar_lines.txt) is off the critical path -- but every warp then
-  // sits on one more chunk at the end of the launch.  Measured on B200 (profiles/r01y_lidar_prefetch.txt): +3.5 % at
-  // 470 items per warp (65536 envs), -4 % at 29 items per warp (4096 envs); the host picks per launch.
   unsigned item = 0, last = 0;
   for (;;) {
     if (item >= last) {
@@ -140,10 +140,6 @@ k_lidar(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict
       have_ahead = false;
       if (item >= total_items) break;
       last = min(item + chunk, total_items);
-      if (AHEAD) {
-        if (lane == 0) ahead = rd_atom_add(ctr, chunk);
-        have_ahead = true;
-      }
     }
     {
       unsigned slot;
@@ -157,18 +153,20 @@ k_lidar(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict
         if (!lp.envs_magic) r = item;
         if (item - r * (unsigned)n_env >= (unsigned)n_env) --r;
         slot = item - r * (unsigned)n_env;
-        const int c = lp.groups >> 1;
+        const int c = lp.units >> 1;
         g = (r & 1u) ? c - (int)((r + 1u) >> 1) : c + (int)(r >> 1);
       } else {
         // item / groups by a multiply: groups_magic = ceil(2^32 / groups) (exact for item < 2^32 / groups; one fix-up
         // step covers the rest of the 31-bit range)
-        slot = lp.groups_magic ? __umulhi(item, lp.groups_magic) : item;   // magic 0: one group per env
-        if (item - slot * (unsigned)lp.groups >= (unsigned)lp.groups) --slot;      // the estimate never falls short
-        g = (int)(item - slot * (unsigned)lp.groups);
+        slot = lp.groups_magic ? __umulhi(item, lp.groups_magic) : item;   // magic 0: one unit per env
+        if (item - slot * (unsigned)lp.units >= (unsigned)lp.units) --slot;        // the estimate never falls short
+        g = (int)(item - slot * (unsigned)lp.units);
       }
       const int env = env_order ? __ldg(env_order + slot) : (int)slot;
       const OriginRec rec = recs[env];
-      const int beam = g * 32 + lane;
+#pragma unroll
+      for (int h = 0; h < GPI; ++h) {
+      const int beam = (g * GPI + h) * 32 + lane;
       if (rec.was_reset != 2 && beam < lp.n_beams) {  // was_reset == 2: frozen env, outputs stay as they are
         float r;
         if (!(rec.valid & 1)) {
@@ -206,6 +204,7 @@ k_lidar(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict
         const float rf = rd_finish_range(lp, r, rec, (uint32_t)beam);
         if (lp.f16) reinterpret_cast<__half*>(out)[(size_t)env * lp.n_beams + beam] = __float2half_rn(rf);   // Collect at precision 16
         else out[(size_t)env * lp.n_beams + beam] = rf;
+      }
       }
     }
     ++item;

@@ -391,7 +391,8 @@ def test_float16_scans_are_the_rounded_float32_scans(torch_cuda):
 
 
 def test_lidar_kernel_variants_mix_on_one_handle(torch_cuda):
-    """One handle launches different k_lidar instantiations depending on the launch size (draw-ahead for long launches) --
+    """One handle launches different k_lidar instantiations depending on the launch size (two beam groups per work item for
+    long launches) --
     e.g. the full batch in rd_step and small chunks in rd_step_host, or a large and a small rd_lidar_cast.  Every
     instantiation must be opted in to the large shared-memory carve-out on its own (regression: 'invalid argument')."""
     torch = torch_cuda
@@ -401,7 +402,7 @@ def test_lidar_kernel_variants_mix_on_one_handle(torch_cuda):
     for track in ("barcelona", "austria", "treitlstrasse_v2"):
         env = make_env(torch, tracks=(track,), n_envs=8)
         orc = make_oracle(env)
-        big = random_poses(env.tracks[0], 40000, rng)              # >= 128 items per resident warp: draw-ahead variant
+        big = random_poses(env.tracks[0], 40000, rng)              # >= 45 beam groups per resident warp: two groups per item
         small = big[:64]
         a = env.lidar_cast(torch.from_numpy(small)).cpu().numpy()   # plain variant first ...
         b = env.lidar_cast(torch.from_numpy(big)).cpu().numpy()     # ... then the other one on the same handle
