@@ -813,7 +813,7 @@ RD_API int rd_host_init(rd_env* env, int n_chunks, rd_outputs* host_out) {
   n_chunks = std::max(1, std::min(n_chunks, n));
   h.n_chunks = n_chunks;
   h.bounds.resize(n_chunks + 1);
-  // progressive chunk sizes (1 : 2 : 4 : ... capped at 8x): the first chunk is small so that the copy engine starts
+  // progressive chunk sizes (1 : 2 : 4 : ... capped at 16x, measured with the round-2 kernels): the first chunk is small so that the copy engine starts
   // early; from then on it is the bottleneck and each chunk's ray casting hides behind the previous chunk's copy.
   // RD_HOST_CHUNKS="1,3,12" overrides the weights (and the chunk count) for tuning.
   {
@@ -828,7 +828,7 @@ RD_API int rd_host_init(rd_env* env, int n_chunks, rd_outputs* host_out) {
       }
       if ((int)w.size() > n) w.resize(n);
     }
-    if (w.empty()) { w.resize(n_chunks); for (int c = 0; c < n_chunks; ++c) w[c] = (double)(1 << std::min(c, 3)); }
+    if (w.empty()) { w.resize(n_chunks); for (int c = 0; c < n_chunks; ++c) w[c] = (double)(1 << std::min(c, 4)); }
     n_chunks = (int)w.size();
     h.n_chunks = n_chunks;
     h.bounds.assign(n_chunks + 1, 0);
