@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: kept for the record -- the RD_HOST_PIPE / RD_HOST_TRACE / RD_HOST_ACT_COPY switches these runs used were removed
+# together with the rejected schedules (profiles/r2p_host_pipeline_trace.txt); the script no longer runs as is.
 # host-facing step A/B: default vs explicit action copy, shard counts.  usage: bash tools/gpu_e2e2.sh tag
 TAG=${1:-e2e}; OUT=gpurun_out/$TAG; mkdir -p $OUT
 timeout 900 python -m pytest tests -x -q -m gpu -k "host or compat or episodes or smoke" > $OUT/pytest_host.log 2>&1; echo "pytest(host) rc=$?"; tail -3 $OUT/pytest_host.log

@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: kept for the record -- the RD_HOST_PIPE / RD_HOST_TRACE / RD_HOST_ACT_COPY switches these runs used were removed
+# together with the rejected schedules (profiles/r2p_host_pipeline_trace.txt); the script no longer runs as is.
 # host-facing step: "flags" schedule (one ray-cast launch, chunk counters + cuStreamWaitValue32) against "streams".
 # usage: bash tools/gpu_e2e3.sh tag
 TAG=${1:-e2e3}; OUT=gpurun_out/$TAG; mkdir -p $OUT

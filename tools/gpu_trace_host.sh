@@ -1,4 +1,6 @@
 B="--steps 30 --warmup 5 --no-closed-loop --no-multi-agent --no-configs --no-cpu-baseline --no-e2e-variants --e2e-steps 60"
+# NOTE: kept for the record -- the RD_HOST_PIPE / RD_HOST_TRACE / RD_HOST_ACT_COPY switches these runs used were removed
+# together with the rejected schedules (profiles/r2p_host_pipeline_trace.txt); the script no longer runs as is.
 for sh in 8 4; do
 echo "== shards $sh"; RD_HOST_TRACE=40 python bench.py $B --e2e-shards $sh 2>&1 >/dev/null | grep trace
 done
