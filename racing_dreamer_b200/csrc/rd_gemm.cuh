@@ -121,11 +121,24 @@ __device__ __forceinline__ void gm_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(rd_smem_u32(bar))
                : "memory");
 }
+// One thread of a converged warp (the compiler then issues the tcgen05 / TMA instructions of the elected region
+// directly instead of wrapping each one in a per-lane election loop).
+__device__ __forceinline__ bool gm_elect_one() {
+  uint32_t p;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(p));
+  return p != 0;
+}
 // K-major operand tile in shared memory, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart
 // (cute::UMMA::SmemDescriptor: start >> 4 | LBO 1 << 16 | SBO 64 << 32 | version 1 << 46 | SWIZZLE_128B 2 << 61)
 __device__ __forceinline__ uint64_t gm_smem_desc(uint32_t addr) {
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// The descriptor's low word (start address >> 4 | LBO) and its constant high word (SBO, version, swizzle): the issuer
+// thread steps the low word by plain additions (32 bytes of K = +2, next slab = +bytes / 16) instead of rebuilding
+// the 64-bit value for every instruction -- its own instruction stream is what bounds a K block (see the kernel).
+__device__ __forceinline__ uint32_t gm_desc_lo(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); }
+#define GM_DESC_HI ((uint32_t)((64ull << 32 | 1ull << 46 | 2ull << 61) >> 32))
+__device__ __forceinline__ uint64_t gm_desc(uint32_t lo) { return ((uint64_t)GM_DESC_HI << 32) | lo; }
 // cute::UMMA::InstrDescriptor: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), both K-major, N >> 3 at bit 17, M >> 4 at 24
 #define GM_IDESC ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GM_BN >> 3) << 17) | ((uint32_t)(GM_BM >> 4) << 24))
 __device__ __forceinline__ void gm_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
@@ -237,7 +250,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
-    if (lane == 0) {   // ===== TMA producer =====
+    if (gm_elect_one()) {   // ===== TMA producer =====
       asm volatile("griddepcontrol.wait;" ::: "memory");
       uint32_t it = 0;
       for (int p = 0; p < g.n_phases; ++p) {
@@ -257,22 +270,38 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {   // ===== MMA issuer =====
+    if (gm_elect_one()) {   // ===== MMA issuer =====
+      // A K block is four small MMAs per slab (128 x 64 x 8): ~130 tensor-pipe cycles.  What a CTA can sustain is set by
+      // THIS thread's instruction stream (measured: ~860 cycles per K block whatever the ring depth, tile width or
+      // operand source, profiles/r3t_dreamer_kdense_analysis.txt), so the loop is kept to the barrier wait, one
+      // descriptor addition per instruction and the issue itself.
       uint32_t it = 0, touched = 0;
+      const uint32_t lo_base = gm_desc_lo(smem_base);
       for (int p = 0; p < g.n_phases; ++p) {
         const GemmPhase& ph = g.ph[p];
-        for (int kb = 0; kb < ph.k_blocks; ++kb, ++it) {
+        const int nb = ph.nb, kbs = ph.k_blocks;
+        uint32_t dcol[3], fresh[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int a = i < nb ? ph.acc[i] : 0;
+          dcol[i] = tmem + (uint32_t)(a * GM_BN);
+          fresh[i] = i < nb ? (((touched >> a) & 1u) ^ 1u) : 0u;   // first instruction into this accumulator overwrites
+          if (i < nb) touched |= 1u << a;
+        }
+        for (int kb = 0; kb < kbs; ++kb, ++it) {
           const uint32_t s = it % GM_STAGES, par = (it / GM_STAGES) & 1u;
           gm_mbar_wait(&full_bar[s], par);
           gm_tc_fence_after();
-          const uint32_t sa = smem_base + s * STAGE_BYTES;
-          for (int i = 0; i < ph.nb; ++i) {
-            const uint32_t d = tmem + (uint32_t)(ph.acc[i] * GM_BN);
-            const uint32_t sw = sa + GM_A_BYTES + i * GM_W_BYTES;
+          const uint32_t a_lo = lo_base + s * (STAGE_BYTES >> 4);
 #pragma unroll
-            for (int k = 0; k < GM_BK / 8; ++k)   // UMMA_K = 8 TF32 = 32 bytes along the swizzled row
-              gm_mma_tf32(d, gm_smem_desc(sa + k * 32), gm_smem_desc(sw + k * 32), ((touched >> ph.acc[i]) & 1u) | (uint32_t)(k > 0));
-            touched |= 1u << ph.acc[i];
+          for (int i = 0; i < 3; ++i) {
+            if (i < nb) {
+              const uint32_t w_lo = a_lo + ((GM_A_BYTES + i * GM_W_BYTES) >> 4);
+              const uint32_t acc0 = (kb > 0) ? 1u : (fresh[i] ^ 1u);
+#pragma unroll
+              for (int k = 0; k < GM_BK / 8; ++k)   // UMMA_K = 8 TF32 = 32 bytes along the swizzled row
+                gm_mma_tf32(dcol[i], gm_desc(a_lo + 2 * k), gm_desc(w_lo + 2 * k), k > 0 ? 1u : acc0);
+            }
           }
           gm_commit(&empty_bar[s]);   // the slot is free once these MMAs have read it
         }
