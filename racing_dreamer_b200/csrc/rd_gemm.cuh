@@ -252,19 +252,26 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
   if (warp == 0) {
     if (gm_elect_one()) {   // ===== TMA producer =====
       asm volatile("griddepcontrol.wait;" ::: "memory");
+      // like the issuer below, this thread's instruction stream bounds a K block: everything that does not change from
+      // one K block to the next is set up per phase
       uint32_t it = 0;
       for (int p = 0; p < g.n_phases; ++p) {
         const GemmPhase& ph = g.ph[p];
         const CUtensorMap* ma = &maps.a[ph.a_map];
         const CUtensorMap* mw = &maps.w[ph.w_map];
-        for (int kb = 0; kb < ph.k_blocks; ++kb, ++it) {
+        const int nb = ph.nb, kbs = ph.k_blocks;
+        const uint32_t tx = GM_A_BYTES + (uint32_t)nb * GM_W_BYTES;
+        int ak = ph.a_k0, wk = ph.w_k0;
+        const int r0 = ph.w_row0[0] + n0, r1 = ph.w_row0[1] + n0, r2 = ph.w_row0[2] + n0;
+        for (int kb = 0; kb < kbs; ++kb, ++it, ak += GM_BK, wk += GM_BK) {
           const uint32_t s = it % GM_STAGES, par = (it / GM_STAGES) & 1u;
           gm_mbar_wait(&empty_bar[s], par ^ 1u);
           const uint32_t sa = smem_base + s * STAGE_BYTES;
-          rd_mbar_expect_tx(&full_bar[s], GM_A_BYTES + ph.nb * GM_W_BYTES);
-          gm_tma_2d(sa, ma, ph.a_k0 + kb * GM_BK, m0, &full_bar[s]);
-          for (int i = 0; i < ph.nb; ++i)
-            gm_tma_2d(sa + GM_A_BYTES + i * GM_W_BYTES, mw, ph.w_k0 + kb * GM_BK, ph.w_row0[i] + n0, &full_bar[s]);
+          rd_mbar_expect_tx(&full_bar[s], tx);
+          gm_tma_2d(sa, ma, ak, m0, &full_bar[s]);
+          gm_tma_2d(sa + GM_A_BYTES, mw, wk, r0, &full_bar[s]);
+          if (nb > 1) gm_tma_2d(sa + GM_A_BYTES + GM_W_BYTES, mw, wk, r1, &full_bar[s]);
+          if (nb > 2) gm_tma_2d(sa + GM_A_BYTES + 2 * GM_W_BYTES, mw, wk, r2, &full_bar[s]);
         }
       }
     }
