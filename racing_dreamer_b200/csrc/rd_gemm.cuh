@@ -94,7 +94,7 @@ __device__ __forceinline__ void gm_prefetch_map(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 // bounded wait: a broken pipeline traps (the launch fails) instead of hanging the device
-__device__ __forceinline__ void gm_mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void gm_mbar_wait(uint64_t* bar, uint32_t parity, bool backoff = false) {
   const uint32_t a = rd_smem_u32(bar);
   for (uint32_t spins = 0;; ++spins) {
     uint32_t ok;
@@ -104,6 +104,9 @@ __device__ __forceinline__ void gm_mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(a), "r"(parity)
         : "memory");
     if (ok) return;
+    // the four epilogue warps wait for the whole K loop: they must not take issue slots from the single issuer /
+    // producer threads their schedulers also serve
+    if (backoff) __nanosleep(256);
     if (spins > (1u << 24)) __trap();
   }
 }
@@ -322,7 +325,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
     const int row = m0 + q * 32 + lane;
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    gm_mbar_wait(&acc_bar, 0);
+    gm_mbar_wait(&acc_bar, 0, true);
     gm_tc_fence_after();
     const bool live = row < g.M;
     if constexpr (EPI == EPI_DENSE) {
