@@ -199,16 +199,23 @@ struct DrTerm { const DreamerPolicy::Operand* a; const DreamerPolicy::Operand* w
 static inline void dr_build(const DreamerPolicy& d, GemmMaps& maps, GemmArgs& g, const DrTerm* terms, int n_terms, int nb,
                             const int* w_row0, const int (*gate)[3], int gates, int slots) {
   g.n_phases = 0;
+  int small_group = 0;   // the accumulator group of the cross products (set below, before the first add)
   auto add = [&](int t, int a_part, int w_part, int kb0, int kbs, int group) {
     GemmPhase& p = g.ph[g.n_phases++];
     p = GemmPhase{};
     p.a_map = 2 * t + a_part;   // maps.a / maps.w slots: term t -> hi at 2t, lo at 2t + 1
     p.w_map = 2 * t + w_part;
+    p.a_map_lo = 2 * t + 1;     // X3 kernels: the lo parts ride in the same K block (k_dense<..., X3 = true>)
+    p.w_map_lo = 2 * t + 1;
     p.k_blocks = kbs;
     p.a_k0 = kb0 * GM_BK;
     p.w_k0 = terms[t].w_k0 + kb0 * GM_BK;
     p.nb = nb;
-    for (int i = 0; i < nb; ++i) { p.w_row0[i] = w_row0 ? w_row0[i] : 0; p.acc[i] = group * gates + (gate ? gate[t][i] : 0); }
+    for (int i = 0; i < nb; ++i) {
+      p.w_row0[i] = w_row0 ? w_row0[i] : 0;
+      p.acc[i] = group * gates + (gate ? gate[t][i] : 0);
+      p.acc_small[i] = small_group * gates + (gate ? gate[t][i] : 0);
+    }
   };
   int total = 0;
   for (int t = 0; t < n_terms; ++t) {
@@ -219,12 +226,8 @@ static inline void dr_build(const DreamerPolicy& d, GemmMaps& maps, GemmArgs& g,
   }
   const int max_groups = slots / gates - (d.x3 ? 1 : 0);
   const int groups = std::max(1, std::min(max_groups, (total + 5) / 6));
-  if (d.x3)
-    for (int t = 0; t < n_terms; ++t) {
-      const int kbs = (terms[t].k_elems + GM_BK - 1) / GM_BK;
-      add(t, 1, 0, 0, kbs, groups);
-      add(t, 0, 1, 0, kbs, groups);
-    }
+  small_group = groups;
+  // x3: no separate lo*hi / hi*lo passes -- every hi*hi K block below carries the lo tiles and feeds all three products
   // hi*hi: walk the concatenated K blocks, group boundaries every total/groups blocks
   int done = 0;
   for (int t = 0; t < n_terms; ++t) {
@@ -264,7 +267,8 @@ static inline int dreamer_step(DreamerPolicy& d, const float* lidar, float* acti
     const DrTerm t[1] = {{&d.v_sa[cur], &d.w_img1, 32, 0}};
     dr_build(d, maps, g, t, 1, 1, nullptr, nullptr, 1, 4);
     g.bias = d.b_img1; g.out = d.x1.p[0]; g.out_lo = d.x1.p[1]; g.ldo = H; g.act = 1;
-    DR_TRY((gm_launch<EPI_DENSE, 1, 4, 4>(maps, g, s)));
+    if (d.x3) DR_TRY((gm_launch<EPI_DENSE, 1, 4, 2, true>(maps, g, s)));
+    else DR_TRY((gm_launch<EPI_DENSE, 1, 4, 4>(maps, g, s)));
     ++*launched;
   }
   // 2. GRU cell [REF models.py:81-82]: z and r accumulate both products, the candidate keeps its halves apart
@@ -277,7 +281,8 @@ static inline int dreamer_step(DreamerPolicy& d, const float* lidar, float* acti
     dr_build(d, maps, g, t, 2, 3, rows, gate, 4, d.x3 ? 8 : 4);   // one main group (every gate slot must be fed), one small
     g.bias = d.b_gru; g.out = d.v_det[nxt].p[0]; g.out_lo = d.v_det[nxt].p[1]; g.ldo = d.ldf;
     g.hold = d.v_det[cur].p[0]; g.hold_lo = d.v_det[cur].p[1]; g.ldh = d.ldf;
-    DR_TRY((gm_launch<EPI_GRU, 3, 8, 4>(maps, g, s)));
+    if (d.x3) DR_TRY((gm_launch<EPI_GRU, 3, 8, 2, true>(maps, g, s)));
+    else DR_TRY((gm_launch<EPI_GRU, 3, 8, 4>(maps, g, s)));
     ++*launched;
   }
   // 3. obs1 = elu(concat([deter, embed]) @ W + b) [REF models.py:66-67]: two K ranges over one weight matrix
@@ -287,7 +292,8 @@ static inline int dreamer_step(DreamerPolicy& d, const float* lidar, float* acti
     const DrTerm t[2] = {{&d.v_det[nxt], &d.w_obs1, D, 0}, {&d.lidar, &d.w_obs1, d.embed, D}};
     dr_build(d, maps, g, t, 2, 1, nullptr, nullptr, 1, 8);
     g.bias = d.b_obs1; g.out = d.hobs.p[0]; g.out_lo = d.hobs.p[1]; g.ldo = H; g.act = 1;
-    DR_TRY((gm_launch<EPI_DENSE, 1, 8, 8>(maps, g, s)));
+    if (d.x3) DR_TRY((gm_launch<EPI_DENSE, 1, 8, 4, true>(maps, g, s)));
+    else DR_TRY((gm_launch<EPI_DENSE, 1, 8, 8>(maps, g, s)));
     ++*launched;
   }
   // 4. obs2 + posterior sample [REF models.py:68-72]
@@ -300,7 +306,8 @@ static inline int dreamer_step(DreamerPolicy& d, const float* lidar, float* acti
     g.noise = noise; g.eps = eps_stoch; g.ld_eps = GM_STOCH;
     g.key0 = (uint32_t)seed; g.key1 = (uint32_t)(seed >> 32) ^ RD_STREAM_STOCH; g.step = d.step; g.gid0 = gid0;
     g.dbg = debug;
-    DR_TRY((gm_launch<EPI_STOCH, 1, 4, 4>(maps, g, s)));
+    if (d.x3) DR_TRY((gm_launch<EPI_STOCH, 1, 4, 4, true>(maps, g, s)));
+    else DR_TRY((gm_launch<EPI_STOCH, 1, 4, 4>(maps, g, s)));
     ++*launched;
   }
   // 5. actor trunk [REF models.py:321-322]
@@ -310,7 +317,8 @@ static inline int dreamer_step(DreamerPolicy& d, const float* lidar, float* acti
     const DrTerm t[1] = {{i == 0 ? &d.feat[nxt] : &d.hid[(i - 1) & 1], &d.w_act[i], i == 0 ? d.ldf : U, 0}};
     dr_build(d, maps, g, t, 1, 1, nullptr, nullptr, 1, 4);
     g.bias = d.b_act[i]; g.out = d.hid[i & 1].p[0]; g.out_lo = d.hid[i & 1].p[1]; g.ldo = U; g.act = 1;
-    DR_TRY((gm_launch<EPI_DENSE, 1, 4, 4>(maps, g, s)));
+    if (d.x3) DR_TRY((gm_launch<EPI_DENSE, 1, 4, 2, true>(maps, g, s)));
+    else DR_TRY((gm_launch<EPI_DENSE, 1, 4, 4>(maps, g, s)));
     ++*launched;
   }
   // 6. hout + distribution head + SampleDist.mode() [REF models.py:323-346; tools.py:70-73]
@@ -326,7 +334,8 @@ static inline int dreamer_step(DreamerPolicy& d, const float* lidar, float* acti
     g.n_samples = d.n_samples;
     g.dbg = debug ? debug + (size_t)d.n * 2 * GM_STOCH : nullptr;
     g.out = d.head_raw;
-    DR_TRY((gm_launch<EPI_ACTOR, 1, 4, 4>(maps, g, s)));
+    if (d.x3) DR_TRY((gm_launch<EPI_ACTOR, 1, 4, 4, true>(maps, g, s)));
+    else DR_TRY((gm_launch<EPI_ACTOR, 1, 4, 4>(maps, g, s)));
     ++*launched;
     k_actor_mode<<<(unsigned)((d.n + 7) / 8), 256, 0, s>>>(g);
     DR_TRY(cudaGetLastError());

@@ -51,6 +51,10 @@ struct GemmPhase {
   int nb;           // weight slabs per block (1..3)
   int w_row0[3];    // first W row of each slab (the CTA's n0 is added)
   int acc[3];       // accumulator fed by each slab
+  // k_dense<..., X3 = true>: the K block also carries the lo parts of both operands (maps a_map_lo / w_map_lo) and feeds
+  // three products: lo*hi and hi*lo into acc_small[i], hi*hi into acc[i]
+  int a_map_lo, w_map_lo;
+  int acc_small[3];
 };
 
 enum { EPI_DENSE = 0, EPI_GRU = 1, EPI_STOCH = 2, EPI_ACTOR = 3 };
@@ -221,20 +225,27 @@ __device__ __forceinline__ void gm_normal4(uint32_t c0, uint32_t c1, uint32_t c2
 // ---------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------
-template <int EPI, int NSLAB, int NACC, int GM_STAGES>
+template <int EPI, int NSLAB, int NACC, int GM_STAGES, bool X3 = false>
 __global__ void __launch_bounds__(GM_THREADS, 1)
     k_dense(const __grid_constant__ GemmMaps maps, const GemmArgs g) {
   extern __shared__ uint8_t gm_smem_raw[];
   __shared__ uint64_t full_bar[GM_STAGES], empty_bar[GM_STAGES], acc_bar;
   __shared__ uint32_t tmem_slot;
-  constexpr uint32_t STAGE_BYTES = GM_A_BYTES + NSLAB * GM_W_BYTES;
+  // X3: a ring stage holds the hi AND the lo tiles of a K block ([A_hi | W_hi slabs | A_lo | W_lo slabs]) and feeds all
+  // three products of the float32-grade scheme from one load: two thirds of the operand bytes of three separate passes
+  // and a third of the producer / issuer hand-offs.
+  constexpr uint32_t SUB_BYTES = GM_A_BYTES + NSLAB * GM_W_BYTES;
+  constexpr uint32_t STAGE_BYTES = (X3 ? 2u : 1u) * SUB_BYTES;
   constexpr uint32_t TM_COLS = (NACC * GM_BN <= 64) ? 64 : (NACC * GM_BN <= 128 ? 128 : (NACC * GM_BN <= 256 ? 256 : 512));
   const uint32_t smem_base = (rd_smem_u32(gm_smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles: 1024-byte aligned
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * GM_BM, n0 = blockIdx.y * GM_BN;
 
   if (threadIdx.x == 0) {
-    for (int p = 0; p < g.n_phases; ++p) { gm_prefetch_map(&maps.a[g.ph[p].a_map]); gm_prefetch_map(&maps.w[g.ph[p].w_map]); }
+    for (int p = 0; p < g.n_phases; ++p) {
+      gm_prefetch_map(&maps.a[g.ph[p].a_map]); gm_prefetch_map(&maps.w[g.ph[p].w_map]);
+      if (X3) { gm_prefetch_map(&maps.a[g.ph[p].a_map_lo]); gm_prefetch_map(&maps.w[g.ph[p].w_map_lo]); }
+    }
 #pragma unroll
     for (int s = 0; s < GM_STAGES; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(rd_smem_u32(&full_bar[s])));
@@ -263,7 +274,9 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
         const CUtensorMap* ma = &maps.a[ph.a_map];
         const CUtensorMap* mw = &maps.w[ph.w_map];
         const int nb = ph.nb, kbs = ph.k_blocks;
-        const uint32_t tx = GM_A_BYTES + (uint32_t)nb * GM_W_BYTES;
+        const CUtensorMap* ma2 = &maps.a[X3 ? ph.a_map_lo : ph.a_map];
+        const CUtensorMap* mw2 = &maps.w[X3 ? ph.w_map_lo : ph.w_map];
+        const uint32_t tx = (X3 ? 2u : 1u) * (GM_A_BYTES + (uint32_t)nb * GM_W_BYTES);
         int ak = ph.a_k0, wk = ph.w_k0;
         const int r0 = ph.w_row0[0] + n0, r1 = ph.w_row0[1] + n0, r2 = ph.w_row0[2] + n0;
         for (int kb = 0; kb < kbs; ++kb, ++it, ak += GM_BK, wk += GM_BK) {
@@ -275,6 +288,13 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
           gm_tma_2d(sa + GM_A_BYTES, mw, wk, r0, &full_bar[s]);
           if (nb > 1) gm_tma_2d(sa + GM_A_BYTES + GM_W_BYTES, mw, wk, r1, &full_bar[s]);
           if (nb > 2) gm_tma_2d(sa + GM_A_BYTES + 2 * GM_W_BYTES, mw, wk, r2, &full_bar[s]);
+          if (X3) {
+            const uint32_t sb = sa + SUB_BYTES;
+            gm_tma_2d(sb, ma2, ak, m0, &full_bar[s]);
+            gm_tma_2d(sb + GM_A_BYTES, mw2, wk, r0, &full_bar[s]);
+            if (nb > 1) gm_tma_2d(sb + GM_A_BYTES + GM_W_BYTES, mw2, wk, r1, &full_bar[s]);
+            if (nb > 2) gm_tma_2d(sb + GM_A_BYTES + 2 * GM_W_BYTES, mw2, wk, r2, &full_bar[s]);
+          }
         }
       }
     }
@@ -290,13 +310,17 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
       for (int p = 0; p < g.n_phases; ++p) {
         const GemmPhase& ph = g.ph[p];
         const int nb = ph.nb, kbs = ph.k_blocks;
-        uint32_t dcol[3], fresh[3];
+        uint32_t dcol[3], fresh[3], dsm[3], fresh_sm[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           const int a = i < nb ? ph.acc[i] : 0;
           dcol[i] = tmem + (uint32_t)(a * GM_BN);
           fresh[i] = i < nb ? (((touched >> a) & 1u) ^ 1u) : 0u;   // first instruction into this accumulator overwrites
           if (i < nb) touched |= 1u << a;
+          const int b = (X3 && i < nb) ? ph.acc_small[i] : 0;
+          dsm[i] = tmem + (uint32_t)(b * GM_BN);
+          fresh_sm[i] = (X3 && i < nb) ? (((touched >> b) & 1u) ^ 1u) : 0u;
+          if (X3 && i < nb) touched |= 1u << b;
         }
         for (int kb = 0; kb < kbs; ++kb, ++it) {
           const uint32_t s = it % GM_STAGES, par = (it / GM_STAGES) & 1u;
@@ -308,6 +332,16 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
             if (i < nb) {
               const uint32_t w_lo = a_lo + ((GM_A_BYTES + i * GM_W_BYTES) >> 4);
               const uint32_t acc0 = (kb > 0) ? 1u : (fresh[i] ^ 1u);
+              if (X3) {   // the two cross products of this K block: A_lo W_hi, then A_hi W_lo, into the small accumulator
+                const uint32_t a2 = a_lo + (SUB_BYTES >> 4), w2 = w_lo + (SUB_BYTES >> 4);
+                const uint32_t sm0 = (kb > 0) ? 1u : (fresh_sm[i] ^ 1u);
+#pragma unroll
+                for (int k = 0; k < GM_BK / 8; ++k)
+                  gm_mma_tf32(dsm[i], gm_desc(a2 + 2 * k), gm_desc(w_lo + 2 * k), k > 0 ? 1u : sm0);
+#pragma unroll
+                for (int k = 0; k < GM_BK / 8; ++k)
+                  gm_mma_tf32(dsm[i], gm_desc(a_lo + 2 * k), gm_desc(w2 + 2 * k), 1u);
+              }
 #pragma unroll
               for (int k = 0; k < GM_BK / 8; ++k)   // UMMA_K = 8 TF32 = 32 bytes along the swizzled row
                 gm_mma_tf32(dcol[i], gm_desc(a_lo + 2 * k), gm_desc(w_lo + 2 * k), k > 0 ? 1u : acc0);
@@ -610,12 +644,12 @@ static inline bool gm_make_map(CUtensorMap* m, const float* base, uint64_t inner
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int EPI, int NSLAB, int NACC, int GM_STAGES>
+template <int EPI, int NSLAB, int NACC, int GM_STAGES, bool X3 = false>
 static inline cudaError_t gm_launch(const GemmMaps& maps, const GemmArgs& g, cudaStream_t s) {
-  constexpr size_t smem = (size_t)GM_STAGES * (GM_A_BYTES + NSLAB * GM_W_BYTES) + 1024;
+  constexpr size_t smem = (size_t)GM_STAGES * (X3 ? 2 : 1) * (GM_A_BYTES + NSLAB * GM_W_BYTES) + 1024;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_dense<EPI, NSLAB, NACC, GM_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_dense<EPI, NSLAB, NACC, GM_STAGES, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr = true;
   }
@@ -629,5 +663,5 @@ static inline cudaError_t gm_launch(const GemmMaps& maps, const GemmArgs& g, cud
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k_dense<EPI, NSLAB, NACC, GM_STAGES>, maps, g);
+  return cudaLaunchKernelEx(&cfg, k_dense<EPI, NSLAB, NACC, GM_STAGES, X3>, maps, g);
 }
