@@ -35,7 +35,10 @@
 #define GM_BK 32                      // float32 elements per K block = one 128-byte swizzle row
 #define GM_A_BYTES (GM_BM * 128)      // 16 KB
 #define GM_W_BYTES (GM_BN * 128)      // 8 KB
-#define GM_THREADS 192                // warp 0: TMA producer, warp 1: TMEM allocator + MMA issuer, warps 2-5: epilogue
+#ifndef GM_EPI_GROUPS
+#define GM_EPI_GROUPS 2               // epilogue warp groups: group p of 4 warps handles columns [p, p + 1) * 64 / GROUPS of the tile
+#endif
+#define GM_THREADS (64 + 128 * GM_EPI_GROUPS)   // warp 0: TMA producer, warp 1: TMEM allocator + MMA issuer, then the epilogue warps
 #define GM_STOCH 30                   // RSSM stochastic state size of the shipped agents [REF racing_dreamer.py:20]
 
 #define GM_MAX_PHASES 12
@@ -354,8 +357,14 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
     }
     __syncwarp();
   } else {
-    // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 = tile rows =====
+    // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 = tile rows; the GM_EPI_GROUPS warps that share a lane
+    // quarter split the tile's columns.  (Per-CTA clock stamps: after the issuer fix the epilogue -- one warp per
+    // scheduler working through 64 columns of bias / activation / TF32 split / row-strided stores -- was 6-7 us of a
+    // 14 us actor layer and 21 us of the GRU cell, profiles/r3t_dreamer_kdense_analysis.txt.) =====
     const int q = warp & 3;
+    const int part = (warp - 2) >> 2;                        // 0 .. GM_EPI_GROUPS - 1
+    constexpr int PART_COLS = GM_BN / GM_EPI_GROUPS;
+    const int cbeg = part * PART_COLS, cend = cbeg + PART_COLS;
     const int row = m0 + q * 32 + lane;
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -364,7 +373,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
     const bool live = row < g.M;
     if constexpr (EPI == EPI_DENSE) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < GM_BN; c0 += 16) {
+      for (int c0 = cbeg; c0 < cend; c0 += 16) {
         if (n0 + c0 >= g.N) break;   // warp-uniform
         float v[16];
         gm_tmem_sum16(tl + c0, g.n_acc, 1, v);
@@ -393,7 +402,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
       const float* bx = g.bias;
       const float* bh = g.bias + 3 * H;
 #pragma unroll 1
-      for (int c0 = 0; c0 < GM_BN; c0 += 8) {
+      for (int c0 = cbeg; c0 < cend; c0 += 8) {
         if (n0 + c0 >= H) break;
         float az[8], ar[8], axh[8], arh[8];
         gm_tmem_sum8(tl + 0 * GM_BN + c0, g.n_acc, 4, az);    // accumulator a of gate q sits at column (4 a + q) * 64
@@ -451,6 +460,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
         const uint32_t gid = g.gid0 + (uint32_t)row;
 #pragma unroll
         for (int j0 = 0; j0 < 32; j0 += 4) {
+          if (j0 / (32 / GM_EPI_GROUPS) != part) continue;   // warp-uniform: this group's share of the 30 latents
           float z[4] = {0.f, 0.f, 0.f, 0.f};
           if (g.noise == GM_NOISE_PHILOX) gm_normal4(gid, g.step, (uint32_t)j0, RD_STREAM_STOCH, g.key0, g.key1, z);
 #pragma unroll
@@ -476,7 +486,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
       // SampleDist.mode() need many more threads than this tile has rows (k_actor_mode)
       float v[8];
       gm_tmem_sum8(tl, g.n_acc, 1, v);
-      if (live) {
+      if (live && part == 0) {
         float4 o;
         o.x = v[0] + __ldg(g.bias + 0); o.y = v[1] + __ldg(g.bias + 1); o.z = v[2] + __ldg(g.bias + 2); o.w = v[3] + __ldg(g.bias + 3);
         *reinterpret_cast<float4*>(g.out + (size_t)row * 4) = o;
