@@ -17,6 +17,11 @@
 
 #include "rd_gemm.cuh"
 
+// epilogue warp groups of the launches that have an SM to themselves (GRU cell, obs1, obs2 + posterior)
+#ifndef DR_EW_WIDE
+#define DR_EW_WIDE 4
+#endif
+
 struct DreamerPolicy {
   bool ready = false;
   int n = 0, deter = 0, hidden = 0, embed = 0, units = 0, layers = 0, ldf = 0;
@@ -281,7 +286,7 @@ static inline int dreamer_step(DreamerPolicy& d, const float* lidar, float* acti
     dr_build(d, maps, g, t, 2, 3, rows, gate, 4, d.x3 ? 8 : 4);   // one main group (every gate slot must be fed), one small
     g.bias = d.b_gru; g.out = d.v_det[nxt].p[0]; g.out_lo = d.v_det[nxt].p[1]; g.ldo = d.ldf;
     g.hold = d.v_det[cur].p[0]; g.hold_lo = d.v_det[cur].p[1]; g.ldh = d.ldf;
-    if (d.x3) DR_TRY((gm_launch<EPI_GRU, 3, 8, 2, true>(maps, g, s)));
+    if (d.x3) DR_TRY((gm_launch<EPI_GRU, 3, 8, 2, true, DR_EW_WIDE>(maps, g, s)));
     else DR_TRY((gm_launch<EPI_GRU, 3, 8, 4>(maps, g, s)));
     ++*launched;
   }
@@ -292,7 +297,7 @@ static inline int dreamer_step(DreamerPolicy& d, const float* lidar, float* acti
     const DrTerm t[2] = {{&d.v_det[nxt], &d.w_obs1, D, 0}, {&d.lidar, &d.w_obs1, d.embed, D}};
     dr_build(d, maps, g, t, 2, 1, nullptr, nullptr, 1, 8);
     g.bias = d.b_obs1; g.out = d.hobs.p[0]; g.out_lo = d.hobs.p[1]; g.ldo = H; g.act = 1;
-    if (d.x3) DR_TRY((gm_launch<EPI_DENSE, 1, 8, 4, true>(maps, g, s)));
+    if (d.x3) DR_TRY((gm_launch<EPI_DENSE, 1, 8, 4, true, DR_EW_WIDE>(maps, g, s)));
     else DR_TRY((gm_launch<EPI_DENSE, 1, 8, 8>(maps, g, s)));
     ++*launched;
   }
@@ -306,7 +311,7 @@ static inline int dreamer_step(DreamerPolicy& d, const float* lidar, float* acti
     g.noise = noise; g.eps = eps_stoch; g.ld_eps = GM_STOCH;
     g.key0 = (uint32_t)seed; g.key1 = (uint32_t)(seed >> 32) ^ RD_STREAM_STOCH; g.step = d.step; g.gid0 = gid0;
     g.dbg = debug;
-    if (d.x3) DR_TRY((gm_launch<EPI_STOCH, 1, 4, 4, true>(maps, g, s)));
+    if (d.x3) DR_TRY((gm_launch<EPI_STOCH, 1, 4, 4, true, DR_EW_WIDE>(maps, g, s)));
     else DR_TRY((gm_launch<EPI_STOCH, 1, 4, 4>(maps, g, s)));
     ++*launched;
   }

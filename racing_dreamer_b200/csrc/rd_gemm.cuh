@@ -228,8 +228,8 @@ __device__ __forceinline__ void gm_normal4(uint32_t c0, uint32_t c1, uint32_t c2
 // ---------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------
-template <int EPI, int NSLAB, int NACC, int GM_STAGES, bool X3 = false>
-__global__ void __launch_bounds__(GM_THREADS, 1)
+template <int EPI, int NSLAB, int NACC, int GM_STAGES, bool X3 = false, int EW = GM_EPI_GROUPS>
+__global__ void __launch_bounds__(64 + 128 * EW, 1)
     k_dense(const __grid_constant__ GemmMaps maps, const GemmArgs g) {
   extern __shared__ uint8_t gm_smem_raw[];
   __shared__ uint64_t full_bar[GM_STAGES], empty_bar[GM_STAGES], acc_bar;
@@ -362,8 +362,8 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
     // scheduler working through 64 columns of bias / activation / TF32 split / row-strided stores -- was 6-7 us of a
     // 14 us actor layer and 21 us of the GRU cell, profiles/r3t_dreamer_kdense_analysis.txt.) =====
     const int q = warp & 3;
-    const int part = (warp - 2) >> 2;                        // 0 .. GM_EPI_GROUPS - 1
-    constexpr int PART_COLS = GM_BN / GM_EPI_GROUPS;
+    const int part = (warp - 2) >> 2;                        // 0 .. EW - 1
+    constexpr int PART_COLS = GM_BN / EW;
     const int cbeg = part * PART_COLS, cend = cbeg + PART_COLS;
     const int row = m0 + q * 32 + lane;
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
         const uint32_t gid = g.gid0 + (uint32_t)row;
 #pragma unroll
         for (int j0 = 0; j0 < 32; j0 += 4) {
-          if (j0 / (32 / GM_EPI_GROUPS) != part) continue;   // warp-uniform: this group's share of the 30 latents
+          if (j0 / (32 / EW) != part) continue;   // warp-uniform: this group's share of the 30 latents
           float z[4] = {0.f, 0.f, 0.f, 0.f};
           if (g.noise == GM_NOISE_PHILOX) gm_normal4(gid, g.step, (uint32_t)j0, RD_STREAM_STOCH, g.key0, g.key1, z);
 #pragma unroll
@@ -654,18 +654,18 @@ static inline bool gm_make_map(CUtensorMap* m, const float* base, uint64_t inner
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int EPI, int NSLAB, int NACC, int GM_STAGES, bool X3 = false>
+template <int EPI, int NSLAB, int NACC, int GM_STAGES, bool X3 = false, int EW = GM_EPI_GROUPS>
 static inline cudaError_t gm_launch(const GemmMaps& maps, const GemmArgs& g, cudaStream_t s) {
   constexpr size_t smem = (size_t)GM_STAGES * (X3 ? 2 : 1) * (GM_A_BYTES + NSLAB * GM_W_BYTES) + 1024;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_dense<EPI, NSLAB, NACC, GM_STAGES, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_dense<EPI, NSLAB, NACC, GM_STAGES, X3, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)((g.M + GM_BM - 1) / GM_BM), (unsigned)((g.N + GM_BN - 1) / GM_BN));
-  cfg.blockDim = dim3(GM_THREADS);
+  cfg.blockDim = dim3(64 + 128 * EW);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute attrs[1];
@@ -673,5 +673,5 @@ static inline cudaError_t gm_launch(const GemmMaps& maps, const GemmArgs& g, cud
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k_dense<EPI, NSLAB, NACC, GM_STAGES, X3>, maps, g);
+  return cudaLaunchKernelEx(&cfg, k_dense<EPI, NSLAB, NACC, GM_STAGES, X3, EW>, maps, g);
 }
