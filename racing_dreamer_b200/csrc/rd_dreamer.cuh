@@ -272,7 +272,7 @@ static inline int dreamer_step(DreamerPolicy& d, const float* lidar, float* acti
     const DrTerm t[1] = {{&d.v_sa[cur], &d.w_img1, 32, 0}};
     dr_build(d, maps, g, t, 1, 1, nullptr, nullptr, 1, 4);
     g.bias = d.b_img1; g.out = d.x1.p[0]; g.out_lo = d.x1.p[1]; g.ldo = H; g.act = 1;
-    if (d.x3) DR_TRY((gm_launch<EPI_DENSE, 1, 4, 2, true>(maps, g, s)));
+    if (d.x3) DR_TRY((gm_launch<EPI_DENSE, 1, 4, 2, true, DR_EW_WIDE>(maps, g, s)));
     else DR_TRY((gm_launch<EPI_DENSE, 1, 4, 4>(maps, g, s)));
     ++*launched;
   }

@@ -268,36 +268,48 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
 
   if (warp == 0) {
     if (gm_elect_one()) {   // ===== TMA producer =====
-      asm volatile("griddepcontrol.wait;" ::: "memory");
       // like the issuer below, this thread's instruction stream bounds a K block: everything that does not change from
-      // one K block to the next is set up per phase
-      uint32_t it = 0;
-      for (int p = 0; p < g.n_phases; ++p) {
-        const GemmPhase& ph = g.ph[p];
-        const CUtensorMap* ma = &maps.a[ph.a_map];
-        const CUtensorMap* mw = &maps.w[ph.w_map];
-        const int nb = ph.nb, kbs = ph.k_blocks;
-        const CUtensorMap* ma2 = &maps.a[X3 ? ph.a_map_lo : ph.a_map];
-        const CUtensorMap* mw2 = &maps.w[X3 ? ph.w_map_lo : ph.w_map];
-        const uint32_t tx = (X3 ? 2u : 1u) * (GM_A_BYTES + (uint32_t)nb * GM_W_BYTES);
-        int ak = ph.a_k0, wk = ph.w_k0;
-        const int r0 = ph.w_row0[0] + n0, r1 = ph.w_row0[1] + n0, r2 = ph.w_row0[2] + n0;
-        for (int kb = 0; kb < kbs; ++kb, ++it, ak += GM_BK, wk += GM_BK) {
-          const uint32_t s = it % GM_STAGES, par = (it / GM_STAGES) & 1u;
-          gm_mbar_wait(&empty_bar[s], par ^ 1u);
-          const uint32_t sa = smem_base + s * STAGE_BYTES;
-          rd_mbar_expect_tx(&full_bar[s], tx);
-          gm_tma_2d(sa, ma, ak, m0, &full_bar[s]);
-          gm_tma_2d(sa + GM_A_BYTES, mw, wk, r0, &full_bar[s]);
-          if (nb > 1) gm_tma_2d(sa + GM_A_BYTES + GM_W_BYTES, mw, wk, r1, &full_bar[s]);
-          if (nb > 2) gm_tma_2d(sa + GM_A_BYTES + 2 * GM_W_BYTES, mw, wk, r2, &full_bar[s]);
-          if (X3) {
-            const uint32_t sb = sa + SUB_BYTES;
-            gm_tma_2d(sb, ma2, ak, m0, &full_bar[s]);
-            gm_tma_2d(sb + GM_A_BYTES, mw2, wk, r0, &full_bar[s]);
-            if (nb > 1) gm_tma_2d(sb + GM_A_BYTES + GM_W_BYTES, mw2, wk, r1, &full_bar[s]);
-            if (nb > 2) gm_tma_2d(sb + GM_A_BYTES + 2 * GM_W_BYTES, mw2, wk, r2, &full_bar[s]);
+      // one K block to the next is set up per phase.
+      // The weights do not depend on the kernel in front of this one: the weight tiles of the first GM_STAGES K blocks
+      // are requested BEFORE griddepcontrol.wait (pass 0), the activation tiles of those K blocks and everything else
+      // after it (pass 1) -- the ring is full of weights by the time the previous layer's outputs exist.
+      for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) asm volatile("griddepcontrol.wait;" ::: "memory");
+        uint32_t it = 0;
+        for (int p = 0; p < g.n_phases; ++p) {
+          const GemmPhase& ph = g.ph[p];
+          const CUtensorMap* ma = &maps.a[ph.a_map];
+          const CUtensorMap* mw = &maps.w[ph.w_map];
+          const int nb = ph.nb, kbs = ph.k_blocks;
+          const CUtensorMap* ma2 = &maps.a[X3 ? ph.a_map_lo : ph.a_map];
+          const CUtensorMap* mw2 = &maps.w[X3 ? ph.w_map_lo : ph.w_map];
+          const uint32_t tx = (X3 ? 2u : 1u) * (GM_A_BYTES + (uint32_t)nb * GM_W_BYTES);
+          int ak = ph.a_k0, wk = ph.w_k0;
+          const int r0 = ph.w_row0[0] + n0, r1 = ph.w_row0[1] + n0, r2 = ph.w_row0[2] + n0;
+          for (int kb = 0; kb < kbs; ++kb, ++it, ak += GM_BK, wk += GM_BK) {
+            if (pass == 0 && it >= (uint32_t)GM_STAGES) break;
+            const uint32_t s = it % GM_STAGES, par = (it / GM_STAGES) & 1u;
+            const bool early = it < (uint32_t)GM_STAGES;       // first use of the slot: nothing to wait for
+            const bool do_w = pass == 0 || !early, do_a = pass == 1;
+            const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + SUB_BYTES;
+            if (!early) gm_mbar_wait(&empty_bar[s], par ^ 1u);
+            if (do_w) {
+              rd_mbar_expect_tx(&full_bar[s], tx);
+              gm_tma_2d(sa + GM_A_BYTES, mw, wk, r0, &full_bar[s]);
+              if (nb > 1) gm_tma_2d(sa + GM_A_BYTES + GM_W_BYTES, mw, wk, r1, &full_bar[s]);
+              if (nb > 2) gm_tma_2d(sa + GM_A_BYTES + 2 * GM_W_BYTES, mw, wk, r2, &full_bar[s]);
+              if (X3) {
+                gm_tma_2d(sb + GM_A_BYTES, mw2, wk, r0, &full_bar[s]);
+                if (nb > 1) gm_tma_2d(sb + GM_A_BYTES + GM_W_BYTES, mw2, wk, r1, &full_bar[s]);
+                if (nb > 2) gm_tma_2d(sb + GM_A_BYTES + 2 * GM_W_BYTES, mw2, wk, r2, &full_bar[s]);
+              }
+            }
+            if (do_a) {
+              gm_tma_2d(sa, ma, ak, m0, &full_bar[s]);
+              if (X3) gm_tma_2d(sb, ma2, ak, m0, &full_bar[s]);
+            }
           }
+          if (pass == 0 && it >= (uint32_t)GM_STAGES) break;
         }
       }
     }
