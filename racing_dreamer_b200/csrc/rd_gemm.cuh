@@ -150,11 +150,11 @@ __device__ __forceinline__ uint32_t gm_desc_lo(uint32_t addr) { return ((addr & 
 #define GM_DESC_HI ((uint32_t)((64ull << 32 | 1ull << 46 | 2ull << 61) >> 32))
 __device__ __forceinline__ uint64_t gm_desc(uint32_t lo) { return ((uint64_t)GM_DESC_HI << 32) | lo; }
 // cute::UMMA::InstrDescriptor: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), both K-major, N >> 3 at bit 17, M >> 4 at 24
-#define GM_IDESC ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GM_BN >> 3) << 17) | ((uint32_t)(GM_BM >> 4) << 24))
-__device__ __forceinline__ void gm_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+#define GM_IDESC_N(BN_) ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((BN_) >> 3) << 17) | ((uint32_t)(GM_BM >> 4) << 24))
+__device__ __forceinline__ void gm_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(GM_IDESC), "r"(accumulate)
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // 32 lanes x 32 bit x N columns: thread i of the warp receives TMEM lane (lane_base + i), N consecutive columns
@@ -181,11 +181,11 @@ __device__ __forceinline__ void gm_tmem_ld8(uint32_t taddr, float (&v)[8]) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 // the same columns of n_acc accumulators (GM_BN * stride columns apart), added in round-to-nearest float32
-__device__ __forceinline__ void gm_tmem_sum16(uint32_t taddr, int n_acc, int stride, float (&v)[16]) {
+__device__ __forceinline__ void gm_tmem_sum16(uint32_t taddr, int n_acc, int stride, float (&v)[16], int bn = GM_BN) {
   gm_tmem_ld16(taddr, v);
   for (int a = 1; a < n_acc; ++a) {
     float t[16];
-    gm_tmem_ld16(taddr + (uint32_t)(a * stride * GM_BN), t);
+    gm_tmem_ld16(taddr + (uint32_t)(a * stride * bn), t);
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] += t[i];
   }
@@ -228,7 +228,7 @@ __device__ __forceinline__ void gm_normal4(uint32_t c0, uint32_t c1, uint32_t c2
 // ---------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------
-template <int EPI, int NSLAB, int NACC, int GM_STAGES, bool X3 = false, int EW = GM_EPI_GROUPS>
+template <int EPI, int NSLAB, int NACC, int GM_STAGES, bool X3 = false, int EW = GM_EPI_GROUPS, int BN = GM_BN>
 __global__ void __launch_bounds__(64 + 128 * EW, 1)
     k_dense(const __grid_constant__ GemmMaps maps, const GemmArgs g) {
   extern __shared__ uint8_t gm_smem_raw[];
@@ -237,12 +237,14 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
   // X3: a ring stage holds the hi AND the lo tiles of a K block ([A_hi | W_hi slabs | A_lo | W_lo slabs]) and feeds all
   // three products of the float32-grade scheme from one load: two thirds of the operand bytes of three separate passes
   // and a third of the producer / issuer hand-offs.
-  constexpr uint32_t SUB_BYTES = GM_A_BYTES + NSLAB * GM_W_BYTES;
+  static_assert(BN % 16 == 0 && BN <= 256 && NACC * BN <= 512, "MMA N and the accumulators' TMEM columns");
+  constexpr uint32_t W_BYTES = BN * 128, IDESC = GM_IDESC_N(BN);
+  constexpr uint32_t SUB_BYTES = GM_A_BYTES + NSLAB * W_BYTES;
   constexpr uint32_t STAGE_BYTES = (X3 ? 2u : 1u) * SUB_BYTES;
-  constexpr uint32_t TM_COLS = (NACC * GM_BN <= 64) ? 64 : (NACC * GM_BN <= 128 ? 128 : (NACC * GM_BN <= 256 ? 256 : 512));
+  constexpr uint32_t TM_COLS = (NACC * BN <= 64) ? 64 : (NACC * BN <= 128 ? 128 : (NACC * BN <= 256 ? 256 : 512));
   const uint32_t smem_base = (rd_smem_u32(gm_smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles: 1024-byte aligned
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * GM_BM, n0 = blockIdx.y * GM_BN;
+  const int m0 = blockIdx.x * GM_BM, n0 = blockIdx.y * BN;
 
   if (threadIdx.x == 0) {
     for (int p = 0; p < g.n_phases; ++p) {
@@ -283,7 +285,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
           const int nb = ph.nb, kbs = ph.k_blocks;
           const CUtensorMap* ma2 = &maps.a[X3 ? ph.a_map_lo : ph.a_map];
           const CUtensorMap* mw2 = &maps.w[X3 ? ph.w_map_lo : ph.w_map];
-          const uint32_t tx = (X3 ? 2u : 1u) * (GM_A_BYTES + (uint32_t)nb * GM_W_BYTES);
+          const uint32_t tx = (X3 ? 2u : 1u) * (GM_A_BYTES + (uint32_t)nb * W_BYTES);
           int ak = ph.a_k0, wk = ph.w_k0;
           const int r0 = ph.w_row0[0] + n0, r1 = ph.w_row0[1] + n0, r2 = ph.w_row0[2] + n0;
           for (int kb = 0; kb < kbs; ++kb, ++it, ak += GM_BK, wk += GM_BK) {
@@ -296,12 +298,12 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
             if (do_w) {
               rd_mbar_expect_tx(&full_bar[s], tx);
               gm_tma_2d(sa + GM_A_BYTES, mw, wk, r0, &full_bar[s]);
-              if (nb > 1) gm_tma_2d(sa + GM_A_BYTES + GM_W_BYTES, mw, wk, r1, &full_bar[s]);
-              if (nb > 2) gm_tma_2d(sa + GM_A_BYTES + 2 * GM_W_BYTES, mw, wk, r2, &full_bar[s]);
+              if (nb > 1) gm_tma_2d(sa + GM_A_BYTES + W_BYTES, mw, wk, r1, &full_bar[s]);
+              if (nb > 2) gm_tma_2d(sa + GM_A_BYTES + 2 * W_BYTES, mw, wk, r2, &full_bar[s]);
               if (X3) {
                 gm_tma_2d(sb + GM_A_BYTES, mw2, wk, r0, &full_bar[s]);
-                if (nb > 1) gm_tma_2d(sb + GM_A_BYTES + GM_W_BYTES, mw2, wk, r1, &full_bar[s]);
-                if (nb > 2) gm_tma_2d(sb + GM_A_BYTES + 2 * GM_W_BYTES, mw2, wk, r2, &full_bar[s]);
+                if (nb > 1) gm_tma_2d(sb + GM_A_BYTES + W_BYTES, mw2, wk, r1, &full_bar[s]);
+                if (nb > 2) gm_tma_2d(sb + GM_A_BYTES + 2 * W_BYTES, mw2, wk, r2, &full_bar[s]);
               }
             }
             if (do_a) {
@@ -329,11 +331,11 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           const int a = i < nb ? ph.acc[i] : 0;
-          dcol[i] = tmem + (uint32_t)(a * GM_BN);
+          dcol[i] = tmem + (uint32_t)(a * BN);
           fresh[i] = i < nb ? (((touched >> a) & 1u) ^ 1u) : 0u;   // first instruction into this accumulator overwrites
           if (i < nb) touched |= 1u << a;
           const int b = (X3 && i < nb) ? ph.acc_small[i] : 0;
-          dsm[i] = tmem + (uint32_t)(b * GM_BN);
+          dsm[i] = tmem + (uint32_t)(b * BN);
           fresh_sm[i] = (X3 && i < nb) ? (((touched >> b) & 1u) ^ 1u) : 0u;
           if (X3 && i < nb) touched |= 1u << b;
         }
@@ -345,21 +347,21 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
             if (i < nb) {
-              const uint32_t w_lo = a_lo + ((GM_A_BYTES + i * GM_W_BYTES) >> 4);
+              const uint32_t w_lo = a_lo + ((GM_A_BYTES + i * W_BYTES) >> 4);
               const uint32_t acc0 = (kb > 0) ? 1u : (fresh[i] ^ 1u);
               if (X3) {   // the two cross products of this K block: A_lo W_hi, then A_hi W_lo, into the small accumulator
                 const uint32_t a2 = a_lo + (SUB_BYTES >> 4), w2 = w_lo + (SUB_BYTES >> 4);
                 const uint32_t sm0 = (kb > 0) ? 1u : (fresh_sm[i] ^ 1u);
 #pragma unroll
                 for (int k = 0; k < GM_BK / 8; ++k)
-                  gm_mma_tf32(dsm[i], gm_desc(a2 + 2 * k), gm_desc(w_lo + 2 * k), k > 0 ? 1u : sm0);
+                  gm_mma_tf32(dsm[i], gm_desc(a2 + 2 * k), gm_desc(w_lo + 2 * k), IDESC, k > 0 ? 1u : sm0);
 #pragma unroll
                 for (int k = 0; k < GM_BK / 8; ++k)
-                  gm_mma_tf32(dsm[i], gm_desc(a_lo + 2 * k), gm_desc(w2 + 2 * k), 1u);
+                  gm_mma_tf32(dsm[i], gm_desc(a_lo + 2 * k), gm_desc(w2 + 2 * k), IDESC, 1u);
               }
 #pragma unroll
               for (int k = 0; k < GM_BK / 8; ++k)   // UMMA_K = 8 TF32 = 32 bytes along the swizzled row
-                gm_mma_tf32(dcol[i], gm_desc(a_lo + 2 * k), gm_desc(w_lo + 2 * k), k > 0 ? 1u : acc0);
+                gm_mma_tf32(dcol[i], gm_desc(a_lo + 2 * k), gm_desc(w_lo + 2 * k), IDESC, k > 0 ? 1u : acc0);
             }
           }
           gm_commit(&empty_bar[s]);   // the slot is free once these MMAs have read it
@@ -375,7 +377,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
     // 14 us actor layer and 21 us of the GRU cell, profiles/r3t_dreamer_kdense_analysis.txt.) =====
     const int q = warp & 3;
     const int part = (warp - 2) >> 2;                        // 0 .. EW - 1
-    constexpr int PART_COLS = GM_BN / EW;
+    constexpr int PART_COLS = (EPI == EPI_DENSE ? BN : GM_BN) / EW;
     const int cbeg = part * PART_COLS, cend = cbeg + PART_COLS;
     const int row = m0 + q * 32 + lane;
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
@@ -388,7 +390,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
       for (int c0 = cbeg; c0 < cend; c0 += 16) {
         if (n0 + c0 >= g.N) break;   // warp-uniform
         float v[16];
-        gm_tmem_sum16(tl + c0, g.n_acc, 1, v);
+        gm_tmem_sum16(tl + c0, g.n_acc, 1, v, BN);
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
           const int col = n0 + c0 + j;
@@ -666,17 +668,17 @@ static inline bool gm_make_map(CUtensorMap* m, const float* base, uint64_t inner
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int EPI, int NSLAB, int NACC, int GM_STAGES, bool X3 = false, int EW = GM_EPI_GROUPS>
+template <int EPI, int NSLAB, int NACC, int GM_STAGES, bool X3 = false, int EW = GM_EPI_GROUPS, int BN = GM_BN>
 static inline cudaError_t gm_launch(const GemmMaps& maps, const GemmArgs& g, cudaStream_t s) {
-  constexpr size_t smem = (size_t)GM_STAGES * (X3 ? 2 : 1) * (GM_A_BYTES + NSLAB * GM_W_BYTES) + 1024;
+  constexpr size_t smem = (size_t)GM_STAGES * (X3 ? 2 : 1) * (GM_A_BYTES + NSLAB * BN * 128) + 1024;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_dense<EPI, NSLAB, NACC, GM_STAGES, X3, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_dense<EPI, NSLAB, NACC, GM_STAGES, X3, EW, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr = true;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)((g.M + GM_BM - 1) / GM_BM), (unsigned)((g.N + GM_BN - 1) / GM_BN));
+  cfg.gridDim = dim3((unsigned)((g.M + GM_BM - 1) / GM_BM), (unsigned)((g.N + BN - 1) / BN));
   cfg.blockDim = dim3(64 + 128 * EW);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
@@ -685,5 +687,5 @@ static inline cudaError_t gm_launch(const GemmMaps& maps, const GemmArgs& g, cud
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k_dense<EPI, NSLAB, NACC, GM_STAGES, X3, EW>, maps, g);
+  return cudaLaunchKernelEx(&cfg, k_dense<EPI, NSLAB, NACC, GM_STAGES, X3, EW, BN>, maps, g);
 }
