@@ -589,6 +589,13 @@ def config_leg(cx, cfg_id, steps, e2e_steps, shards):
            "l2": "flushed between steps", "episode_stats_rank0": d["stats"]}
     if cfg_id == 4:   # collisions / laps / time limits fire: terminations per second of device time
         leg["terminations_per_s"] = cx.world * d["stats"]["episodes"] / (d["ms_per_step"] * d["steps"] / 1e3)
+    if cfg_id == 5 and n % 8 == 0:
+        # Strong scaling of this config needs no second box: the envs shard with no exchange, so the step time of an
+        # 8-GPU job over these n envs IS one GPU's step time over n/8 envs (measured here, same flush, same events).
+        s = device_leg(cx, wl, n // 8, steps, 3, back_to_back=False)
+        leg["strong_shard_of_8"] = {"envs_per_gpu": n // 8, "ms_per_step": s["ms_per_step"], "kernel_ms": s["kernel_ms"],
+                                    "speedup_over_one_gpu": d["ms_per_step"] / s["ms_per_step"],
+                                    "note": "time of one of eight shards of the same batch; no collective in step"}
     return leg
 
 

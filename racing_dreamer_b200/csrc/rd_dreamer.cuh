@@ -11,6 +11,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -49,6 +50,12 @@ struct DreamerPolicy {
   // activations.  feat[p]: latent rows; sa/det/all are views of the same rows (img1 input, deter, actor input)
   Operand feat[2], v_sa[2], v_det[2], x1, hobs, hid[2], lidar;
   float* head_raw = nullptr;   // [n][4] hout pre-activations
+  // k_dense_chain (the actor trunk in one launch): per-row-block layer counters and the values they have reached
+  bool chain = true;           // RD_DREAMER_CHAIN=0: one k_dense launch per actor layer instead
+  bool tma_out = true;         // RD_DREAMER_TMA_OUT=0: Dense / GRU epilogues store from registers (see gm_stage_f4)
+  unsigned* chain_flags = nullptr;
+  unsigned chain_count[GM_CHAIN_MAX] = {};
+  int sm_count = 148;
   int cur = 0;           // feat[cur] holds the latest latent
   uint32_t step = 0;     // agent steps taken (Philox counter)
   std::string err;
@@ -180,6 +187,20 @@ static inline int dreamer_init(DreamerPolicy& d, int n, int n_beams, bool lidar_
   }
   DR_TRY(cudaMalloc(&d.head_raw, N * 4 * sizeof(float)));
   d.owned.push_back(d.head_raw);
+  {
+    const size_t row_blocks = (N + GM_BM - 1) / GM_BM;
+    DR_TRY(cudaMalloc(&d.chain_flags, GM_CHAIN_MAX * row_blocks * sizeof(unsigned)));
+    d.owned.push_back(reinterpret_cast<float*>(d.chain_flags));
+    DR_TRY(cudaMemset(d.chain_flags, 0, GM_CHAIN_MAX * row_blocks * sizeof(unsigned)));
+    for (unsigned& c : d.chain_count) c = 0;
+    int dev = 0;
+    DR_TRY(cudaGetDevice(&dev));
+    DR_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
+    d.chain = true;
+    if (const char* ev = std::getenv("RD_DREAMER_CHAIN")) d.chain = std::atoi(ev) != 0;
+    d.tma_out = true;
+    if (const char* ev = std::getenv("RD_DREAMER_TMA_OUT")) d.tma_out = std::atoi(ev) != 0;
+  }
   DR_TRY(dr_alloc(d, d.x1, N, H));
   DR_TRY(dr_alloc(d, d.hobs, N, H));
   DR_TRY(dr_alloc(d, d.lidar, N, E));   // the embedded scans (k_embed_lidar)
@@ -282,6 +303,7 @@ static inline int dreamer_step(DreamerPolicy& d, const float* lidar, float* acti
     const DrTerm t[1] = {{&d.v_sa[cur], &d.w_img1, 32, 0}};
     dr_build(d, maps, g, t, 1, 1, nullptr, nullptr, 1, 4);
     g.bias = d.b_img1; g.out = d.x1.p[0]; g.out_lo = d.x1.p[1]; g.ldo = H; g.act = 1;
+    g.tma_out = d.tma_out; maps.o[0] = d.x1.m[0]; maps.o[1] = d.x1.m[1];
     if (d.x3) DR_TRY((gm_launch<EPI_DENSE, 1, 4, 2, true, DR_EW_WIDE>(maps, g, s)));
     else DR_TRY((gm_launch<EPI_DENSE, 1, 4, 4>(maps, g, s)));
     ++*launched;
@@ -296,6 +318,7 @@ static inline int dreamer_step(DreamerPolicy& d, const float* lidar, float* acti
     dr_build(d, maps, g, t, 2, 3, rows, gate, 4, d.x3 ? 8 : 4);   // one main group (every gate slot must be fed), one small
     g.bias = d.b_gru; g.out = d.v_det[nxt].p[0]; g.out_lo = d.v_det[nxt].p[1]; g.ldo = d.ldf;
     g.hold = d.v_det[cur].p[0]; g.hold_lo = d.v_det[cur].p[1]; g.ldh = d.ldf;
+    g.tma_out = d.tma_out; maps.o[0] = d.v_det[nxt].m[0]; maps.o[1] = d.v_det[nxt].m[1];
     if (d.x3) DR_TRY((gm_launch<EPI_GRU, 3, 8, 2, true, DR_EW_WIDE>(maps, g, s)));
     else DR_TRY((gm_launch<EPI_GRU, 3, 8, 4>(maps, g, s)));
     ++*launched;
@@ -307,6 +330,7 @@ static inline int dreamer_step(DreamerPolicy& d, const float* lidar, float* acti
     const DrTerm t[2] = {{&d.v_det[nxt], &d.w_obs1, D, 0}, {&d.lidar, &d.w_obs1, d.embed, D}};
     dr_build(d, maps, g, t, 2, 1, nullptr, nullptr, 1, 8);
     g.bias = d.b_obs1; g.out = d.hobs.p[0]; g.out_lo = d.hobs.p[1]; g.ldo = H; g.act = 1;
+    g.tma_out = d.tma_out; maps.o[0] = d.hobs.m[0]; maps.o[1] = d.hobs.m[1];
     if (d.x3) DR_TRY((gm_launch<EPI_DENSE, 1, 8, 4, true, DR_EW_WIDE>(maps, g, s)));
     else DR_TRY((gm_launch<EPI_DENSE, 1, 8, 8>(maps, g, s)));
     ++*launched;
@@ -325,13 +349,41 @@ static inline int dreamer_step(DreamerPolicy& d, const float* lidar, float* acti
     else DR_TRY((gm_launch<EPI_STOCH, 1, 4, 4>(maps, g, s)));
     ++*launched;
   }
-  // 5. actor trunk [REF models.py:321-322]
-  for (int i = 0; i < d.layers; ++i) {
+  // 5. actor trunk [REF models.py:321-322]: float32-grade mode runs up to GM_CHAIN_MAX layers per launch (k_dense_chain)
+  const bool chain = d.x3 && d.chain;
+  for (int i0 = 0; chain && i0 < d.layers; i0 += GM_CHAIN_MAX) {
+    ChainMaps cm;
+    ChainArgs c{};
+    c.M = d.n; c.N = U; c.ldo = U; c.n_layers = std::min(GM_CHAIN_MAX, d.layers - i0);
+    c.row_blocks = (d.n + GM_BM - 1) / GM_BM;
+    c.flags = d.chain_flags;
+    const unsigned nt = (unsigned)((U + DR_ACT_BN - 1) / DR_ACT_BN) * DR_ACT_EW;   // counter increments per row block and layer
+    for (int j = 0; j < c.n_layers; ++j) {
+      const int i = i0 + j;
+      const DreamerPolicy::Operand& a = i == 0 ? d.feat[nxt] : d.hid[(i - 1) & 1];
+      GemmArgs g{};   // the K blocks and accumulator groups of the per-layer launch (bitwise the same sums)
+      const DrTerm t[1] = {{&a, &d.w_act[i], i == 0 ? d.ldf : U, 0}};
+      dr_build(d, maps, g, t, 1, 1, nullptr, nullptr, 1, 4);
+      ChainLayer& L = c.L[j];
+      L.n_groups = g.n_acc - 1;
+      L.kb_total = 0;
+      for (int p = 0; p < g.n_phases; ++p) { L.grp_blocks[g.ph[p].acc[0]] = g.ph[p].k_blocks; L.kb_total += g.ph[p].k_blocks; }
+      L.bias = d.b_act[i]; L.out = d.hid[i & 1].p[0]; L.out_lo = d.hid[i & 1].p[1];
+      if (j + 1 < c.n_layers) { d.chain_count[j] += nt; L.target = d.chain_count[j]; }
+      cm.a[j][0] = a.m[0]; cm.a[j][1] = a.m[1];
+      cm.w[j][0] = d.w_act[i].m[0]; cm.w[j][1] = d.w_act[i].m[1];
+      if (j + 1 == c.n_layers) { cm.o_last[0] = d.hid[i & 1].m[0]; cm.o_last[1] = d.hid[i & 1].m[1]; }
+    }
+    DR_TRY((gm_launch_chain<DR_ACT_STAGES, DR_ACT_EW, DR_ACT_BN>(cm, c, d.sm_count, s)));
+    ++*launched;
+  }
+  for (int i = 0; !chain && i < d.layers; ++i) {
     GemmArgs g{};
     g.M = d.n; g.N = U;
     const DrTerm t[1] = {{i == 0 ? &d.feat[nxt] : &d.hid[(i - 1) & 1], &d.w_act[i], i == 0 ? d.ldf : U, 0}};
     dr_build(d, maps, g, t, 1, 1, nullptr, nullptr, 1, 4);
     g.bias = d.b_act[i]; g.out = d.hid[i & 1].p[0]; g.out_lo = d.hid[i & 1].p[1]; g.ldo = U; g.act = 1;
+    g.tma_out = d.tma_out; maps.o[0] = d.hid[i & 1].m[0]; maps.o[1] = d.hid[i & 1].m[1];
     if (d.x3) DR_TRY((gm_launch<EPI_DENSE, 1, 4, DR_ACT_STAGES, true, DR_ACT_EW, DR_ACT_BN>(maps, g, s)));
     else DR_TRY((gm_launch<EPI_DENSE, 1, 4, 4>(maps, g, s)));
     ++*launched;
@@ -352,8 +404,18 @@ static inline int dreamer_step(DreamerPolicy& d, const float* lidar, float* acti
     if (d.x3) DR_TRY((gm_launch<EPI_ACTOR, 1, 4, 4, true>(maps, g, s)));
     else DR_TRY((gm_launch<EPI_ACTOR, 1, 4, 4>(maps, g, s)));
     ++*launched;
-    k_actor_mode<<<(unsigned)((d.n + 7) / 8), 256, 0, s>>>(g);
-    DR_TRY(cudaGetLastError());
+    {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)((d.n + 7) / 8));
+      cfg.blockDim = dim3(256);
+      cfg.stream = s;
+      cudaLaunchAttribute attrs[1];
+      attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // griddepcontrol.wait in k_actor_mode
+      attrs[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attrs;
+      cfg.numAttrs = 1;
+      DR_TRY(cudaLaunchKernelEx(&cfg, k_actor_mode, g));
+    }
     ++*launched;
   }
   d.cur = nxt;

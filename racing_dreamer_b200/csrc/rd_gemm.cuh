@@ -28,6 +28,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <algorithm>
+
 #include "rd_common.cuh"
 
 #define GM_BM 128
@@ -45,6 +47,7 @@
 struct GemmMaps {   // tensor maps of one launch: A sources and weight matrices, hi parts and (x3 mode) lo parts
   CUtensorMap a[4];
   CUtensorMap w[4];
+  CUtensorMap o[2];  // GemmArgs::tma_out: the output rows (hi, lo), box 32 columns x 128 rows -- the view the next layer loads
 };
 struct GemmPhase {
   int a_map, w_map; // indices into GemmMaps
@@ -74,6 +77,7 @@ struct GemmArgs {
   float* out; int ldo;      // DENSE / GRU: output rows, TF32-rounded (they are only ever read as MMA operands)
   float* out_lo;            // x3 mode: TF32-rounded remainder of the same rows (same pitch), or null
   int act;                  // DENSE: 1 = ELU, 0 = linear
+  int tma_out;              // DENSE / GRU: 1 = the tile leaves through shared memory and the copy engine (maps.o), see gm_stage_f4
   const float* hold; const float* hold_lo; int ldh;   // GRU: previous deterministic state (hi [+ lo])
   // STOCH / ACTOR
   int noise;                // GM_NOISE_*
@@ -222,6 +226,36 @@ __device__ __forceinline__ void gm_normal4(uint32_t c0, uint32_t c1, uint32_t c2
     sincospif(2.0f * u2, &sn, &cs);
     z[2 * h] = r * cs;
     z[2 * h + 1] = r * sn;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Output tiles through the copy engine.  In the epilogue a thread owns a tile ROW (its TMEM lane), so a store from
+// registers puts 16 bytes into each of 32 different rows per instruction: thousands of half-sector writes per CTA,
+// measured at 8.5 us of a 16.5 us actor layer (profiles/r5b_dreamer_chain.txt).  Instead the warps build [128 rows]
+// [32 columns] tiles in shared memory -- the ring is idle by then -- in the 128-byte-swizzled layout of the tensor
+// map the NEXT layer loads these rows through, and one thread hands each tile to cp.async.bulk.tensor (rows >= M and
+// columns >= N are clipped by the map).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gm_stage_f4(uint32_t tile_smem, uint32_t r, int col_in_tile, const float4& v) {
+  const uint32_t off = r * 128u + ((((uint32_t)col_in_tile >> 2) ^ (r & 7u)) << 4);   // SWIZZLE_128B
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(tile_smem + off), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void gm_tile_store(const CUtensorMap* map, int x, int y, uint32_t tile_smem) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(x), "r"(y), "r"(tile_smem)
+               : "memory");
+}
+// The warps that share a 32-column tile (n_threads of them, barrier `bar_id`) have staged it; `leader` stores it.
+__device__ __forceinline__ void gm_tiles_out(int bar_id, int n_threads, bool leader, bool any, const CUtensorMap* m_hi,
+                                             const CUtensorMap* m_lo, int x, int y, uint32_t s_hi, uint32_t s_lo) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tiles were written through the generic proxy
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(n_threads) : "memory");
+  if (leader && any) {
+    gm_tile_store(m_hi, x, y, s_hi);
+    if (m_lo) gm_tile_store(m_lo, x, y, s_lo);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory stays valid until the engine has read it
   }
 }
 
@@ -385,16 +419,21 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
     gm_mbar_wait(&acc_bar, 0, true);
     gm_tc_fence_after();
     const bool live = row < g.M;
+    // tma_out: this part's 32-column staging tile (hi, lo) in the idle ring, and who shares it
+    constexpr int TILE_PARTS = PART_COLS >= 32 ? 1 : 32 / PART_COLS;       // column parts per staging tile
+    static_assert(PART_COLS == 16 || PART_COLS % 32 == 0, "staging tiles are 32 columns wide");
+    const uint32_t rt = (uint32_t)(q * 32 + lane);                          // tile row
     if constexpr (EPI == EPI_DENSE) {
 #pragma unroll 1
       for (int c0 = cbeg; c0 < cend; c0 += 16) {
         if (n0 + c0 >= g.N) break;   // warp-uniform
         float v[16];
         gm_tmem_sum16(tl + c0, g.n_acc, 1, v, BN);
+        const uint32_t s_hi = smem_base + (uint32_t)(c0 >> 5) * (2u * GM_A_BYTES), s_lo = s_hi + GM_A_BYTES;
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
           const int col = n0 + c0 + j;
-          if (live && col < g.N) {   // N % 4 == 0
+          if ((live || g.tma_out) && col < g.N) {   // N % 4 == 0
             float4 o, ol;
             float* po = &o.x;
             float* pl = &ol.x;
@@ -405,9 +444,22 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
               po[t] = gm_round_tf32(x);
               pl[t] = gm_round_tf32(x - po[t]);
             }
-            *reinterpret_cast<float4*>(g.out + (size_t)row * g.ldo + col) = o;
-            if (g.out_lo) *reinterpret_cast<float4*>(g.out_lo + (size_t)row * g.ldo + col) = ol;
+            if (g.tma_out) {
+              gm_stage_f4(s_hi, rt, (c0 + j) & 31, o);
+              if (g.out_lo) gm_stage_f4(s_lo, rt, (c0 + j) & 31, ol);
+            } else {
+              *reinterpret_cast<float4*>(g.out + (size_t)row * g.ldo + col) = o;
+              if (g.out_lo) *reinterpret_cast<float4*>(g.out_lo + (size_t)row * g.ldo + col) = ol;
+            }
           }
+        }
+      }
+      if (g.tma_out) {
+#pragma unroll 1
+        for (int t0 = cbeg & ~31; t0 < cend; t0 += 32) {   // the 32-column tiles this part contributes to (one, unless PART_COLS > 32)
+          const uint32_t s_hi = smem_base + (uint32_t)(t0 >> 5) * (2u * GM_A_BYTES);
+          gm_tiles_out(1 + (t0 >> 5), 128 * TILE_PARTS, (part % TILE_PARTS) == 0 && q == 0 && lane == 0, n0 + t0 < g.N, &maps.o[0],
+                       g.out_lo ? &maps.o[1] : nullptr, n0 + t0, m0, s_hi, s_hi + GM_A_BYTES);
         }
       }
     } else if constexpr (EPI == EPI_GRU) {
@@ -426,7 +478,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
 #pragma unroll
         for (int j = 0; j < 8; j += 4) {
           const int col = n0 + c0 + j;
-          if (live && col < H) {
+          if (live && col < H) {   // (rows >= M stage nothing: the copy engine clips them)
             float4 hp = *reinterpret_cast<const float4*>(g.hold + (size_t)row * g.ldh + col);
             if (g.hold_lo) {
               const float4 hl = *reinterpret_cast<const float4*>(g.hold_lo + (size_t)row * g.ldh + col);
@@ -446,9 +498,23 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
               po[t] = gm_round_tf32(hn);
               pl[t] = gm_round_tf32(hn - po[t]);
             }
-            *reinterpret_cast<float4*>(g.out + (size_t)row * g.ldo + col) = o;
-            if (g.out_lo) *reinterpret_cast<float4*>(g.out_lo + (size_t)row * g.ldo + col) = ol;
+            if (g.tma_out) {
+              const uint32_t s_hi = smem_base + (uint32_t)(c0 >> 5) * (2u * GM_A_BYTES);
+              gm_stage_f4(s_hi, rt, (c0 + j) & 31, o);
+              if (g.out_lo) gm_stage_f4(s_hi + GM_A_BYTES, rt, (c0 + j) & 31, ol);
+            } else {
+              *reinterpret_cast<float4*>(g.out + (size_t)row * g.ldo + col) = o;
+              if (g.out_lo) *reinterpret_cast<float4*>(g.out_lo + (size_t)row * g.ldo + col) = ol;
+            }
           }
+        }
+      }
+      if (g.tma_out) {
+#pragma unroll 1
+        for (int t0 = cbeg & ~31; t0 < cend; t0 += 32) {
+          const uint32_t s_hi = smem_base + (uint32_t)(t0 >> 5) * (2u * GM_A_BYTES);
+          gm_tiles_out(1 + (t0 >> 5), 128 * TILE_PARTS, (part % TILE_PARTS) == 0 && q == 0 && lane == 0, n0 + t0 < H, &maps.o[0],
+                       g.out_lo ? &maps.o[1] : nullptr, n0 + t0, m0, s_hi, s_hi + GM_A_BYTES);
         }
       }
     } else if constexpr (EPI == EPI_STOCH) {
@@ -520,6 +586,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
 // `g.out` holds hout's pre-activations [M][4] (k_dense<EPI_ACTOR>); the other fields are the ACTOR ones of GemmArgs.
 __global__ void __launch_bounds__(256) k_actor_mode(const GemmArgs g) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // launched while the head's k_dense still runs (programmatic dependent launch)
   if (row >= g.M) return;
   const float4 x4 = *reinterpret_cast<const float4*>(g.out + (size_t)row * 4);
   float x[4] = {x4.x, x4.y, x4.z, x4.w};
@@ -635,6 +702,303 @@ __global__ void __launch_bounds__(256) k_latent_copy(float* __restrict__ feat, f
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// k_dense_chain: a stack of equally wide Dense + ELU layers (the ActionDecoder trunk [REF models.py:321-322]) in ONE
+// launch.  The arithmetic of every layer is k_dense<EPI_DENSE, 1, 4, STAGES, X3 = true, EW, BN>'s, instruction for
+// instruction (same K blocks, same accumulator groups, same epilogue), so the results are bitwise those of the
+// per-layer launches; what goes away is, per layer, a launch, a CTA set-up (barriers, TMEM, tensor maps) and the
+// drain / fill of the whole grid around a kernel boundary.
+//   * grid (N tiles, row-block groups): CTA (x, y) owns output columns [x BN, (x + 1) BN) of the 128-env row blocks
+//     y, y + gridDim.y, ...; the host keeps the grid within one CTA per SM, so all CTAs are resident together.
+//   * layer l + 1 of a row block reads what ALL N tiles of layer l wrote for that row block: each CTA bumps the
+//     counter flags[l][row block] (stores -> __threadfence -> CTA barrier of the epilogue warps -> atomic) and the
+//     producer thread of each CTA waits for it to reach `target[l]` (acquire load, then fence.proxy.async before the
+//     TMA reads) -- no grid-wide barrier, row blocks run ahead of each other freely.  Counters only ever grow
+//     (the host passes the value they must reach in this launch), so nothing has to be cleared between launches.
+//   * while waiting, the producer has already filled the ring with the weight tiles of the layer's first K blocks
+//     (weights depend on nothing); the accumulators are handed back and forth between the issuer and the epilogue
+//     warps through acc_bar / tmem_free_bar.
+// Waits are bounded (trap instead of hang), like gm_mbar_wait.
+// ---------------------------------------------------------------------------------------------------------------
+#define GM_CHAIN_MAX 4
+struct ChainMaps {   // [layer][hi, lo]; layer l stores its output through a[l + 1] (the same rows), the last one through o_last
+  CUtensorMap a[GM_CHAIN_MAX][2];
+  CUtensorMap w[GM_CHAIN_MAX][2];
+  CUtensorMap o_last[2];
+};
+struct ChainLayer {
+  int kb_total;            // K blocks of the layer
+  int n_groups;            // accumulator groups of the hi*hi products (the cross products go to accumulator n_groups)
+  int grp_blocks[3];       // K blocks per group
+  const float* bias;
+  float* out; float* out_lo;
+  unsigned target;         // value flags[layer][row block] reaches when every column part of every N tile of this launch
+                           // has stored the layer (EW parts per CTA)
+};
+struct ChainArgs {
+  int M, N, ldo, n_layers, row_blocks;
+  unsigned* flags;         // [GM_CHAIN_MAX][row_blocks]
+  ChainLayer L[GM_CHAIN_MAX];
+};
+
+__device__ __forceinline__ void gm_flag_wait(const unsigned* flag, unsigned target) {
+  for (uint32_t spins = 0;; ++spins) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if ((int)(v - target) >= 0) break;
+    if (spins > (1u << 22)) __trap();
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");   // the rows were written through the generic proxy, TMA reads them
+}
+
+template <int GM_STAGES, int EW, int BN>
+__global__ void __launch_bounds__(64 + 128 * EW, 1)
+    k_dense_chain(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
+  extern __shared__ uint8_t gm_smem_raw[];
+  __shared__ uint64_t full_bar[GM_STAGES], empty_bar[GM_STAGES], acc_bar, tmem_free_bar, epi_done_bar;
+  __shared__ uint32_t tmem_slot;
+#ifdef GM_CHAIN_TRACE   // per-role clock stamps of the first row block (tools/gpu_chain_trace.sh)
+  __shared__ long long tr[GM_CHAIN_MAX][16];
+  __shared__ long long tr0;
+#define GM_TR(l, k) do { if (mb == (int)blockIdx.y) tr[l][k] = clock64(); } while (0)
+#else
+#define GM_TR(l, k) do { } while (0)
+#endif
+  static_assert(BN % 16 == 0 && BN <= 256 && 4 * BN <= 512, "MMA N and the accumulators' TMEM columns");
+  constexpr uint32_t W_BYTES = BN * 128, IDESC = GM_IDESC_N(BN);
+  constexpr uint32_t SUB_BYTES = GM_A_BYTES + W_BYTES, STAGE_BYTES = 2u * SUB_BYTES;
+  constexpr uint32_t TM_COLS = 512;
+  const uint32_t smem_base = (rd_smem_u32(gm_smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+
+  if (threadIdx.x == 0) {
+    for (int l = 0; l < g.n_layers; ++l) {
+      gm_prefetch_map(&maps.a[l][0]); gm_prefetch_map(&maps.a[l][1]);
+      gm_prefetch_map(&maps.w[l][0]); gm_prefetch_map(&maps.w[l][1]);
+    }
+#pragma unroll
+    for (int s = 0; s < GM_STAGES; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(rd_smem_u32(&full_bar[s])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(rd_smem_u32(&empty_bar[s])));
+    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(rd_smem_u32(&acc_bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rd_smem_u32(&tmem_free_bar)), "r"(4 * EW));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rd_smem_u32(&epi_done_bar)), "r"(EW));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) gm_tmem_alloc(&tmem_slot, TM_COLS);
+  gm_tc_fence_before();
+  __syncthreads();
+  gm_tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#ifdef GM_CHAIN_TRACE
+  if (threadIdx.x == 0) tr0 = clock64();
+#endif
+
+  if (warp == 0) {
+    if (gm_elect_one()) {   // ===== TMA producer =====
+      uint32_t it = 0, tile = 0;
+      bool first = true;
+      for (int mb = blockIdx.y; mb < g.row_blocks; mb += gridDim.y) {
+        const int m0 = mb * GM_BM;
+        for (int l = 0; l < g.n_layers; ++l) {
+          const CUtensorMap* ma = &maps.a[l][0];
+          const CUtensorMap* ma2 = &maps.a[l][1];
+          const CUtensorMap* mw = &maps.w[l][0];
+          const CUtensorMap* mw2 = &maps.w[l][1];
+          const int kbs = g.L[l].kb_total;
+          const int pre = kbs < GM_STAGES - 1 ? kbs : GM_STAGES - 1;
+          // weight tiles of the first K blocks: they depend on nothing but a free ring slot (the last stage and the
+          // activation slots of these ones are the staging space of the epilogue that may still be running)
+          for (int j = 0; j < pre; ++j) {
+            const uint32_t i = it + (uint32_t)j, s = i % GM_STAGES, par = (i / GM_STAGES) & 1u;
+            const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + SUB_BYTES;
+            if (i >= (uint32_t)GM_STAGES) gm_mbar_wait(&empty_bar[s], par ^ 1u);
+            rd_mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+            gm_tma_2d(sa + GM_A_BYTES, mw, j * GM_BK, n0, &full_bar[s]);
+            gm_tma_2d(sb + GM_A_BYTES, mw2, j * GM_BK, n0, &full_bar[s]);
+          }
+          GM_TR(l, 0);
+          // the layer's input rows: the kernel in front of this one (first layer) or every N tile of the layer before
+          if (first) { asm volatile("griddepcontrol.wait;" ::: "memory"); first = false; }
+          if (tile > 0) gm_mbar_wait(&epi_done_bar, (tile - 1) & 1u);   // the copy engine has read the staged tiles
+          GM_TR(l, 14);
+          if (l > 0) gm_flag_wait(g.flags + (size_t)(l - 1) * g.row_blocks + mb, g.L[l - 1].target);
+          GM_TR(l, 1);
+          for (int j = 0; j < pre; ++j) {
+            const uint32_t s = (it + (uint32_t)j) % GM_STAGES;
+            const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + SUB_BYTES;
+            gm_tma_2d(sa, ma, j * GM_BK, m0, &full_bar[s]);
+            gm_tma_2d(sb, ma2, j * GM_BK, m0, &full_bar[s]);
+          }
+          for (int j = pre; j < kbs; ++j) {
+            const uint32_t i = it + (uint32_t)j, s = i % GM_STAGES, par = (i / GM_STAGES) & 1u;
+            const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + SUB_BYTES;
+            gm_mbar_wait(&empty_bar[s], par ^ 1u);
+            rd_mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+            gm_tma_2d(sa + GM_A_BYTES, mw, j * GM_BK, n0, &full_bar[s]);
+            gm_tma_2d(sb + GM_A_BYTES, mw2, j * GM_BK, n0, &full_bar[s]);
+            gm_tma_2d(sa, ma, j * GM_BK, m0, &full_bar[s]);
+            gm_tma_2d(sb, ma2, j * GM_BK, m0, &full_bar[s]);
+          }
+          it += (uint32_t)kbs;
+          ++tile;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (gm_elect_one()) {   // ===== MMA issuer =====
+      uint32_t it = 0, tile = 0;
+      const uint32_t lo_base = gm_desc_lo(smem_base);
+      for (int mb = blockIdx.y; mb < g.row_blocks; mb += gridDim.y) {
+        for (int l = 0; l < g.n_layers; ++l, ++tile) {
+          if (tile > 0) {   // the epilogue warps have read the accumulators of the tile before
+            gm_mbar_wait(&tmem_free_bar, (tile - 1) & 1u);
+            gm_tc_fence_after();
+          }
+          const ChainLayer& L = g.L[l];
+          const uint32_t dsm = tmem + (uint32_t)(L.n_groups * BN);
+          bool small_fresh = true;
+          for (int grp = 0; grp < L.n_groups; ++grp) {
+            const uint32_t dcol = tmem + (uint32_t)(grp * BN);
+            const int kbs = L.grp_blocks[grp];
+            for (int kb = 0; kb < kbs; ++kb, ++it) {
+              const uint32_t s = it % GM_STAGES, par = (it / GM_STAGES) & 1u;
+              gm_mbar_wait(&full_bar[s], par);
+              gm_tc_fence_after();
+              if (grp == 0 && kb == 0) GM_TR(l, 2);
+              const uint32_t a_lo = lo_base + s * (STAGE_BYTES >> 4);
+              const uint32_t w_lo = a_lo + (GM_A_BYTES >> 4);
+              const uint32_t a2 = a_lo + (SUB_BYTES >> 4), w2 = w_lo + (SUB_BYTES >> 4);
+              const uint32_t sm0 = small_fresh ? 0u : 1u;
+              small_fresh = false;
+#pragma unroll
+              for (int k = 0; k < GM_BK / 8; ++k)
+                gm_mma_tf32(dsm, gm_desc(a2 + 2 * k), gm_desc(w_lo + 2 * k), IDESC, k > 0 ? 1u : sm0);
+#pragma unroll
+              for (int k = 0; k < GM_BK / 8; ++k)
+                gm_mma_tf32(dsm, gm_desc(a_lo + 2 * k), gm_desc(w2 + 2 * k), IDESC, 1u);
+#pragma unroll
+              for (int k = 0; k < GM_BK / 8; ++k)
+                gm_mma_tf32(dcol, gm_desc(a_lo + 2 * k), gm_desc(w_lo + 2 * k), IDESC, (k > 0 || kb > 0) ? 1u : 0u);
+              gm_commit(&empty_bar[s]);
+            }
+          }
+          gm_commit(&acc_bar);
+          GM_TR(l, 3);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue (k_dense's EPI_DENSE with ELU), then the row block's counter =====
+    // Thread = tile row (TMEM lane), so storing straight from registers would put 16 bytes into each of 32 different rows
+    // per instruction: 8192 half-sector writes per CTA and layer, measured at 8.5 us of a 16.5 us layer (clock stamps,
+    // profiles/r5b_dreamer_chain.txt).  Instead the four warps of a column part build their [128 rows][32 columns]
+    // hi and lo tiles in shared memory, in the 128-byte-swizzled layout of the tensor maps the NEXT layer loads its
+    // A operand through, and one thread hands each tile to the copy engine (cp.async.bulk.tensor store; rows >= M and
+    // columns >= N are clipped by the map).  Staging space: the ring itself -- the producer only prefetches WEIGHT
+    // tiles of GM_STAGES - 1 K blocks while an epilogue runs, so their activation slots and the whole remaining stage
+    // are idle (it waits for epi_done_bar before it loads activations again).
+    const int q = warp & 3;
+    const int part = (warp - 2) >> 2;
+    constexpr int PART_COLS = BN / EW;
+    static_assert(PART_COLS == 32 && GM_STAGES == 3 && EW == 4 && W_BYTES == GM_A_BYTES, "staging tiles overlay a 3-stage ring");
+    const int cbeg = part * PART_COLS, cend = cbeg + PART_COLS;
+    const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+    const uint32_t r = (uint32_t)(q * 32 + lane);     // tile row
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    uint32_t tile = 0, it_end = 0;
+    for (int mb = blockIdx.y; mb < g.row_blocks; mb += gridDim.y) {
+      for (int l = 0; l < g.n_layers; ++l, ++tile) {
+        const ChainLayer& L = g.L[l];
+        it_end += (uint32_t)L.kb_total;
+        // stages it_end % 3 and (it_end + 1) % 3 receive the next tile's first weight tiles; stage (it_end + 2) % 3 is idle
+        const uint32_t st = part < 2 ? (it_end + (uint32_t)part) % 3u : (it_end + 2u) % 3u;
+        const uint32_t s_hi = smem_base + st * STAGE_BYTES + (part == 3 ? GM_A_BYTES : 0u), s_lo = s_hi + SUB_BYTES;
+        const bool any = n0 + cbeg < g.N;   // warp-uniform (and uniform over the part's four warps)
+        gm_mbar_wait(&acc_bar, tile & 1u, true);
+        gm_tc_fence_after();
+        if (threadIdx.x == 64) GM_TR(l, 4);
+#pragma unroll 1
+        for (int c0 = cbeg; c0 < cend; c0 += 16) {
+          if (n0 + c0 >= g.N) break;   // warp-uniform
+          float v[16];
+          gm_tmem_sum16(tl + c0, L.n_groups + 1, 1, v, BN);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const int col = n0 + c0 + j;
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f), ol = o;
+            if (col < g.N) {   // N % 4 == 0
+              float* po = &o.x;
+              float* pl = &ol.x;
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float x = gm_elu(v[j + t] + __ldg(L.bias + col + t));
+                po[t] = gm_round_tf32(x);
+                pl[t] = gm_round_tf32(x - po[t]);
+              }
+            }
+            const uint32_t chunk = (uint32_t)((c0 - cbeg + j) >> 2);                 // 16-byte chunk of the 128-byte row
+            const uint32_t off = r * 128u + ((chunk ^ (r & 7u)) << 4);               // SWIZZLE_128B
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(s_hi + off), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(s_lo + off), "f"(ol.x), "f"(ol.y), "f"(ol.z), "f"(ol.w) : "memory");
+          }
+        }
+        gm_tc_fence_before();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tiles were written through the generic proxy
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rd_smem_u32(&tmem_free_bar)) : "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + part) : "memory");    // the part's four warps
+        if (q == 0 && lane == 0) {
+          if (any) {
+            const CUtensorMap* mo = l + 1 < g.n_layers ? &maps.a[l + 1][0] : &maps.o_last[0];
+            const CUtensorMap* mo2 = l + 1 < g.n_layers ? &maps.a[l + 1][1] : &maps.o_last[1];
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                             reinterpret_cast<uint64_t>(mo)), "r"(n0 + cbeg), "r"(mb * GM_BM), "r"(s_hi) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                             reinterpret_cast<uint64_t>(mo2)), "r"(n0 + cbeg), "r"(mb * GM_BM), "r"(s_lo) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            GM_TR(l, 6 + part);
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rd_smem_u32(&epi_done_bar)) : "memory");
+          if (l + 1 < g.n_layers) {
+            if (any) {
+              asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+              asm volatile("fence.proxy.async;" ::: "memory");
+            }
+            GM_TR(l, 10 + part);
+            __threadfence();
+            atomicAdd(g.flags + (size_t)l * g.row_blocks + mb, 1u);
+          }
+        }
+        if (threadIdx.x == 64) GM_TR(l, 5);
+      }
+    }
+    if (q == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the last tile's stores
+    gm_tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    gm_tc_fence_after();
+    gm_tmem_free(tmem, TM_COLS);
+  }
+#ifdef GM_CHAIN_TRACE
+  if (threadIdx.x == 0 && g.L[0].target == 40u * gridDim.x * EW && (blockIdx.y % 8) == 0)
+    for (int l = 0; l < g.n_layers; ++l)
+      printf("CHAIN cta (%d,%d) layer %d: W issued %lld | staged tiles read %lld | A issued %lld | first full %lld | MMAs issued %lld | acc ready %lld | "
+             "stores issued %lld %lld %lld %lld | stores complete %lld %lld %lld %lld | part 0 counted %lld\n",
+             blockIdx.x, blockIdx.y, l, tr[l][0] - tr0, tr[l][14] - tr0, tr[l][1] - tr0, tr[l][2] - tr0, tr[l][3] - tr0, tr[l][4] - tr0,
+             tr[l][6] - tr0, tr[l][7] - tr0, tr[l][8] - tr0, tr[l][9] - tr0, tr[l][10] - tr0, tr[l][11] - tr0, tr[l][12] - tr0,
+             tr[l][13] - tr0, tr[l][5] - tr0);
+#endif
+#undef GM_TR
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side: tensor maps and launches
 // ---------------------------------------------------------------------------------------------------------------
 typedef CUresult (*gm_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -688,4 +1052,28 @@ static inline cudaError_t gm_launch(const GemmMaps& maps, const GemmArgs& g, cud
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, k_dense<EPI, NSLAB, NACC, GM_STAGES, X3, EW, BN>, maps, g);
+}
+
+template <int GM_STAGES, int EW, int BN>
+static inline cudaError_t gm_launch_chain(const ChainMaps& maps, const ChainArgs& g, int sm_count, cudaStream_t s) {
+  constexpr size_t smem = (size_t)GM_STAGES * 2 * (GM_A_BYTES + BN * 128) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_dense_chain<GM_STAGES, EW, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  const int nt = (g.N + BN - 1) / BN;
+  cudaLaunchConfig_t cfg = {};
+  // every CTA must be resident (they wait for each other's row-block counters): one CTA per SM, whole row-block groups
+  cfg.gridDim = dim3((unsigned)nt, (unsigned)std::max(1, std::min(g.row_blocks, sm_count / nt)));
+  cfg.blockDim = dim3(64 + 128 * EW);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k_dense_chain<GM_STAGES, EW, BN>, maps, g);
 }

@@ -267,6 +267,26 @@ def test_rollout_equals_stepwise(torch_cuda, weights):
     assert stats["episodes"] < 0.5 * n, stats
 
 
+@pytest.mark.parametrize("n", [300, 5000])
+def test_actor_chain_is_bitwise_the_per_layer_launches(torch_cuda, weights, monkeypatch, n):
+    """k_dense_chain (the actor trunk in one launch, row-block counters between the layers) == one k_dense launch per
+    layer, bit for bit: partial row tile (300 envs) and more row blocks than resident CTA groups (5000 envs = 40)"""
+    torch = torch_cuda
+    from racing_dreamer_b200 import DreamerPolicy
+    outs = []
+    for chain in ("1", "0"):
+        monkeypatch.setenv("RD_DREAMER_CHAIN", chain)
+        env = make_env(tracks=("austria",), n_envs=n, action_repeat=4, reset_mode="random", seed=9, auto_reset=True)
+        env.reset()
+        pol = DreamerPolicy(env, weights, noise="philox")
+        pol.rollout(12)
+        torch.cuda.synchronize()
+        outs.append((pol.actions.clone(),) + tuple(t.clone() for t in pol.get_state()) + (env.buf["pose"].clone(),))
+        env.close()
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
 def test_error_paths(torch_cuda, weights):
     torch = torch_cuda
     from racing_dreamer_b200 import DreamerPolicy
