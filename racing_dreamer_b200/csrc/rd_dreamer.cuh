@@ -302,7 +302,7 @@ static inline int dreamer_step(DreamerPolicy& d, const float* lidar, float* acti
     g.M = d.n; g.N = H;
     const DrTerm t[1] = {{&d.v_sa[cur], &d.w_img1, 32, 0}};
     dr_build(d, maps, g, t, 1, 1, nullptr, nullptr, 1, 4);
-    g.bias = d.b_img1; g.out = d.x1.p[0]; g.out_lo = d.x1.p[1]; g.ldo = H; g.act = 1;
+    g.step = d.step; g.bias = d.b_img1; g.out = d.x1.p[0]; g.out_lo = d.x1.p[1]; g.ldo = H; g.act = 1;
     g.tma_out = d.tma_out; maps.o[0] = d.x1.m[0]; maps.o[1] = d.x1.m[1];
     if (d.x3) DR_TRY((gm_launch<EPI_DENSE, 1, 4, 2, true, DR_EW_WIDE>(maps, g, s)));
     else DR_TRY((gm_launch<EPI_DENSE, 1, 4, 4>(maps, g, s)));
@@ -316,7 +316,7 @@ static inline int dreamer_step(DreamerPolicy& d, const float* lidar, float* acti
     const int rows[3] = {0, D, 2 * D};
     const int gate[2][3] = {{0, 1, 2}, {0, 1, 3}};
     dr_build(d, maps, g, t, 2, 3, rows, gate, 4, d.x3 ? 8 : 4);   // one main group (every gate slot must be fed), one small
-    g.bias = d.b_gru; g.out = d.v_det[nxt].p[0]; g.out_lo = d.v_det[nxt].p[1]; g.ldo = d.ldf;
+    g.step = d.step; g.bias = d.b_gru; g.out = d.v_det[nxt].p[0]; g.out_lo = d.v_det[nxt].p[1]; g.ldo = d.ldf;
     g.hold = d.v_det[cur].p[0]; g.hold_lo = d.v_det[cur].p[1]; g.ldh = d.ldf;
     g.tma_out = d.tma_out; maps.o[0] = d.v_det[nxt].m[0]; maps.o[1] = d.v_det[nxt].m[1];
     if (d.x3) DR_TRY((gm_launch<EPI_GRU, 3, 8, 2, true, DR_EW_WIDE>(maps, g, s)));
@@ -329,7 +329,7 @@ static inline int dreamer_step(DreamerPolicy& d, const float* lidar, float* acti
     g.M = d.n; g.N = H;
     const DrTerm t[2] = {{&d.v_det[nxt], &d.w_obs1, D, 0}, {&d.lidar, &d.w_obs1, d.embed, D}};
     dr_build(d, maps, g, t, 2, 1, nullptr, nullptr, 1, 8);
-    g.bias = d.b_obs1; g.out = d.hobs.p[0]; g.out_lo = d.hobs.p[1]; g.ldo = H; g.act = 1;
+    g.step = d.step; g.bias = d.b_obs1; g.out = d.hobs.p[0]; g.out_lo = d.hobs.p[1]; g.ldo = H; g.act = 1;
     g.tma_out = d.tma_out; maps.o[0] = d.hobs.m[0]; maps.o[1] = d.hobs.m[1];
     if (d.x3) DR_TRY((gm_launch<EPI_DENSE, 1, 8, 4, true, DR_EW_WIDE>(maps, g, s)));
     else DR_TRY((gm_launch<EPI_DENSE, 1, 8, 8>(maps, g, s)));

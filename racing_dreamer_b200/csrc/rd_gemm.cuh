@@ -268,6 +268,12 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
   extern __shared__ uint8_t gm_smem_raw[];
   __shared__ uint64_t full_bar[GM_STAGES], empty_bar[GM_STAGES], acc_bar;
   __shared__ uint32_t tmem_slot;
+#ifdef GM_CHAIN_TRACE   // per-role clock stamps (tools/gpu_chain_trace.sh)
+  __shared__ long long trd[8];
+#define GM_TRD(k) trd[k] = clock64()
+#else
+#define GM_TRD(k) do { } while (0)
+#endif
   // X3: a ring stage holds the hi AND the lo tiles of a K block ([A_hi | W_hi slabs | A_lo | W_lo slabs]) and feeds all
   // three products of the float32-grade scheme from one load: two thirds of the operand bytes of three separate passes
   // and a third of the producer / issuer hand-offs.
@@ -301,6 +307,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
   // Programmatic dependent launch: the next k_dense of the stream may start its own set-up (barriers, TMEM, tensor-map
   // fetch) now; everything that touches global memory first waits for the previous kernel to have completed.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (threadIdx.x == 0) GM_TRD(0);
 
   if (warp == 0) {
     if (gm_elect_one()) {   // ===== TMA producer =====
@@ -310,7 +317,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
       // are requested BEFORE griddepcontrol.wait (pass 0), the activation tiles of those K blocks and everything else
       // after it (pass 1) -- the ring is full of weights by the time the previous layer's outputs exist.
       for (int pass = 0; pass < 2; ++pass) {
-        if (pass == 1) asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (pass == 1) { asm volatile("griddepcontrol.wait;" ::: "memory"); GM_TRD(1); }
         uint32_t it = 0;
         for (int p = 0; p < g.n_phases; ++p) {
           const GemmPhase& ph = g.ph[p];
@@ -377,6 +384,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
           const uint32_t s = it % GM_STAGES, par = (it / GM_STAGES) & 1u;
           gm_mbar_wait(&full_bar[s], par);
           gm_tc_fence_after();
+          if (it == 0) GM_TRD(2);
           const uint32_t a_lo = lo_base + s * (STAGE_BYTES >> 4);
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
@@ -402,6 +410,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
         }
       }
       gm_commit(&acc_bar);            // accumulators complete
+      GM_TRD(3);
     }
     __syncwarp();
   } else {
@@ -416,9 +425,36 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
     const int row = m0 + q * 32 + lane;
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    const bool live = row < g.M;
+    // What does not depend on the accumulators is done here, while the K loop runs: the posterior's normal draws
+    // (Philox + Box-Muller: most of that epilogue's arithmetic) and the GRU's previous state (row-strided loads).
+    [[maybe_unused]] float zpre[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    if constexpr (EPI == EPI_STOCH && EW == 4) {
+      if (live && g.noise == GM_NOISE_PHILOX) {
+        const uint32_t gid = g.gid0 + (uint32_t)row;
+        gm_normal4(gid, g.step, (uint32_t)(8 * part), RD_STREAM_STOCH, g.key0, g.key1, zpre[0]);
+        gm_normal4(gid, g.step, (uint32_t)(8 * part + 4), RD_STREAM_STOCH, g.key0, g.key1, zpre[1]);
+      }
+    }
+    [[maybe_unused]] float hpre[16];
+    if constexpr (EPI == EPI_GRU && EW == 4) {
+#pragma unroll
+      for (int c = 0; c < 16; c += 4) {
+        const int col = n0 + part * 16 + c;
+        float4 hp = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live && col < g.N) {
+          hp = *reinterpret_cast<const float4*>(g.hold + (size_t)row * g.ldh + col);
+          if (g.hold_lo) {
+            const float4 hl = *reinterpret_cast<const float4*>(g.hold_lo + (size_t)row * g.ldh + col);
+            hp.x += hl.x; hp.y += hl.y; hp.z += hl.z; hp.w += hl.w;
+          }
+        }
+        hpre[c] = hp.x; hpre[c + 1] = hp.y; hpre[c + 2] = hp.z; hpre[c + 3] = hp.w;
+      }
+    }
     gm_mbar_wait(&acc_bar, 0, true);
     gm_tc_fence_after();
-    const bool live = row < g.M;
+    if (threadIdx.x == 64) GM_TRD(4);
     // tma_out: this part's 32-column staging tile (hi, lo) in the idle ring, and who shares it
     constexpr int TILE_PARTS = PART_COLS >= 32 ? 1 : 32 / PART_COLS;       // column parts per staging tile
     static_assert(PART_COLS == 16 || PART_COLS % 32 == 0, "staging tiles are 32 columns wide");
@@ -467,8 +503,8 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
       const int H = g.N;
       const float* bx = g.bias;
       const float* bh = g.bias + 3 * H;
-#pragma unroll 1
-      for (int c0 = cbeg; c0 < cend; c0 += 8) {
+#pragma unroll
+      for (int c0 = cbeg; c0 < cend; c0 += 8) {   // (unrolled: hpre is indexed statically)
         if (n0 + c0 >= H) break;
         float az[8], ar[8], axh[8], arh[8];
         gm_tmem_sum8(tl + 0 * GM_BN + c0, g.n_acc, 4, az);    // accumulator a of gate q sits at column (4 a + q) * 64
@@ -479,10 +515,16 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
         for (int j = 0; j < 8; j += 4) {
           const int col = n0 + c0 + j;
           if (live && col < H) {   // (rows >= M stage nothing: the copy engine clips them)
-            float4 hp = *reinterpret_cast<const float4*>(g.hold + (size_t)row * g.ldh + col);
-            if (g.hold_lo) {
-              const float4 hl = *reinterpret_cast<const float4*>(g.hold_lo + (size_t)row * g.ldh + col);
-              hp.x += hl.x; hp.y += hl.y; hp.z += hl.z; hp.w += hl.w;
+            float4 hp;
+            if constexpr (EW == 4) {
+              const int c = (c0 - cbeg + j) & 15;
+              hp = make_float4(hpre[c], hpre[c + 1], hpre[c + 2], hpre[c + 3]);
+            } else {
+              hp = *reinterpret_cast<const float4*>(g.hold + (size_t)row * g.ldh + col);
+              if (g.hold_lo) {
+                const float4 hl = *reinterpret_cast<const float4*>(g.hold_lo + (size_t)row * g.ldh + col);
+                hp.x += hl.x; hp.y += hl.y; hp.z += hl.z; hp.w += hl.w;
+              }
             }
             const float* ph_ = &hp.x;
             float4 o, ol;
@@ -519,6 +561,40 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
       }
     } else if constexpr (EPI == EPI_STOCH) {
       // RSSM posterior [REF models.py:69-73]: mean, std = split(x); std = softplus(std) + 0.1; stoch = mean + std * eps
+      if constexpr (EW == 4) {
+        // part p owns latents 8p .. 8p + 7: their means are accumulator columns 8p .. 8p + 7, their raw deviations
+        // columns 30 + 8p .. 37 + 8p = entries 6 .. 13 of the 16 columns from 24 + 8p; two TMEM reads per accumulator
+        // instead of four, whole 16-byte stores (latent slots 30 / 31 of the row are the action's: k_actor_mode
+        // fills them later in the step, the zero written here is never read as anything but a zero-weight input)
+        float mu[8], sr[16];
+        gm_tmem_sum8(tl + 8 * part, g.n_acc, 1, mu);
+        gm_tmem_sum16(tl + 24 + 8 * part, g.n_acc, 1, sr);
+        if (live) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int j0 = 8 * part + 4 * h;
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f), ol = o;
+            float* po = &o.x;
+            float* pl = &ol.x;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int j = j0 + t;
+              if (j < GM_STOCH) {
+                const float mean = mu[4 * h + t] + __ldg(g.bias + j);
+                const float sd = gm_softplus(sr[6 + 4 * h + t] + __ldg(g.bias + GM_STOCH + j)) + 0.1f;
+                float e = zpre[h][t];
+                if (g.noise == GM_NOISE_EXPLICIT) e = g.eps[(size_t)row * g.ld_eps + j];
+                const float sv = mean + sd * e;
+                po[t] = gm_round_tf32(sv);
+                pl[t] = gm_round_tf32(sv - po[t]);
+                if (g.dbg) { g.dbg[(size_t)row * 2 * GM_STOCH + j] = mean; g.dbg[(size_t)row * 2 * GM_STOCH + GM_STOCH + j] = sd; }
+              }
+            }
+            *reinterpret_cast<float4*>(g.feat + (size_t)row * g.ldf + j0) = o;
+            if (g.feat_lo) *reinterpret_cast<float4*>(g.feat_lo + (size_t)row * g.ldf + j0) = ol;
+          }
+        }
+      } else {
       float lo[32], hi[32];
       {
         float t[16];
@@ -561,6 +637,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
           }
         }
       }
+      }   // EW != 4
     } else {
       // hout: the four pre-activations of the ActionDecoder head, in full float32; the head itself and
       // SampleDist.mode() need many more threads than this tile has rows (k_actor_mode)
@@ -573,12 +650,19 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
       }
     }
     gm_tc_fence_before();
+    if (threadIdx.x == 64) GM_TRD(5);
   }
   __syncthreads();
   if (warp == 1) {
     gm_tc_fence_after();
     gm_tmem_free(tmem, TM_COLS);
   }
+#ifdef GM_CHAIN_TRACE
+  if (threadIdx.x == 0 && g.step == 40u && blockIdx.x % 16 == 0)
+    printf("DENSE epi %d cta (%d,%d): inputs ready %lld | first full %lld | MMAs issued %lld | acc ready %lld | epilogue done %lld | end %lld\n",
+           EPI, blockIdx.x, blockIdx.y, trd[1] - trd[0], trd[2] - trd[0], trd[3] - trd[0], trd[4] - trd[0], trd[5] - trd[0], clock64() - trd[0]);
+#endif
+#undef GM_TRD
 }
 
 // ActionDecoder distribution head [REF models.py:323-346] + SampleDist.mode() [REF ros_agent/helpers/tools.py:70-73]:
@@ -586,8 +670,18 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
 // `g.out` holds hout's pre-activations [M][4] (k_dense<EPI_ACTOR>); the other fields are the ACTOR ones of GemmArgs.
 __global__ void __launch_bounds__(256) k_actor_mode(const GemmArgs g) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  asm volatile("griddepcontrol.wait;" ::: "memory");   // launched while the head's k_dense still runs (programmatic dependent launch)
   if (row >= g.M) return;
+  // Launched while the head's k_dense still runs (programmatic dependent launch): the normal draws -- Philox and
+  // Box-Muller, most of this kernel's arithmetic -- depend on nothing it produces and are made before the wait.
+  constexpr int PRE = 4;   // draws 2 lane + 64 it, it < PRE, kept in registers; beyond 256 draws they are made in the loop
+  float zp[PRE][4];
+  if (g.noise == GM_NOISE_PHILOX) {
+#pragma unroll
+    for (int it = 0; it < PRE; ++it)
+      if (2 * lane + 64 * it < g.n_samples)
+        gm_normal4(g.gid0 + (uint32_t)row, g.step, (uint32_t)(2 * lane + 64 * it), RD_STREAM_ACTOR, g.key0, g.key1, zp[it]);
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const float4 x4 = *reinterpret_cast<const float4*>(g.out + (size_t)row * 4);
   float x[4] = {x4.x, x4.y, x4.z, x4.w};
   float mean[2], sd[2];
@@ -616,9 +710,19 @@ __global__ void __launch_bounds__(256) k_actor_mode(const GemmArgs g) {
       best += (-logf(sd[d]) - half_log_2pi) - 2.f * ((log2f_ - u) - gm_softplus(-2.f * u));
     }
   } else {
-    for (int s0 = 2 * lane; s0 < g.n_samples; s0 += 64) {
+    int it = 0;
+#pragma unroll 1
+    for (int s0 = 2 * lane; s0 < g.n_samples; s0 += 64, ++it) {
       float z[4] = {0.f, 0.f, 0.f, 0.f};
-      if (g.noise == GM_NOISE_PHILOX) gm_normal4(gid, g.step, (uint32_t)s0, RD_STREAM_ACTOR, g.key0, g.key1, z);
+      if (g.noise == GM_NOISE_PHILOX) {
+        if (it < PRE) {
+#pragma unroll
+          for (int k = 0; k < PRE; ++k)
+            if (k == it) { z[0] = zp[k][0]; z[1] = zp[k][1]; z[2] = zp[k][2]; z[3] = zp[k][3]; }
+        } else {
+          gm_normal4(gid, g.step, (uint32_t)s0, RD_STREAM_ACTOR, g.key0, g.key1, z);
+        }
+      }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int s = s0 + h;

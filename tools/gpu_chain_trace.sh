@@ -13,4 +13,4 @@ env.reset()
 pol.rollout(45)
 torch.cuda.synchronize()
 PY
-echo "rc=$?"; grep CHAIN $OUT/trace.txt | sort | head -80
+echo "rc=$?"; grep "CHAIN\|DENSE" $OUT/trace.txt | sort | head -120
