@@ -526,14 +526,15 @@ def closed_loop_leg(cx, wl, n, steps, warmup):
             macs = 32 * 200 + 2 * 200 * 600 + 1280 * 200 + 200 * 60 + 230 * 400 + 3 * 400 * 400 + 400 * 4
             tf = 2.0 * macs * n / (policy_ms * 1e-3) / 1e12
             bf16 = float(peaks.get("bf16_tflops", 1590.0))
-            leg["policy"] = ("shipped Dreamer agent austria_dreamer on device: k_embed_lidar + k_dense launches (tcgen05 "
-                             "kind::tf32, hi/lo x3 passes, float32-grade), Philox draws, back-to-back steps")
+            leg["policy"] = ("shipped Dreamer agent austria_dreamer on device: k_embed_lidar + k_dense launches + k_dense_chain "
+                             "(the actor trunk in one launch) + k_actor_mode (tcgen05 kind::tf32, hi/lo x3 products, "
+                             "float32-grade), Philox draws, back-to-back steps")
             leg["roofline"] = {"bound": "tensor", "kernel": "k_dense", "achieved": tf, "unit": "TFLOP/s",
                                "executed_tf32_tflops": 3.0 * tf, "peak": bf16 / 2.0,
                                "peak_source": ("measured bf16 cuBLAS peak / 2 (TF32 runs at half the bf16 rate)" if peaks else
                                                "fallback 1.59 PFLOP/s bf16 / 2"),
                                "frac": 3.0 * tf / (bf16 / 2.0), "flops_per_env_step": 2 * macs,
-                               "note": "launch- and latency-bound at this batch: dependent launches of 32-224 CTAs each"}
+                               "note": "latency-bound at this batch: eight dependent launches of 32-128 CTAs each"}
         closed[pname] = leg
         cenv.close()
     return closed

@@ -27,4 +27,9 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_oc
    python bench.py --config 3 --envs 4096 --steps 4 --warmup 3 --no-cpu-baseline --no-closed-loop --no-multi-agent --no-configs --e2e-steps 2 > $OUT/ncu_k_occupancy.log 2>&1; echo "ncu k_occupancy rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_step_ma -s 5 -c 1 -o $OUT/prof_k_step_ma -f \
    python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-closed-loop --no-configs --e2e-steps 2 > $OUT/ncu_k_step_ma.log 2>&1; echo "ncu k_step_ma rc=$?"
-ls -la $OUT | head -30
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_dense_chain -s 5 -c 1 -o $OUT/prof_k_dense_chain -f \
+   python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-multi-agent --no-configs --no-e2e-variants --e2e-steps 2 > $OUT/ncu_k_dense_chain.log 2>&1; echo "ncu k_dense_chain rc=$?"
+echo "== Dreamer agent step: per-kernel launch list and step time"
+bash tools/gpu_dreamer_launches.sh $TAG > $OUT/dreamer_launches.txt 2>&1; tail -12 $OUT/dreamer_launches.txt
+timeout 300 python tools/dreamer_precision_probe.py > $OUT/dreamer_probe.txt 2>&1; cat $OUT/dreamer_probe.txt
+ls -la $OUT | head -40
