@@ -114,6 +114,13 @@ struct rd_env {
     bool attr_set = false;        // kernel opted in to > 48 KB of dynamic shared memory
   } pol;
   DreamerPolicy dr;   // on-device Dreamer agent (rd_policy_dreamer_init)
+  // device-resident steps over several tracks: the observation kernels of every track but the first run on their own
+  // stream (fork behind the step kernel, join at the end), so that a track's kernels fill the SMs the previous track's
+  // persistent CTAs leave in their tail.  RD_FORK_MAPS=0 keeps everything on the caller's stream.
+  bool fork_maps = true;
+  bool in_fork = false;           // set while observe() enqueues a forked track's kernels
+  cudaStream_t map_stream[RD_MAX_MAPS] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[RD_MAX_MAPS] = {};
   // optional per-kernel timing (rd_enable_timing)
   bool timing = false;
   struct Timed { cudaEvent_t a, b; int kind; };
@@ -225,8 +232,8 @@ cudaEvent_t take_event(rd_env* env) {
 // brackets the launches issued during its lifetime with two events on `s`
 struct ScopedTiming {
   rd_env* env; cudaStream_t s; int kind; cudaEvent_t a = nullptr;
-  ScopedTiming(rd_env* e, cudaStream_t st, int k) : env(e), s(st), kind(k) {
-    if (env->timing) { a = take_event(env); cudaEventRecord(a, s); }
+  ScopedTiming(rd_env* e, cudaStream_t st, int k, bool on = true) : env(e), s(st), kind(k) {
+    if (env->timing && on) { a = take_event(env); cudaEventRecord(a, s); }
   }
   ~ScopedTiming() {
     if (a) { cudaEvent_t b = take_event(env); cudaEventRecord(b, s); env->timed.push_back({a, b, kind}); }
@@ -329,7 +336,9 @@ int launch_lidar_t(rd_env* env, int map_id, const OriginRec* recs, const int32_t
   long long grid = std::min<long long>((items + WARPS - 1) / WARPS, (long long)env->sm_count * per_sm);
   if (grid < 1) return RD_OK;
   {
-    ScopedTiming tm(env, s, T_LIDAR);
+    // (a forked track's launch queues behind the first track's persistent CTAs: its event bracket would measure the
+    // wait, so only launches on the caller's stream are timed)
+    ScopedTiming tm(env, s, T_LIDAR, !env->in_fork);
     // Programmatic dependent launch: k_lidar's set-up (mbarrier, the bulk copy of the map into shared memory, the beam
     // table, the first draw from the work counter) overlaps the tail of the kernel in front of it on the stream
     // (k_step / k_reset trigger early with griddepcontrol.launch_dependents); k_lidar executes griddepcontrol.wait before
@@ -377,7 +386,7 @@ int launch_lidar(rd_env* env, int map_id, const OriginRec* recs, const int32_t* 
 
 int launch_occupancy(rd_env* env, int map_id, const OriginRec* recs, const double* poses_xyyaw,
                      const int32_t* order, int n_env, uint8_t* out, cudaStream_t s) {
-  ScopedTiming tm(env, s, T_OCC);
+  ScopedTiming tm(env, s, T_OCC, !env->in_fork);
   int rc = occ_launch(env->occ, env->d_maps, map_id, env->maps[map_id].dev, recs, poses_xyyaw, env->d_f2, env->n,
                       order, n_env, out, env->sm_count, s, &env->launches);
   if (rc != 0) return fail(env, RD_ERR_CUDA, "occupancy launch: %s", cudaGetErrorString((cudaError_t)rc));
@@ -452,9 +461,15 @@ int launch_step(rd_env* env, const rd_outputs* out, const float* actions_dev, cu
 }
 
 // LiDAR / occupancy launches for the envs [e0, e1) (grouped by map; each map's env list is ascending)
-int observe(rd_env* env, const rd_outputs* out, cudaStream_t s, int e0 = 0, int e1 = -1, unsigned int* ctr = nullptr) {
+int observe(rd_env* env, const rd_outputs* out, cudaStream_t s, int e0 = 0, int e1 = -1, unsigned int* ctr = nullptr,
+            bool fork = false) {
   if (!out) return RD_OK;
   if (e1 < 0) e1 = env->n;
+  int tracks = 0;
+  for (int mid = 0; mid < RD_MAX_MAPS; ++mid) tracks += env->order_offset[mid + 1] > env->order_offset[mid] ? 1 : 0;
+  fork = fork && env->fork_maps && tracks > 1;
+  bool forked[RD_MAX_MAPS] = {};
+  int seen = 0;
   for (int mid = 0; mid < RD_MAX_MAPS; ++mid) {
     const int32_t* hb = env->h_order.data() + env->order_offset[mid];
     const int32_t* he = env->h_order.data() + env->order_offset[mid + 1];
@@ -462,15 +477,34 @@ int observe(rd_env* env, const rd_outputs* out, cudaStream_t s, int e0 = 0, int 
     const int n_env = last - first;
     if (n_env == 0) continue;
     const int32_t* order = env->d_env_order + env->order_offset[mid] + first;
+    cudaStream_t sm = s;
+    if (fork && seen++ > 0) {   // the first track stays on the caller's stream (programmatic launch behind the step kernel)
+      if (!env->map_stream[mid]) {
+        CUDA_TRY(env, cudaStreamCreateWithFlags(&env->map_stream[mid], cudaStreamNonBlocking));
+        CUDA_TRY(env, cudaEventCreateWithFlags(&env->ev_join[mid], cudaEventDisableTiming));
+      }
+      sm = env->map_stream[mid];
+      CUDA_TRY(env, cudaStreamWaitEvent(sm, env->ev_fork, 0));
+      forked[mid] = true;
+    } else if (fork) {
+      // fork point: everything enqueued on `s` so far (the step / reset kernel), NOT the first track's observation kernels
+      if (!env->ev_fork) CUDA_TRY(env, cudaEventCreateWithFlags(&env->ev_fork, cudaEventDisableTiming));
+      CUDA_TRY(env, cudaEventRecord(env->ev_fork, s));
+    }
+    env->in_fork = forked[mid];
     if (out->lidar_dev && (env->cfg.obs_flags & RD_OBS_LIDAR)) {
-      int rc = launch_lidar(env, mid, env->d_recs, order, n_env, out->lidar_dev, s, ctr);
-      if (rc) return rc;
+      int rc = launch_lidar(env, mid, env->d_recs, order, n_env, out->lidar_dev, sm, ctr);
+      if (rc) { env->in_fork = false; return rc; }
     }
     if (out->occupancy_dev && (env->cfg.obs_flags & RD_OBS_OCCUPANCY)) {
-      int rc = launch_occupancy(env, mid, env->d_recs, nullptr, order, n_env, out->occupancy_dev, s);
-      if (rc) return rc;
+      int rc = launch_occupancy(env, mid, env->d_recs, nullptr, order, n_env, out->occupancy_dev, sm);
+      if (rc) { env->in_fork = false; return rc; }
     }
+    env->in_fork = false;
+    if (forked[mid]) CUDA_TRY(env, cudaEventRecord(env->ev_join[mid], sm));
   }
+  for (int mid = 0; mid < RD_MAX_MAPS; ++mid)
+    if (forked[mid]) CUDA_TRY(env, cudaStreamWaitEvent(s, env->ev_join[mid], 0));
   return RD_OK;
 }
 
@@ -579,9 +613,12 @@ RD_API int rd_create(const rd_config* cfg, rd_env** out) {
   if (const char* ev = std::getenv("RD_LIDAR_ORDER")) env->lidar_centre_first = std::atoi(ev) != 0;
   if (const char* ev = std::getenv("RD_LIDAR_GPI")) { const int v = std::atoi(ev); if (v == 1 || v == 2) env->lidar_gpi_force = v; }
   if (const char* ev = std::getenv("RD_LIDAR_GPI_MIN")) { const int v = std::atoi(ev); if (v > 0) env->lidar_gpi_min = v; }
-  env->step_split = env->n <= 64 * env->sm_count;   // up to two CTAs per SM (measured: 22.9 vs 31.9 us at 8192 envs, 39.3 vs 33.1 us
-                                                     // at 16384): larger batches are throughput-bound and one warp per 32 envs does less work
+  env->step_split = env->n <= 64 * env->sm_count;   // up to two CTAs per SM -- what the kernel's registers allow, a third CTA
+                                                     // would wait for a second wave (measured: 22.9 vs 31.9 us at 8192 envs, 39.1 vs
+                                                     // 33.0 us at 12 288; rotating the warp roles of co-resident CTAs over the
+                                                     // schedulers changes nothing, profiles/r6b_two_tracks_strong_scaling.txt)
   if (const char* ev = std::getenv("RD_STEP_SPLIT")) env->step_split = std::atoi(ev) != 0;
+  if (const char* ev = std::getenv("RD_FORK_MAPS")) env->fork_maps = std::atoi(ev) != 0;
   if (const char* ev = std::getenv("RD_STEP_BLOCK")) { int v = std::atoi(ev); if (v == 32 || v == 64 || v == 128) env->step_block = v; }
   const size_t n = (size_t)env->n;
   cudaError_t e = cudaSuccess;
@@ -646,6 +683,11 @@ RD_API void rd_destroy(rd_env* env) {
   }
   for (auto& t : env->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (auto& e : env->event_pool) cudaEventDestroy(e);
+  for (int mid = 0; mid < RD_MAX_MAPS; ++mid) {
+    if (env->map_stream[mid]) cudaStreamDestroy(env->map_stream[mid]);
+    if (env->ev_join[mid]) cudaEventDestroy(env->ev_join[mid]);
+  }
+  if (env->ev_fork) cudaEventDestroy(env->ev_fork);
   for (auto& m : env->maps) { cudaFree(m.d_bits); cudaFree(m.d_dist); cudaFree(m.d_start); cudaFree(m.d_reset); cudaFree(m.d_next); }
   delete env;
 }
@@ -789,7 +831,7 @@ RD_API int rd_reset(rd_env* env, const uint8_t* mask_dev, int mode, const rd_out
   env->launches++;
   CUDA_TRY(env, cudaGetLastError());
   env->was_reset = true;
-  return observe(env, out, s);
+  return observe(env, out, s, 0, -1, nullptr, true);
 }
 
 RD_API int rd_step(rd_env* env, const float* actions_dev, const rd_outputs* out, void* stream) {
@@ -799,7 +841,7 @@ RD_API int rd_step(rd_env* env, const float* actions_dev, const rd_outputs* out,
   cudaStream_t s = (cudaStream_t)stream;
   int rc = launch_step(env, out, actions_dev, s);
   if (rc) return rc;
-  return observe(env, out, s);
+  return observe(env, out, s, 0, -1, nullptr, true);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -630,3 +630,30 @@ def test_split_step_kernel_is_bitwise_the_single_warp_kernel(torch_cuda, monkeyp
         assert abs(sa[key] - sb[key]) <= 1e-9 * max(1.0, abs(sb[key])), key   # sums of the same terms in another order
     for e in envs:
         e.close()
+
+
+def test_tracks_on_their_own_streams_are_bitwise_one_stream(torch_cuda, monkeypatch):
+    """Batches over several tracks run every track's observation kernels but the first's on a stream of their own
+    (fork behind the step kernel, join before the call returns): same outputs as everything on the caller's stream,
+    step after step, and the outputs are complete when the caller's stream says so (read right after each call)."""
+    torch = torch_cuda
+    n = 3000
+    envs = []
+    for fork in ("1", "0"):
+        monkeypatch.setenv("RD_FORK_MAPS", fork)
+        envs.append(make_env(torch, tracks=("barcelona", "austria", "columbia"), n_envs=n, action_repeat=4, auto_reset=True,
+                             reset_mode="random", seed=12, obs_type="lidar_occupancy"))
+    first = [e.reset() for e in envs]
+    for key in first[0]:
+        assert torch.equal(first[0][key], first[1][key]), f"reset: {key}"
+    rng = np.random.RandomState(4)
+    for k in range(12):
+        a = torch.from_numpy(rng.uniform(-1, 1, (n, 2)).astype(np.float32)).cuda()
+        outs = []
+        for e in envs:
+            obs, rew, done, info = e.step(a)
+            outs.append({**{f"obs.{key}": v.clone() for key, v in obs.items()}, "reward": rew.clone(), "done": done.clone()})
+        for key in outs[0]:
+            assert torch.equal(outs[0][key], outs[1][key]), f"step {k}: {key}"
+    for e in envs:
+        e.close()
