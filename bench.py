@@ -199,9 +199,10 @@ def roofline_of(wl, n, timing, step_ms_total, value_per_gpu):
     tot = {"k_step": timing["step_ms"], "k_lidar": timing["lidar_ms"], "k_occupancy": timing["occupancy_ms"]}
     kern = max(tot, key=tot.get)
     launches = {"k_step": timing["step_launches"], "k_lidar": timing["lidar_launches"], "k_occupancy": timing["occupancy_launches"]}[kern]
-    steps = max(1, timing["step_launches"])
-    # a launch of k_lidar / k_occupancy handles the envs of ONE map: n * steps / launches envs on average
-    envs_per_launch = n * steps / max(1, launches)
+    # a launch of k_lidar / k_occupancy handles the envs of ONE track (envs alternate between the tracks).  With several
+    # tracks only the first track's launch is event-bracketed: the others run on streams of their own and queue behind
+    # its persistent CTAs, so `per` is that launch's time and the bytes are that launch's.
+    envs_per_launch = n / len(wl.tracks) if kern != "k_step" else n
     algo = KERNEL_BYTES_PER_ENV[kern] * envs_per_launch
     peak, peak_src, _ = measured_peaks()
     gbs = algo / (per[kern] * 1e-3) / 1e9 if per[kern] > 0 else 0.0
