@@ -52,6 +52,7 @@ struct DreamerPolicy {
   float* head_raw = nullptr;   // [n][4] hout pre-activations
   // k_dense_chain (the actor trunk in one launch): per-row-block layer counters and the values they have reached
   bool chain = true;           // RD_DREAMER_CHAIN=0: one k_dense launch per actor layer instead
+  bool chain_cluster = true;   // the N tiles of a row block are launched as a thread-block cluster (RD_DREAMER_CLUSTER=0: plain grid)
   bool tma_out = true;         // RD_DREAMER_TMA_OUT=0: Dense / GRU epilogues store from registers (see gm_stage_f4)
   unsigned* chain_flags = nullptr;
   unsigned chain_count[GM_CHAIN_MAX] = {};
@@ -198,6 +199,8 @@ static inline int dreamer_init(DreamerPolicy& d, int n, int n_beams, bool lidar_
     DR_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
     d.chain = true;
     if (const char* ev = std::getenv("RD_DREAMER_CHAIN")) d.chain = std::atoi(ev) != 0;
+    d.chain_cluster = true;
+    if (const char* ev = std::getenv("RD_DREAMER_CLUSTER")) d.chain_cluster = std::atoi(ev) != 0;
     d.tma_out = true;
     if (const char* ev = std::getenv("RD_DREAMER_TMA_OUT")) d.tma_out = std::atoi(ev) != 0;
   }
@@ -374,7 +377,7 @@ static inline int dreamer_step(DreamerPolicy& d, const float* lidar, float* acti
       cm.w[j][0] = d.w_act[i].m[0]; cm.w[j][1] = d.w_act[i].m[1];
       if (j + 1 == c.n_layers) { cm.o_last[0] = d.hid[i & 1].m[0]; cm.o_last[1] = d.hid[i & 1].m[1]; }
     }
-    DR_TRY((gm_launch_chain<DR_ACT_STAGES, DR_ACT_EW, DR_ACT_BN>(cm, c, d.sm_count, s)));
+    DR_TRY((gm_launch_chain<DR_ACT_STAGES, DR_ACT_EW, DR_ACT_BN>(cm, c, d.sm_count, d.chain_cluster, s)));
     ++*launched;
   }
   for (int i = 0; !chain && i < d.layers; ++i) {

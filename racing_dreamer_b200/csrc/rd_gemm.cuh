@@ -29,6 +29,8 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 #include "rd_common.cuh"
 
@@ -812,7 +814,9 @@ __global__ void __launch_bounds__(256) k_latent_copy(float* __restrict__ feat, f
 // per-layer launches; what goes away is, per layer, a launch, a CTA set-up (barriers, TMEM, tensor maps) and the
 // drain / fill of the whole grid around a kernel boundary.
 //   * grid (N tiles, row-block groups): CTA (x, y) owns output columns [x BN, (x + 1) BN) of the 128-env row blocks
-//     y, y + gridDim.y, ...; the host keeps the grid within one CTA per SM, so all CTAs are resident together.
+//     y, y + gridDim.y, ...  The N tiles of a row block are launched as ONE thread-block cluster, so the hardware runs
+//     the CTAs that wait for each other together whatever else occupies the SMs (33 such clusters fit a B200 at once;
+//     the host sizes the grid to that to keep the work in one wave).
 //   * layer l + 1 of a row block reads what ALL N tiles of layer l wrote for that row block: each CTA bumps the
 //     counter flags[l][row block] (stores -> __threadfence -> CTA barrier of the epilogue warps -> atomic) and the
 //     producer thread of each CTA waits for it to reach `target[l]` (acquire load, then fence.proxy.async before the
@@ -1159,9 +1163,10 @@ static inline cudaError_t gm_launch(const GemmMaps& maps, const GemmArgs& g, cud
 }
 
 template <int GM_STAGES, int EW, int BN>
-static inline cudaError_t gm_launch_chain(const ChainMaps& maps, const ChainArgs& g, int sm_count, cudaStream_t s) {
+static inline cudaError_t gm_launch_chain(const ChainMaps& maps, const ChainArgs& g, int sm_count, bool cluster, cudaStream_t s) {
   constexpr size_t smem = (size_t)GM_STAGES * 2 * (GM_A_BYTES + BN * 128) + 1024;
   static bool attr = false;
+  static int max_clusters = -1;   // co-resident clusters of this shape on this device (cluster launches)
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(k_dense_chain<GM_STAGES, EW, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1169,15 +1174,33 @@ static inline cudaError_t gm_launch_chain(const ChainMaps& maps, const ChainArgs
   }
   const int nt = (g.N + BN - 1) / BN;
   cudaLaunchConfig_t cfg = {};
-  // every CTA must be resident (they wait for each other's row-block counters): one CTA per SM, whole row-block groups
-  cfg.gridDim = dim3((unsigned)nt, (unsigned)std::max(1, std::min(g.row_blocks, sm_count / nt)));
   cfg.blockDim = dim3(64 + 128 * EW);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attrs[1];
+  cudaLaunchAttribute attrs[2];
   attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
+  // The CTAs of a row block wait for each other's counters, so they must run together.  As a thread-block cluster
+  // (the N tiles of a row block = one cluster) the hardware guarantees exactly that, whatever else occupies the SMs;
+  // the grid is then sized to the clusters that fit at once only to keep the work in one wave.  Without clusters the
+  // guarantee is the grid size (one CTA per SM, whole row-block groups, CTAs dispatched in index order).
+  int groups = std::max(1, std::min(g.row_blocks, sm_count / nt));
+  if (cluster && nt <= 8) {
+    attrs[1].id = cudaLaunchAttributeClusterDimension;
+    attrs[1].val.clusterDim.x = (unsigned)nt; attrs[1].val.clusterDim.y = 1; attrs[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+    if (max_clusters < 0) {
+      cfg.gridDim = dim3((unsigned)nt, (unsigned)groups);
+      int q = 0;
+      cudaError_t e = cudaOccupancyMaxActiveClusters(&q, k_dense_chain<GM_STAGES, EW, BN>, &cfg);
+      if (e != cudaSuccess) return e;
+      max_clusters = std::max(1, q);
+      if (std::getenv("RD_DREAMER_DEBUG")) std::fprintf(stderr, "k_dense_chain: %d clusters of %d CTAs fit at once\n", max_clusters, nt);
+    }
+    groups = std::min(groups, max_clusters);
+  }
+  cfg.gridDim = dim3((unsigned)nt, (unsigned)groups);
   return cudaLaunchKernelEx(&cfg, k_dense_chain<GM_STAGES, EW, BN>, maps, g);
 }
