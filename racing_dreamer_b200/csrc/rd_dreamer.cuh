@@ -2,7 +2,8 @@
 //
 // One agent step = RacingDreamer.action [REF ros_agent/models/dreamer/racing_dreamer.py:62-82] for every env:
 //   img1 -> GRU cell -> obs1 (concat([deter, embed])) -> obs2 + posterior sample -> actor h0..h3 -> hout + mode()
-// = nine launches of k_dense (rd_gemm.cuh); activations live in a handful of [envs][width] float32 arrays that stay in
+// = k_embed_lidar, five launches of k_dense, one of k_dense_chain (the actor trunk) and k_actor_mode (rd_gemm.cuh);
+// activations live in a handful of [envs][width] float32 arrays that stay in
 // L2 between launches, the recurrent state in two ping-pong "latent" arrays whose rows are
 //   [ stoch (30) | previous action (2) | deter (200) ]          (232 floats, 928 bytes)
 // so that img1's input concat([stoch, action]), the GRU's state, obs1's concat([deter, ...]) and the actor's
