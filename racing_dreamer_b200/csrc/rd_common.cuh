@@ -45,8 +45,6 @@ struct LidarParams {
   int gpi;               // beam groups per work item (1 or 2, see k_lidar)
   int units;             // work items per env: ceil(groups / gpi)
   unsigned groups_magic; // ceil(2^32 / units): item / units == umulhi(item, groups_magic) (k_lidar)
-  unsigned chunk_draws;  // k_lidar work counter: draws below this hand out RD_LIDAR_CHUNK items each, the ones after it ONE
-                         // item (the tail of the list: the warps finish within one item of each other, not one chunk)
   unsigned envs_magic;   // ceil(2^32 / n_env of the launch), centre_first order
   int centre_first;      // work order: beam groups from the centre of the scan outwards, envs innermost
   int normalize;         // 1: RD_OBS_LIDAR_NORM (r / range_max - 0.5); 2: RD_OBS_NORM_BASELINES ((r - norm_lo) * norm_sc)

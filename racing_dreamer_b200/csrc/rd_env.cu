@@ -117,7 +117,6 @@ struct rd_env {
   // device-resident steps over several tracks: the observation kernels of every track but the first run on their own
   // stream (fork behind the step kernel, join at the end), so that a track's kernels fill the SMs the previous track's
   // persistent CTAs leave in their tail.  RD_FORK_MAPS=0 keeps everything on the caller's stream.
-  int lidar_tail = 2;             // k_lidar: single-item draws per resident warp at the end of the work list
   bool fork_maps = true;
   bool in_fork = false;           // set while observe() enqueues a forked track's kernels
   cudaStream_t map_stream[RD_MAX_MAPS] = {};
@@ -336,10 +335,6 @@ int launch_lidar_t(rd_env* env, int map_id, const OriginRec* recs, const int32_t
                 map_id, m.w, m.h, (long long)(lp.rsub >> RD_SUB_BITS));
   long long grid = std::min<long long>((items + WARPS - 1) / WARPS, (long long)env->sm_count * per_sm);
   if (grid < 1) return RD_OK;
-  {   // the last lidar_tail items per resident warp are drawn one at a time (RD_LIDAR_TAIL overrides, 0 = whole chunks only)
-    const long long tail = std::min<long long>(items, (long long)env->lidar_tail * grid * WARPS);
-    lp.chunk_draws = (unsigned)((items - tail) / RD_LIDAR_CHUNK);
-  }
   {
     // (a forked track's launch queues behind the first track's persistent CTAs: its event bracket would measure the
     // wait, so only launches on the caller's stream are timed)
@@ -624,7 +619,6 @@ RD_API int rd_create(const rd_config* cfg, rd_env** out) {
                                                      // schedulers changes nothing, profiles/r6b_two_tracks_strong_scaling.txt)
   if (const char* ev = std::getenv("RD_STEP_SPLIT")) env->step_split = std::atoi(ev) != 0;
   if (const char* ev = std::getenv("RD_FORK_MAPS")) env->fork_maps = std::atoi(ev) != 0;
-  if (const char* ev = std::getenv("RD_LIDAR_TAIL")) { const int v = std::atoi(ev); if (v >= 0 && v <= 64) env->lidar_tail = v; }
   if (const char* ev = std::getenv("RD_STEP_BLOCK")) { int v = std::atoi(ev); if (v == 32 || v == 64 || v == 128) env->step_block = v; }
   const size_t n = (size_t)env->n;
   cudaError_t e = cudaSuccess;

@@ -115,7 +115,7 @@ k_lidar(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict
   const int lane = threadIdx.x & 31;
   unsigned ahead = 0;
   bool have_ahead = true;
-  if (lane == 0) ahead = rd_atom_add(ctr, 1u);
+  if (lane == 0) ahead = rd_atom_add(ctr, (unsigned)RD_LIDAR_CHUNK);
   MarchGrid grid;
   grid.bits = bits;
   grid.coarse = reinterpret_cast<const uint8_t*>(bits) + m.coarse_off;
@@ -134,14 +134,12 @@ k_lidar(const DevMap* __restrict__ maps, int map_id, const OriginRec* __restrict
   unsigned item = 0, last = 0;
   for (;;) {
     if (item >= last) {
-      // the counter counts DRAWS: the first lp.chunk_draws of them are RD_LIDAR_CHUNK items each, the rest one item
-      if (!have_ahead && lane == 0) ahead = rd_atom_add(ctr, 1u);
-      const unsigned d = __shfl_sync(0xffffffffu, ahead, 0);
+      const unsigned chunk = RD_LIDAR_CHUNK;
+      if (!have_ahead && lane == 0) ahead = rd_atom_add(ctr, chunk);
+      item = __shfl_sync(0xffffffffu, ahead, 0);
       have_ahead = false;
-      const bool whole = d < lp.chunk_draws;
-      item = whole ? d * (unsigned)RD_LIDAR_CHUNK : lp.chunk_draws * (unsigned)RD_LIDAR_CHUNK + (d - lp.chunk_draws);
       if (item >= total_items) break;
-      last = min(item + (whole ? (unsigned)RD_LIDAR_CHUNK : 1u), total_items);
+      last = min(item + chunk, total_items);
     }
     {
       unsigned slot;
