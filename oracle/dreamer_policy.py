@@ -66,8 +66,14 @@ def load_checkpoint(checkpoint_dir) -> Dict[str, np.ndarray]:
     return {k: np.asarray(v, np.float32) for k, v in w.items()}
 
 
-def random_weights(seed: int, n_beams: int = 1080, normalized: bool = False) -> Dict[str, np.ndarray]:
-    """Glorot-ish random weights of the shipped architecture (for tests on machines without the checkpoints)."""
+def n_actor_layers(w) -> int:
+    """Trunk layers of a weight dict: h0_w, h1_w, ... (the shipped agents have ACTOR_LAYERS)."""
+    return sum(1 for k in w if k.startswith("h") and k.endswith("_w") and k[1:-2].isdigit())
+
+
+def random_weights(seed: int, n_beams: int = 1080, normalized: bool = False, actor_layers: int = ACTOR_LAYERS) -> Dict[str, np.ndarray]:
+    """Glorot-ish random weights of the shipped architecture (for tests on machines without the checkpoints);
+    actor_layers other than the shipped four exercise the product's general trunk path."""
     rng = np.random.RandomState(seed)
 
     def dense(i, o):
@@ -83,7 +89,7 @@ def random_weights(seed: int, n_beams: int = 1080, normalized: bool = False) -> 
     w["obs1_w"], w["obs1_b"] = dense(DETER + n_beams, HIDDEN)
     w["obs2_w"], w["obs2_b"] = dense(HIDDEN, 2 * STOCH)
     i = STOCH + DETER
-    for k in range(ACTOR_LAYERS):
+    for k in range(actor_layers):
         w[f"h{k}_w"], w[f"h{k}_b"] = dense(i, ACTOR_UNITS)
         i = ACTOR_UNITS
     w["hout_w"], w["hout_b"] = dense(ACTOR_UNITS, 4)
@@ -144,7 +150,7 @@ def actor_dist(w, feat, dtype=np.float64):
     """ActionDecoder.__call__ -> (mean, std) of the pre-tanh Normal [REF models.py:320-346]."""
     dt = dtype
     x = feat.astype(dt)
-    for i in range(ACTOR_LAYERS):
+    for i in range(n_actor_layers(w)):
         x = _elu(x @ w[f"h{i}_w"].astype(dt) + w[f"h{i}_b"].astype(dt))
     x = x @ w["hout_w"].astype(dt) + w["hout_b"].astype(dt)
     if "bn_gamma" in w:   # 'normalized_tanhtransformed_normal' [REF models.py:335-346], training=False

@@ -164,23 +164,29 @@ class DreamerPolicy:
         hidden = w["img1_w"].shape[1]
         units = w["h0_w"].shape[1]
         embed = w["obs1_w"].shape[0] - deter
+        # the shipped agents have four trunk layers [REF racing_dreamer.py:22-26]; a weight dict may hold 1..7 (h0_w ...)
+        layers = sum(1 for k in w if k.startswith("h") and k.endswith("_w") and k[1:-2].isdigit())
+        if not 1 <= layers <= 7 or any(f"h{i}_w" not in w or f"h{i}_b" not in w for i in range(layers)):
+            raise ValueError(f"actor trunk: expected h0_w/h0_b .. h{{k}}_w/h{{k}}_b for 1..7 layers, found {layers}")
         expect = {"gru_kernel": (hidden, 3 * deter), "gru_recurrent": (deter, 3 * deter), "gru_bias": (2, 3 * deter),
                   "img1_w": (_STOCH + 2, hidden), "img1_b": (hidden,), "obs1_w": (deter + embed, hidden),
                   "obs1_b": (hidden,), "obs2_w": (hidden, 2 * _STOCH), "obs2_b": (2 * _STOCH,),
                   "h0_w": (_STOCH + deter, units), "hout_w": (units, 4), "hout_b": (4,)}
+        expect.update({f"h{i}_w": (units, units) for i in range(1, layers)})
+        expect.update({f"h{i}_b": (units,) for i in range(layers)})
         for k, shp in expect.items():
             if w[k].shape != shp:
                 raise ValueError(f"checkpoint array {k} has shape {w[k].shape}, expected {shp}")
         if embed != env.n_beams:
             raise ValueError(f"the checkpoint embeds {embed} beams, the env casts {env.n_beams}")
         s = _abi.RdDreamerWeights()
-        s.stoch, s.deter, s.hidden, s.embed, s.actor_units, s.actor_layers = _STOCH, deter, hidden, embed, units, _ACTOR_LAYERS
+        s.stoch, s.deter, s.hidden, s.embed, s.actor_units, s.actor_layers = _STOCH, deter, hidden, embed, units, layers
         ptr = lambda a: a.ctypes.data_as(C.c_void_p)   # noqa: E731
         for k in ("gru_kernel", "gru_recurrent", "gru_bias", "img1_w", "img1_b", "obs1_w", "obs1_b", "obs2_w", "obs2_b"):
             setattr(s, k, ptr(w[k]))
-        for i in range(_ACTOR_LAYERS):
+        for i in range(layers):
             s.actor_w[i], s.actor_b[i] = ptr(w[f"h{i}_w"]), ptr(w[f"h{i}_b"])
-        s.actor_w[_ACTOR_LAYERS], s.actor_b[_ACTOR_LAYERS] = ptr(w["hout_w"]), ptr(w["hout_b"])
+        s.actor_w[layers], s.actor_b[layers] = ptr(w["hout_w"]), ptr(w["hout_b"])
         self._bn = None
         if has_bn:
             self._bn = np.ascontiguousarray(np.stack([w["bn_gamma"], w["bn_beta"], w["bn_mean"], w["bn_var"]]), np.float32)

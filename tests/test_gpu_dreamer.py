@@ -287,6 +287,32 @@ def test_actor_chain_is_bitwise_the_per_layer_launches(torch_cuda, weights, monk
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("layers", [1, 6])
+def test_actor_trunk_depths_other_than_the_shipped_four(torch_cuda, layers):
+    """The C ABI takes 1..7 trunk layers; k_dense_chain runs them four per launch (6 = a launch of four and one of two,
+    1 = a launch without any counter).  Random weights, explicit noise, against the float64 restatement."""
+    torch = torch_cuda
+    from racing_dreamer_b200 import DreamerPolicy
+    n = 700
+    w = dp.random_weights(30 + layers, actor_layers=layers)
+    env = make_env(tracks=("austria",), n_envs=n, action_repeat=4, reset_mode="random", seed=4)
+    scans = env.reset()["lidar"].clone()
+    pol = DreamerPolicy(env, w, noise="explicit")
+    rng = np.random.RandomState(6)
+    state = (rng.standard_normal((n, 30)), rng.uniform(-1, 1, (n, 200)), rng.uniform(-1, 1, (n, 2)))
+    pol.set_state(*[torch.from_numpy(s.astype(np.float32)) for s in state])
+    es, ea = rng.standard_normal((n, 30)).astype(np.float32), rng.standard_normal((n, 100, 2)).astype(np.float32)
+    state32 = tuple(s.astype(np.float32).astype(np.float64) for s in state)
+    act_ref, new_state, ref = dp.policy_step(w, scans.cpu().numpy(), state32, es, ea, np.float64)
+    for rep in range(2):   # twice: the counters of the second launch start where the first one left them
+        pol.set_state(*[torch.from_numpy(s.astype(np.float32)) for s in state])
+        pol.act(scans, torch.from_numpy(es), torch.from_numpy(ea), debug=True)
+        d = pol.diagnostics()
+        close(f"actor_mean (pass {rep})", d["actor_mean"].cpu().numpy(), ref["actor_mean"], RTOL * HEAD, ATOL * HEAD, dp.MEAN_SCALE)
+        close(f"actor_std (pass {rep})", d["actor_std"].cpu().numpy(), ref["actor_std"], RTOL * HEAD, ATOL * HEAD, dp.MEAN_SCALE)
+    env.close()
+
+
 def test_error_paths(torch_cuda, weights):
     torch = torch_cuda
     from racing_dreamer_b200 import DreamerPolicy
