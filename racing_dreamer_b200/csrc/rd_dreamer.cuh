@@ -2,7 +2,8 @@
 //
 // One agent step = RacingDreamer.action [REF ros_agent/models/dreamer/racing_dreamer.py:62-82] for every env:
 //   img1 -> GRU cell -> obs1 (concat([deter, embed])) -> obs2 + posterior sample -> actor h0..h3 -> hout + mode()
-// = k_embed_lidar, five launches of k_dense, one of k_dense_chain (the actor trunk) and k_actor_mode (rd_gemm.cuh);
+// = k_embed_lidar, four launches of k_dense, one of k_dense_chain (the actor trunk and, up to 33 x 128 envs, hout: a
+// fifth k_dense launch otherwise) and k_actor_mode (rd_gemm.cuh);
 // activations live in a handful of [envs][width] float32 arrays that stay in
 // L2 between launches, the recurrent state in two ping-pong "latent" arrays whose rows are
 //   [ stoch (30) | previous action (2) | deter (200) ]          (232 floats, 928 bytes)
@@ -53,6 +54,7 @@ struct DreamerPolicy {
   float* head_raw = nullptr;   // [n][4] hout pre-activations
   // k_dense_chain (the actor trunk in one launch): per-row-block layer counters and the values they have reached
   bool chain = true;           // RD_DREAMER_CHAIN=0: one k_dense launch per actor layer instead
+  bool head_fused = true;      // hout inside the last k_dense_chain launch (cluster launches of <= 33 row blocks; RD_DREAMER_HEAD=0: own launch)
   bool chain_cluster = true;   // the N tiles of a row block are launched as a thread-block cluster (RD_DREAMER_CLUSTER=0: plain grid)
   bool tma_out = true;         // RD_DREAMER_TMA_OUT=0: Dense / GRU epilogues store from registers (see gm_stage_f4)
   unsigned* chain_flags = nullptr;
@@ -200,6 +202,8 @@ static inline int dreamer_init(DreamerPolicy& d, int n, int n_beams, bool lidar_
     DR_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
     d.chain = true;
     if (const char* ev = std::getenv("RD_DREAMER_CHAIN")) d.chain = std::atoi(ev) != 0;
+    d.head_fused = true;
+    if (const char* ev = std::getenv("RD_DREAMER_HEAD")) d.head_fused = std::atoi(ev) != 0;
     d.chain_cluster = true;
     if (const char* ev = std::getenv("RD_DREAMER_CLUSTER")) d.chain_cluster = std::atoi(ev) != 0;
     d.tma_out = true;
@@ -355,6 +359,7 @@ static inline int dreamer_step(DreamerPolicy& d, const float* lidar, float* acti
   }
   // 5. actor trunk [REF models.py:321-322]: float32-grade mode runs up to GM_CHAIN_MAX layers per launch (k_dense_chain)
   const bool chain = d.x3 && d.chain;
+  bool head_fused = false;   // hout computed by the last chain launch (k_dense_chain's fused head)
   for (int i0 = 0; chain && i0 < d.layers; i0 += GM_CHAIN_MAX) {
     ChainMaps cm;
     ChainArgs c{};
@@ -378,7 +383,11 @@ static inline int dreamer_step(DreamerPolicy& d, const float* lidar, float* acti
       cm.w[j][0] = d.w_act[i].m[0]; cm.w[j][1] = d.w_act[i].m[1];
       if (j + 1 == c.n_layers) { cm.o_last[0] = d.hid[i & 1].m[0]; cm.o_last[1] = d.hid[i & 1].m[1]; }
     }
-    DR_TRY((gm_launch_chain<DR_ACT_STAGES, DR_ACT_EW, DR_ACT_BN>(cm, c, d.sm_count, d.chain_cluster, s)));
+    if (d.head_fused && i0 + c.n_layers == d.layers) {
+      c.head = 1; c.head_bias = d.b_act[d.layers]; c.head_out = d.head_raw;
+      cm.wh[0] = d.w_act[d.layers].m[0]; cm.wh[1] = d.w_act[d.layers].m[1];
+    }
+    DR_TRY((gm_launch_chain<DR_ACT_STAGES, DR_ACT_EW, DR_ACT_BN>(cm, c, d.sm_count, d.chain_cluster, s, &head_fused)));
     ++*launched;
   }
   for (int i = 0; !chain && i < d.layers; ++i) {
@@ -405,9 +414,11 @@ static inline int dreamer_step(DreamerPolicy& d, const float* lidar, float* acti
     g.n_samples = d.n_samples;
     g.dbg = debug ? debug + (size_t)d.n * 2 * GM_STOCH : nullptr;
     g.out = d.head_raw;
-    if (d.x3) DR_TRY((gm_launch<EPI_ACTOR, 1, 4, 4, true>(maps, g, s)));
-    else DR_TRY((gm_launch<EPI_ACTOR, 1, 4, 4>(maps, g, s)));
-    ++*launched;
+    if (!head_fused) {
+      if (d.x3) DR_TRY((gm_launch<EPI_ACTOR, 1, 4, 4, true>(maps, g, s)));
+      else DR_TRY((gm_launch<EPI_ACTOR, 1, 4, 4>(maps, g, s)));
+      ++*launched;
+    }
     {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)((d.n + 7) / 8));

@@ -832,6 +832,7 @@ struct ChainMaps {   // [layer][hi, lo]; layer l stores its output through a[l +
   CUtensorMap a[GM_CHAIN_MAX][2];
   CUtensorMap w[GM_CHAIN_MAX][2];
   CUtensorMap o_last[2];
+  CUtensorMap wh[2];          // ChainArgs::head: the head's weights [4][K] (hi, lo), box 32 x 64 rows
 };
 struct ChainLayer {
   int kb_total;            // K blocks of the layer
@@ -846,6 +847,13 @@ struct ChainArgs {
   int M, N, ldo, n_layers, row_blocks;
   unsigned* flags;         // [GM_CHAIN_MAX][row_blocks]
   ChainLayer L[GM_CHAIN_MAX];
+  // Fused output head (ActionDecoder hout, 4 columns): cluster launches with one row block per cluster only.  The last
+  // layer's output tiles never leave shared memory: every CTA multiplies its own 128 columns -- staged as MMA-ready
+  // 128-byte-swizzled tiles anyway -- with its K slice of the head's weights, and the cluster's first CTA adds the
+  // four partial [128][4] products (distributed shared memory) and the bias.
+  int head;
+  const float* head_bias;  // [4]
+  float* head_out;         // [M][4] pre-activations (k_actor_mode reads them)
 };
 
 __device__ __forceinline__ void gm_flag_wait(const unsigned* flag, unsigned target) {
@@ -863,6 +871,8 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
     k_dense_chain(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
   extern __shared__ uint8_t gm_smem_raw[];
   __shared__ uint64_t full_bar[GM_STAGES], empty_bar[GM_STAGES], acc_bar, tmem_free_bar, epi_done_bar;
+  __shared__ uint64_t head_full_bar, stage_ready_bar, head_acc_bar;   // fused head (g.head)
+  __shared__ float4 head_red[4][GM_BM];                              // CTA 0 of the cluster: the four partial products
   __shared__ uint32_t tmem_slot;
 #ifdef GM_CHAIN_TRACE   // per-role clock stamps of the first row block (tools/gpu_chain_trace.sh)
   __shared__ long long tr[GM_CHAIN_MAX][16];
@@ -878,8 +888,23 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
   const uint32_t smem_base = (rd_smem_u32(gm_smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;
+  // fused head: this CTA's live 32-column parts, and where the ring stands after the last K block (g.head implies one
+  // row block per CTA, so the K blocks of the launch are those of its layers)
+  const int head_parts = g.head ? min(EW, (g.N - n0 + 31) / 32) : 0;
+  uint32_t head_it = 0;
+  for (int l = 0; l < g.n_layers; ++l) head_it += (uint32_t)g.L[l].kb_total;
+  // staging tile of part p (see the epilogue) and the idle weight slot that receives the head's K slice for it
+  auto head_a_hi = [&](int p) -> uint32_t {
+    const uint32_t st = p < 2 ? (head_it + (uint32_t)p) % 3u : (head_it + 2u) % 3u;
+    return smem_base + st * STAGE_BYTES + (p == 3 ? GM_A_BYTES : 0u);
+  };
+  auto head_w_hi = [&](int p) -> uint32_t {   // parts 0, 1 -> W slots of stage head_it % 3; parts 2, 3 -> of the next stage
+    const uint32_t st = (head_it + (uint32_t)(p >> 1)) % 3u;
+    return smem_base + st * STAGE_BYTES + GM_A_BYTES + (uint32_t)(p & 1) * SUB_BYTES;
+  };
 
   if (threadIdx.x == 0) {
+    if (g.head) { gm_prefetch_map(&maps.wh[0]); gm_prefetch_map(&maps.wh[1]); }
     for (int l = 0; l < g.n_layers; ++l) {
       gm_prefetch_map(&maps.a[l][0]); gm_prefetch_map(&maps.a[l][1]);
       gm_prefetch_map(&maps.w[l][0]); gm_prefetch_map(&maps.w[l][1]);
@@ -892,6 +917,9 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(rd_smem_u32(&acc_bar)));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rd_smem_u32(&tmem_free_bar)), "r"(4 * EW));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rd_smem_u32(&epi_done_bar)), "r"(EW));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(rd_smem_u32(&head_full_bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rd_smem_u32(&stage_ready_bar)), "r"(EW));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(rd_smem_u32(&head_acc_bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) gm_tmem_alloc(&tmem_slot, TM_COLS);
@@ -954,6 +982,16 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
           ++tile;
         }
       }
+      if (g.head) {
+        // the head's weights go into ring slots no staging tile uses; the ring is idle once the last MMAs are complete
+        gm_mbar_wait(&acc_bar, (tile - 1) & 1u);
+        rd_mbar_expect_tx(&head_full_bar, (uint32_t)head_parts * 2u * GM_W_BYTES);
+        for (int p = 0; p < head_parts; ++p) {
+          const uint32_t w = head_w_hi(p);
+          gm_tma_2d(w, &maps.wh[0], n0 + 32 * p, 0, &head_full_bar);
+          gm_tma_2d(w + GM_W_BYTES, &maps.wh[1], n0 + 32 * p, 0, &head_full_bar);
+        }
+      }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -997,6 +1035,29 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
           gm_commit(&acc_bar);
           GM_TR(l, 3);
         }
+      }
+      if (g.head) {
+        // hout's partial product over this CTA's K slice, straight from the staged output tiles: hi*hi into TMEM
+        // columns 0..15, the two cross products into columns 16..31 (N = 16: the head's 4 rows + zero-filled ones)
+        gm_mbar_wait(&tmem_free_bar, (tile - 1) & 1u);   // the last layer's accumulators have been read
+        gm_mbar_wait(&stage_ready_bar, 0);                // its output tiles are staged (and fenced for the async proxy)
+        gm_mbar_wait(&head_full_bar, 0);                  // the weights' K slice has landed
+        gm_tc_fence_after();
+        constexpr uint32_t IDESC16 = GM_IDESC_N(16);
+        for (int p = 0; p < head_parts; ++p) {
+          const uint32_t a_hi = gm_desc_lo(head_a_hi(p)), a_lo = a_hi + (SUB_BYTES >> 4);
+          const uint32_t w_hi = gm_desc_lo(head_w_hi(p)), w_lo = w_hi + (GM_W_BYTES >> 4);
+#pragma unroll
+          for (int k = 0; k < GM_BK / 8; ++k)
+            gm_mma_tf32(tmem + 16u, gm_desc(a_lo + 2 * k), gm_desc(w_hi + 2 * k), IDESC16, (p > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < GM_BK / 8; ++k)
+            gm_mma_tf32(tmem + 16u, gm_desc(a_hi + 2 * k), gm_desc(w_lo + 2 * k), IDESC16, 1u);
+#pragma unroll
+          for (int k = 0; k < GM_BK / 8; ++k)
+            gm_mma_tf32(tmem, gm_desc(a_hi + 2 * k), gm_desc(w_hi + 2 * k), IDESC16, (p > 0 || k > 0) ? 1u : 0u);
+        }
+        gm_commit(&head_acc_bar);
       }
     }
     __syncwarp();
@@ -1060,7 +1121,10 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rd_smem_u32(&tmem_free_bar)) : "memory");
         asm volatile("bar.sync %0, 128;" ::"r"(1 + part) : "memory");    // the part's four warps
-        if (q == 0 && lane == 0) {
+        const bool to_head = g.head && l + 1 == g.n_layers;   // the tiles feed the fused head instead of leaving the SM
+        if (q == 0 && lane == 0 && to_head) {
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rd_smem_u32(&stage_ready_bar)) : "memory");
+        } else if (q == 0 && lane == 0) {
           if (any) {
             const CUtensorMap* mo = l + 1 < g.n_layers ? &maps.a[l + 1][0] : &maps.o_last[0];
             const CUtensorMap* mo2 = l + 1 < g.n_layers ? &maps.a[l + 1][1] : &maps.o_last[1];
@@ -1087,12 +1151,42 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
       }
     }
     if (q == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the last tile's stores
+    if (g.head && part == 0) {
+      // this CTA's partial [128][4] of hout -> slot blockIdx.x of the cluster's first CTA (distributed shared memory)
+      gm_mbar_wait(&head_acc_bar, 0, true);
+      gm_tc_fence_after();
+      float m8[8], s8[8];
+      gm_tmem_ld8(tl, m8);
+      gm_tmem_ld8(tl + 16u, s8);
+      const float4 v = make_float4(m8[0] + s8[0], m8[1] + s8[1], m8[2] + s8[2], m8[3] + s8[3]);
+      uint32_t remote;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(rd_smem_u32(&head_red[blockIdx.x][r])), "r"(0));
+      asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    }
     gm_tc_fence_before();
   }
   __syncthreads();
   if (warp == 1) {
     gm_tc_fence_after();
     gm_tmem_free(tmem, TM_COLS);
+  }
+  if (g.head) {
+    // every thread of the cluster arrives; the first CTA waits for the other three's partials, adds them in CTA order
+    // and stores hout's pre-activations (the others may exit: nobody writes into their shared memory)
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    if (blockIdx.x == 0) {
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+      if (warp >= 2 && ((warp - 2) >> 2) == 0) {
+        const int rr = (warp & 3) * 32 + lane;
+        const int row = (int)blockIdx.y * GM_BM + rr;
+        if (row < g.M) {
+          float4 o = head_red[0][rr];
+          for (int x = 1; x < (int)gridDim.x; ++x) { const float4 t = head_red[x][rr]; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+          o.x += __ldg(g.head_bias + 0); o.y += __ldg(g.head_bias + 1); o.z += __ldg(g.head_bias + 2); o.w += __ldg(g.head_bias + 3);
+          *reinterpret_cast<float4*>(g.head_out + (size_t)row * 4) = o;
+        }
+      }
+    }
   }
 #ifdef GM_CHAIN_TRACE
   if (threadIdx.x == 0 && g.L[0].target == 40u * gridDim.x * EW && (blockIdx.y % 8) == 0)
@@ -1163,7 +1257,11 @@ static inline cudaError_t gm_launch(const GemmMaps& maps, const GemmArgs& g, cud
 }
 
 template <int GM_STAGES, int EW, int BN>
-static inline cudaError_t gm_launch_chain(const ChainMaps& maps, const ChainArgs& g, int sm_count, bool cluster, cudaStream_t s) {
+// g.head != 0 asks for the fused output head; *head_fused tells whether this launch could take it (cluster launch, one
+// row block per cluster) -- if not, the caller runs the head as a k_dense launch of its own.
+static inline cudaError_t gm_launch_chain(const ChainMaps& maps, const ChainArgs& g_in, int sm_count, bool cluster, cudaStream_t s,
+                                          bool* head_fused) {
+  ChainArgs g = g_in;
   constexpr size_t smem = (size_t)GM_STAGES * 2 * (GM_A_BYTES + BN * 128) + 1024;
   static bool attr = false;
   static int max_clusters = -1;   // co-resident clusters of this shape on this device (cluster launches)
@@ -1201,6 +1299,8 @@ static inline cudaError_t gm_launch_chain(const ChainMaps& maps, const ChainArgs
     }
     groups = std::min(groups, max_clusters);
   }
+  g.head = (g.head && cfg.numAttrs == 2 && groups == g.row_blocks && nt <= 4) ? 1 : 0;
+  if (head_fused) *head_fused = g.head != 0;
   cfg.gridDim = dim3((unsigned)nt, (unsigned)groups);
   return cudaLaunchKernelEx(&cfg, k_dense_chain<GM_STAGES, EW, BN>, maps, g);
 }

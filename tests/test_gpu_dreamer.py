@@ -274,6 +274,7 @@ def test_actor_chain_is_bitwise_the_per_layer_launches(torch_cuda, weights, monk
     torch = torch_cuda
     from racing_dreamer_b200 import DreamerPolicy
     outs = []
+    monkeypatch.setenv("RD_DREAMER_HEAD", "0")   # (the fused head sums hout's K range in another order: own test below)
     for chain in ("1", "0"):
         monkeypatch.setenv("RD_DREAMER_CHAIN", chain)
         env = make_env(tracks=("austria",), n_envs=n, action_repeat=4, reset_mode="random", seed=9, auto_reset=True)
@@ -311,6 +312,35 @@ def test_actor_trunk_depths_other_than_the_shipped_four(torch_cuda, layers):
         close(f"actor_mean (pass {rep})", d["actor_mean"].cpu().numpy(), ref["actor_mean"], RTOL * HEAD, ATOL * HEAD, dp.MEAN_SCALE)
         close(f"actor_std (pass {rep})", d["actor_std"].cpu().numpy(), ref["actor_std"], RTOL * HEAD, ATOL * HEAD, dp.MEAN_SCALE)
     env.close()
+
+
+@pytest.mark.parametrize("n", [300, 4096, 5000])
+def test_fused_head_agrees_with_the_head_launch(torch_cuda, weights, monkeypatch, n):
+    """hout inside the last k_dense_chain launch (each CTA of a cluster multiplies its own 128 staged output columns
+    with its K slice of the head's weights, the first CTA adds the four partial products) against hout as a k_dense
+    launch of its own: the same float32-grade products summed in another order.  5000 envs = 40 row blocks: more than
+    fit at once, so the library falls back to the separate launch by itself and the two runs are bitwise equal."""
+    torch = torch_cuda
+    from racing_dreamer_b200 import DreamerPolicy
+    rng = np.random.RandomState(8)
+    es, ea = rng.standard_normal((n, 30)).astype(np.float32), rng.standard_normal((n, 100, 2)).astype(np.float32)
+    diags = []
+    for head in ("1", "0"):
+        monkeypatch.setenv("RD_DREAMER_HEAD", head)
+        env = make_env(tracks=("austria",), n_envs=n, action_repeat=4, reset_mode="random", seed=9)
+        scans = env.reset()["lidar"].clone()
+        pol = DreamerPolicy(env, weights, noise="explicit")
+        for _ in range(3):
+            pol.act(scans, torch.from_numpy(es), torch.from_numpy(ea), debug=True)
+        diags.append({k: v.cpu().numpy().copy() for k, v in pol.diagnostics().items()})
+        env.close()
+    a, b = diags
+    if n > 33 * 128:
+        assert np.array_equal(a["actor_mean"], b["actor_mean"]) and np.array_equal(a["actor_std"], b["actor_std"])
+    else:
+        assert np.abs(a["actor_mean"] - b["actor_mean"]).max() <= 2e-5 * max(1.0, np.abs(b["actor_mean"]).max())
+        assert np.abs(a["actor_std"] - b["actor_std"]).max() <= 2e-5 * max(1.0, np.abs(b["actor_std"]).max())
+        assert not np.array_equal(a["actor_mean"], b["actor_mean"]), "the fused head did not run"
 
 
 def test_error_paths(torch_cuda, weights):
