@@ -2,8 +2,8 @@
 //
 // One agent step = RacingDreamer.action [REF ros_agent/models/dreamer/racing_dreamer.py:62-82] for every env:
 //   img1 -> GRU cell -> obs1 (concat([deter, embed])) -> obs2 + posterior sample -> actor h0..h3 -> hout + mode()
-// = k_embed_lidar, four launches of k_dense, one of k_dense_chain (the actor trunk and, up to 33 x 128 envs, hout: a
-// fifth k_dense launch otherwise) and k_actor_mode (rd_gemm.cuh);
+// = k_embed_lidar, five launches of k_dense, one of k_dense_chain (the actor trunk; with RD_DREAMER_HEAD=1 and up to
+// 33 x 128 envs also hout, which is the fifth k_dense launch otherwise) and k_actor_mode (rd_gemm.cuh);
 // activations live in a handful of [envs][width] float32 arrays that stay in
 // L2 between launches, the recurrent state in two ping-pong "latent" arrays whose rows are
 //   [ stoch (30) | previous action (2) | deter (200) ]          (232 floats, 928 bytes)
@@ -54,7 +54,9 @@ struct DreamerPolicy {
   float* head_raw = nullptr;   // [n][4] hout pre-activations
   // k_dense_chain (the actor trunk in one launch): per-row-block layer counters and the values they have reached
   bool chain = true;           // RD_DREAMER_CHAIN=0: one k_dense launch per actor layer instead
-  bool head_fused = true;      // hout inside the last k_dense_chain launch (cluster launches of <= 33 row blocks; RD_DREAMER_HEAD=0: own launch)
+  bool head_fused = false;     // RD_DREAMER_HEAD=1: hout inside the last k_dense_chain launch (cluster launches of <= 33 row
+                               // blocks).  Opt-in: 4 % faster, tests / memcheck / synccheck green, but racecheck flags the
+                               // remote stores ("block might not have entered yet"), see profiles/r5b_dreamer_chain.txt
   bool chain_cluster = true;   // the N tiles of a row block are launched as a thread-block cluster (RD_DREAMER_CLUSTER=0: plain grid)
   bool tma_out = true;         // RD_DREAMER_TMA_OUT=0: Dense / GRU epilogues store from registers (see gm_stage_f4)
   unsigned* chain_flags = nullptr;
@@ -202,7 +204,7 @@ static inline int dreamer_init(DreamerPolicy& d, int n, int n_beams, bool lidar_
     DR_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
     d.chain = true;
     if (const char* ev = std::getenv("RD_DREAMER_CHAIN")) d.chain = std::atoi(ev) != 0;
-    d.head_fused = true;
+    d.head_fused = false;
     if (const char* ev = std::getenv("RD_DREAMER_HEAD")) d.head_fused = std::atoi(ev) != 0;
     d.chain_cluster = true;
     if (const char* ev = std::getenv("RD_DREAMER_CLUSTER")) d.chain_cluster = std::atoi(ev) != 0;
