@@ -1152,7 +1152,11 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
     }
     if (q == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the last tile's stores
     if (g.head && part == 0) {
-      // this CTA's partial [128][4] of hout -> slot blockIdx.x of the cluster's first CTA (distributed shared memory)
+      // this CTA's partial [128][4] of hout -> slot blockIdx.x of the cluster's first CTA (distributed shared memory).
+      // NOTE (why the fused head is opt-in): nothing but the co-scheduling of a cluster and the row-block counters this
+      // CTA has consumed tells it that the first CTA is running; the programming model wants a cluster barrier before the
+      // first remote access (a plain arrive + wait right after the set-up would do), and racecheck says so.  That
+      // variant is not shipped because it could not be re-validated on a GPU (profiles/r5b_dreamer_chain.txt).
       gm_mbar_wait(&head_acc_bar, 0, true);
       gm_tc_fence_after();
       float m8[8], s8[8];
