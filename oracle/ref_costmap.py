@@ -103,3 +103,26 @@ def reference_layers(yaml_path, start_xy=(0.0, 0.0), full_run=False, out_path=No
     return {"drivable_area": drivable, "norm_distance_from_start": norm,
             "norm_distance_to_obstacle": d / np.amax(d.flatten()),
             "grid_starting_position": np.asarray(gen.grid_starting_position)}
+
+
+def reference_raceline(yaml_path, start_xy=(0.0, 0.0), out_path=None):
+    """-> (race-line layer of the ERODED track as the reference's run() computes it [REF generate-costmap.py:378,
+    compute_raceline :280-360], the generator's per-map settings).  run() only exports that layer as an image, so the
+    UNMODIFIED method is wrapped to keep what it returns; nothing of the reference is changed."""
+    mod = load_generator()
+    with contextlib.redirect_stdout(_io.StringIO()):
+        gen = mod.CostmapGenerator(starting_position=start_xy, input_yaml_path=str(yaml_path),
+                                   output_path=str(out_path or "/tmp/ref_raceline_out.npz"))
+        gen.verbose = False
+        kept = {}
+        original = gen.compute_raceline
+
+        def keep(*args):
+            kept[args[4]] = original(*args)
+            return kept[args[4]]
+
+        gen.compute_raceline = keep
+        gen.run()
+    settings = dict(erosion=gen.erosion_value, degree=gen.d_value, blurred=gen.use_blurred_factor, sample_every=gen.sample_every)
+    return kept["eroded"], settings
+

@@ -281,15 +281,30 @@ def compile_track(yaml_path: os.PathLike, name: Optional[str] = None, start_xy=(
 _NO_BLUR_MAPS = ("f1_aut", "columbia_small")
 
 
+# per-map settings of the generator [REF docs/maps/costmaps/generate-costmap.py:83-106]:
+# erosion of the track for the race line (pixels), B-spline degree, whether the blurred terms enter the smoothed distance,
+# and every how many steps of the greedy descent a control point is taken
+_GENERATOR_SETTINGS = {
+    "Treitlstrasse_3-U_v3": dict(erosion=9, degree=25, blurred=True, sample_every=10),
+    "f1_aut": dict(erosion=12, degree=30, blurred=False, sample_every=10),
+    "columbia_small": dict(erosion=27, degree=40, blurred=False, sample_every=30),
+}
+_GENERATOR_DEFAULTS = dict(erosion=12, degree=25, blurred=True, sample_every=15)
+
+
+def generator_settings(stem: str) -> Dict[str, object]:
+    return dict(_GENERATOR_SETTINGS.get(stem, _GENERATOR_DEFAULTS))
+
+
 def compile_distance_to_target(yaml_path: os.PathLike, start_xy=(0.0, 0.0), reference_quirks: bool = False,
-                               use_blurred_factor: Optional[bool] = None) -> Dict[str, np.ndarray]:
+                               use_blurred_factor: Optional[bool] = None, erosion: int = 0) -> Dict[str, np.ndarray]:
     """The fourth layer of the reference's costmap files, ``norm_distance_to`` = normalised SMOOTHED distance to the
     target (the finish line approached in driving direction) [REF docs/maps/costmaps/generate-costmap.py:227-276
     compute_distance_transform_smoothed(forward_direction=False), saved at :405-420], full image size, float64.
     SURVEY.md §8-f4.  No env-path function reads it (the env uses the forward progress map); it completes the map
     compiler's output for tools that load the reference's ``maps.npz`` keys.  Returns ``{'drivable_area',
-    'norm_distance_to'}``.  The race-line image the generator also draws [REF :280-360] is exported as PNG only, never
-    stored, and is not built.
+    'norm_distance_to', 'distance_to'}`` (the latter un-normalised).  ``erosion`` > 0 shrinks the free space by a disk of
+    that radius first [REF :135-138]: the variant the race line is traced on (`compile_raceline`).
 
     Restated steps: backward wavefront (the finish line is blocked one column AFTER the start [REF :160]); 'start' /
     'target' areas = cells within 100 (small: 50) wavefront steps of the pixels two columns ahead of / behind the start
@@ -309,6 +324,9 @@ def compile_distance_to_target(yaml_path: os.PathLike, start_xy=(0.0, 0.0), refe
     binary = (gray / np.amax(gray)) > float(props["occupied_thresh"])
     if reference_quirks and H > REFERENCE_CLEARED_PIXEL[0] and W > REFERENCE_CLEARED_PIXEL[1]:
         binary[REFERENCE_CLEARED_PIXEL] = False
+    if erosion > 0:   # skimage.morphology.binary_erosion(selem=disk(erosion)): outside the image counts as free
+        k = np.arange(-erosion, erosion + 1) ** 2
+        binary = ndimage.binary_erosion(binary, structure=np.add.outer(k, k) <= erosion * erosion, border_value=True)
     if use_blurred_factor is None:
         use_blurred_factor = yaml_path.stem not in _NO_BLUR_MAPS
     gx = int((start_xy[0] - ox) / res)
@@ -356,7 +374,68 @@ def compile_distance_to_target(yaml_path: os.PathLike, start_xy=(0.0, 0.0), refe
     border = split_blur(dist * drv + top * (1.0 - drv), 5)
     out = dist + blurred * 0.08 + border * 0.06 if use_blurred_factor else dist
     out = out * res                                  # ... and the smoothed variant scales once more [REF :273]; it cancels below
-    return {"drivable_area": drivable, "norm_distance_to": out / np.amax(out)}
+    return {"drivable_area": drivable, "norm_distance_to": out / np.amax(out), "distance_to": out,
+            "grid_start": (gy, gx)}
+
+
+def compile_raceline(yaml_path: os.PathLike, start_xy=(0.0, 0.0), reference_quirks: bool = False) -> Dict[str, np.ndarray]:
+    """The race-line layer of the reference's map generator [REF docs/maps/costmaps/generate-costmap.py:280-360
+    compute_raceline, called at :378 on the ERODED track]: SURVEY.md §8-f4.  The generator only exports it as an image
+    (`.spline_line.colorized.png`), it is not one of the keys of `maps.npz` and nothing on the env path reads it; built
+    for tools that want the same cost layer.  Returns ``{'raceline'`` (full image, float64, normalised to 1),
+    ``'control_points'`` (row, col), ``'spline'`` (1000 samples, row, col)``}``.
+
+    Restated steps: on the track eroded by the map's disk, follow the steepest descent of the smoothed distance to the
+    target from ten pixels ahead of the start (8-neighbourhood, rows before columns, first minimum wins) until the path
+    meets itself; every `sample_every`-th position is a control point of a closed B-spline of the map's degree, sampled
+    1000 times and rasterised; ten Gaussian blurs (sigma 3) of 150 x that line, each masked by the UN-eroded drivable
+    area; normalised by its maximum."""
+    from scipy import interpolate, ndimage
+
+    yaml_path = Path(yaml_path)
+    cfg = generator_settings(yaml_path.stem)
+    full = compile_distance_to_target(yaml_path, start_xy, reference_quirks, use_blurred_factor=cfg["blurred"])
+    eroded = compile_distance_to_target(yaml_path, start_xy, reference_quirks, use_blurred_factor=cfg["blurred"],
+                                        erosion=int(cfg["erosion"]))
+    field, free = eroded["distance_to"], eroded["drivable_area"]
+    gy, gx = eroded["grid_start"]
+    H, W = free.shape
+    on_line = np.zeros((H, W), dtype=bool)
+    pos = (gy, gx + 10)
+    on_line[pos] = True
+    cv = [pos]
+    steps = ((0, 1), (0, -1), (1, 0), (-1, 0), (1, 1), (-1, 1), (1, -1), (-1, -1))   # (row, col), the generator's order
+    n = 0
+    while True:
+        n += 1
+        best_val, best = 100000.0, pos
+        for dr, dc in steps:
+            r, c = pos[0] + dr, pos[1] + dc
+            if field[r, c] < best_val and free[r, c]:
+                best_val, best = field[r, c], (r, c)
+        if n % int(cfg["sample_every"]) == 0:
+            cv.append(pos)
+        pos = best
+        if on_line[pos]:          # the path met itself (or there was nowhere to go)
+            break
+        on_line[pos] = True
+        if n >= 5000:
+            break
+    cv = np.asarray(cv, dtype=np.int64)
+    # closed B-spline through the control polygon [REF :430-456 scipy_bspline(periodic=True)]
+    degree, count = int(cfg["degree"]), cv.shape[0]
+    kv = np.arange(-degree, count + degree + 1)
+    factor, fraction = divmod(count + degree + 1, count)
+    ring = np.roll(np.concatenate((cv,) * factor + (cv[:fraction],)), -1, axis=0)
+    spline = interpolate.BSpline(kv, ring, degree)(np.linspace(0, count, 1000))
+    line = np.zeros((H, W), dtype=np.float64)
+    idx = spline.astype(int)
+    line[idx[:, 0], idx[:, 1]] = 1.0
+    area = full["drivable_area"].astype(np.float64)
+    blurred = ndimage.gaussian_filter(line * 150, sigma=3) * area
+    for _ in range(9):
+        blurred = ndimage.gaussian_filter(blurred, sigma=3) * area
+    return {"raceline": blurred / np.amax(blurred), "control_points": cv, "spline": spline}
 
 
 def _heading_field(tm: TrackMap, rows: np.ndarray, cols: np.ndarray, k: int = 6) -> np.ndarray:

@@ -19,7 +19,10 @@ committed so that the parity tests can run where /root/reference does not exist 
 
   costmap_golden.npz       the UNMODIFIED map generator [REF docs/maps/costmaps/generate-costmap.py] (skimage/cmapy
                            stubbed over scipy.ndimage, oracle/ref_costmap.py) run on two of the reference's maps:
-                           drivable_area, norm_distance_from_start, norm_distance_to_obstacle.
+                           drivable_area, norm_distance_from_start, norm_distance_to_obstacle (+ norm_distance_to).
+  raceline_golden.npz      the same generator's race-line layer [REF :280-360,378]: what the UNMODIFIED compute_raceline
+                           returned inside run() on f1_aut and columbia_small (sha256 of the float64 layer, track crop,
+                           control points).  `python tests/golden/make_golden.py raceline_golden`, ~2 minutes per map.
 
   multi_agent_stack_golden.npz  one world of four cars (A maximize_progress, B..D n_step_progress as in the baselines'
                            scenario files [REF baselines/scenarios/max_progress/austria.yml]) under the UNMODIFIED
@@ -406,6 +409,32 @@ def costmap_golden():
     out["treitlstrasse_v2_norm_distance_to_crop_f32"] = ndt[r0:r0 + h, c0:c0 + w].astype(np.float32)
     print("costmap_golden: norm_distance_to max", float(ndt.max()), "nonzero", int((ndt > 0).sum()))
     np.savez_compressed(OUT / "costmap_golden.npz", **out)
+
+
+def raceline_golden():
+    """the race-line layer [REF docs/maps/costmaps/generate-costmap.py:280-360,378] from the UNMODIFIED
+    generator's run() on the two maps with their own settings (f1_aut, columbia_small): sha256 of the full float64 layer,
+    the track crop in float32 and the number of non-zero pixels.  ~2 minutes per map."""
+    import hashlib
+    from oracle.ref_costmap import reference_raceline
+    from racing_dreamer_b200 import TRACK_FILES, maps
+    out = {}
+    for name in ("austria", "columbia"):
+        y = ref_stubs.REFERENCE_ROOT / "docs" / "maps" / "maps" / f"{TRACK_FILES[name]}.yaml"
+        layer, settings = reference_raceline(y)
+        assert settings == maps.generator_settings(TRACK_FILES[name]), (settings, maps.generator_settings(TRACK_FILES[name]))
+        mine = maps.compile_raceline(y, reference_quirks=True)
+        assert np.array_equal(layer, mine["raceline"]), name
+        layer = np.ascontiguousarray(layer, dtype=np.float64)
+        rows, cols = np.flatnonzero((layer > 0).any(axis=1)), np.flatnonzero((layer > 0).any(axis=0))
+        r0, c0, h, w = int(rows[0]), int(cols[0]), int(rows[-1] - rows[0] + 1), int(cols[-1] - cols[0] + 1)
+        out[f"{name}_r0c0hw"] = np.array([r0, c0, h, w], np.int64)
+        out[f"{name}_sha256"] = np.array(hashlib.sha256(layer.tobytes()).hexdigest())
+        out[f"{name}_crop_f32"] = layer[r0:r0 + h, c0:c0 + w].astype(np.float32)
+        out[f"{name}_nonzero"] = np.array(int((layer > 0).sum()))
+        out[f"{name}_control_points"] = mine["control_points"]
+        print(f"raceline_golden: {name} nonzero {int((layer > 0).sum())} control points {mine['control_points'].shape[0]}")
+    np.savez_compressed(OUT / "raceline_golden.npz", **out)
 
 
 def multi_agent_episodes_golden(n_steps=120, action_repeat=4, duration=15, n_agents=3):

@@ -131,3 +131,28 @@ def test_distance_to_target_layer_reproduces_generator(golden_dir):
     d = plain["norm_distance_to"][plain["drivable_area"]]
     steps = np.unique(np.round(d * d.size))          # a pure wavefront distance takes few distinct values per cell count
     assert len(np.unique(d)) <= 2000 and steps.size > 10
+
+@pytest.mark.skipif(not ref_stubs.available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("name", ["austria", "columbia"])
+def test_raceline_layer_reproduces_generator(golden_dir, name):
+    """§8-f4: the race-line layer the generator draws on the eroded track [REF docs/maps/costmaps/generate-costmap.py:
+    280-360, called at :378], restated in maps.compile_raceline; the fixture is what the UNMODIFIED compute_raceline
+    returned inside the script's full run() (tests/golden/make_golden.py::raceline_golden), on the two maps that carry
+    their own erosion / spline degree / sampling settings [REF :83-106]."""
+    import hashlib
+    g = np.load(golden_dir / "raceline_golden.npz")
+    out = maps.compile_raceline(ref_stubs.REFERENCE_ROOT / "docs/maps/maps" / f"{TRACK_FILES[name]}.yaml", reference_quirks=True)
+    layer = np.ascontiguousarray(out["raceline"], dtype=np.float64)
+    r0, c0, h, w = (int(v) for v in g[f"{name}_r0c0hw"])
+    assert np.array_equal(out["control_points"], g[f"{name}_control_points"])
+    assert np.abs(layer[r0:r0 + h, c0:c0 + w].astype(np.float32) - g[f"{name}_crop_f32"]).max() == 0.0
+    assert int((layer > 0).sum()) == int(g[f"{name}_nonzero"])
+    assert hashlib.sha256(layer.tobytes()).hexdigest() == str(g[f"{name}_sha256"])
+    # properties: normalised, confined to the drivable area, a closed loop of control points that stays on the track
+    drivable = maps.compile_distance_to_target(ref_stubs.REFERENCE_ROOT / "docs/maps/maps" / f"{TRACK_FILES[name]}.yaml",
+                                               reference_quirks=True)["drivable_area"]
+    assert layer.max() == 1.0 and layer.min() >= 0.0 and (layer[~drivable] == 0).all()
+    cp = out["control_points"]
+    assert cp.shape[0] > 20 and drivable[cp[:, 0], cp[:, 1]].all()
+    assert np.abs(cp[0] - cp[-1]).max() < 60          # the descent comes back to where it started
+
