@@ -340,7 +340,9 @@ def test_fused_head_agrees_with_the_head_launch(torch_cuda, weights, monkeypatch
     else:
         assert np.abs(a["actor_mean"] - b["actor_mean"]).max() <= 2e-5 * max(1.0, np.abs(b["actor_mean"]).max())
         assert np.abs(a["actor_std"] - b["actor_std"]).max() <= 2e-5 * max(1.0, np.abs(b["actor_std"]).max())
-        assert not np.array_equal(a["actor_mean"], b["actor_mean"]), "the fused head did not run"
+        if n <= 8 * 128:   # a handful of clusters fit any B200; 32 of them (4096 envs) fit the pool's boxes (33 at once),
+            # but a part with fewer SMs enabled would fall back to the separate launch, which is correct behaviour
+            assert not np.array_equal(a["actor_mean"], b["actor_mean"]), "the fused head did not run"
 
 
 def test_error_paths(torch_cuda, weights):
